@@ -1,0 +1,185 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in this
+container through tests/golden/ref_harness.py.  Run:  python tests/golden/make_golden.py [names]
+
+The .npz files are committed; this script cannot run on the GPU box (no /root/reference).
+Every fixture stores its inputs next to the reference's outputs so it is self-contained.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import ref_harness as rh  # noqa: E402
+from yolo_tracking_b200.synth import make_stream  # noqa: E402
+
+
+def _save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}.npz  {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+def _ragged(list_of_arrays, width):
+    """-> (flat[n,width], offsets[len+1])"""
+    offs = np.zeros(len(list_of_arrays) + 1, dtype=np.int64)
+    rows = []
+    for i, a in enumerate(list_of_arrays):
+        a = np.asarray(a, dtype=np.float64).reshape(-1, width)
+        rows.append(a)
+        offs[i + 1] = offs[i] + len(a)
+    return (np.concatenate(rows, axis=0) if rows else np.zeros((0, width))), offs
+
+
+# ----------------------------------------------------------------------------- Kalman filters
+def gen_kf():
+    rh.install()
+    from boxmot.motion.kalman_filters.bytetrack_kf import KalmanFilter as KFxyah
+    from boxmot.motion.kalman_filters.botsort_kf import KalmanFilter as KFxywh
+    from boxmot.motion.kalman_filters.strongsort_kf import KalmanFilter as KFconf
+    rng = np.random.default_rng(11)
+    n, steps = 48, 6
+    for name, cls in (("xyah", KFxyah), ("xywh", KFxywh), ("xyah_conf", KFconf)):
+        kf = cls()
+        z0 = np.stack([rng.uniform(100, 1800, n), rng.uniform(100, 1000, n),
+                       rng.uniform(0.3, 0.8, n) if name != "xywh" else rng.uniform(30, 90, n),
+                       rng.uniform(60, 220, n)], axis=1)
+        out = dict(z0=z0)
+        mean = np.zeros((n, 8))
+        cov = np.zeros((n, 8, 8))
+        for i in range(n):
+            mean[i], cov[i] = kf.initiate(z0[i])
+        out["init_mean"], out["init_cov"] = mean.copy(), cov.copy()
+        zs = np.zeros((steps, n, 4))
+        confs = rng.uniform(0.3, 0.95, (steps, n))
+        pm_all, pc_all = np.zeros((steps, n, 8)), np.zeros((steps, n, 8, 8))
+        um_all, uc_all = np.zeros((steps, n, 8)), np.zeros((steps, n, 8, 8))
+        prj_m, prj_c = np.zeros((steps, n, 4)), np.zeros((steps, n, 4, 4))
+        for s in range(steps):
+            if name == "xyah_conf":
+                for i in range(n):
+                    mean[i], cov[i] = kf.predict(mean[i], cov[i])
+            else:
+                mean, cov = kf.multi_predict(mean, cov)
+            pm_all[s], pc_all[s] = mean, cov
+            zs[s] = mean[:, :4] + rng.normal(0, 1, (n, 4)) * np.array([2, 2, 0.01 if name != "xywh" else 2, 2])
+            for i in range(n):
+                if name == "xyah_conf":
+                    prj_m[s, i], prj_c[s, i] = kf.project(mean[i], cov[i], confs[s, i])
+                    mean[i], cov[i] = kf.update(mean[i], cov[i], zs[s, i], confs[s, i])
+                else:
+                    prj_m[s, i], prj_c[s, i] = kf.project(mean[i], cov[i])
+                    mean[i], cov[i] = kf.update(mean[i], cov[i], zs[s, i])
+            um_all[s], uc_all[s] = mean, cov
+        out.update(z=zs, conf=confs, pred_mean=pm_all, pred_cov=pc_all, proj_mean=prj_m,
+                   proj_cov=prj_c, upd_mean=um_all, upd_cov=uc_all)
+        # gating distance: every track of the last predicted state against 40 measurements
+        D = 40
+        pick = rng.integers(0, n, D)
+        meas = pm_all[-1, pick, :4] + rng.normal(0, 1, (D, 4)) * np.array([6, 6, 0.02 if name != "xywh" else 6, 6])
+        g4 = np.zeros((n, D))
+        g2 = np.zeros((n, D))
+        gg = np.zeros((n, D))
+        for i in range(n):
+            g4[i] = kf.gating_distance(pm_all[-1, i], pc_all[-1, i], meas.copy(), False)
+            g2[i] = kf.gating_distance(pm_all[-1, i], pc_all[-1, i], meas.copy(), True)
+            if name != "xyah_conf":
+                gg[i] = kf.gating_distance(pm_all[-1, i], pc_all[-1, i], meas.copy(), False, "gaussian")
+        out.update(gate_meas=meas, gate_maha4=g4, gate_maha2=g2, gate_gauss=gg)
+        _save("kf_" + name, **out)
+
+
+# ----------------------------------------------------------------------------- pairwise costs
+def gen_costs():
+    rh.install()
+    from boxmot.utils import iou as riou
+    from boxmot.utils import matching as rm
+    rng = np.random.default_rng(12)
+
+    def rand_boxes(n):
+        c = rng.uniform(0, 400, (n, 2))
+        wh = rng.uniform(20, 160, (n, 2))
+        return np.concatenate([c - wh / 2, c + wh / 2], axis=1)
+    a, b = rand_boxes(37), rand_boxes(29)
+    out = dict(a=a, b=b, iou=riou.iou_batch(a, b), giou=riou.giou_batch(a, b),
+               diou=riou.diou_batch(a, b), ciou=riou.ciou_batch(a, b),
+               centroid=riou.centroid_batch(a, b, 640, 480))
+    score = rng.uniform(0.1, 1.0, 29)
+
+    class _D:
+        def __init__(self, s): self.score = s
+    cost = rm.iou_distance(list(a), list(b))
+    out["iou_distance"] = cost
+    out["score"] = score
+    out["fuse_score"] = rm.fuse_score(cost.copy(), [_D(s) for s in score])
+    # embedding_distance (matching.py:145-167): fp32 cast, cdist cosine, clamp at 0
+    ta = rng.standard_normal((37, 512))
+    tb = rng.standard_normal((29, 512)) + 0.5 * ta[rng.integers(0, 37, 29)]
+
+    class _T:
+        def __init__(self, f): self.smooth_feat = f; self.curr_feat = f
+    out["feat_a"], out["feat_b"] = ta, tb
+    out["embedding_distance"] = rm.embedding_distance([_T(f) for f in ta], [_T(f) for f in tb])
+    _save("costs", **out)
+
+
+# ----------------------------------------------------------------------------- ByteTrack
+def _bt_snapshot(trk):
+    ts = trk.tracked_stracks + trk.lost_stracks
+    ints = np.array([[t.track_id, t.state, int(t.is_activated), t.frame_id, t.start_frame,
+                      t.tracklet_len] for t in ts], dtype=np.int32).reshape(-1, 6)
+    mean = np.stack([t.mean for t in ts]) if ts else np.zeros((0, 8))
+    cov = np.stack([t.covariance for t in ts]) if ts else np.zeros((0, 8, 8))
+    return len(trk.tracked_stracks), len(trk.lost_stracks), ints, mean, cov
+
+
+def gen_bytetrack():
+    scenarios = {
+        # BASELINE config 1 shape (53 objects ~ 50 dets/frame), shortened to keep the file small
+        "bytetrack_c1": dict(config=1, stream=0, n_objects=53, n_frames=150, kw={}),
+        # heavy misses + false positives: exercises lost / re-found / removed-lag / sticky-removed
+        "bytetrack_churn": dict(config=1, stream=901, n_objects=20, n_frames=300,
+                                kw=dict(miss_prob=0.3, fp_rate=3.0)),
+    }
+    for name, sc in scenarios.items():
+        dets, nd, _ = make_stream(sc["config"], sc["stream"], sc["n_objects"], sc["n_frames"], **sc["kw"])
+        trk = rh.make_tracker("bytetrack")
+        outs, ints, counts, means, covs, pool, cov_frames = [], [], [], [], [], [], []
+        for f in range(sc["n_frames"]):
+            pool.append(len(trk.tracked_stracks) + len(trk.lost_stracks))
+            o = trk.update(dets[f, :nd[f]], None)
+            outs.append(o)
+            nt, nl, ii, m, c = _bt_snapshot(trk)
+            counts.append((nt, nl))
+            ints.append(ii)
+            means.append(m)
+            if f % 10 == 9 or f == sc["n_frames"] - 1:      # dense covariances every 10th frame
+                covs.append(c.reshape(-1, 64))
+                cov_frames.append(f)
+        out_flat, out_offs = _ragged(outs, 8)
+        int_flat, int_offs = _ragged(ints, 6)
+        mean_flat, _ = _ragged(means, 8)
+        cov_flat, _ = _ragged(covs, 64)
+        _save(name, dets=dets, ndets=nd, out=out_flat, out_offs=out_offs,
+              rec=int_flat.astype(np.int32), rec_offs=int_offs, counts=np.array(counts, dtype=np.int32),
+              mean=mean_flat, cov=cov_flat.astype(np.float64), cov_frames=np.array(cov_frames, dtype=np.int32), pool=np.array(pool, dtype=np.int32),
+              params=np.array([0.5, 0.8, 30, 30], dtype=np.float64))
+    # the reference's own known-answer test input (tests/test_python.py:165-185)
+    trk = rh.make_tracker("bytetrack")
+    det = np.array([[144, 212, 578, 480, 0.82, 0], [425, 281, 576, 472, 0.86, 65]], dtype=np.float64)
+    outs = [trk.update(det, None) for _ in range(3)]
+    _save("bytetrack_2box", det=det, out=np.stack(outs))
+
+
+GENERATORS = {"kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack}
+
+if __name__ == "__main__":
+    names = sys.argv[1:] or list(GENERATORS)
+    for n in names:
+        GENERATORS[n]()

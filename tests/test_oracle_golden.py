@@ -1,0 +1,117 @@
+"""The oracle (oracle/) against golden vectors produced by the live reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from _util import assert_close, load_golden
+from oracle import boxes, kalman
+from oracle.bytetrack import ByteTrackOracle
+from oracle.lap import assign_no_limit, assign_with_limit, lapjv_extended
+
+
+@pytest.mark.parametrize("kind", ["xyah", "xywh", "xyah_conf"])
+def test_kalman_matches_reference(kind):
+    g = load_golden("kf_" + kind)
+    m, c = kalman.initiate(kind, g["z0"])
+    assert_close(m, g["init_mean"], what="initiate mean")
+    assert_close(c, g["init_cov"], what="initiate cov")
+    steps = g["z"].shape[0]
+    for s in range(steps):
+        m, c = kalman.predict(kind, m, c)
+        assert_close(m, g["pred_mean"][s], what=f"predict mean {s}")
+        assert_close(c, g["pred_cov"][s], what=f"predict cov {s}")
+        conf = g["conf"][s] if kind == "xyah_conf" else 0.0
+        pm, pc = kalman.project(kind, m, c, conf)
+        assert_close(pm, g["proj_mean"][s], what="project mean")
+        assert_close(pc, g["proj_cov"][s], what="project cov")
+        m, c = kalman.update(kind, m, c, g["z"][s], conf)
+        assert_close(m, g["upd_mean"][s], what=f"update mean {s}")
+        assert_close(c, g["upd_cov"][s], abs_=1e-10, what=f"update cov {s}")
+    pm_, pc_ = g["pred_mean"][-1], g["pred_cov"][-1]
+    for i in range(pm_.shape[0]):
+        assert_close(kalman.gating_distance(kind, pm_[i], pc_[i], g["gate_meas"]), g["gate_maha4"][i], what="maha4")
+        assert_close(kalman.gating_distance(kind, pm_[i], pc_[i], g["gate_meas"], True), g["gate_maha2"][i], what="maha2")
+        if kind != "xyah_conf":
+            assert_close(kalman.gating_distance(kind, pm_[i], pc_[i], g["gate_meas"], False, "gaussian"),
+                         g["gate_gauss"][i], what="gauss")
+
+
+def test_pairwise_costs_match_reference():
+    g = load_golden("costs")
+    a, b = g["a"], g["b"]
+    for name in ("iou", "giou", "diou", "ciou"):
+        assert np.array_equal(boxes.ASSO[name](a, b), g[name]), name      # same op order -> same bits
+    assert np.array_equal(boxes.centroid(a, b, 640, 480), g["centroid"])
+    cost = 1 - boxes.iou(a, b)
+    assert np.array_equal(cost, g["iou_distance"])
+    assert np.array_equal(1 - (1 - cost) * g["score"][None, :], g["fuse_score"])
+
+
+def test_lapjv_known_answer():
+    # distinguishes lapjv's extended-matrix optimum from "Hungarian then threshold"
+    opt, x, y = lapjv_extended(np.array([[0.1, 0.79], [0.2, 2.0]]), 0.8)
+    assert x.tolist() == [0, -1] and y.tolist() == [0, -1]
+    m, ua, ub = assign_with_limit(np.array([[0.1, 0.79], [0.2, 2.0]]), 0.8)
+    assert m.tolist() == [[0, 0]] and ua.tolist() == [1] and ub.tolist() == [1]
+    m, ua, ub = assign_with_limit(np.zeros((0, 3)), 0.8)
+    assert m.shape == (0, 2) and list(ua) == [] and list(ub) == [0, 1, 2]
+    # no limit: every min(R, C) row is matched
+    rng = np.random.default_rng(0)
+    c = rng.random((5, 3))
+    assert len(assign_no_limit(c)) == 3
+
+
+def _replay(name):
+    g = load_golden(name)
+    p = g["params"]
+    trk = ByteTrackOracle(p[0], p[1], int(p[2]), int(p[3]))
+    dets, nd = g["dets"], g["ndets"]
+    cov_frames = {int(f): k for k, f in enumerate(g["cov_frames"])}
+    cov_pos = 0
+    cov_offs = [0]
+    for f in g["cov_frames"]:
+        cov_offs.append(cov_offs[-1] + int(g["counts"][f].sum()))
+    for f in range(dets.shape[0]):
+        assert trk.track_updates == int(g["pool"][:f].sum())
+        out = trk.update(dets[f, :nd[f]], None)
+        ref = g["out"][g["out_offs"][f]:g["out_offs"][f + 1]]
+        assert out.reshape(-1, 8).shape == ref.shape, f"frame {f}"
+        if ref.size:
+            assert np.array_equal(out[:, 4:], ref[:, 4:]), f"frame {f}: id/conf/cls/det_ind"
+            assert_close(out[:, :4], ref[:, :4], what=f"frame {f} boxes")
+        s = trk.snapshot()
+        assert (int(s["n_tracked"]), int(s["n_lost"])) == tuple(g["counts"][f])
+        rec = g["rec"][g["rec_offs"][f]:g["rec_offs"][f + 1]]
+        mine = np.stack([s["track_id"], s["state"], s["is_activated"], s["frame_id"],
+                         s["start_frame"], s["tracklet_len"]], axis=1).reshape(-1, 6)
+        assert np.array_equal(mine, rec), f"frame {f}: lifecycle records"
+        assert_close(s["mean"], g["mean"][g["rec_offs"][f]:g["rec_offs"][f + 1]], what=f"frame {f} mean")
+        if f in cov_frames:
+            k = cov_frames[f]
+            assert_close(s["cov"].reshape(-1, 64), g["cov"][cov_offs[k]:cov_offs[k + 1]], abs_=1e-10,
+                         what=f"frame {f} cov")
+
+
+@pytest.mark.parametrize("name", ["bytetrack_c1", "bytetrack_churn"])
+def test_bytetrack_oracle_replays_reference(name):
+    _replay(name)
+
+
+def test_bytetrack_reference_known_answer():
+    # the reference's own test input (tests/test_python.py:165-185)
+    g = load_golden("bytetrack_2box")
+    trk = ByteTrackOracle(0.5, 0.8, 30, 30)
+    for k in range(3):
+        out = trk.update(g["det"], None)
+        assert out.shape == (2, 8)
+        assert_close(out, g["out"][k])
+    assert_close(np.delete(out, [4, 7], axis=1), g["det"], rel=7e-3, abs_=1.0)
+
+
+def test_bytetrack_empty_and_asserts():
+    trk = ByteTrackOracle(0.5, 0.8, 30, 30)
+    assert trk.update(np.empty((0, 6))).shape == (0,)
+    with pytest.raises(AssertionError):
+        trk.update(np.zeros((2, 5)))
+    with pytest.raises(AssertionError):
+        trk.update([[0, 0, 1, 1, 0.9, 0]])
