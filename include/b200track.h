@@ -1,0 +1,166 @@
+/* b200track - C-ABI of the B200-native multi-stream tracking-by-detection hot path.
+ *
+ * Drop-in boundary for BoxMOT's per-frame loop (reference: /root/reference, BoxMOT 10.0.51).
+ * The reference is pure Python, so there is no reference FFI to mirror; every entry point
+ * below names the reference Python interface it replaces (file:line).  The Python binding a
+ * maintainer adds is a ctypes stub; yolo_tracking_b200/_lib.py is that stub.
+ *
+ * Conventions: plain pointers and sizes, no torch types.  Functions return 0 on success and
+ * a negative b200track_status otherwise; b200track_last_error() gives the message of the last
+ * failure on the calling thread.  Pointers named d_* are DEVICE pointers, h_* are HOST
+ * pointers.  `stream` is a cudaStream_t passed as void* (NULL = default stream).  A context
+ * is bound to one device and is not thread-safe (like a reference tracker object).
+ */
+#ifndef B200TRACK_H
+#define B200TRACK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200TRACK_ABI_VERSION 1
+
+typedef enum {
+    B200TRACK_OK = 0,
+    B200TRACK_ERR_ARG = -1,       /* bad argument                                        */
+    B200TRACK_ERR_CUDA = -2,      /* CUDA runtime error (no device, launch failure ...)  */
+    B200TRACK_ERR_CAPACITY = -3,  /* more tracks / detections than max_tracks / max_dets */
+    B200TRACK_ERR_STATE = -4      /* call not valid for this context kind                */
+} b200track_status;
+
+typedef enum {
+    B200TRACK_BYTETRACK = 0,      /* boxmot/trackers/bytetrack/byte_tracker.py:114 BYTETracker */
+    B200TRACK_OCSORT = 1,         /* boxmot/trackers/ocsort/ocsort.py:190 OCSort               */
+    B200TRACK_BOTSORT = 2         /* boxmot/trackers/botsort/bot_sort.py:184 BoTSORT           */
+} b200track_kind;
+
+typedef enum { B200TRACK_KF_XYAH = 0, B200TRACK_KF_XYWH = 1, B200TRACK_KF_XYAH_CONF = 2 } b200track_kf_kind;
+typedef enum {
+    B200TRACK_SIM_IOU = 0, B200TRACK_SIM_GIOU = 1, B200TRACK_SIM_DIOU = 2,
+    B200TRACK_SIM_CIOU = 3, B200TRACK_SIM_CENTROID = 4
+} b200track_sim;
+
+/* Constructor arguments of the reference trackers (tracker_zoo.py:43-81), plus capacities. */
+typedef struct {
+    int32_t kind;            /* b200track_kind                                              */
+    int32_t n_streams;       /* independent video streams tracked by this context           */
+    int32_t max_tracks;      /* slots per stream (tracked + lost lists), multiple of 32     */
+    int32_t max_dets;        /* detections per stream per frame, multiple of 32             */
+    int32_t feat_dim;        /* appearance embedding size (BoTSORT), else 0                 */
+    int32_t device;          /* CUDA device ordinal                                         */
+    /* ByteTrack (byte_tracker.py:115-130) / BoTSORT (bot_sort.py:185-229) */
+    double track_thresh;     /* track_thresh | track_high_thresh                            */
+    double track_low_thresh; /* 0.1 (hard-coded in ByteTrack) | track_low_thresh            */
+    double new_track_thresh; /* det_thresh = track_thresh | new_track_thresh                */
+    double match_thresh;
+    double proximity_thresh;
+    double appearance_thresh;
+    int32_t track_buffer;
+    int32_t frame_rate;
+    /* OCSORT (ocsort.py:191-216) */
+    double det_thresh;
+    double iou_thresh;
+    double inertia;
+    int32_t max_age;
+    int32_t min_hits;
+    int32_t delta_t;
+    int32_t asso_func;       /* b200track_sim                                               */
+    int32_t use_byte;
+    int32_t with_reid;       /* BoTSORT: use the embedding cost                             */
+    int32_t reserved;
+} b200track_config;
+
+typedef struct b200track_ctx b200track_ctx;
+
+int b200track_abi_version(void);
+const char* b200track_last_error(void);
+
+/* ---- tracker contexts: create_tracker(...) / tracker.update(dets, img) ------------------
+ * b200track_create      <- tracker_zoo.py:18-118 create_tracker (one ctx = n_streams trackers)
+ * b200track_step        <- BYTETracker.update byte_tracker.py:132-281 / OCSort.update
+ *                          ocsort.py:218-379 / BoTSORT.update bot_sort.py:231-420, for every
+ *                          stream at once; everything stays on the device, asynchronous.
+ *   d_dets  [n_streams, max_dets, 6]  (x1, y1, x2, y2, conf, cls), rows >= d_ndets[s] ignored
+ *   d_feats [n_streams, max_dets, feat_dim] fp32 appearance rows (BoTSORT) or NULL
+ *   img_h, img_w: frame size (OCSORT reads only img.shape[:2]; ocsort.py:239)
+ *   d_out   [n_streams, max_tracks, 8] (x1, y1, x2, y2, id, conf, cls, det_ind) in the
+ *           reference's row order; d_nout[s] rows are valid.
+ * b200track_step_host   same call with HOST buffers: copies in, steps, copies out, waits.
+ * b200track_submit_host / b200track_wait_host: pipelined variant - up to
+ *   b200track_host_slots() frames in flight (copy-in of frame k+1 and copy-out of frame k-1
+ *   overlap the step of frame k).  Host buffers must stay valid until the wait returns.
+ */
+int b200track_create(const b200track_config* cfg, b200track_ctx** out_ctx);
+void b200track_destroy(b200track_ctx* ctx);
+int b200track_reset(b200track_ctx* ctx);
+int b200track_step(b200track_ctx* ctx, const double* d_dets, const int32_t* d_ndets,
+                   const float* d_feats, int32_t img_h, int32_t img_w,
+                   double* d_out, int32_t* d_nout, void* stream);
+int b200track_step_host(b200track_ctx* ctx, const double* h_dets, const int32_t* h_ndets,
+                        const float* h_feats, int32_t img_h, int32_t img_w,
+                        double* h_out, int32_t* h_nout);
+int b200track_host_slots(b200track_ctx* ctx);
+int b200track_submit_host(b200track_ctx* ctx, int32_t slot, const double* h_dets,
+                          const int32_t* h_ndets, const float* h_feats, int32_t img_h,
+                          int32_t img_w, double* h_out, int32_t* h_nout);
+int b200track_wait_host(b200track_ctx* ctx, int32_t slot);
+/* Waits for all work of the context, then reports capacity overflows seen since the last call. */
+int b200track_sync(b200track_ctx* ctx);
+/* Sum over streams of the tracks that entered association so far (SURVEY.md 8(d) metric). */
+int b200track_track_updates(b200track_ctx* ctx, uint64_t* h_total);
+/* Kernel launches issued by this context so far (bench.py's gpu_launches). */
+int b200track_launch_count(b200track_ctx* ctx, uint64_t* h_launches);
+/* Bytes one stream's state occupies on the device / dynamic shared memory of the step kernel. */
+int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state_bytes_per_stream, uint64_t* h_smem_bytes);
+
+/* Parity probe: the track records of one stream in list order (tracked list, then lost
+ * list), expanded to the reference's dense form.  Buffers hold max_tracks rows.
+ *   h_counts[4] = n_tracked, n_lost, id counter, frame_id
+ *   h_rec [max_tracks, 6] = track_id, state, is_activated, frame_id, start_frame, tracklet_len
+ *   h_mean[max_tracks, 8], h_cov[max_tracks, 64], h_aux[max_tracks, 3] = score, cls, det_ind */
+int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int32_t* h_counts,
+                        int32_t* h_rec, double* h_mean, double* h_cov, double* h_aux);
+
+/* ---- operator level: the reference's functional API, batched, device pointers -----------
+ * Dense [n, 8] means / [n, 8, 8] covariances in the reference's memory layout.
+ * b200track_kf_initiate        <- KalmanFilter.initiate        bytetrack_kf.py:55 / botsort_kf.py:55
+ * b200track_kf_predict         <- KalmanFilter.multi_predict   bytetrack_kf.py:155 / botsort_kf.py:154
+ * b200track_kf_project         <- KalmanFilter.project         bytetrack_kf.py:126 / strongsort_kf.py:124
+ * b200track_kf_update          <- KalmanFilter.update          bytetrack_kf.py:194 / strongsort_kf.py:157
+ * b200track_kf_gating_distance <- KalmanFilter.gating_distance bytetrack_kf.py:228 / strongsort_kf.py:191
+ *     (T tracks x D measurements -> d2[T, D]; metric 0 = 'maha', 1 = 'gaussian')
+ * d_conf (per row, [n]) is only read for B200TRACK_KF_XYAH_CONF and may be NULL otherwise. */
+int b200track_kf_initiate(int32_t kf_kind, int32_t n, const double* d_z, double* d_mean, double* d_cov, void* stream);
+int b200track_kf_predict(int32_t kf_kind, int32_t n, double* d_mean, double* d_cov, void* stream);
+int b200track_kf_project(int32_t kf_kind, int32_t n, const double* d_mean, const double* d_cov,
+                         const double* d_conf, double* d_pmean, double* d_pcov, void* stream);
+int b200track_kf_update(int32_t kf_kind, int32_t n, double* d_mean, double* d_cov, const double* d_z,
+                        const double* d_conf, void* stream);
+int b200track_kf_gating_distance(int32_t kf_kind, int32_t n_tracks, int32_t n_meas, const double* d_mean,
+                                 const double* d_cov, const double* d_meas, int32_t only_position,
+                                 int32_t metric, const double* d_conf, double* d_out, void* stream);
+/* b200track_box_similarity <- iou_batch / giou_batch / diou_batch / ciou_batch / centroid_batch
+ *     boxmot/utils/iou.py:6-188 ; a[n,4] x b[m,4] -> out[n,m] (img_w, img_h only for centroid)
+ * b200track_iou_distance   <- matching.py:94-119 (1 - iou), optional fuse_score :213-221 when
+ *     d_score != NULL */
+int b200track_box_similarity(int32_t sim, int32_t n, int32_t m, const double* d_a, const double* d_b,
+                             double img_w, double img_h, double* d_out, void* stream);
+int b200track_iou_distance(int32_t n, int32_t m, const double* d_a, const double* d_b,
+                           const double* d_score, double* d_out, void* stream);
+/* b200track_embedding_distance <- matching.py:145-167: fp32 features, max(0, cosine distance)
+ *     in double on the fp32 values; a[n, dim] x b[m, dim] -> out[n, m] fp64 */
+int b200track_embedding_distance(int32_t n, int32_t m, int32_t dim, const float* d_a, const float* d_b,
+                                 double* d_out, void* stream);
+/* b200track_lapjv <- lap.lapjv(cost, extend_cost=True, cost_limit=L) as called from
+ *     matching.py:64 (finite limit) and association.py:23 (cost_limit = +inf): `batch`
+ *     independent problems cost[batch, rows, cols] -> x[batch, rows], y[batch, cols] (-1 = unmatched) */
+int b200track_lapjv(int32_t batch, int32_t rows, int32_t cols, const double* d_cost, double cost_limit,
+                    int32_t* d_x, int32_t* d_y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200TRACK_H */

@@ -1,0 +1,111 @@
+"""GPU parity: the fused CUDA ByteTrack step (through the C-ABI) against the oracle and the
+golden vectors produced by the live reference."""
+import numpy as np
+import pytest
+
+from _util import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _pad(dets_list, dmax):
+    S = len(dets_list)
+    d = np.zeros((S, dmax, 6))
+    n = np.zeros(S, dtype=np.int32)
+    for s, a in enumerate(dets_list):
+        d[s, :len(a)] = a
+        n[s] = len(a)
+    return d, n
+
+
+def _check_stream_state(st, snap, f, s):
+    assert (st["n_tracked"], st["n_lost"]) == (int(snap["n_tracked"]), int(snap["n_lost"])), f"frame {f} stream {s}: list sizes"
+    for k_mine, k_ref in (("track_id", "track_id"), ("state", "state"), ("is_activated", "is_activated"),
+                          ("frame_id_t", "frame_id"), ("start_frame", "start_frame"), ("tracklet_len", "tracklet_len")):
+        assert np.array_equal(st[k_mine], snap[k_ref]), f"frame {f} stream {s}: {k_ref}\n{st[k_mine]}\n{snap[k_ref]}"
+    assert_close(st["mean"], snap["mean"], what=f"frame {f} stream {s} mean")
+    assert_close(st["cov"], snap["cov"], abs_=1e-10, what=f"frame {f} stream {s} cov")
+    assert np.array_equal(st["score"], snap["score"]) and np.array_equal(st["cls"], snap["cls"])
+    assert np.array_equal(st["det_ind"], snap["det_ind"])
+
+
+def test_bytetrack_replays_reference_golden():
+    from yolo_tracking_b200.batch import BatchedTracker
+    for name in ("bytetrack_c1", "bytetrack_churn"):
+        g = load_golden(name)
+        p = g["params"]
+        dets, nd = g["dets"], g["ndets"]
+        trk = BatchedTracker("bytetrack", 1, max_tracks=128, max_dets=128, track_thresh=p[0], match_thresh=p[1],
+                             track_buffer=int(p[2]), frame_rate=int(p[3]))
+        cov_frames = {int(f): k for k, f in enumerate(g["cov_frames"])}
+        cov_offs = [0]
+        for f in g["cov_frames"]:
+            cov_offs.append(cov_offs[-1] + int(g["counts"][f].sum()))
+        for f in range(dets.shape[0]):
+            d, n = _pad([dets[f, :nd[f]]], 128)
+            out, nout = trk.update_batch(d, n)
+            ref = g["out"][g["out_offs"][f]:g["out_offs"][f + 1]]
+            assert nout[0] == len(ref), f"{name} frame {f}: {nout[0]} rows vs {len(ref)}"
+            o = out[0, :nout[0]]
+            assert np.array_equal(o[:, 4:], ref[:, 4:]), f"{name} frame {f}: id/conf/cls/det_ind"
+            assert_close(o[:, :4], ref[:, :4], what=f"{name} frame {f} boxes")
+            st = trk.state(0)
+            assert (st["n_tracked"], st["n_lost"]) == tuple(g["counts"][f])
+            rec = g["rec"][g["rec_offs"][f]:g["rec_offs"][f + 1]]
+            mine = np.stack([st["track_id"], st["state"], st["is_activated"], st["frame_id_t"], st["start_frame"],
+                             st["tracklet_len"]], axis=1).reshape(-1, 6)
+            assert np.array_equal(mine, rec), f"{name} frame {f}: lifecycle records"
+            assert_close(st["mean"], g["mean"][g["rec_offs"][f]:g["rec_offs"][f + 1]], what=f"{name} frame {f} mean")
+            if f in cov_frames:
+                k = cov_frames[f]
+                assert_close(st["cov"].reshape(-1, 64), g["cov"][cov_offs[k]:cov_offs[k + 1]], abs_=1e-10, what=f"{name} frame {f} cov")
+        trk.sync()
+        assert trk.track_updates() == int(g["pool"].sum())
+        trk.close()
+
+
+def test_bytetrack_known_answer_and_empty():
+    from yolo_tracking_b200.batch import BatchedTracker
+    g = load_golden("bytetrack_2box")
+    trk = BatchedTracker("bytetrack", 1, max_tracks=32, max_dets=32, track_thresh=0.5, match_thresh=0.8,
+                         track_buffer=30, frame_rate=30)
+    for k in range(3):
+        d, n = _pad([g["det"]], 32)
+        out, nout = trk.update_batch(d, n)
+        assert nout[0] == 2
+        assert_close(out[0, :2], g["out"][k])
+    trk.reset()
+    d, n = _pad([np.zeros((0, 6))], 32)
+    out, nout = trk.update_batch(d, n)
+    assert nout[0] == 0
+    trk.close()
+
+
+@pytest.mark.parametrize("n_streams,n_objects,n_frames,kw", [
+    (16, 40, 60, {}),
+    (8, 20, 120, dict(miss_prob=0.3, fp_rate=3.0)),
+    (4, 200, 30, {}),
+])
+def test_bytetrack_multistream_vs_oracle(n_streams, n_objects, n_frames, kw):
+    from oracle.bytetrack import ByteTrackOracle
+    from yolo_tracking_b200.batch import BatchedTracker
+    from yolo_tracking_b200.synth import make_batch
+    dmax = 256 if n_objects > 100 else 64
+    dets, nd, _ = make_batch(5, n_streams, n_objects, n_frames, dmax=dmax, **kw)
+    trk = BatchedTracker("bytetrack", n_streams, max_tracks=dmax, max_dets=dmax, track_thresh=0.5, match_thresh=0.8,
+                         track_buffer=30, frame_rate=30)
+    oracles = [ByteTrackOracle(0.5, 0.8, 30, 30) for _ in range(n_streams)]
+    for f in range(n_frames):
+        out, nout = trk.update_batch(np.ascontiguousarray(dets[f]), np.ascontiguousarray(nd[f]))
+        for s in range(n_streams):
+            ref = oracles[s].update(dets[f, s, :nd[f, s]], None).reshape(-1, 8)
+            assert nout[s] == len(ref), f"frame {f} stream {s}: rows {nout[s]} vs {len(ref)}"
+            o = out[s, :nout[s]]
+            assert np.array_equal(o[:, 4:], ref[:, 4:]), f"frame {f} stream {s}: ids"
+            assert_close(o[:, :4], ref[:, :4], what=f"frame {f} stream {s} boxes")
+        if f % 10 == 9 or f == n_frames - 1:
+            for s in range(n_streams):
+                _check_stream_state(trk.state(s), oracles[s].snapshot(), f, s)
+    trk.sync()
+    assert trk.track_updates() == sum(o.track_updates for o in oracles)
+    trk.close()

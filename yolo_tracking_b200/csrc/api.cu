@@ -1,0 +1,314 @@
+// C-ABI of the tracker contexts (include/b200track.h): device state, the batched frame step,
+// the host-buffer step with a 3-deep copy/compute/copy pipeline, and the parity probe.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200track.h"
+#include "api_util.h"
+#include "layout.h"
+#include "step_params.h"
+
+namespace b200 {
+thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+}  // namespace b200
+
+using b200::set_error;
+
+#define CU_TRY(expr)                                                                       \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                 \
+            return B200TRACK_ERR_CUDA;                                                     \
+        }                                                                                  \
+    } while (0)
+
+namespace {
+constexpr int NSLOT = 3;
+
+struct HostSlot {
+    double* d_dets = nullptr;
+    int32_t* d_ndets = nullptr;
+    float* d_feats = nullptr;
+    double* d_out = nullptr;
+    int32_t* d_nout = nullptr;
+    cudaEvent_t in_ready = nullptr, done = nullptr, out_ready = nullptr;
+    bool used = false;
+};
+}  // namespace
+
+struct b200track_ctx {
+    b200track_config cfg;
+    b200::StepParams p;
+    int kf_kind = 0;
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    HostSlot slot[NSLOT];
+    uint64_t launches = 0;
+    int32_t* h_err = nullptr;   // pinned
+};
+
+static int check_cfg(const b200track_config* c) {
+    if (!c) { set_error("cfg is NULL"); return B200TRACK_ERR_ARG; }
+    if (c->n_streams <= 0) { set_error("n_streams must be > 0"); return B200TRACK_ERR_ARG; }
+    if (c->max_tracks <= 0 || c->max_tracks % 32 || c->max_tracks > 992) {
+        set_error("max_tracks must be a multiple of 32 in [32, 992]"); return B200TRACK_ERR_ARG; }
+    if (c->max_dets <= 0 || c->max_dets % 32 || c->max_dets > 992) {
+        set_error("max_dets must be a multiple of 32 in [32, 992]"); return B200TRACK_ERR_ARG; }
+    if (c->kind != B200TRACK_BYTETRACK && c->kind != B200TRACK_OCSORT && c->kind != B200TRACK_BOTSORT) {
+        set_error("unknown tracker kind"); return B200TRACK_ERR_ARG; }
+    return 0;
+}
+
+extern "C" int b200track_abi_version(void) { return B200TRACK_ABI_VERSION; }
+extern "C" const char* b200track_last_error(void) { return b200::g_last_error.c_str(); }
+
+extern "C" void b200track_destroy(b200track_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    cudaDeviceSynchronize();
+    cudaFree(ctx->p.state_f); cudaFree(ctx->p.state_i); cudaFree(ctx->p.counts);
+    cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err);
+    for (auto& s : ctx->slot) {
+        cudaFree(s.d_dets); cudaFree(s.d_ndets); cudaFree(s.d_feats); cudaFree(s.d_out); cudaFree(s.d_nout);
+        if (s.in_ready) cudaEventDestroy(s.in_ready);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.out_ready) cudaEventDestroy(s.out_ready);
+    }
+    if (ctx->s_compute) cudaStreamDestroy(ctx->s_compute);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    delete ctx;
+}
+
+extern "C" int b200track_reset(b200track_ctx* ctx) {
+    if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
+    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t S = ctx->cfg.n_streams, T = ctx->cfg.max_tracks;
+    CU_TRY(cudaMemset(ctx->p.state_f, 0, S * B200_NF * T * sizeof(double)));
+    CU_TRY(cudaMemset(ctx->p.state_i, 0, S * B200_NI * T * sizeof(int)));
+    CU_TRY(cudaMemset(ctx->p.counts, 0, S * 4 * sizeof(int)));
+    CU_TRY(cudaMemset(ctx->p.track_updates, 0, S * sizeof(unsigned long long)));
+    CU_TRY(cudaMemset(ctx->p.err, 0, sizeof(int)));
+    return 0;
+}
+
+extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out_ctx) {
+    if (!out_ctx) { set_error("out_ctx is NULL"); return B200TRACK_ERR_ARG; }
+    *out_ctx = nullptr;
+    if (int rc = check_cfg(cfg)) return rc;
+    if (cfg->kind != B200TRACK_BYTETRACK) {
+        set_error("tracker kind not built yet in this library version");
+        return B200TRACK_ERR_STATE;
+    }
+    int ndev = 0;
+    CU_TRY(cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) { set_error("no such CUDA device"); return B200TRACK_ERR_CUDA; }
+    CU_TRY(cudaSetDevice(cfg->device));
+    b200track_ctx* ctx = new b200track_ctx();
+    ctx->cfg = *cfg;
+    b200::StepParams& p = ctx->p;
+    memset(&p, 0, sizeof(p));
+    p.n_streams = cfg->n_streams; p.max_tracks = cfg->max_tracks; p.max_dets = cfg->max_dets; p.feat_dim = cfg->feat_dim;
+    p.track_thresh = cfg->track_thresh;
+    p.low_thresh = cfg->track_low_thresh;
+    p.new_thresh = cfg->new_track_thresh;
+    p.match_thresh = cfg->match_thresh;
+    p.second_thresh = 0.5;      // byte_tracker.py:211
+    p.unconf_thresh = 0.7;      // byte_tracker.py:233
+    p.dup_thresh = 0.15;        // byte_tracker.py:314
+    p.proximity_thresh = cfg->proximity_thresh;
+    p.appearance_thresh = cfg->appearance_thresh;
+    p.max_time_lost = (int)(cfg->frame_rate / 30.0 * cfg->track_buffer);   // byte_tracker.py:128-129
+    ctx->kf_kind = cfg->kind == B200TRACK_BOTSORT ? B200TRACK_KF_XYWH : B200TRACK_KF_XYAH;
+    const size_t S = cfg->n_streams, T = cfg->max_tracks, D = cfg->max_dets;
+    int rc = 0;
+    auto fail = [&](int code) { b200track_destroy(ctx); return code; };
+#define CU_TRY_CTX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return fail(B200TRACK_ERR_CUDA); } } while (0)
+    CU_TRY_CTX(cudaMalloc(&p.state_f, S * B200_NF * T * sizeof(double)));
+    CU_TRY_CTX(cudaMalloc(&p.state_i, S * B200_NI * T * sizeof(int)));
+    CU_TRY_CTX(cudaMalloc(&p.counts, S * 4 * sizeof(int)));
+    CU_TRY_CTX(cudaMalloc(&p.track_updates, S * sizeof(unsigned long long)));
+    CU_TRY_CTX(cudaMalloc(&p.err, sizeof(int)));
+    CU_TRY_CTX(cudaMallocHost(&ctx->h_err, sizeof(int32_t)));
+    CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
+    CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+    CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+    for (auto& s : ctx->slot) {
+        CU_TRY_CTX(cudaMalloc(&s.d_dets, S * D * 6 * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&s.d_ndets, S * sizeof(int32_t)));
+        if (cfg->feat_dim > 0) CU_TRY_CTX(cudaMalloc(&s.d_feats, S * D * (size_t)cfg->feat_dim * sizeof(float)));
+        CU_TRY_CTX(cudaMalloc(&s.d_out, S * T * 8 * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&s.d_nout, S * sizeof(int32_t)));
+        CU_TRY_CTX(cudaEventCreateWithFlags(&s.in_ready, cudaEventDisableTiming));
+        CU_TRY_CTX(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CU_TRY_CTX(cudaEventCreateWithFlags(&s.out_ready, cudaEventDisableTiming));
+    }
+    const size_t smem = b200::bytetrack_step_smem(cfg->max_tracks, cfg->max_dets);
+    int max_smem = 0;
+    CU_TRY_CTX(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
+    if (smem > (size_t)max_smem) {
+        set_error("max_tracks / max_dets need more shared memory than one CTA can have");
+        return fail(B200TRACK_ERR_CAPACITY);
+    }
+    rc = b200track_reset(ctx);
+    if (rc) return fail(rc);
+    *out_ctx = ctx;
+    return 0;
+}
+
+static int launch_step(b200track_ctx* ctx, const double* d_dets, const int32_t* d_ndets, const float* d_feats,
+                       int32_t img_h, int32_t img_w, double* d_out, int32_t* d_nout, cudaStream_t st) {
+    (void)img_h; (void)img_w;
+    b200::StepParams p = ctx->p;
+    p.dets = d_dets; p.ndets = d_ndets; p.feats = d_feats; p.out = d_out; p.nout = d_nout;
+    CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, st));
+    ctx->launches += 1;
+    return 0;
+}
+
+extern "C" int b200track_step(b200track_ctx* ctx, const double* d_dets, const int32_t* d_ndets,
+                              const float* d_feats, int32_t img_h, int32_t img_w,
+                              double* d_out, int32_t* d_nout, void* stream) {
+    if (!ctx || !d_dets || !d_ndets || !d_out || !d_nout) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    return launch_step(ctx, d_dets, d_ndets, d_feats, img_h, img_w, d_out, d_nout, (cudaStream_t)stream);
+}
+
+extern "C" int b200track_host_slots(b200track_ctx* ctx) { return ctx ? NSLOT : B200TRACK_ERR_ARG; }
+
+extern "C" int b200track_submit_host(b200track_ctx* ctx, int32_t slot, const double* h_dets,
+                                     const int32_t* h_ndets, const float* h_feats, int32_t img_h,
+                                     int32_t img_w, double* h_out, int32_t* h_nout) {
+    if (!ctx || !h_dets || !h_ndets || !h_out || !h_nout) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    if (slot < 0 || slot >= NSLOT) { set_error("slot out of range"); return B200TRACK_ERR_ARG; }
+    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    HostSlot& s = ctx->slot[slot];
+    const size_t S = ctx->cfg.n_streams, T = ctx->cfg.max_tracks, D = ctx->cfg.max_dets;
+    if (s.used) {
+        CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.done, 0));        // previous step on this slot consumed its inputs
+        CU_TRY(cudaStreamWaitEvent(ctx->s_compute, s.out_ready, 0)); // ... and its outputs have been read back
+    }
+    // only the rows any stream actually uses are copied (pitch = one stream's padded block)
+    int maxnd = 0;
+    for (size_t i = 0; i < S; ++i) maxnd = h_ndets[i] > maxnd ? h_ndets[i] : maxnd;
+    if (maxnd > (int)D) maxnd = (int)D;
+    CU_TRY(cudaMemcpyAsync(s.d_ndets, h_ndets, S * sizeof(int32_t), cudaMemcpyHostToDevice, ctx->s_h2d));
+    if (maxnd > 0)
+        CU_TRY(cudaMemcpy2DAsync(s.d_dets, D * 6 * sizeof(double), h_dets, D * 6 * sizeof(double),
+                                 (size_t)maxnd * 6 * sizeof(double), S, cudaMemcpyHostToDevice, ctx->s_h2d));
+    if (ctx->cfg.feat_dim > 0 && h_feats && maxnd > 0) {
+        const size_t row = (size_t)ctx->cfg.feat_dim * sizeof(float);
+        CU_TRY(cudaMemcpy2DAsync(s.d_feats, D * row, h_feats, D * row, maxnd * row, S, cudaMemcpyHostToDevice, ctx->s_h2d));
+    }
+    CU_TRY(cudaEventRecord(s.in_ready, ctx->s_h2d));
+    CU_TRY(cudaStreamWaitEvent(ctx->s_compute, s.in_ready, 0));
+    if (int rc = launch_step(ctx, s.d_dets, s.d_ndets, ctx->cfg.feat_dim > 0 ? s.d_feats : nullptr, img_h, img_w,
+                             s.d_out, s.d_nout, ctx->s_compute)) return rc;
+    CU_TRY(cudaEventRecord(s.done, ctx->s_compute));
+    CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, s.done, 0));
+    CU_TRY(cudaMemcpyAsync(h_nout, s.d_nout, S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU_TRY(cudaMemcpyAsync(h_out, s.d_out, S * T * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU_TRY(cudaEventRecord(s.out_ready, ctx->s_d2h));
+    s.used = true;
+    return 0;
+}
+
+extern "C" int b200track_wait_host(b200track_ctx* ctx, int32_t slot) {
+    if (!ctx || slot < 0 || slot >= NSLOT) { set_error("bad ctx / slot"); return B200TRACK_ERR_ARG; }
+    if (!ctx->slot[slot].used) return 0;
+    CU_TRY(cudaEventSynchronize(ctx->slot[slot].out_ready));
+    return 0;
+}
+
+extern "C" int b200track_step_host(b200track_ctx* ctx, const double* h_dets, const int32_t* h_ndets,
+                                   const float* h_feats, int32_t img_h, int32_t img_w,
+                                   double* h_out, int32_t* h_nout) {
+    if (int rc = b200track_submit_host(ctx, 0, h_dets, h_ndets, h_feats, img_h, img_w, h_out, h_nout)) return rc;
+    return b200track_wait_host(ctx, 0);
+}
+
+extern "C" int b200track_sync(b200track_ctx* ctx) {
+    if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
+    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(ctx->h_err, ctx->p.err, sizeof(int), cudaMemcpyDeviceToHost));
+    const int e = *ctx->h_err;
+    if (e) {
+        CU_TRY(cudaMemset(ctx->p.err, 0, sizeof(int)));
+        set_error(std::string("capacity overflow:") + ((e & B200_ERR_DET_OVERFLOW) ? " detections > max_dets" : "") +
+                  ((e & B200_ERR_TRACK_OVERFLOW) ? " tracks > max_tracks" : ""));
+        return B200TRACK_ERR_CAPACITY;
+    }
+    return 0;
+}
+
+extern "C" int b200track_track_updates(b200track_ctx* ctx, uint64_t* h_total) {
+    if (!ctx || !h_total) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    std::vector<unsigned long long> h(ctx->cfg.n_streams);
+    CU_TRY(cudaMemcpy(h.data(), ctx->p.track_updates, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    uint64_t tot = 0;
+    for (auto v : h) tot += v;
+    *h_total = tot;
+    return 0;
+}
+
+extern "C" int b200track_launch_count(b200track_ctx* ctx, uint64_t* h_launches) {
+    if (!ctx || !h_launches) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    *h_launches = ctx->launches;
+    return 0;
+}
+
+extern "C" int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state, uint64_t* h_smem) {
+    if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
+    if (h_state) *h_state = (uint64_t)ctx->cfg.max_tracks * B200_SLOT_BYTES + 4 * sizeof(int) + sizeof(unsigned long long);
+    if (h_smem) *h_smem = b200::bytetrack_step_smem(ctx->cfg.max_tracks, ctx->cfg.max_dets);
+    return 0;
+}
+
+extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int32_t* h_counts,
+                                   int32_t* h_rec, double* h_mean, double* h_cov, double* h_aux) {
+    if (!ctx || !h_counts) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    if (stream_index < 0 || stream_index >= ctx->cfg.n_streams) { set_error("stream_index out of range"); return B200TRACK_ERR_ARG; }
+    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t T = ctx->cfg.max_tracks, s = stream_index;
+    std::vector<double> f(B200_NF * T);
+    std::vector<int> iv(B200_NI * T);
+    CU_TRY(cudaMemcpy(h_counts, ctx->p.counts + 4 * s, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(f.data(), ctx->p.state_f + s * B200_NF * T, f.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(iv.data(), ctx->p.state_i + s * B200_NI * T, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    const int n = h_counts[0] + h_counts[1];
+    for (int t = 0; t < n && t < (int)T; ++t) {
+        const int fl = iv[B200_TI_FLAGS * T + t];
+        if (h_rec) {
+            int32_t* r = h_rec + 6 * t;
+            r[0] = iv[B200_TI_ID * T + t]; r[1] = fl & 3; r[2] = (fl & B200_FLAG_ACTIVATED) ? 1 : 0;
+            r[3] = iv[B200_TI_FRAME * T + t]; r[4] = iv[B200_TI_START * T + t]; r[5] = iv[B200_TI_LEN * T + t];
+        }
+        if (h_mean) for (int c = 0; c < 8; ++c) h_mean[8 * t + c] = f[(B200_TF_MEAN + c) * T + t];
+        if (h_cov) {
+            double* c = h_cov + 64 * t;
+            for (int k = 0; k < 64; ++k) c[k] = 0.0;
+            for (int a = 0; a < 4; ++a) {
+                c[a * 8 + a] = f[(B200_TF_COV + 3 * a + 0) * T + t];
+                c[a * 8 + a + 4] = c[(a + 4) * 8 + a] = f[(B200_TF_COV + 3 * a + 1) * T + t];
+                c[(a + 4) * 8 + a + 4] = f[(B200_TF_COV + 3 * a + 2) * T + t];
+            }
+        }
+        if (h_aux) {
+            h_aux[3 * t + 0] = f[B200_TF_SCORE * T + t];
+            h_aux[3 * t + 1] = f[B200_TF_CLS * T + t];
+            h_aux[3 * t + 2] = (double)iv[B200_TI_DET * T + t];
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,166 @@
+// Exact linear assignment with lap.lapjv(cost, extend_cost=True, cost_limit=L) semantics on a
+// pruned (sparse) candidate graph, one CTA per stream.
+//
+// lapjv's (R+C)x(R+C) extended matrix (reference call site
+// boxmot/utils/matching.py:56-71) has the optimum of
+//     sum_{matched} c_ij + L/2 * (#unmatched rows + #unmatched cols)
+//  =  const + sum_{matched} (c_ij - L),
+// so a pair with c_ij > L is never used and can be pruned EXACTLY.  What is left is a sparse
+// bipartite graph that falls apart into many small connected components; each component is
+// an independent assignment problem.  Here:
+//   1. all threads build the candidate bitmask adj[word][row] (caller),
+//   2. components are found with a lock-free union-find in shared memory,
+//   3. the thread that owns a component's root row solves it with the shortest-augmenting-
+//      path (Hungarian / JV augmentation) algorithm over the sparse rows.  Every row owns a
+//      private "stay unmatched" column of cost L, real edges keep their cost c_ij (columns
+//      stay unmatched for free): the same objective up to a constant, with the dummy block
+//      of the extended matrix never materialised and no cost ever rescaled.
+// The dual variables, predecessor links and work lists are shared-memory arrays indexed by
+// the stream-global row / column id, so concurrent components never touch the same entry.
+// On tie-free inputs the optimum is unique, hence identical to lapjv's x, y.
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct LapWork {
+    int Tmax, Dmax;
+    uint32_t* adj;      // [Dmax/32][Tmax]
+    double* u;          // [Tmax]
+    double* v;          // [Dmax]
+    double* dist;       // [Dmax]
+    int* parent;        // [Tmax + Dmax]
+    int* head;          // [Tmax]
+    short* rnext;       // [Tmax]
+    short* xr;          // [Tmax]  column of row, -1 = unmatched
+    short* yc;          // [Dmax]  row of column, -1 = free
+    short* pred;        // [Dmax]
+    short* nextc;       // [Dmax]
+    short* mark;        // [Dmax]  stamp when reached
+    short* scn;         // [Dmax]  stamp when scanned
+};
+
+__device__ __forceinline__ int uf_find(volatile int* parent, int x) {
+    while (true) {
+        const int p = parent[x];
+        if (p == x) return x;
+        const int g = parent[p];
+        parent[x] = g;          // path halving: g is always an ancestor of x, races are benign
+        x = g;
+    }
+}
+
+__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return;
+        if (a > b) { const int t = a; a = b; b = t; }
+        if (atomicCAS(&parent[b], b, a) == b) return;   // link the larger root under the smaller
+    }
+}
+
+// Insert one row into the matching of its component (one shortest augmenting path).
+template <class Cost>
+__device__ void lap_insert_row(const LapWork& w, int words, double lambda, const Cost& cost, int i0) {
+    const short stamp = (short)(i0 + 1);
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double minVal = 0.0;
+    int i = i0;
+    double bestDummy = INF;
+    int bestDummyRow = -1;
+    int rhead = -1, rtail = -1;
+    int sink = -1;
+    while (true) {
+        const double ui = w.u[i];
+        const double dd = minVal + lambda - ui;        // row i may stay unmatched at cost lambda
+        if (dd < bestDummy) { bestDummy = dd; bestDummyRow = i; }
+        for (int wd = 0; wd < words; ++wd) {
+            uint32_t bits = w.adj[wd * w.Tmax + i];
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int j = wd * 32 + b;
+                if (w.scn[j] == stamp) continue;
+                const double r = minVal + cost(i, j) - ui - w.v[j];
+                if (w.mark[j] != stamp) {
+                    w.mark[j] = stamp; w.dist[j] = r; w.pred[j] = (short)i; w.nextc[j] = -1;
+                    if (rtail < 0) rhead = j; else w.nextc[rtail] = (short)j;
+                    rtail = j;
+                } else if (r < w.dist[j]) { w.dist[j] = r; w.pred[j] = (short)i; }
+            }
+        }
+        int jmin = -1;
+        double dmin = INF;
+        for (int j = rhead; j >= 0; j = w.nextc[j])
+            if (w.scn[j] != stamp && w.dist[j] < dmin) { dmin = w.dist[j]; jmin = j; }
+        if (jmin < 0 || bestDummy <= dmin) { sink = -1; minVal = bestDummy; break; }
+        minVal = dmin;
+        w.scn[jmin] = stamp;
+        if (w.yc[jmin] < 0) { sink = jmin; break; }
+        i = w.yc[jmin];
+    }
+    // dual update (rows of the tree are the mates of the scanned columns, plus i0)
+    w.u[i0] += minVal;
+    for (int j = rhead; j >= 0; j = w.nextc[j]) {
+        if (w.scn[j] != stamp) continue;
+        const double delta = minVal - w.dist[j];
+        const int r = w.yc[j];
+        if (r >= 0) w.u[r] += delta;
+        w.v[j] -= delta;
+    }
+    // augment
+    int j;
+    if (sink >= 0) j = sink;
+    else {
+        if (bestDummyRow == i0) return;               // i0 itself stays unmatched
+        j = w.xr[bestDummyRow];
+        w.xr[bestDummyRow] = -1;
+    }
+    while (true) {
+        const int r = w.pred[j];
+        w.yc[j] = (short)r;
+        const int t = w.xr[r];
+        w.xr[r] = (short)j;
+        j = t;
+        if (r == i0) break;
+    }
+}
+
+// Whole-CTA solve.  adj[word][row] must be complete (and zero for rows/cols not taking
+// part); rows are 0..nrows-1, columns 0..32*words-1.  Results in xr / yc.
+template <int NT, class Cost>
+__device__ void lap_sparse_solve(const LapWork& w, int nrows, int words, double lambda, const Cost& cost) {
+    const int tid = threadIdx.x;
+    const int ncols = words * 32;
+    for (int t = tid; t < nrows; t += NT) { w.xr[t] = -1; w.u[t] = 0.0; w.parent[t] = t; w.head[t] = -1; }
+    for (int j = tid; j < ncols; j += NT) {
+        w.yc[j] = -1; w.v[j] = 0.0; w.parent[w.Tmax + j] = w.Tmax + j; w.mark[j] = 0; w.scn[j] = 0;
+    }
+    __syncthreads();
+    for (int task = tid; task < nrows * words; task += NT) {
+        const int wd = task / nrows, t = task - wd * nrows;
+        uint32_t bits = w.adj[wd * w.Tmax + t];
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            uf_union(w.parent, t, w.Tmax + wd * 32 + b);
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < nrows; t += NT) {
+        bool any = false;
+        for (int wd = 0; wd < words; ++wd) any |= w.adj[wd * w.Tmax + t] != 0;
+        if (any) {
+            const int root = uf_find(w.parent, t);      // smallest row of the component
+            w.rnext[t] = (short)atomicExch(&w.head[root], t);
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < nrows; t += NT) {
+        for (int r = w.head[t]; r >= 0; r = w.rnext[r]) lap_insert_row(w, words, lambda, cost, r);
+    }
+    __syncthreads();
+}
+
+}  // namespace b200

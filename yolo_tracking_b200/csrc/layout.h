@@ -1,0 +1,38 @@
+// Device-resident track-state layout shared by the kernels and the C-ABI (api.cu).
+//
+// Per stream s, slot t (capacity Tmax), "stream-major, component-planar":
+//   state_f[(s * NF + c) * Tmax + t]   fp64 components
+//   state_i[(s * NI + c) * Tmax + t]   int32 components
+//   counts [s * 4 + {0: n_tracked, 1: n_lost, 2: id counter, 3: frame_id}]
+// Slots [0, n_tracked) are the reference's tracked_stracks list IN LIST ORDER, slots
+// [n_tracked, n_tracked + n_lost) its lost_stracks list in list order; every frame step
+// rewrites the slots in the new list order, so list order never needs an indirection.
+// One CTA owns one stream, so a warp reads/writes contiguous 8-byte runs per component
+// (coalesced) and the whole stream state is one contiguous block.
+#pragma once
+
+#define B200_NF 22          // 8 mean + 4 x (pp, pv, vv) + score + cls
+#define B200_NI 6
+#define B200_TF_MEAN 0
+#define B200_TF_COV 8       // + 3 * axis + {0: pp, 1: pv, 2: vv}
+#define B200_TF_SCORE 20
+#define B200_TF_CLS 21
+#define B200_TI_ID 0
+#define B200_TI_FRAME 1
+#define B200_TI_START 2
+#define B200_TI_LEN 3
+#define B200_TI_DET 4
+#define B200_TI_FLAGS 5     // bits 0-1 TrackState, bit 2 is_activated, bit 3 "id is in removed_stracks"
+
+#define B200_ST_NEW 0
+#define B200_ST_TRACKED 1
+#define B200_ST_LOST 2
+#define B200_ST_REMOVED 3
+#define B200_FLAG_ACTIVATED 4
+#define B200_FLAG_STICKY 8
+
+#define B200_ERR_DET_OVERFLOW 1
+#define B200_ERR_TRACK_OVERFLOW 2
+
+// bytes a track slot occupies in HBM (one direction)
+#define B200_SLOT_BYTES (B200_NF * 8 + B200_NI * 4)

@@ -1,0 +1,521 @@
+// Operator-level kernels: the reference's functional API, batched (include/b200track.h).
+// Dense [n,8] / [n,8,8] arrays in the reference's layout, so these also accept covariances
+// that are NOT block-sparse (e.g. after an externally applied camera-motion warp).
+//
+// Kalman kernels: a CTA stages a contiguous run of tracks (mean + covariance, 72 doubles
+// each) in shared memory with coalesced loads, one thread then owns one track (row stride
+// 73 doubles = conflict-free), results go back with coalesced stores.  HBM-bound:
+// 2 x 576 B per track for predict / update.
+#include <type_traits>
+
+#include "api_util.h"
+#include "boxes.cuh"
+#include "kf.cuh"
+#include "lap_sparse.cuh"
+
+namespace b200 {
+namespace {
+
+constexpr int KF_TPB = 64;          // tracks (= threads) per CTA
+constexpr int KF_STRIDE = 73;       // 8 mean + 64 cov + 1 pad
+
+__device__ __forceinline__ void kf_stage_in(double* sm, const double* mean, const double* cov, int base, int cnt) {
+    for (int i = threadIdx.x; i < cnt * 8; i += blockDim.x) sm[(i >> 3) * KF_STRIDE + (i & 7)] = mean[(size_t)base * 8 + i];
+    for (int i = threadIdx.x; i < cnt * 64; i += blockDim.x) sm[(i >> 6) * KF_STRIDE + 8 + (i & 63)] = cov[(size_t)base * 64 + i];
+    __syncthreads();
+}
+__device__ __forceinline__ void kf_stage_out(const double* sm, double* mean, double* cov, int base, int cnt) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * 8; i += blockDim.x) mean[(size_t)base * 8 + i] = sm[(i >> 3) * KF_STRIDE + (i & 7)];
+    for (int i = threadIdx.x; i < cnt * 64; i += blockDim.x) cov[(size_t)base * 64 + i] = sm[(i >> 6) * KF_STRIDE + 8 + (i & 63)];
+}
+
+// per-axis standard deviations (bytetrack_kf.py:76-85,107-116,143-148 / botsort_kf.py same lines)
+template <int KIND>
+__device__ __forceinline__ void kf_std(const double* ref4, double ps, double vs, double cp, double cv, double* std8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (KIND != KF_XYWH && i == 2) { std8[i] = cp; std8[i + 4] = cv; }
+        else {
+            const double r = kf_ref<KIND>(ref4, i);
+            std8[i] = xmul(ps, r);
+            std8[i + 4] = xmul(vs, r);
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(KF_TPB) kf_initiate_kernel(int n, const double* __restrict__ z, double* mean, double* cov) {
+    __shared__ double sm[KF_TPB * KF_STRIDE];
+    const int base = blockIdx.x * KF_TPB, cnt = min(KF_TPB, n - base), t = threadIdx.x;
+    if (t < cnt) {
+        double* m = sm + t * KF_STRIDE;
+        double* P = m + 8;
+        double zz[4], sd[8];
+        for (int i = 0; i < 4; ++i) zz[i] = z[(size_t)(base + t) * 4 + i];
+        kf_std<KIND>(zz, 2 * KF_W_POS, 10 * KF_W_VEL, 1e-2, 1e-5, sd);
+        for (int i = 0; i < 64; ++i) P[i] = 0.0;
+        for (int i = 0; i < 4; ++i) { m[i] = zz[i]; m[i + 4] = 0.0; }
+        for (int i = 0; i < 8; ++i) P[i * 9] = xmul(sd[i], sd[i]);
+    }
+    kf_stage_out(sm, mean, cov, base, cnt);
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(KF_TPB) kf_predict_kernel(int n, double* mean, double* cov) {
+    __shared__ double sm[KF_TPB * KF_STRIDE];
+    const int base = blockIdx.x * KF_TPB, cnt = min(KF_TPB, n - base), t = threadIdx.x;
+    kf_stage_in(sm, mean, cov, base, cnt);
+    if (t < cnt) {
+        double* m = sm + t * KF_STRIDE;
+        double* P = m + 8;
+        double sd[8];
+        kf_std<KIND>(m, KF_W_POS, KF_W_VEL, 1e-2, 1e-5, sd);
+        for (int i = 0; i < 4; ++i) m[i] = xadd(m[i], m[i + 4]);
+        for (int i = 0; i < 4; ++i)                       // left = F P
+            for (int j = 0; j < 8; ++j) P[i * 8 + j] = xadd(P[i * 8 + j], P[(i + 4) * 8 + j]);
+        for (int i = 0; i < 8; ++i)                       // left F^T
+            for (int j = 0; j < 4; ++j) P[i * 8 + j] = xadd(P[i * 8 + j], P[i * 8 + j + 4]);
+        for (int i = 0; i < 8; ++i) P[i * 9] = xadd(P[i * 9], xmul(sd[i], sd[i]));
+    }
+    kf_stage_out(sm, mean, cov, base, cnt);
+}
+
+// S = H P H^T + R (4x4) and its lower Cholesky factor
+template <int KIND>
+__device__ __forceinline__ void kf_innovation(const double* m, const double* P, double conf, double S[4][4]) {
+    double sd[8];
+    kf_std<KIND>(m, KF_W_POS, KF_W_VEL, 1e-1, 0.0, sd);
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) S[i][j] = P[i * 8 + j];
+    for (int i = 0; i < 4; ++i) {
+        double s = sd[i];
+        if (KIND == KF_XYAH_CONF) s = xmul(xsub(1.0, conf), s);
+        S[i][i] = xadd(S[i][i], xmul(s, s));
+    }
+}
+template <int N>
+__device__ __forceinline__ void chol_lower(double S[4][4], double L[4][4]) {
+    for (int j = 0; j < N; ++j) {
+        double d = S[j][j];
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+        L[j][j] = sqrt(d);
+        for (int i = j + 1; i < N; ++i) {
+            double v = S[i][j];
+            for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+            L[i][j] = v / L[j][j];
+        }
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(KF_TPB) kf_project_kernel(int n, const double* mean, const double* cov,
+                                                            const double* conf, double* pmean, double* pcov) {
+    __shared__ double sm[KF_TPB * KF_STRIDE];
+    const int base = blockIdx.x * KF_TPB, cnt = min(KF_TPB, n - base), t = threadIdx.x;
+    kf_stage_in(sm, mean, cov, base, cnt);
+    if (t < cnt) {
+        const double* m = sm + t * KF_STRIDE;
+        double S[4][4];
+        kf_innovation<KIND>(m, m + 8, conf ? conf[base + t] : 0.0, S);
+        for (int i = 0; i < 4; ++i) pmean[(size_t)(base + t) * 4 + i] = m[i];
+        for (int i = 0; i < 4; ++i)
+            for (int j = 0; j < 4; ++j) pcov[(size_t)(base + t) * 16 + i * 4 + j] = S[i][j];
+    }
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(KF_TPB) kf_update_kernel(int n, double* mean, double* cov, const double* __restrict__ z,
+                                                           const double* __restrict__ conf) {
+    __shared__ double sm[KF_TPB * KF_STRIDE];
+    const int base = blockIdx.x * KF_TPB, cnt = min(KF_TPB, n - base), t = threadIdx.x;
+    kf_stage_in(sm, mean, cov, base, cnt);
+    if (t < cnt) {
+        double* m = sm + t * KF_STRIDE;
+        double* P = m + 8;
+        double S[4][4], L[4][4];
+        kf_innovation<KIND>(m, P, conf ? conf[base + t] : 0.0, S);
+        chol_lower<4>(S, L);
+        // K[r,:] solves S k = P[r,:4]  (cho_solve on (P H^T)^T, bytetrack_kf.py:216-220)
+        double K[8][4];
+        for (int r = 0; r < 8; ++r) {
+            double y[4];
+            for (int i = 0; i < 4; ++i) {
+                double v = P[r * 8 + i];
+                for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
+                y[i] = v / L[i][i];
+            }
+            for (int i = 3; i >= 0; --i) {
+                double v = y[i];
+                for (int k = i + 1; k < 4; ++k) v -= L[k][i] * K[r][k];
+                K[r][i] = v / L[i][i];
+            }
+        }
+        double innov[4];
+        for (int i = 0; i < 4; ++i) innov[i] = xsub(z[(size_t)(base + t) * 4 + i], m[i]);
+        // P -= K (S K^T)
+        double M[4][8];
+        for (int k = 0; k < 4; ++k)
+            for (int c = 0; c < 8; ++c) {
+                double a = 0.0;
+                for (int q = 0; q < 4; ++q) a += S[k][q] * K[c][q];
+                M[k][c] = a;
+            }
+        for (int r = 0; r < 8; ++r) {
+            double a = 0.0;
+            for (int k = 0; k < 4; ++k) a += innov[k] * K[r][k];
+            m[r] = xadd(m[r], a);
+            for (int c = 0; c < 8; ++c) {
+                double b = 0.0;
+                for (int k = 0; k < 4; ++k) b += K[r][k] * M[k][c];
+                P[r * 8 + c] = xsub(P[r * 8 + c], b);
+            }
+        }
+    }
+    kf_stage_out(sm, mean, cov, base, cnt);
+}
+
+// gating_distance: 8 tracks per CTA factor S once, then every thread sweeps measurements
+constexpr int GD_TRACKS = 8;
+template <int KIND>
+__global__ void __launch_bounds__(256) kf_gating_kernel(int T, int D, const double* __restrict__ mean, const double* __restrict__ cov,
+                                                        const double* __restrict__ meas, int only_position, int metric,
+                                                        const double* __restrict__ conf, double* __restrict__ out) {
+    __shared__ double sL[GD_TRACKS][16];
+    __shared__ double sM[GD_TRACKS][4];
+    const int t0 = blockIdx.x * GD_TRACKS, cnt = min(GD_TRACKS, T - t0);
+    const int nd = only_position ? 2 : 4;
+    if (threadIdx.x < cnt) {
+        const int t = t0 + threadIdx.x;
+        double m[8], S[4][4], L[4][4];
+        for (int i = 0; i < 8; ++i) m[i] = mean[(size_t)t * 8 + i];
+        kf_innovation<KIND>(m, cov + (size_t)t * 64, conf ? conf[t] : 0.0, S);
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) L[i][j] = 0.0;
+        if (only_position) chol_lower<2>(S, L); else chol_lower<4>(S, L);
+        for (int i = 0; i < 16; ++i) sL[threadIdx.x][i] = L[i >> 2][i & 3];
+        for (int i = 0; i < 4; ++i) sM[threadIdx.x][i] = m[i];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < cnt * D; idx += blockDim.x) {
+        const int tl = idx / D, j = idx - tl * D;
+        double d[4], zz[4];
+        for (int i = 0; i < nd; ++i) d[i] = xsub(meas[(size_t)j * 4 + i], sM[tl][i]);
+        double acc = 0.0;
+        if (metric == 1) {
+            for (int i = 0; i < nd; ++i) acc = i ? xadd(acc, xmul(d[i], d[i])) : xmul(d[i], d[i]);
+        } else {
+            for (int i = 0; i < nd; ++i) {               // solve_triangular(L, d)
+                double v = d[i];
+                for (int k = 0; k < i; ++k) v -= sL[tl][i * 4 + k] * zz[k];
+                zz[i] = v / sL[tl][i * 4 + i];
+                acc = i ? xadd(acc, xmul(zz[i], zz[i])) : xmul(zz[i], zz[i]);
+            }
+        }
+        out[(size_t)(t0 + tl) * D + j] = acc;
+    }
+}
+
+// pairwise similarities / costs: thread per (i, j), j fastest (coalesced stores)
+__global__ void box_similarity_kernel(int sim, int n, int m, const double* __restrict__ a, const double* __restrict__ b,
+                                      double W, double H, const double* __restrict__ score, int as_distance,
+                                      double* __restrict__ out) {
+    const size_t total = (size_t)n * m;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / m), j = (int)(idx - (size_t)i * m);
+        Box A, Bx;
+        A.x1 = a[i * 4]; A.y1 = a[i * 4 + 1]; A.x2 = a[i * 4 + 2]; A.y2 = a[i * 4 + 3];
+        Bx.x1 = b[j * 4]; Bx.y1 = b[j * 4 + 1]; Bx.x2 = b[j * 4 + 2]; Bx.y2 = b[j * 4 + 3];
+        double v;
+        switch (sim) {
+            case B200TRACK_SIM_GIOU: v = box_giou(A, Bx); break;
+            case B200TRACK_SIM_DIOU: v = box_diou(A, Bx); break;
+            case B200TRACK_SIM_CIOU: v = box_ciou(A, Bx); break;
+            case B200TRACK_SIM_CENTROID: v = box_centroid(A, Bx, W, H); break;
+            default: v = box_iou(A, Bx);
+        }
+        if (as_distance) v = score ? fused_cost(v, score[j]) : xsub(1.0, v);
+        out[idx] = v;
+    }
+}
+
+// embedding_distance (matching.py:145-167): fp32 features, double accumulation, max(0, 1 - cos).
+// 16x16 output tile per CTA, K staged through shared memory in chunks of 64.
+constexpr int ED_TILE = 16, ED_K = 64;
+__global__ void __launch_bounds__(ED_TILE * ED_TILE) embedding_distance_kernel(int n, int m, int dim, const float* __restrict__ a,
+                                                                               const float* __restrict__ b, double* __restrict__ out) {
+    __shared__ float sa[ED_TILE][ED_K + 1], sb[ED_TILE][ED_K + 1];
+    const int tx = threadIdx.x % ED_TILE, ty = threadIdx.x / ED_TILE;
+    const int i0 = blockIdx.y * ED_TILE, j0 = blockIdx.x * ED_TILE;
+    double dot = 0.0, na = 0.0, nb = 0.0;
+    for (int k0 = 0; k0 < dim; k0 += ED_K) {
+        for (int idx = threadIdx.x; idx < ED_TILE * ED_K; idx += ED_TILE * ED_TILE) {
+            const int r = idx / ED_K, k = idx - r * ED_K;
+            sa[r][k] = (i0 + r < n && k0 + k < dim) ? a[(size_t)(i0 + r) * dim + k0 + k] : 0.f;
+            sb[r][k] = (j0 + r < m && k0 + k < dim) ? b[(size_t)(j0 + r) * dim + k0 + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int k = 0; k < ED_K; ++k) {
+            const double x = (double)sa[ty][k], y = (double)sb[tx][k];
+            dot = fma(x, y, dot); na = fma(x, x, na); nb = fma(y, y, nb);
+        }
+        __syncthreads();
+    }
+    const int i = i0 + ty, j = j0 + tx;
+    if (i < n && j < m) {
+        double c = dot / (sqrt(na) * sqrt(nb));
+        if (fabs(c) > 1.0) c = copysign(1.0, c);
+        out[(size_t)i * m + j] = fmax(0.0, 1.0 - c);
+    }
+}
+
+// ---- lapjv: one CTA per problem -------------------------------------------------------
+struct GlobalCost {
+    const double* c; int cols;
+    __device__ __forceinline__ double operator()(int i, int j) const { return c[(size_t)i * cols + j]; }
+};
+
+// finite cost_limit: prune c > L exactly, then the sparse component solver
+__global__ void __launch_bounds__(256) lapjv_sparse_kernel(int rows, int cols, int Rpad, int Cpad, const double* __restrict__ cost,
+                                                           double limit, int* __restrict__ x, int* __restrict__ y) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    const int words = Cpad / 32;
+    LapWork w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { unsigned char* p = raw + off; off = (off + bytes + 15) & ~size_t(15); return p; };
+    w.Tmax = Rpad; w.Dmax = Cpad;
+    w.u = (double*)take(8 * Rpad); w.v = (double*)take(8 * Cpad); w.dist = (double*)take(8 * Cpad);
+    w.adj = (uint32_t*)take(4 * (size_t)words * Rpad);
+    w.parent = (int*)take(4 * (Rpad + Cpad)); w.head = (int*)take(4 * Rpad);
+    w.rnext = (short*)take(2 * Rpad); w.xr = (short*)take(2 * Rpad); w.yc = (short*)take(2 * Cpad);
+    w.pred = (short*)take(2 * Cpad); w.nextc = (short*)take(2 * Cpad); w.mark = (short*)take(2 * Cpad); w.scn = (short*)take(2 * Cpad);
+    const double* c = cost + (size_t)blockIdx.x * rows * cols;
+    GlobalCost gc{c, cols};
+    for (int task = threadIdx.x; task < rows * words; task += blockDim.x) {
+        const int t = task / words, wd = task - t * words;
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int j = wd * 32 + b;
+            if (j < cols && c[(size_t)t * cols + j] <= limit) bits |= 1u << b;
+        }
+        w.adj[wd * Rpad + t] = bits;
+    }
+    __syncthreads();
+    lap_sparse_solve<256>(w, rows, words, limit, gc);
+    for (int t = threadIdx.x; t < rows; t += blockDim.x) x[(size_t)blockIdx.x * rows + t] = w.xr[t];
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) y[(size_t)blockIdx.x * cols + j] = w.yc[j];
+}
+
+// cost_limit = +inf (association.py:23): the dummy entries are max(cost)+1, so every
+// min(R, C) row is matched - a dense problem.  Whole-CTA shortest augmenting path: threads
+// own columns, one block-wide arg-min per Dijkstra step.  A row's private "unmatched" column
+// costs 2 * (max + 1) (= the two dummy entries lapjv pays for an unmatched row + column).
+__global__ void __launch_bounds__(256) lapjv_dense_kernel(int rows, int cols, const double* __restrict__ cost,
+                                                          int* __restrict__ x, int* __restrict__ y) {
+    extern __shared__ __align__(16) unsigned char raw[];
+    constexpr int NT = 256;
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { unsigned char* p = raw + off; off = (off + bytes + 15) & ~size_t(15); return p; };
+    double* u = (double*)take(8 * rows); double* v = (double*)take(8 * cols); double* dist = (double*)take(8 * cols);
+    double* red_v = (double*)take(8 * 32);
+    int* red_i = (int*)take(4 * 32);
+    int* xr = (int*)take(4 * rows); int* yc = (int*)take(4 * cols); int* pred = (int*)take(4 * cols);
+    unsigned char* scn = take(cols);
+    __shared__ double s_min, s_bestDummy, s_lambda;
+    __shared__ int s_jmin, s_cur, s_sink, s_bestRow;
+    const double* c = cost + (size_t)blockIdx.x * rows * cols;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // lambda = 2 * (max + 1)
+    double mx = -INF;
+    for (int i = tid; i < rows * cols; i += NT) mx = fmax(mx, c[i]);
+    for (int d = 16; d; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if (lane == 0) red_v[warp] = mx;
+    __syncthreads();
+    if (tid == 0) { double m2 = red_v[0]; for (int k = 1; k < NT / 32; ++k) m2 = fmax(m2, red_v[k]); s_lambda = 2.0 * (m2 + 1.0); }
+    for (int i = tid; i < rows; i += NT) { u[i] = 0.0; xr[i] = -1; }
+    for (int j = tid; j < cols; j += NT) { v[j] = 0.0; yc[j] = -1; }
+    __syncthreads();
+    const double lambda = s_lambda;
+    for (int i0 = 0; i0 < rows; ++i0) {
+        for (int j = tid; j < cols; j += NT) { dist[j] = INF; scn[j] = 0; pred[j] = -1; }
+        if (tid == 0) { s_min = 0.0; s_cur = i0; s_bestDummy = INF; s_bestRow = -1; s_sink = -2; }
+        __syncthreads();
+        while (true) {
+            const int i = s_cur;
+            const double minVal = s_min, ui = u[i];
+            double best = INF; int bj = -1;
+            for (int j = tid; j < cols; j += NT) {
+                if (scn[j]) continue;
+                const double r = minVal + c[(size_t)i * cols + j] - ui - v[j];
+                double dj = dist[j];
+                if (r < dj) { dj = r; dist[j] = r; pred[j] = i; }
+                if (dj < best) { best = dj; bj = j; }
+            }
+            for (int d = 16; d; d >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, d);
+                const int oj = __shfl_xor_sync(0xffffffffu, bj, d);
+                if (ob < best || (ob == best && oj >= 0 && (bj < 0 || oj < bj))) { best = ob; bj = oj; }
+            }
+            if (lane == 0) { red_v[warp] = best; red_i[warp] = bj; }
+            __syncthreads();
+            if (tid == 0) {
+                double b = red_v[0]; int j = red_i[0];
+                for (int k = 1; k < NT / 32; ++k)
+                    if (red_v[k] < b || (red_v[k] == b && red_i[k] >= 0 && (j < 0 || red_i[k] < j))) { b = red_v[k]; j = red_i[k]; }
+                const double dd = minVal + lambda - ui;
+                if (dd < s_bestDummy) { s_bestDummy = dd; s_bestRow = i; }
+                if (j < 0 || s_bestDummy <= b) { s_sink = -1; s_min = s_bestDummy; }
+                else {
+                    s_min = b; scn[j] = 1; s_jmin = j;
+                    if (yc[j] < 0) s_sink = j; else s_cur = yc[j];
+                }
+            }
+            __syncthreads();
+            if (s_sink != -2) break;
+        }
+        const double minVal = s_min;
+        const int sink = s_sink;
+        for (int j = tid; j < cols; j += NT) {
+            if (!scn[j]) continue;
+            const double delta = minVal - dist[j];
+            const int r = yc[j];
+            if (r >= 0) u[r] += delta;
+            v[j] -= delta;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            u[i0] += minVal;
+            int j = -1;
+            bool go = true;
+            if (sink >= 0) j = sink;
+            else if (s_bestRow == i0) go = false;
+            else { j = xr[s_bestRow]; xr[s_bestRow] = -1; }
+            while (go) {
+                const int r = pred[j];
+                yc[j] = r;
+                const int t = xr[r];
+                xr[r] = j;
+                j = t;
+                if (r == i0) break;
+            }
+        }
+        __syncthreads();
+    }
+    for (int t = tid; t < rows; t += NT) x[(size_t)blockIdx.x * rows + t] = xr[t];
+    for (int j = tid; j < cols; j += NT) y[(size_t)blockIdx.x * cols + j] = yc[j];
+}
+
+template <class F>
+int dispatch_kind(int kind, F&& f) {
+    switch (kind) {
+        case B200TRACK_KF_XYAH: f(std::integral_constant<int, KF_XYAH>{}); return 0;
+        case B200TRACK_KF_XYWH: f(std::integral_constant<int, KF_XYWH>{}); return 0;
+        case B200TRACK_KF_XYAH_CONF: f(std::integral_constant<int, KF_XYAH_CONF>{}); return 0;
+    }
+    set_error("unknown kf_kind");
+    return B200TRACK_ERR_ARG;
+}
+
+}  // namespace
+}  // namespace b200
+
+using namespace b200;
+
+#define LAUNCH_CHECK() B200_CU_TRY(cudaGetLastError())
+
+extern "C" int b200track_kf_initiate(int32_t kind, int32_t n, const double* z, double* mean, double* cov, void* st) {
+    if (n < 0 || !z || !mean || !cov) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n == 0) return 0;
+    int rc = dispatch_kind(kind, [&](auto K) { kf_initiate_kernel<decltype(K)::value><<<(n + KF_TPB - 1) / KF_TPB, KF_TPB, 0, (cudaStream_t)st>>>(n, z, mean, cov); });
+    if (rc) return rc;
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_kf_predict(int32_t kind, int32_t n, double* mean, double* cov, void* st) {
+    if (n < 0 || !mean || !cov) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n == 0) return 0;
+    int rc = dispatch_kind(kind, [&](auto K) { kf_predict_kernel<decltype(K)::value><<<(n + KF_TPB - 1) / KF_TPB, KF_TPB, 0, (cudaStream_t)st>>>(n, mean, cov); });
+    if (rc) return rc;
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_kf_project(int32_t kind, int32_t n, const double* mean, const double* cov, const double* conf,
+                                    double* pmean, double* pcov, void* st) {
+    if (n < 0 || !mean || !cov || !pmean || !pcov) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n == 0) return 0;
+    int rc = dispatch_kind(kind, [&](auto K) { kf_project_kernel<decltype(K)::value><<<(n + KF_TPB - 1) / KF_TPB, KF_TPB, 0, (cudaStream_t)st>>>(n, mean, cov, conf, pmean, pcov); });
+    if (rc) return rc;
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_kf_update(int32_t kind, int32_t n, double* mean, double* cov, const double* z, const double* conf, void* st) {
+    if (n < 0 || !mean || !cov || !z) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n == 0) return 0;
+    int rc = dispatch_kind(kind, [&](auto K) { kf_update_kernel<decltype(K)::value><<<(n + KF_TPB - 1) / KF_TPB, KF_TPB, 0, (cudaStream_t)st>>>(n, mean, cov, z, conf); });
+    if (rc) return rc;
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_kf_gating_distance(int32_t kind, int32_t T, int32_t D, const double* mean, const double* cov,
+                                            const double* meas, int32_t only_position, int32_t metric, const double* conf,
+                                            double* out, void* st) {
+    if (T < 0 || D < 0 || !mean || !cov || !meas || !out) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (metric != 0 && metric != 1) { set_error("invalid distance metric"); return B200TRACK_ERR_ARG; }
+    if (T == 0 || D == 0) return 0;
+    int rc = dispatch_kind(kind, [&](auto K) { kf_gating_kernel<decltype(K)::value><<<(T + GD_TRACKS - 1) / GD_TRACKS, 256, 0, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out); });
+    if (rc) return rc;
+    LAUNCH_CHECK();
+    return 0;
+}
+static int launch_sim(int sim, int n, int m, const double* a, const double* b, double W, double H, const double* score,
+                      int as_distance, double* out, void* st) {
+    if (n < 0 || m < 0 || !a || !b || !out) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (sim < 0 || sim > B200TRACK_SIM_CENTROID) { set_error("Invalid function specified"); return B200TRACK_ERR_ARG; }
+    if (n == 0 || m == 0) return 0;
+    const size_t total = (size_t)n * m;
+    const int blocks = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    box_similarity_kernel<<<blocks, 256, 0, (cudaStream_t)st>>>(sim, n, m, a, b, W, H, score, as_distance, out);
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_box_similarity(int32_t sim, int32_t n, int32_t m, const double* a, const double* b, double W, double H,
+                                        double* out, void* st) {
+    return launch_sim(sim, n, m, a, b, W, H, nullptr, 0, out, st);
+}
+extern "C" int b200track_iou_distance(int32_t n, int32_t m, const double* a, const double* b, const double* score, double* out, void* st) {
+    return launch_sim(B200TRACK_SIM_IOU, n, m, a, b, 0, 0, score, 1, out, st);
+}
+extern "C" int b200track_embedding_distance(int32_t n, int32_t m, int32_t dim, const float* a, const float* b, double* out, void* st) {
+    if (n < 0 || m < 0 || dim <= 0 || !a || !b || !out) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n == 0 || m == 0) return 0;
+    dim3 grid((m + ED_TILE - 1) / ED_TILE, (n + ED_TILE - 1) / ED_TILE);
+    embedding_distance_kernel<<<grid, ED_TILE * ED_TILE, 0, (cudaStream_t)st>>>(n, m, dim, a, b, out);
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_lapjv(int32_t batch, int32_t rows, int32_t cols, const double* cost, double limit, int32_t* x, int32_t* y, void* st) {
+    if (batch < 0 || rows < 0 || cols < 0 || !x || !y || (!cost && rows * cols > 0)) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (rows > 4096 || cols > 4096) { set_error("lapjv: at most 4096 rows / cols"); return B200TRACK_ERR_CAPACITY; }
+    if (batch == 0) return 0;
+    if (rows == 0 || cols == 0) {
+        if (rows) B200_CU_TRY(cudaMemsetAsync(x, 0xff, sizeof(int32_t) * (size_t)batch * rows, (cudaStream_t)st));
+        if (cols) B200_CU_TRY(cudaMemsetAsync(y, 0xff, sizeof(int32_t) * (size_t)batch * cols, (cudaStream_t)st));
+        return 0;
+    }
+    if (limit < __builtin_inf()) {
+        const int Rpad = (rows + 31) & ~31, Cpad = (cols + 31) & ~31;
+        size_t smem = 8 * (size_t)Rpad + 16 * (size_t)Cpad + 4 * (size_t)(Cpad / 32) * Rpad + 4 * (size_t)(Rpad + Cpad) + 4 * (size_t)Rpad +
+                      4 * (size_t)Rpad + 10 * (size_t)Cpad + 16 * 16;
+        if (smem > 227 * 1024) { set_error("lapjv: problem too large for shared memory"); return B200TRACK_ERR_CAPACITY; }
+        B200_CU_TRY(cudaFuncSetAttribute(lapjv_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lapjv_sparse_kernel<<<batch, 256, smem, (cudaStream_t)st>>>(rows, cols, Rpad, Cpad, cost, limit, x, y);
+    } else {
+        size_t smem = 8 * (size_t)rows + 16 * (size_t)cols + 8 * 32 + 4 * 32 + 4 * (size_t)rows + 8 * (size_t)cols + cols + 16 * 12;
+        if (smem > 227 * 1024) { set_error("lapjv: problem too large for shared memory"); return B200TRACK_ERR_CAPACITY; }
+        B200_CU_TRY(cudaFuncSetAttribute(lapjv_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        lapjv_dense_kernel<<<batch, 256, smem, (cudaStream_t)st>>>(rows, cols, cost, x, y);
+    }
+    LAUNCH_CHECK();
+    return 0;
+}

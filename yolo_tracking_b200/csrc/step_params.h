@@ -1,0 +1,38 @@
+// Kernel-side parameter block of one batched frame step (filled by api.cu from b200track_config).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace b200 {
+
+struct StepParams {
+    int n_streams, max_tracks, max_dets, feat_dim;
+    // ByteTrack / BoTSORT thresholds (bytetrack.yaml / botsort.yaml keys)
+    double track_thresh;      // track_thresh | track_high_thresh
+    double low_thresh;        // 0.1          | track_low_thresh
+    double new_thresh;        // det_thresh (= track_thresh) | new_track_thresh
+    double match_thresh;      // first association cost limit
+    double second_thresh;     // 0.5
+    double unconf_thresh;     // 0.7
+    double dup_thresh;        // 0.15
+    double proximity_thresh, appearance_thresh;   // BoTSORT
+    int max_time_lost;
+    // device state (layout.h)
+    double* state_f;
+    int* state_i;
+    int* counts;
+    unsigned long long* track_updates;
+    int* err;
+    // per-step inputs / outputs (device)
+    const double* dets;       // [S, max_dets, 6]
+    const int* ndets;         // [S]
+    const float* feats;       // [S, max_dets, feat_dim] or null
+    double* out;              // [S, max_tracks, 8]
+    int* nout;                // [S]
+};
+
+size_t bytetrack_step_smem(int Tmax, int Dmax);
+cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, cudaStream_t stream);
+
+}  // namespace b200
