@@ -1,9 +1,9 @@
 """Synthetic MOT-shaped detection streams.
 
 Every stream is generated from its own ``numpy.random.default_rng(1000 * config + stream)``
-so the oracle, the golden fixtures, the GPU parity tests and ``bench.py`` all see the same
-arrays.  All values are continuous draws (no rounding) so the inputs are tie-free: no two
-association costs coincide and no confidence sits exactly on a threshold.
+so the oracle, the GPU parity tests and ``bench.py`` all see the same arrays.  All values are
+continuous draws (no rounding) so the inputs are tie-free: no two association costs coincide
+and no confidence sits exactly on a threshold.
 
 Scene model: ``n_objects`` constant-velocity boxes on a 1920x1080 canvas (3840x2160 above 64
 objects); a detection is the true box plus N(0, 1 px) noise per coordinate; each object is
@@ -62,54 +62,56 @@ def make_stream(config: int, stream: int, n_objects: int, n_frames: int, *,
     fw = rng.uniform(30.0, 90.0, (F, max_fp))
     fh = rng.uniform(60.0, 220.0, (F, max_fp))
     fconf = rng.uniform(0.1, 0.6, (F, max_fp))
-    shuffle_keys = rng.random((F, N + max_fp))
-    proto = emb = None
-    if emb_dim:
-        proto = rng.standard_normal((N, emb_dim))
-        fp_proto = rng.standard_normal((F, max_fp, emb_dim))
-        emb_noise_seed = rng.integers(0, 2**31 - 1)
+    keys = rng.random((F, N + max_fp))
 
-    counts = seen.sum(1) + n_fp
-    cap = int(dmax) if dmax is not None else int(counts.max()) if F else 0
+    # all candidate rows [F, N + max_fp, 6]; invalid ones are sorted to the back
+    cand = np.zeros((F, N + max_fp, 6))
+    cand[:, :N, :4] = boxes
+    cand[:, :N, 4] = conf
+    cand[:, N:, 0] = fcx - fw / 2
+    cand[:, N:, 1] = fcy - fh / 2
+    cand[:, N:, 2] = fcx + fw / 2
+    cand[:, N:, 3] = fcy + fh / 2
+    cand[:, N:, 4] = fconf
+    valid = np.concatenate([seen, np.arange(max_fp)[None, :] < n_fp[:, None]], axis=1)
+    order = np.argsort(np.where(valid, keys, 2.0), axis=1, kind="stable")
+    cand = np.take_along_axis(cand, order[:, :, None], axis=1)
+    counts = valid.sum(1)
+    cand *= (np.arange(N + max_fp)[None, :] < counts[:, None])[:, :, None]
+
+    cap = int(dmax) if dmax is not None else (int(counts.max()) if F else 0)
     if F and counts.max() > cap:
         raise ValueError(f"stream {stream}: {int(counts.max())} detections exceed dmax={cap}")
     dets = np.zeros((F, cap, 6), dtype=np.float64)
+    k = min(cap, N + max_fp)
+    dets[:, :k] = cand[:, :k]
     ndets = counts.astype(np.int32)
-    embs = np.zeros((F, cap, emb_dim), dtype=np.float32) if emb_dim else None
+    embs = None
     if emb_dim:
-        erng = np.random.default_rng(int(emb_noise_seed))
-    for f in range(F):
-        idx = np.nonzero(seen[f])[0]
-        k = int(n_fp[f])
-        rows = np.empty((len(idx) + k, 6))
-        rows[:len(idx), :4] = boxes[f, idx]
-        rows[:len(idx), 4] = conf[f, idx]
-        rows[len(idx):, 0] = fcx[f, :k] - fw[f, :k] / 2
-        rows[len(idx):, 1] = fcy[f, :k] - fh[f, :k] / 2
-        rows[len(idx):, 2] = fcx[f, :k] + fw[f, :k] / 2
-        rows[len(idx):, 3] = fcy[f, :k] + fh[f, :k] / 2
-        rows[len(idx):, 4] = fconf[f, :k]
-        rows[:, 5] = 0.0
-        keys = np.concatenate([shuffle_keys[f, idx], shuffle_keys[f, N:N + k]])
-        order = np.argsort(keys, kind="stable")
-        dets[f, :len(rows)] = rows[order]
-        if emb_dim:
-            e = np.concatenate([proto[idx], fp_proto[f, :k]], axis=0)
-            e = e + 0.3 * erng.standard_normal(e.shape)
-            embs[f, :len(rows)] = e[order].astype(np.float32)
+        proto = rng.standard_normal((N, emb_dim))
+        e = np.empty((F, N + max_fp, emb_dim), dtype=np.float32)
+        for f in range(F):                      # frame at a time: bounds the fp64 temporaries
+            src = np.concatenate([proto, rng.standard_normal((max_fp, emb_dim))], axis=0)
+            ef = src + 0.3 * rng.standard_normal(src.shape)
+            e[f] = ef[order[f]].astype(np.float32)
+        e *= (np.arange(N + max_fp)[None, :] < counts[:, None])[:, :, None]
+        embs = np.zeros((F, cap, emb_dim), dtype=np.float32)
+        embs[:, :k] = e[:, :k]
     return dets, ndets, embs
 
 
 def make_batch(config: int, n_streams: int, n_objects: int, n_frames: int, *, dmax: int,
                first_stream: int = 0, **kw):
     """Stack ``n_streams`` streams: ``dets[F, S, dmax, 6]``, ``ndets[F, S]``, ``embs`` or None."""
-    D, Nd, E = [], [], []
-    for s in range(first_stream, first_stream + n_streams):
-        d, n, e = make_stream(config, s, n_objects, n_frames, dmax=dmax, **kw)
-        D.append(d)
-        Nd.append(n)
-        E.append(e)
-    dets = np.ascontiguousarray(np.stack(D, axis=1))
-    ndets = np.ascontiguousarray(np.stack(Nd, axis=1))
-    embs = np.ascontiguousarray(np.stack(E, axis=1)) if E and E[0] is not None else None
+    dets = np.zeros((n_frames, n_streams, dmax, 6), dtype=np.float64)
+    ndets = np.zeros((n_frames, n_streams), dtype=np.int32)
+    embs = None
+    for i in range(n_streams):
+        d, n, e = make_stream(config, first_stream + i, n_objects, n_frames, dmax=dmax, **kw)
+        dets[:, i] = d
+        ndets[:, i] = n
+        if e is not None:
+            if embs is None:
+                embs = np.zeros((n_frames, n_streams, dmax, e.shape[-1]), dtype=np.float32)
+            embs[:, i] = e
     return dets, ndets, embs
