@@ -10,25 +10,24 @@ struct Box { double x1, y1, x2, y2; };
 // xyxy2xywh (ops.py:17-20)
 __device__ __forceinline__ void xyxy_to_xywh(double x1, double y1, double x2, double y2,
                                              double& xc, double& yc, double& w, double& h) {
-    xc = xdiv(xadd(x1, x2), 2.0);
-    yc = xdiv(xadd(y1, y2), 2.0);
+    xc = xmul(xadd(x1, x2), 0.5);
+    yc = xmul(xadd(y1, y2), 0.5);
     w = xsub(x2, x1);
     h = xsub(y2, y1);
 }
 // xywh2xyxy (ops.py:36-39)
 __device__ __forceinline__ Box xywh_to_xyxy(double xc, double yc, double w, double h) {
     Box b;
-    const double hw = xdiv(w, 2.0), hh = xdiv(h, 2.0);
+    const double hw = xmul(w, 0.5), hh = xmul(h, 0.5);   // x / 2 == x * 0.5 exactly
     b.x1 = xsub(xc, hw); b.y1 = xsub(yc, hh);
     b.x2 = xadd(xc, hw); b.y2 = xadd(yc, hh);
     return b;
 }
 // xywh2tlwh then tlwh2xyah (ops.py:54-57, :93-96): the measurement an STrack feeds the XYAH filter
 __device__ __forceinline__ void xywh_to_xyah(double xc, double yc, double w, double h, double* z) {
-    const double tl_x = xsub(xc, xdiv(w, 2.0));
-    const double tl_y = xsub(yc, xdiv(h, 2.0));
-    z[0] = xadd(tl_x, xdiv(w, 2.0));
-    z[1] = xadd(tl_y, xdiv(h, 2.0));
+    const double hw = xmul(w, 0.5), hh = xmul(h, 0.5);
+    z[0] = xadd(xsub(xc, hw), hw);
+    z[1] = xadd(xsub(yc, hh), hh);
     z[2] = xdiv(w, h);
     z[3] = h;
 }
@@ -61,11 +60,11 @@ __device__ __forceinline__ double box_giou(const Box& a, const Box& b) {
     const double eh = xsub(fmax(a.y2, b.y2), fmin(a.y1, b.y1));
     const double enc = xmul(ew, eh);
     const double g = xsub(v, xdiv(xsub(enc, inter), enc));
-    return xdiv(xadd(g, 1.0), 2.0);
+    return xmul(xadd(g, 1.0), 0.5);
 }
 __device__ __forceinline__ void centre_terms(const Box& a, const Box& b, double& inner, double& outer) {
-    const double cxa = xdiv(xadd(a.x1, a.x2), 2.0), cya = xdiv(xadd(a.y1, a.y2), 2.0);
-    const double cxb = xdiv(xadd(b.x1, b.x2), 2.0), cyb = xdiv(xadd(b.y1, b.y2), 2.0);
+    const double cxa = xmul(xadd(a.x1, a.x2), 0.5), cya = xmul(xadd(a.y1, a.y2), 0.5);
+    const double cxb = xmul(xadd(b.x1, b.x2), 0.5), cyb = xmul(xadd(b.y1, b.y2), 0.5);
     const double dx = xsub(cxa, cxb), dy = xsub(cya, cyb);
     inner = xadd(xmul(dx, dx), xmul(dy, dy));
     const double ex = xsub(fmax(a.x2, b.x2), fmin(a.x1, b.x1));
@@ -77,7 +76,7 @@ __device__ __forceinline__ double box_diou(const Box& a, const Box& b) {
     const double v = box_iou(a, b);
     double inner, outer;
     centre_terms(a, b, inner, outer);
-    return xdiv(xadd(xsub(v, xdiv(inner, outer)), 1.0), 2.0);
+    return xmul(xadd(xsub(v, xdiv(inner, outer)), 1.0), 0.5);
 }
 // ciou_batch (iou.py:108-161); atan is CUDA's (<= 1-2 ulp from glibc's - only matters at ties)
 __device__ __forceinline__ double box_ciou(const Box& a, const Box& b) {
@@ -92,12 +91,12 @@ __device__ __forceinline__ double box_ciou(const Box& a, const Box& b) {
     const double S = xsub(1.0, v);
     const double alpha = xdiv(vv, xadd(S, vv));
     const double c = xsub(xsub(v, xdiv(inner, outer)), xmul(alpha, vv));
-    return xdiv(xadd(c, 1.0), 2.0);
+    return xmul(xadd(c, 1.0), 0.5);
 }
 // centroid_batch (iou.py:164-188)
 __device__ __forceinline__ double box_centroid(const Box& a, const Box& b, double w, double h) {
-    const double cxa = xdiv(xadd(a.x1, a.x2), 2.0), cya = xdiv(xadd(a.y1, a.y2), 2.0);
-    const double cxb = xdiv(xadd(b.x1, b.x2), 2.0), cyb = xdiv(xadd(b.y1, b.y2), 2.0);
+    const double cxa = xmul(xadd(a.x1, a.x2), 0.5), cya = xmul(xadd(a.y1, a.y2), 0.5);
+    const double cxb = xmul(xadd(b.x1, b.x2), 0.5), cyb = xmul(xadd(b.y1, b.y2), 0.5);
     const double dx = xsub(cxa, cxb), dy = xsub(cya, cyb);
     const double dist = sqrt(xadd(xmul(dx, dx), xmul(dy, dy)));
     const double norm = sqrt(xadd(xmul(w, w), xmul(h, h)));

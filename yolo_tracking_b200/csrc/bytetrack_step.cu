@@ -2,7 +2,10 @@
 // stream.  The CTA reads the stream's detections and its whole track state from HBM once,
 // keeps everything (Kalman state, boxes, candidate graph, assignment duals) in shared memory
 // for the entire step, and writes the state back once, already in the reference's new list
-// order, together with the output rows.  Nothing T x D ever touches HBM.
+// order, together with the output rows.  Nothing T x D ever touches HBM - or is even computed:
+// candidates come from per-frame cell masks (64 x-cells and 64 y-cells, each a bitmask of the
+// detections whose box touches the cell), so a track only runs the exact IoU test against the
+// handful of detections that share a cell range with it in both axes.
 //
 // Replaces BYTETracker.update (boxmot/trackers/bytetrack/byte_tracker.py:132-281) and what it
 // calls: STrack.multi_predict :35-48 -> KalmanFilter.multi_predict (bytetrack_kf.py:155-192),
@@ -27,13 +30,19 @@ constexpr int DF_HIGH = 1, DF_LOW = 2, DF_USED = 4;
 
 constexpr int CAT_NONE = 0, CAT_KEEP = 1, CAT_REFOUND = 2, CAT_LOST_OLD = 3, CAT_LOST_NEW = 4;
 
+constexpr int NCELL = 64;         // cells per axis of the candidate masks
+
+// row types of one association pass: which detection set / limit / cost a row uses
+constexpr int RT_NONE = 0, RT_A = 1, RT_B = 2;
+
 struct Sm {
     double *tf, *tbox, *dxywh, *dbox, *dconf, *dcls, *u, *v, *dist;
     unsigned long long* scratch;
-    int *ti, *parent, *head;
-    uint32_t *adj, *colbits;
+    int *ti, *parent, *head, *coldeg, *ncomplex;
+    uint32_t *adj, *colbitsA, *colbitsB, *xmask, *ymask;
+    float* fext;
     short *rnext, *xr, *yc, *pred, *nextc, *mark, *scn, *lostlist;
-    unsigned char *role, *rowsel, *dflag, *cat, *drop;
+    unsigned char *role, *rowtype, *dflag, *cat, *drop;
 };
 
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
@@ -42,41 +51,42 @@ __host__ __device__ inline size_t carve(Sm* sm, unsigned char* base, int Tmax, i
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off = align16(off + bytes); return base ? base + o : (unsigned char*)nullptr; };
     const int DW = Dmax / 32;
-    double* tf = (double*)take(sizeof(double) * B200_NF * Tmax);
-    double* tbox = (double*)take(sizeof(double) * 4 * Tmax);
-    double* dxywh = (double*)take(sizeof(double) * 4 * Dmax);
-    double* dbox = (double*)take(sizeof(double) * 4 * Dmax);
-    double* dconf = (double*)take(sizeof(double) * Dmax);
-    double* dcls = (double*)take(sizeof(double) * Dmax);
-    double* u = (double*)take(sizeof(double) * Tmax);
-    double* v = (double*)take(sizeof(double) * Dmax);
-    double* dist = (double*)take(sizeof(double) * Dmax);
-    unsigned long long* scratch = (unsigned long long*)take(sizeof(unsigned long long) * 40);
-    int* ti = (int*)take(sizeof(int) * B200_NI * Tmax);
-    int* parent = (int*)take(sizeof(int) * (Tmax + Dmax));
-    int* head = (int*)take(sizeof(int) * Tmax);
-    uint32_t* adj = (uint32_t*)take(sizeof(uint32_t) * DW * Tmax);
-    uint32_t* colbits = (uint32_t*)take(sizeof(uint32_t) * DW);
-    short* rnext = (short*)take(sizeof(short) * Tmax);
-    short* xr = (short*)take(sizeof(short) * Tmax);
-    short* yc = (short*)take(sizeof(short) * Dmax);
-    short* pred = (short*)take(sizeof(short) * Dmax);
-    short* nextc = (short*)take(sizeof(short) * Dmax);
-    short* mark = (short*)take(sizeof(short) * Dmax);
-    short* scn = (short*)take(sizeof(short) * Dmax);
-    short* lostlist = (short*)take(sizeof(short) * Tmax);
-    unsigned char* role = take(Tmax);
-    unsigned char* rowsel = take(Tmax);
-    unsigned char* dflag = take(Dmax);
-    unsigned char* cat = take(Tmax);
-    unsigned char* drop = take(Tmax + Dmax);
-    if (sm) {
-        sm->tf = tf; sm->tbox = tbox; sm->dxywh = dxywh; sm->dbox = dbox; sm->dconf = dconf; sm->dcls = dcls;
-        sm->u = u; sm->v = v; sm->dist = dist; sm->scratch = scratch; sm->ti = ti; sm->parent = parent;
-        sm->head = head; sm->adj = adj; sm->colbits = colbits; sm->rnext = rnext; sm->xr = xr; sm->yc = yc;
-        sm->pred = pred; sm->nextc = nextc; sm->mark = mark; sm->scn = scn; sm->lostlist = lostlist;
-        sm->role = role; sm->rowsel = rowsel; sm->dflag = dflag; sm->cat = cat; sm->drop = drop;
-    }
+    Sm s;
+    s.tf = (double*)take(sizeof(double) * B200_NF * Tmax);
+    s.tbox = (double*)take(sizeof(double) * 4 * Tmax);
+    s.dxywh = (double*)take(sizeof(double) * 4 * Dmax);
+    s.dbox = (double*)take(sizeof(double) * 4 * Dmax);
+    s.dconf = (double*)take(sizeof(double) * Dmax);
+    s.dcls = (double*)take(sizeof(double) * Dmax);
+    s.u = (double*)take(sizeof(double) * Tmax);
+    s.v = (double*)take(sizeof(double) * Dmax);
+    s.dist = (double*)take(sizeof(double) * Dmax);
+    s.scratch = (unsigned long long*)take(sizeof(unsigned long long) * 40);
+    s.ti = (int*)take(sizeof(int) * B200_NI * Tmax);
+    s.parent = (int*)take(sizeof(int) * (Tmax + Dmax));
+    s.head = (int*)take(sizeof(int) * Tmax);
+    s.coldeg = (int*)take(sizeof(int) * Dmax);
+    s.ncomplex = (int*)take(sizeof(int) * 4);
+    s.adj = (uint32_t*)take(sizeof(uint32_t) * DW * Tmax);
+    s.colbitsA = (uint32_t*)take(sizeof(uint32_t) * DW);
+    s.colbitsB = (uint32_t*)take(sizeof(uint32_t) * DW);
+    s.xmask = (uint32_t*)take(sizeof(uint32_t) * NCELL * DW);
+    s.ymask = (uint32_t*)take(sizeof(uint32_t) * NCELL * DW);
+    s.fext = (float*)take(sizeof(float) * 32 * 4);
+    s.rnext = (short*)take(sizeof(short) * Tmax);
+    s.xr = (short*)take(sizeof(short) * Tmax);
+    s.yc = (short*)take(sizeof(short) * Dmax);
+    s.pred = (short*)take(sizeof(short) * Dmax);
+    s.nextc = (short*)take(sizeof(short) * Dmax);
+    s.mark = (short*)take(sizeof(short) * Dmax);
+    s.scn = (short*)take(sizeof(short) * Dmax);
+    s.lostlist = (short*)take(sizeof(short) * Tmax);
+    s.role = take(Tmax);
+    s.rowtype = take(Tmax);
+    s.dflag = take(Dmax);
+    s.cat = take(Tmax);
+    s.drop = take(Tmax + Dmax);
+    if (sm) *sm = s;
     return off;
 }
 
@@ -126,49 +136,78 @@ __device__ __forceinline__ void det_measurement(const Sm& sm, int Dmax, int j, d
     else xywh_to_xyah(xc, yc, w, h, z);
 }
 
-struct IouCost {
+// cost of (track row, detection): iou_distance, optionally fuse_score, chosen by the row type
+struct PassCost {
     const double *tbox, *dbox, *dconf;
+    const unsigned char* rowtype;
     int Tmax, Dmax;
-    bool fuse;
-    __device__ __forceinline__ double operator()(int t, int j) const {
-        const Box a = load_box(tbox, Tmax, t), b = load_box(dbox, Dmax, j);
+    bool fuseA, fuseB;
+    __device__ __forceinline__ double eval(const Box& a, int j, bool fuse) const {
+        const Box b = load_box(dbox, Dmax, j);
         const double v = box_iou(a, b);
         return fuse ? fused_cost(v, dconf[j]) : xsub(1.0, v);
     }
+    __device__ __forceinline__ double operator()(int t, int j) const {
+        return eval(load_box(tbox, Tmax, t), j, rowtype[t] == RT_A ? fuseA : fuseB);
+    }
+};
+struct PassLimit {
+    const unsigned char* rowtype;
+    double limA, limB;
+    __device__ __forceinline__ double operator()(int t) const { return rowtype[t] == RT_A ? limA : limB; }
 };
 
-template <int NT>
-__device__ void build_colbits(const Sm& sm, int nd, int words, int want, int forbid) {
-    for (int j = threadIdx.x; j < words * 32; j += NT) {
-        const bool ok = j < nd && (sm.dflag[j] & want) && !(sm.dflag[j] & forbid);
-        const uint32_t m = __ballot_sync(0xffffffffu, ok);
-        if ((threadIdx.x & 31) == 0) sm.colbits[j >> 5] = m;
+struct CellMap {
+    float x0, y0, sx, sy;
+    __device__ __forceinline__ int cx(double x) const {
+        return min(max((int)(((float)x - x0) * sx), 0), NCELL - 1);      // monotone in x
     }
-    __syncthreads();
-}
+    __device__ __forceinline__ int cy(double y) const {
+        return min(max((int)(((float)y - y0) * sy), 0), NCELL - 1);
+    }
+};
 
-// candidate graph: edge (t, j) iff the boxes overlap and cost <= limit (exact pruning, see
-// lap_sparse.cuh).  No overlap => iou == 0 => cost == 1 > limit, so the cheap overlap test
-// rejects almost every pair before any division.
-template <int NT, class Cost>
-__device__ void build_adjacency(const Sm& sm, int Tmax, int Dmax, int n, int words, double limit, const Cost& cost) {
-    for (int task = threadIdx.x; task < n * words; task += NT) {
-        const int wd = task / n, t = task - wd * n;
-        uint32_t bits = sm.rowsel[t] ? sm.colbits[wd] : 0u;
-        uint32_t res = 0u;
-        if (bits) {
-            const Box a = load_box(sm.tbox, Tmax, t);
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int j = wd * 32 + b;
-                const Box d = load_box(sm.dbox, Dmax, j);
-                if (box_overlap(a, d)) {
-                    if (cost(t, j) <= limit) res |= 1u << b;
+// Candidate graph of one association pass.  Row t (type rowtype[t]) is tested against the
+// detections of its column set that share a cell range with it in x AND in y (a superset of
+// the overlapping ones because the cell maps are monotone); edge iff the boxes overlap and
+// cost <= limit - exact pruning, see lap_sparse.cuh (no overlap => iou = 0 => cost = 1 > limit).
+template <int NT>
+__device__ void build_graph(const Sm& sm, const LapWork& lw, int Tmax, int Dmax, int n, int words, const CellMap& cm,
+                            const PassCost& cost, const PassLimit& lim) {
+    const int DW = Dmax / 32;
+    for (int t = threadIdx.x; t < n; t += NT) {
+        const int rt = sm.rowtype[t];
+        if (rt == RT_NONE) {
+            for (int wd = 0; wd < words; ++wd) sm.adj[wd * Tmax + t] = 0u;
+            continue;
+        }
+        const Box a = load_box(sm.tbox, Tmax, t);
+        const int cx0 = cm.cx(a.x1), cx1 = cm.cx(a.x2), cy0 = cm.cy(a.y1), cy1 = cm.cy(a.y2);
+        const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
+        const bool fuse = rt == RT_A ? cost.fuseA : cost.fuseB;
+        const double limit = rt == RT_A ? lim.limA : lim.limB;
+        for (int wd = 0; wd < words; ++wd) {
+            uint32_t res = 0u;
+            const uint32_t cb = colbits[wd];
+            if (cb) {
+                uint32_t mx = 0u, my = 0u;
+                for (int c = cx0; c <= cx1; ++c) mx |= sm.xmask[c * DW + wd];
+                for (int c = cy0; c <= cy1; ++c) my |= sm.ymask[c * DW + wd];
+                uint32_t cand = mx & my & cb;
+                while (cand) {
+                    const int b = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const int j = wd * 32 + b;
+                    const Box d = load_box(sm.dbox, Dmax, j);
+                    if (box_overlap(a, d)) {
+                        const double v = box_iou(a, d);
+                        const double c = fuse ? fused_cost(v, sm.dconf[j]) : xsub(1.0, v);
+                        if (c <= limit) { res |= 1u << b; atomicAdd(&lw.coldeg[j], 1); }
+                    }
                 }
             }
+            sm.adj[wd * Tmax + t] = res;
         }
-        sm.adj[wd * Tmax + t] = res;
     }
     __syncthreads();
 }
@@ -177,7 +216,7 @@ __device__ void build_adjacency(const Sm& sm, int Tmax, int Dmax, int n, int wor
 template <int NT, int KIND>
 __device__ void apply_matches(const Sm& sm, int Tmax, int Dmax, int n, int frame) {
     for (int t = threadIdx.x; t < n; t += NT) {
-        if (!sm.rowsel[t]) continue;
+        if (sm.rowtype[t] == RT_NONE) continue;
         const int j = sm.xr[t];
         if (j < 0) continue;
         KfState s;
@@ -198,15 +237,14 @@ __device__ void apply_matches(const Sm& sm, int Tmax, int Dmax, int n, int frame
         sm.tf[B200_TF_CLS * Tmax + t] = sm.dcls[j];
         sm.dflag[j] |= DF_USED;
     }
-    __syncthreads();
 }
 
 template <int NT, int KIND>
 __global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int s = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int Tmax = p.max_tracks, Dmax = p.max_dets;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Tmax = p.max_tracks, Dmax = p.max_dets, DW = Dmax / 32;
     Sm sm;
     carve(&sm, smem_raw, Tmax, Dmax);
 
@@ -219,7 +257,7 @@ __global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) 
     if (nd < 0) nd = 0;
     const int words = (nd + 31) >> 5;
 
-    // ---- detections: [nd, 6] rows -> planar shared memory ------------------------------
+    // ---- HBM -> shared memory, once: detections [nd, 6] (planar) and the track state ----
     {
         const double* g = p.dets + (size_t)s * Dmax * 6;
         for (int i = tid; i < nd * 6; i += NT) {
@@ -229,9 +267,6 @@ __global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) 
             else if (c == 4) sm.dconf[j] = val;
             else sm.dcls[j] = val;
         }
-    }
-    // ---- track state: HBM -> shared memory, once ---------------------------------------
-    {
         const double* gf = p.state_f + (size_t)s * B200_NF * Tmax;
         const int* gi = p.state_i + (size_t)s * B200_NI * Tmax;
         for (int t = tid; t < n; t += NT) {
@@ -240,12 +275,16 @@ __global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) 
 #pragma unroll
             for (int c = 0; c < B200_NI; ++c) sm.ti[c * Tmax + t] = gi[c * Tmax + t];
         }
+        for (int i = tid; i < NCELL * DW; i += NT) { sm.xmask[i] = 0u; sm.ymask[i] = 0u; }
+        for (int i = tid; i < Tmax + Dmax; i += NT) sm.drop[i] = 0;
     }
     __syncthreads();
 
-    // detection side: xyxy -> xywh, the round-trip box used by iou_distance, and the two
-    // confidence bands (byte_tracker.py:151-158; strict inequalities on both sides)
-    for (int j = tid; j < Dmax; j += NT) {
+    // ---- detection side: xyxy -> xywh, the round-trip box used by iou_distance, the two
+    // confidence bands (byte_tracker.py:151-158; strict inequalities), frame extents --------
+    const float FBIG = 3.0e38f;
+    float ex0 = FBIG, ey0 = FBIG, ex1 = -FBIG, ey1 = -FBIG;
+    for (int j = tid; j < words * 32; j += NT) {
         int fl = 0;
         if (j < nd) {
             double xc, yc, w, h;
@@ -256,10 +295,24 @@ __global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) 
             const double c = sm.dconf[j];
             if (c > p.track_thresh) fl = DF_HIGH;
             else if (c > p.low_thresh && c < p.track_thresh) fl = DF_LOW;
+            if (fl) {
+                ex0 = fminf(ex0, (float)b.x1); ey0 = fminf(ey0, (float)b.y1);
+                ex1 = fmaxf(ex1, (float)b.x2); ey1 = fmaxf(ey1, (float)b.y2);
+            }
         }
         sm.dflag[j] = (unsigned char)fl;
+        const uint32_t mh = __ballot_sync(0xffffffffu, fl == DF_HIGH);
+        if (lane == 0) sm.colbitsA[j >> 5] = mh;           // first association: all high detections
     }
-    // track side: roles, Kalman predict of the pool (unconfirmed tracks are NOT predicted), boxes
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        ex0 = fminf(ex0, __shfl_xor_sync(0xffffffffu, ex0, d)); ey0 = fminf(ey0, __shfl_xor_sync(0xffffffffu, ey0, d));
+        ex1 = fmaxf(ex1, __shfl_xor_sync(0xffffffffu, ex1, d)); ey1 = fmaxf(ey1, __shfl_xor_sync(0xffffffffu, ey1, d));
+    }
+    if (lane == 0) { sm.fext[warp * 4] = ex0; sm.fext[warp * 4 + 1] = ey0; sm.fext[warp * 4 + 2] = ex1; sm.fext[warp * 4 + 3] = ey1; }
+
+    // ---- track side: roles, Kalman predict of the pool (unconfirmed tracks are NOT
+    // predicted, byte_tracker.py:178-180), boxes ---------------------------------------------
     for (int t = tid; t < n; t += NT) {
         const int fl = sm.ti[B200_TI_FLAGS * Tmax + t];
         const int role = t >= nT ? ROLE_LOST : ((fl & B200_FLAG_ACTIVATED) ? ROLE_TRACKED : ROLE_UNCONF);
@@ -275,59 +328,85 @@ __global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) 
             store_kf(sm.tf, Tmax, t, k);
         }
         refresh_box<KIND>(sm, Tmax, t);
-        sm.rowsel[t] = role != ROLE_UNCONF;
+        sm.rowtype[t] = role != ROLE_UNCONF ? RT_A : RT_NONE;
         sm.cat[t] = CAT_NONE;
     }
-    for (int i = tid; i < Tmax + Dmax; i += NT) sm.drop[i] = 0;
-    __syncthreads();
 
     LapWork lw;
     lw.Tmax = Tmax; lw.Dmax = Dmax; lw.adj = sm.adj; lw.u = sm.u; lw.v = sm.v; lw.dist = sm.dist;
     lw.parent = sm.parent; lw.head = sm.head; lw.rnext = sm.rnext; lw.xr = sm.xr; lw.yc = sm.yc;
     lw.pred = sm.pred; lw.nextc = sm.nextc; lw.mark = sm.mark; lw.scn = sm.scn;
-    IouCost cost;
-    cost.tbox = sm.tbox; cost.dbox = sm.dbox; cost.dconf = sm.dconf; cost.Tmax = Tmax; cost.Dmax = Dmax;
+    lw.coldeg = sm.coldeg; lw.ncomplex = sm.ncomplex;
+    lap_prepare<NT>(lw, n, words);
+    __syncthreads();
+
+    // ---- cell masks over the banded detections ---------------------------------------------
+    CellMap cm;
+    {
+        float x0 = FBIG, y0 = FBIG, x1 = -FBIG, y1 = -FBIG;
+        for (int k = 0; k < NT / 32; ++k) {
+            x0 = fminf(x0, sm.fext[k * 4]); y0 = fminf(y0, sm.fext[k * 4 + 1]);
+            x1 = fmaxf(x1, sm.fext[k * 4 + 2]); y1 = fmaxf(y1, sm.fext[k * 4 + 3]);
+        }
+        cm.x0 = x0; cm.y0 = y0;
+        cm.sx = (x1 > x0) ? (float)NCELL / (x1 - x0) : 0.f;
+        cm.sy = (y1 > y0) ? (float)NCELL / (y1 - y0) : 0.f;
+    }
+    for (int j = tid; j < nd; j += NT) {
+        if (!sm.dflag[j]) continue;
+        const Box b = load_box(sm.dbox, Dmax, j);
+        const uint32_t bit = 1u << (j & 31);
+        const int wd = j >> 5;
+        const int cx0 = cm.cx(b.x1), cx1 = cm.cx(b.x2), cy0 = cm.cy(b.y1), cy1 = cm.cy(b.y2);
+        for (int c = cx0; c <= cx1; ++c) atomicOr(&sm.xmask[c * DW + wd], bit);
+        for (int c = cy0; c <= cy1; ++c) atomicOr(&sm.ymask[c * DW + wd], bit);
+    }
+    __syncthreads();
+
+    PassCost cost;
+    cost.tbox = sm.tbox; cost.dbox = sm.dbox; cost.dconf = sm.dconf; cost.rowtype = sm.rowtype; cost.Tmax = Tmax; cost.Dmax = Dmax;
+    PassLimit lim;
+    lim.rowtype = sm.rowtype;
 
     // ---- first association: pool x high detections, fused score, limit match_thresh ----
-    cost.fuse = true;
-    build_colbits<NT>(sm, nd, words, DF_HIGH, 0);
-    build_adjacency<NT>(sm, Tmax, Dmax, n, words, p.match_thresh, cost);
-    lap_sparse_solve<NT>(lw, n, words, p.match_thresh, cost);
+    cost.fuseA = true; cost.fuseB = true;
+    lim.limA = p.match_thresh; lim.limB = p.match_thresh;
+    build_graph<NT>(sm, lw, Tmax, Dmax, n, words, cm, cost, lim);
+    lap_sparse_solve<NT>(lw, n, words, lim, cost);
     apply_matches<NT, KIND>(sm, Tmax, Dmax, n, frame);
-
-    // ---- second association: still-Tracked leftovers x low detections, plain IoU, 0.5 ---
-    for (int t = tid; t < n; t += NT) {
-        const bool matched = sm.rowsel[t] && sm.xr[t] >= 0;
-        if (matched && sm.role[t] == ROLE_LOST) sm.cat[t] = CAT_REFOUND;
-        sm.rowsel[t] = sm.role[t] == ROLE_TRACKED && !matched;
-    }
-    __syncthreads();
-    cost.fuse = false;
-    build_colbits<NT>(sm, nd, words, DF_LOW, 0);
-    build_adjacency<NT>(sm, Tmax, Dmax, n, words, p.second_thresh, cost);
-    lap_sparse_solve<NT>(lw, n, words, p.second_thresh, cost);
-    apply_matches<NT, KIND>(sm, Tmax, Dmax, n, frame);
-    for (int t = tid; t < n; t += NT) {
-        if (sm.rowsel[t] && sm.xr[t] < 0) {             // mark_lost; frame_id stays = end_frame
-            const int fl = sm.ti[B200_TI_FLAGS * Tmax + t];
-            sm.ti[B200_TI_FLAGS * Tmax + t] = (fl & ~3) | B200_ST_LOST;
-        }
-        sm.rowsel[t] = sm.role[t] == ROLE_UNCONF;
-    }
     __syncthreads();
 
-    // ---- unconfirmed x remaining high detections, fused score, 0.7 ---------------------
-    cost.fuse = true;
-    build_colbits<NT>(sm, nd, words, DF_HIGH, DF_USED);
-    build_adjacency<NT>(sm, Tmax, Dmax, n, words, p.unconf_thresh, cost);
-    lap_sparse_solve<NT>(lw, n, words, p.unconf_thresh, cost);
+    // ---- second pass: two independent problems solved together (disjoint rows AND columns):
+    //   A: still-Tracked leftovers x low detections, plain IoU, limit 0.5   (byte_tracker.py:198-226)
+    //   B: unconfirmed x remaining high detections, fused score, limit 0.7  (byte_tracker.py:228-240)
+    for (int t = tid; t < n; t += NT) {
+        const bool matched = sm.rowtype[t] != RT_NONE && sm.xr[t] >= 0;
+        const int role = sm.role[t];
+        sm.rowtype[t] = (role == ROLE_TRACKED && !matched) ? RT_A : (role == ROLE_UNCONF ? RT_B : RT_NONE);
+    }
+    for (int j = tid; j < words * 32; j += NT) {
+        const int fl = j < nd ? sm.dflag[j] : 0;
+        const uint32_t ma = __ballot_sync(0xffffffffu, fl == DF_LOW);
+        const uint32_t mb = __ballot_sync(0xffffffffu, fl == DF_HIGH);      // high and not used
+        if (lane == 0) { sm.colbitsA[j >> 5] = ma; sm.colbitsB[j >> 5] = mb; }
+    }
+    __syncthreads();                 // xr of pass 1 fully consumed before lap_prepare resets it
+    lap_prepare<NT>(lw, n, words);
+    __syncthreads();
+    cost.fuseA = false; cost.fuseB = true;
+    lim.limA = p.second_thresh; lim.limB = p.unconf_thresh;
+    build_graph<NT>(sm, lw, Tmax, Dmax, n, words, cm, cost, lim);
+    lap_sparse_solve<NT>(lw, n, words, lim, cost);
     apply_matches<NT, KIND>(sm, Tmax, Dmax, n, frame);
+    __syncthreads();
 
-    // ---- lifecycle: removed / aged-out, list categories (byte_tracker.py:237-268) -------
+    // ---- lifecycle: lost / removed / aged-out, list categories (byte_tracker.py:222-268) ----
     for (int t = tid; t < n; t += NT) {
         int fl = sm.ti[B200_TI_FLAGS * Tmax + t];
         const int role = sm.role[t];
-        if (role == ROLE_UNCONF && sm.xr[t] < 0) fl = (fl & ~3) | B200_ST_REMOVED;
+        const bool unmatched_now = sm.rowtype[t] != RT_NONE && sm.xr[t] < 0;
+        if (role == ROLE_TRACKED && unmatched_now) fl = (fl & ~3) | B200_ST_LOST;       // mark_lost; frame_id stays = end_frame
+        if (role == ROLE_UNCONF && unmatched_now) fl = (fl & ~3) | B200_ST_REMOVED;     // mark_removed
         int st = fl & 3;
         const bool sticky_old = fl & B200_FLAG_STICKY;      // id already in removed_stracks
         int cat = CAT_NONE;
@@ -374,163 +453,155 @@ __global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) 
 
     // ---- remove_duplicate_stracks (byte_tracker.py:312-325): tracked' x lost', 1-iou < 0.15
     // tracked' = kept slots, new tracks (unmatched high detections), re-found slots
-    for (int e = tid; e < n + nd; e += NT) {
-        Box a;
-        int age;
-        if (e < n) {
-            const int cat = sm.cat[e];
-            if (cat != CAT_KEEP && cat != CAT_REFOUND) continue;
-            a = load_box(sm.tbox, Tmax, e);
-            age = sm.ti[B200_TI_FRAME * Tmax + e] - sm.ti[B200_TI_START * Tmax + e];
-        } else {
-            const int j = e - n;
-            if ((sm.dflag[j] & (DF_HIGH | DF_USED)) != DF_HIGH) continue;
-            if (sm.dconf[j] < p.new_thresh) continue;
-            double z[4];
-            det_measurement<KIND>(sm, Dmax, j, z);
-            a = mean_to_box<KIND>(z[0], z[1], z[2], z[3]);
-            age = 0;
-        }
-        bool dropme = false;
-        for (int k = 0; k < nLostList; ++k) {
-            const int q = sm.lostlist[k];
-            const Box b = load_box(sm.tbox, Tmax, q);
-            if (!box_overlap(a, b)) continue;
-            if (xsub(1.0, box_iou(a, b)) < p.dup_thresh) {
-                const int ageq = sm.ti[B200_TI_FRAME * Tmax + q] - sm.ti[B200_TI_START * Tmax + q];
-                if (age > ageq) sm.drop[q] = 1; else dropme = true;
+    if (nLostList > 0) {
+        for (int e = tid; e < n + nd; e += NT) {
+            Box a;
+            int age;
+            if (e < n) {
+                const int cat = sm.cat[e];
+                if (cat != CAT_KEEP && cat != CAT_REFOUND) continue;
+                a = load_box(sm.tbox, Tmax, e);
+                age = sm.ti[B200_TI_FRAME * Tmax + e] - sm.ti[B200_TI_START * Tmax + e];
+            } else {
+                const int j = e - n;
+                if ((sm.dflag[j] & (DF_HIGH | DF_USED)) != DF_HIGH) continue;
+                if (sm.dconf[j] < p.new_thresh) continue;
+                double z[4];
+                det_measurement<KIND>(sm, Dmax, j, z);
+                a = mean_to_box<KIND>(z[0], z[1], z[2], z[3]);
+                age = 0;
             }
+            bool dropme = false;
+            for (int k = 0; k < nLostList; ++k) {
+                const int q = sm.lostlist[k];
+                const Box b = load_box(sm.tbox, Tmax, q);
+                if (!box_overlap(a, b)) continue;
+                if (xsub(1.0, box_iou(a, b)) < p.dup_thresh) {
+                    const int ageq = sm.ti[B200_TI_FRAME * Tmax + q] - sm.ti[B200_TI_START * Tmax + q];
+                    if (age > ageq) sm.drop[q] = 1; else dropme = true;
+                }
+            }
+            if (dropme) sm.drop[e < n ? e : Tmax + (e - n)] = 1;
         }
-        if (dropme) sm.drop[e < n ? e : Tmax + (e - n)] = 1;
+        __syncthreads();
     }
-    __syncthreads();
 
-    // ---- destinations.  Packed counters (10 bits each):
-    //   slots: keep, keep&activated, refound, lostOld, lostNew ; dets: born, born&activated
-    int totKeep, totKeepAct, totRef, totLostOld, totLostNew, totBorn, totBornAct;
+    // ---- destinations.  One packed scan (10-bit fields):
+    //   slots: [0) keep, [10) refound, [20) lostOld, [30) lostNew ; dets: [40) born kept, [50) born (all)
+    // Every CAT_KEEP / CAT_REFOUND entry is activated, so output rows = keep ++ born (frame 1 only) ++ refound.
     const bool born_active = frame == 1;                 // STrack.activate: is_activated only on frame 1
     double* gf = p.state_f + (size_t)s * B200_NF * Tmax;
     int* gi = p.state_i + (size_t)s * B200_NI * Tmax;
     double* gout = p.out + (size_t)s * Tmax * 8;
+    const int m = max(n, nd);
+    auto elem_val = [&](int i) -> unsigned long long {
+        unsigned long long v = 0ull;
+        if (i < n && !sm.drop[i]) {
+            const int cat = sm.cat[i];
+            if (cat != CAT_NONE) v = 1ull << (10 * (cat - 1));
+        }
+        if (i < nd && (sm.dflag[i] & (DF_HIGH | DF_USED)) == DF_HIGH && !(sm.dconf[i] < p.new_thresh)) {
+            v |= 1ull << 50;                              // activate() ran: consumes an id even if dropped below
+            if (!sm.drop[Tmax + i]) v |= 1ull << 40;
+        }
+        return v;
+    };
+    // block totals first (segment bases depend on them): warp reduce + shared atomics
+    if (tid == 0) sm.scratch[36] = 0ull;
+    __syncthreads();
     {
-        // pass 1: totals
-        unsigned long long acc = 0;
-        const int m = max(n, nd);
-        // per-thread element values are recomputed in pass 2; keep them cheap
-        auto slot_val = [&](int t) -> unsigned long long {
-            if (t >= n || sm.drop[t]) return 0ull;
-            const int cat = sm.cat[t];
-            const unsigned long long act = (sm.ti[B200_TI_FLAGS * Tmax + t] & B200_FLAG_ACTIVATED) ? 1ull : 0ull;
-            if (cat == CAT_KEEP) return 1ull | (act << 10);
-            if (cat == CAT_REFOUND) return 1ull << 20;
-            if (cat == CAT_LOST_OLD) return 1ull << 30;
-            if (cat == CAT_LOST_NEW) return 1ull << 40;
-            return 0ull;
-        };
-        auto det_val = [&](int j) -> unsigned long long {
-            if (j >= nd || sm.drop[Tmax + j]) return 0ull;
-            if ((sm.dflag[j] & (DF_HIGH | DF_USED)) != DF_HIGH) return 0ull;
-            if (sm.dconf[j] < p.new_thresh) return 0ull;
-            return (1ull << 50);
-        };
-        // block totals first (the segment bases depend on them)
-        for (int c0 = 0; c0 < m; c0 += NT) {
-            unsigned long long tot;
-            block_exscan<NT>(slot_val(c0 + tid) + det_val(c0 + tid), sm.scratch, tot);
-            acc += tot;
-        }
-        totKeep = (int)(acc & 1023); totKeepAct = (int)((acc >> 10) & 1023); totRef = (int)((acc >> 20) & 1023);
-        totLostOld = (int)((acc >> 30) & 1023); totLostNew = (int)((acc >> 40) & 1023);
-        totBorn = (int)((acc >> 50) & 1023);
-        totBornAct = born_active ? totBorn : 0;
-        // the born tracks that were dropped as duplicates still consumed an id (activate ran
-        // before remove_duplicate_stracks), so ids are numbered over ALL born tracks below.
-        int newT = totKeep + totBorn + totRef;
-        int newL = totLostOld + totLostNew;
-        if (newT + newL > Tmax) err |= B200_ERR_TRACK_OVERFLOW;
+        unsigned long long acc = 0ull;
+        for (int i = tid; i < m; i += NT) acc += elem_val(i);
+#pragma unroll
+        for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+        if (lane == 0 && acc) atomicAdd(&sm.scratch[36], acc);
+    }
+    __syncthreads();
+    const unsigned long long totals = sm.scratch[36];
+    const int totKeep = (int)(totals & 1023), totRef = (int)((totals >> 10) & 1023);
+    const int totLostOld = (int)((totals >> 20) & 1023), totLostNew = (int)((totals >> 30) & 1023);
+    const int totBorn = (int)((totals >> 40) & 1023), totBornAll = (int)((totals >> 50) & 1023);
+    const int newT = totKeep + totBorn + totRef;
+    const int newL = totLostOld + totLostNew;
+    if (newT + newL > Tmax) err |= B200_ERR_TRACK_OVERFLOW;
+    const int rowsBorn = born_active ? totBorn : 0;
 
-        // pass 2: scatter
-        unsigned long long base = 0;
-        unsigned long long idbase = 0;
-        for (int c0 = 0; c0 < m; c0 += NT) {
-            const int i = c0 + tid;
-            const unsigned long long sv = slot_val(i), dv = det_val(i);
-            // id numbering counts every born track, dropped or not
-            unsigned long long bornraw = 0ull;
-            if (i < nd && (sm.dflag[i] & (DF_HIGH | DF_USED)) == DF_HIGH && !(sm.dconf[i] < p.new_thresh)) bornraw = 1ull;
-            unsigned long long tot, idtot;
-            const unsigned long long ex = block_exscan<NT>(sv + dv, sm.scratch, tot) + base;
-            const unsigned long long idex = block_exscan<NT>(bornraw, sm.scratch, idtot) + idbase;
-            base += tot; idbase += idtot;
-            if (sv) {
-                const int cat = sm.cat[i];
-                int dst, orow = -1;
-                if (cat == CAT_KEEP) { dst = (int)(ex & 1023); if (sv >> 10) orow = (int)((ex >> 10) & 1023); }
-                else if (cat == CAT_REFOUND) { dst = totKeep + totBorn + (int)((ex >> 20) & 1023); orow = totKeepAct + totBornAct + (int)((ex >> 20) & 1023); }
-                else if (cat == CAT_LOST_OLD) dst = newT + (int)((ex >> 30) & 1023);
-                else dst = newT + totLostOld + (int)((ex >> 40) & 1023);
-                if (dst < Tmax) {
+    unsigned long long base = 0;
+    for (int c0 = 0; c0 < m; c0 += NT) {
+        const int i = c0 + tid;
+        const unsigned long long val = elem_val(i);
+        unsigned long long tot;
+        const unsigned long long ex = block_exscan<NT>(val, sm.scratch, tot) + base;
+        base += tot;
+        const unsigned long long sv = val & ((1ull << 40) - 1);
+        if (sv) {
+            const int cat = sm.cat[i];
+            int dst, orow = -1;
+            if (cat == CAT_KEEP) { dst = (int)(ex & 1023); orow = dst; }
+            else if (cat == CAT_REFOUND) { const int k = (int)((ex >> 10) & 1023); dst = totKeep + totBorn + k; orow = totKeep + rowsBorn + k; }
+            else if (cat == CAT_LOST_OLD) dst = newT + (int)((ex >> 20) & 1023);
+            else dst = newT + totLostOld + (int)((ex >> 30) & 1023);
+            if (dst < Tmax) {
 #pragma unroll
-                    for (int c = 0; c < B200_NF; ++c) gf[c * Tmax + dst] = sm.tf[c * Tmax + i];
+                for (int c = 0; c < B200_NF; ++c) gf[c * Tmax + dst] = sm.tf[c * Tmax + i];
 #pragma unroll
-                    for (int c = 0; c < B200_NI; ++c) gi[c * Tmax + dst] = sm.ti[c * Tmax + i];
+                for (int c = 0; c < B200_NI; ++c) gi[c * Tmax + dst] = sm.ti[c * Tmax + i];
+            }
+            if (orow >= 0 && orow < Tmax) {
+                double* o = gout + (size_t)orow * 8;
+                o[0] = sm.tbox[i]; o[1] = sm.tbox[Tmax + i]; o[2] = sm.tbox[2 * Tmax + i]; o[3] = sm.tbox[3 * Tmax + i];
+                o[4] = (double)sm.ti[B200_TI_ID * Tmax + i];
+                o[5] = sm.tf[B200_TF_SCORE * Tmax + i];
+                o[6] = sm.tf[B200_TF_CLS * Tmax + i];
+                o[7] = (double)sm.ti[B200_TI_DET * Tmax + i];
+            }
+        }
+        if (val & (1ull << 40)) {                       // STrack.activate (byte_tracker.py:50-62)
+            const int j = i;
+            const int k = (int)((ex >> 40) & 1023);
+            const int dst = totKeep + k;
+            const int id = id0 + (int)((ex >> 50) & 1023) + 1;
+            double z[4];
+            det_measurement<KIND>(sm, Dmax, j, z);
+            KfState ks;
+            kf_initiate<KIND>(z, ks);
+            if (dst < Tmax) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) gf[(B200_TF_MEAN + c) * Tmax + dst] = ks.m[c];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    gf[(B200_TF_COV + 3 * a + 0) * Tmax + dst] = ks.pp[a];
+                    gf[(B200_TF_COV + 3 * a + 1) * Tmax + dst] = ks.pv[a];
+                    gf[(B200_TF_COV + 3 * a + 2) * Tmax + dst] = ks.vv[a];
                 }
-                if (orow >= 0 && orow < Tmax) {
+                gf[B200_TF_SCORE * Tmax + dst] = sm.dconf[j];
+                gf[B200_TF_CLS * Tmax + dst] = sm.dcls[j];
+                gi[B200_TI_ID * Tmax + dst] = id;
+                gi[B200_TI_FRAME * Tmax + dst] = frame;
+                gi[B200_TI_START * Tmax + dst] = frame;
+                gi[B200_TI_LEN * Tmax + dst] = 0;
+                gi[B200_TI_DET * Tmax + dst] = j;
+                gi[B200_TI_FLAGS * Tmax + dst] = B200_ST_TRACKED | (born_active ? B200_FLAG_ACTIVATED : 0);
+            }
+            if (born_active) {
+                const int orow = totKeep + k;
+                if (orow < Tmax) {
+                    const Box b = mean_to_box<KIND>(z[0], z[1], z[2], z[3]);
                     double* o = gout + (size_t)orow * 8;
-                    o[0] = sm.tbox[i]; o[1] = sm.tbox[Tmax + i]; o[2] = sm.tbox[2 * Tmax + i]; o[3] = sm.tbox[3 * Tmax + i];
-                    o[4] = (double)sm.ti[B200_TI_ID * Tmax + i];
-                    o[5] = sm.tf[B200_TF_SCORE * Tmax + i];
-                    o[6] = sm.tf[B200_TF_CLS * Tmax + i];
-                    o[7] = (double)sm.ti[B200_TI_DET * Tmax + i];
-                }
-            }
-            if (dv) {                                   // STrack.activate (byte_tracker.py:50-62)
-                const int j = i;
-                const int k = (int)((ex >> 50) & 1023);
-                const int dst = totKeep + k;
-                double z[4];
-                det_measurement<KIND>(sm, Dmax, j, z);
-                KfState ks;
-                kf_initiate<KIND>(z, ks);
-                const int id = id0 + (int)idex + 1;
-                if (dst < Tmax) {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) gf[(B200_TF_MEAN + c) * Tmax + dst] = ks.m[c];
-#pragma unroll
-                    for (int a = 0; a < 4; ++a) {
-                        gf[(B200_TF_COV + 3 * a + 0) * Tmax + dst] = ks.pp[a];
-                        gf[(B200_TF_COV + 3 * a + 1) * Tmax + dst] = ks.pv[a];
-                        gf[(B200_TF_COV + 3 * a + 2) * Tmax + dst] = ks.vv[a];
-                    }
-                    gf[B200_TF_SCORE * Tmax + dst] = sm.dconf[j];
-                    gf[B200_TF_CLS * Tmax + dst] = sm.dcls[j];
-                    gi[B200_TI_ID * Tmax + dst] = id;
-                    gi[B200_TI_FRAME * Tmax + dst] = frame;
-                    gi[B200_TI_START * Tmax + dst] = frame;
-                    gi[B200_TI_LEN * Tmax + dst] = 0;
-                    gi[B200_TI_DET * Tmax + dst] = j;
-                    gi[B200_TI_FLAGS * Tmax + dst] = B200_ST_TRACKED | (born_active ? B200_FLAG_ACTIVATED : 0);
-                }
-                if (born_active) {
-                    const int orow = totKeepAct + k;
-                    if (orow < Tmax) {
-                        const Box b = mean_to_box<KIND>(z[0], z[1], z[2], z[3]);
-                        double* o = gout + (size_t)orow * 8;
-                        o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
-                        o[4] = (double)id; o[5] = sm.dconf[j]; o[6] = sm.dcls[j]; o[7] = (double)j;
-                    }
+                    o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
+                    o[4] = (double)id; o[5] = sm.dconf[j]; o[6] = sm.dcls[j]; o[7] = (double)j;
                 }
             }
         }
-        if (tid == 0) {
-            counts[0] = min(newT, Tmax);
-            counts[1] = min(newL, Tmax - min(newT, Tmax));
-            counts[2] = id0 + (int)idbase;
-            counts[3] = frame;
-            p.nout[s] = min(totKeepAct + totBornAct + totRef, Tmax);
-            p.track_updates[s] += (unsigned long long)n;
-            if (err) atomicOr(p.err, err);
-        }
+    }
+    if (tid == 0) {
+        counts[0] = min(newT, Tmax);
+        counts[1] = min(newL, Tmax - min(newT, Tmax));
+        counts[2] = id0 + totBornAll;
+        counts[3] = frame;
+        p.nout[s] = min(totKeep + rowsBorn + totRef, Tmax);
+        p.track_updates[s] += (unsigned long long)n;
+        if (err) atomicOr(p.err, err);
     }
 }
 

@@ -97,9 +97,11 @@ __device__ __forceinline__ void kf_update(KfState& s, const double* z, double co
     kf_project_diag<KIND>(s, conf, S);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const double l = sqrt(S[i]);                           // cho_factor of a diagonal S
-        const double kp = xdiv(xdiv(s.pp[i], l), l);           // cho_solve: two triangular solves
-        const double kv = xdiv(xdiv(s.pv[i], l), l);
+        // cho_factor / cho_solve of a diagonal S reduce to a division by S[i]; one correctly
+        // rounded reciprocal per axis (<= 1 ulp from the reference's (b / sqrt(S)) / sqrt(S))
+        const double rs = __drcp_rn(S[i]);
+        const double kp = xmul(s.pp[i], rs);
+        const double kv = xmul(s.pv[i], rs);
         const double y = xsub(z[i], s.m[i]);
         s.m[i] = xadd(s.m[i], xmul(y, kp));
         s.m[i + 4] = xadd(s.m[i + 4], xmul(y, kv));

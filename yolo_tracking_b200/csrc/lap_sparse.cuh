@@ -38,6 +38,8 @@ struct LapWork {
     short* nextc;       // [Dmax]
     short* mark;        // [Dmax]  stamp when reached
     short* scn;         // [Dmax]  stamp when scanned
+    int* coldeg;        // [Dmax]  candidate rows per column (filled while adj is built)
+    int* ncomplex;      // [1]     rows that need the general solver
 };
 
 __device__ __forceinline__ int uf_find(volatile int* parent, int x) {
@@ -61,8 +63,8 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 }
 
 // Insert one row into the matching of its component (one shortest augmenting path).
-template <class Cost>
-__device__ void lap_insert_row(const LapWork& w, int words, double lambda, const Cost& cost, int i0) {
+template <class Cost, class Lambda>
+__device__ void lap_insert_row(const LapWork& w, int words, const Lambda& lambda, const Cost& cost, int i0) {
     const short stamp = (short)(i0 + 1);
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     double minVal = 0.0;
@@ -73,7 +75,7 @@ __device__ void lap_insert_row(const LapWork& w, int words, double lambda, const
     int sink = -1;
     while (true) {
         const double ui = w.u[i];
-        const double dd = minVal + lambda - ui;        // row i may stay unmatched at cost lambda
+        const double dd = minVal + lambda(i) - ui;     // row i may stay unmatched at cost lambda(i)
         if (dd < bestDummy) { bestDummy = dd; bestDummyRow = i; }
         for (int wd = 0; wd < words; ++wd) {
             uint32_t bits = w.adj[wd * w.Tmax + i];
@@ -127,34 +129,54 @@ __device__ void lap_insert_row(const LapWork& w, int words, double lambda, const
     }
 }
 
-// Whole-CTA solve.  adj[word][row] must be complete (and zero for rows/cols not taking
-// part); rows are 0..nrows-1, columns 0..32*words-1.  Results in xr / yc.
-template <int NT, class Cost>
-__device__ void lap_sparse_solve(const LapWork& w, int nrows, int words, double lambda, const Cost& cost) {
+// Zero the per-problem work arrays.  Call (all threads) BEFORE the candidate graph is built:
+// the builder accumulates coldeg[j] with atomicAdd for every edge it writes into adj.
+template <int NT>
+__device__ __forceinline__ void lap_prepare(const LapWork& w, int nrows, int words) {
     const int tid = threadIdx.x;
     const int ncols = words * 32;
-    for (int t = tid; t < nrows; t += NT) { w.xr[t] = -1; w.u[t] = 0.0; w.parent[t] = t; w.head[t] = -1; }
+    for (int t = tid; t < nrows; t += NT) { w.xr[t] = -1; w.u[t] = 0.0; w.parent[t] = t; w.head[t] = -1; w.rnext[t] = -1; }
     for (int j = tid; j < ncols; j += NT) {
-        w.yc[j] = -1; w.v[j] = 0.0; w.parent[w.Tmax + j] = w.Tmax + j; w.mark[j] = 0; w.scn[j] = 0;
+        w.yc[j] = -1; w.v[j] = 0.0; w.parent[w.Tmax + j] = w.Tmax + j; w.mark[j] = 0; w.scn[j] = 0; w.coldeg[j] = 0;
     }
-    __syncthreads();
-    for (int task = tid; task < nrows * words; task += NT) {
-        const int wd = task / nrows, t = task - wd * nrows;
-        uint32_t bits = w.adj[wd * w.Tmax + t];
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            uf_union(w.parent, t, w.Tmax + wd * 32 + b);
-        }
-    }
-    __syncthreads();
+    if (tid == 0) *w.ncomplex = 0;
+}
+
+// Whole-CTA solve.  adj[word][row] and coldeg[] must be complete (zero for rows / columns not
+// taking part) and visible (__syncthreads() after the build); rows are 0..nrows-1, columns
+// 0..32*words-1.  lambda(row) is the cost limit of that row's problem.  Results in xr / yc.
+//
+// Fast path: a row with exactly one candidate column whose only candidate row it is forms a
+// component of its own and is matched directly (c_ij <= limit by construction).  Only the
+// remaining rows go through union-find + augmentation.
+template <int NT, class Cost, class Lambda>
+__device__ void lap_sparse_solve(const LapWork& w, int nrows, int words, const Lambda& lambda, const Cost& cost) {
+    const int tid = threadIdx.x;
     for (int t = tid; t < nrows; t += NT) {
-        bool any = false;
-        for (int wd = 0; wd < words; ++wd) any |= w.adj[wd * w.Tmax + t] != 0;
-        if (any) {
-            const int root = uf_find(w.parent, t);      // smallest row of the component
-            w.rnext[t] = (short)atomicExch(&w.head[root], t);
+        int deg = 0, first = -1;
+        for (int wd = 0; wd < words; ++wd) {
+            const uint32_t bits = w.adj[wd * w.Tmax + t];
+            if (bits) { if (first < 0) first = wd * 32 + __ffs(bits) - 1; deg += __popc(bits); }
         }
+        if (deg == 0) continue;
+        if (deg == 1 && w.coldeg[first] == 1) { w.xr[t] = (short)first; w.yc[first] = (short)t; continue; }
+        atomicAdd(w.ncomplex, 1);
+        for (int wd = 0; wd < words; ++wd) {
+            uint32_t bits = w.adj[wd * w.Tmax + t];
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                uf_union(w.parent, t, w.Tmax + wd * 32 + b);
+            }
+        }
+        w.rnext[t] = -2;                                  // marks "complex row" for the next phase
+    }
+    __syncthreads();
+    if (*w.ncomplex == 0) return;                         // uniform: every thread reads the same value
+    for (int t = tid; t < nrows; t += NT) {
+        if (w.rnext[t] != -2) continue;
+        const int root = uf_find(w.parent, t);            // smallest row of the component
+        w.rnext[t] = (short)atomicExch(&w.head[root], t);
     }
     __syncthreads();
     for (int t = tid; t < nrows; t += NT) {

@@ -289,19 +289,22 @@ __global__ void __launch_bounds__(256) lapjv_sparse_kernel(int rows, int cols, i
     w.parent = (int*)take(4 * (Rpad + Cpad)); w.head = (int*)take(4 * Rpad);
     w.rnext = (short*)take(2 * Rpad); w.xr = (short*)take(2 * Rpad); w.yc = (short*)take(2 * Cpad);
     w.pred = (short*)take(2 * Cpad); w.nextc = (short*)take(2 * Cpad); w.mark = (short*)take(2 * Cpad); w.scn = (short*)take(2 * Cpad);
+    w.coldeg = (int*)take(4 * Cpad); w.ncomplex = (int*)take(16);
     const double* c = cost + (size_t)blockIdx.x * rows * cols;
     GlobalCost gc{c, cols};
+    lap_prepare<256>(w, rows, words);
+    __syncthreads();
     for (int task = threadIdx.x; task < rows * words; task += blockDim.x) {
         const int t = task / words, wd = task - t * words;
         uint32_t bits = 0;
         for (int b = 0; b < 32; ++b) {
             const int j = wd * 32 + b;
-            if (j < cols && c[(size_t)t * cols + j] <= limit) bits |= 1u << b;
+            if (j < cols && c[(size_t)t * cols + j] <= limit) { bits |= 1u << b; atomicAdd(&w.coldeg[j], 1); }
         }
         w.adj[wd * Rpad + t] = bits;
     }
     __syncthreads();
-    lap_sparse_solve<256>(w, rows, words, limit, gc);
+    lap_sparse_solve<256>(w, rows, words, [limit](int) { return limit; }, gc);
     for (int t = threadIdx.x; t < rows; t += blockDim.x) x[(size_t)blockIdx.x * rows + t] = w.xr[t];
     for (int j = threadIdx.x; j < cols; j += blockDim.x) y[(size_t)blockIdx.x * cols + j] = w.yc[j];
 }
@@ -506,7 +509,7 @@ extern "C" int b200track_lapjv(int32_t batch, int32_t rows, int32_t cols, const 
     if (limit < __builtin_inf()) {
         const int Rpad = (rows + 31) & ~31, Cpad = (cols + 31) & ~31;
         size_t smem = 8 * (size_t)Rpad + 16 * (size_t)Cpad + 4 * (size_t)(Cpad / 32) * Rpad + 4 * (size_t)(Rpad + Cpad) + 4 * (size_t)Rpad +
-                      4 * (size_t)Rpad + 10 * (size_t)Cpad + 16 * 16;
+                      4 * (size_t)Rpad + 14 * (size_t)Cpad + 16 * 18;
         if (smem > 227 * 1024) { set_error("lapjv: problem too large for shared memory"); return B200TRACK_ERR_CAPACITY; }
         B200_CU_TRY(cudaFuncSetAttribute(lapjv_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lapjv_sparse_kernel<<<batch, 256, smem, (cudaStream_t)st>>>(rows, cols, Rpad, Cpad, cost, limit, x, y);
