@@ -46,6 +46,8 @@ struct b200track_ctx {
     b200track_config cfg;
     b200::StepParams p;
     int kf_kind = 0;
+    int variant = 0;
+    int tcap = 0;               // slot stride of the device state (the kernel variant's capacity)
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     HostSlot slot[NSLOT];
     uint64_t launches = 0;
@@ -55,10 +57,10 @@ struct b200track_ctx {
 static int check_cfg(const b200track_config* c) {
     if (!c) { set_error("cfg is NULL"); return B200TRACK_ERR_ARG; }
     if (c->n_streams <= 0) { set_error("n_streams must be > 0"); return B200TRACK_ERR_ARG; }
-    if (c->max_tracks <= 0 || c->max_tracks % 32 || c->max_tracks > 992) {
-        set_error("max_tracks must be a multiple of 32 in [32, 992]"); return B200TRACK_ERR_ARG; }
-    if (c->max_dets <= 0 || c->max_dets % 32 || c->max_dets > 992) {
-        set_error("max_dets must be a multiple of 32 in [32, 992]"); return B200TRACK_ERR_ARG; }
+    if (c->max_tracks <= 0 || c->max_tracks % 32 || c->max_tracks > 512) {
+        set_error("max_tracks must be a multiple of 32 in [32, 512]"); return B200TRACK_ERR_ARG; }
+    if (c->max_dets <= 0 || c->max_dets % 32 || c->max_dets > 512) {
+        set_error("max_dets must be a multiple of 32 in [32, 512]"); return B200TRACK_ERR_ARG; }
     if (c->kind != B200TRACK_BYTETRACK && c->kind != B200TRACK_OCSORT && c->kind != B200TRACK_BOTSORT) {
         set_error("unknown tracker kind"); return B200TRACK_ERR_ARG; }
     return 0;
@@ -90,7 +92,7 @@ extern "C" int b200track_reset(b200track_ctx* ctx) {
     if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
     CU_TRY(cudaSetDevice(ctx->cfg.device));
     CU_TRY(cudaDeviceSynchronize());
-    const size_t S = ctx->cfg.n_streams, T = ctx->cfg.max_tracks;
+    const size_t S = ctx->cfg.n_streams, T = ctx->tcap;
     CU_TRY(cudaMemset(ctx->p.state_f, 0, S * B200_NF * T * sizeof(double)));
     CU_TRY(cudaMemset(ctx->p.state_i, 0, S * B200_NI * T * sizeof(int)));
     CU_TRY(cudaMemset(ctx->p.counts, 0, S * 4 * sizeof(int)));
@@ -127,7 +129,10 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     p.appearance_thresh = cfg->appearance_thresh;
     p.max_time_lost = (int)(cfg->frame_rate / 30.0 * cfg->track_buffer);   // byte_tracker.py:128-129
     ctx->kf_kind = cfg->kind == B200TRACK_BOTSORT ? B200TRACK_KF_XYWH : B200TRACK_KF_XYAH;
-    const size_t S = cfg->n_streams, T = cfg->max_tracks, D = cfg->max_dets;
+    ctx->variant = b200::bytetrack_step_variant(cfg->max_tracks, cfg->max_dets);
+    if (ctx->variant < 0) { set_error("no kernel variant covers max_tracks / max_dets"); delete ctx; return B200TRACK_ERR_CAPACITY; }
+    ctx->tcap = b200::bytetrack_step_tmax(ctx->variant);
+    const size_t S = cfg->n_streams, T = ctx->tcap, D = cfg->max_dets;
     int rc = 0;
     auto fail = [&](int code) { b200track_destroy(ctx); return code; };
 #define CU_TRY_CTX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return fail(B200TRACK_ERR_CUDA); } } while (0)
@@ -144,13 +149,13 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         CU_TRY_CTX(cudaMalloc(&s.d_dets, S * D * 6 * sizeof(double)));
         CU_TRY_CTX(cudaMalloc(&s.d_ndets, S * sizeof(int32_t)));
         if (cfg->feat_dim > 0) CU_TRY_CTX(cudaMalloc(&s.d_feats, S * D * (size_t)cfg->feat_dim * sizeof(float)));
-        CU_TRY_CTX(cudaMalloc(&s.d_out, S * T * 8 * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&s.d_out, S * (size_t)cfg->max_tracks * 8 * sizeof(double)));
         CU_TRY_CTX(cudaMalloc(&s.d_nout, S * sizeof(int32_t)));
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.in_ready, cudaEventDisableTiming));
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.out_ready, cudaEventDisableTiming));
     }
-    const size_t smem = b200::bytetrack_step_smem(cfg->max_tracks, cfg->max_dets);
+    const size_t smem = b200::bytetrack_step_smem(ctx->variant);
     int max_smem = 0;
     CU_TRY_CTX(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     if (smem > (size_t)max_smem) {
@@ -168,7 +173,7 @@ static int launch_step(b200track_ctx* ctx, const double* d_dets, const int32_t* 
     (void)img_h; (void)img_w;
     b200::StepParams p = ctx->p;
     p.dets = d_dets; p.ndets = d_ndets; p.feats = d_feats; p.out = d_out; p.nout = d_nout;
-    CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, st));
+    CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, ctx->variant, st));
     ctx->launches += 1;
     return 0;
 }
@@ -269,8 +274,8 @@ extern "C" int b200track_launch_count(b200track_ctx* ctx, uint64_t* h_launches) 
 
 extern "C" int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state, uint64_t* h_smem) {
     if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
-    if (h_state) *h_state = (uint64_t)ctx->cfg.max_tracks * B200_SLOT_BYTES + 4 * sizeof(int) + sizeof(unsigned long long);
-    if (h_smem) *h_smem = b200::bytetrack_step_smem(ctx->cfg.max_tracks, ctx->cfg.max_dets);
+    if (h_state) *h_state = (uint64_t)ctx->tcap * B200_SLOT_BYTES + 4 * sizeof(int) + sizeof(unsigned long long);
+    if (h_smem) *h_smem = b200::bytetrack_step_smem(ctx->variant);
     return 0;
 }
 
@@ -280,14 +285,14 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
     if (stream_index < 0 || stream_index >= ctx->cfg.n_streams) { set_error("stream_index out of range"); return B200TRACK_ERR_ARG; }
     CU_TRY(cudaSetDevice(ctx->cfg.device));
     CU_TRY(cudaDeviceSynchronize());
-    const size_t T = ctx->cfg.max_tracks, s = stream_index;
+    const size_t T = ctx->tcap, s = stream_index;
     std::vector<double> f(B200_NF * T);
     std::vector<int> iv(B200_NI * T);
     CU_TRY(cudaMemcpy(h_counts, ctx->p.counts + 4 * s, 4 * sizeof(int), cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(f.data(), ctx->p.state_f + s * B200_NF * T, f.size() * sizeof(double), cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(iv.data(), ctx->p.state_i + s * B200_NI * T, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
     const int n = h_counts[0] + h_counts[1];
-    for (int t = 0; t < n && t < (int)T; ++t) {
+    for (int t = 0; t < n && t < ctx->cfg.max_tracks; ++t) {
         const int fl = iv[B200_TI_FLAGS * T + t];
         if (h_rec) {
             int32_t* r = h_rec + 6 * t;

@@ -1,11 +1,18 @@
 // ByteTrack frame step for many independent streams: ONE kernel launch per frame, one CTA per
-// stream.  The CTA reads the stream's detections and its whole track state from HBM once,
-// keeps everything (Kalman state, boxes, candidate graph, assignment duals) in shared memory
-// for the entire step, and writes the state back once, already in the reference's new list
-// order, together with the output rows.  Nothing T x D ever touches HBM - or is even computed:
-// candidates come from per-frame cell masks (64 x-cells and 64 y-cells, each a bitmask of the
-// detections whose box touches the cell), so a track only runs the exact IoU test against the
-// handful of detections that share a cell range with it in both axes.
+// stream, one thread per track slot.
+//
+// Data flow per stream (HBM is touched exactly once in each direction):
+//   * detections [nd, 6] and the 8 Kalman means + 3 lifecycle ints of every slot are staged
+//     in shared memory; the 12 covariance terms of a slot are NOT needed for association
+//     (ByteTrack costs only use boxes), so each thread loads them straight into registers at
+//     the single deferred predict+update point and keeps them there until the final write;
+//   * candidate pairs come from per-frame cell masks (64 x-cells and 64 y-cells, each a
+//     bitmask of the detections whose box touches the cell): a track runs the exact IoU test
+//     only against detections sharing a cell range with it in both axes - nothing T x D is
+//     ever computed, let alone written to HBM;
+//   * the assignment is solved on the pruned graph in shared memory (lap_sparse.cuh);
+//   * the state is written back already in the reference's new list order (tracked list, then
+//     lost list), together with the output rows.
 //
 // Replaces BYTETracker.update (boxmot/trackers/bytetrack/byte_tracker.py:132-281) and what it
 // calls: STrack.multi_predict :35-48 -> KalmanFilter.multi_predict (bytetrack_kf.py:155-192),
@@ -35,85 +42,26 @@ constexpr int NCELL = 64;         // cells per axis of the candidate masks
 // row types of one association pass: which detection set / limit / cost a row uses
 constexpr int RT_NONE = 0, RT_A = 1, RT_B = 2;
 
-struct Sm {
-    double *tf, *tbox, *dxywh, *dbox, *dconf, *dcls, *u, *v, *dist;
-    unsigned long long* scratch;
-    int *ti, *parent, *head, *coldeg, *ncomplex;
-    uint32_t *adj, *colbitsA, *colbitsB, *xmask, *ymask;
-    float* fext;
-    short *rnext, *xr, *yc, *pred, *nextc, *mark, *scn, *lostlist;
-    unsigned char *role, *rowtype, *dflag, *cat, *drop;
+template <int TMAX, int DMAX>
+struct alignas(16) StepSmem {
+    static constexpr int DW = DMAX / 32;
+    static constexpr int DWP = (DW + 3) / 4 * 4;      // mask rows padded to 16-byte multiples
+    double mean[8][TMAX];
+    double dbox[4][DMAX];                             // raw x1, y1, x2, y2
+    double dconf[DMAX];
+    double dcls[DMAX];
+    double u[TMAX], v[DMAX], dist[DMAX];
+    unsigned long long scratch[40];
+    int frame_t[TMAX], start_t[TMAX];
+    int parent[TMAX + DMAX], head[TMAX], coldeg[DMAX], ncomplex[4];
+    uint32_t adj[DW][TMAX];
+    uint32_t colbitsA[DWP], colbitsB[DWP];
+    uint32_t xmask[NCELL][DWP], ymask[NCELL][DWP];
+    float fext[32][4];
+    short rnext[TMAX], xr[TMAX], match[TMAX], lostlist[TMAX];
+    short yc[DMAX], pred[DMAX], nextc[DMAX], mark[DMAX], scn[DMAX];
+    unsigned char role[TMAX], rowtype[TMAX], cat[TMAX], drop[TMAX + DMAX], dflag[DMAX];
 };
-
-__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
-
-__host__ __device__ inline size_t carve(Sm* sm, unsigned char* base, int Tmax, int Dmax) {
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off = align16(off + bytes); return base ? base + o : (unsigned char*)nullptr; };
-    const int DW = Dmax / 32;
-    Sm s;
-    s.tf = (double*)take(sizeof(double) * B200_NF * Tmax);
-    s.tbox = (double*)take(sizeof(double) * 4 * Tmax);
-    s.dxywh = (double*)take(sizeof(double) * 4 * Dmax);
-    s.dbox = (double*)take(sizeof(double) * 4 * Dmax);
-    s.dconf = (double*)take(sizeof(double) * Dmax);
-    s.dcls = (double*)take(sizeof(double) * Dmax);
-    s.u = (double*)take(sizeof(double) * Tmax);
-    s.v = (double*)take(sizeof(double) * Dmax);
-    s.dist = (double*)take(sizeof(double) * Dmax);
-    s.scratch = (unsigned long long*)take(sizeof(unsigned long long) * 40);
-    s.ti = (int*)take(sizeof(int) * B200_NI * Tmax);
-    s.parent = (int*)take(sizeof(int) * (Tmax + Dmax));
-    s.head = (int*)take(sizeof(int) * Tmax);
-    s.coldeg = (int*)take(sizeof(int) * Dmax);
-    s.ncomplex = (int*)take(sizeof(int) * 4);
-    s.adj = (uint32_t*)take(sizeof(uint32_t) * DW * Tmax);
-    s.colbitsA = (uint32_t*)take(sizeof(uint32_t) * DW);
-    s.colbitsB = (uint32_t*)take(sizeof(uint32_t) * DW);
-    s.xmask = (uint32_t*)take(sizeof(uint32_t) * NCELL * DW);
-    s.ymask = (uint32_t*)take(sizeof(uint32_t) * NCELL * DW);
-    s.fext = (float*)take(sizeof(float) * 32 * 4);
-    s.rnext = (short*)take(sizeof(short) * Tmax);
-    s.xr = (short*)take(sizeof(short) * Tmax);
-    s.yc = (short*)take(sizeof(short) * Dmax);
-    s.pred = (short*)take(sizeof(short) * Dmax);
-    s.nextc = (short*)take(sizeof(short) * Dmax);
-    s.mark = (short*)take(sizeof(short) * Dmax);
-    s.scn = (short*)take(sizeof(short) * Dmax);
-    s.lostlist = (short*)take(sizeof(short) * Tmax);
-    s.role = take(Tmax);
-    s.rowtype = take(Tmax);
-    s.dflag = take(Dmax);
-    s.cat = take(Tmax);
-    s.drop = take(Tmax + Dmax);
-    if (sm) *sm = s;
-    return off;
-}
-
-__device__ __forceinline__ Box load_box(const double* b, int stride, int i) {
-    Box r; r.x1 = b[i]; r.y1 = b[stride + i]; r.x2 = b[2 * stride + i]; r.y2 = b[3 * stride + i]; return r;
-}
-
-__device__ __forceinline__ void load_kf(const double* tf, int Tmax, int t, KfState& s) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) s.m[c] = tf[(B200_TF_MEAN + c) * Tmax + t];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        s.pp[i] = tf[(B200_TF_COV + 3 * i + 0) * Tmax + t];
-        s.pv[i] = tf[(B200_TF_COV + 3 * i + 1) * Tmax + t];
-        s.vv[i] = tf[(B200_TF_COV + 3 * i + 2) * Tmax + t];
-    }
-}
-__device__ __forceinline__ void store_kf(double* tf, int Tmax, int t, const KfState& s) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) tf[(B200_TF_MEAN + c) * Tmax + t] = s.m[c];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        tf[(B200_TF_COV + 3 * i + 0) * Tmax + t] = s.pp[i];
-        tf[(B200_TF_COV + 3 * i + 1) * Tmax + t] = s.pv[i];
-        tf[(B200_TF_COV + 3 * i + 2) * Tmax + t] = s.vv[i];
-    }
-}
 
 // STrack.xyxy (byte_tracker.py:100-111): XYAH mean -> (xc, yc, a*h, h) -> corners
 template <int KIND>
@@ -122,33 +70,40 @@ __device__ __forceinline__ Box mean_to_box(double xc, double yc, double a_or_w, 
     return xywh_to_xyxy(xc, yc, w, h);
 }
 
-template <int KIND>
-__device__ __forceinline__ void refresh_box(const Sm& sm, int Tmax, int t) {
-    const Box b = mean_to_box<KIND>(sm.tf[0 * Tmax + t], sm.tf[1 * Tmax + t], sm.tf[2 * Tmax + t], sm.tf[3 * Tmax + t]);
-    sm.tbox[t] = b.x1; sm.tbox[Tmax + t] = b.y1; sm.tbox[2 * Tmax + t] = b.x2; sm.tbox[3 * Tmax + t] = b.y2;
+template <int KIND, class SM>
+__device__ __forceinline__ Box track_box(const SM& sm, int t) {
+    return mean_to_box<KIND>(sm.mean[0][t], sm.mean[1][t], sm.mean[2][t], sm.mean[3][t]);
+}
+
+// The box iou_distance sees for a detection is the round trip xyxy -> xywh -> xyxy
+// (STrack.__init__ + STrack.xyxy with mean None, byte_tracker.py:16, :105-110).
+template <class SM>
+__device__ __forceinline__ Box det_box(const SM& sm, int j) {
+    double xc, yc, w, h;
+    xyxy_to_xywh(sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j], xc, yc, w, h);
+    return xywh_to_xyxy(xc, yc, w, h);
 }
 
 // measurement fed to the filter for detection j (STrack.__init__, byte_tracker.py:16-18)
-template <int KIND>
-__device__ __forceinline__ void det_measurement(const Sm& sm, int Dmax, int j, double* z) {
-    const double xc = sm.dxywh[j], yc = sm.dxywh[Dmax + j], w = sm.dxywh[2 * Dmax + j], h = sm.dxywh[3 * Dmax + j];
+template <int KIND, class SM>
+__device__ __forceinline__ void det_measurement(const SM& sm, int j, double* z) {
+    double xc, yc, w, h;
+    xyxy_to_xywh(sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j], xc, yc, w, h);
     if (KIND == KF_XYWH) { z[0] = xc; z[1] = yc; z[2] = w; z[3] = h; }
     else xywh_to_xyah(xc, yc, w, h, z);
 }
 
 // cost of (track row, detection): iou_distance, optionally fuse_score, chosen by the row type
+template <int KIND, class SM>
 struct PassCost {
-    const double *tbox, *dbox, *dconf;
-    const unsigned char* rowtype;
-    int Tmax, Dmax;
+    const SM* sm;
     bool fuseA, fuseB;
-    __device__ __forceinline__ double eval(const Box& a, int j, bool fuse) const {
-        const Box b = load_box(dbox, Dmax, j);
-        const double v = box_iou(a, b);
-        return fuse ? fused_cost(v, dconf[j]) : xsub(1.0, v);
+    __device__ __forceinline__ double pair(const Box& a, int j, bool fuse) const {
+        const double v = box_iou(a, det_box(*sm, j));
+        return fuse ? fused_cost(v, sm->dconf[j]) : xsub(1.0, v);
     }
     __device__ __forceinline__ double operator()(int t, int j) const {
-        return eval(load_box(tbox, Tmax, t), j, rowtype[t] == RT_A ? fuseA : fuseB);
+        return pair(track_box<KIND>(*sm, t), j, sm->rowtype[t] == RT_A ? fuseA : fuseB);
     }
 };
 struct PassLimit {
@@ -167,141 +122,123 @@ struct CellMap {
     }
 };
 
-// Candidate graph of one association pass.  Row t (type rowtype[t]) is tested against the
+// Candidate graph of one association pass, thread t = row t.  The row is tested against the
 // detections of its column set that share a cell range with it in x AND in y (a superset of
 // the overlapping ones because the cell maps are monotone); edge iff the boxes overlap and
 // cost <= limit - exact pruning, see lap_sparse.cuh (no overlap => iou = 0 => cost = 1 > limit).
-template <int NT>
-__device__ void build_graph(const Sm& sm, const LapWork& lw, int Tmax, int Dmax, int n, int words, const CellMap& cm,
-                            const PassCost& cost, const PassLimit& lim) {
-    const int DW = Dmax / 32;
-    for (int t = threadIdx.x; t < n; t += NT) {
-        const int rt = sm.rowtype[t];
-        if (rt == RT_NONE) {
-            for (int wd = 0; wd < words; ++wd) sm.adj[wd * Tmax + t] = 0u;
-            continue;
+template <int KIND, class SM>
+__device__ __forceinline__ void build_graph_row(SM& sm, int t, int n, int words, const CellMap& cm,
+                                                const PassCost<KIND, SM>& cost, const PassLimit& lim) {
+    constexpr int DWP = SM::DWP;
+    if (t >= n) return;
+    const int rt = sm.rowtype[t];
+    if (rt == RT_NONE) {
+        for (int wd = 0; wd < words; ++wd) sm.adj[wd][t] = 0u;
+        return;
+    }
+    const Box a = track_box<KIND>(sm, t);
+    const int cx0 = cm.cx(a.x1), cx1 = cm.cx(a.x2), cy0 = cm.cy(a.y1), cy1 = cm.cy(a.y2);
+    const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
+    const bool fuse = rt == RT_A ? cost.fuseA : cost.fuseB;
+    const double limit = rt == RT_A ? lim.limA : lim.limB;
+#pragma unroll
+    for (int q = 0; q < DWP / 4; ++q) {
+        if (q * 4 >= words) break;
+        uint4 mx = make_uint4(0, 0, 0, 0), my = make_uint4(0, 0, 0, 0);
+        for (int c = cx0; c <= cx1; ++c) {
+            const uint4 m = *reinterpret_cast<const uint4*>(&sm.xmask[c][q * 4]);
+            mx.x |= m.x; mx.y |= m.y; mx.z |= m.z; mx.w |= m.w;
         }
-        const Box a = load_box(sm.tbox, Tmax, t);
-        const int cx0 = cm.cx(a.x1), cx1 = cm.cx(a.x2), cy0 = cm.cy(a.y1), cy1 = cm.cy(a.y2);
-        const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
-        const bool fuse = rt == RT_A ? cost.fuseA : cost.fuseB;
-        const double limit = rt == RT_A ? lim.limA : lim.limB;
-        for (int wd = 0; wd < words; ++wd) {
-            uint32_t res = 0u;
-            const uint32_t cb = colbits[wd];
-            if (cb) {
-                uint32_t mx = 0u, my = 0u;
-                for (int c = cx0; c <= cx1; ++c) mx |= sm.xmask[c * DW + wd];
-                for (int c = cy0; c <= cy1; ++c) my |= sm.ymask[c * DW + wd];
-                uint32_t cand = mx & my & cb;
-                while (cand) {
-                    const int b = __ffs(cand) - 1;
-                    cand &= cand - 1;
-                    const int j = wd * 32 + b;
-                    const Box d = load_box(sm.dbox, Dmax, j);
-                    if (box_overlap(a, d)) {
-                        const double v = box_iou(a, d);
-                        const double c = fuse ? fused_cost(v, sm.dconf[j]) : xsub(1.0, v);
-                        if (c <= limit) { res |= 1u << b; atomicAdd(&lw.coldeg[j], 1); }
-                    }
+        for (int c = cy0; c <= cy1; ++c) {
+            const uint4 m = *reinterpret_cast<const uint4*>(&sm.ymask[c][q * 4]);
+            my.x |= m.x; my.y |= m.y; my.z |= m.z; my.w |= m.w;
+        }
+        const uint4 cb = *reinterpret_cast<const uint4*>(&colbits[q * 4]);
+        uint32_t cand4[4] = {mx.x & my.x & cb.x, mx.y & my.y & cb.y, mx.z & my.z & cb.z, mx.w & my.w & cb.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int wd = q * 4 + k;
+            if (wd >= words) break;
+            uint32_t cand = cand4[k], res = 0u;
+            while (cand) {
+                const int b = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const int j = wd * 32 + b;
+                const Box d = det_box(sm, j);
+                if (box_overlap(a, d)) {
+                    const double v = box_iou(a, d);
+                    const double c = fuse ? fused_cost(v, sm.dconf[j]) : xsub(1.0, v);
+                    if (c <= limit) { res |= 1u << b; atomicAdd(&sm.coldeg[j], 1); }
                 }
             }
-            sm.adj[wd * Tmax + t] = res;
+            sm.adj[wd][t] = res;
         }
     }
-    __syncthreads();
 }
 
-// STrack.update / re_activate for every matched row (byte_tracker.py:64-98)
-template <int NT, int KIND>
-__device__ void apply_matches(const Sm& sm, int Tmax, int Dmax, int n, int frame) {
-    for (int t = threadIdx.x; t < n; t += NT) {
-        if (sm.rowtype[t] == RT_NONE) continue;
-        const int j = sm.xr[t];
-        if (j < 0) continue;
-        KfState s;
-        load_kf(sm.tf, Tmax, t, s);
-        double z[4];
-        det_measurement<KIND>(sm, Dmax, j, z);
-        kf_update<KIND>(s, z);
-        store_kf(sm.tf, Tmax, t, s);
-        int fl = sm.ti[B200_TI_FLAGS * Tmax + t];
-        const int st = fl & 3;
-        int len = sm.ti[B200_TI_LEN * Tmax + t];
-        len = (st == B200_ST_TRACKED) ? len + 1 : 0;
-        sm.ti[B200_TI_LEN * Tmax + t] = len;
-        sm.ti[B200_TI_FRAME * Tmax + t] = frame;
-        sm.ti[B200_TI_DET * Tmax + t] = j;
-        sm.ti[B200_TI_FLAGS * Tmax + t] = (fl & ~3) | B200_ST_TRACKED | B200_FLAG_ACTIVATED;
-        sm.tf[B200_TF_SCORE * Tmax + t] = sm.dconf[j];
-        sm.tf[B200_TF_CLS * Tmax + t] = sm.dcls[j];
-        sm.dflag[j] |= DF_USED;
-    }
-}
-
-template <int NT, int KIND>
-__global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) {
+template <int NT, int KIND, int TMAX, int DMAX>
+__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : (NT == 256 ? 3 : (NT == 128 ? 6 : 8))))
+bytetrack_step_kernel(const StepParams p) {
+    static_assert(NT == TMAX && DMAX <= NT, "one thread per track slot; detections fit one pass");
+    using SM = StepSmem<TMAX, DMAX>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
+    constexpr int DWP = SM::DWP;
     const int s = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int Tmax = p.max_tracks, Dmax = p.max_dets, DW = Dmax / 32;
-    Sm sm;
-    carve(&sm, smem_raw, Tmax, Dmax);
 
     int* counts = p.counts + 4 * s;
     const int nT = counts[0], nL = counts[1], id0 = counts[2], frame = counts[3] + 1;
     const int n = nT + nL;
     int nd = p.ndets[s];
     int err = 0;
-    if (nd > Dmax) { nd = Dmax; err |= B200_ERR_DET_OVERFLOW; }
+    if (nd > min(DMAX, p.max_dets)) { nd = min(DMAX, p.max_dets); err |= B200_ERR_DET_OVERFLOW; }
     if (nd < 0) nd = 0;
     const int words = (nd + 31) >> 5;
+    const int t = tid;                                   // this thread's track slot
+    const double* gf = p.state_f + (size_t)s * B200_NF * TMAX;
+    const int* gi = p.state_i + (size_t)s * B200_NI * TMAX;
 
-    // ---- HBM -> shared memory, once: detections [nd, 6] (planar) and the track state ----
+    // ---- HBM -> shared memory: detections [nd, 6] (planar), means, lifecycle ints ----------
+    int fl = 0, frame_t = 0;
     {
-        const double* g = p.dets + (size_t)s * Dmax * 6;
+        const double* g = p.dets + (size_t)s * p.max_dets * 6;
         for (int i = tid; i < nd * 6; i += NT) {
             const double val = g[i];
             const int j = i / 6, c = i - 6 * j;
-            if (c < 4) sm.dbox[c * Dmax + j] = val;
+            if (c < 4) sm.dbox[c][j] = val;
             else if (c == 4) sm.dconf[j] = val;
             else sm.dcls[j] = val;
         }
-        const double* gf = p.state_f + (size_t)s * B200_NF * Tmax;
-        const int* gi = p.state_i + (size_t)s * B200_NI * Tmax;
-        for (int t = tid; t < n; t += NT) {
+        if (t < n) {
 #pragma unroll
-            for (int c = 0; c < B200_NF; ++c) sm.tf[c * Tmax + t] = gf[c * Tmax + t];
-#pragma unroll
-            for (int c = 0; c < B200_NI; ++c) sm.ti[c * Tmax + t] = gi[c * Tmax + t];
+            for (int c = 0; c < 8; ++c) sm.mean[c][t] = gf[(B200_TF_MEAN + c) * TMAX + t];
+            fl = gi[B200_TI_FLAGS * TMAX + t];
+            frame_t = gi[B200_TI_FRAME * TMAX + t];
+            sm.start_t[t] = gi[B200_TI_START * TMAX + t];
         }
-        for (int i = tid; i < NCELL * DW; i += NT) { sm.xmask[i] = 0u; sm.ymask[i] = 0u; }
-        for (int i = tid; i < Tmax + Dmax; i += NT) sm.drop[i] = 0;
+        for (int i = tid; i < NCELL * DWP; i += NT) { (&sm.xmask[0][0])[i] = 0u; (&sm.ymask[0][0])[i] = 0u; }
+        for (int i = tid; i < TMAX + DMAX; i += NT) sm.drop[i] = 0;
     }
     __syncthreads();
 
-    // ---- detection side: xyxy -> xywh, the round-trip box used by iou_distance, the two
-    // confidence bands (byte_tracker.py:151-158; strict inequalities), frame extents --------
+    // ---- detection side (thread j): confidence bands (byte_tracker.py:151-158, strict
+    // inequalities), frame extents for the cell maps -------------------------------------------
     const float FBIG = 3.0e38f;
     float ex0 = FBIG, ey0 = FBIG, ex1 = -FBIG, ey1 = -FBIG;
-    for (int j = tid; j < words * 32; j += NT) {
-        int fl = 0;
+    Box mybox = {0, 0, 0, 0};
+    int mydfl = 0;
+    if (tid < words * 32) {
+        const int j = tid;
         if (j < nd) {
-            double xc, yc, w, h;
-            xyxy_to_xywh(sm.dbox[j], sm.dbox[Dmax + j], sm.dbox[2 * Dmax + j], sm.dbox[3 * Dmax + j], xc, yc, w, h);
-            sm.dxywh[j] = xc; sm.dxywh[Dmax + j] = yc; sm.dxywh[2 * Dmax + j] = w; sm.dxywh[3 * Dmax + j] = h;
-            const Box b = xywh_to_xyxy(xc, yc, w, h);
-            sm.dbox[j] = b.x1; sm.dbox[Dmax + j] = b.y1; sm.dbox[2 * Dmax + j] = b.x2; sm.dbox[3 * Dmax + j] = b.y2;
+            mybox = det_box(sm, j);
             const double c = sm.dconf[j];
-            if (c > p.track_thresh) fl = DF_HIGH;
-            else if (c > p.low_thresh && c < p.track_thresh) fl = DF_LOW;
-            if (fl) {
-                ex0 = fminf(ex0, (float)b.x1); ey0 = fminf(ey0, (float)b.y1);
-                ex1 = fmaxf(ex1, (float)b.x2); ey1 = fmaxf(ey1, (float)b.y2);
-            }
+            if (c > p.track_thresh) mydfl = DF_HIGH;
+            else if (c > p.low_thresh && c < p.track_thresh) mydfl = DF_LOW;
+            if (mydfl) { ex0 = (float)mybox.x1; ey0 = (float)mybox.y1; ex1 = (float)mybox.x2; ey1 = (float)mybox.y2; }
         }
-        sm.dflag[j] = (unsigned char)fl;
-        const uint32_t mh = __ballot_sync(0xffffffffu, fl == DF_HIGH);
+        sm.dflag[j] = (unsigned char)mydfl;
+        const uint32_t mh = __ballot_sync(0xffffffffu, mydfl == DF_HIGH);
         if (lane == 0) sm.colbitsA[j >> 5] = mh;           // first association: all high detections
     }
 #pragma unroll
@@ -309,31 +246,31 @@ __global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) 
         ex0 = fminf(ex0, __shfl_xor_sync(0xffffffffu, ex0, d)); ey0 = fminf(ey0, __shfl_xor_sync(0xffffffffu, ey0, d));
         ex1 = fmaxf(ex1, __shfl_xor_sync(0xffffffffu, ex1, d)); ey1 = fmaxf(ey1, __shfl_xor_sync(0xffffffffu, ey1, d));
     }
-    if (lane == 0) { sm.fext[warp * 4] = ex0; sm.fext[warp * 4 + 1] = ey0; sm.fext[warp * 4 + 2] = ex1; sm.fext[warp * 4 + 3] = ey1; }
+    if (lane == 0) { sm.fext[warp][0] = ex0; sm.fext[warp][1] = ey0; sm.fext[warp][2] = ex1; sm.fext[warp][3] = ey1; }
 
-    // ---- track side: roles, Kalman predict of the pool (unconfirmed tracks are NOT
-    // predicted, byte_tracker.py:178-180), boxes ---------------------------------------------
-    for (int t = tid; t < n; t += NT) {
-        const int fl = sm.ti[B200_TI_FLAGS * Tmax + t];
-        const int role = t >= nT ? ROLE_LOST : ((fl & B200_FLAG_ACTIVATED) ? ROLE_TRACKED : ROLE_UNCONF);
+    // ---- track side (thread t): role; motion step of the mean for the pool (unconfirmed
+    // tracks are NOT predicted, byte_tracker.py:178-180).  The covariance half of the predict
+    // happens later in registers; it needs the pre-motion w / h, kept in ref_w / ref_h. -------
+    int role = ROLE_UNCONF;
+    double ref_w = 0.0, ref_h = 0.0;
+    if (t < n) {
+        role = t >= nT ? ROLE_LOST : ((fl & B200_FLAG_ACTIVATED) ? ROLE_TRACKED : ROLE_UNCONF);
         sm.role[t] = (unsigned char)role;
         if (role != ROLE_UNCONF) {
-            KfState k;
-            load_kf(sm.tf, Tmax, t, k);
+            ref_w = sm.mean[2][t]; ref_h = sm.mean[3][t];
             if ((fl & 3) != B200_ST_TRACKED) {          // multi_predict: zero the height (w, h) velocity
-                k.m[7] = 0.0;
-                if (KIND == KF_XYWH) k.m[6] = 0.0;
+                sm.mean[7][t] = 0.0;
+                if (KIND == KF_XYWH) sm.mean[6][t] = 0.0;
             }
-            kf_predict<KIND>(k);
-            store_kf(sm.tf, Tmax, t, k);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sm.mean[i][t] = xadd(sm.mean[i][t], sm.mean[i + 4][t]);
         }
-        refresh_box<KIND>(sm, Tmax, t);
         sm.rowtype[t] = role != ROLE_UNCONF ? RT_A : RT_NONE;
-        sm.cat[t] = CAT_NONE;
+        sm.match[t] = -1;
     }
 
     LapWork lw;
-    lw.Tmax = Tmax; lw.Dmax = Dmax; lw.adj = sm.adj; lw.u = sm.u; lw.v = sm.v; lw.dist = sm.dist;
+    lw.Tmax = TMAX; lw.Dmax = DMAX; lw.adj = &sm.adj[0][0]; lw.u = sm.u; lw.v = sm.v; lw.dist = sm.dist;
     lw.parent = sm.parent; lw.head = sm.head; lw.rnext = sm.rnext; lw.xr = sm.xr; lw.yc = sm.yc;
     lw.pred = sm.pred; lw.nextc = sm.nextc; lw.mark = sm.mark; lw.scn = sm.scn;
     lw.coldeg = sm.coldeg; lw.ncomplex = sm.ncomplex;
@@ -344,76 +281,126 @@ __global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) 
     CellMap cm;
     {
         float x0 = FBIG, y0 = FBIG, x1 = -FBIG, y1 = -FBIG;
+#pragma unroll
         for (int k = 0; k < NT / 32; ++k) {
-            x0 = fminf(x0, sm.fext[k * 4]); y0 = fminf(y0, sm.fext[k * 4 + 1]);
-            x1 = fmaxf(x1, sm.fext[k * 4 + 2]); y1 = fmaxf(y1, sm.fext[k * 4 + 3]);
+            x0 = fminf(x0, sm.fext[k][0]); y0 = fminf(y0, sm.fext[k][1]);
+            x1 = fmaxf(x1, sm.fext[k][2]); y1 = fmaxf(y1, sm.fext[k][3]);
         }
         cm.x0 = x0; cm.y0 = y0;
         cm.sx = (x1 > x0) ? (float)NCELL / (x1 - x0) : 0.f;
         cm.sy = (y1 > y0) ? (float)NCELL / (y1 - y0) : 0.f;
     }
-    for (int j = tid; j < nd; j += NT) {
-        if (!sm.dflag[j]) continue;
-        const Box b = load_box(sm.dbox, Dmax, j);
+    if (mydfl) {
+        const int j = tid;
         const uint32_t bit = 1u << (j & 31);
         const int wd = j >> 5;
-        const int cx0 = cm.cx(b.x1), cx1 = cm.cx(b.x2), cy0 = cm.cy(b.y1), cy1 = cm.cy(b.y2);
-        for (int c = cx0; c <= cx1; ++c) atomicOr(&sm.xmask[c * DW + wd], bit);
-        for (int c = cy0; c <= cy1; ++c) atomicOr(&sm.ymask[c * DW + wd], bit);
+        const int cx0 = cm.cx(mybox.x1), cx1 = cm.cx(mybox.x2), cy0 = cm.cy(mybox.y1), cy1 = cm.cy(mybox.y2);
+        for (int c = cx0; c <= cx1; ++c) atomicOr(&sm.xmask[c][wd], bit);
+        for (int c = cy0; c <= cy1; ++c) atomicOr(&sm.ymask[c][wd], bit);
     }
     __syncthreads();
 
-    PassCost cost;
-    cost.tbox = sm.tbox; cost.dbox = sm.dbox; cost.dconf = sm.dconf; cost.rowtype = sm.rowtype; cost.Tmax = Tmax; cost.Dmax = Dmax;
+    PassCost<KIND, SM> cost;
+    cost.sm = &sm;
     PassLimit lim;
     lim.rowtype = sm.rowtype;
 
     // ---- first association: pool x high detections, fused score, limit match_thresh ----
     cost.fuseA = true; cost.fuseB = true;
     lim.limA = p.match_thresh; lim.limB = p.match_thresh;
-    build_graph<NT>(sm, lw, Tmax, Dmax, n, words, cm, cost, lim);
+    build_graph_row<KIND>(sm, t, n, words, cm, cost, lim);
+    __syncthreads();
     lap_sparse_solve<NT>(lw, n, words, lim, cost);
-    apply_matches<NT, KIND>(sm, Tmax, Dmax, n, frame);
+    bool matched1 = false;
+    if (t < n && sm.rowtype[t] != RT_NONE) {
+        const int j = sm.xr[t];
+        if (j >= 0) { matched1 = true; sm.match[t] = (short)j; sm.dflag[j] |= DF_USED; }
+    }
     __syncthreads();
 
     // ---- second pass: two independent problems solved together (disjoint rows AND columns):
     //   A: still-Tracked leftovers x low detections, plain IoU, limit 0.5   (byte_tracker.py:198-226)
     //   B: unconfirmed x remaining high detections, fused score, limit 0.7  (byte_tracker.py:228-240)
-    for (int t = tid; t < n; t += NT) {
-        const bool matched = sm.rowtype[t] != RT_NONE && sm.xr[t] >= 0;
-        const int role = sm.role[t];
-        sm.rowtype[t] = (role == ROLE_TRACKED && !matched) ? RT_A : (role == ROLE_UNCONF ? RT_B : RT_NONE);
+    if (t < n) sm.rowtype[t] = (role == ROLE_TRACKED && !matched1) ? RT_A : (role == ROLE_UNCONF ? RT_B : RT_NONE);
+    if (tid < words * 32) {
+        const int dfl = tid < nd ? sm.dflag[tid] : 0;
+        const uint32_t ma = __ballot_sync(0xffffffffu, dfl == DF_LOW);
+        const uint32_t mb = __ballot_sync(0xffffffffu, dfl == DF_HIGH);     // high and not used
+        if (lane == 0) { sm.colbitsA[tid >> 5] = ma; sm.colbitsB[tid >> 5] = mb; }
     }
-    for (int j = tid; j < words * 32; j += NT) {
-        const int fl = j < nd ? sm.dflag[j] : 0;
-        const uint32_t ma = __ballot_sync(0xffffffffu, fl == DF_LOW);
-        const uint32_t mb = __ballot_sync(0xffffffffu, fl == DF_HIGH);      // high and not used
-        if (lane == 0) { sm.colbitsA[j >> 5] = ma; sm.colbitsB[j >> 5] = mb; }
-    }
-    __syncthreads();                 // xr of pass 1 fully consumed before lap_prepare resets it
     lap_prepare<NT>(lw, n, words);
     __syncthreads();
     cost.fuseA = false; cost.fuseB = true;
     lim.limA = p.second_thresh; lim.limB = p.unconf_thresh;
-    build_graph<NT>(sm, lw, Tmax, Dmax, n, words, cm, cost, lim);
-    lap_sparse_solve<NT>(lw, n, words, lim, cost);
-    apply_matches<NT, KIND>(sm, Tmax, Dmax, n, frame);
+    build_graph_row<KIND>(sm, t, n, words, cm, cost, lim);
     __syncthreads();
+    lap_sparse_solve<NT>(lw, n, words, lim, cost);
 
-    // ---- lifecycle: lost / removed / aged-out, list categories (byte_tracker.py:222-268) ----
-    for (int t = tid; t < n; t += NT) {
-        int fl = sm.ti[B200_TI_FLAGS * Tmax + t];
-        const int role = sm.role[t];
-        const bool unmatched_now = sm.rowtype[t] != RT_NONE && sm.xr[t] < 0;
-        if (role == ROLE_TRACKED && unmatched_now) fl = (fl & ~3) | B200_ST_LOST;       // mark_lost; frame_id stays = end_frame
-        if (role == ROLE_UNCONF && unmatched_now) fl = (fl & ~3) | B200_ST_REMOVED;     // mark_removed
+    // ---- deferred Kalman work + lifecycle, thread t (byte_tracker.py:64-98, :222-253) --------
+    // covariance: HBM -> registers (first and only read), predict, update; it stays in
+    // registers until the final write.
+    KfState ks;
+    int tid_id = 0, len = 0, det_ind = 0, start = 0;
+    double score = 0.0, cls = 0.0;
+    int cat = CAT_NONE;
+    if (t < n) {
+        bool unmatched2 = false;
+        int j = sm.match[t];
+        if (sm.rowtype[t] != RT_NONE) {
+            j = sm.xr[t];
+            if (j >= 0) sm.dflag[j] |= DF_USED; else unmatched2 = true;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ks.pp[i] = gf[(B200_TF_COV + 3 * i + 0) * TMAX + t];
+            ks.pv[i] = gf[(B200_TF_COV + 3 * i + 1) * TMAX + t];
+            ks.vv[i] = gf[(B200_TF_COV + 3 * i + 2) * TMAX + t];
+        }
+        tid_id = gi[B200_TI_ID * TMAX + t];
+        len = gi[B200_TI_LEN * TMAX + t];
+        det_ind = gi[B200_TI_DET * TMAX + t];
+        score = gf[B200_TF_SCORE * TMAX + t];
+        cls = gf[B200_TF_CLS * TMAX + t];
+        start = sm.start_t[t];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ks.m[c] = sm.mean[c][t];
+        if (role != ROLE_UNCONF) {
+            // covariance half of multi_predict; the noise uses the pre-motion w / h
+            double ref4[4] = {0.0, 0.0, ref_w, ref_h};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                double sp, sv;
+                if (KIND != KF_XYWH && i == 2) { sp = 1e-2; sv = 1e-5; }
+                else { const double r = kf_ref<KIND>(ref4, i); sp = xmul(KF_W_POS, r); sv = xmul(KF_W_VEL, r); }
+                const double a = xadd(ks.pp[i], ks.pv[i]);
+                const double b = xadd(ks.pv[i], ks.vv[i]);
+                ks.pp[i] = xadd(xadd(a, b), xmul(sp, sp));
+                ks.pv[i] = b;
+                ks.vv[i] = xadd(ks.vv[i], xmul(sv, sv));
+            }
+        }
+        const int st0 = fl & 3;
+        if (j >= 0) {                                   // STrack.update / re_activate
+            double z[4];
+            det_measurement<KIND>(sm, j, z);
+            kf_update<KIND>(ks, z);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) sm.mean[c][t] = ks.m[c];
+            len = (st0 == B200_ST_TRACKED) ? len + 1 : 0;
+            frame_t = frame;
+            det_ind = j;
+            score = sm.dconf[j];
+            cls = sm.dcls[j];
+            fl = (fl & ~3) | B200_ST_TRACKED | B200_FLAG_ACTIVATED;
+        } else if (unmatched2) {
+            fl = (fl & ~3) | (role == ROLE_TRACKED ? B200_ST_LOST : B200_ST_REMOVED);   // mark_lost / mark_removed
+        }
         int st = fl & 3;
         const bool sticky_old = fl & B200_FLAG_STICKY;      // id already in removed_stracks
-        int cat = CAT_NONE;
         if (role == ROLE_LOST) {
             if (st == B200_ST_TRACKED) cat = CAT_REFOUND;
             else {
-                if (frame - sm.ti[B200_TI_FRAME * Tmax + t] > p.max_time_lost) {
+                if (frame - frame_t > p.max_time_lost) {
                     fl = (fl & ~3) | B200_ST_REMOVED;       // stays listed one more frame (removed-lag)
                     st = B200_ST_REMOVED;
                 }
@@ -422,201 +409,210 @@ __global__ void __launch_bounds__(NT) bytetrack_step_kernel(const StepParams p) 
             }
         } else if (st == B200_ST_TRACKED) cat = CAT_KEEP;
         else if (st == B200_ST_LOST && !sticky_old) cat = CAT_LOST_NEW;
-        sm.ti[B200_TI_FLAGS * Tmax + t] = fl;
         sm.cat[t] = (unsigned char)cat;
-        if (cat != CAT_NONE) refresh_box<KIND>(sm, Tmax, t);
+        sm.frame_t[t] = frame_t;
     }
     __syncthreads();
 
     // compact list of the new lost list (old entries first, then the newly lost) for the
     // duplicate test; packed counters: [0:16) old-lost, [16:32) new-lost
-    int nLostOld = 0, nLostNew = 0;
+    int nLostList;
     {
-        unsigned long long base = 0;
-        for (int c0 = 0; c0 < n; c0 += NT) {
-            const int t = c0 + tid;
-            const int cat = t < n ? sm.cat[t] : CAT_NONE;
-            const unsigned long long val = (cat == CAT_LOST_OLD ? 1ull : 0ull) | (cat == CAT_LOST_NEW ? (1ull << 16) : 0ull);
-            unsigned long long tot;
-            const unsigned long long ex = block_exscan<NT>(val, sm.scratch, tot) + base;
-            if (cat == CAT_LOST_OLD) sm.lostlist[ex & 0xffff] = (short)t;
-            if (cat == CAT_LOST_NEW) sm.head[(ex >> 16) & 0xffff] = t;      // staged, shifted below
-            base += tot;
-        }
-        nLostOld = (int)(base & 0xffff);
-        nLostNew = (int)((base >> 16) & 0xffff);
-        __syncthreads();
-        for (int k = tid; k < nLostNew; k += NT) sm.lostlist[nLostOld + k] = (short)sm.head[k];
+        const unsigned long long val = (cat == CAT_LOST_OLD ? 1ull : 0ull) | (cat == CAT_LOST_NEW ? (1ull << 16) : 0ull);
+        unsigned long long tot;
+        const unsigned long long ex = block_exscan<NT>(val, sm.scratch, tot);
+        const int nLostOld = (int)(tot & 0xffff);
+        if (cat == CAT_LOST_OLD) sm.lostlist[ex & 0xffff] = (short)t;
+        if (cat == CAT_LOST_NEW) sm.lostlist[nLostOld + ((ex >> 16) & 0xffff)] = (short)t;
+        nLostList = nLostOld + (int)((tot >> 16) & 0xffff);
         __syncthreads();
     }
-    const int nLostList = nLostOld + nLostNew;
+
+    // is detection `tid` the seed of a new track?  (unmatched high detection, byte_tracker.py:242-248)
+    const bool born = tid < nd && (sm.dflag[tid] & (DF_HIGH | DF_USED)) == DF_HIGH && !(sm.dconf[tid] < p.new_thresh);
 
     // ---- remove_duplicate_stracks (byte_tracker.py:312-325): tracked' x lost', 1-iou < 0.15
-    // tracked' = kept slots, new tracks (unmatched high detections), re-found slots
+    // tracked' = kept slots, new tracks, re-found slots
     if (nLostList > 0) {
-        for (int e = tid; e < n + nd; e += NT) {
+        for (int pass = 0; pass < 2; ++pass) {
             Box a;
             int age;
-            if (e < n) {
-                const int cat = sm.cat[e];
+            if (pass == 0) {
                 if (cat != CAT_KEEP && cat != CAT_REFOUND) continue;
-                a = load_box(sm.tbox, Tmax, e);
-                age = sm.ti[B200_TI_FRAME * Tmax + e] - sm.ti[B200_TI_START * Tmax + e];
+                a = track_box<KIND>(sm, t);
+                age = frame_t - start;
             } else {
-                const int j = e - n;
-                if ((sm.dflag[j] & (DF_HIGH | DF_USED)) != DF_HIGH) continue;
-                if (sm.dconf[j] < p.new_thresh) continue;
+                if (!born) continue;
                 double z[4];
-                det_measurement<KIND>(sm, Dmax, j, z);
+                det_measurement<KIND>(sm, tid, z);
                 a = mean_to_box<KIND>(z[0], z[1], z[2], z[3]);
                 age = 0;
             }
             bool dropme = false;
             for (int k = 0; k < nLostList; ++k) {
                 const int q = sm.lostlist[k];
-                const Box b = load_box(sm.tbox, Tmax, q);
+                const Box b = track_box<KIND>(sm, q);
                 if (!box_overlap(a, b)) continue;
                 if (xsub(1.0, box_iou(a, b)) < p.dup_thresh) {
-                    const int ageq = sm.ti[B200_TI_FRAME * Tmax + q] - sm.ti[B200_TI_START * Tmax + q];
+                    const int ageq = sm.frame_t[q] - sm.start_t[q];
                     if (age > ageq) sm.drop[q] = 1; else dropme = true;
                 }
             }
-            if (dropme) sm.drop[e < n ? e : Tmax + (e - n)] = 1;
+            if (dropme) sm.drop[pass == 0 ? t : TMAX + tid] = 1;
         }
         __syncthreads();
     }
 
-    // ---- destinations.  One packed scan (10-bit fields):
+    // ---- destinations.  One packed scan (10-bit fields), element i = slot i and detection i:
     //   slots: [0) keep, [10) refound, [20) lostOld, [30) lostNew ; dets: [40) born kept, [50) born (all)
     // Every CAT_KEEP / CAT_REFOUND entry is activated, so output rows = keep ++ born (frame 1 only) ++ refound.
     const bool born_active = frame == 1;                 // STrack.activate: is_activated only on frame 1
-    double* gf = p.state_f + (size_t)s * B200_NF * Tmax;
-    int* gi = p.state_i + (size_t)s * B200_NI * Tmax;
-    double* gout = p.out + (size_t)s * Tmax * 8;
-    const int m = max(n, nd);
-    auto elem_val = [&](int i) -> unsigned long long {
-        unsigned long long v = 0ull;
-        if (i < n && !sm.drop[i]) {
-            const int cat = sm.cat[i];
-            if (cat != CAT_NONE) v = 1ull << (10 * (cat - 1));
-        }
-        if (i < nd && (sm.dflag[i] & (DF_HIGH | DF_USED)) == DF_HIGH && !(sm.dconf[i] < p.new_thresh)) {
-            v |= 1ull << 50;                              // activate() ran: consumes an id even if dropped below
-            if (!sm.drop[Tmax + i]) v |= 1ull << 40;
-        }
-        return v;
-    };
-    // block totals first (segment bases depend on them): warp reduce + shared atomics
-    if (tid == 0) sm.scratch[36] = 0ull;
-    __syncthreads();
-    {
-        unsigned long long acc = 0ull;
-        for (int i = tid; i < m; i += NT) acc += elem_val(i);
-#pragma unroll
-        for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
-        if (lane == 0 && acc) atomicAdd(&sm.scratch[36], acc);
+    double* wf = p.state_f + (size_t)s * B200_NF * TMAX;
+    int* wi = p.state_i + (size_t)s * B200_NI * TMAX;
+    double* gout = p.out + (size_t)s * p.max_tracks * 8;
+    const int out_cap = p.max_tracks;
+    unsigned long long val = 0ull;
+    if (cat != CAT_NONE && !sm.drop[t]) val = 1ull << (10 * (cat - 1));
+    if (born) {
+        val |= 1ull << 50;                                // activate() ran: consumes an id even if dropped
+        if (!sm.drop[TMAX + tid]) val |= 1ull << 40;
     }
-    __syncthreads();
-    const unsigned long long totals = sm.scratch[36];
+    unsigned long long totals;
+    const unsigned long long ex = block_exscan<NT>(val, sm.scratch, totals);
     const int totKeep = (int)(totals & 1023), totRef = (int)((totals >> 10) & 1023);
     const int totLostOld = (int)((totals >> 20) & 1023), totLostNew = (int)((totals >> 30) & 1023);
     const int totBorn = (int)((totals >> 40) & 1023), totBornAll = (int)((totals >> 50) & 1023);
     const int newT = totKeep + totBorn + totRef;
     const int newL = totLostOld + totLostNew;
-    if (newT + newL > Tmax) err |= B200_ERR_TRACK_OVERFLOW;
+    if (newT + newL > min(TMAX, p.max_tracks)) err |= B200_ERR_TRACK_OVERFLOW;
+    const int cap = min(TMAX, p.max_tracks);
     const int rowsBorn = born_active ? totBorn : 0;
 
-    unsigned long long base = 0;
-    for (int c0 = 0; c0 < m; c0 += NT) {
-        const int i = c0 + tid;
-        const unsigned long long val = elem_val(i);
-        unsigned long long tot;
-        const unsigned long long ex = block_exscan<NT>(val, sm.scratch, tot) + base;
-        base += tot;
-        const unsigned long long sv = val & ((1ull << 40) - 1);
-        if (sv) {
-            const int cat = sm.cat[i];
-            int dst, orow = -1;
-            if (cat == CAT_KEEP) { dst = (int)(ex & 1023); orow = dst; }
-            else if (cat == CAT_REFOUND) { const int k = (int)((ex >> 10) & 1023); dst = totKeep + totBorn + k; orow = totKeep + rowsBorn + k; }
-            else if (cat == CAT_LOST_OLD) dst = newT + (int)((ex >> 20) & 1023);
-            else dst = newT + totLostOld + (int)((ex >> 30) & 1023);
-            if (dst < Tmax) {
+    if (val & ((1ull << 40) - 1)) {
+        int dst, orow = -1;
+        if (cat == CAT_KEEP) { dst = (int)(ex & 1023); orow = dst; }
+        else if (cat == CAT_REFOUND) { const int k = (int)((ex >> 10) & 1023); dst = totKeep + totBorn + k; orow = totKeep + rowsBorn + k; }
+        else if (cat == CAT_LOST_OLD) dst = newT + (int)((ex >> 20) & 1023);
+        else dst = newT + totLostOld + (int)((ex >> 30) & 1023);
+        if (dst < cap) {
 #pragma unroll
-                for (int c = 0; c < B200_NF; ++c) gf[c * Tmax + dst] = sm.tf[c * Tmax + i];
+            for (int c = 0; c < 8; ++c) wf[(B200_TF_MEAN + c) * TMAX + dst] = ks.m[c];
 #pragma unroll
-                for (int c = 0; c < B200_NI; ++c) gi[c * Tmax + dst] = sm.ti[c * Tmax + i];
+            for (int i = 0; i < 4; ++i) {
+                wf[(B200_TF_COV + 3 * i + 0) * TMAX + dst] = ks.pp[i];
+                wf[(B200_TF_COV + 3 * i + 1) * TMAX + dst] = ks.pv[i];
+                wf[(B200_TF_COV + 3 * i + 2) * TMAX + dst] = ks.vv[i];
             }
-            if (orow >= 0 && orow < Tmax) {
-                double* o = gout + (size_t)orow * 8;
-                o[0] = sm.tbox[i]; o[1] = sm.tbox[Tmax + i]; o[2] = sm.tbox[2 * Tmax + i]; o[3] = sm.tbox[3 * Tmax + i];
-                o[4] = (double)sm.ti[B200_TI_ID * Tmax + i];
-                o[5] = sm.tf[B200_TF_SCORE * Tmax + i];
-                o[6] = sm.tf[B200_TF_CLS * Tmax + i];
-                o[7] = (double)sm.ti[B200_TI_DET * Tmax + i];
-            }
+            wf[B200_TF_SCORE * TMAX + dst] = score;
+            wf[B200_TF_CLS * TMAX + dst] = cls;
+            wi[B200_TI_ID * TMAX + dst] = tid_id;
+            wi[B200_TI_FRAME * TMAX + dst] = frame_t;
+            wi[B200_TI_START * TMAX + dst] = start;
+            wi[B200_TI_LEN * TMAX + dst] = len;
+            wi[B200_TI_DET * TMAX + dst] = det_ind;
+            wi[B200_TI_FLAGS * TMAX + dst] = fl;
         }
-        if (val & (1ull << 40)) {                       // STrack.activate (byte_tracker.py:50-62)
-            const int j = i;
-            const int k = (int)((ex >> 40) & 1023);
-            const int dst = totKeep + k;
-            const int id = id0 + (int)((ex >> 50) & 1023) + 1;
-            double z[4];
-            det_measurement<KIND>(sm, Dmax, j, z);
-            KfState ks;
-            kf_initiate<KIND>(z, ks);
-            if (dst < Tmax) {
+        if (orow >= 0 && orow < out_cap) {
+            const Box b = mean_to_box<KIND>(ks.m[0], ks.m[1], ks.m[2], ks.m[3]);
+            double* o = gout + (size_t)orow * 8;
+            o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
+            o[4] = (double)tid_id; o[5] = score; o[6] = cls; o[7] = (double)det_ind;
+        }
+    }
+    if (val & (1ull << 40)) {                           // STrack.activate (byte_tracker.py:50-62)
+        const int j = tid;
+        const int k = (int)((ex >> 40) & 1023);
+        const int dst = totKeep + k;
+        const int id = id0 + (int)((ex >> 50) & 1023) + 1;
+        double z[4];
+        det_measurement<KIND>(sm, j, z);
+        KfState kn;
+        kf_initiate<KIND>(z, kn);
+        if (dst < cap) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) gf[(B200_TF_MEAN + c) * Tmax + dst] = ks.m[c];
+            for (int c = 0; c < 8; ++c) wf[(B200_TF_MEAN + c) * TMAX + dst] = kn.m[c];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    gf[(B200_TF_COV + 3 * a + 0) * Tmax + dst] = ks.pp[a];
-                    gf[(B200_TF_COV + 3 * a + 1) * Tmax + dst] = ks.pv[a];
-                    gf[(B200_TF_COV + 3 * a + 2) * Tmax + dst] = ks.vv[a];
-                }
-                gf[B200_TF_SCORE * Tmax + dst] = sm.dconf[j];
-                gf[B200_TF_CLS * Tmax + dst] = sm.dcls[j];
-                gi[B200_TI_ID * Tmax + dst] = id;
-                gi[B200_TI_FRAME * Tmax + dst] = frame;
-                gi[B200_TI_START * Tmax + dst] = frame;
-                gi[B200_TI_LEN * Tmax + dst] = 0;
-                gi[B200_TI_DET * Tmax + dst] = j;
-                gi[B200_TI_FLAGS * Tmax + dst] = B200_ST_TRACKED | (born_active ? B200_FLAG_ACTIVATED : 0);
+            for (int a = 0; a < 4; ++a) {
+                wf[(B200_TF_COV + 3 * a + 0) * TMAX + dst] = kn.pp[a];
+                wf[(B200_TF_COV + 3 * a + 1) * TMAX + dst] = kn.pv[a];
+                wf[(B200_TF_COV + 3 * a + 2) * TMAX + dst] = kn.vv[a];
             }
-            if (born_active) {
-                const int orow = totKeep + k;
-                if (orow < Tmax) {
-                    const Box b = mean_to_box<KIND>(z[0], z[1], z[2], z[3]);
-                    double* o = gout + (size_t)orow * 8;
-                    o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
-                    o[4] = (double)id; o[5] = sm.dconf[j]; o[6] = sm.dcls[j]; o[7] = (double)j;
-                }
+            wf[B200_TF_SCORE * TMAX + dst] = sm.dconf[j];
+            wf[B200_TF_CLS * TMAX + dst] = sm.dcls[j];
+            wi[B200_TI_ID * TMAX + dst] = id;
+            wi[B200_TI_FRAME * TMAX + dst] = frame;
+            wi[B200_TI_START * TMAX + dst] = frame;
+            wi[B200_TI_LEN * TMAX + dst] = 0;
+            wi[B200_TI_DET * TMAX + dst] = j;
+            wi[B200_TI_FLAGS * TMAX + dst] = B200_ST_TRACKED | (born_active ? B200_FLAG_ACTIVATED : 0);
+        }
+        if (born_active) {
+            const int orow = totKeep + k;
+            if (orow < out_cap) {
+                const Box b = mean_to_box<KIND>(z[0], z[1], z[2], z[3]);
+                double* o = gout + (size_t)orow * 8;
+                o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
+                o[4] = (double)id; o[5] = sm.dconf[j]; o[6] = sm.dcls[j]; o[7] = (double)j;
             }
         }
     }
     if (tid == 0) {
-        counts[0] = min(newT, Tmax);
-        counts[1] = min(newL, Tmax - min(newT, Tmax));
+        counts[0] = min(newT, cap);
+        counts[1] = min(newL, cap - min(newT, cap));
         counts[2] = id0 + totBornAll;
         counts[3] = frame;
-        p.nout[s] = min(totKeep + rowsBorn + totRef, Tmax);
+        p.nout[s] = min(totKeep + rowsBorn + totRef, out_cap);
         p.track_updates[s] += (unsigned long long)n;
         if (err) atomicOr(p.err, err);
     }
 }
 
-}  // namespace
+struct Variant { int tmax, dmax; };
+constexpr Variant kVariants[] = {{64, 64}, {128, 128}, {256, 224}, {256, 256}, {512, 512}};
 
-size_t bytetrack_step_smem(int Tmax, int Dmax) { return carve(nullptr, nullptr, Tmax, Dmax); }
-
-cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, cudaStream_t stream) {
-    constexpr int NT = 256;
-    const size_t smem = bytetrack_step_smem(p.max_tracks, p.max_dets);
-    auto kern = kf_kind == KF_XYWH ? bytetrack_step_kernel<NT, KF_XYWH> : bytetrack_step_kernel<NT, KF_XYAH>;
+template <int KIND, int TMAX, int DMAX>
+cudaError_t launch_variant(const StepParams& p, cudaStream_t stream) {
+    auto kern = bytetrack_step_kernel<TMAX, KIND, TMAX, DMAX>;
+    const size_t smem = sizeof(StepSmem<TMAX, DMAX>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<p.n_streams, NT, smem, stream>>>(p);
+    kern<<<p.n_streams, TMAX, smem, stream>>>(p);
     return cudaGetLastError();
+}
+
+template <int KIND>
+cudaError_t launch_kind(const StepParams& p, int v, cudaStream_t stream) {
+    switch (v) {
+        case 0: return launch_variant<KIND, 64, 64>(p, stream);
+        case 1: return launch_variant<KIND, 128, 128>(p, stream);
+        case 2: return launch_variant<KIND, 256, 224>(p, stream);
+        case 3: return launch_variant<KIND, 256, 256>(p, stream);
+        case 4: return launch_variant<KIND, 512, 512>(p, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
+
+int bytetrack_step_variant(int max_tracks, int max_dets) {
+    for (int v = 0; v < (int)(sizeof(kVariants) / sizeof(kVariants[0])); ++v)
+        if (max_tracks <= kVariants[v].tmax && max_dets <= kVariants[v].dmax) return v;
+    return -1;
+}
+int bytetrack_step_tmax(int variant) { return kVariants[variant].tmax; }
+size_t bytetrack_step_smem(int variant) {
+    switch (variant) {
+        case 0: return sizeof(StepSmem<64, 64>);
+        case 1: return sizeof(StepSmem<128, 128>);
+        case 2: return sizeof(StepSmem<256, 224>);
+        case 3: return sizeof(StepSmem<256, 256>);
+        case 4: return sizeof(StepSmem<512, 512>);
+    }
+    return 0;
+}
+
+cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, int variant, cudaStream_t stream) {
+    return kf_kind == KF_XYWH ? launch_kind<KF_XYWH>(p, variant, stream) : launch_kind<KF_XYAH>(p, variant, stream);
 }
 
 }  // namespace b200

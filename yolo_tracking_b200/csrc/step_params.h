@@ -32,7 +32,12 @@ struct StepParams {
     int* nout;                // [S]
 };
 
-size_t bytetrack_step_smem(int Tmax, int Dmax);
-cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, cudaStream_t stream);
+// The step kernel is compiled for a few (slot capacity, detection capacity) pairs; a context
+// uses the smallest one that covers its max_tracks / max_dets.  The device state is laid out
+// with the variant's slot capacity as stride.
+int bytetrack_step_variant(int max_tracks, int max_dets);   // -1: nothing large enough
+int bytetrack_step_tmax(int variant);
+size_t bytetrack_step_smem(int variant);
+cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, int variant, cudaStream_t stream);
 
 }  // namespace b200
