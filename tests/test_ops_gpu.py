@@ -1,0 +1,124 @@
+"""GPU parity of the operator-level C-ABI (Kalman filters, box costs, cosine distance, lapjv)
+against the golden vectors of the live reference and against the oracle."""
+import numpy as np
+import pytest
+
+from _util import assert_close, load_golden
+
+pytestmark = pytest.mark.gpu
+
+KINDS = {"xyah": 0, "xywh": 1, "xyah_conf": 2}
+
+
+@pytest.mark.parametrize("kind", ["xyah", "xywh", "xyah_conf"])
+def test_kalman_ops_match_reference(kind):
+    from yolo_tracking_b200 import _ops
+    g = load_golden("kf_" + kind)
+    k = KINDS[kind]
+    m, c = _ops.kf_initiate(k, g["z0"])
+    assert_close(m, g["init_mean"], what="initiate mean")
+    assert_close(c, g["init_cov"], what="initiate cov")
+    for s in range(g["z"].shape[0]):
+        m, c = _ops.kf_predict(k, m, c)
+        assert_close(m, g["pred_mean"][s], what=f"predict mean {s}")
+        assert_close(c, g["pred_cov"][s], what=f"predict cov {s}")
+        conf = g["conf"][s] if kind == "xyah_conf" else None
+        pm, pc = _ops.kf_project(k, m, c, conf)
+        assert_close(pm, g["proj_mean"][s], what="project mean")
+        assert_close(pc, g["proj_cov"][s], what="project cov")
+        m, c = _ops.kf_update(k, m, c, g["z"][s], conf)
+        assert_close(m, g["upd_mean"][s], what=f"update mean {s}")
+        assert_close(c, g["upd_cov"][s], abs_=1e-10, what=f"update cov {s}")
+    pm_, pc_ = g["pred_mean"][-1], g["pred_cov"][-1]
+    conf0 = np.zeros(len(pm_)) if kind == "xyah_conf" else None
+    assert_close(_ops.kf_gating_distance(k, pm_, pc_, g["gate_meas"], False, "maha", conf0), g["gate_maha4"], what="maha4")
+    assert_close(_ops.kf_gating_distance(k, pm_, pc_, g["gate_meas"], True, "maha", conf0), g["gate_maha2"], what="maha2")
+    if kind != "xyah_conf":
+        assert_close(_ops.kf_gating_distance(k, pm_, pc_, g["gate_meas"], False, "gaussian"), g["gate_gauss"], what="gauss")
+
+
+def test_kalman_ops_dense_covariance_vs_oracle():
+    """A dense (not block-sparse) SPD covariance, as after an external camera-motion warp."""
+    from oracle import kalman
+    from yolo_tracking_b200 import _ops
+    rng = np.random.default_rng(3)
+    n = 200
+    A = rng.normal(size=(n, 8, 8))
+    cov = A @ np.transpose(A, (0, 2, 1)) + 8 * np.eye(8)
+    mean = rng.normal(size=(n, 8)) * 10 + np.array([500, 400, 0.5, 120, 0, 0, 0, 0])
+    z = mean[:, :4] + rng.normal(size=(n, 4))
+    for kind in ("xyah", "xywh"):
+        k = KINDS[kind]
+        pm, pc = _ops.kf_predict(k, mean, cov)
+        om, oc = kalman.predict(kind, mean, cov)
+        assert_close(pm, om); assert_close(pc, oc)
+        um, uc = _ops.kf_update(k, om, oc, z)
+        qm, qc = kalman.update(kind, om, oc, z)
+        assert_close(um, qm, rel=1e-9, abs_=1e-9); assert_close(uc, qc, rel=1e-9, abs_=1e-9)
+        d = _ops.kf_gating_distance(k, om[:5], oc[:5], z[:50])
+        for i in range(5):
+            assert_close(d[i], kalman.gating_distance(kind, om[i], oc[i], z[:50]), rel=1e-9, abs_=1e-9)
+
+
+def test_box_costs_bit_exact():
+    from yolo_tracking_b200 import _ops
+    g = load_golden("costs")
+    a, b = g["a"], g["b"]
+    for name in ("iou", "giou", "diou"):
+        assert np.array_equal(_ops.box_similarity(name, a, b), g[name]), name      # same op order -> same bits
+    assert_close(_ops.box_similarity("ciou", a, b), g["ciou"], rel=1e-12)          # atan differs by <= 1-2 ulp
+    assert np.array_equal(_ops.box_similarity("centroid", a, b, 640, 480), g["centroid"])
+    assert np.array_equal(_ops.iou_distance(a, b), g["iou_distance"])
+    assert np.array_equal(_ops.iou_distance(a, b, g["score"]), g["fuse_score"])
+    with pytest.raises(ValueError):
+        _ops.box_similarity("nosuch", a, b)
+
+
+def test_embedding_distance():
+    from yolo_tracking_b200 import _ops
+    g = load_golden("costs")
+    got = _ops.embedding_distance(g["feat_a"], g["feat_b"])
+    assert_close(got, g["embedding_distance"], rel=1e-9, abs_=1e-12)
+
+
+def test_lapjv_known_answer_and_shapes():
+    from yolo_tracking_b200 import _ops
+    from yolo_tracking_b200.utils import association, matching
+    x, y = _ops.lapjv(np.array([[0.1, 0.79], [0.2, 2.0]]), 0.8)
+    assert x.tolist() == [0, -1] and y.tolist() == [0, -1]
+    m, ua, ub = matching.linear_assignment(np.array([[0.1, 0.79], [0.2, 2.0]]), 0.8)
+    assert m.tolist() == [[0, 0]] and list(ua) == [1] and list(ub) == [1]
+    m, ua, ub = matching.linear_assignment(np.zeros((0, 3)), 0.8)
+    assert m.shape == (0, 2) and list(ua) == [] and list(ub) == [0, 1, 2]
+    assert association.linear_assignment(np.zeros((0, 3))).shape == (0, 2)
+
+
+@pytest.mark.parametrize("rows,cols,limit,density", [
+    (60, 50, 0.8, 0.05), (200, 200, 0.8, 0.02), (200, 180, 0.5, 0.2), (37, 91, 0.7, 1.0),
+    (64, 64, np.inf, 1.0), (200, 150, np.inf, 1.0), (90, 200, np.inf, 1.0), (1, 1, 0.5, 1.0), (5, 1, np.inf, 1.0),
+])
+def test_lapjv_random_vs_oracle(rows, cols, limit, density):
+    from oracle.lap import lapjv_extended
+    from yolo_tracking_b200 import _ops
+    rng = np.random.default_rng(rows * 1000 + cols)
+    B = 6
+    cost = rng.random((B, rows, cols))
+    if density < 1.0:                       # most pairs are far apart: cost 1.0 > limit, like iou_distance
+        cost = np.where(rng.random((B, rows, cols)) < density, cost, 1.0)
+    x, y = _ops.lapjv(cost, limit)
+    for b in range(B):
+        _, ox, oy = lapjv_extended(cost[b], limit)
+        assert np.array_equal(x[b], ox), f"problem {b}: x"
+        assert np.array_equal(y[b], oy), f"problem {b}: y"
+
+
+def test_lapjv_negative_costs_no_limit():
+    """OCSORT calls lapjv on -(iou + angle) without a limit (association.py:171-172)."""
+    from oracle.lap import lapjv_extended
+    from yolo_tracking_b200 import _ops
+    rng = np.random.default_rng(77)
+    cost = -(rng.random((4, 120, 130)) * 1.5)
+    x, y = _ops.lapjv(cost)
+    for b in range(4):
+        _, ox, oy = lapjv_extended(cost[b])
+        assert np.array_equal(x[b], ox) and np.array_equal(y[b], oy)

@@ -1,0 +1,141 @@
+"""numpy-in / numpy-out wrappers over the operator-level C-ABI (b200track_kf_*, _box_similarity,
+_iou_distance, _embedding_distance, _lapjv).  torch only provides the device buffers."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("yolo_tracking_b200 needs a CUDA device (there is no CPU fallback)")
+    return torch
+
+
+def _dev(a, dtype, device=0):
+    torch = _torch()
+    arr = np.ascontiguousarray(a, dtype=dtype)
+    return torch.from_numpy(arr).to(f"cuda:{device}")
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _sync_check(rc):
+    _lib.check(rc)
+    _torch().cuda.synchronize()
+
+
+def kf_initiate(kind, z):
+    lib = _lib.load()
+    torch = _torch()
+    z = np.asarray(z, dtype=np.float64).reshape(-1, 4)
+    n = len(z)
+    dz = _dev(z, np.float64)
+    mean = torch.empty((n, 8), dtype=torch.float64, device=dz.device)
+    cov = torch.empty((n, 8, 8), dtype=torch.float64, device=dz.device)
+    _sync_check(lib.b200track_kf_initiate(kind, n, _p(dz), _p(mean), _p(cov), None))
+    return mean.cpu().numpy(), cov.cpu().numpy()
+
+
+def kf_predict(kind, mean, cov):
+    lib = _lib.load()
+    m = _dev(np.asarray(mean).reshape(-1, 8), np.float64)
+    c = _dev(np.asarray(cov).reshape(-1, 8, 8), np.float64)
+    _sync_check(lib.b200track_kf_predict(kind, m.shape[0], _p(m), _p(c), None))
+    return m.cpu().numpy(), c.cpu().numpy()
+
+
+def kf_project(kind, mean, cov, conf=None):
+    lib = _lib.load()
+    torch = _torch()
+    m = _dev(np.asarray(mean).reshape(-1, 8), np.float64)
+    c = _dev(np.asarray(cov).reshape(-1, 8, 8), np.float64)
+    n = m.shape[0]
+    cf = _dev(np.broadcast_to(np.asarray(conf, dtype=np.float64), (n,)), np.float64) if conf is not None else None
+    pm = torch.empty((n, 4), dtype=torch.float64, device=m.device)
+    pc = torch.empty((n, 4, 4), dtype=torch.float64, device=m.device)
+    _sync_check(lib.b200track_kf_project(kind, n, _p(m), _p(c), _p(cf), _p(pm), _p(pc), None))
+    return pm.cpu().numpy(), pc.cpu().numpy()
+
+
+def kf_update(kind, mean, cov, z, conf=None):
+    lib = _lib.load()
+    m = _dev(np.asarray(mean).reshape(-1, 8), np.float64)
+    c = _dev(np.asarray(cov).reshape(-1, 8, 8), np.float64)
+    n = m.shape[0]
+    dz = _dev(np.asarray(z).reshape(-1, 4), np.float64)
+    cf = _dev(np.broadcast_to(np.asarray(conf, dtype=np.float64), (n,)), np.float64) if conf is not None else None
+    _sync_check(lib.b200track_kf_update(kind, n, _p(m), _p(c), _p(dz), _p(cf), None))
+    return m.cpu().numpy(), c.cpu().numpy()
+
+
+def kf_gating_distance(kind, mean, cov, meas, only_position=False, metric="maha", conf=None):
+    if metric not in ("maha", "gaussian"):
+        raise ValueError("invalid distance metric")
+    lib = _lib.load()
+    torch = _torch()
+    m = _dev(np.asarray(mean).reshape(-1, 8), np.float64)
+    c = _dev(np.asarray(cov).reshape(-1, 8, 8), np.float64)
+    z = _dev(np.asarray(meas).reshape(-1, 4), np.float64)
+    T, D = m.shape[0], z.shape[0]
+    cf = _dev(np.broadcast_to(np.asarray(conf, dtype=np.float64), (T,)), np.float64) if conf is not None else None
+    out = torch.empty((T, D), dtype=torch.float64, device=m.device)
+    _sync_check(lib.b200track_kf_gating_distance(kind, T, D, _p(m), _p(c), _p(z), int(bool(only_position)),
+                                                 0 if metric == "maha" else 1, _p(cf), _p(out), None))
+    return out.cpu().numpy()
+
+
+def box_similarity(name, a, b, w=0.0, h=0.0):
+    if name not in _lib.SIM:
+        raise ValueError("Invalid function specified. Must be either '(g,d,c, )iou_batch' or 'centroid_batch'.")
+    lib = _lib.load()
+    torch = _torch()
+    da = _dev(np.asarray(a, dtype=np.float64).reshape(-1, 4), np.float64)
+    db = _dev(np.asarray(b, dtype=np.float64).reshape(-1, 4), np.float64)
+    out = torch.empty((da.shape[0], db.shape[0]), dtype=torch.float64, device=da.device)
+    _sync_check(lib.b200track_box_similarity(_lib.SIM[name], da.shape[0], db.shape[0], _p(da), _p(db), float(w), float(h),
+                                             _p(out), None))
+    return out.cpu().numpy()
+
+
+def iou_distance(a, b, score=None):
+    lib = _lib.load()
+    torch = _torch()
+    da = _dev(np.asarray(a, dtype=np.float64).reshape(-1, 4), np.float64)
+    db = _dev(np.asarray(b, dtype=np.float64).reshape(-1, 4), np.float64)
+    ds = _dev(score, np.float64) if score is not None else None
+    out = torch.empty((da.shape[0], db.shape[0]), dtype=torch.float64, device=da.device)
+    _sync_check(lib.b200track_iou_distance(da.shape[0], db.shape[0], _p(da), _p(db), _p(ds), _p(out), None))
+    return out.cpu().numpy()
+
+
+def embedding_distance(a, b):
+    lib = _lib.load()
+    torch = _torch()
+    da = _dev(np.asarray(a), np.float32)
+    db = _dev(np.asarray(b), np.float32)
+    out = torch.empty((da.shape[0], db.shape[0]), dtype=torch.float64, device=da.device)
+    _sync_check(lib.b200track_embedding_distance(da.shape[0], db.shape[0], da.shape[1], _p(da), _p(db), _p(out), None))
+    return out.cpu().numpy()
+
+
+def lapjv(cost, cost_limit=np.inf):
+    """cost [R, C] or [B, R, C] -> x [.., R], y [.., C] (int32, -1 = unmatched)."""
+    lib = _lib.load()
+    torch = _torch()
+    cost = np.asarray(cost, dtype=np.float64)
+    single = cost.ndim == 2
+    c3 = cost[None] if single else cost
+    B, R, Cc = c3.shape
+    dc = _dev(c3, np.float64)
+    x = torch.full((B, max(R, 1)), -1, dtype=torch.int32, device=dc.device)
+    y = torch.full((B, max(Cc, 1)), -1, dtype=torch.int32, device=dc.device)
+    _sync_check(lib.b200track_lapjv(B, R, Cc, _p(dc) if R * Cc else None, float(cost_limit), _p(x), _p(y), None))
+    x, y = x.cpu().numpy()[:, :R], y.cpu().numpy()[:, :Cc]
+    return (x[0], y[0]) if single else (x, y)
