@@ -299,6 +299,14 @@ def run_b200(args, rank, world, local_rank):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                tr = json.load(fh)["bytetrack_step_kernel"]
+            if tr["streams"] == S:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         # rank-0 kernel: algorithmic bytes per launch / mean launch duration (events on the launch stream)
         alg_bytes = (tu_dev * B_SLOT + dets_timed * B_DET + rows * B_ROW) / args.steps     # rank-0 shard
         mean_ms = float(step_ms.mean())
@@ -321,7 +329,7 @@ def run_b200(args, rank, world, local_rank):
                     "output_rows_per_step": rows_all / args.steps},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "kernel": "bytetrack_step_kernel", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "alg_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_ms,
                          "bytes_per_track_update": alg_bytes * args.steps / max(1, tu_dev)},
