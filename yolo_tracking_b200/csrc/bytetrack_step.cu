@@ -60,6 +60,11 @@ struct alignas(16) StepSmem {
     float fext[32][4];
     short rnext[TMAX], xr[TMAX], match[TMAX], lostlist[TMAX];
     short yc[DMAX], pred[DMAX], nextc[DMAX], mark[DMAX], scn[DMAX];
+    // candidate edge cache (cost computed once, while the graph is built)
+    static constexpr int ECAP = 2 * TMAX;
+    double ecost[ECAP];
+    short ecol[ECAP], enext[ECAP], ehead[TMAX];
+    int ecount[4];
     unsigned char role[TMAX], rowtype[TMAX], cat[TMAX], drop[TMAX + DMAX], dflag[DMAX];
 };
 
@@ -141,6 +146,7 @@ __device__ __forceinline__ void build_graph_row(SM& sm, int t, int n, int words,
     const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
     const bool fuse = rt == RT_A ? cost.fuseA : cost.fuseB;
     const double limit = rt == RT_A ? lim.limA : lim.limB;
+    int ehead = -1;
 #pragma unroll
     for (int q = 0; q < DWP / 4; ++q) {
         if (q * 4 >= words) break;
@@ -168,12 +174,18 @@ __device__ __forceinline__ void build_graph_row(SM& sm, int t, int n, int words,
                 if (box_overlap(a, d)) {
                     const double v = box_iou(a, d);
                     const double c = fuse ? fused_cost(v, sm.dconf[j]) : xsub(1.0, v);
-                    if (c <= limit) { res |= 1u << b; atomicAdd(&sm.coldeg[j], 1); }
+                    if (c <= limit) {
+                        res |= 1u << b;
+                        atomicAdd(&sm.coldeg[j], 1);
+                        const int e = atomicAdd(&sm.ecount[0], 1);
+                        if (e < SM::ECAP) { sm.ecost[e] = c; sm.ecol[e] = (short)j; sm.enext[e] = (short)ehead; ehead = e; }
+                    }
                 }
             }
             sm.adj[wd][t] = res;
         }
     }
+    sm.ehead[t] = (short)ehead;
 }
 
 template <int NT, int KIND, int TMAX, int DMAX>
@@ -216,6 +228,17 @@ bytetrack_step_kernel(const StepParams p) {
             fl = gi[B200_TI_FLAGS * TMAX + t];
             frame_t = gi[B200_TI_FRAME * TMAX + t];
             sm.start_t[t] = gi[B200_TI_START * TMAX + t];
+        }
+        // the covariance / id / score lines are first used after the association: pull them into L2 now
+        if (t < n && (t & 15) == 0) {
+#pragma unroll
+            for (int c = B200_TF_COV; c < B200_NF; ++c)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(gf + c * TMAX + t));
+        }
+        if (t < n && (t & 31) == 0) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + B200_TI_ID * TMAX + t));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + B200_TI_LEN * TMAX + t));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + B200_TI_DET * TMAX + t));
         }
         for (int i = tid; i < NCELL * DWP; i += NT) { (&sm.xmask[0][0])[i] = 0u; (&sm.ymask[0][0])[i] = 0u; }
         for (int i = tid; i < TMAX + DMAX; i += NT) sm.drop[i] = 0;
@@ -274,6 +297,7 @@ bytetrack_step_kernel(const StepParams p) {
     lw.parent = sm.parent; lw.head = sm.head; lw.rnext = sm.rnext; lw.xr = sm.xr; lw.yc = sm.yc;
     lw.pred = sm.pred; lw.nextc = sm.nextc; lw.mark = sm.mark; lw.scn = sm.scn;
     lw.coldeg = sm.coldeg; lw.ncomplex = sm.ncomplex;
+    lw.ecost = sm.ecost; lw.ecol = sm.ecol; lw.enext = sm.enext; lw.ehead = sm.ehead; lw.ecount = sm.ecount; lw.ecap = SM::ECAP;
     lap_prepare<NT>(lw, n, words);
     __syncthreads();
 
@@ -434,6 +458,16 @@ bytetrack_step_kernel(const StepParams p) {
     // ---- remove_duplicate_stracks (byte_tracker.py:312-325): tracked' x lost', 1-iou < 0.15
     // tracked' = kept slots, new tracks, re-found slots
     if (nLostList > 0) {
+        // boxes / ages of the lost list once, in scratch (u: 4 planes of TMAX/4; coldeg: ages)
+        constexpr int LCAP = TMAX / 4;
+        const bool lost_cached = nLostList <= LCAP && nLostList <= DMAX;
+        if (lost_cached && tid < nLostList) {
+            const int q = sm.lostlist[tid];
+            const Box b = track_box<KIND>(sm, q);
+            sm.u[tid] = b.x1; sm.u[LCAP + tid] = b.y1; sm.u[2 * LCAP + tid] = b.x2; sm.u[3 * LCAP + tid] = b.y2;
+            sm.coldeg[tid] = sm.frame_t[q] - sm.start_t[q];
+        }
+        __syncthreads();
         for (int pass = 0; pass < 2; ++pass) {
             Box a;
             int age;
@@ -450,11 +484,13 @@ bytetrack_step_kernel(const StepParams p) {
             }
             bool dropme = false;
             for (int k = 0; k < nLostList; ++k) {
-                const int q = sm.lostlist[k];
-                const Box b = track_box<KIND>(sm, q);
+                Box b;
+                if (lost_cached) { b.x1 = sm.u[k]; b.y1 = sm.u[LCAP + k]; b.x2 = sm.u[2 * LCAP + k]; b.y2 = sm.u[3 * LCAP + k]; }
+                else b = track_box<KIND>(sm, sm.lostlist[k]);
                 if (!box_overlap(a, b)) continue;
                 if (xsub(1.0, box_iou(a, b)) < p.dup_thresh) {
-                    const int ageq = sm.frame_t[q] - sm.start_t[q];
+                    const int q = sm.lostlist[k];
+                    const int ageq = lost_cached ? sm.coldeg[k] : sm.frame_t[q] - sm.start_t[q];
                     if (age > ageq) sm.drop[q] = 1; else dropme = true;
                 }
             }

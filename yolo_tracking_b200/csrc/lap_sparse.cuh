@@ -40,6 +40,14 @@ struct LapWork {
     short* scn;         // [Dmax]  stamp when scanned
     int* coldeg;        // [Dmax]  candidate rows per column (filled while adj is built)
     int* ncomplex;      // [1]     rows that need the general solver
+    // optional edge cache (costs computed while the graph was built): per-row linked lists in a
+    // fixed pool.  ecount[0] > ecap means the pool overflowed and costs are recomputed instead.
+    double* ecost = nullptr;   // [ecap]
+    short* ecol = nullptr;     // [ecap]
+    short* enext = nullptr;    // [ecap]
+    short* ehead = nullptr;    // [Tmax]
+    int* ecount = nullptr;     // [1]
+    int ecap = 0;
 };
 
 __device__ __forceinline__ int uf_find(volatile int* parent, int x) {
@@ -66,6 +74,7 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 template <class Cost, class Lambda>
 __device__ void lap_insert_row(const LapWork& w, int words, const Lambda& lambda, const Cost& cost, int i0) {
     const short stamp = (short)(i0 + 1);
+    const bool cached = w.ecost != nullptr && *w.ecount <= w.ecap;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     double minVal = 0.0;
     int i = i0;
@@ -77,19 +86,26 @@ __device__ void lap_insert_row(const LapWork& w, int words, const Lambda& lambda
         const double ui = w.u[i];
         const double dd = minVal + lambda(i) - ui;     // row i may stay unmatched at cost lambda(i)
         if (dd < bestDummy) { bestDummy = dd; bestDummyRow = i; }
-        for (int wd = 0; wd < words; ++wd) {
-            uint32_t bits = w.adj[wd * w.Tmax + i];
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int j = wd * 32 + b;
-                if (w.scn[j] == stamp) continue;
-                const double r = minVal + cost(i, j) - ui - w.v[j];
-                if (w.mark[j] != stamp) {
-                    w.mark[j] = stamp; w.dist[j] = r; w.pred[j] = (short)i; w.nextc[j] = -1;
-                    if (rtail < 0) rhead = j; else w.nextc[rtail] = (short)j;
-                    rtail = j;
-                } else if (r < w.dist[j]) { w.dist[j] = r; w.pred[j] = (short)i; }
+        auto relax = [&](int j, double c) {
+            if (w.scn[j] == stamp) return;
+            const double r = minVal + c - ui - w.v[j];
+            if (w.mark[j] != stamp) {
+                w.mark[j] = stamp; w.dist[j] = r; w.pred[j] = (short)i; w.nextc[j] = -1;
+                if (rtail < 0) rhead = j; else w.nextc[rtail] = (short)j;
+                rtail = j;
+            } else if (r < w.dist[j]) { w.dist[j] = r; w.pred[j] = (short)i; }
+        };
+        if (cached) {
+            for (int e = w.ehead[i]; e >= 0; e = w.enext[e]) relax(w.ecol[e], w.ecost[e]);
+        } else {
+            for (int wd = 0; wd < words; ++wd) {
+                uint32_t bits = w.adj[wd * w.Tmax + i];
+                while (bits) {
+                    const int b = __ffs(bits) - 1;
+                    bits &= bits - 1;
+                    const int j = wd * 32 + b;
+                    relax(j, cost(i, j));
+                }
             }
         }
         int jmin = -1;
@@ -139,7 +155,8 @@ __device__ __forceinline__ void lap_prepare(const LapWork& w, int nrows, int wor
     for (int j = tid; j < ncols; j += NT) {
         w.yc[j] = -1; w.v[j] = 0.0; w.parent[w.Tmax + j] = w.Tmax + j; w.mark[j] = 0; w.scn[j] = 0; w.coldeg[j] = 0;
     }
-    if (tid == 0) *w.ncomplex = 0;
+    if (tid == 0) { *w.ncomplex = 0; if (w.ecount) *w.ecount = 0; }
+    if (w.ehead) for (int t = tid; t < nrows; t += NT) w.ehead[t] = -1;
 }
 
 // Whole-CTA solve.  adj[word][row] and coldeg[] must be complete (zero for rows / columns not
