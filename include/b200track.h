@@ -113,6 +113,10 @@ int b200track_sync(b200track_ctx* ctx);
 int b200track_track_updates(b200track_ctx* ctx, uint64_t* h_total);
 /* Kernel launches issued by this context so far (bench.py's gpu_launches). */
 int b200track_launch_count(b200track_ctx* ctx, uint64_t* h_launches);
+/* Profiling aid: the first call switches on per-phase cycle counters inside the step kernel (thread 0 of
+ * every CTA, clock64 deltas between block barriers); later calls read them.  h_out16[0] = CTAs counted,
+ * h_out16[k] = cycles spent before barrier k.  reset != 0 zeroes the counters after reading. */
+int b200track_phase_cycles(b200track_ctx* ctx, uint64_t* h_out16, int32_t reset);
 /* Bytes one stream's state occupies on the device / dynamic shared memory of the step kernel. */
 int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state_bytes_per_stream, uint64_t* h_smem_bytes);
 

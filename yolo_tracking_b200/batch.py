@@ -143,6 +143,12 @@ class BatchedTracker:
         _lib.check(self._lib.b200track_launch_count(self._ctx, C.byref(v)))
         return v.value
 
+    def phase_cycles(self, reset=True):
+        """Per-phase cycle counters of the step kernel (first call enables them)."""
+        buf = (C.c_uint64 * 16)()
+        _lib.check(self._lib.b200track_phase_cycles(self._ctx, C.byref(buf), int(reset)))
+        return list(buf)
+
     def footprint(self):
         a, b = C.c_uint64(), C.c_uint64()
         _lib.check(self._lib.b200track_footprint(self._ctx, C.byref(a), C.byref(b)))

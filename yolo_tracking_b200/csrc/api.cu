@@ -74,7 +74,7 @@ extern "C" void b200track_destroy(b200track_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(ctx->p.state_f); cudaFree(ctx->p.state_i); cudaFree(ctx->p.counts);
-    cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err);
+    cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.dbg);
     for (auto& s : ctx->slot) {
         cudaFree(s.d_dets); cudaFree(s.d_ndets); cudaFree(s.d_feats); cudaFree(s.d_out); cudaFree(s.d_nout);
         if (s.in_ready) cudaEventDestroy(s.in_ready);
@@ -269,6 +269,19 @@ extern "C" int b200track_track_updates(b200track_ctx* ctx, uint64_t* h_total) {
 extern "C" int b200track_launch_count(b200track_ctx* ctx, uint64_t* h_launches) {
     if (!ctx || !h_launches) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
     *h_launches = ctx->launches;
+    return 0;
+}
+
+extern "C" int b200track_phase_cycles(b200track_ctx* ctx, uint64_t* h_out16, int32_t reset) {
+    if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
+    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    if (!ctx->p.dbg) {
+        CU_TRY(cudaMalloc(&ctx->p.dbg, 16 * sizeof(unsigned long long)));
+        CU_TRY(cudaMemset(ctx->p.dbg, 0, 16 * sizeof(unsigned long long)));
+    }
+    if (h_out16) CU_TRY(cudaMemcpy(h_out16, ctx->p.dbg, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (reset) CU_TRY(cudaMemset(ctx->p.dbg, 0, 16 * sizeof(unsigned long long)));
     return 0;
 }
 

@@ -63,8 +63,14 @@ struct alignas(16) StepSmem {
     // candidate edge cache (cost computed once, while the graph is built)
     static constexpr int ECAP = 2 * TMAX;
     double ecost[ECAP];
-    short ecol[ECAP], enext[ECAP], ehead[TMAX];
+    short ecol[ECAP], enext[ECAP];
+    int ehead[TMAX], colxor[DMAX];
     int ecount[4];
+    // candidate pairs that passed the conservative fp32 overlap filter: (row << 16) | det
+    static constexpr int PCAP = 4 * TMAX;
+    uint32_t pairs[PCAP];
+    int npairs[4];
+    float4 dboxf[DMAX];                               // detection boxes rounded outwards to fp32
     unsigned char role[TMAX], rowtype[TMAX], cat[TMAX], drop[TMAX + DMAX], dflag[DMAX];
 };
 
@@ -127,26 +133,26 @@ struct CellMap {
     }
 };
 
-// Candidate graph of one association pass, thread t = row t.  The row is tested against the
-// detections of its column set that share a cell range with it in x AND in y (a superset of
-// the overlapping ones because the cell maps are monotone); edge iff the boxes overlap and
-// cost <= limit - exact pruning, see lap_sparse.cuh (no overlap => iou = 0 => cost = 1 > limit).
+// Candidate graph of one association pass.
+//   phase A (thread t = row t): AND the ORs of the cell masks the row's box covers (a superset
+//     of the overlapping detections because the cell maps are monotone), run a conservative
+//     fp32 overlap test (boxes rounded outwards) on the survivors and append the pairs that
+//     pass to a shared list;
+//   phase B (thread k = pair k): exact cost; edge iff cost <= limit - exact pruning, see
+//     lap_sparse.cuh (no overlap => iou = 0 => cost = 1 > limit).  Every thread evaluates at
+//     most a couple of pairs, all lanes busy, one fp64 division each.
 template <int KIND, class SM>
-__device__ __forceinline__ void build_graph_row(SM& sm, int t, int n, int words, const CellMap& cm,
-                                                const PassCost<KIND, SM>& cost, const PassLimit& lim) {
+__device__ __forceinline__ void graph_phase_a(SM& sm, int t, int n, int words, const CellMap& cm) {
     constexpr int DWP = SM::DWP;
     if (t >= n) return;
+    for (int wd = 0; wd < words; ++wd) sm.adj[wd][t] = 0u;
     const int rt = sm.rowtype[t];
-    if (rt == RT_NONE) {
-        for (int wd = 0; wd < words; ++wd) sm.adj[wd][t] = 0u;
-        return;
-    }
+    if (rt == RT_NONE) return;
     const Box a = track_box<KIND>(sm, t);
+    const float ax1 = __double2float_rd(a.x1), ay1 = __double2float_rd(a.y1);
+    const float ax2 = __double2float_ru(a.x2), ay2 = __double2float_ru(a.y2);
     const int cx0 = cm.cx(a.x1), cx1 = cm.cx(a.x2), cy0 = cm.cy(a.y1), cy1 = cm.cy(a.y2);
     const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
-    const bool fuse = rt == RT_A ? cost.fuseA : cost.fuseB;
-    const double limit = rt == RT_A ? lim.limA : lim.limB;
-    int ehead = -1;
 #pragma unroll
     for (int q = 0; q < DWP / 4; ++q) {
         if (q * 4 >= words) break;
@@ -163,29 +169,64 @@ __device__ __forceinline__ void build_graph_row(SM& sm, int t, int n, int words,
         uint32_t cand4[4] = {mx.x & my.x & cb.x, mx.y & my.y & cb.y, mx.z & my.z & cb.z, mx.w & my.w & cb.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int wd = q * 4 + k;
-            if (wd >= words) break;
-            uint32_t cand = cand4[k], res = 0u;
+            uint32_t cand = cand4[k];
             while (cand) {
                 const int b = __ffs(cand) - 1;
                 cand &= cand - 1;
-                const int j = wd * 32 + b;
-                const Box d = det_box(sm, j);
-                if (box_overlap(a, d)) {
-                    const double v = box_iou(a, d);
-                    const double c = fuse ? fused_cost(v, sm.dconf[j]) : xsub(1.0, v);
-                    if (c <= limit) {
-                        res |= 1u << b;
-                        atomicAdd(&sm.coldeg[j], 1);
-                        const int e = atomicAdd(&sm.ecount[0], 1);
-                        if (e < SM::ECAP) { sm.ecost[e] = c; sm.ecol[e] = (short)j; sm.enext[e] = (short)ehead; ehead = e; }
-                    }
+                const int j = (q * 4 + k) * 32 + b;
+                const float4 d = sm.dboxf[j];
+                if (d.x < ax2 && ax1 < d.z && d.y < ay2 && ay1 < d.w) {
+                    const int pi = atomicAdd(&sm.npairs[0], 1);
+                    if (pi < SM::PCAP) sm.pairs[pi] = ((uint32_t)t << 16) | (uint32_t)j;
                 }
             }
-            sm.adj[wd][t] = res;
         }
     }
-    sm.ehead[t] = (short)ehead;
+}
+
+template <int KIND, class SM>
+__device__ __forceinline__ void graph_add_edge(SM& sm, int t, int j, double c) {
+    atomicOr(&sm.adj[j >> 5][t], 1u << (j & 31));
+    atomicAdd(&sm.coldeg[j], 1);
+    atomicXor(&sm.colxor[j], t);
+    const int e = atomicAdd(&sm.ecount[0], 1);
+    if (e < SM::ECAP) {
+        sm.ecost[e] = c; sm.ecol[e] = (short)j;
+        sm.enext[e] = (short)atomicExch(&sm.ehead[t], e);
+    }
+}
+
+template <int NT, int KIND, class SM>
+__device__ __forceinline__ void graph_phase_b(SM& sm, int n, int words, const PassCost<KIND, SM>& cost, const PassLimit& lim) {
+    const int np = sm.npairs[0];
+    if (np <= SM::PCAP) {
+        for (int k = threadIdx.x; k < np; k += NT) {
+            const uint32_t pr = sm.pairs[k];
+            const int t = pr >> 16, j = pr & 0xffff;
+            const bool isA = sm.rowtype[t] == RT_A;
+            const double c = cost.pair(track_box<KIND>(sm, t), j, isA ? cost.fuseA : cost.fuseB);
+            if (c <= (isA ? lim.limA : lim.limB)) graph_add_edge<KIND>(sm, t, j, c);
+        }
+    } else {
+        // pair list overflowed (pathologically crowded frame): every row re-walks its columns
+        for (int t = threadIdx.x; t < n; t += NT) {
+            const int rt = sm.rowtype[t];
+            if (rt == RT_NONE) continue;
+            const Box a = track_box<KIND>(sm, t);
+            const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
+            for (int wd = 0; wd < words; ++wd) {
+                uint32_t cand = colbits[wd];
+                while (cand) {
+                    const int b = __ffs(cand) - 1;
+                    cand &= cand - 1;
+                    const int j = wd * 32 + b;
+                    if (!box_overlap(a, det_box(sm, j))) continue;
+                    const double c = cost.pair(a, j, rt == RT_A ? cost.fuseA : cost.fuseB);
+                    if (c <= (rt == RT_A ? lim.limA : lim.limB)) graph_add_edge<KIND>(sm, t, j, c);
+                }
+            }
+        }
+    }
 }
 
 template <int NT, int KIND, int TMAX, int DMAX>
@@ -198,6 +239,9 @@ bytetrack_step_kernel(const StepParams p) {
     constexpr int DWP = SM::DWP;
     const int s = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // optional per-phase cycle counters (thread 0 of every CTA; b200track_phase_cycles)
+    long long ph_last = p.dbg ? clock64() : 0;
+#define PHASE(k) do { if (p.dbg && tid == 0) { const long long now_ = clock64(); atomicAdd(&p.dbg[k], (unsigned long long)(now_ - ph_last)); ph_last = now_; } } while (0)
 
     int* counts = p.counts + 4 * s;
     const int nT = counts[0], nL = counts[1], id0 = counts[2], frame = counts[3] + 1;
@@ -244,6 +288,7 @@ bytetrack_step_kernel(const StepParams p) {
         for (int i = tid; i < TMAX + DMAX; i += NT) sm.drop[i] = 0;
     }
     __syncthreads();
+    PHASE(1);
 
     // ---- detection side (thread j): confidence bands (byte_tracker.py:151-158, strict
     // inequalities), frame extents for the cell maps -------------------------------------------
@@ -259,6 +304,8 @@ bytetrack_step_kernel(const StepParams p) {
             if (c > p.track_thresh) mydfl = DF_HIGH;
             else if (c > p.low_thresh && c < p.track_thresh) mydfl = DF_LOW;
             if (mydfl) { ex0 = (float)mybox.x1; ey0 = (float)mybox.y1; ex1 = (float)mybox.x2; ey1 = (float)mybox.y2; }
+            sm.dboxf[j] = make_float4(__double2float_rd(mybox.x1), __double2float_rd(mybox.y1),
+                                      __double2float_ru(mybox.x2), __double2float_ru(mybox.y2));
         }
         sm.dflag[j] = (unsigned char)mydfl;
         const uint32_t mh = __ballot_sync(0xffffffffu, mydfl == DF_HIGH);
@@ -298,8 +345,11 @@ bytetrack_step_kernel(const StepParams p) {
     lw.pred = sm.pred; lw.nextc = sm.nextc; lw.mark = sm.mark; lw.scn = sm.scn;
     lw.coldeg = sm.coldeg; lw.ncomplex = sm.ncomplex;
     lw.ecost = sm.ecost; lw.ecol = sm.ecol; lw.enext = sm.enext; lw.ehead = sm.ehead; lw.ecount = sm.ecount; lw.ecap = SM::ECAP;
+    lw.colxor = sm.colxor;
+    if (tid == 0) sm.npairs[0] = 0;
     lap_prepare<NT>(lw, n, words);
     __syncthreads();
+    PHASE(2);
 
     // ---- cell masks over the banded detections ---------------------------------------------
     CellMap cm;
@@ -323,6 +373,7 @@ bytetrack_step_kernel(const StepParams p) {
         for (int c = cy0; c <= cy1; ++c) atomicOr(&sm.ymask[c][wd], bit);
     }
     __syncthreads();
+    PHASE(3);
 
     PassCost<KIND, SM> cost;
     cost.sm = &sm;
@@ -332,8 +383,11 @@ bytetrack_step_kernel(const StepParams p) {
     // ---- first association: pool x high detections, fused score, limit match_thresh ----
     cost.fuseA = true; cost.fuseB = true;
     lim.limA = p.match_thresh; lim.limB = p.match_thresh;
-    build_graph_row<KIND>(sm, t, n, words, cm, cost, lim);
+    graph_phase_a<KIND>(sm, t, n, words, cm);
     __syncthreads();
+    graph_phase_b<NT, KIND>(sm, n, words, cost, lim);
+    __syncthreads();
+    PHASE(4);
     lap_sparse_solve<NT>(lw, n, words, lim, cost);
     bool matched1 = false;
     if (t < n && sm.rowtype[t] != RT_NONE) {
@@ -341,6 +395,7 @@ bytetrack_step_kernel(const StepParams p) {
         if (j >= 0) { matched1 = true; sm.match[t] = (short)j; sm.dflag[j] |= DF_USED; }
     }
     __syncthreads();
+    PHASE(5);
 
     // ---- second pass: two independent problems solved together (disjoint rows AND columns):
     //   A: still-Tracked leftovers x low detections, plain IoU, limit 0.5   (byte_tracker.py:198-226)
@@ -352,12 +407,17 @@ bytetrack_step_kernel(const StepParams p) {
         const uint32_t mb = __ballot_sync(0xffffffffu, dfl == DF_HIGH);     // high and not used
         if (lane == 0) { sm.colbitsA[tid >> 5] = ma; sm.colbitsB[tid >> 5] = mb; }
     }
+    if (tid == 0) sm.npairs[0] = 0;
     lap_prepare<NT>(lw, n, words);
     __syncthreads();
+    PHASE(6);
     cost.fuseA = false; cost.fuseB = true;
     lim.limA = p.second_thresh; lim.limB = p.unconf_thresh;
-    build_graph_row<KIND>(sm, t, n, words, cm, cost, lim);
+    graph_phase_a<KIND>(sm, t, n, words, cm);
     __syncthreads();
+    graph_phase_b<NT, KIND>(sm, n, words, cost, lim);
+    __syncthreads();
+    PHASE(7);
     lap_sparse_solve<NT>(lw, n, words, lim, cost);
 
     // ---- deferred Kalman work + lifecycle, thread t (byte_tracker.py:64-98, :222-253) --------
@@ -437,6 +497,7 @@ bytetrack_step_kernel(const StepParams p) {
         sm.frame_t[t] = frame_t;
     }
     __syncthreads();
+    PHASE(8);
 
     // compact list of the new lost list (old entries first, then the newly lost) for the
     // duplicate test; packed counters: [0:16) old-lost, [16:32) new-lost
@@ -450,6 +511,7 @@ bytetrack_step_kernel(const StepParams p) {
         if (cat == CAT_LOST_NEW) sm.lostlist[nLostOld + ((ex >> 16) & 0xffff)] = (short)t;
         nLostList = nLostOld + (int)((tot >> 16) & 0xffff);
         __syncthreads();
+        PHASE(9);
     }
 
     // is detection `tid` the seed of a new track?  (unmatched high detection, byte_tracker.py:242-248)
@@ -468,6 +530,7 @@ bytetrack_step_kernel(const StepParams p) {
             sm.coldeg[tid] = sm.frame_t[q] - sm.start_t[q];
         }
         __syncthreads();
+        PHASE(10);
         for (int pass = 0; pass < 2; ++pass) {
             Box a;
             int age;
@@ -497,6 +560,7 @@ bytetrack_step_kernel(const StepParams p) {
             if (dropme) sm.drop[pass == 0 ? t : TMAX + tid] = 1;
         }
         __syncthreads();
+        PHASE(11);
     }
 
     // ---- destinations.  One packed scan (10-bit fields), element i = slot i and detection i:
@@ -592,7 +656,9 @@ bytetrack_step_kernel(const StepParams p) {
             }
         }
     }
+    PHASE(15);
     if (tid == 0) {
+        if (p.dbg) atomicAdd(&p.dbg[0], 1ull);
         counts[0] = min(newT, cap);
         counts[1] = min(newL, cap - min(newT, cap));
         counts[2] = id0 + totBornAll;
@@ -603,6 +669,7 @@ bytetrack_step_kernel(const StepParams p) {
     }
 }
 
+#undef PHASE
 struct Variant { int tmax, dmax; };
 constexpr Variant kVariants[] = {{64, 64}, {128, 128}, {256, 224}, {256, 256}, {512, 512}};
 

@@ -45,9 +45,10 @@ struct LapWork {
     double* ecost = nullptr;   // [ecap]
     short* ecol = nullptr;     // [ecap]
     short* enext = nullptr;    // [ecap]
-    short* ehead = nullptr;    // [Tmax]
+    int* ehead = nullptr;      // [Tmax]
     int* ecount = nullptr;     // [1]
     int ecap = 0;
+    int* colxor = nullptr;     // [Dmax] XOR of the candidate rows of a column (with coldeg: the other row of a 2-row column)
 };
 
 __device__ __forceinline__ int uf_find(volatile int* parent, int x) {
@@ -154,21 +155,27 @@ __device__ __forceinline__ void lap_prepare(const LapWork& w, int nrows, int wor
     for (int t = tid; t < nrows; t += NT) { w.xr[t] = -1; w.u[t] = 0.0; w.parent[t] = t; w.head[t] = -1; w.rnext[t] = -1; }
     for (int j = tid; j < ncols; j += NT) {
         w.yc[j] = -1; w.v[j] = 0.0; w.parent[w.Tmax + j] = w.Tmax + j; w.mark[j] = 0; w.scn[j] = 0; w.coldeg[j] = 0;
+        if (w.colxor) w.colxor[j] = 0;
     }
     if (tid == 0) { *w.ncomplex = 0; if (w.ecount) *w.ecount = 0; }
     if (w.ehead) for (int t = tid; t < nrows; t += NT) w.ehead[t] = -1;
 }
 
-// Whole-CTA solve.  adj[word][row] and coldeg[] must be complete (zero for rows / columns not
-// taking part) and visible (__syncthreads() after the build); rows are 0..nrows-1, columns
-// 0..32*words-1.  lambda(row) is the cost limit of that row's problem.  Results in xr / yc.
+// Whole-CTA solve.  adj[word][row], coldeg[] (and, when used, the edge cache and colxor[]) must be
+// complete (zero for rows / columns not taking part) and visible (__syncthreads() after the
+// build); rows are 0..nrows-1, columns 0..32*words-1.  lambda(row) is the cost limit of that
+// row's problem.  Results in xr / yc.
 //
-// Fast path: a row with exactly one candidate column whose only candidate row it is forms a
-// component of its own and is matched directly (c_ij <= limit by construction).  Only the
-// remaining rows go through union-find + augmentation.
+// Small components are solved in place by the thread of their first row, without any barrier:
+//   * 1 row x 1 column: matched directly (c_ij <= limit by construction);
+//   * 1 row with several private columns, and 2-row components (every column touched by the
+//     two rows has no other row): exhaustive enumeration of the partial matchings over the
+//     cached edge costs - the same objective (sum of matched costs + lambda per unmatched row);
+// everything else goes through union-find + shortest augmenting paths.
 template <int NT, class Cost, class Lambda>
 __device__ void lap_sparse_solve(const LapWork& w, int nrows, int words, const Lambda& lambda, const Cost& cost) {
     const int tid = threadIdx.x;
+    const bool small_ok = w.ecost != nullptr && w.colxor != nullptr && *w.ecount <= w.ecap;
     for (int t = tid; t < nrows; t += NT) {
         int deg = 0, first = -1;
         for (int wd = 0; wd < words; ++wd) {
@@ -177,6 +184,52 @@ __device__ void lap_sparse_solve(const LapWork& w, int nrows, int words, const L
         }
         if (deg == 0) continue;
         if (deg == 1 && w.coldeg[first] == 1) { w.xr[t] = (short)first; w.yc[first] = (short)t; continue; }
+        if (small_ok) {
+            int partner = -1;
+            bool general = false;
+            for (int e = w.ehead[t]; e >= 0; e = w.enext[e]) {
+                const int j = w.ecol[e], cd = w.coldeg[j];
+                if (cd == 1) continue;
+                if (cd == 2) { const int o = w.colxor[j] ^ t; if (partner < 0) partner = o; else if (partner != o) general = true; }
+                else general = true;
+            }
+            if (!general && partner >= 0) {
+                for (int e = w.ehead[partner]; e >= 0; e = w.enext[e]) {
+                    const int j = w.ecol[e], cd = w.coldeg[j];
+                    if (cd == 1) continue;
+                    if (cd != 2 || (w.colxor[j] ^ partner) != t) general = true;
+                }
+            }
+            if (!general) {
+                const double lamA = lambda(t);
+                if (partner < 0) {                        // one row, private columns: cheapest edge or nothing
+                    double best = lamA; int bj = -1;
+                    for (int e = w.ehead[t]; e >= 0; e = w.enext[e])
+                        if (w.ecost[e] < best) { best = w.ecost[e]; bj = w.ecol[e]; }
+                    if (bj >= 0) { w.xr[t] = (short)bj; w.yc[bj] = (short)t; }
+                } else if (t < partner) {                 // two rows: enumerate (col or none) x (col or none)
+                    const double lamB = lambda(partner);
+                    double best = lamA + lamB; int ja = -1, jb = -1;
+                    for (int ea = w.ehead[t]; ; ea = w.enext[ea]) {
+                        const double ca = ea >= 0 ? w.ecost[ea] : lamA;
+                        const int cola = ea >= 0 ? w.ecol[ea] : -1;
+                        for (int eb = w.ehead[partner]; ; eb = w.enext[eb]) {
+                            const double cb = eb >= 0 ? w.ecost[eb] : lamB;
+                            const int colb = eb >= 0 ? w.ecol[eb] : -1;
+                            if (!(cola >= 0 && cola == colb)) {
+                                const double tot = ca + cb;
+                                if (tot < best) { best = tot; ja = cola; jb = colb; }
+                            }
+                            if (eb < 0) break;
+                        }
+                        if (ea < 0) break;
+                    }
+                    if (ja >= 0) { w.xr[t] = (short)ja; w.yc[ja] = (short)t; }
+                    if (jb >= 0) { w.xr[partner] = (short)jb; w.yc[jb] = (short)partner; }
+                }
+                continue;
+            }
+        }
         atomicAdd(w.ncomplex, 1);
         for (int wd = 0; wd < words; ++wd) {
             uint32_t bits = w.adj[wd * w.Tmax + t];

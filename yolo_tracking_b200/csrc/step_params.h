@@ -24,6 +24,7 @@ struct StepParams {
     int* counts;
     unsigned long long* track_updates;
     int* err;
+    unsigned long long* dbg;  // [16] optional phase cycle counters, null = off
     // per-step inputs / outputs (device)
     const double* dets;       // [S, max_dets, 6]
     const int* ndets;         // [S]
