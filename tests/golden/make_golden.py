@@ -177,7 +177,69 @@ def gen_bytetrack():
     _save("bytetrack_2box", det=det, out=np.stack(outs))
 
 
-GENERATORS = {"kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack}
+# ----------------------------------------------------------------------------- OC-SORT
+def _oc_snapshot(trk):
+    ts = trk.trackers
+    ints = np.array([[t.id, t.age, t.time_since_update, t.hits, t.hit_streak, int(t.kf.observed)] for t in ts],
+                    dtype=np.int32).reshape(-1, 6)
+    x = np.stack([t.kf.x[:, 0] for t in ts]) if ts else np.zeros((0, 7))
+    P = np.stack([t.kf.P.reshape(49) for t in ts]) if ts else np.zeros((0, 49))
+    vel = np.array([t.velocity if t.velocity is not None else np.zeros(2) for t in ts]).reshape(-1, 2)
+    last = np.array([t.last_observation for t in ts], dtype=np.float64).reshape(-1, 5)
+    return ints, x, P, vel, last
+
+
+def gen_ocsort():
+    rh.install()
+    from boxmot.trackers.ocsort.ocsort import OCSort
+    base = dict(det_thresh=0, max_age=30, min_hits=1, asso_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2,
+                use_byte=False)                                      # boxmot/configs/ocsort.yaml
+    scenarios = {
+        # BASELINE config 2 shape, scaled down: occlusion runs exercise freeze / ORU / OCR
+        "ocsort_c2": dict(stream=0, n_objects=30, n_frames=150, kw=dict(occlusion=True), params={}),
+        "ocsort_churn": dict(stream=902, n_objects=16, n_frames=160, kw=dict(miss_prob=0.3, fp_rate=3.0),
+                             params=dict(min_hits=3, max_age=8, det_thresh=0.3)),
+    }
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    for name, sc in scenarios.items():
+        dets, nd, _ = make_stream(2, sc["stream"], sc["n_objects"], sc["n_frames"], **sc["kw"])
+        cfg = dict(base)
+        cfg.update(sc["params"])
+        rh.install()
+        rh.reset_counters()
+        trk = OCSort(False, **cfg)
+        outs, ints, xs, Ps, vels, lasts, pool, heavy_frames = [], [], [], [], [], [], [], []
+        for f in range(sc["n_frames"]):
+            o = trk.update(dets[f, :nd[f]], img)
+            outs.append(o)
+            ii, x, P, vel, last = _oc_snapshot(trk)
+            ints.append(ii)
+            vels.append(vel)
+            lasts.append(last)
+            xs.append(x)
+            if f % 10 == 9 or f == sc["n_frames"] - 1:
+                Ps.append(P)
+                heavy_frames.append(f)
+        out_flat, out_offs = _ragged(outs, 8)
+        int_flat, int_offs = _ragged(ints, 6)
+        _save(name, dets=dets, ndets=nd, out=out_flat, out_offs=out_offs, rec=int_flat.astype(np.int32),
+              rec_offs=int_offs, x=_ragged(xs, 7)[0], vel=_ragged(vels, 2)[0], last=_ragged(lasts, 5)[0],
+              P=_ragged(Ps, 49)[0], heavy_frames=np.array(heavy_frames, dtype=np.int32),
+              params=np.array([cfg["det_thresh"], cfg["max_age"], cfg["min_hits"], cfg["asso_threshold"], cfg["delta_t"],
+                               cfg["inertia"]], dtype=np.float64), img_hw=np.array([1080, 1920]))
+    # the reference's own known-answer inputs (tests/test_python.py:97-139)
+    det = np.array([[144, 212, 578, 480, 0.82, 0], [425, 281, 576, 472, 0.56, 65]], dtype=np.float64)
+    rh.reset_counters()
+    trk = OCSort(False, **base)
+    outs = [trk.update(det, img) for _ in range(3)]
+    rh.reset_counters()
+    trk = OCSort(False, **dict(base, min_hits=2))
+    seq = [np.empty((0, 6)), np.empty((0, 6)), det, np.empty((0, 6)), det, det, det]
+    sizes = [trk.update(d, img).size for d in seq]
+    _save("ocsort_2box", det=det, out=np.stack(outs), min_hits_sizes=np.array(sizes))
+
+
+GENERATORS = {"kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(GENERATORS)

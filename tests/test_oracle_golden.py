@@ -115,3 +115,55 @@ def test_bytetrack_empty_and_asserts():
         trk.update(np.zeros((2, 5)))
     with pytest.raises(AssertionError):
         trk.update([[0, 0, 1, 1, 0.9, 0]])
+
+
+# ----------------------------------------------------------------------------- OC-SORT
+def _ocsort_from_params(p, **kw):
+    from oracle.ocsort import OCSortOracle
+    return OCSortOracle(False, det_thresh=p[0], max_age=int(p[1]), min_hits=int(p[2]), asso_threshold=p[3],
+                        delta_t=int(p[4]), asso_func="giou", inertia=p[5], use_byte=False, **kw)
+
+
+@pytest.mark.parametrize("name", ["ocsort_c2", "ocsort_churn"])
+def test_ocsort_oracle_replays_reference(name):
+    g = load_golden(name)
+    trk = _ocsort_from_params(g["params"])
+    dets, nd = g["dets"], g["ndets"]
+    hw = tuple(int(v) for v in g["img_hw"])
+    heavy = {int(f): k for k, f in enumerate(g["heavy_frames"])}
+    p_offs = [0]
+    for f in g["heavy_frames"]:
+        p_offs.append(p_offs[-1] + int(g["rec_offs"][f + 1] - g["rec_offs"][f]))
+    for f in range(dets.shape[0]):
+        out = trk.update(dets[f, :nd[f]], hw)
+        ref = g["out"][g["out_offs"][f]:g["out_offs"][f + 1]]
+        assert out.reshape(-1, 8).shape == ref.shape, f"frame {f}"
+        if ref.size:
+            assert np.array_equal(out[:, 4:], ref[:, 4:]), f"frame {f}: id/conf/cls/det_ind"
+            assert_close(out[:, :4], ref[:, :4], what=f"frame {f} boxes")
+        s = trk.snapshot()
+        lo, hi = g["rec_offs"][f], g["rec_offs"][f + 1]
+        mine = np.stack([s["track_id"], s["age"], s["time_since_update"], s["hits"], s["hit_streak"], s["observed"]],
+                        axis=1).reshape(-1, 6)
+        assert np.array_equal(mine, g["rec"][lo:hi]), f"frame {f}: lifecycle records"
+        assert_close(s["x"], g["x"][lo:hi], what=f"frame {f} x")
+        assert_close(s["velocity"], g["vel"][lo:hi], what=f"frame {f} velocity")
+        assert_close(s["last_observation"], g["last"][lo:hi], what=f"frame {f} last_observation")
+        if f in heavy:
+            k = heavy[f]
+            assert_close(s["P"].reshape(-1, 49), g["P"][p_offs[k]:p_offs[k + 1]], abs_=1e-9, what=f"frame {f} P")
+    assert trk.stats["oru"] > 0 and trk.stats["lap_frames"] > 0
+
+
+def test_ocsort_reference_known_answer():
+    from oracle.ocsort import OCSortOracle
+    g = load_golden("ocsort_2box")
+    base = dict(det_thresh=0, max_age=30, min_hits=1, asso_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2)
+    trk = OCSortOracle(False, **base)
+    for k in range(3):
+        out = trk.update(g["det"], (1080, 1920))
+        assert out.shape == (2, 8)
+        assert_close(out, g["out"][k])
+    trk = OCSortOracle(False, **dict(base, min_hits=2))
+    seq = [np.empty((0, 6)), np.empty((0, 6)), g["det"], np.empty((0, 6)), g["det"], g["det"], g["det"]]
+    assert [trk.update(d, (1080, 1920)).size for d in seq] == g["min_hits_sizes"].tolist()
