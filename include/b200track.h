@@ -124,7 +124,10 @@ int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state_bytes_per_stream, 
  * list), expanded to the reference's dense form.  Buffers hold max_tracks rows.
  *   h_counts[4] = n_tracked, n_lost, id counter, frame_id
  *   h_rec [max_tracks, 6] = track_id, state, is_activated, frame_id, start_frame, tracklet_len
- *   h_mean[max_tracks, 8], h_cov[max_tracks, 64], h_aux[max_tracks, 3] = score, cls, det_ind */
+ *   h_mean[max_tracks, 8], h_cov[max_tracks, 64], h_aux[max_tracks, 3] = score, cls, det_ind
+ * OC-SORT contexts (KalmanBoxTracker fields, ocsort.py:65-128): h_counts[0] = live trackers;
+ *   h_rec = id, age, time_since_update, hits, hit_streak, kf.observed; h_mean = kf.x[7], has-observation;
+ *   h_cov[0:49] = dense 7x7 kf.P, [49:51] = velocity, [51:56] = last_observation. */
 int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int32_t* h_counts,
                         int32_t* h_rec, double* h_mean, double* h_cov, double* h_aux);
 

@@ -17,11 +17,31 @@ The extended matrix is built literally and solved exactly with scipy's
 returns the same x, y.  Parity anchor: the reference's call sites
   boxmot/utils/matching.py:56-71     linear_assignment(cost, thresh)  (ByteTrack/BoTSORT)
   boxmot/utils/association.py:20-24  linear_assignment(cost)          (OCSORT family)
+
+Ties.  lapjv's behaviour on EXACTLY tied optima is an implementation detail of the absent
+package.  ByteTrack / BoTSORT costs are tie-free on continuous inputs, but the OC-SORT cost
+-(similarity + angle) is structurally full of exact zeros (disjoint boxes, trackers without a
+velocity yet), and which of several junk detections stays unassigned decides the creation
+order - hence the ids - of new trackers.  To make that well defined, the no-limit call site
+(`assign_no_limit`) breaks ties canonically towards lower indices: cost[r, c] += 2**-50 *
+(r * C + c) before the solve (at most ~1e-8 in total, far below any real cost gap).  The same
+rule is used by the lap shim that generates the goldens (tests/golden/ref_harness.py) and by
+the CUDA path (csrc/ocsort_step.cu).
 """
 from __future__ import annotations
 
 import numpy as np
 from scipy.optimize import linear_sum_assignment
+
+TIE_EPS = 2.0 ** -50
+
+
+def tie_break(cost):
+    """cost[r, c] + TIE_EPS * (r * C + c), evaluated exactly like the CUDA path."""
+    cost = np.asarray(cost, dtype=np.float64)
+    R, C = cost.shape
+    idx = (np.arange(R, dtype=np.float64)[:, None] * C + np.arange(C, dtype=np.float64)[None, :])
+    return cost + idx * TIE_EPS
 
 
 def lapjv_extended(cost, cost_limit=np.inf):
@@ -58,6 +78,6 @@ def assign_no_limit(cost):
     cost = np.asarray(cost)
     if cost.size == 0:
         return np.empty((0, 2), dtype=int)
-    _, x, _ = lapjv_extended(cost)
+    _, x, _ = lapjv_extended(tie_break(cost))
     rows = np.nonzero(x >= 0)[0]
     return np.stack([rows, x[rows]], axis=1).astype(int).reshape(-1, 2)

@@ -8,7 +8,9 @@ Shims (none of them touches the reference sources):
   * ``lap`` (pip ``lapx``, un-vendored, not installable offline): ``lap.lapjv`` is restated
     from gatagat/lap's ``_lapjv.pyx`` semantics - build the (R+C)x(R+C) extended matrix and
     solve it exactly with scipy's ``linear_sum_assignment``.  On tie-free inputs the optimum
-    is unique, so any exact solver returns the same ``x, y``.
+    is unique, so any exact solver returns the same ``x, y``.  Exact ties of the no-limit call
+    (OC-SORT's structurally zero costs) are broken canonically towards lower indices by a
+    2**-50 * (r * C + c) perturbation - see oracle/lap.py "Ties".
   * ``filterpy.common.reshape_z`` / ``filterpy.stats.logpdf`` (only ``reshape_z`` executes).
   * ReID model -> queued fixed embeddings; GMC -> identity warp.
 """
@@ -26,6 +28,9 @@ def _lapjv(cost, extend_cost=False, cost_limit=np.inf, return_cost=True):
     from scipy.optimize import linear_sum_assignment
     cost = np.ascontiguousarray(cost, dtype=np.float64)
     R, C = cost.shape
+    if not cost_limit < np.inf and R and C:
+        # canonical tie-break of the no-limit call site (oracle/lap.py "Ties")
+        cost = cost + (np.arange(R, dtype=np.float64)[:, None] * C + np.arange(C, dtype=np.float64)[None, :]) * 2.0 ** -50
     if extend_cost or cost_limit < np.inf:
         n = R + C
         ext = np.empty((n, n), dtype=np.float64)

@@ -122,3 +122,33 @@ def test_lapjv_negative_costs_no_limit():
     for b in range(4):
         _, ox, oy = lapjv_extended(cost[b])
         assert np.array_equal(x[b], ox) and np.array_equal(y[b], oy)
+
+
+@pytest.mark.parametrize("rows,cols", [(27, 34), (34, 27), (150, 200), (200, 150)])
+def test_lapjv_no_limit_mostly_zero_costs(rows, cols):
+    """OC-SORT-shaped matrices: exact zeros (disjoint boxes) almost everywhere, one strong pair per
+    object plus a few weak ones, canonical tie-break (oracle/lap.py "Ties").  Free columns must end
+    with a zero dual, which a column-reduction start gets wrong."""
+    from oracle.lap import lapjv_extended, tie_break
+    from yolo_tracking_b200 import _ops
+    rng = np.random.default_rng(rows * 7 + cols)
+    B = 5
+    cost = np.zeros((B, rows, cols))
+    for b in range(B):
+        k = min(rows, cols) - 3
+        rr, cc = rng.permutation(rows)[:k], rng.permutation(cols)[:k]
+        cost[b, rr, cc] = -rng.uniform(0.3, 1.0, k)
+        extra = rng.random((rows, cols)) < 0.03
+        cost[b] = np.where(extra & (cost[b] == 0), -rng.uniform(0.0, 0.6, (rows, cols)), cost[b])
+        cost[b] = tie_break(cost[b])
+    x, y = _ops.lapjv(cost)
+    for b in range(B):
+        _, ox, oy = lapjv_extended(cost[b])
+        # the tie-break is separable in (row, column): it fixes WHICH rows / columns stay unmatched and
+        # the real pairs, while exactly tied zero-cost pairs may be permuted among themselves
+        assert np.array_equal(x[b] >= 0, ox >= 0) and np.array_equal(y[b] >= 0, oy >= 0), f"problem {b}: matched sets"
+        r = np.nonzero(ox >= 0)[0]
+        assert all(y[b][x[b][i]] == i for i in r)
+        strong = cost[b][r, ox[r]] < -1e-6
+        assert np.array_equal(x[b][r][strong], ox[r][strong]), f"problem {b}: real pairs"
+        assert abs(cost[b][r, x[b][r]].sum() - cost[b][r, ox[r]].sum()) < 1e-12, f"problem {b}: objective"

@@ -165,6 +165,14 @@ class BatchedTracker:
         _lib.check(self._lib.b200track_get_state(self._ctx, int(stream), _ptr(counts), _ptr(rec), _ptr(mean),
                                                  _ptr(cov), _ptr(aux)))
         n = int(counts[0] + counts[1])
+        if self.kind == "ocsort":
+            c = cov[:n]
+            return dict(n=n, id_count=int(counts[2]), frame_count=int(counts[3]),
+                        track_id=rec[:n, 0].copy(), age=rec[:n, 1].copy(), time_since_update=rec[:n, 2].copy(),
+                        hits=rec[:n, 3].copy(), hit_streak=rec[:n, 4].copy(), observed=rec[:n, 5].copy(),
+                        x=mean[:n, :7].copy(), P=c[:, :49].reshape(n, 7, 7).copy(), velocity=c[:, 49:51].copy(),
+                        last_observation=c[:, 51:56].copy(), conf=aux[:n, 0].copy(), cls=aux[:n, 1].copy(),
+                        det_ind=aux[:n, 2].copy())
         return dict(n_tracked=int(counts[0]), n_lost=int(counts[1]), id_count=int(counts[2]), frame_id=int(counts[3]),
                     track_id=rec[:n, 0].copy(), state=rec[:n, 1].copy(), is_activated=rec[:n, 2].copy(),
                     frame_id_t=rec[:n, 3].copy(), start_frame=rec[:n, 4].copy(), tracklet_len=rec[:n, 5].copy(),

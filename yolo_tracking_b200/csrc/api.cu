@@ -48,6 +48,7 @@ struct b200track_ctx {
     int kf_kind = 0;
     int variant = 0;
     int tcap = 0;               // slot stride of the device state (the kernel variant's capacity)
+    int nf = B200_NF, ni = B200_NI;   // fp64 / int32 components per slot (depends on the tracker kind)
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     HostSlot slot[NSLOT];
     uint64_t launches = 0;
@@ -74,7 +75,7 @@ extern "C" void b200track_destroy(b200track_ctx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(ctx->p.state_f); cudaFree(ctx->p.state_i); cudaFree(ctx->p.counts);
-    cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.dbg);
+    cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.dbg); cudaFree(ctx->p.scratch);
     for (auto& s : ctx->slot) {
         cudaFree(s.d_dets); cudaFree(s.d_ndets); cudaFree(s.d_feats); cudaFree(s.d_out); cudaFree(s.d_nout);
         if (s.in_ready) cudaEventDestroy(s.in_ready);
@@ -93,8 +94,8 @@ extern "C" int b200track_reset(b200track_ctx* ctx) {
     CU_TRY(cudaSetDevice(ctx->cfg.device));
     CU_TRY(cudaDeviceSynchronize());
     const size_t S = ctx->cfg.n_streams, T = ctx->tcap;
-    CU_TRY(cudaMemset(ctx->p.state_f, 0, S * B200_NF * T * sizeof(double)));
-    CU_TRY(cudaMemset(ctx->p.state_i, 0, S * B200_NI * T * sizeof(int)));
+    CU_TRY(cudaMemset(ctx->p.state_f, 0, S * ctx->nf * T * sizeof(double)));
+    CU_TRY(cudaMemset(ctx->p.state_i, 0, S * ctx->ni * T * sizeof(int)));
     CU_TRY(cudaMemset(ctx->p.counts, 0, S * 4 * sizeof(int)));
     CU_TRY(cudaMemset(ctx->p.track_updates, 0, S * sizeof(unsigned long long)));
     CU_TRY(cudaMemset(ctx->p.err, 0, sizeof(int)));
@@ -105,9 +106,14 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     if (!out_ctx) { set_error("out_ctx is NULL"); return B200TRACK_ERR_ARG; }
     *out_ctx = nullptr;
     if (int rc = check_cfg(cfg)) return rc;
-    if (cfg->kind != B200TRACK_BYTETRACK) {
+    if (cfg->kind == B200TRACK_BOTSORT) {
         set_error("tracker kind not built yet in this library version");
         return B200TRACK_ERR_STATE;
+    }
+    if (cfg->kind == B200TRACK_OCSORT) {
+        if (cfg->use_byte) { set_error("OC-SORT use_byte=True is not built (ocsort.yaml default is false)"); return B200TRACK_ERR_STATE; }
+        if (cfg->delta_t < 1 || cfg->delta_t > 3) { set_error("OC-SORT delta_t must be in [1, 3]"); return B200TRACK_ERR_ARG; }
+        if (cfg->asso_func < 0 || cfg->asso_func > B200TRACK_SIM_CENTROID) { set_error("unknown asso_func"); return B200TRACK_ERR_ARG; }
     }
     int ndev = 0;
     CU_TRY(cudaGetDeviceCount(&ndev));
@@ -128,6 +134,9 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     p.proximity_thresh = cfg->proximity_thresh;
     p.appearance_thresh = cfg->appearance_thresh;
     p.max_time_lost = (int)(cfg->frame_rate / 30.0 * cfg->track_buffer);   // byte_tracker.py:128-129
+    p.det_thresh = cfg->det_thresh; p.iou_thresh = cfg->iou_thresh; p.inertia = cfg->inertia;
+    p.max_age = cfg->max_age; p.min_hits = cfg->min_hits; p.delta_t = cfg->delta_t; p.asso_func = cfg->asso_func;
+    if (cfg->kind == B200TRACK_OCSORT) { ctx->nf = B200_OC_NF; ctx->ni = B200_OC_NI; }
     ctx->kf_kind = cfg->kind == B200TRACK_BOTSORT ? B200TRACK_KF_XYWH : B200TRACK_KF_XYAH;
     ctx->variant = b200::bytetrack_step_variant(cfg->max_tracks, cfg->max_dets);
     if (ctx->variant < 0) { set_error("no kernel variant covers max_tracks / max_dets"); delete ctx; return B200TRACK_ERR_CAPACITY; }
@@ -136,8 +145,10 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     int rc = 0;
     auto fail = [&](int code) { b200track_destroy(ctx); return code; };
 #define CU_TRY_CTX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return fail(B200TRACK_ERR_CUDA); } } while (0)
-    CU_TRY_CTX(cudaMalloc(&p.state_f, S * B200_NF * T * sizeof(double)));
-    CU_TRY_CTX(cudaMalloc(&p.state_i, S * B200_NI * T * sizeof(int)));
+    CU_TRY_CTX(cudaMalloc(&p.state_f, S * ctx->nf * T * sizeof(double)));
+    CU_TRY_CTX(cudaMalloc(&p.state_i, S * ctx->ni * T * sizeof(int)));
+    if (cfg->kind == B200TRACK_OCSORT)
+        CU_TRY_CTX(cudaMalloc(&p.scratch, S * T * (size_t)b200::step_variant_dmax(ctx->variant) * sizeof(double)));
     CU_TRY_CTX(cudaMalloc(&p.counts, S * 4 * sizeof(int)));
     CU_TRY_CTX(cudaMalloc(&p.track_updates, S * sizeof(unsigned long long)));
     CU_TRY_CTX(cudaMalloc(&p.err, sizeof(int)));
@@ -155,7 +166,7 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.out_ready, cudaEventDisableTiming));
     }
-    const size_t smem = b200::bytetrack_step_smem(ctx->variant);
+    const size_t smem = cfg->kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant) : b200::bytetrack_step_smem(ctx->variant);
     int max_smem = 0;
     CU_TRY_CTX(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     if (smem > (size_t)max_smem) {
@@ -170,10 +181,11 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
 
 static int launch_step(b200track_ctx* ctx, const double* d_dets, const int32_t* d_ndets, const float* d_feats,
                        int32_t img_h, int32_t img_w, double* d_out, int32_t* d_nout, cudaStream_t st) {
-    (void)img_h; (void)img_w;
     b200::StepParams p = ctx->p;
     p.dets = d_dets; p.ndets = d_ndets; p.feats = d_feats; p.out = d_out; p.nout = d_nout;
-    CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, ctx->variant, st));
+    p.img_h = img_h; p.img_w = img_w;
+    if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
+    else CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, ctx->variant, st));
     ctx->launches += 1;
     return 0;
 }
@@ -287,8 +299,8 @@ extern "C" int b200track_phase_cycles(b200track_ctx* ctx, uint64_t* h_out16, int
 
 extern "C" int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state, uint64_t* h_smem) {
     if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
-    if (h_state) *h_state = (uint64_t)ctx->tcap * B200_SLOT_BYTES + 4 * sizeof(int) + sizeof(unsigned long long);
-    if (h_smem) *h_smem = b200::bytetrack_step_smem(ctx->variant);
+    if (h_state) *h_state = (uint64_t)ctx->tcap * (ctx->nf * 8 + ctx->ni * 4) + 4 * sizeof(int) + sizeof(unsigned long long);
+    if (h_smem) *h_smem = ctx->cfg.kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant) : b200::bytetrack_step_smem(ctx->variant);
     return 0;
 }
 
@@ -299,11 +311,52 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
     CU_TRY(cudaSetDevice(ctx->cfg.device));
     CU_TRY(cudaDeviceSynchronize());
     const size_t T = ctx->tcap, s = stream_index;
-    std::vector<double> f(B200_NF * T);
-    std::vector<int> iv(B200_NI * T);
+    std::vector<double> f((size_t)ctx->nf * T);
+    std::vector<int> iv((size_t)ctx->ni * T);
     CU_TRY(cudaMemcpy(h_counts, ctx->p.counts + 4 * s, 4 * sizeof(int), cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(f.data(), ctx->p.state_f + s * B200_NF * T, f.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    CU_TRY(cudaMemcpy(iv.data(), ctx->p.state_i + s * B200_NI * T, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(f.data(), ctx->p.state_f + s * ctx->nf * T, f.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(iv.data(), ctx->p.state_i + s * ctx->ni * T, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    if (ctx->cfg.kind == B200TRACK_OCSORT) {
+        // alive slots in list order; h_rec = id, age, time_since_update, hits, hit_streak, observed;
+        // h_mean[8] = x[7], has-observation flag; h_cov = dense 7x7 P in the first 49 entries;
+        // h_aux = conf, cls, det_ind
+        int k = 0;
+        for (int t = 0; t < h_counts[0] && t < ctx->cfg.max_tracks; ++t) {
+            const int fl = iv[B200_OCI_FLAGS * T + t];
+            if (!(fl & 8)) continue;
+            if (h_rec) {
+                int32_t* r = h_rec + 6 * k;
+                r[0] = iv[B200_OCI_ID * T + t]; r[1] = iv[B200_OCI_AGE * T + t]; r[2] = iv[B200_OCI_TSU * T + t];
+                r[3] = iv[B200_OCI_HITS * T + t]; r[4] = iv[B200_OCI_STREAK * T + t]; r[5] = fl & B200_OCF_OBSERVED;
+            }
+            if (h_mean) {
+                for (int c = 0; c < 7; ++c) h_mean[8 * k + c] = f[(B200_OC_X + c) * T + t];
+                h_mean[8 * k + 7] = (fl & B200_OCF_HASOBS) ? 1.0 : 0.0;
+            }
+            if (h_cov) {
+                double* c = h_cov + 64 * k;
+                for (int q = 0; q < 64; ++q) c[q] = 0.0;
+                for (int a = 0; a < 3; ++a) {
+                    c[a * 7 + a] = f[(B200_OC_P + 3 * a + 0) * T + t];
+                    c[a * 7 + a + 4] = c[(a + 4) * 7 + a] = f[(B200_OC_P + 3 * a + 1) * T + t];
+                    c[(a + 4) * 7 + a + 4] = f[(B200_OC_P + 3 * a + 2) * T + t];
+                }
+                c[3 * 7 + 3] = f[(B200_OC_P + 9) * T + t];
+                // velocity and last observation ride in the unused tail of the 64-entry row
+                c[49] = f[(B200_OC_VEL + 0) * T + t]; c[50] = f[(B200_OC_VEL + 1) * T + t];
+                for (int q = 0; q < 4; ++q) c[51 + q] = (fl & B200_OCF_HASOBS) ? f[(B200_OC_LAST + q) * T + t] : -1.0;
+                c[55] = (fl & B200_OCF_HASOBS) ? f[B200_OC_CONF * T + t] : -1.0;
+            }
+            if (h_aux) {
+                h_aux[3 * k + 0] = f[B200_OC_CONF * T + t];
+                h_aux[3 * k + 1] = f[B200_OC_CLS * T + t];
+                h_aux[3 * k + 2] = (double)iv[B200_OCI_DET * T + t];
+            }
+            ++k;
+        }
+        h_counts[0] = k; h_counts[1] = 0;
+        return 0;
+    }
     const int n = h_counts[0] + h_counts[1];
     for (int t = 0; t < n && t < ctx->cfg.max_tracks; ++t) {
         const int fl = iv[B200_TI_FLAGS * T + t];

@@ -703,6 +703,7 @@ int bytetrack_step_variant(int max_tracks, int max_dets) {
     return -1;
 }
 int bytetrack_step_tmax(int variant) { return kVariants[variant].tmax; }
+int step_variant_dmax(int variant) { return kVariants[variant].dmax; }
 size_t bytetrack_step_smem(int variant) {
     switch (variant) {
         case 0: return sizeof(StepSmem<64, 64>);

@@ -36,3 +36,33 @@
 
 // bytes a track slot occupies in HBM (one direction)
 #define B200_SLOT_BYTES (B200_NF * 8 + B200_NI * 4)
+
+// ---- OC-SORT slot (ocsort_step.cu) -------------------------------------------------------
+// Same stream-major, component-planar arrangement; slots [0, n) are the reference's
+// `self.trackers` list in list order.  fp64 components:
+#define B200_OC_NF 58
+#define B200_OC_X 0          // x[7] = x, y, s, r, vx, vy, vs
+#define B200_OC_P 7          // 3 x (pp, pv, vv) for (x,vx) (y,vy) (s,vs), then P_rr            (10)
+#define B200_OC_LAST 17      // last_observation box (valid when the has-observation flag is set)
+#define B200_OC_CONF 21
+#define B200_OC_CLS 22
+#define B200_OC_VEL 23       // velocity = (dy, dx) / norm, zeros while None
+#define B200_OC_RING 25      // observations of the last 3 ages: ring[age % 3][4]
+#define B200_OC_SX 37        // frozen x   (attr_saved, written at the first missed frame)
+#define B200_OC_SP 44        // frozen P   (10, same order as B200_OC_P)
+#define B200_OC_LASTZ 54     // history_obs[index1]: last measurement [x, y, s, r] before a gap
+// int32 components:
+#define B200_OC_NI 10
+#define B200_OCI_ID 0
+#define B200_OCI_AGE 1
+#define B200_OCI_TSU 2       // time_since_update
+#define B200_OCI_HITS 3
+#define B200_OCI_STREAK 4
+#define B200_OCI_DET 5
+#define B200_OCI_RINGAGE 6   // age key of ring[0..2], -1 = empty
+#define B200_OCI_FLAGS 9     // bit 0 kf.observed, bit 1 kf.attr_saved is not None, bit 2 last_observation is real
+#define B200_OCF_OBSERVED 1
+#define B200_OCF_SAVED 2
+#define B200_OCF_HASOBS 4
+// regular per-step traffic of a slot: x, P, last, conf, cls, vel, ring (37 doubles) + 10 ints
+#define B200_OC_SLOT_BYTES (37 * 8 + B200_OC_NI * 4)

@@ -1,0 +1,680 @@
+// OC-SORT frame step for many independent streams: one kernel launch per frame, one CTA per
+// stream, one thread per tracker slot.
+//
+// Replaces OCSort.update (boxmot/trackers/ocsort/ocsort.py:218-379) and what it calls:
+// KalmanBoxTracker.predict / update :130-181 -> KalmanFilter.predict / update / freeze /
+// unfreeze (boxmot/motion/kalman_filters/ocsort_kf.py:339-526), associate
+// (boxmot/utils/association.py:111-201: velocity-direction cost, permutation shortcut, lapjv
+// without a limit), the observation-centric recovery round :319-345, new trackers :351-353 and
+// the reversed output scan :354-379.
+//
+// The 7-d filter (F couples x-vx, y-vy, s-vs; H = [I 0]; diagonal Q, R) keeps an exactly
+// block-sparse covariance: three position/velocity 2x2 blocks and P_rr, so S is diagonal and the
+// reference's inv(S) / Joseph form reduce to a handful of scalar operations per axis.
+//
+// Unlike ByteTrack the assignment is DENSE: lapjv is called without a cost limit on
+// -(similarity + angle cost), every min(D, T) row is matched and pairs are filtered by the
+// similarity threshold afterwards, so nothing can be pruned.  The D x T cost matrix of a stream
+// is written once to a per-stream scratch block (L2 resident) while the column minima are
+// accumulated, then solved by lap_dense.cuh.  Slots are updated in place; a tracker that dies
+// leaves a hole and the stream is compacted only when its slot range runs short.
+#include "boxes.cuh"
+#include "lap_dense.cuh"
+#include "layout.h"
+#include "step_params.h"
+
+namespace b200 {
+namespace {
+
+constexpr int DS_NONE = 0, DS_FREE0 = 1, DS_FREE1 = 2, DS_MATCHED = 3;
+constexpr int OCF_ALIVE = 8;
+// canonical tie-break of the no-limit assignment (oracle/lap.py "Ties"): cost[r][c] += 2^-50 * (r * C + c)
+constexpr double TIE_EPS = 8.8817841970012523e-16;
+
+template <int TMAX, int DMAX>
+struct alignas(16) OcSmem {
+    double x[7][TMAX];
+    double tbox[4][TMAX];           // predicted box, convert_x_to_bbox
+    double lbox[4][TMAX];           // last_observation box (placeholder -1)
+    double kc[2][TMAX];             // centre of k_previous_obs
+    double vel[2][TMAX];            // (vy, vx)
+    double dbox[4][DMAX];
+    double dconf[DMAX], dcls[DMAX];
+    double u[DMAX], v[TMAX], dist[TMAX];
+    double red_v[32], sh_d[4];
+    unsigned long long scratch[40];
+    int pred[TMAX], xr[DMAX], yc[TMAX], claim[DMAX], partner[TMAX];
+    int red_i[32], sh_i[4];
+    int rowcnt[DMAX], rowmatch[DMAX];
+    int misc[8];
+    short hd[DMAX], ht[TMAX], dmatch[DMAX], tmatch[TMAX], ud[DMAX], ut[TMAX];
+    unsigned char scn[TMAX], kvalid[TMAX], alive[TMAX], dstate[DMAX];
+};
+
+__device__ __forceinline__ Box oc_x_to_box(double x, double y, double s, double r) {
+    const double w = sqrt(xmul(s, r));
+    const double h = xdiv(s, w);
+    Box b;
+    b.x1 = xsub(x, xmul(w, 0.5)); b.y1 = xsub(y, xmul(h, 0.5));
+    b.x2 = xadd(x, xmul(w, 0.5)); b.y2 = xadd(y, xmul(h, 0.5));
+    return b;
+}
+__device__ __forceinline__ void oc_box_to_z(double x1, double y1, double x2, double y2, double* z) {
+    const double w = xsub(x2, x1), h = xsub(y2, y1);
+    z[0] = xadd(x1, xmul(w, 0.5));
+    z[1] = xadd(y1, xmul(h, 0.5));
+    z[2] = xmul(w, h);
+    z[3] = xdiv(w, xadd(h, 1e-6));
+}
+
+// run_asso_func (iou.py:191-212).  For iou / giou a pair of disjoint, non-degenerate boxes gives
+// exactly +0.0 in the reference's arithmetic (inter = 0, (enc - 0) / enc = 1), so it is returned
+// without the divisions; everything else is evaluated in full.
+__device__ __forceinline__ double oc_sim(int func, const Box& a, const Box& b, double W, double H) {
+    if (func <= 1 && !box_overlap(a, b)) {
+        const double un = xadd(xmul(xsub(a.x2, a.x1), xsub(a.y2, a.y1)), xmul(xsub(b.x2, b.x1), xsub(b.y2, b.y1)));
+        const double ew = xsub(fmax(a.x2, b.x2), fmin(a.x1, b.x1)), eh = xsub(fmax(a.y2, b.y2), fmin(a.y1, b.y1));
+        if (un > 0.0 && un < 1e300 && (func == 0 || (xmul(ew, eh) > 0.0 && xmul(ew, eh) < 1e300))) return 0.0;
+    }
+    switch (func) {
+        case 1: return box_giou(a, b);
+        case 2: return box_diou(a, b);
+        case 3: return box_ciou(a, b);
+        case 4: return box_centroid(a, b, W, H);
+        default: return box_iou(a, b);
+    }
+}
+
+// velocity-direction consistency cost of (track, detection), association.py:134-154
+__device__ __forceinline__ double oc_angle(double vy, double vx, double kcx, double kcy, bool valid, double dcx, double dcy,
+                                           double inertia, double score) {
+    const double PI = 3.141592653589793;
+    const double dx = xsub(dcx, kcx), dy = xsub(dcy, kcy);
+    const double norm = xadd(sqrt(xadd(xmul(dx, dx), xmul(dy, dy))), 1e-6);
+    const double X = xdiv(dx, norm), Y = xdiv(dy, norm);
+    double c = xadd(xmul(vx, X), xmul(vy, Y));
+    c = fmin(fmax(c, -1.0), 1.0);
+    const double diff = xdiv(xsub(xdiv(PI, 2.0), fabs(acos(c))), PI);
+    return xmul(xmul(xmul(valid ? 1.0 : 0.0, diff), inertia), score);
+}
+
+struct OcKf {
+    double x[7];
+    double pp[3], pv[3], vv[3], prr;
+};
+
+__device__ __forceinline__ void oc_predict_cov(OcKf& k) {
+    const double qv[3] = {0.01, 0.01, 0.0001};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double a = xadd(k.pp[i], k.pv[i]);
+        const double b = xadd(k.pv[i], k.vv[i]);
+        k.pp[i] = xadd(xadd(a, b), 1.0);
+        k.pv[i] = b;
+        k.vv[i] = xadd(k.vv[i], qv[i]);
+    }
+    k.prr = xadd(k.prr, 1.0);
+}
+__device__ __forceinline__ void oc_predict_full(OcKf& k) {          // kf.predict (no tracker-level guard)
+#pragma unroll
+    for (int i = 0; i < 3; ++i) k.x[i] = xadd(k.x[i], k.x[i + 4]);
+    oc_predict_cov(k);
+}
+// Joseph-form update, ocsort_kf.py:496-521, on the block-sparse covariance
+__device__ __forceinline__ void oc_correct(OcKf& k, const double* z) {
+    const double R[4] = {1.0, 1.0, 10.0, 10.0};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double S = xadd(k.pp[i], R[i]);
+        const double si = xdiv(1.0, S);
+        const double kp = xmul(k.pp[i], si), kv = xmul(k.pv[i], si);
+        const double y = xsub(z[i], k.x[i]);
+        k.x[i] = xadd(k.x[i], xmul(kp, y));
+        k.x[i + 4] = xadd(k.x[i + 4], xmul(kv, y));
+        const double a = xsub(1.0, kp);
+        const double ap00 = xmul(a, k.pp[i]), ap01 = xmul(a, k.pv[i]);
+        const double ap10 = xadd(xmul(-kv, k.pp[i]), k.pv[i]), ap11 = xadd(xmul(-kv, k.pv[i]), k.vv[i]);
+        const double n00 = xmul(ap00, a);
+        const double n01 = xadd(xmul(ap00, -kv), ap01);
+        const double n11 = xadd(xmul(ap10, -kv), ap11);
+        const double krp = xmul(kp, R[i]), krv = xmul(kv, R[i]);
+        k.pp[i] = xadd(n00, xmul(krp, kp));
+        k.pv[i] = xadd(n01, xmul(krp, kv));
+        k.vv[i] = xadd(n11, xmul(krv, kv));
+    }
+    {
+        const double S = xadd(k.prr, R[3]);
+        const double si = xdiv(1.0, S);
+        const double kr = xmul(k.prr, si);
+        const double y = xsub(z[3], k.x[3]);
+        k.x[3] = xadd(k.x[3], xmul(kr, y));
+        const double a = xsub(1.0, kr);
+        k.prr = xadd(xmul(xmul(a, k.prr), a), xmul(xmul(kr, R[3]), kr));
+    }
+}
+
+template <int NT, class SM>
+__device__ __forceinline__ DenseLap make_dense(SM& sm) {
+    DenseLap w;
+    w.u = sm.u; w.v = sm.v; w.dist = sm.dist; w.pred = sm.pred; w.xr = sm.xr; w.yc = sm.yc; w.claim = sm.claim;
+    w.scn = sm.scn; w.red_v = sm.red_v; w.red_i = sm.red_i; w.sh_d = sm.sh_d; w.sh_i = sm.sh_i;
+    return w;
+}
+
+// block-wide max of a double and of two ints (all threads get the results)
+template <int NT, class SM>
+__device__ __forceinline__ void block_max3(SM& sm, double& d, int& a, int& b) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int s = 16; s; s >>= 1) {
+        d = fmax(d, __shfl_xor_sync(0xffffffffu, d, s));
+        a = max(a, __shfl_xor_sync(0xffffffffu, a, s));
+        b = max(b, __shfl_xor_sync(0xffffffffu, b, s));
+    }
+    __syncthreads();
+    if (lane == 0) { sm.red_v[warp] = d; sm.red_i[warp] = a; sm.pred[warp] = b; }
+    __syncthreads();
+    d = sm.red_v[0]; a = sm.red_i[0]; b = sm.pred[0];
+    for (int k = 1; k < NT / 32; ++k) { d = fmax(d, sm.red_v[k]); a = max(a, sm.red_i[k]); b = max(b, sm.pred[k]); }
+    __syncthreads();
+}
+
+template <int NT, int TMAX, int DMAX>
+__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : (NT == 256 ? 2 : (NT == 128 ? 4 : 8))))
+ocsort_step_kernel(const StepParams p) {
+    static_assert(NT == TMAX && DMAX <= NT, "one thread per tracker slot; detections fit one pass");
+    using SM = OcSmem<TMAX, DMAX>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SM& sm = *reinterpret_cast<SM*>(smem_raw);
+    const int s = blockIdx.x, tid = threadIdx.x, t = tid;
+    int* counts = p.counts + 4 * s;
+    const int n0 = counts[0], id0 = counts[2], frame = counts[3] + 1;
+    int nd = p.ndets[s];
+    int err = 0;
+    const int dcap = min(DMAX, p.max_dets), tcap = min(TMAX, p.max_tracks);
+    if (nd > dcap) { nd = dcap; err |= B200_ERR_DET_OVERFLOW; }
+    if (nd < 0) nd = 0;
+    double* gf = p.state_f + (size_t)s * B200_OC_NF * TMAX;
+    int* gi = p.state_i + (size_t)s * B200_OC_NI * TMAX;
+    double* C = p.scratch + (size_t)s * TMAX * DMAX;
+    const double thr = p.iou_thresh, W = p.img_w, H = p.img_h;
+    const int func = p.asso_func;
+
+    // ---- HBM -> shared memory: detections, hot part of the tracker state --------------------
+    {
+        const double* g = p.dets + (size_t)s * p.max_dets * 6;
+        for (int i = tid; i < nd * 6; i += NT) {
+            const double val = g[i];
+            const int j = i / 6, c = i - 6 * j;
+            if (c < 4) sm.dbox[c][j] = val;
+            else if (c == 4) sm.dconf[j] = val;
+            else sm.dcls[j] = val;
+        }
+    }
+    int fl = 0, age = 0, tsu = 0, streak = 0;
+    bool live = false;
+    if (t < n0) {
+        fl = gi[B200_OCI_FLAGS * TMAX + t];
+        live = fl & OCF_ALIVE;
+    }
+    if (live) {
+        age = gi[B200_OCI_AGE * TMAX + t];
+        tsu = gi[B200_OCI_TSU * TMAX + t];
+        streak = gi[B200_OCI_STREAK * TMAX + t];
+        double x[7];
+#pragma unroll
+        for (int c = 0; c < 7; ++c) x[c] = gf[(B200_OC_X + c) * TMAX + t];
+        // KalmanBoxTracker.predict (ocsort.py:168-181); the covariance half is deferred
+        if (xadd(x[6], x[2]) <= 0.0) x[6] = xmul(x[6], 0.0);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[c] = xadd(x[c], x[c + 4]);
+        age += 1;
+        if (tsu > 0) streak = 0;
+        tsu += 1;
+#pragma unroll
+        for (int c = 0; c < 7; ++c) sm.x[c][t] = x[c];
+        const Box b = oc_x_to_box(x[0], x[1], x[2], x[3]);
+        sm.tbox[0][t] = b.x1; sm.tbox[1][t] = b.y1; sm.tbox[2][t] = b.x2; sm.tbox[3][t] = b.y2;
+        if (isnan(b.x1) || isnan(b.y1) || isnan(b.x2) || isnan(b.y2)) { live = false; fl &= ~OCF_ALIVE; }   // :260-264
+        const bool hasobs = fl & B200_OCF_HASOBS;
+        double l[4] = {-1.0, -1.0, -1.0, -1.0};
+        if (hasobs) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) l[c] = gf[(B200_OC_LAST + c) * TMAX + t];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) sm.lbox[c][t] = l[c];
+        sm.vel[0][t] = gf[(B200_OC_VEL + 0) * TMAX + t];
+        sm.vel[1][t] = gf[(B200_OC_VEL + 1) * TMAX + t];
+        // k_previous_obs (ocsort.py:14-22): oldest observation among ages age-3 .. age-1, else the newest
+        double kb[4] = {l[0], l[1], l[2], l[3]};
+        if (hasobs) {
+            const int ra[3] = {gi[(B200_OCI_RINGAGE + 0) * TMAX + t], gi[(B200_OCI_RINGAGE + 1) * TMAX + t], gi[(B200_OCI_RINGAGE + 2) * TMAX + t]};
+            for (int dt = p.delta_t; dt >= 1; --dt) {
+                const int a = age - dt;
+                if (a < 0) continue;
+                const int slot = a % 3;
+                if (dt <= 3 && ra[slot] == a) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) kb[c] = gf[(B200_OC_RING + 4 * slot + c) * TMAX + t];
+                    break;
+                }
+            }
+        }
+        sm.kc[0][t] = xdiv(xadd(kb[0], kb[2]), 2.0);
+        sm.kc[1][t] = xdiv(xadd(kb[1], kb[3]), 2.0);
+        sm.kvalid[t] = hasobs;
+    }
+    if (t < TMAX) { sm.alive[t] = live; sm.tmatch[t] = -1; }
+    if (tid < DMAX) { sm.dmatch[tid] = -1; sm.rowcnt[tid] = 0; sm.rowmatch[tid] = -1; }
+    __syncthreads();
+    if (tid < DMAX) sm.dstate[tid] = (tid < nd && sm.dconf[tid] > p.det_thresh) ? DS_FREE0 : DS_NONE;    // ocsort.py:250-251
+
+    // compact row (high detections) and column (alive trackers) lists
+    int R, Cn;
+    {
+        const bool isrow = tid < nd && sm.dconf[tid] > p.det_thresh;
+        const unsigned long long val = (isrow ? 1ull : 0ull) | (live ? (1ull << 16) : 0ull);
+        unsigned long long tot;
+        const unsigned long long ex = block_exscan<NT>(val, sm.scratch, tot);
+        if (isrow) sm.hd[ex & 0xffff] = (short)tid;
+        if (live) sm.ht[(ex >> 16) & 0xffff] = (short)t;
+        R = (int)(tot & 0xffff); Cn = (int)((tot >> 16) & 0xffff);
+        __syncthreads();
+    }
+
+    // ---- first round: associate(dets, trks, ...) ------------------------------------------------
+    if (R > 0 && Cn > 0) {
+        double mx = -1e300;
+        int ccnt = 0, dummy = 0;
+        if (tid < Cn) {
+            const int sl = sm.ht[tid];
+            const Box tb = {sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]};
+            const double vy = sm.vel[0][sl], vx = sm.vel[1][sl], kcx = sm.kc[0][sl], kcy = sm.kc[1][sl];
+            const bool valid = sm.kvalid[sl];
+            const bool moving = valid && !(vx == 0.0 && vy == 0.0);
+            for (int r = 0; r < R; ++r) {
+                const int j = sm.hd[r];
+                const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
+                const double sim = oc_sim(func, db, tb, W, H);
+                double ang = 0.0;
+                if (moving) {
+                    const double dcx = xdiv(xadd(db.x1, db.x2), 2.0), dcy = xdiv(xadd(db.y1, db.y2), 2.0);
+                    ang = oc_angle(vy, vx, kcx, kcy, valid, dcx, dcy, p.inertia, sm.dconf[j]);
+                }
+                const double c = xadd(-xadd(xadd(sim, ang), 0.0), xmul((double)(r * Cn + tid), TIE_EPS));
+                C[(size_t)r * TMAX + tid] = c;
+                mx = fmax(mx, c);
+                if (sim > thr) { ++ccnt; atomicAdd(&sm.rowcnt[r], 1); sm.rowmatch[r] = tid; }
+            }
+        }
+        block_max3<NT>(sm, mx, ccnt, dummy);
+        int rc = tid < R ? sm.rowcnt[tid] : 0;
+        double dd = 0.0;
+        block_max3<NT>(sm, dd, rc, dummy);
+        const bool shortcut = (rc == 1 && ccnt == 1);                          // association.py:157-159
+        if (shortcut) {
+            if (tid < R) sm.xr[tid] = sm.rowcnt[tid] == 1 ? sm.rowmatch[tid] : -1;
+            __syncthreads();
+        } else {
+            const DenseLap w = make_dense<NT>(sm);
+            const double lambda = 2.0 * (mx + 1.0);
+            dense_lap_init<NT>(w, C, TMAX, R, Cn, lambda);
+            dense_lap_augment<NT>(w, C, TMAX, R, Cn, lambda);
+        }
+        // matched pairs below the similarity threshold fall back to unmatched (association.py:187-193)
+        if (tid < R) {
+            const int c = sm.xr[tid];
+            const int j = sm.hd[tid];
+            if (c >= 0) {
+                const int sl = sm.ht[c];
+                const Box tb = {sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]};
+                const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
+                if (oc_sim(func, db, tb, W, H) < thr) sm.dstate[j] = DS_FREE1;
+                else { sm.dstate[j] = DS_MATCHED; sm.dmatch[j] = (short)sl; sm.tmatch[sl] = (short)j; }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- observation-centric recovery (ocsort.py:319-345): leftover detections x last observations
+    bool ocr_ran = false;
+    // unmatched lists in associate()'s order (association.py:179-193): never matched first (ascending),
+    // then the members of low-similarity matches in match order (= ascending detection index)
+    {
+        const int ds = tid < DMAX ? sm.dstate[tid] : DS_NONE;
+        // mark trackers that sit in a low-similarity match
+        if (t < TMAX) sm.partner[t] = -1;
+        __syncthreads();
+        if (tid < R && sm.xr[tid] >= 0 && sm.dstate[sm.hd[tid]] == DS_FREE1) sm.partner[sm.ht[sm.xr[tid]]] = tid;   // slot -> row of its partner
+        __syncthreads();
+        const bool ufree = live && sm.tmatch[t] < 0;
+        const bool ufree1 = ufree && (R > 0 && Cn > 0) && sm.partner[t] >= 0;
+        const bool ufree0 = ufree && !ufree1;
+        const unsigned long long val = (ds == DS_FREE0 ? 1ull : 0ull) | (ds == DS_FREE1 ? (1ull << 16) : 0ull) | (ufree0 ? (1ull << 32) : 0ull);
+        unsigned long long tot;
+        const unsigned long long ex = block_exscan<NT>(val, sm.scratch, tot);
+        const int n0d = (int)(tot & 0xffff), n1d = (int)((tot >> 16) & 0xffff), n0t = (int)((tot >> 32) & 0xffff);
+        if (ds == DS_FREE0) sm.ud[ex & 0xffff] = (short)tid;
+        if (ds == DS_FREE1) sm.ud[n0d + ((ex >> 16) & 0xffff)] = (short)tid;
+        if (ufree0) sm.ut[(ex >> 32) & 0xffff] = (short)t;
+        // low-similarity trackers follow in the order of their partner detections
+        if (ds == DS_FREE1) sm.claim[tid] = (int)((ex >> 16) & 0xffff);          // rank of this detection among FREE1
+        __syncthreads();
+        if (ufree1) sm.ut[n0t + sm.claim[sm.hd[sm.partner[t]]]] = (short)t;
+        const int nUd = n0d + n1d, nUt = n0t + n1d;
+        __syncthreads();
+        if (nUd > 0 && nUt > 0) {
+            double mx = -1e300, smax = -1e300;
+            int d1 = 0, d2 = 0;
+            if (tid < nUt) {
+                const int sl = sm.ut[tid];
+                const Box lb = {sm.lbox[0][sl], sm.lbox[1][sl], sm.lbox[2][sl], sm.lbox[3][sl]};
+                for (int r = 0; r < nUd; ++r) {
+                    const int j = sm.ud[r];
+                    const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
+                    const double sim = oc_sim(func, db, lb, W, H);
+                    const double c = xadd(-sim, xmul((double)(r * nUt + tid), TIE_EPS));
+                    C[(size_t)r * TMAX + tid] = c;
+                    mx = fmax(mx, c);
+                    smax = fmax(smax, sim);
+                }
+            }
+            block_max3<NT>(sm, smax, d1, d2);
+            block_max3<NT>(sm, mx, d1, d2);
+            if (smax > thr) {
+                ocr_ran = true;
+                const DenseLap w = make_dense<NT>(sm);
+                const double lambda = 2.0 * (mx + 1.0);
+                dense_lap_init<NT>(w, C, TMAX, nUd, nUt, lambda);
+                dense_lap_augment<NT>(w, C, TMAX, nUd, nUt, lambda);
+                if (tid < nUd) {
+                    const int c = sm.xr[tid];
+                    if (c >= 0) {
+                        const int j = sm.ud[tid], sl = sm.ut[c];
+                        const Box lb = {sm.lbox[0][sl], sm.lbox[1][sl], sm.lbox[2][sl], sm.lbox[3][sl]};
+                        const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
+                        if (!(oc_sim(func, db, lb, W, H) < thr)) {
+                            sm.dstate[j] = DS_MATCHED; sm.dmatch[j] = (short)sl; sm.tmatch[sl] = (short)j;
+                        }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+    }
+
+    // ---- deferred Kalman work and bookkeeping, thread t = slot t ---------------------------------
+    int hits = 0, det_ind = 0, tid_id = 0;
+    double conf = 0.0, cls = 0.0;
+    OcKf k;
+    if (live) {
+#pragma unroll
+        for (int c = 0; c < 7; ++c) k.x[c] = sm.x[c][t];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            k.pp[i] = gf[(B200_OC_P + 3 * i + 0) * TMAX + t];
+            k.pv[i] = gf[(B200_OC_P + 3 * i + 1) * TMAX + t];
+            k.vv[i] = gf[(B200_OC_P + 3 * i + 2) * TMAX + t];
+        }
+        k.prr = gf[(B200_OC_P + 9) * TMAX + t];
+        oc_predict_cov(k);
+        hits = gi[B200_OCI_HITS * TMAX + t];
+        det_ind = gi[B200_OCI_DET * TMAX + t];
+        tid_id = gi[B200_OCI_ID * TMAX + t];
+        conf = gf[B200_OC_CONF * TMAX + t];
+        cls = gf[B200_OC_CLS * TMAX + t];
+        const int j = sm.tmatch[t];
+        if (j >= 0) {                                                   // KalmanBoxTracker.update(bbox), ocsort.py:130-164
+            const double b0 = sm.dbox[0][j], b1 = sm.dbox[1][j], b2 = sm.dbox[2][j], b3 = sm.dbox[3][j];
+            const bool hasobs = fl & B200_OCF_HASOBS;
+            const double lsum = hasobs ? xadd(xadd(xadd(xadd(sm.lbox[0][t], sm.lbox[1][t]), sm.lbox[2][t]), sm.lbox[3][t]), conf) : -5.0;
+            if (lsum >= 0.0) {                                          // speed_direction(previous_box, bbox)
+                const double cx2 = xdiv(xadd(b0, b2), 2.0), cy2 = xdiv(xadd(b1, b3), 2.0);
+                const double dy = xsub(cy2, sm.kc[1][t]), dx = xsub(cx2, sm.kc[0][t]);
+                const double norm = xadd(sqrt(xadd(xmul(dy, dy), xmul(dx, dx))), 1e-6);
+                gf[(B200_OC_VEL + 0) * TMAX + t] = xdiv(dy, norm);
+                gf[(B200_OC_VEL + 1) * TMAX + t] = xdiv(dx, norm);
+            }
+            conf = sm.dconf[j]; cls = sm.dcls[j]; det_ind = j;
+            gf[(B200_OC_LAST + 0) * TMAX + t] = b0; gf[(B200_OC_LAST + 1) * TMAX + t] = b1;
+            gf[(B200_OC_LAST + 2) * TMAX + t] = b2; gf[(B200_OC_LAST + 3) * TMAX + t] = b3;
+            const int rs = age % 3;
+            gf[(B200_OC_RING + 4 * rs + 0) * TMAX + t] = b0; gf[(B200_OC_RING + 4 * rs + 1) * TMAX + t] = b1;
+            gf[(B200_OC_RING + 4 * rs + 2) * TMAX + t] = b2; gf[(B200_OC_RING + 4 * rs + 3) * TMAX + t] = b3;
+            gi[(B200_OCI_RINGAGE + rs) * TMAX + t] = age;
+            double z[4];
+            oc_box_to_z(b0, b1, b2, b3, z);
+            bool virt = false;
+            double vz[4];
+            if (!(fl & B200_OCF_OBSERVED) && (fl & B200_OCF_SAVED)) {   // unfreeze: observation-centric re-update
+#pragma unroll
+                for (int c = 0; c < 7; ++c) k.x[c] = gf[(B200_OC_SX + c) * TMAX + t];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    k.pp[i] = gf[(B200_OC_SP + 3 * i + 0) * TMAX + t];
+                    k.pv[i] = gf[(B200_OC_SP + 3 * i + 1) * TMAX + t];
+                    k.vv[i] = gf[(B200_OC_SP + 3 * i + 2) * TMAX + t];
+                }
+                k.prr = gf[(B200_OC_SP + 9) * TMAX + t];
+                const double x1 = gf[(B200_OC_LASTZ + 0) * TMAX + t], y1 = gf[(B200_OC_LASTZ + 1) * TMAX + t];
+                const double s1 = gf[(B200_OC_LASTZ + 2) * TMAX + t], r1 = gf[(B200_OC_LASTZ + 3) * TMAX + t];
+                const double w1 = sqrt(xmul(s1, r1)), h1 = sqrt(xdiv(s1, r1));
+                const double w2 = sqrt(xmul(z[2], z[3])), h2 = sqrt(xdiv(z[2], z[3]));
+                const int g = tsu;                                      // index2 - index1 of history_obs
+                const double gd = (double)g;
+                const double dx = xdiv(xsub(z[0], x1), gd), dy = xdiv(xsub(z[1], y1), gd);
+                const double dw = xdiv(xsub(w2, w1), gd), dh = xdiv(xsub(h2, h1), gd);
+                for (int i = 0; i < g; ++i) {
+                    const double f = (double)(i + 1);
+                    const double w = xadd(w1, xmul(f, dw)), h = xadd(h1, xmul(f, dh));
+                    vz[0] = xadd(x1, xmul(f, dx)); vz[1] = xadd(y1, xmul(f, dy)); vz[2] = xmul(w, h); vz[3] = xdiv(w, h);
+                    oc_correct(k, vz);
+                    if (i != g - 1) oc_predict_full(k);
+                }
+                virt = g > 0;
+                fl &= ~B200_OCF_SAVED;
+            }
+            fl |= B200_OCF_OBSERVED | B200_OCF_HASOBS;
+            oc_correct(k, z);                                            // the real measurement on top
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gf[(B200_OC_LASTZ + c) * TMAX + t] = virt ? vz[c] : z[c];
+            tsu = 0; hits += 1; streak += 1;
+            sm.lbox[0][t] = b0; sm.lbox[1][t] = b1; sm.lbox[2][t] = b2; sm.lbox[3][t] = b3;
+        } else {                                                        // kf.update(None), ocsort_kf.py:465-477
+            if (fl & B200_OCF_OBSERVED) {
+#pragma unroll
+                for (int c = 0; c < 7; ++c) gf[(B200_OC_SX + c) * TMAX + t] = k.x[c];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    gf[(B200_OC_SP + 3 * i + 0) * TMAX + t] = k.pp[i];
+                    gf[(B200_OC_SP + 3 * i + 1) * TMAX + t] = k.pv[i];
+                    gf[(B200_OC_SP + 3 * i + 2) * TMAX + t] = k.vv[i];
+                }
+                gf[(B200_OC_SP + 9) * TMAX + t] = k.prr;
+                fl |= B200_OCF_SAVED;
+            }
+            fl &= ~B200_OCF_OBSERVED;
+        }
+    }
+
+    // ---- new trackers (ocsort.py:351-353) and the reversed output scan (:354-379) -------------------
+    // creation order: associate()'s unmatched list order, or ascending when the recovery round ran setdiff1d
+    const int ds = tid < DMAX ? sm.dstate[tid] : DS_NONE;
+    const bool newborn = ds == DS_FREE0 || ds == DS_FREE1;
+    bool emit_old = false, emit_new = false, die = false;
+    bool box_from_obs = false;
+    if (live) {
+        emit_old = tsu < 1 && (streak >= p.min_hits || frame <= p.min_hits);
+        die = tsu > p.max_age;
+        const double lsum = (fl & B200_OCF_HASOBS) ? xadd(xadd(xadd(xadd(sm.lbox[0][t], sm.lbox[1][t]), sm.lbox[2][t]), sm.lbox[3][t]), conf) : -5.0;
+        box_from_obs = !(lsum < 0.0);
+    }
+    if (newborn) emit_new = (0 >= p.min_hits || frame <= p.min_hits);
+    unsigned long long val = (emit_old ? 1ull : 0ull) | (emit_new ? (1ull << 10) : 0ull) | (ds == DS_FREE0 ? (1ull << 20) : 0ull) |
+                             (ds == DS_FREE1 ? (1ull << 30) : 0ull) | ((live && !die) ? (1ull << 40) : 0ull);
+    unsigned long long tot;
+    const unsigned long long ex = block_exscan<NT>(val, sm.scratch, tot);
+    const int E_old = (int)(tot & 1023), E_new = (int)((tot >> 10) & 1023);
+    const int n_free0 = (int)((tot >> 20) & 1023), n_free1 = (int)((tot >> 30) & 1023), n_keep = (int)((tot >> 40) & 1023);
+    const int n_new = n_free0 + n_free1;
+    double* gout = p.out + (size_t)s * p.max_tracks * 8;
+    if (n0 + n_new > tcap) err |= B200_ERR_TRACK_OVERFLOW;
+
+    if (live) {
+        // write the slot back in place
+#pragma unroll
+        for (int c = 0; c < 7; ++c) gf[(B200_OC_X + c) * TMAX + t] = k.x[c];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            gf[(B200_OC_P + 3 * i + 0) * TMAX + t] = k.pp[i];
+            gf[(B200_OC_P + 3 * i + 1) * TMAX + t] = k.pv[i];
+            gf[(B200_OC_P + 3 * i + 2) * TMAX + t] = k.vv[i];
+        }
+        gf[(B200_OC_P + 9) * TMAX + t] = k.prr;
+        gf[B200_OC_CONF * TMAX + t] = conf;
+        gf[B200_OC_CLS * TMAX + t] = cls;
+        gi[B200_OCI_AGE * TMAX + t] = age;
+        gi[B200_OCI_TSU * TMAX + t] = tsu;
+        gi[B200_OCI_HITS * TMAX + t] = hits;
+        gi[B200_OCI_STREAK * TMAX + t] = streak;
+        gi[B200_OCI_DET * TMAX + t] = det_ind;
+        gi[B200_OCI_FLAGS * TMAX + t] = die ? (fl & ~OCF_ALIVE) : fl;
+        if (emit_old) {
+            const int row = E_new + (E_old - 1 - (int)(ex & 1023));
+            if (row < p.max_tracks) {
+                Box b;
+                if (box_from_obs) { b.x1 = sm.lbox[0][t]; b.y1 = sm.lbox[1][t]; b.x2 = sm.lbox[2][t]; b.y2 = sm.lbox[3][t]; }
+                else b = oc_x_to_box(k.x[0], k.x[1], k.x[2], k.x[3]);
+                double* o = gout + (size_t)row * 8;
+                o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
+                o[4] = (double)(tid_id + 1); o[5] = conf; o[6] = cls; o[7] = (double)det_ind;
+            }
+        }
+    } else if (t < n0 && (fl & OCF_ALIVE) == 0 && t < TMAX) {
+        // NaN-purged this frame: make the hole permanent
+        if (gi[B200_OCI_FLAGS * TMAX + t] & OCF_ALIVE) gi[B200_OCI_FLAGS * TMAX + t] = fl;
+    }
+    if (newborn) {
+        const int j = tid;
+        int order;                      // position in the creation order
+        if (ocr_ran) order = (int)((ex >> 20) & 1023) + (int)((ex >> 30) & 1023);
+        else order = ds == DS_FREE0 ? (int)((ex >> 20) & 1023) : n_free0 + (int)((ex >> 30) & 1023);
+        const int dst = n0 + order;
+        const int id = id0 + order;
+        double z[4];
+        oc_box_to_z(sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j], z);
+        if (dst < tcap) {
+            const double P0[10] = {10.0, 0.0, 1e4, 10.0, 0.0, 1e4, 10.0, 0.0, 1e4, 10.0};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { gf[(B200_OC_X + c) * TMAX + dst] = z[c]; gf[(B200_OC_LAST + c) * TMAX + dst] = -1.0; }
+#pragma unroll
+            for (int c = 4; c < 7; ++c) gf[(B200_OC_X + c) * TMAX + dst] = 0.0;
+#pragma unroll
+            for (int c = 0; c < 10; ++c) gf[(B200_OC_P + c) * TMAX + dst] = P0[c];
+            gf[B200_OC_CONF * TMAX + dst] = sm.dconf[j];
+            gf[B200_OC_CLS * TMAX + dst] = sm.dcls[j];
+            gf[(B200_OC_VEL + 0) * TMAX + dst] = 0.0; gf[(B200_OC_VEL + 1) * TMAX + dst] = 0.0;
+            gi[B200_OCI_ID * TMAX + dst] = id;
+            gi[B200_OCI_AGE * TMAX + dst] = 0;
+            gi[B200_OCI_TSU * TMAX + dst] = 0;
+            gi[B200_OCI_HITS * TMAX + dst] = 0;
+            gi[B200_OCI_STREAK * TMAX + dst] = 0;
+            gi[B200_OCI_DET * TMAX + dst] = j;
+            gi[(B200_OCI_RINGAGE + 0) * TMAX + dst] = -1; gi[(B200_OCI_RINGAGE + 1) * TMAX + dst] = -1; gi[(B200_OCI_RINGAGE + 2) * TMAX + dst] = -1;
+            gi[B200_OCI_FLAGS * TMAX + dst] = OCF_ALIVE;
+        }
+        if (emit_new) {
+            // reversed list order: the newest tracker first; rows of the new trackers precede the old ones
+            const int row = n_new - 1 - order;
+            if (row < p.max_tracks) {
+                const Box b = oc_x_to_box(z[0], z[1], z[2], z[3]);
+                double* o = gout + (size_t)row * 8;
+                o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
+                o[4] = (double)(id + 1); o[5] = sm.dconf[j]; o[6] = sm.dcls[j]; o[7] = (double)j;
+            }
+        }
+    }
+    const int n1 = min(n0 + n_new, tcap);
+    const int alive_after = n_keep + min(n_new, tcap - n0 > 0 ? tcap - n0 : 0);
+    __syncthreads();
+
+    // ---- compaction, only when the slot range runs short for the next frame ----------------------
+    int n_final = n1;
+    if (n1 > alive_after && n1 + dcap > tcap) {
+        bool lv = false;
+        if (t < n1) lv = gi[B200_OCI_FLAGS * TMAX + t] & OCF_ALIVE;
+        unsigned long long tt;
+        const int dst = (int)block_exscan<NT>(lv ? 1ull : 0ull, sm.scratch, tt);
+        n_final = (int)tt;
+        for (int c0 = 0; c0 < B200_OC_NF; c0 += 8) {
+            double tmp[8];
+            if (lv && dst != t) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c0 + c < B200_OC_NF) tmp[c] = gf[(c0 + c) * TMAX + t];
+            }
+            __syncthreads();
+            if (lv && dst != t) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c0 + c < B200_OC_NF) gf[(c0 + c) * TMAX + dst] = tmp[c];
+            }
+            __syncthreads();
+        }
+        int itmp[B200_OC_NI];
+        if (lv && dst != t) {
+#pragma unroll
+            for (int c = 0; c < B200_OC_NI; ++c) itmp[c] = gi[c * TMAX + t];
+        }
+        __syncthreads();
+        if (lv && dst != t) {
+#pragma unroll
+            for (int c = 0; c < B200_OC_NI; ++c) gi[c * TMAX + dst] = itmp[c];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        counts[0] = n_final;
+        counts[1] = alive_after;
+        counts[2] = id0 + n_new;
+        counts[3] = frame;
+        p.nout[s] = min(E_old + E_new, p.max_tracks);
+        p.track_updates[s] += (unsigned long long)Cn;
+        if (err) atomicOr(p.err, err);
+    }
+}
+
+template <int TMAX, int DMAX>
+cudaError_t launch_oc_variant(const StepParams& p, cudaStream_t stream) {
+    auto kern = ocsort_step_kernel<TMAX, TMAX, DMAX>;
+    const size_t smem = sizeof(OcSmem<TMAX, DMAX>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<p.n_streams, TMAX, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+size_t ocsort_step_smem(int variant) {
+    switch (variant) {
+        case 0: return sizeof(OcSmem<64, 64>);
+        case 1: return sizeof(OcSmem<128, 128>);
+        case 2: return sizeof(OcSmem<256, 224>);
+        case 3: return sizeof(OcSmem<256, 256>);
+        case 4: return sizeof(OcSmem<512, 512>);
+    }
+    return 0;
+}
+
+cudaError_t launch_ocsort_step(const StepParams& p, int variant, cudaStream_t stream) {
+    switch (variant) {
+        case 0: return launch_oc_variant<64, 64>(p, stream);
+        case 1: return launch_oc_variant<128, 128>(p, stream);
+        case 2: return launch_oc_variant<256, 224>(p, stream);
+        case 3: return launch_oc_variant<256, 256>(p, stream);
+        case 4: return launch_oc_variant<512, 512>(p, stream);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace b200

@@ -11,6 +11,7 @@
 #include "api_util.h"
 #include "boxes.cuh"
 #include "kf.cuh"
+#include "lap_dense.cuh"
 #include "lap_sparse.cuh"
 
 namespace b200 {
@@ -309,10 +310,7 @@ __global__ void __launch_bounds__(256) lapjv_sparse_kernel(int rows, int cols, i
     for (int j = threadIdx.x; j < cols; j += blockDim.x) y[(size_t)blockIdx.x * cols + j] = w.yc[j];
 }
 
-// cost_limit = +inf (association.py:23): the dummy entries are max(cost)+1, so every
-// min(R, C) row is matched - a dense problem.  Whole-CTA shortest augmenting path: threads
-// own columns, one block-wide arg-min per Dijkstra step.  A row's private "unmatched" column
-// costs 2 * (max + 1) (= the two dummy entries lapjv pays for an unmatched row + column).
+// cost_limit = +inf (association.py:23): dense problem, see lap_dense.cuh
 __global__ void __launch_bounds__(256) lapjv_dense_kernel(int rows, int cols, const double* __restrict__ cost,
                                                           int* __restrict__ x, int* __restrict__ y) {
     extern __shared__ __align__(16) unsigned char raw[];
@@ -320,93 +318,27 @@ __global__ void __launch_bounds__(256) lapjv_dense_kernel(int rows, int cols, co
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     size_t off = 0;
     auto take = [&](size_t bytes) { unsigned char* p = raw + off; off = (off + bytes + 15) & ~size_t(15); return p; };
-    double* u = (double*)take(8 * rows); double* v = (double*)take(8 * cols); double* dist = (double*)take(8 * cols);
-    double* red_v = (double*)take(8 * 32);
-    int* red_i = (int*)take(4 * 32);
-    int* xr = (int*)take(4 * rows); int* yc = (int*)take(4 * cols); int* pred = (int*)take(4 * cols);
-    unsigned char* scn = take(cols);
-    __shared__ double s_min, s_bestDummy, s_lambda;
-    __shared__ int s_jmin, s_cur, s_sink, s_bestRow;
+    DenseLap w;
+    w.u = (double*)take(8 * rows); w.v = (double*)take(8 * cols); w.dist = (double*)take(8 * cols);
+    w.red_v = (double*)take(8 * 32); w.sh_d = (double*)take(8 * 4);
+    w.red_i = (int*)take(4 * 32); w.sh_i = (int*)take(4 * 4);
+    w.xr = (int*)take(4 * rows); w.claim = (int*)take(4 * rows); w.yc = (int*)take(4 * cols); w.pred = (int*)take(4 * cols);
+    w.scn = take(cols);
     const double* c = cost + (size_t)blockIdx.x * rows * cols;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // lambda = 2 * (max + 1)
     double mx = -INF;
     for (int i = tid; i < rows * cols; i += NT) mx = fmax(mx, c[i]);
     for (int d = 16; d; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
-    if (lane == 0) red_v[warp] = mx;
+    if (lane == 0) w.red_v[warp] = mx;
     __syncthreads();
-    if (tid == 0) { double m2 = red_v[0]; for (int k = 1; k < NT / 32; ++k) m2 = fmax(m2, red_v[k]); s_lambda = 2.0 * (m2 + 1.0); }
-    for (int i = tid; i < rows; i += NT) { u[i] = 0.0; xr[i] = -1; }
-    for (int j = tid; j < cols; j += NT) { v[j] = 0.0; yc[j] = -1; }
+    double m2 = w.red_v[0];
+    for (int k = 1; k < NT / 32; ++k) m2 = fmax(m2, w.red_v[k]);
+    const double lambda = 2.0 * (m2 + 1.0);
     __syncthreads();
-    const double lambda = s_lambda;
-    for (int i0 = 0; i0 < rows; ++i0) {
-        for (int j = tid; j < cols; j += NT) { dist[j] = INF; scn[j] = 0; pred[j] = -1; }
-        if (tid == 0) { s_min = 0.0; s_cur = i0; s_bestDummy = INF; s_bestRow = -1; s_sink = -2; }
-        __syncthreads();
-        while (true) {
-            const int i = s_cur;
-            const double minVal = s_min, ui = u[i];
-            double best = INF; int bj = -1;
-            for (int j = tid; j < cols; j += NT) {
-                if (scn[j]) continue;
-                const double r = minVal + c[(size_t)i * cols + j] - ui - v[j];
-                double dj = dist[j];
-                if (r < dj) { dj = r; dist[j] = r; pred[j] = i; }
-                if (dj < best) { best = dj; bj = j; }
-            }
-            for (int d = 16; d; d >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, d);
-                const int oj = __shfl_xor_sync(0xffffffffu, bj, d);
-                if (ob < best || (ob == best && oj >= 0 && (bj < 0 || oj < bj))) { best = ob; bj = oj; }
-            }
-            if (lane == 0) { red_v[warp] = best; red_i[warp] = bj; }
-            __syncthreads();
-            if (tid == 0) {
-                double b = red_v[0]; int j = red_i[0];
-                for (int k = 1; k < NT / 32; ++k)
-                    if (red_v[k] < b || (red_v[k] == b && red_i[k] >= 0 && (j < 0 || red_i[k] < j))) { b = red_v[k]; j = red_i[k]; }
-                const double dd = minVal + lambda - ui;
-                if (dd < s_bestDummy) { s_bestDummy = dd; s_bestRow = i; }
-                if (j < 0 || s_bestDummy <= b) { s_sink = -1; s_min = s_bestDummy; }
-                else {
-                    s_min = b; scn[j] = 1; s_jmin = j;
-                    if (yc[j] < 0) s_sink = j; else s_cur = yc[j];
-                }
-            }
-            __syncthreads();
-            if (s_sink != -2) break;
-        }
-        const double minVal = s_min;
-        const int sink = s_sink;
-        for (int j = tid; j < cols; j += NT) {
-            if (!scn[j]) continue;
-            const double delta = minVal - dist[j];
-            const int r = yc[j];
-            if (r >= 0) u[r] += delta;
-            v[j] -= delta;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            u[i0] += minVal;
-            int j = -1;
-            bool go = true;
-            if (sink >= 0) j = sink;
-            else if (s_bestRow == i0) go = false;
-            else { j = xr[s_bestRow]; xr[s_bestRow] = -1; }
-            while (go) {
-                const int r = pred[j];
-                yc[j] = r;
-                const int t = xr[r];
-                xr[r] = j;
-                j = t;
-                if (r == i0) break;
-            }
-        }
-        __syncthreads();
-    }
-    for (int t = tid; t < rows; t += NT) x[(size_t)blockIdx.x * rows + t] = xr[t];
-    for (int j = tid; j < cols; j += NT) y[(size_t)blockIdx.x * cols + j] = yc[j];
+    dense_lap_init<NT>(w, c, cols, rows, cols, lambda);
+    dense_lap_augment<NT>(w, c, cols, rows, cols, lambda);
+    for (int t = tid; t < rows; t += NT) x[(size_t)blockIdx.x * rows + t] = w.xr[t];
+    for (int j = tid; j < cols; j += NT) y[(size_t)blockIdx.x * cols + j] = w.yc[j];
 }
 
 template <class F>
@@ -514,7 +446,7 @@ extern "C" int b200track_lapjv(int32_t batch, int32_t rows, int32_t cols, const 
         B200_CU_TRY(cudaFuncSetAttribute(lapjv_sparse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lapjv_sparse_kernel<<<batch, 256, smem, (cudaStream_t)st>>>(rows, cols, Rpad, Cpad, cost, limit, x, y);
     } else {
-        size_t smem = 8 * (size_t)rows + 16 * (size_t)cols + 8 * 32 + 4 * 32 + 4 * (size_t)rows + 8 * (size_t)cols + cols + 16 * 12;
+        size_t smem = 8 * (size_t)rows + 16 * (size_t)cols + 8 * 36 + 4 * 36 + 8 * (size_t)rows + 8 * (size_t)cols + cols + 16 * 14;
         if (smem > 227 * 1024) { set_error("lapjv: problem too large for shared memory"); return B200TRACK_ERR_CAPACITY; }
         B200_CU_TRY(cudaFuncSetAttribute(lapjv_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lapjv_dense_kernel<<<batch, 256, smem, (cudaStream_t)st>>>(rows, cols, cost, x, y);

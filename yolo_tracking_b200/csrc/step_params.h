@@ -18,6 +18,10 @@ struct StepParams {
     double dup_thresh;        // 0.15
     double proximity_thresh, appearance_thresh;   // BoTSORT
     int max_time_lost;
+    // OC-SORT (ocsort.yaml keys)
+    double det_thresh, iou_thresh, inertia, img_w, img_h;
+    int max_age, min_hits, delta_t, asso_func;
+    double* scratch;          // [S, Tcap, Dcap] dense cost matrices (OC-SORT)
     // device state (layout.h)
     double* state_f;
     int* state_i;
@@ -40,5 +44,8 @@ int bytetrack_step_variant(int max_tracks, int max_dets);   // -1: nothing large
 int bytetrack_step_tmax(int variant);
 size_t bytetrack_step_smem(int variant);
 cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, int variant, cudaStream_t stream);
+size_t ocsort_step_smem(int variant);
+cudaError_t launch_ocsort_step(const StepParams& p, int variant, cudaStream_t stream);
+int step_variant_dmax(int variant);
 
 }  // namespace b200
