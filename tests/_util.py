@@ -21,3 +21,20 @@ def assert_close(a, b, rel=1e-9, abs_=1e-12, what=""):
     tol = abs_ + rel * np.maximum(np.abs(a), np.abs(b))
     bad = err > tol
     assert not bad.any(), f"{what}: max err {err.max():.3e} at {np.argwhere(bad)[:3].tolist()}"
+
+
+def botsort_scenario(name):
+    """(scenario dict, reference params, dets, ndets, seam features) of a BoT-SORT golden; the inputs are
+    re-generated (tests/golden/scenarios.py) and checked against the checksum stored in the fixture."""
+    import sys
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    from scenarios import BOTSORT_SCENARIOS, BOTSORT_YAML, botsort_inputs
+    sc = BOTSORT_SCENARIOS[name]
+    cfg = dict(BOTSORT_YAML)
+    cfg.update(sc["params"])
+    dets, nd, _, feats = botsort_inputs(sc)
+    g = load_golden(name)
+    assert np.array_equal(nd, g["ndets"]) and np.allclose([dets.sum(), float(np.abs(feats).sum())], g["dets_sum"], rtol=1e-12), \
+        "synthetic inputs drifted from the ones the golden was generated on"
+    return sc, cfg, dets, nd, feats, g

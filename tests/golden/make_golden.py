@@ -239,7 +239,59 @@ def gen_ocsort():
     _save("ocsort_2box", det=det, out=np.stack(outs), min_hits_sizes=np.array(sizes))
 
 
-GENERATORS = {"kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort}
+# ----------------------------------------------------------------------------- BoT-SORT
+from scenarios import BOTSORT_SCENARIOS, BOTSORT_YAML, botsort_inputs  # noqa: E402
+
+
+def _bs_snapshot(trk):
+    ts = trk.tracked_stracks + trk.lost_stracks
+    ints = np.array([[t.id, t.state, int(t.is_activated), t.frame_id, t.start_frame, t.tracklet_len] for t in ts],
+                    dtype=np.int32).reshape(-1, 6)
+    mean = np.stack([t.mean for t in ts]) if ts else np.zeros((0, 8))
+    cov = np.stack([t.covariance for t in ts]) if ts else np.zeros((0, 8, 8))
+    aux = np.array([[t.score, t.cls, t.det_ind] for t in ts], dtype=np.float64).reshape(-1, 3)
+    feat = [t.smooth_feat for t in ts]
+    return len(trk.tracked_stracks), len(trk.lost_stracks), ints, mean, cov, aux, feat
+
+
+def gen_botsort():
+    rh.install()
+    from boxmot.trackers.botsort.bot_sort import BoTSORT
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    for name, sc in BOTSORT_SCENARIOS.items():
+        dets, nd, embs, feats = botsort_inputs(sc)
+        cfg = dict(BOTSORT_YAML)
+        cfg.update(sc["params"])
+        rh.reset_counters()
+        trk = BoTSORT(None, "cpu", False, **cfg)
+        trk.cmc = rh.IdentityCMC()
+        outs, ints, counts, means, auxs, covs, cov_frames = [], [], [], [], [], [], []
+        for f in range(sc["n_frames"]):
+            rows = np.nonzero(dets[f, :nd[f], 4] > cfg["track_high_thresh"])[0]
+            if cfg.get("with_reid", True) and len(rows):
+                rh.FakeReID.queue.append(embs[f, rows])
+            o = trk.update(dets[f, :nd[f]], img)
+            outs.append(o)
+            nt, nl, ii, m, c, aux, feat = _bs_snapshot(trk)
+            counts.append((nt, nl))
+            ints.append(ii)
+            means.append(m)
+            auxs.append(aux)
+            if f % 10 == 9 or f == sc["n_frames"] - 1:
+                covs.append(c.reshape(-1, 64))
+                cov_frames.append(f)
+        assert not rh.FakeReID.queue
+        final_feat = (np.stack([x for x in feat]).astype(np.float32) if cfg.get("with_reid", True) and feat
+                      else np.zeros((0, sc["emb_dim"]), dtype=np.float32))
+        out_flat, out_offs = _ragged(outs, 8)
+        int_flat, int_offs = _ragged(ints, 6)
+        _save(name, ndets=nd, dets_sum=np.array([dets.sum(), float(np.abs(feats).sum())]),
+              out=out_flat, out_offs=out_offs, rec=int_flat.astype(np.int32), rec_offs=int_offs,
+              counts=np.array(counts, dtype=np.int32), mean=_ragged(means, 8)[0], aux=_ragged(auxs, 3)[0],
+              cov=_ragged(covs, 64)[0], cov_frames=np.array(cov_frames, dtype=np.int32), final_feat=final_feat)
+
+
+GENERATORS = {"kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(GENERATORS)

@@ -1,0 +1,48 @@
+"""Deterministic inputs of the BoT-SORT golden scenarios.  Shared by make_golden.py (which runs the live
+reference on them) and by the tests (which re-generate them instead of storing ~10 MB of embeddings;
+the fixtures keep a checksum).  No reference access here."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from yolo_tracking_b200.synth import make_stream  # noqa: E402
+
+BOTSORT_YAML = dict(track_high_thresh=0.33824964456239337, track_low_thresh=0.1, new_track_thresh=0.21144301345190655,
+                    track_buffer=60, match_thresh=0.22734550911325851, proximity_thresh=0.5945380911899254,
+                    appearance_thresh=0.4818211117541298, frame_rate=30)       # boxmot/configs/botsort.yaml
+
+
+def botsort_inputs(sc):
+    """Deterministic inputs of a BoT-SORT scenario (shared with the tests, which re-generate them instead
+    of storing ~10 MB of embeddings): dets[F, D, 6], ndets[F], seam features[F, D, emb] (what
+    ReIDDetectMultiBackend.get_features returns for the first-round rows: raw / Frobenius norm, scattered
+    back to detection rows; zero elsewhere)."""
+    dets, nd, embs = make_stream(3, sc["stream"], sc["n_objects"], sc["n_frames"], emb_dim=sc["emb_dim"], **sc["kw"])
+    if sc.get("classes"):
+        rng = np.random.default_rng(sc["stream"] + 7)
+        dets[..., 5] = rng.integers(0, sc["classes"], dets.shape[:2]).astype(np.float64) * (dets[..., 4] > 0)
+    high = sc["params"].get("track_high_thresh", BOTSORT_YAML["track_high_thresh"])
+    feats = np.zeros_like(embs)
+    for f in range(sc["n_frames"]):
+        rows = np.nonzero(dets[f, :nd[f], 4] > high)[0]
+        if len(rows):
+            raw = embs[f, rows]
+            feats[f, rows] = raw / np.linalg.norm(raw)
+    return dets, nd, embs, feats
+
+
+BOTSORT_SCENARIOS = {
+    # BASELINE config 3 shape, scaled down
+    "botsort_c3": dict(stream=0, n_objects=40, n_frames=100, emb_dim=512, kw={}, params={}),
+    # misses, false positives, three classes (class voting), ByteTrack-like thresholds
+    "botsort_churn": dict(stream=903, n_objects=18, n_frames=220, emb_dim=128, kw=dict(miss_prob=0.3, fp_rate=3.0),
+                          classes=3, params=dict(track_high_thresh=0.5, new_track_thresh=0.6, match_thresh=0.8,
+                                                 proximity_thresh=0.5, appearance_thresh=0.25, track_buffer=30)),
+    # appearance disabled: IoU-only association with the XYWH filter
+    "botsort_noreid": dict(stream=904, n_objects=25, n_frames=120, emb_dim=32, kw=dict(miss_prob=0.15, fp_rate=2.0),
+                           params=dict(with_reid=False)),
+}

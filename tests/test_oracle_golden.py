@@ -167,3 +167,38 @@ def test_ocsort_reference_known_answer():
     trk = OCSortOracle(False, **dict(base, min_hits=2))
     seq = [np.empty((0, 6)), np.empty((0, 6)), g["det"], np.empty((0, 6)), g["det"], g["det"], g["det"]]
     assert [trk.update(d, (1080, 1920)).size for d in seq] == g["min_hits_sizes"].tolist()
+
+
+# ----------------------------------------------------------------------------- BoT-SORT
+@pytest.mark.parametrize("name", ["botsort_c3", "botsort_churn", "botsort_noreid"])
+def test_botsort_oracle_replays_reference(name):
+    from _util import botsort_scenario
+    from oracle.botsort import BoTSORTOracle
+    sc, cfg, dets, nd, feats, g = botsort_scenario(name)
+    trk = BoTSORTOracle(**cfg)
+    cov_frames = {int(f): k for k, f in enumerate(g["cov_frames"])}
+    cov_offs = [0]
+    for f in g["cov_frames"]:
+        cov_offs.append(cov_offs[-1] + int(g["counts"][f].sum()))
+    for f in range(sc["n_frames"]):
+        out = trk.update(dets[f, :nd[f]], feats[f, :nd[f]])
+        ref = g["out"][g["out_offs"][f]:g["out_offs"][f + 1]]
+        assert out.reshape(-1, 8).shape == ref.shape, f"frame {f}"
+        if ref.size:
+            assert np.array_equal(out[:, 4:], ref[:, 4:]), f"frame {f}: id/conf/cls/det_ind"
+            assert_close(out[:, :4], ref[:, :4], what=f"frame {f} boxes")
+        s = trk.snapshot()
+        assert (int(s["n_tracked"]), int(s["n_lost"])) == tuple(g["counts"][f])
+        lo, hi = g["rec_offs"][f], g["rec_offs"][f + 1]
+        mine = np.stack([s["track_id"], s["state"], s["is_activated"], s["frame_id"], s["start_frame"],
+                         s["tracklet_len"]], axis=1).reshape(-1, 6)
+        assert np.array_equal(mine, g["rec"][lo:hi]), f"frame {f}: lifecycle records"
+        assert_close(s["mean"], g["mean"][lo:hi], what=f"frame {f} mean")
+        assert np.array_equal(np.stack([s["score"], s["cls"], s["det_ind"]], axis=1).reshape(-1, 3), g["aux"][lo:hi])
+        if f in cov_frames:
+            k = cov_frames[f]
+            assert_close(s["cov"].reshape(-1, 64), g["cov"][cov_offs[k]:cov_offs[k + 1]], abs_=1e-10, what=f"frame {f} cov")
+    if cfg.get("with_reid", True):
+        assert np.array_equal(s["smooth_feat"], g["final_feat"])       # same numpy float32 operations -> same bits
+    if sc.get("classes"):
+        assert len(np.unique(g["aux"][:, 1])) > 1
