@@ -130,6 +130,9 @@ int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state_bytes_per_stream, 
  *   h_cov[0:49] = dense 7x7 kf.P, [49:51] = velocity, [51:56] = last_observation. */
 int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int32_t* h_counts,
                         int32_t* h_rec, double* h_mean, double* h_cov, double* h_aux);
+/* BoT-SORT contexts (with_reid): STrack.smooth_feat (bot_sort.py:40-48) of every listed track of one
+ * stream, in the same list order as b200track_get_state; h_feat[max_tracks, feat_dim] fp32. */
+int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, float* h_feat);
 
 /* ---- operator level: the reference's functional API, batched, device pointers -----------
  * Dense [n, 8] means / [n, 8, 8] covariances in the reference's memory layout.

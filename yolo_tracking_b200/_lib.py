@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200track_phase_cycles": (C.c_int, [_P, C.POINTER(C.c_uint64 * 16), _I]),
     "b200track_footprint": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "b200track_get_state": (C.c_int, [_P, _I, _P, _P, _P, _P, _P]),
+    "b200track_get_features": (C.c_int, [_P, _I, _P]),
     "b200track_kf_initiate": (C.c_int, [_I, _I, _P, _P, _P, _P]),
     "b200track_kf_predict": (C.c_int, [_I, _I, _P, _P, _P]),
     "b200track_kf_project": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P]),

@@ -173,8 +173,13 @@ class BatchedTracker:
                         x=mean[:n, :7].copy(), P=c[:, :49].reshape(n, 7, 7).copy(), velocity=c[:, 49:51].copy(),
                         last_observation=c[:, 51:56].copy(), conf=aux[:n, 0].copy(), cls=aux[:n, 1].copy(),
                         det_ind=aux[:n, 2].copy())
-        return dict(n_tracked=int(counts[0]), n_lost=int(counts[1]), id_count=int(counts[2]), frame_id=int(counts[3]),
-                    track_id=rec[:n, 0].copy(), state=rec[:n, 1].copy(), is_activated=rec[:n, 2].copy(),
-                    frame_id_t=rec[:n, 3].copy(), start_frame=rec[:n, 4].copy(), tracklet_len=rec[:n, 5].copy(),
-                    mean=mean[:n].copy(), cov=cov[:n].reshape(n, 8, 8).copy(), score=aux[:n, 0].copy(),
-                    cls=aux[:n, 1].copy(), det_ind=aux[:n, 2].copy())
+        st = dict(n_tracked=int(counts[0]), n_lost=int(counts[1]), id_count=int(counts[2]), frame_id=int(counts[3]),
+                  track_id=rec[:n, 0].copy(), state=rec[:n, 1].copy(), is_activated=rec[:n, 2].copy(),
+                  frame_id_t=rec[:n, 3].copy(), start_frame=rec[:n, 4].copy(), tracklet_len=rec[:n, 5].copy(),
+                  mean=mean[:n].copy(), cov=cov[:n].reshape(n, 8, 8).copy(), score=aux[:n, 0].copy(),
+                  cls=aux[:n, 1].copy(), det_ind=aux[:n, 2].copy())
+        if self.kind == "botsort" and self._cfg.with_reid:
+            feat = np.zeros((T, self.feat_dim), dtype=np.float32)
+            _lib.check(self._lib.b200track_get_features(self._ctx, int(stream), _ptr(feat)))
+            st["smooth_feat"] = feat[:n].copy()
+        return st

@@ -76,6 +76,7 @@ extern "C" void b200track_destroy(b200track_ctx* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->p.state_f); cudaFree(ctx->p.state_i); cudaFree(ctx->p.counts);
     cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.dbg); cudaFree(ctx->p.scratch);
+    cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.cls_hist);
     for (auto& s : ctx->slot) {
         cudaFree(s.d_dets); cudaFree(s.d_ndets); cudaFree(s.d_feats); cudaFree(s.d_out); cudaFree(s.d_nout);
         if (s.in_ready) cudaEventDestroy(s.in_ready);
@@ -106,9 +107,9 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     if (!out_ctx) { set_error("out_ctx is NULL"); return B200TRACK_ERR_ARG; }
     *out_ctx = nullptr;
     if (int rc = check_cfg(cfg)) return rc;
-    if (cfg->kind == B200TRACK_BOTSORT) {
-        set_error("tracker kind not built yet in this library version");
-        return B200TRACK_ERR_STATE;
+    if (cfg->kind == B200TRACK_BOTSORT && cfg->with_reid) {
+        if (cfg->feat_dim <= 0 || cfg->feat_dim % 128 || cfg->feat_dim > 4096) {
+            set_error("BoT-SORT with_reid needs feat_dim to be a multiple of 128 in [128, 4096]"); return B200TRACK_ERR_ARG; }
     }
     if (cfg->kind == B200TRACK_OCSORT) {
         if (cfg->use_byte) { set_error("OC-SORT use_byte=True is not built (ocsort.yaml default is false)"); return B200TRACK_ERR_STATE; }
@@ -137,6 +138,7 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     p.det_thresh = cfg->det_thresh; p.iou_thresh = cfg->iou_thresh; p.inertia = cfg->inertia;
     p.max_age = cfg->max_age; p.min_hits = cfg->min_hits; p.delta_t = cfg->delta_t; p.asso_func = cfg->asso_func;
     if (cfg->kind == B200TRACK_OCSORT) { ctx->nf = B200_OC_NF; ctx->ni = B200_OC_NI; }
+    if (cfg->kind == B200TRACK_BOTSORT) { ctx->ni = B200_NI_BOT; p.with_reid = cfg->with_reid ? 1 : 0; }
     ctx->kf_kind = cfg->kind == B200TRACK_BOTSORT ? B200TRACK_KF_XYWH : B200TRACK_KF_XYAH;
     ctx->variant = b200::bytetrack_step_variant(cfg->max_tracks, cfg->max_dets);
     if (ctx->variant < 0) { set_error("no kernel variant covers max_tracks / max_dets"); delete ctx; return B200TRACK_ERR_CAPACITY; }
@@ -149,6 +151,10 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     CU_TRY_CTX(cudaMalloc(&p.state_i, S * ctx->ni * T * sizeof(int)));
     if (cfg->kind == B200TRACK_OCSORT)
         CU_TRY_CTX(cudaMalloc(&p.scratch, S * T * (size_t)b200::step_variant_dmax(ctx->variant) * sizeof(double)));
+    if (cfg->kind == B200TRACK_BOTSORT) {
+        CU_TRY_CTX(cudaMalloc(&p.cls_hist, S * T * 9 * sizeof(double)));
+        if (cfg->with_reid) CU_TRY_CTX(cudaMalloc(&p.feat_pool, S * T * (size_t)cfg->feat_dim * sizeof(float)));
+    }
     CU_TRY_CTX(cudaMalloc(&p.counts, S * 4 * sizeof(int)));
     CU_TRY_CTX(cudaMalloc(&p.track_updates, S * sizeof(unsigned long long)));
     CU_TRY_CTX(cudaMalloc(&p.err, sizeof(int)));
@@ -166,7 +172,8 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.out_ready, cudaEventDisableTiming));
     }
-    const size_t smem = cfg->kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant) : b200::bytetrack_step_smem(ctx->variant);
+    const size_t smem = cfg->kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
+                                                      : b200::bytetrack_step_smem(ctx->variant, cfg->kind == B200TRACK_BOTSORT);
     int max_smem = 0;
     CU_TRY_CTX(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     if (smem > (size_t)max_smem) {
@@ -185,7 +192,10 @@ static int launch_step(b200track_ctx* ctx, const double* d_dets, const int32_t* 
     p.dets = d_dets; p.ndets = d_ndets; p.feats = d_feats; p.out = d_out; p.nout = d_nout;
     p.img_h = img_h; p.img_w = img_w;
     if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
-    else CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, ctx->variant, st));
+    else if (ctx->cfg.kind == B200TRACK_BOTSORT) {
+        if (p.with_reid && !d_feats) { set_error("BoT-SORT with_reid: the embedding buffer is NULL"); return B200TRACK_ERR_ARG; }
+        CU_TRY(b200::launch_botsort_step(p, ctx->variant, st));
+    } else CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, ctx->variant, st));
     ctx->launches += 1;
     return 0;
 }
@@ -260,7 +270,8 @@ extern "C" int b200track_sync(b200track_ctx* ctx) {
     if (e) {
         CU_TRY(cudaMemset(ctx->p.err, 0, sizeof(int)));
         set_error(std::string("capacity overflow:") + ((e & B200_ERR_DET_OVERFLOW) ? " detections > max_dets" : "") +
-                  ((e & B200_ERR_TRACK_OVERFLOW) ? " tracks > max_tracks" : ""));
+                  ((e & B200_ERR_TRACK_OVERFLOW) ? " tracks > max_tracks" : "") +
+                  ((e & B200_ERR_BOT_CAPACITY) ? " BoT-SORT candidate graph or class history (> 4 classes on a track)" : ""));
         return B200TRACK_ERR_CAPACITY;
     }
     return 0;
@@ -300,7 +311,8 @@ extern "C" int b200track_phase_cycles(b200track_ctx* ctx, uint64_t* h_out16, int
 extern "C" int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state, uint64_t* h_smem) {
     if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
     if (h_state) *h_state = (uint64_t)ctx->tcap * (ctx->nf * 8 + ctx->ni * 4) + 4 * sizeof(int) + sizeof(unsigned long long);
-    if (h_smem) *h_smem = ctx->cfg.kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant) : b200::bytetrack_step_smem(ctx->variant);
+    if (h_smem) *h_smem = ctx->cfg.kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
+                                                            : b200::bytetrack_step_smem(ctx->variant, ctx->cfg.kind == B200TRACK_BOTSORT);
     return 0;
 }
 
@@ -363,6 +375,7 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
         if (h_rec) {
             int32_t* r = h_rec + 6 * t;
             r[0] = iv[B200_TI_ID * T + t]; r[1] = fl & 3; r[2] = (fl & B200_FLAG_ACTIVATED) ? 1 : 0;
+            if (ctx->cfg.kind == B200TRACK_BOTSORT && r[1] == 3) r[1] = 4;      // botsort/basetrack.py:7-12: Removed = 4
             r[3] = iv[B200_TI_FRAME * T + t]; r[4] = iv[B200_TI_START * T + t]; r[5] = iv[B200_TI_LEN * T + t];
         }
         if (h_mean) for (int c = 0; c < 8; ++c) h_mean[8 * t + c] = f[(B200_TF_MEAN + c) * T + t];
@@ -381,5 +394,22 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
             h_aux[3 * t + 2] = (double)iv[B200_TI_DET * T + t];
         }
     }
+    return 0;
+}
+
+extern "C" int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, float* h_feat) {
+    if (!ctx || !h_feat) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    if (ctx->cfg.kind != B200TRACK_BOTSORT || !ctx->p.feat_pool) { set_error("context holds no embeddings"); return B200TRACK_ERR_STATE; }
+    if (stream_index < 0 || stream_index >= ctx->cfg.n_streams) { set_error("stream_index out of range"); return B200TRACK_ERR_ARG; }
+    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t T = ctx->tcap, s = stream_index, F = ctx->cfg.feat_dim;
+    int counts[4];
+    CU_TRY(cudaMemcpy(counts, ctx->p.counts + 4 * s, sizeof(counts), cudaMemcpyDeviceToHost));
+    std::vector<int> rows(T);
+    CU_TRY(cudaMemcpy(rows.data(), ctx->p.state_i + (s * ctx->ni + B200_TI_FROW) * T, T * sizeof(int), cudaMemcpyDeviceToHost));
+    const int n = counts[0] + counts[1];
+    for (int t = 0; t < n && t < ctx->cfg.max_tracks; ++t)
+        CU_TRY(cudaMemcpy(h_feat + (size_t)t * F, ctx->p.feat_pool + (s * T + rows[t]) * F, F * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;
 }

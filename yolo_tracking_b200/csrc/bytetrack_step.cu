@@ -19,6 +19,17 @@
 // iou_distance / fuse_score / linear_assignment (matching.py:94-119, :213-221, :56-71 ->
 // lap.lapjv), STrack.update / re_activate / activate :50-98 -> KalmanFilter.update / initiate,
 // joint_stracks / sub_stracks / remove_duplicate_stracks :287-325.
+//
+// The same kernel, instantiated with BOT = true and the XYWH filter, is the BoT-SORT frame step
+// (boxmot/trackers/botsort/bot_sort.py:231-420, camera-motion warp = identity): the association
+// costs become min(iou distance, appearance distance) with the appearance term gated by the
+// proximity mask (:298-309, :356-368), matched tracks blend the detection embedding into their
+// smoothed embedding in fp32 (STrack.update_features :40-48) and vote on their class
+// (update_cls :50-67).  The appearance distance is only ever needed for pairs that pass the
+// proximity mask (iou distance <= proximity_thresh) - one or two per track - so it is
+// evaluated per candidate pair, one warp per pair, in double on the fp32 values exactly like
+// matching.py:145-167; nothing T x D x F is computed.  Embeddings live in a per-stream pool of
+// rows that never move (a slot carries its row index); rows of dead tracks are recycled.
 #include "boxes.cuh"
 #include "kf.cuh"
 #include "lap_sparse.cuh"
@@ -42,8 +53,26 @@ constexpr int NCELL = 64;         // cells per axis of the candidate masks
 // row types of one association pass: which detection set / limit / cost a row uses
 constexpr int RT_NONE = 0, RT_A = 1, RT_B = 2;
 
+// BoT-SORT extras (empty for ByteTrack)
+template <int TMAX, int DMAX, bool BOT>
+struct BotSmem {};
 template <int TMAX, int DMAX>
+struct BotSmem<TMAX, DMAX, true> {
+    static constexpr int PCAP = 4 * TMAX;
+    double pcost[PCAP];              // iou-side cost of a pair waiting for its appearance distance
+    uint32_t epairs[PCAP];           // (row << 16) | det
+    float dn0[DMAX], dn1[DMAX], dn2[DMAX];   // norms of the three in-place normalisations of a detection embedding
+    int nepairs[4];
+    short frow[TMAX];                // embedding-pool row of a slot
+    short emadet[TMAX];              // detection whose embedding is blended into the slot's, -1 = none
+    short freelist[TMAX];
+    short nbdet[DMAX], nbrow[DMAX];  // stored newborn k: its detection and its pool row
+    unsigned char rowused[TMAX];
+};
+
+template <int TMAX, int DMAX, bool BOT = false>
 struct alignas(16) StepSmem {
+    static constexpr int TCAP = TMAX;
     static constexpr int DW = DMAX / 32;
     static constexpr int DWP = (DW + 3) / 4 * 4;      // mask rows padded to 16-byte multiples
     double mean[8][TMAX];
@@ -72,6 +101,7 @@ struct alignas(16) StepSmem {
     int npairs[4];
     float4 dboxf[DMAX];                               // detection boxes rounded outwards to fp32
     unsigned char role[TMAX], rowtype[TMAX], cat[TMAX], drop[TMAX + DMAX], dflag[DMAX];
+    BotSmem<TMAX, DMAX, BOT> bot;
 };
 
 // STrack.xyxy (byte_tracker.py:100-111): XYAH mean -> (xc, yc, a*h, h) -> corners
@@ -109,6 +139,7 @@ template <int KIND, class SM>
 struct PassCost {
     const SM* sm;
     bool fuseA, fuseB;
+    bool embA = false, embB = false;      // BoT-SORT: min(iou cost, gated appearance distance) for this row type
     __device__ __forceinline__ double pair(const Box& a, int j, bool fuse) const {
         const double v = box_iou(a, det_box(*sm, j));
         return fuse ? fused_cost(v, sm->dconf[j]) : xsub(1.0, v);
@@ -196,16 +227,28 @@ __device__ __forceinline__ void graph_add_edge(SM& sm, int t, int j, double c) {
     }
 }
 
-template <int NT, int KIND, class SM>
-__device__ __forceinline__ void graph_phase_b(SM& sm, int n, int words, const PassCost<KIND, SM>& cost, const PassLimit& lim) {
+template <int NT, int KIND, bool BOT, class SM>
+__device__ __forceinline__ void graph_phase_b(SM& sm, int n, int words, const PassCost<KIND, SM>& cost, const PassLimit& lim,
+                                              double proximity) {
     const int np = sm.npairs[0];
     if (np <= SM::PCAP) {
         for (int k = threadIdx.x; k < np; k += NT) {
             const uint32_t pr = sm.pairs[k];
             const int t = pr >> 16, j = pr & 0xffff;
             const bool isA = sm.rowtype[t] == RT_A;
-            const double c = cost.pair(track_box<KIND>(sm, t), j, isA ? cost.fuseA : cost.fuseB);
-            if (c <= (isA ? lim.limA : lim.limB)) graph_add_edge<KIND>(sm, t, j, c);
+            if constexpr (BOT) {
+                // bot_sort.py:298-309 / :356-368: the proximity mask is taken on the plain iou distance
+                const double v = box_iou(track_box<KIND>(sm, t), det_box(sm, j));
+                const double ci = xsub(1.0, v);
+                const double c = (isA ? cost.fuseA : cost.fuseB) ? fused_cost(v, sm.dconf[j]) : ci;
+                if ((isA ? cost.embA : cost.embB) && !(ci > proximity)) {
+                    const int e = atomicAdd(&sm.bot.nepairs[0], 1);
+                    sm.bot.epairs[e] = pr; sm.bot.pcost[e] = c;       // e < np <= PCAP
+                } else if (c <= (isA ? lim.limA : lim.limB)) graph_add_edge<KIND>(sm, t, j, c);
+            } else {
+                const double c = cost.pair(track_box<KIND>(sm, t), j, isA ? cost.fuseA : cost.fuseB);
+                if (c <= (isA ? lim.limA : lim.limB)) graph_add_edge<KIND>(sm, t, j, c);
+            }
         }
     } else {
         // pair list overflowed (pathologically crowded frame): every row re-walks its columns
@@ -229,11 +272,96 @@ __device__ __forceinline__ void graph_phase_b(SM& sm, int n, int words, const Pa
     }
 }
 
-template <int NT, int KIND, int TMAX, int DMAX>
+// ---- BoT-SORT embedding arithmetic, one warp per row / pair -------------------------------------
+// Rows are feat_dim fp32 values, feat_dim a multiple of 128: lane l owns the float4 groups l, l + 32, ...
+// Everything the reference does on embeddings is float32 numpy (bot_sort.py:40-48): norms are
+// sqrt(dot(x, x)) rounded to fp32 (accumulated in double here; BLAS order is unspecified), divisions and
+// the 0.9 / 0.1 blend are separate correctly rounded fp32 operations.
+__device__ __forceinline__ double warp_sum(double x) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    return x;
+}
+__device__ __forceinline__ float4 f4_div(float4 a, float n) {
+    return make_float4(__fdiv_rn(a.x, n), __fdiv_rn(a.y, n), __fdiv_rn(a.z, n), __fdiv_rn(a.w, n));
+}
+__device__ __forceinline__ double f4_sq(float4 a) {
+    return (double)a.x * a.x + (double)a.y * a.y + (double)a.z * a.z + (double)a.w * a.w;
+}
+__device__ __forceinline__ float norm_f32(double sumsq) { return sqrtf((float)sumsq); }
+
+// the three successive norms of a detection embedding: get_features row -> STrack.__init__ (feat /= |feat|,
+// then the aliased smooth_feat /= |smooth_feat|) -> update_features of the matched track (feat /= |feat|)
+__device__ __forceinline__ void det_feat_norms(const float4* row, int nv, int lane, float& n0, float& n1, float& n2) {
+    double a = 0.0;
+    for (int i = lane; i < nv; i += 32) a += f4_sq(row[i]);
+    n0 = norm_f32(warp_sum(a));
+    a = 0.0;
+    for (int i = lane; i < nv; i += 32) a += f4_sq(f4_div(row[i], n0));
+    n1 = norm_f32(warp_sum(a));
+    a = 0.0;
+    for (int i = lane; i < nv; i += 32) a += f4_sq(f4_div(f4_div(row[i], n0), n1));
+    n2 = norm_f32(warp_sum(a));
+}
+
+// embedding_distance (matching.py:145-167) of one (smoothed track embedding, detection curr_feat) pair:
+// scipy cdist 'cosine' in double on the fp32 values, clamped at 0
+__device__ __forceinline__ double emb_distance(const float4* trk, const float4* det, int nv, int lane, float n0, float n1) {
+    double uv = 0.0, uu = 0.0, vv = 0.0;
+    for (int i = lane; i < nv; i += 32) {
+        const float4 a = trk[i];
+        const float4 b = f4_div(f4_div(det[i], n0), n1);
+        uv += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
+        uu += f4_sq(a);
+        vv += f4_sq(b);
+    }
+    uv = warp_sum(uv); uu = warp_sum(uu); vv = warp_sum(vv);
+    double c = uv / (sqrt(uu) * sqrt(vv));
+    if (fabs(c) > 1.0) c = copysign(1.0, c);
+    return fmax(0.0, 1.0 - c);
+}
+
+// appearance stage of the candidate graph (BoT-SORT): one warp per pair that passed the proximity mask
+template <int NT, int KIND, class SM>
+__device__ __forceinline__ void graph_phase_emb(SM& sm, const StepParams& p, int s, const PassLimit& lim) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ne = sm.bot.nepairs[0];
+    const int nv = p.feat_dim >> 2;
+    for (int k = warp; k < ne; k += NT / 32) {
+        const uint32_t pr = sm.bot.epairs[k];
+        const int t = pr >> 16, j = pr & 0xffff;
+        const float4* trk = reinterpret_cast<const float4*>(p.feat_pool + ((size_t)s * SM::TCAP + sm.bot.frow[t]) * p.feat_dim);
+        const float4* det = reinterpret_cast<const float4*>(p.feats + ((size_t)s * p.max_dets + j) * p.feat_dim);
+        double e = xmul(emb_distance(trk, det, nv, lane, sm.bot.dn0[j], sm.bot.dn1[j]), 0.5);
+        if (e > p.appearance_thresh) e = 1.0;
+        const double c = fmin(sm.bot.pcost[k], e);
+        if (lane == 0 && c <= (sm.rowtype[t] == RT_A ? lim.limA : lim.limB)) graph_add_edge<KIND>(sm, t, j, c);
+    }
+}
+
+// update_cls (bot_sort.py:50-67) on a fixed-capacity history {cls[4], score sum[4], n}; returns the new track class
+__device__ __forceinline__ double cls_vote(double* h, double cls, double score, int& err) {
+    int n = (int)h[8];
+    double best = 0.0, out = cls;
+    bool found = false;
+    for (int k = 0; k < n; ++k) {
+        if (cls == h[k]) { h[4 + k] = xadd(h[4 + k], score); found = true; }
+        if (h[4 + k] > best) { best = h[4 + k]; out = h[k]; }
+    }
+    if (!found) {
+        if (n < 4) { h[n] = cls; h[4 + n] = score; h[8] = (double)(n + 1); } else err |= B200_ERR_BOT_CAPACITY;
+        out = cls;
+    }
+    return out;
+}
+
+template <int NT, int KIND, int TMAX, int DMAX, bool BOT>
 __global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : (NT == 256 ? 3 : (NT == 128 ? 6 : 8))))
 bytetrack_step_kernel(const StepParams p) {
     static_assert(NT == TMAX && DMAX <= NT, "one thread per track slot; detections fit one pass");
-    using SM = StepSmem<TMAX, DMAX>;
+    static_assert(!BOT || KIND == KF_XYWH, "BoT-SORT runs on the XYWH filter");
+    using SM = StepSmem<TMAX, DMAX, BOT>;
+    constexpr int NI = BOT ? B200_NI_BOT : B200_NI;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     constexpr int DWP = SM::DWP;
@@ -253,7 +381,7 @@ bytetrack_step_kernel(const StepParams p) {
     const int words = (nd + 31) >> 5;
     const int t = tid;                                   // this thread's track slot
     const double* gf = p.state_f + (size_t)s * B200_NF * TMAX;
-    const int* gi = p.state_i + (size_t)s * B200_NI * TMAX;
+    const int* gi = p.state_i + (size_t)s * NI * TMAX;
 
     // ---- HBM -> shared memory: detections [nd, 6] (planar), means, lifecycle ints ----------
     int fl = 0, frame_t = 0;
@@ -272,6 +400,7 @@ bytetrack_step_kernel(const StepParams p) {
             fl = gi[B200_TI_FLAGS * TMAX + t];
             frame_t = gi[B200_TI_FRAME * TMAX + t];
             sm.start_t[t] = gi[B200_TI_START * TMAX + t];
+            if constexpr (BOT) { sm.bot.frow[t] = (short)gi[B200_TI_FROW * TMAX + t]; sm.bot.emadet[t] = -1; }
         }
         // the covariance / id / score lines are first used after the association: pull them into L2 now
         if (t < n && (t & 15) == 0) {
@@ -286,6 +415,7 @@ bytetrack_step_kernel(const StepParams p) {
         }
         for (int i = tid; i < NCELL * DWP; i += NT) { (&sm.xmask[0][0])[i] = 0u; (&sm.ymask[0][0])[i] = 0u; }
         for (int i = tid; i < TMAX + DMAX; i += NT) sm.drop[i] = 0;
+        if constexpr (BOT) sm.bot.rowused[t] = 0;
     }
     __syncthreads();
     PHASE(1);
@@ -374,6 +504,19 @@ bytetrack_step_kernel(const StepParams p) {
     }
     __syncthreads();
     PHASE(3);
+    if constexpr (BOT) {
+        // norms of the first-round detection embeddings (features only exist for dets_first, bot_sort.py:266)
+        if (p.with_reid) {
+            const int nv = p.feat_dim >> 2;
+            for (int j = warp; j < nd; j += NT / 32) {
+                if (sm.dflag[j] != DF_HIGH) continue;
+                float n0, n1, n2;
+                det_feat_norms(reinterpret_cast<const float4*>(p.feats + ((size_t)s * p.max_dets + j) * p.feat_dim), nv, lane, n0, n1, n2);
+                if (lane == 0) { sm.bot.dn0[j] = n0; sm.bot.dn1[j] = n1; sm.bot.dn2[j] = n2; }
+            }
+        }
+        if (tid == 0) sm.bot.nepairs[0] = 0;
+    }
 
     PassCost<KIND, SM> cost;
     cost.sm = &sm;
@@ -381,12 +524,18 @@ bytetrack_step_kernel(const StepParams p) {
     lim.rowtype = sm.rowtype;
 
     // ---- first association: pool x high detections, fused score, limit match_thresh ----
-    cost.fuseA = true; cost.fuseB = true;
+    cost.fuseA = !BOT; cost.fuseB = !BOT;                 // BoT-SORT: fuse_first_associate = False (bot_sort.py:300-301)
+    cost.embA = cost.embB = BOT && p.with_reid;
     lim.limA = p.match_thresh; lim.limB = p.match_thresh;
     graph_phase_a<KIND>(sm, t, n, words, cm);
     __syncthreads();
-    graph_phase_b<NT, KIND>(sm, n, words, cost, lim);
+    graph_phase_b<NT, KIND, BOT>(sm, n, words, cost, lim, p.proximity_thresh);
     __syncthreads();
+    if constexpr (BOT) {
+        if (sm.npairs[0] > SM::PCAP || sm.ecount[0] > SM::ECAP) err |= B200_ERR_BOT_CAPACITY;
+        graph_phase_emb<NT, KIND>(sm, p, s, lim);
+        __syncthreads();
+    }
     PHASE(4);
     lap_sparse_solve<NT>(lw, n, words, lim, cost);
     bool matched1 = false;
@@ -407,16 +556,22 @@ bytetrack_step_kernel(const StepParams p) {
         const uint32_t mb = __ballot_sync(0xffffffffu, dfl == DF_HIGH);     // high and not used
         if (lane == 0) { sm.colbitsA[tid >> 5] = ma; sm.colbitsB[tid >> 5] = mb; }
     }
-    if (tid == 0) sm.npairs[0] = 0;
+    if (tid == 0) { sm.npairs[0] = 0; if constexpr (BOT) sm.bot.nepairs[0] = 0; }
     lap_prepare<NT>(lw, n, words);
     __syncthreads();
     PHASE(6);
     cost.fuseA = false; cost.fuseB = true;
+    cost.embA = false; cost.embB = BOT && p.with_reid;
     lim.limA = p.second_thresh; lim.limB = p.unconf_thresh;
     graph_phase_a<KIND>(sm, t, n, words, cm);
     __syncthreads();
-    graph_phase_b<NT, KIND>(sm, n, words, cost, lim);
+    graph_phase_b<NT, KIND, BOT>(sm, n, words, cost, lim, p.proximity_thresh);
     __syncthreads();
+    if constexpr (BOT) {
+        if (sm.npairs[0] > SM::PCAP || sm.ecount[0] > SM::ECAP) err |= B200_ERR_BOT_CAPACITY;
+        graph_phase_emb<NT, KIND>(sm, p, s, lim);
+        __syncthreads();
+    }
     PHASE(7);
     lap_sparse_solve<NT>(lw, n, words, lim, cost);
 
@@ -475,6 +630,11 @@ bytetrack_step_kernel(const StepParams p) {
             det_ind = j;
             score = sm.dconf[j];
             cls = sm.dcls[j];
+            if constexpr (BOT) {
+                double* h = p.cls_hist + ((size_t)s * TMAX + sm.bot.frow[t]) * 9;
+                cls = cls_vote(h, cls, score, err);
+                if (p.with_reid && (sm.dflag[j] & DF_HIGH)) sm.bot.emadet[t] = (short)j;   // low detections carry no embedding
+            }
             fl = (fl & ~3) | B200_ST_TRACKED | B200_FLAG_ACTIVATED;
         } else if (unmatched2) {
             fl = (fl & ~3) | (role == ROLE_TRACKED ? B200_ST_LOST : B200_ST_REMOVED);   // mark_lost / mark_removed
@@ -498,6 +658,30 @@ bytetrack_step_kernel(const StepParams p) {
     }
     __syncthreads();
     PHASE(8);
+    if constexpr (BOT) {
+        // STrack.update_features (bot_sort.py:40-48) of every track matched to a first-round detection
+        if (p.with_reid) {
+            const int nv = p.feat_dim >> 2;
+            const float A = 0.9f, B = 0.1f;             // alpha, float32(1 - alpha)
+            for (int q = warp; q < n; q += NT / 32) {
+                const int j = sm.bot.emadet[q];
+                if (j < 0) continue;
+                float4* trk = reinterpret_cast<float4*>(p.feat_pool + ((size_t)s * TMAX + sm.bot.frow[q]) * p.feat_dim);
+                const float4* det = reinterpret_cast<const float4*>(p.feats + ((size_t)s * p.max_dets + j) * p.feat_dim);
+                const float n0 = sm.bot.dn0[j], n1 = sm.bot.dn1[j], n2 = sm.bot.dn2[j];
+                auto blend = [&](int i) {
+                    const float4 f = f4_div(f4_div(f4_div(det[i], n0), n1), n2);
+                    const float4 a = trk[i];
+                    return make_float4(__fadd_rn(__fmul_rn(A, a.x), __fmul_rn(B, f.x)), __fadd_rn(__fmul_rn(A, a.y), __fmul_rn(B, f.y)),
+                                       __fadd_rn(__fmul_rn(A, a.z), __fmul_rn(B, f.z)), __fadd_rn(__fmul_rn(A, a.w), __fmul_rn(B, f.w)));
+                };
+                double acc = 0.0;
+                for (int i = lane; i < nv; i += 32) acc += f4_sq(blend(i));
+                const float nn = norm_f32(warp_sum(acc));
+                for (int i = lane; i < nv; i += 32) trk[i] = f4_div(blend(i), nn);
+            }
+        }
+    }
 
     // compact list of the new lost list (old entries first, then the newly lost) for the
     // duplicate test; packed counters: [0:16) old-lost, [16:32) new-lost
@@ -568,7 +752,7 @@ bytetrack_step_kernel(const StepParams p) {
     // Every CAT_KEEP / CAT_REFOUND entry is activated, so output rows = keep ++ born (frame 1 only) ++ refound.
     const bool born_active = frame == 1;                 // STrack.activate: is_activated only on frame 1
     double* wf = p.state_f + (size_t)s * B200_NF * TMAX;
-    int* wi = p.state_i + (size_t)s * B200_NI * TMAX;
+    int* wi = p.state_i + (size_t)s * NI * TMAX;
     double* gout = p.out + (size_t)s * p.max_tracks * 8;
     const int out_cap = p.max_tracks;
     unsigned long long val = 0ull;
@@ -577,8 +761,21 @@ bytetrack_step_kernel(const StepParams p) {
         val |= 1ull << 50;                                // activate() ran: consumes an id even if dropped
         if (!sm.drop[TMAX + tid]) val |= 1ull << 40;
     }
+    if constexpr (BOT) {
+        if (val & ((1ull << 40) - 1)) sm.bot.rowused[sm.bot.frow[t]] = 1;      // rows of the tracks that stay listed
+    }
     unsigned long long totals;
     const unsigned long long ex = block_exscan<NT>(val, sm.scratch, totals);
+    int nfree = 0;
+    if constexpr (BOT) {
+        // embedding-pool rows of dead tracks are recycled: the k-th stored newborn takes the k-th free row
+        const bool isfree = !sm.bot.rowused[t];
+        unsigned long long tf;
+        const int rank = (int)block_exscan<NT>(isfree ? 1ull : 0ull, sm.scratch, tf);
+        nfree = (int)tf;
+        if (isfree) sm.bot.freelist[rank] = (short)t;
+        __syncthreads();
+    }
     const int totKeep = (int)(totals & 1023), totRef = (int)((totals >> 10) & 1023);
     const int totLostOld = (int)((totals >> 20) & 1023), totLostNew = (int)((totals >> 30) & 1023);
     const int totBorn = (int)((totals >> 40) & 1023), totBornAll = (int)((totals >> 50) & 1023);
@@ -611,6 +808,7 @@ bytetrack_step_kernel(const StepParams p) {
             wi[B200_TI_LEN * TMAX + dst] = len;
             wi[B200_TI_DET * TMAX + dst] = det_ind;
             wi[B200_TI_FLAGS * TMAX + dst] = fl;
+            if constexpr (BOT) wi[B200_TI_FROW * TMAX + dst] = sm.bot.frow[t];
         }
         if (orow >= 0 && orow < out_cap) {
             const Box b = mean_to_box<KIND>(ks.m[0], ks.m[1], ks.m[2], ks.m[3]);
@@ -646,6 +844,17 @@ bytetrack_step_kernel(const StepParams p) {
             wi[B200_TI_DET * TMAX + dst] = j;
             wi[B200_TI_FLAGS * TMAX + dst] = B200_ST_TRACKED | (born_active ? B200_FLAG_ACTIVATED : 0);
         }
+        if constexpr (BOT) {
+            const bool stored = dst < cap && k < nfree;
+            const int row = stored ? sm.bot.freelist[k] : -1;
+            sm.bot.nbdet[k] = stored ? (short)j : (short)-1;
+            sm.bot.nbrow[k] = (short)row;
+            if (stored) {
+                wi[B200_TI_FROW * TMAX + dst] = row;
+                double* h = p.cls_hist + ((size_t)s * TMAX + row) * 9;     // STrack.__init__: cls_hist = [[cls, score]]
+                h[0] = sm.dcls[j]; h[4] = sm.dconf[j]; h[8] = 1.0;
+            }
+        }
         if (born_active) {
             const int orow = totKeep + k;
             if (orow < out_cap) {
@@ -656,7 +865,23 @@ bytetrack_step_kernel(const StepParams p) {
             }
         }
     }
+    if constexpr (BOT) {
+        // a new track's smoothed embedding is its detection's (twice normalised) embedding (bot_sort.py:40-48)
+        if (p.with_reid) {
+            __syncthreads();
+            const int nv = p.feat_dim >> 2;
+            for (int k = warp; k < totBorn; k += NT / 32) {
+                const int j = sm.bot.nbdet[k];
+                if (j < 0) continue;
+                float4* trk = reinterpret_cast<float4*>(p.feat_pool + ((size_t)s * TMAX + sm.bot.nbrow[k]) * p.feat_dim);
+                const float4* det = reinterpret_cast<const float4*>(p.feats + ((size_t)s * p.max_dets + j) * p.feat_dim);
+                const float n0 = sm.bot.dn0[j], n1 = sm.bot.dn1[j];
+                for (int i = lane; i < nv; i += 32) trk[i] = f4_div(f4_div(det[i], n0), n1);
+            }
+        }
+    }
     PHASE(15);
+    if (err) atomicOr(p.err, err);
     if (tid == 0) {
         if (p.dbg) atomicAdd(&p.dbg[0], 1ull);
         counts[0] = min(newT, cap);
@@ -665,7 +890,6 @@ bytetrack_step_kernel(const StepParams p) {
         counts[3] = frame;
         p.nout[s] = min(totKeep + rowsBorn + totRef, out_cap);
         p.track_updates[s] += (unsigned long long)n;
-        if (err) atomicOr(p.err, err);
     }
 }
 
@@ -673,24 +897,24 @@ bytetrack_step_kernel(const StepParams p) {
 struct Variant { int tmax, dmax; };
 constexpr Variant kVariants[] = {{64, 64}, {128, 128}, {256, 224}, {256, 256}, {512, 512}};
 
-template <int KIND, int TMAX, int DMAX>
+template <int KIND, int TMAX, int DMAX, bool BOT>
 cudaError_t launch_variant(const StepParams& p, cudaStream_t stream) {
-    auto kern = bytetrack_step_kernel<TMAX, KIND, TMAX, DMAX>;
-    const size_t smem = sizeof(StepSmem<TMAX, DMAX>);
+    auto kern = bytetrack_step_kernel<TMAX, KIND, TMAX, DMAX, BOT>;
+    const size_t smem = sizeof(StepSmem<TMAX, DMAX, BOT>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<p.n_streams, TMAX, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-template <int KIND>
+template <int KIND, bool BOT>
 cudaError_t launch_kind(const StepParams& p, int v, cudaStream_t stream) {
     switch (v) {
-        case 0: return launch_variant<KIND, 64, 64>(p, stream);
-        case 1: return launch_variant<KIND, 128, 128>(p, stream);
-        case 2: return launch_variant<KIND, 256, 224>(p, stream);
-        case 3: return launch_variant<KIND, 256, 256>(p, stream);
-        case 4: return launch_variant<KIND, 512, 512>(p, stream);
+        case 0: return launch_variant<KIND, 64, 64, BOT>(p, stream);
+        case 1: return launch_variant<KIND, 128, 128, BOT>(p, stream);
+        case 2: return launch_variant<KIND, 256, 224, BOT>(p, stream);
+        case 3: return launch_variant<KIND, 256, 256, BOT>(p, stream);
+        case 4: return launch_variant<KIND, 512, 512, BOT>(p, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -704,19 +928,23 @@ int bytetrack_step_variant(int max_tracks, int max_dets) {
 }
 int bytetrack_step_tmax(int variant) { return kVariants[variant].tmax; }
 int step_variant_dmax(int variant) { return kVariants[variant].dmax; }
-size_t bytetrack_step_smem(int variant) {
+size_t bytetrack_step_smem(int variant, bool botsort) {
     switch (variant) {
-        case 0: return sizeof(StepSmem<64, 64>);
-        case 1: return sizeof(StepSmem<128, 128>);
-        case 2: return sizeof(StepSmem<256, 224>);
-        case 3: return sizeof(StepSmem<256, 256>);
-        case 4: return sizeof(StepSmem<512, 512>);
+        case 0: return botsort ? sizeof(StepSmem<64, 64, true>) : sizeof(StepSmem<64, 64>);
+        case 1: return botsort ? sizeof(StepSmem<128, 128, true>) : sizeof(StepSmem<128, 128>);
+        case 2: return botsort ? sizeof(StepSmem<256, 224, true>) : sizeof(StepSmem<256, 224>);
+        case 3: return botsort ? sizeof(StepSmem<256, 256, true>) : sizeof(StepSmem<256, 256>);
+        case 4: return botsort ? sizeof(StepSmem<512, 512, true>) : sizeof(StepSmem<512, 512>);
     }
     return 0;
 }
 
 cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, int variant, cudaStream_t stream) {
-    return kf_kind == KF_XYWH ? launch_kind<KF_XYWH>(p, variant, stream) : launch_kind<KF_XYAH>(p, variant, stream);
+    return kf_kind == KF_XYWH ? launch_kind<KF_XYWH, false>(p, variant, stream) : launch_kind<KF_XYAH, false>(p, variant, stream);
+}
+
+cudaError_t launch_botsort_step(const StepParams& p, int variant, cudaStream_t stream) {
+    return launch_kind<KF_XYWH, true>(p, variant, stream);
 }
 
 }  // namespace b200

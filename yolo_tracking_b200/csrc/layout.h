@@ -33,6 +33,13 @@
 
 #define B200_ERR_DET_OVERFLOW 1
 #define B200_ERR_TRACK_OVERFLOW 2
+#define B200_ERR_BOT_CAPACITY 4     // BoT-SORT: candidate graph overflow or more than 4 classes voted on one track
+
+// BoT-SORT contexts carry one more int32 component per slot: the row of the track in the stream's
+// embedding pool feat_pool[(s * Tmax + row) * feat_dim] (fp32) and class-vote table
+// cls_hist[(s * Tmax + row) * 9] = {cls[4], score sum[4], n}.  Rows never move; slots do.
+#define B200_NI_BOT 7
+#define B200_TI_FROW 6
 
 // bytes a track slot occupies in HBM (one direction)
 #define B200_SLOT_BYTES (B200_NF * 8 + B200_NI * 4)

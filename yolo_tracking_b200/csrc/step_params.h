@@ -22,6 +22,10 @@ struct StepParams {
     double det_thresh, iou_thresh, inertia, img_w, img_h;
     int max_age, min_hits, delta_t, asso_func;
     double* scratch;          // [S, Tcap, Dcap] dense cost matrices (OC-SORT)
+    // BoT-SORT
+    int with_reid;
+    float* feat_pool;         // [S, Tcap, feat_dim] smoothed track embeddings, row-indexed (layout.h)
+    double* cls_hist;         // [S, Tcap, 9] class-vote tables, row-indexed
     // device state (layout.h)
     double* state_f;
     int* state_i;
@@ -42,8 +46,9 @@ struct StepParams {
 // with the variant's slot capacity as stride.
 int bytetrack_step_variant(int max_tracks, int max_dets);   // -1: nothing large enough
 int bytetrack_step_tmax(int variant);
-size_t bytetrack_step_smem(int variant);
+size_t bytetrack_step_smem(int variant, bool botsort = false);
 cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, int variant, cudaStream_t stream);
+cudaError_t launch_botsort_step(const StepParams& p, int variant, cudaStream_t stream);
 size_t ocsort_step_smem(int variant);
 cudaError_t launch_ocsort_step(const StepParams& p, int variant, cudaStream_t stream);
 int step_variant_dmax(int variant);
