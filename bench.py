@@ -27,14 +27,58 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-CONFIG_ID = 5
-N_OBJECTS = 200
-STREAMS_PER_GPU = 4096
-MAX_DETS = 224
-MAX_TRACKS = 256
-PARAMS = dict(track_thresh=0.5, match_thresh=0.8, track_buffer=30, frame_rate=30)   # bytetrack.yaml
-# algorithmic HBM bytes: track slot in+out, detection row in, output row out
-B_SLOT, B_DET, B_ROW = 2 * 200, 48, 64
+# Workloads (BASELINE.json configs).  The headline (default) is config 5; the others are reported in DESIGN.md.
+# b_slot: algorithmic HBM bytes of one track slot, in + out; b_feat: embedding bytes per
+# track-update (smoothed row read + detection row read + smoothed row written).
+WORKLOADS = {
+    "bytetrack": dict(kind="bytetrack", config=5, objects=200, streams=4096, max_dets=224, max_tracks=256, emb=0,
+                      params=dict(track_thresh=0.5, match_thresh=0.8, track_buffer=30, frame_rate=30),      # bytetrack.yaml
+                      b_slot=2 * 200, b_feat=0, kernel="bytetrack_step_kernel", img_hw=(0, 0),
+                      label="config5: ByteTrack multi-stream (bytetrack.yaml: track_thresh 0.5, match_thresh 0.8, "
+                            "track_buffer 30), 200 objects/stream, sharded by stream"),
+    "ocsort": dict(kind="ocsort", config=2, objects=100, streams=64, max_dets=128, max_tracks=256, emb=0,
+                   params=dict(det_thresh=0, max_age=30, min_hits=1, asso_threshold=0.3, delta_t=3, asso_func="giou",
+                               inertia=0.2), occlusion=True,                                                  # ocsort.yaml
+                   b_slot=2 * (37 * 8 + 10 * 4), b_feat=0, kernel="ocsort_step_kernel", img_hw=(2160, 3840),
+                   label="config2: OC-SORT (ocsort.yaml: giou, det_thresh 0, min_hits 1, max_age 30, delta_t 3, inertia 0.2), "
+                         "100 objects/stream with occlusion runs, sharded by stream"),
+    "botsort": dict(kind="botsort", config=3, objects=100, streams=256, max_dets=128, max_tracks=256, emb=512,
+                    params=dict(track_high_thresh=0.33824964456239337, track_low_thresh=0.1,
+                                new_track_thresh=0.21144301345190655, track_buffer=60, match_thresh=0.22734550911325851,
+                                proximity_thresh=0.5945380911899254, appearance_thresh=0.4818211117541298, frame_rate=30),
+                    b_slot=2 * (22 * 8 + 7 * 4 + 72), b_feat=3 * 512 * 4, kernel="bytetrack_step_kernel<BOT>", img_hw=(0, 0),
+                    label="config3: BoT-SORT (botsort.yaml, identity camera motion, 512-d appearance embeddings), "
+                          "100 objects/stream, sharded by stream"),
+}
+W = dict(WORKLOADS["bytetrack"])          # the active workload (set in main)
+CONFIG_ID, N_OBJECTS, STREAMS_PER_GPU = W["config"], W["objects"], W["streams"]
+MAX_DETS, MAX_TRACKS, PARAMS = W["max_dets"], W["max_tracks"], W["params"]
+B_DET, B_ROW = 48, 64
+
+
+def select_workload(name):
+    global CONFIG_ID, N_OBJECTS, STREAMS_PER_GPU, MAX_DETS, MAX_TRACKS, PARAMS
+    W.clear()
+    W.update(WORKLOADS[name])
+    CONFIG_ID, N_OBJECTS, STREAMS_PER_GPU = W["config"], W["objects"], W["streams"]
+    MAX_DETS, MAX_TRACKS, PARAMS = W["max_dets"], W["max_tracks"], W["params"]
+
+
+def _stream_inputs(stream, n_frames):
+    """dets[F, MAX_DETS, 6], ndets[F], seam features[F, MAX_DETS, emb] or None for one stream of the workload."""
+    from yolo_tracking_b200.synth import make_stream
+    kw = dict(occlusion=True) if W.get("occlusion") else {}
+    d, n, e = make_stream(CONFIG_ID, stream, N_OBJECTS, n_frames, dmax=MAX_DETS, emb_dim=W["emb"], **kw)
+    if e is not None:
+        # the ReID seam (reid_multibackend.py:304-311): first-round rows / Frobenius norm of their matrix
+        high = PARAMS["track_high_thresh"]
+        feats = np.zeros_like(e)
+        for f in range(n_frames):
+            rows = np.nonzero(d[f, :n[f], 4] > high)[0]
+            if len(rows):
+                feats[f, rows] = e[f, rows] / np.linalg.norm(e[f, rows])
+        e = feats
+    return d, n, e
 
 
 def host_cores():
@@ -50,23 +94,28 @@ _shared = {}
 
 def _gen_worker(args):
     first, count, stream0, n_frames = args
-    from yolo_tracking_b200.synth import make_stream
-    dets, nd = _shared["dets"], _shared["nd"]
+    dets, nd, feats = _shared["dets"], _shared["nd"], _shared.get("feats")
     for i in range(first, first + count):
-        d, n, _ = make_stream(CONFIG_ID, stream0 + i, N_OBJECTS, n_frames, dmax=MAX_DETS)
+        d, n, e = _stream_inputs(stream0 + i, n_frames)
         dets[:, i] = d
         nd[:, i] = n
+        if feats is not None:
+            feats[:, i] = e
     return count
 
 
 def generate(n_streams, stream0, n_frames, workers):
-    """dets[F, S, MAX_DETS, 6] f64, ndets[F, S] i32 in fork-shared anonymous memory."""
+    """dets[F, S, MAX_DETS, 6] f64, ndets[F, S] i32 (and feats[F, S, MAX_DETS, emb] f32) in fork-shared anonymous memory."""
     nbytes = n_frames * n_streams * MAX_DETS * 6 * 8
     buf = mmap.mmap(-1, nbytes)
     buf2 = mmap.mmap(-1, n_frames * n_streams * 4)
     dets = np.frombuffer(buf, dtype=np.float64).reshape(n_frames, n_streams, MAX_DETS, 6)
     nd = np.frombuffer(buf2, dtype=np.int32).reshape(n_frames, n_streams)
     _shared["dets"], _shared["nd"] = dets, nd
+    _shared.pop("feats", None)
+    if W["emb"]:
+        buf3 = mmap.mmap(-1, n_frames * n_streams * MAX_DETS * W["emb"] * 4)
+        _shared["feats"] = np.frombuffer(buf3, dtype=np.float32).reshape(n_frames, n_streams, MAX_DETS, W["emb"])
     workers = max(1, min(workers, n_streams))
     chunk = max(1, (n_streams + workers * 4 - 1) // (workers * 4))
     tasks = [(i, min(chunk, n_streams - i), stream0, n_frames) for i in range(0, n_streams, chunk)]
@@ -76,30 +125,43 @@ def generate(n_streams, stream0, n_frames, workers):
     else:
         with mp.get_context("fork").Pool(workers) as pool:
             pool.map(_gen_worker, tasks)
-    return dets, nd
+    return dets, nd, _shared.get("feats")
 
 
 # ----------------------------------------------------------------------------- CPU legs
+def _make_oracle():
+    if W["kind"] == "bytetrack":
+        from oracle.bytetrack import ByteTrackOracle
+        return ByteTrackOracle(**PARAMS)
+    if W["kind"] == "ocsort":
+        from oracle.ocsort import OCSortOracle
+        return OCSortOracle(False, use_byte=False, **PARAMS)
+    from oracle.botsort import BoTSORTOracle
+    return BoTSORTOracle(**PARAMS)
+
+
 def _oracle_worker(args):
     streams, n_frames, warm = args
-    from oracle.bytetrack import ByteTrackOracle
-    from yolo_tracking_b200.synth import make_stream
-    data = [make_stream(CONFIG_ID, s, N_OBJECTS, n_frames, dmax=MAX_DETS) for s in streams]
-    trks = [ByteTrackOracle(**PARAMS) for _ in streams]
-    for f in range(warm):
+    data = [_stream_inputs(s, n_frames) for s in streams]
+    trks = [_make_oracle() for _ in streams]
+
+    def step(f):
         for k, t in enumerate(trks):
-            t.update(data[k][0][f, :data[k][1][f]], None)
+            d, n, e = data[k]
+            second = W["img_hw"] if W["kind"] == "ocsort" else (e[f, :n[f]] if e is not None else None)
+            t.update(d[f, :n[f]], second)
+    for f in range(warm):
+        step(f)
     base = sum(t.track_updates for t in trks)
     t0 = time.perf_counter()
     for f in range(warm, n_frames):
-        for k, t in enumerate(trks):
-            t.update(data[k][0][f, :data[k][1][f]], None)
+        step(f)
     dt = time.perf_counter() - t0
     return sum(t.track_updates for t in trks) - base, dt
 
 
 def cpu_oracle_run(n_workers, streams_per_worker, steps, warmup):
-    """The oracle port (oracle/bytetrack.py) on `n_workers` processes; returns
+    """The oracle port (oracle/<tracker>.py) on `n_workers` processes; returns
     (track_updates, wall_seconds = slowest worker)."""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     tasks = [([100000 + w * streams_per_worker + k for k in range(streams_per_worker)], steps + warmup, warmup)
@@ -169,11 +231,10 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "track-updates/s", "value": val, "unit": "track-updates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "config5: ByteTrack 4096 streams/GPU x 200 objects (bytetrack.yaml)",
-                   "sample_streams": cores * spw, "objects": N_OBJECTS},
+        "config": {"workload": W["label"], "streams_per_gpu": args.streams, "sample_streams": cores * spw, "objects": N_OBJECTS},
         "cpu_baseline": {"value": val, "unit": "track-updates/s", "cores": cores, "kind": "port",
                          "sample": f"{cores * spw} streams x {args.steps} frames after {args.warmup} warm-up frames, "
-                                   f"oracle/bytetrack.py (numpy port of the reference; /root/reference is Python and "
+                                   f"oracle/{W['kind']}.py (numpy port of the reference; /root/reference is Python and "
                                    f"cannot travel), one process per core"},
         "e2e": {"value": val, "unit": "track-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -186,7 +247,10 @@ def run_b200(args, rank, world, local_rank):
     cores = host_cores()
     gen_workers = max(1, cores // max(1, world))
     t_gen = time.time()
-    dets_h, nd_h = generate(S, rank * S, F, gen_workers)
+    from yolo_tracking_b200.shard import shard_bounds
+    stream0, stream1 = shard_bounds(S * world, rank, world)          # weak scaling: S streams per GPU, block-sharded
+    assert stream1 - stream0 == S
+    dets_h, nd_h, feats_h = generate(S, stream0, F, gen_workers)
     t_gen = time.time() - t_gen
 
     cpu_base = None
@@ -194,7 +258,7 @@ def run_b200(args, rank, world, local_rank):
         tu, dt = cpu_oracle_run(cores, 1, 40, 10)
         cpu_base = {"value": tu / dt, "unit": "track-updates/s", "cores": cores, "kind": "port",
                     "sample": f"{cores} streams x 40 frames after 10 warm-up frames of the same workload, "
-                              f"oracle/bytetrack.py, one process per core"}
+                              f"oracle/{W['kind']}.py, one process per core"}
 
     import torch
     import torch.distributed as dist
@@ -212,9 +276,22 @@ def run_b200(args, rank, world, local_rank):
     dets_h, nd_h = pin_all.numpy(), pin_nd_all.numpy()
     d_dets = pin_all.to(dev)                            # all frames resident in HBM for the device leg
     d_nd = pin_nd_all.to(dev)
+    d_feats = None
+    if feats_h is not None:
+        pin_feats = torch.empty(feats_h.shape, dtype=torch.float32, pin_memory=True)
+        pin_feats.numpy()[...] = feats_h
+        feats_h = pin_feats.numpy()
+        d_feats = pin_feats.to(dev)
+    hw = W["img_hw"]
+
+    def feats_dev(f):
+        return d_feats[f] if d_feats is not None else None
+
+    def feats_host(f):
+        return feats_h[f] if feats_h is not None else None
     d_out = torch.empty((S, MAX_TRACKS, 8), dtype=torch.float64, device=dev)
     d_nout = torch.empty((S,), dtype=torch.int32, device=dev)
-    trk = BatchedTracker("bytetrack", S, max_tracks=MAX_TRACKS, max_dets=MAX_DETS, device=local_rank, **PARAMS)
+    trk = BatchedTracker(W["kind"], S, max_tracks=MAX_TRACKS, max_dets=MAX_DETS, device=local_rank, feat_dim=W["emb"], **PARAMS)
     stream = torch.cuda.Stream(device=dev)
 
     def barrier():
@@ -226,26 +303,33 @@ def run_b200(args, rank, world, local_rank):
     # ---------------- device-resident leg -------------------------------------------------
     with torch.cuda.stream(stream):
         for f in range(args.warmup):
-            trk.step_device(d_dets[f], d_nd[f], d_out, d_nout, stream=stream.cuda_stream)
+            trk.step_device(d_dets[f], d_nd[f], d_out, d_nout, d_feats=feats_dev(f), img_hw=hw, stream=stream.cuda_stream)
     barrier()
     tu0, l0 = trk.track_updates(), trk.launches()
     rows = 0
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    nout_acc = torch.zeros((), dtype=torch.int64, device=dev)
+    # L2 hygiene: config 5's per-step working set is several times the 126 MB L2 and every step reads new
+    # detections; small workloads (config 2 / 3 at their own stream counts) get a 256 MB L2 flush between steps,
+    # outside the per-step event pairs.
+    working_set = S * N_OBJECTS * (W["b_slot"] + W["b_feat"] + 48 + 64)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev) if working_set < (256 << 20) else None
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
     with torch.cuda.stream(stream):
-        evs[0].record(stream)
         for k in range(args.steps):
             f = args.warmup + k
-            trk.step_device(d_dets[f], d_nd[f], d_out, d_nout, stream=stream.cuda_stream)
-            evs[k + 1].record(stream)
+            if flush is not None:
+                flush.zero_()
+            ev0[k].record(stream)
+            trk.step_device(d_dets[f], d_nd[f], d_out, d_nout, d_feats=feats_dev(f), img_hw=hw, stream=stream.cuda_stream)
+            ev1[k].record(stream)
     barrier()
     sampler.stop_flag = True
     sampler.join()
-    step_ms = np.array([evs[k].elapsed_time(evs[k + 1]) for k in range(args.steps)])
-    total_ms = evs[0].elapsed_time(evs[-1])
+    step_ms = np.array([ev0[k].elapsed_time(ev1[k]) for k in range(args.steps)])
+    total_ms = ev0[0].elapsed_time(ev1[-1]) if flush is None else float(step_ms.sum())
     tu_dev = trk.track_updates() - tu0
     launches = trk.launches() - l0
     dets_timed = int(nd_h[args.warmup:].sum())
@@ -258,7 +342,7 @@ def run_b200(args, rank, world, local_rank):
     pin_nout = [torch.empty((S,), dtype=torch.int32).pin_memory() for _ in range(nslot)]
 
     def submit(f, slot):
-        trk.submit(slot, dets_h[f], nd_h[f], pin_out[slot].numpy(), pin_nout[slot].numpy())
+        trk.submit(slot, dets_h[f], nd_h[f], pin_out[slot].numpy(), pin_nout[slot].numpy(), feats=feats_host(f), img_hw=hw)
 
     for f in range(args.warmup):
         submit(f, f % nslot)
@@ -273,7 +357,7 @@ def run_b200(args, rank, world, local_rank):
             trk.wait(slot)
             rows += int(pin_nout[slot].numpy().sum())      # device->host read of the step's result
         submit(args.warmup + k, slot)
-        h2d += int(nd_h[args.warmup + k].max()) * 48 * S + 4 * S
+        h2d += int(nd_h[args.warmup + k].max()) * (48 + 4 * W["emb"]) * S + 4 * S
         d2h += S * MAX_TRACKS * 64 + 4 * S
     for k in range(max(0, args.steps - nslot), args.steps):
         trk.wait(k % nslot)
@@ -284,13 +368,10 @@ def run_b200(args, rank, world, local_rank):
     trk.sync()
 
     # ---------------- reduce over ranks ----------------------------------------------------
-    vals = torch.tensor([total_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    sums = torch.tensor([tu_dev, tu_e2e, launches, rows, dets_timed], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
-    total_ms_max, e2e_ms_max = vals.tolist()
-    tu_all, tu_e2e_all, launches_all, rows_all, dets_all = sums.tolist()
+    from yolo_tracking_b200.shard import reduce_timing
+    total_ms_max, (tu_all, tu_e2e_all, launches_all, rows_all, dets_all) = reduce_timing(
+        total_ms, [tu_dev, tu_e2e, launches, rows, dets_timed], device=dev)
+    e2e_ms_max, _ = reduce_timing(e2e_s * 1e3, [], device=dev)
     if rank == 0:
         peaks = {}
         try:
@@ -302,25 +383,26 @@ def run_b200(args, rank, world, local_rank):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                tr = json.load(fh)["bytetrack_step_kernel"]
+                tr = json.load(fh)[W["kernel"]]
             if tr["streams"] == S:
                 traffic = tr["dram_bytes_per_launch"]
         except Exception:
             pass
         # rank-0 kernel: algorithmic bytes per launch / mean launch duration (events on the launch stream)
-        alg_bytes = (tu_dev * B_SLOT + dets_timed * B_DET + rows * B_ROW) / args.steps     # rank-0 shard
+        alg_bytes = (tu_dev * (W["b_slot"] + W["b_feat"]) + dets_timed * B_DET + rows * B_ROW) / args.steps     # rank-0 shard
         mean_ms = float(step_ms.mean())
         achieved = alg_bytes / (mean_ms * 1e-3) / 1e9
         line = {
             "metric": "track-updates/s", "value": tu_all / (total_ms_max * 1e-3), "unit": "track-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "config5: ByteTrack multi-stream (bytetrack.yaml: track_thresh 0.5, match_thresh 0.8, "
-                                   "track_buffer 30), 200 objects/stream, sharded by stream",
+            "config": {"workload": W["label"],
                        "streams_per_gpu": S, "streams_total": S * world, "objects_per_stream": N_OBJECTS,
                        "max_tracks": MAX_TRACKS, "max_dets": MAX_DETS,
-                       "l2": "per-step working set (state + detections + outputs) is ~%.0f MB > 126 MB L2; "
-                             "every step reads new detections" % ((S * MAX_TRACKS * 200 * 2 + S * 200 * 48 + S * MAX_TRACKS * 64) / 1e6),
+                       "l2": ("per-step working set (state + detections + outputs) is ~%.0f MB > 126 MB L2; every step reads "
+                              "new detections" % (working_set / 1e6)) if flush is None else
+                             ("per-step working set ~%.0f MB: a 256 MB buffer is rewritten between steps (L2 flush), outside "
+                              "the per-step event pairs; value = units / sum of step times" % (working_set / 1e6)),
                        "data_gen_s": round(t_gen, 1)},
             "p50_step_ms": float(np.percentile(step_ms, 50)), "p99_step_ms": float(np.percentile(step_ms, 99)),
             "e2e": {"value": tu_e2e_all / (e2e_ms_max * 1e-3), "unit": "track-updates/s",
@@ -328,7 +410,7 @@ def run_b200(args, rank, world, local_rank):
                     "ms_per_step": e2e_ms_max / args.steps, "pipeline_depth": nslot,
                     "output_rows_per_step": rows_all / args.steps},
             "gpu_launches": int(launches_all),
-            "roofline": {"bound": "hbm", "kernel": "bytetrack_step_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": W["kernel"], "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "alg_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_ms,
@@ -348,9 +430,14 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--streams", type=int, default=STREAMS_PER_GPU, help="streams per GPU")
+    ap.add_argument("--workload", default="bytetrack", choices=sorted(WORKLOADS),
+                    help="bytetrack = BASELINE config 5 (the headline); ocsort = config 2; botsort = config 3")
+    ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's own count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    select_workload(args.workload)
+    if args.streams <= 0:
+        args.streams = STREAMS_PER_GPU
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -10,7 +10,7 @@ import bench  # noqa: E402
 
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 F = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-dets, nd = bench.generate(S, 0, F, bench.host_cores())
+dets, nd, _ = bench.generate(S, 0, F, bench.host_cores())
 import torch  # noqa: E402
 from yolo_tracking_b200.batch import BatchedTracker  # noqa: E402
 
