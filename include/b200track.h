@@ -164,6 +164,20 @@ int b200track_iou_distance(int32_t n, int32_t m, const double* d_a, const double
  *     in double on the fp32 values; a[n, dim] x b[m, dim] -> out[n, m] fp64 */
 int b200track_embedding_distance(int32_t n, int32_t m, int32_t dim, const float* d_a, const float* d_b,
                                  double* d_out, void* stream);
+/* b200track_appearance_cost <- the thresholded appearance cost its callers build from embedding_distance
+ *     (matching.py:145-167): BoT-SORT bot_sort.py:304-306 / :363-365 (emb / 2; emb[emb > appearance_thresh] = 1;
+ *     emb[iou mask] = 1), StrongSORT strongsort/sort/linear_assignment.py:59-78 (cost > max_distance ->
+ *     max_distance + 1e-5), for `batch` streams at once:
+ *       out[b, t, d] = fill  if d_gate && d_gate[b, t, d]  or  scale * max(0, cosine distance) > thresh
+ *                    = scale * max(0, cosine distance)   otherwise, exact (fp64 on the fp32 values).
+ *     d_trk [batch, n_tracks, dim], d_det [batch, n_dets, dim] fp32, dim a multiple of 64; d_gate uint8
+ *     [batch, n_tracks, n_dets] or NULL.  A bf16 tcgen05 GEMM pre-filters, survivors are re-evaluated in
+ *     fp64 in the same kernel.  d_workspace: b200track_appearance_cost_workspace() bytes of device memory.
+ *     d_stats (device, may be NULL): [0] += entries evaluated exactly, [1] += internal protocol errors. */
+int b200track_appearance_cost_workspace(int32_t batch, int32_t n_tracks, int32_t n_dets, int32_t dim, uint64_t* h_bytes);
+int b200track_appearance_cost(int32_t batch, int32_t n_tracks, int32_t n_dets, int32_t dim, const float* d_trk,
+                              const float* d_det, const uint8_t* d_gate, double scale, double thresh, double fill,
+                              double* d_out, void* d_workspace, uint64_t workspace_bytes, uint64_t* d_stats, void* stream);
 /* b200track_lapjv <- lap.lapjv(cost, extend_cost=True, cost_limit=L) as called from
  *     matching.py:64 (finite limit) and association.py:23 (cost_limit = +inf): `batch`
  *     independent problems cost[batch, rows, cols] -> x[batch, rows], y[batch, cols] (-1 = unmatched) */

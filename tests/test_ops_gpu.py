@@ -152,3 +152,39 @@ def test_lapjv_no_limit_mostly_zero_costs(rows, cols):
         strong = cost[b][r, ox[r]] < -1e-6
         assert np.array_equal(x[b][r][strong], ox[r][strong]), f"problem {b}: real pairs"
         assert abs(cost[b][r, x[b][r]].sum() - cost[b][r, ox[r]].sum()) < 1e-12, f"problem {b}: objective"
+
+
+def _exact_appearance(trk, det, scale, thresh, fill, gate=None):
+    from scipy.spatial.distance import cdist
+    out = np.empty((trk.shape[0], trk.shape[1], det.shape[1]))
+    for b in range(trk.shape[0]):
+        e = scale * np.maximum(0.0, cdist(trk[b].astype(np.float32), det[b].astype(np.float32), "cosine"))   # matching.py:156-166
+        e[e > thresh] = fill
+        if gate is not None:
+            e[gate[b] != 0] = fill
+        out[b] = e
+    return out
+
+
+@pytest.mark.parametrize("B,T,D,F,scale,thresh,fill", [
+    (3, 100, 90, 512, 0.5, 0.25, 1.0),            # BoT-SORT default appearance_thresh
+    (2, 200, 200, 512, 0.5, 0.4818211117541298, 1.0),   # botsort.yaml: the threshold sits inside the bulk of unrelated pairs
+    (2, 130, 37, 128, 1.0, 0.2, 0.2 + 1e-5),      # StrongSORT max_dist = 0.2 -> max_dist + 1e-5; ragged tile edges
+    (1, 300, 260, 256, 0.5, 0.3, 1.0),            # more than one tile in both directions
+    (4, 1, 1, 64, 0.5, 0.25, 1.0),
+])
+def test_appearance_cost_tensor_core_prefilter_is_exact(B, T, D, F, scale, thresh, fill):
+    """tcgen05 bf16 pre-filter + fp64 re-check == the reference's thresholded cosine cost (1e-9 relative)."""
+    from yolo_tracking_b200 import _ops
+    rng = np.random.default_rng(B * 1000 + T)
+    proto = rng.standard_normal((B, max(T, D), F))
+    trk = (proto[:, :T] + 0.3 * rng.standard_normal((B, T, F))).astype(np.float32) * rng.uniform(0.5, 2.0, (B, T, 1)).astype(np.float32)
+    det = (proto[:, :D] + 0.3 * rng.standard_normal((B, D, F))).astype(np.float32)
+    gate = rng.random((B, T, D)) < 0.2
+    for gt in (None, gate):
+        out, n_exact = _ops.appearance_cost(trk, det, scale, thresh, fill, gate=gt, return_stats=True)
+        ref = _exact_appearance(trk, det, scale, thresh, fill, gt)
+        assert np.array_equal(out == fill, ref == fill), "threshold decisions"
+        assert_close(out, ref, what="appearance cost")
+        assert n_exact < B * T * D or T * D <= 4           # the pre-filter did discard work
+        assert (ref != fill).sum() <= n_exact

@@ -125,6 +125,37 @@ def embedding_distance(a, b):
     return out.cpu().numpy()
 
 
+def appearance_cost(trk, det, scale=0.5, thresh=0.25, fill=1.0, gate=None, return_stats=False):
+    """Thresholded cosine cost of `batch` streams: trk [B, T, F], det [B, D, F] (fp32) -> out [B, T, D] fp64, where
+    out = fill if gated or scale * max(0, cosine distance) > thresh, else that value exactly.  tcgen05 bf16
+    pre-filter + fp64 re-evaluation of the survivors (include/b200track.h: b200track_appearance_cost)."""
+    lib = _lib.load()
+    torch = _torch()
+    trk = np.asarray(trk, dtype=np.float32)
+    det = np.asarray(det, dtype=np.float32)
+    single = trk.ndim == 2
+    if single:
+        trk, det = trk[None], det[None]
+        gate = None if gate is None else np.asarray(gate)[None]
+    B, T, F = trk.shape
+    D = det.shape[1]
+    dt, dd = _dev(trk, np.float32), _dev(det, np.float32)
+    dg = _dev(np.asarray(gate) != 0, np.uint8) if gate is not None else None
+    nbytes = C.c_uint64()
+    _lib.check(lib.b200track_appearance_cost_workspace(B, T, D, F, C.byref(nbytes)))
+    ws = torch.empty((max(int(nbytes.value), 1),), dtype=torch.uint8, device=dt.device)
+    stats = torch.zeros((2,), dtype=torch.int64, device=dt.device)
+    out = torch.full((B, T, D), float("nan"), dtype=torch.float64, device=dt.device)
+    _sync_check(lib.b200track_appearance_cost(B, T, D, F, _p(dt), _p(dd), _p(dg), float(scale), float(thresh), float(fill),
+                                              _p(out), _p(ws), int(nbytes.value), _p(stats), None))
+    st = stats.cpu().numpy()
+    if st[1]:
+        raise RuntimeError(f"appearance_cost: {int(st[1])} tile(s) hit an internal pipeline error")
+    res = out.cpu().numpy()
+    res = res[0] if single else res
+    return (res, int(st[0])) if return_stats else res
+
+
 def lapjv(cost, cost_limit=np.inf):
     """cost [R, C] or [B, R, C] -> x [.., R], y [.., C] (int32, -1 = unmatched)."""
     lib = _lib.load()
