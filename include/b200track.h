@@ -152,6 +152,11 @@ int b200track_kf_update(int32_t kf_kind, int32_t n, double* d_mean, double* d_co
 int b200track_kf_gating_distance(int32_t kf_kind, int32_t n_tracks, int32_t n_meas, const double* d_mean,
                                  const double* d_cov, const double* d_meas, int32_t only_position,
                                  int32_t metric, const double* d_conf, double* d_out, void* stream);
+/* The same for `batch` independent (tracks, measurements) problems - one per stream - in one launch:
+ * mean [batch, T, 8], cov [batch, T, 8, 8], meas [batch, D, 4], conf [batch, T] -> out [batch, T, D]. */
+int b200track_kf_gating_distance_batched(int32_t kf_kind, int32_t batch, int32_t n_tracks, int32_t n_meas, const double* d_mean,
+                                         const double* d_cov, const double* d_meas, int32_t only_position,
+                                         int32_t metric, const double* d_conf, double* d_out, void* stream);
 /* b200track_box_similarity <- iou_batch / giou_batch / diou_batch / ciou_batch / centroid_batch
  *     boxmot/utils/iou.py:6-188 ; a[n,4] x b[m,4] -> out[n,m] (img_w, img_h only for centroid)
  * b200track_iou_distance   <- matching.py:94-119 (1 - iou), optional fuse_score :213-221 when

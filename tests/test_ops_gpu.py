@@ -188,3 +188,30 @@ def test_appearance_cost_tensor_core_prefilter_is_exact(B, T, D, F, scale, thres
         assert_close(out, ref, what="appearance cost")
         assert n_exact < B * T * D or T * D <= 4           # the pre-filter did discard work
         assert (ref != fill).sum() <= n_exact
+
+
+def test_gating_distance_batched_equals_per_stream_calls():
+    """b200track_kf_gating_distance_batched == one b200track_kf_gating_distance call per stream == the oracle."""
+    import ctypes as C
+    import torch
+    from oracle import kalman
+    from yolo_tracking_b200 import _lib, _ops
+    lib = _lib.load()
+    rng = np.random.default_rng(5)
+    B, T, D = 3, 21, 17
+    z = np.stack([rng.uniform(100, 1800, B * T), rng.uniform(100, 1000, B * T), rng.uniform(0.3, 0.8, B * T),
+                  rng.uniform(60, 220, B * T)], axis=1)
+    mean, cov = kalman.initiate("xyah", z)
+    mean, cov = kalman.predict("xyah", mean, cov)
+    meas = mean.reshape(B, T, 8)[:, rng.integers(0, T, D), :4] + rng.normal(0, 3, (B, D, 4))
+    dm, dc, dz = (torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in (mean, cov, meas))
+    out = torch.empty((B, T, D), dtype=torch.float64, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())
+    _lib.check(lib.b200track_kf_gating_distance_batched(_lib.KF_XYAH, B, T, D, p(dm), p(dc), p(dz), 0, 0, None, p(out), None))
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    for b in range(B):
+        one = _ops.kf_gating_distance(_lib.KF_XYAH, mean[b * T:(b + 1) * T], cov[b * T:(b + 1) * T], meas[b])
+        assert np.array_equal(got[b], one)
+        for t in range(T):
+            assert_close(got[b, t], kalman.gating_distance("xyah", mean[b * T + t], cov[b * T + t], meas[b]), what="maha")

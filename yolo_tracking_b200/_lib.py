@@ -63,6 +63,7 @@ SIGNATURES = {
     "b200track_kf_project": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "b200track_kf_update": (C.c_int, [_I, _I, _P, _P, _P, _P, _P]),
     "b200track_kf_gating_distance": (C.c_int, [_I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "b200track_kf_gating_distance_batched": (C.c_int, [_I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),
     "b200track_box_similarity": (C.c_int, [_I, _I, _I, _P, _P, _D, _D, _P, _P]),
     "b200track_iou_distance": (C.c_int, [_I, _I, _P, _P, _P, _P, _P]),
     "b200track_embedding_distance": (C.c_int, [_I, _I, _I, _P, _P, _P, _P]),

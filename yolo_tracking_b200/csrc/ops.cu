@@ -184,6 +184,11 @@ __global__ void __launch_bounds__(256) kf_gating_kernel(int T, int D, const doub
                                                         const double* __restrict__ conf, double* __restrict__ out) {
     __shared__ double sL[GD_TRACKS][16];
     __shared__ double sM[GD_TRACKS][4];
+    {   // blockIdx.y = independent problem (stream): [T] tracks x [D] measurements each
+        const size_t bi = blockIdx.y;
+        mean += bi * T * 8; cov += bi * T * 64; meas += bi * D * 4; out += bi * T * D;
+        if (conf) conf += bi * T;
+    }
     const int t0 = blockIdx.x * GD_TRACKS, cnt = min(GD_TRACKS, T - t0);
     const int nd = only_position ? 2 : 4;
     if (threadIdx.x < cnt) {
@@ -399,6 +404,18 @@ extern "C" int b200track_kf_gating_distance(int32_t kind, int32_t T, int32_t D, 
     if (metric != 0 && metric != 1) { set_error("invalid distance metric"); return B200TRACK_ERR_ARG; }
     if (T == 0 || D == 0) return 0;
     int rc = dispatch_kind(kind, [&](auto K) { kf_gating_kernel<decltype(K)::value><<<(T + GD_TRACKS - 1) / GD_TRACKS, 256, 0, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out); });
+    if (rc) return rc;
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_kf_gating_distance_batched(int32_t kind, int32_t batch, int32_t T, int32_t D, const double* mean,
+                                                    const double* cov, const double* meas, int32_t only_position, int32_t metric,
+                                                    const double* conf, double* out, void* st) {
+    if (batch < 0 || batch > 65535 || T < 0 || D < 0 || !mean || !cov || !meas || !out) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (metric != 0 && metric != 1) { set_error("invalid distance metric"); return B200TRACK_ERR_ARG; }
+    if (batch == 0 || T == 0 || D == 0) return 0;
+    dim3 grid((T + GD_TRACKS - 1) / GD_TRACKS, batch);
+    int rc = dispatch_kind(kind, [&](auto K) { kf_gating_kernel<decltype(K)::value><<<grid, 256, 0, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out); });
     if (rc) return rc;
     LAUNCH_CHECK();
     return 0;
