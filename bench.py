@@ -358,7 +358,7 @@ def run_b200(args, rank, world, local_rank):
             rows += int(pin_nout[slot].numpy().sum())      # device->host read of the step's result
         submit(args.warmup + k, slot)
         h2d += int(nd_h[args.warmup + k].max()) * (48 + 4 * W["emb"]) * S + 4 * S
-        d2h += S * MAX_TRACKS * 64 + 4 * S
+        d2h += min(int(nd_h[args.warmup + k].max()), MAX_TRACKS) * 64 * S + 4 * S
     for k in range(max(0, args.steps - nslot), args.steps):
         trk.wait(k % nslot)
         rows += int(pin_nout[k % nslot].numpy().sum())

@@ -241,7 +241,11 @@ extern "C" int b200track_submit_host(b200track_ctx* ctx, int32_t slot, const dou
     CU_TRY(cudaEventRecord(s.done, ctx->s_compute));
     CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, s.done, 0));
     CU_TRY(cudaMemcpyAsync(h_nout, s.d_nout, S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
-    CU_TRY(cudaMemcpyAsync(h_out, s.d_out, S * T * 8 * sizeof(double), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    // every output row carries a distinct detection of this frame (a track is only listed as tracked in the frame it
+    // was matched or born), so at most maxnd rows per stream are valid: copy that prefix of each stream's block
+    if (maxnd > 0)
+        CU_TRY(cudaMemcpy2DAsync(h_out, T * 8 * sizeof(double), s.d_out, T * 8 * sizeof(double),
+                                 (size_t)(maxnd < (int)T ? maxnd : (int)T) * 8 * sizeof(double), S, cudaMemcpyDeviceToHost, ctx->s_d2h));
     CU_TRY(cudaEventRecord(s.out_ready, ctx->s_d2h));
     s.used = true;
     return 0;

@@ -386,21 +386,36 @@ bytetrack_step_kernel(const StepParams p) {
     // ---- HBM -> shared memory: detections [nd, 6] (planar), means, lifecycle ints ----------
     int fl = 0, frame_t = 0;
     {
+        // every global load of this phase is issued before the first value is used (one memory latency, not six)
         const double* g = p.dets + (size_t)s * p.max_dets * 6;
-        for (int i = tid; i < nd * 6; i += NT) {
-            const double val = g[i];
-            const int j = i / 6, c = i - 6 * j;
-            if (c < 4) sm.dbox[c][j] = val;
-            else if (c == 4) sm.dconf[j] = val;
-            else sm.dcls[j] = val;
+        constexpr int DITER = (DMAX * 6 + NT - 1) / NT;
+        const int nd6 = nd * 6;
+        double dv[DITER], mv[8];
+        int start_v = 0;
+#pragma unroll
+        for (int k = 0; k < DITER; ++k) { const int i = tid + k * NT; dv[k] = i < nd6 ? g[i] : 0.0; }
+        if (t < n) {
+#pragma unroll
+            for (int c = 0; c < 8; ++c) mv[c] = gf[(B200_TF_MEAN + c) * TMAX + t];
+            fl = gi[B200_TI_FLAGS * TMAX + t];
+            frame_t = gi[B200_TI_FRAME * TMAX + t];
+            start_v = gi[B200_TI_START * TMAX + t];
+            if constexpr (BOT) { sm.bot.frow[t] = (short)gi[B200_TI_FROW * TMAX + t]; sm.bot.emadet[t] = -1; }
+        }
+#pragma unroll
+        for (int k = 0; k < DITER; ++k) {
+            const int i = tid + k * NT;
+            if (i < nd6) {
+                const int j = i / 6, c = i - 6 * j;
+                if (c < 4) sm.dbox[c][j] = dv[k];
+                else if (c == 4) sm.dconf[j] = dv[k];
+                else sm.dcls[j] = dv[k];
+            }
         }
         if (t < n) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) sm.mean[c][t] = gf[(B200_TF_MEAN + c) * TMAX + t];
-            fl = gi[B200_TI_FLAGS * TMAX + t];
-            frame_t = gi[B200_TI_FRAME * TMAX + t];
-            sm.start_t[t] = gi[B200_TI_START * TMAX + t];
-            if constexpr (BOT) { sm.bot.frow[t] = (short)gi[B200_TI_FROW * TMAX + t]; sm.bot.emadet[t] = -1; }
+            for (int c = 0; c < 8; ++c) sm.mean[c][t] = mv[c];
+            sm.start_t[t] = start_v;
         }
         // the covariance / id / score lines are first used after the association: pull them into L2 now
         if (t < n && (t & 15) == 0) {

@@ -45,7 +45,7 @@ struct alignas(16) OcSmem {
     unsigned long long scratch[40];
     int pred[TMAX], xr[DMAX], yc[TMAX], claim[DMAX], partner[TMAX];
     int red_i[32], sh_i[4];
-    int rowcnt[DMAX], rowmatch[DMAX];
+    int rowcnt[DMAX], rowmatch[DMAX], colcnt[TMAX];
     int misc[8];
     short hd[DMAX], ht[TMAX], dmatch[DMAX], tmatch[TMAX], ud[DMAX], ut[TMAX];
     unsigned char scn[TMAX], kvalid[TMAX], alive[TMAX], dstate[DMAX];
@@ -88,13 +88,15 @@ __device__ __forceinline__ double oc_sim(int func, const Box& a, const Box& b, d
 // velocity-direction consistency cost of (track, detection), association.py:134-154
 __device__ __forceinline__ double oc_angle(double vy, double vx, double kcx, double kcy, bool valid, double dcx, double dcy,
                                            double inertia, double score) {
-    const double PI = 3.141592653589793;
+    // One reciprocal instead of the reference's two divisions by the norm and a multiplication by 1/pi instead of
+    // its division: <= 2 ulp away from numpy's value, like CUDA's acos already is from glibc's; the term only
+    // has to be exact at exact ties, and the structural tie (no velocity yet -> exactly 0) is handled by the caller.
+    const double HALF_PI = 1.5707963267948966, INV_PI = 0.3183098861837907;
     const double dx = xsub(dcx, kcx), dy = xsub(dcy, kcy);
-    const double norm = xadd(sqrt(xadd(xmul(dx, dx), xmul(dy, dy))), 1e-6);
-    const double X = xdiv(dx, norm), Y = xdiv(dy, norm);
-    double c = xadd(xmul(vx, X), xmul(vy, Y));
+    const double inv = __drcp_rn(xadd(sqrt(xadd(xmul(dx, dx), xmul(dy, dy))), 1e-6));
+    double c = xadd(xmul(vx, xmul(dx, inv)), xmul(vy, xmul(dy, inv)));
     c = fmin(fmax(c, -1.0), 1.0);
-    const double diff = xdiv(xsub(xdiv(PI, 2.0), fabs(acos(c))), PI);
+    const double diff = xmul(xsub(HALF_PI, fabs(acos(c))), INV_PI);
     return xmul(xmul(xmul(valid ? 1.0 : 0.0, diff), inertia), score);
 }
 
@@ -286,32 +288,34 @@ ocsort_step_kernel(const StepParams p) {
     // ---- first round: associate(dets, trks, ...) ------------------------------------------------
     if (R > 0 && Cn > 0) {
         double mx = -1e300;
-        int ccnt = 0, dummy = 0;
-        if (tid < Cn) {
-            const int sl = sm.ht[tid];
-            const Box tb = {sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]};
-            const double vy = sm.vel[0][sl], vx = sm.vel[1][sl], kcx = sm.kc[0][sl], kcy = sm.kc[1][sl];
-            const bool valid = sm.kvalid[sl];
-            const bool moving = valid && !(vx == 0.0 && vy == 0.0);
-            for (int r = 0; r < R; ++r) {
-                const int j = sm.hd[r];
+        if (tid < Cn) sm.colcnt[tid] = 0;
+        __syncthreads();
+        {   // all threads share the R x Cn pairs evenly: pair k -> (row k / Cn, column k % Cn), stepped without divisions
+            const int total = R * Cn, dr = NT / Cn, dc = NT - dr * Cn;
+            int r = tid / Cn, c = tid - r * Cn;
+            for (int k = tid; k < total; k += NT) {
+                const int sl = sm.ht[c], j = sm.hd[r];
+                const Box tb = {sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]};
                 const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
                 const double sim = oc_sim(func, db, tb, W, H);
                 double ang = 0.0;
-                if (moving) {
+                const double vy = sm.vel[0][sl], vx = sm.vel[1][sl];
+                if (sm.kvalid[sl] && !(vx == 0.0 && vy == 0.0)) {
                     const double dcx = xdiv(xadd(db.x1, db.x2), 2.0), dcy = xdiv(xadd(db.y1, db.y2), 2.0);
-                    ang = oc_angle(vy, vx, kcx, kcy, valid, dcx, dcy, p.inertia, sm.dconf[j]);
+                    ang = oc_angle(vy, vx, sm.kc[0][sl], sm.kc[1][sl], true, dcx, dcy, p.inertia, sm.dconf[j]);
                 }
-                const double c = xadd(-xadd(xadd(sim, ang), 0.0), xmul((double)(r * Cn + tid), TIE_EPS));
-                C[(size_t)r * TMAX + tid] = c;
-                mx = fmax(mx, c);
-                if (sim > thr) { ++ccnt; atomicAdd(&sm.rowcnt[r], 1); sm.rowmatch[r] = tid; }
+                const double cst = xadd(-xadd(xadd(sim, ang), 0.0), xmul((double)k, TIE_EPS));      // k == r * Cn + c
+                C[(size_t)r * TMAX + c] = cst;
+                mx = fmax(mx, cst);
+                if (sim > thr) { atomicAdd(&sm.colcnt[c], 1); atomicAdd(&sm.rowcnt[r], 1); sm.rowmatch[r] = c; }
+                r += dr; c += dc;
+                if (c >= Cn) { c -= Cn; ++r; }
             }
         }
-        block_max3<NT>(sm, mx, ccnt, dummy);
+        __syncthreads();
+        int ccnt = tid < Cn ? sm.colcnt[tid] : 0;
         int rc = tid < R ? sm.rowcnt[tid] : 0;
-        double dd = 0.0;
-        block_max3<NT>(sm, dd, rc, dummy);
+        block_max3<NT>(sm, mx, ccnt, rc);
         const bool shortcut = (rc == 1 && ccnt == 1);                          // association.py:157-159
         if (shortcut) {
             if (tid < R) sm.xr[tid] = sm.rowcnt[tid] == 1 ? sm.rowmatch[tid] : -1;
