@@ -209,7 +209,7 @@ class OCSortOracle:
         self.frame_count = 0
         self.count = 0
         self.track_updates = 0
-        self.stats = dict(lap_frames=0, ocr_frames=0, oru=0)
+        self.stats = dict(lap_frames=0, ocr_frames=0, oru=0, byte_matches=0)
 
     def update(self, dets, img):
         assert isinstance(dets, np.ndarray), "dets must be np.ndarray"
@@ -254,6 +254,7 @@ class OCSortOracle:
                     if left[d, k] < self.asso_threshold:
                         continue
                     self._upd(self.trackers[ut[k]], d2[d, :5], d2[d, 5], ind2[d])
+                    self.stats["byte_matches"] += 1
                     gone.append(ut[k])
                 ut = np.setdiff1d(ut, np.array(gone))
 

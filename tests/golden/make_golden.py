@@ -199,7 +199,13 @@ def gen_ocsort():
         "ocsort_c2": dict(stream=0, n_objects=30, n_frames=150, kw=dict(occlusion=True), params={}),
         "ocsort_churn": dict(stream=902, n_objects=16, n_frames=160, kw=dict(miss_prob=0.3, fp_rate=3.0),
                              params=dict(min_hits=3, max_age=8, det_thresh=0.3)),
+        # BYTE stage (ocsort.py:293-317): low-confidence detections rescue unmatched trackers
+        "ocsort_byte": dict(stream=905, n_objects=24, n_frames=140, kw=dict(miss_prob=0.1, fp_rate=2.0, occlusion=True),
+                            params=dict(use_byte=True, det_thresh=0.5, min_hits=2)),
     }
+    only = os.environ.get("GOLDEN_ONLY")
+    if only:
+        scenarios = {k: v for k, v in scenarios.items() if k in only.split(",")}
     img = np.zeros((1080, 1920, 3), dtype=np.uint8)
     for name, sc in scenarios.items():
         dets, nd, _ = make_stream(2, sc["stream"], sc["n_objects"], sc["n_frames"], **sc["kw"])
@@ -226,7 +232,9 @@ def gen_ocsort():
               rec_offs=int_offs, x=_ragged(xs, 7)[0], vel=_ragged(vels, 2)[0], last=_ragged(lasts, 5)[0],
               P=_ragged(Ps, 49)[0], heavy_frames=np.array(heavy_frames, dtype=np.int32),
               params=np.array([cfg["det_thresh"], cfg["max_age"], cfg["min_hits"], cfg["asso_threshold"], cfg["delta_t"],
-                               cfg["inertia"]], dtype=np.float64), img_hw=np.array([1080, 1920]))
+                               cfg["inertia"], float(cfg["use_byte"])], dtype=np.float64), img_hw=np.array([1080, 1920]))
+    if only:
+        return
     # the reference's own known-answer inputs (tests/test_python.py:97-139)
     det = np.array([[144, 212, 578, 480, 0.82, 0], [425, 281, 576, 472, 0.56, 65]], dtype=np.float64)
     rh.reset_counters()

@@ -26,7 +26,7 @@ def _check_state(st, snap, what):
     assert_close(st["last_observation"], snap["last_observation"], what=what + " last_observation")
 
 
-@pytest.mark.parametrize("name", ["ocsort_c2", "ocsort_churn"])
+@pytest.mark.parametrize("name", ["ocsort_c2", "ocsort_churn", "ocsort_byte"])
 def test_ocsort_replays_reference_golden(name):
     from yolo_tracking_b200.batch import BatchedTracker
     g = load_golden(name)
@@ -34,7 +34,8 @@ def test_ocsort_replays_reference_golden(name):
     dets, nd = g["dets"], g["ndets"]
     hw = tuple(int(v) for v in g["img_hw"])
     trk = BatchedTracker("ocsort", 1, max_tracks=128, max_dets=128, det_thresh=p[0], max_age=int(p[1]), min_hits=int(p[2]),
-                         asso_threshold=p[3], delta_t=int(p[4]), asso_func="giou", inertia=p[5])
+                         asso_threshold=p[3], delta_t=int(p[4]), asso_func="giou", inertia=p[5],
+                         use_byte=bool(p[6]) if len(p) > 6 else False)
     heavy = {int(f): k for k, f in enumerate(g["heavy_frames"])}
     p_offs = [0]
     for f in g["heavy_frames"]:
@@ -83,6 +84,8 @@ def test_ocsort_reference_known_answers():
     (2, 100, 40, dict(occlusion=True), {}),
     (4, 30, 60, dict(occlusion=True), dict(asso_func="iou", det_thresh=0.3)),
     (2, 30, 50, dict(occlusion=True), dict(asso_func="diou")),
+    (4, 40, 80, dict(occlusion=True, miss_prob=0.1), dict(use_byte=True, det_thresh=0.5, min_hits=2)),
+    (3, 24, 90, dict(miss_prob=0.25, fp_rate=3.0), dict(use_byte=True, det_thresh=0.6, max_age=10, asso_func="iou")),
 ])
 def test_ocsort_multistream_vs_oracle(n_streams, n_objects, n_frames, kw, params):
     from oracle.ocsort import OCSortOracle
@@ -93,7 +96,7 @@ def test_ocsort_multistream_vs_oracle(n_streams, n_objects, n_frames, kw, params
     cfg.update(params)
     dets, nd, _ = make_batch(2, n_streams, n_objects, n_frames, dmax=cap, first_stream=50, **kw)
     trk = BatchedTracker("ocsort", n_streams, max_tracks=cap, max_dets=cap, **cfg)
-    oracles = [OCSortOracle(False, use_byte=False, **cfg) for _ in range(n_streams)]
+    oracles = [OCSortOracle(False, **dict(dict(use_byte=False), **cfg)) for _ in range(n_streams)]
     hw = (2160, 3840) if n_objects > 64 else (1080, 1920)
     for f in range(n_frames):
         out, nout = trk.update_batch(np.ascontiguousarray(dets[f]), np.ascontiguousarray(nd[f]), img_hw=hw)

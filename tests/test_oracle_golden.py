@@ -121,10 +121,10 @@ def test_bytetrack_empty_and_asserts():
 def _ocsort_from_params(p, **kw):
     from oracle.ocsort import OCSortOracle
     return OCSortOracle(False, det_thresh=p[0], max_age=int(p[1]), min_hits=int(p[2]), asso_threshold=p[3],
-                        delta_t=int(p[4]), asso_func="giou", inertia=p[5], use_byte=False, **kw)
+                        delta_t=int(p[4]), asso_func="giou", inertia=p[5], use_byte=bool(p[6]) if len(p) > 6 else False, **kw)
 
 
-@pytest.mark.parametrize("name", ["ocsort_c2", "ocsort_churn"])
+@pytest.mark.parametrize("name", ["ocsort_c2", "ocsort_churn", "ocsort_byte"])
 def test_ocsort_oracle_replays_reference(name):
     g = load_golden(name)
     trk = _ocsort_from_params(g["params"])
@@ -153,6 +153,8 @@ def test_ocsort_oracle_replays_reference(name):
             k = heavy[f]
             assert_close(s["P"].reshape(-1, 49), g["P"][p_offs[k]:p_offs[k + 1]], abs_=1e-9, what=f"frame {f} P")
     assert trk.stats["oru"] > 0 and trk.stats["lap_frames"] > 0
+    if name == "ocsort_byte":
+        assert trk.stats["byte_matches"] > 20
 
 
 def test_ocsort_reference_known_answer():

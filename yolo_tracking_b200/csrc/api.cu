@@ -112,7 +112,6 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
             set_error("BoT-SORT with_reid needs feat_dim to be a multiple of 128 in [128, 4096]"); return B200TRACK_ERR_ARG; }
     }
     if (cfg->kind == B200TRACK_OCSORT) {
-        if (cfg->use_byte) { set_error("OC-SORT use_byte=True is not built (ocsort.yaml default is false)"); return B200TRACK_ERR_STATE; }
         if (cfg->delta_t < 1 || cfg->delta_t > 3) { set_error("OC-SORT delta_t must be in [1, 3]"); return B200TRACK_ERR_ARG; }
         if (cfg->asso_func < 0 || cfg->asso_func > B200TRACK_SIM_CENTROID) { set_error("unknown asso_func"); return B200TRACK_ERR_ARG; }
     }
@@ -136,7 +135,7 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     p.appearance_thresh = cfg->appearance_thresh;
     p.max_time_lost = (int)(cfg->frame_rate / 30.0 * cfg->track_buffer);   // byte_tracker.py:128-129
     p.det_thresh = cfg->det_thresh; p.iou_thresh = cfg->iou_thresh; p.inertia = cfg->inertia;
-    p.max_age = cfg->max_age; p.min_hits = cfg->min_hits; p.delta_t = cfg->delta_t; p.asso_func = cfg->asso_func;
+    p.max_age = cfg->max_age; p.min_hits = cfg->min_hits; p.delta_t = cfg->delta_t; p.asso_func = cfg->asso_func; p.use_byte = cfg->use_byte ? 1 : 0;
     if (cfg->kind == B200TRACK_OCSORT) { ctx->nf = B200_OC_NF; ctx->ni = B200_OC_NI; }
     if (cfg->kind == B200TRACK_BOTSORT) { ctx->ni = B200_NI_BOT; p.with_reid = cfg->with_reid ? 1 : 0; }
     ctx->kf_kind = cfg->kind == B200TRACK_BOTSORT ? B200TRACK_KF_XYWH : B200TRACK_KF_XYAH;

@@ -341,71 +341,94 @@ ocsort_step_kernel(const StepParams p) {
         __syncthreads();
     }
 
-    // ---- observation-centric recovery (ocsort.py:319-345): leftover detections x last observations
-    bool ocr_ran = false;
-    // unmatched lists in associate()'s order (association.py:179-193): never matched first (ascending),
-    // then the members of low-similarity matches in match order (= ascending detection index)
-    {
+    // ---- second-round associations on leftovers: BYTE (ocsort.py:293-317, only with use_byte) and the
+    // observation-centric recovery (:319-345).  Both are: similarity of a detection list x a tracker list,
+    // and if any entry clears the threshold, a no-limit assignment whose pairs are kept when they clear it.
+    // rows = sm.ud[0..nr), columns = sm.ut[0..nc) (slot indices); boxes of the columns: predicted or last observed.
+    auto second_round = [&](int nr, int nc, bool last_boxes) -> bool {
+        if (nr <= 0 || nc <= 0) return false;                        // uniform
+        double mx = -1e300, smax = -1e300;
+        int d1 = 0, d2 = 0;
+        const double (*bx)[TMAX] = last_boxes ? sm.lbox : sm.tbox;
+        if (tid < nc) {
+            const int sl = sm.ut[tid];
+            const Box tb = {bx[0][sl], bx[1][sl], bx[2][sl], bx[3][sl]};
+            for (int r = 0; r < nr; ++r) {
+                const int j = sm.ud[r];
+                const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
+                const double sim = oc_sim(func, db, tb, W, H);
+                const double c = xadd(-sim, xmul((double)(r * nc + tid), TIE_EPS));
+                C[(size_t)r * TMAX + tid] = c;
+                mx = fmax(mx, c);
+                smax = fmax(smax, sim);
+            }
+        }
+        block_max3<NT>(sm, smax, d1, d2);
+        block_max3<NT>(sm, mx, d1, d2);
+        if (!(smax > thr)) return false;
+        const DenseLap w = make_dense<NT>(sm);
+        const double lambda = 2.0 * (mx + 1.0);
+        dense_lap_init<NT>(w, C, TMAX, nr, nc, lambda);
+        dense_lap_augment<NT>(w, C, TMAX, nr, nc, lambda);
+        if (tid < nr) {
+            const int c = sm.xr[tid];
+            if (c >= 0) {
+                const int j = sm.ud[tid], sl = sm.ut[c];
+                const Box tb = {bx[0][sl], bx[1][sl], bx[2][sl], bx[3][sl]};
+                const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
+                if (!(oc_sim(func, db, tb, W, H) < thr)) {
+                    if (sm.dstate[j] != DS_NONE) sm.dstate[j] = DS_MATCHED;
+                    sm.dmatch[j] = (short)sl; sm.tmatch[sl] = (short)j;
+                }
+            }
+        }
+        __syncthreads();
+        return true;
+    };
+    // unmatched lists in associate()'s order (association.py:179-193): never matched first (ascending), then the
+    // members of low-similarity matches in match order (= ascending detection index).  `sorted_trks`: the tracker
+    // list went through np.setdiff1d (ascending) because the BYTE stage ran its assignment.
+    if (t < TMAX) sm.partner[t] = -1;
+    __syncthreads();
+    if (tid < R && Cn > 0 && sm.xr[tid] >= 0 && sm.dstate[sm.hd[tid]] == DS_FREE1) sm.partner[sm.ht[sm.xr[tid]]] = tid;   // slot -> row of its partner
+    __syncthreads();
+    auto build_lists = [&](bool low_dets, bool sorted_trks, int& nUd, int& nUt) {
         const int ds = tid < DMAX ? sm.dstate[tid] : DS_NONE;
-        // mark trackers that sit in a low-similarity match
-        if (t < TMAX) sm.partner[t] = -1;
-        __syncthreads();
-        if (tid < R && sm.xr[tid] >= 0 && sm.dstate[sm.hd[tid]] == DS_FREE1) sm.partner[sm.ht[sm.xr[tid]]] = tid;   // slot -> row of its partner
-        __syncthreads();
+        const bool islow = low_dets && tid < nd && sm.dconf[tid] > 0.1 && sm.dconf[tid] < p.det_thresh;     // ocsort.py:244-249
         const bool ufree = live && sm.tmatch[t] < 0;
-        const bool ufree1 = ufree && (R > 0 && Cn > 0) && sm.partner[t] >= 0;
+        const bool ufree1 = ufree && !sorted_trks && sm.partner[t] >= 0;
         const bool ufree0 = ufree && !ufree1;
-        const unsigned long long val = (ds == DS_FREE0 ? 1ull : 0ull) | (ds == DS_FREE1 ? (1ull << 16) : 0ull) | (ufree0 ? (1ull << 32) : 0ull);
+        const bool d0 = low_dets ? islow : ds == DS_FREE0, dlate = !low_dets && ds == DS_FREE1;
+        const unsigned long long val = (d0 ? 1ull : 0ull) | (dlate ? (1ull << 16) : 0ull) | (ufree0 ? (1ull << 32) : 0ull) |
+                                       (ds == DS_FREE1 ? (1ull << 48) : 0ull);
         unsigned long long tot;
         const unsigned long long ex = block_exscan<NT>(val, sm.scratch, tot);
         const int n0d = (int)(tot & 0xffff), n1d = (int)((tot >> 16) & 0xffff), n0t = (int)((tot >> 32) & 0xffff);
-        if (ds == DS_FREE0) sm.ud[ex & 0xffff] = (short)tid;
-        if (ds == DS_FREE1) sm.ud[n0d + ((ex >> 16) & 0xffff)] = (short)tid;
+        if (d0) sm.ud[ex & 0xffff] = (short)tid;
+        if (dlate) sm.ud[n0d + ((ex >> 16) & 0xffff)] = (short)tid;
         if (ufree0) sm.ut[(ex >> 32) & 0xffff] = (short)t;
         // low-similarity trackers follow in the order of their partner detections
-        if (ds == DS_FREE1) sm.claim[tid] = (int)((ex >> 16) & 0xffff);          // rank of this detection among FREE1
+        if (ds == DS_FREE1) sm.claim[tid] = (int)((ex >> 48) & 0xffff);          // rank of this detection among FREE1
         __syncthreads();
-        if (ufree1) sm.ut[n0t + sm.claim[sm.hd[sm.partner[t]]]] = (short)t;
-        const int nUd = n0d + n1d, nUt = n0t + n1d;
-        __syncthreads();
-        if (nUd > 0 && nUt > 0) {
-            double mx = -1e300, smax = -1e300;
-            int d1 = 0, d2 = 0;
-            if (tid < nUt) {
-                const int sl = sm.ut[tid];
-                const Box lb = {sm.lbox[0][sl], sm.lbox[1][sl], sm.lbox[2][sl], sm.lbox[3][sl]};
-                for (int r = 0; r < nUd; ++r) {
-                    const int j = sm.ud[r];
-                    const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
-                    const double sim = oc_sim(func, db, lb, W, H);
-                    const double c = xadd(-sim, xmul((double)(r * nUt + tid), TIE_EPS));
-                    C[(size_t)r * TMAX + tid] = c;
-                    mx = fmax(mx, c);
-                    smax = fmax(smax, sim);
-                }
-            }
-            block_max3<NT>(sm, smax, d1, d2);
-            block_max3<NT>(sm, mx, d1, d2);
-            if (smax > thr) {
-                ocr_ran = true;
-                const DenseLap w = make_dense<NT>(sm);
-                const double lambda = 2.0 * (mx + 1.0);
-                dense_lap_init<NT>(w, C, TMAX, nUd, nUt, lambda);
-                dense_lap_augment<NT>(w, C, TMAX, nUd, nUt, lambda);
-                if (tid < nUd) {
-                    const int c = sm.xr[tid];
-                    if (c >= 0) {
-                        const int j = sm.ud[tid], sl = sm.ut[c];
-                        const Box lb = {sm.lbox[0][sl], sm.lbox[1][sl], sm.lbox[2][sl], sm.lbox[3][sl]};
-                        const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
-                        if (!(oc_sim(func, db, lb, W, H) < thr)) {
-                            sm.dstate[j] = DS_MATCHED; sm.dmatch[j] = (short)sl; sm.tmatch[sl] = (short)j;
-                        }
-                    }
-                }
-                __syncthreads();
-            }
+        int n1t = 0;
+        if (!sorted_trks) {
+            if (ufree1) sm.ut[n0t + sm.claim[sm.hd[sm.partner[t]]]] = (short)t;
+            n1t = (int)((tot >> 48) & 0xffff);       // every FREE1 detection has exactly one (still unmatched) partner tracker
         }
+        nUd = n0d + n1d; nUt = n0t + n1t;
+        __syncthreads();
+    };
+    bool byte_ran = false;
+    if (p.use_byte) {
+        int nr, nc;
+        build_lists(true, false, nr, nc);
+        byte_ran = second_round(nr, nc, false);
+    }
+    bool ocr_ran;
+    {
+        int nr, nc;
+        build_lists(false, byte_ran, nr, nc);
+        ocr_ran = second_round(nr, nc, true);
     }
 
     // ---- deferred Kalman work and bookkeeping, thread t = slot t ---------------------------------

@@ -20,7 +20,7 @@ struct StepParams {
     int max_time_lost;
     // OC-SORT (ocsort.yaml keys)
     double det_thresh, iou_thresh, inertia, img_w, img_h;
-    int max_age, min_hits, delta_t, asso_func;
+    int max_age, min_hits, delta_t, asso_func, use_byte;
     double* scratch;          // [S, Tcap, Dcap] dense cost matrices (OC-SORT)
     // BoT-SORT
     int with_reid;
