@@ -299,7 +299,50 @@ def gen_botsort():
               cov=_ragged(covs, 64)[0], cov_frames=np.array(cov_frames, dtype=np.int32), final_feat=final_feat)
 
 
-GENERATORS = {"kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort}
+# ----------------------------------------------------------------------------- MOT17-mini replay
+MOT_SEQS = ["MOT17-02-FRCNN", "MOT17-05-FRCNN", "MOT17-09-FRCNN"]
+
+
+def gen_mot():
+    """Public detections of three MOT17-mini sequences (assets/MOT17-mini/train/*/det/det.txt, dataset data) replayed
+    through the reference's ByteTrack and OC-SORT; the fixture holds the detection rows and the integer MOT rows the
+    reference's writer (examples/utils.py:8-28) would put in the result files."""
+    rh.install()
+    from yolo_tracking_b200 import mot_io
+    from yolo_tracking_b200.replay import dense_frames
+    from boxmot.trackers.ocsort.ocsort import OCSort
+    out = {}
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    for name in MOT_SEQS:
+        base = os.path.join(rh.REF_ROOT, "assets", "MOT17-mini", "train", name)
+        raw = np.loadtxt(os.path.join(base, "det", "det.txt"), delimiter=",", ndmin=2)[:, :7]
+        info = mot_io.read_seqinfo(base)
+        length = min(info["length"], 300)
+        raw = raw[raw[:, 0] <= length]
+        out[name + "_det"] = raw
+        out[name + "_len"] = np.int64(length)
+        frames, dets = mot_io.split_det_rows(raw)
+        seq = dense_frames(frames, dets, length)
+        for kind in ("bytetrack", "ocsort"):
+            if kind == "bytetrack":
+                trk = rh.make_tracker("bytetrack")
+            else:
+                rh.reset_counters()
+                trk = OCSort(False, det_thresh=0, max_age=30, min_hits=1, asso_threshold=0.3, delta_t=3, asso_func="giou",
+                             inertia=0.2, use_byte=False)
+            rows = []
+            for f, d in enumerate(seq):
+                o = trk.update(d, img)
+                if o.size:
+                    rows.append(mot_io.mot_rows(o, f))
+            rows = np.concatenate(rows, axis=0)
+            out[f"{name}_{kind}"] = mot_io.as_int_rows(rows)
+            print(name, kind, len(rows), "rows")
+    _save("mot17_mini", **out)
+
+
+GENERATORS = {"kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
+              "mot": gen_mot}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(GENERATORS)

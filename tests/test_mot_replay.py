@@ -1,0 +1,85 @@
+"""MOTChallenge formats either side of the path: real MOT17 public detections replayed through
+the trackers, result rows as the reference's writer prints them (examples/utils.py:8-28).  The fixture
+tests/golden/mot17_mini.npz holds the detection rows of three MOT17-mini sequences (first 300 frames) and the
+integer MOT rows produced by the live reference's ByteTrack and OC-SORT."""
+import numpy as np
+import pytest
+
+from _util import load_golden
+from yolo_tracking_b200 import mot_io
+from yolo_tracking_b200.replay import dense_frames, tracker_params
+
+SEQS = ["MOT17-02-FRCNN", "MOT17-05-FRCNN", "MOT17-09-FRCNN"]
+
+
+def _sequences(g):
+    seqs = []
+    for name in SEQS:
+        frames, dets = mot_io.split_det_rows(g[name + "_det"])
+        seqs.append(dense_frames(frames, dets, int(g[name + "_len"])))
+    return seqs
+
+
+def test_det_txt_round_trip(tmp_path):
+    g = load_golden("mot17_mini")
+    raw = g["MOT17-05-FRCNN_det"]
+    path = tmp_path / "seq" / "det" / "det.txt"
+    path.parent.mkdir(parents=True)
+    np.savetxt(path, np.concatenate([raw, -np.ones((len(raw), 3))], axis=1), delimiter=",", fmt="%.10g")
+    frames, dets = mot_io.read_det_txt(path)
+    f2, d2 = mot_io.split_det_rows(raw)
+    assert np.array_equal(frames, f2) and all(np.array_equal(a, b) for a, b in zip(dets, d2))
+    assert frames[0] >= 1 and np.all(np.diff(frames) > 0)
+    k = 3
+    rows = raw[raw[:, 0] == frames[k]]
+    assert np.array_equal(dets[k][:, 0], rows[:, 2]) and np.array_equal(dets[k][:, 2], rows[:, 2] + rows[:, 4])
+    assert np.array_equal(dets[k][:, 4], rows[:, 6]) and np.all(dets[k][:, 5] == 0)
+    # writer: frame is 1-based, ltwh, integers by truncation, trailing -1
+    out = np.array([[10.7, 20.2, 50.9, 80.1, 3, 0.93, 0, 5], [1.5, 2.5, 4.0, 9.75, 7, 0.4, 2, 1]])
+    txt = tmp_path / "res" / "a.txt"
+    mot_io.write_mot_results(txt, out, 0)
+    mot_io.write_mot_results(txt, out[:1], 1)
+    got = np.loadtxt(txt, dtype=np.int64, ndmin=2)
+    assert got.tolist() == [[1, 3, 10, 20, 40, 59, 0, 0, -1], [1, 7, 1, 2, 2, 7, 0, 2, -1], [2, 3, 10, 20, 40, 59, 0, 0, -1]]
+
+
+@pytest.mark.parametrize("kind", ["bytetrack", "ocsort"])
+def test_oracle_replay_matches_reference_files(kind):
+    from oracle.bytetrack import ByteTrackOracle
+    from oracle.ocsort import OCSortOracle
+    g = load_golden("mot17_mini")
+    p = tracker_params(kind)
+    for name, seq in zip(SEQS, _sequences(g)):
+        trk = ByteTrackOracle(**p) if kind == "bytetrack" else OCSortOracle(False, **p)
+        rows = []
+        for f, d in enumerate(seq):
+            o = trk.update(d, (1080, 1920)) if kind == "ocsort" else trk.update(d)
+            if o.size:
+                rows.append(mot_io.mot_rows(o, f))
+        assert np.array_equal(mot_io.as_int_rows(np.concatenate(rows)), g[f"{name}_{kind}"]), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["bytetrack", "ocsort"])
+def test_cuda_replay_matches_reference_files(kind):
+    """All three sequences as streams of one batched context; the files equal the reference's, row for row."""
+    from yolo_tracking_b200.replay import replay
+    g = load_golden("mot17_mini")
+    res = replay(kind, _sequences(g), tracker_params(kind), img_hw=(1080, 1920))
+    for name, rows in zip(SEQS, res):
+        assert np.array_equal(mot_io.as_int_rows(rows), g[f"{name}_{kind}"]), name
+
+
+@pytest.mark.gpu
+def test_replay_cli_writes_result_files(tmp_path):
+    from yolo_tracking_b200 import replay as rp
+    g = load_golden("mot17_mini")
+    for name in SEQS[1:]:
+        d = tmp_path / "src" / name / "det"
+        d.mkdir(parents=True)
+        raw = g[name + "_det"]
+        np.savetxt(d / "det.txt", np.concatenate([raw, -np.ones((len(raw), 3))], axis=1), delimiter=",", fmt="%.10g")
+    rp.main(["--tracker", "bytetrack", "--source", str(tmp_path / "src"), "--out", str(tmp_path / "out")])
+    for name in SEQS[1:]:
+        got = np.loadtxt(tmp_path / "out" / (name + ".txt"), dtype=np.int64, ndmin=2)
+        assert np.array_equal(got, g[f"{name}_bytetrack"]), name
