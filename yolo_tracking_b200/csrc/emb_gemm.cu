@@ -18,9 +18,9 @@
 //
 // Kernel 1 (unit_bf16_kernel): fp32 rows -> unit-norm bf16 rows (one warp per row, HBM bound).
 // Kernel 2 (appearance_cost_kernel): one CTA per (128-track tile, <=256-detection tile, stream):
-//   warp 0: TMA producer (4-stage ring of 128x64 + Nx64 bf16 tiles), warp 1: TMEM allocation + single-thread
-//   tcgen05.mma issue, warps 2-5: epilogue (tcgen05.ld, threshold test, candidate list in the freed ring),
-//   then all six warps run the fp64 recheck of the candidates.
+//   warp 0: TMA producer (2-stage ring of 128x64 + Nx64 bf16 tiles; two CTAs share an SM), warp 1: TMEM allocation +
+//   single-thread tcgen05.mma issue, warps 2-5: fill the output tile while the GEMM runs, then tcgen05.ld + threshold
+//   test into a candidate bitmask; then all six warps run the fp64 recheck of the candidates.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -35,7 +35,7 @@
 namespace b200 {
 namespace {
 
-constexpr int BM = 128, BK = 64, STAGES = 4, BN_MAX = 256;
+constexpr int BM = 128, BK = 64, STAGES = 2, BN_MAX = 256;       // 2 stages -> 97 KB: two CTAs per SM overlap each other's phases
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = BN_MAX * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int GEMM_THREADS = 192;
 constexpr double BAND_COS = 1e-2;
@@ -115,13 +115,14 @@ struct CostArgs {
 };
 
 // ---- kernel 2 -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
 appearance_cost_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const CostArgs g) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);     // 128B swizzle atoms are 1024 B
     __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ int ncand_s, fail_s;
+    __shared__ int fail_s;
+    __shared__ uint32_t cand_bits[BM * (BN_MAX / 32)];     // one bit per entry of the tile: survives the bf16 pre-filter
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN_MAX, b = blockIdx.z;
     const int nk = g.dim / BK;
@@ -131,7 +132,7 @@ appearance_cost_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(&acc_bar, 1);
-        ncand_s = 0; fail_s = 0;
+        fail_s = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {                                       // TMEM: 256 fp32 columns x 128 lanes
@@ -174,8 +175,18 @@ appearance_cost_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             umma_commit(&acc_bar);                         // accumulator complete
         }
     }
-    // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31 =====
-    uint32_t* cand = reinterpret_cast<uint32_t*>(smem);    // the ring is free once acc_bar fires
+    // ===== epilogue warps 2..5 =====
+    // (1) while the GEMM runs: the whole tile is filled with `fill`, coalesced (row by row, lanes across columns);
+    //     entries that survive the pre-filter are overwritten with their exact value in (3).
+    const int rows_valid = min(BM, g.n_trk - m0);
+    if (warp >= 2) {
+        for (int r = warp - 2; r < rows_valid; r += 4) {
+            double* orow = g.out + ((size_t)b * g.n_trk + m0 + r) * g.n_det + n0;
+            for (int c = lane; c < ncols; c += 32) orow[c] = g.fill;
+        }
+    }
+    // (2) accumulator -> one candidate bit per entry: warp w owns TMEM lanes 32 * (w % 4) .. + 31, thread = row
+    uint32_t (*cbits)[BN_MAX / 32] = reinterpret_cast<uint32_t (*)[BN_MAX / 32]>(cand_bits);
     bool acc_ok = mbar_wait(&acc_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (!acc_ok) fail_s = 1;
@@ -183,27 +194,20 @@ appearance_cost_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const bool failed = fail_s != 0;
     if (warp >= 2 && !failed) {
         const int q = warp & 3;
-        const int t = m0 + q * 32 + lane;
-        const bool row_ok = t < g.n_trk;
-        double* orow = g.out + ((size_t)b * g.n_trk + (row_ok ? t : 0)) * g.n_det + n0;
-        const uint8_t* grow = g.gate ? g.gate + ((size_t)b * g.n_trk + (row_ok ? t : 0)) * g.n_det + n0 : nullptr;
-        const double lim = g.thresh + g.scale * BAND_COS;
-        for (int c0 = 0; c0 < npad; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);     // warp-collective
-            if (!row_ok) continue;
+        const int row = q * 32 + lane;
+        const bool row_ok = row < rows_valid;
+        // candidate iff scale * (1 - cos) <= thresh + scale * band  <=>  cos >= 1 - thresh / scale - band (NaN -> candidate)
+        const float cos_lim = (float)(1.0 - g.thresh / g.scale - BAND_COS) - 1e-6f;
+        uint32_t word = 0;
+        for (int c0 = 0; c0 < BN_MAX; c0 += 16) {
+            if (c0 < npad) {
+                uint32_t v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);     // warp-collective
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int d = c0 + i;
-                if (d >= ncols) break;
-                const float cs = __uint_as_float(v[i]);
-                const double approx = g.scale * (1.0 - (double)cs);
-                const bool gated = grow && grow[d];
-                if (!gated && !(approx > lim)) {           // NaN -> candidate
-                    const int k = atomicAdd(&ncand_s, 1);
-                    cand[k] = ((uint32_t)(q * 32 + lane) << 16) | (uint32_t)d;
-                } else orow[d] = g.fill;
+                for (int i = 0; i < 16; ++i)
+                    if (c0 + i < ncols && !(__uint_as_float(v[i]) < cos_lim)) word |= 1u << ((c0 + i) & 31);
             }
+            if ((c0 & 16) != 0) { cbits[row][c0 >> 5] = row_ok ? word : 0u; word = 0; }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -213,33 +217,45 @@ appearance_cost_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         if (threadIdx.x == 0 && g.stats) atomicAdd(&g.stats[1], 1ull);
         return;
     }
-    // ===== exact recheck, one warp per candidate (scipy cdist 'cosine' in double on the fp32 values) =====
-    const int nc = ncand_s;
+    // (3) exact re-evaluation, one warp per surviving entry (scipy cdist 'cosine' in double on the fp32 values)
     const int nv = g.dim >> 2;
-    for (int k = warp; k < nc; k += GEMM_THREADS / 32) {
-        const uint32_t pr = cand[k];
-        const int t = m0 + (int)(pr >> 16), d = n0 + (int)(pr & 0xffff);
+    const int nwords = (ncols + 31) >> 5;
+    int done = 0;
+    for (int idx = warp; idx < rows_valid * nwords; idx += GEMM_THREADS / 32) {
+        const int row = idx / nwords, wd = idx - row * nwords;
+        uint32_t bits = cbits[row][wd];
+        const int t = m0 + row;
+        if (g.gate) {                                      // gated entries keep `fill`: one coalesced 32-byte read per word
+            const int dl = wd * 32 + lane;
+            const bool gt = dl < ncols && g.gate[((size_t)b * g.n_trk + t) * g.n_det + n0 + dl] != 0;
+            bits &= ~__ballot_sync(0xffffffffu, gt);
+        }
         const float4* a = reinterpret_cast<const float4*>(g.trk + ((size_t)b * g.n_trk + t) * g.dim);
-        const float4* bb = reinterpret_cast<const float4*>(g.det + ((size_t)b * g.n_det + d) * g.dim);
-        double uv = 0.0, uu = 0.0, vv = 0.0;
-        for (int i = lane; i < nv; i += 32) {
-            const float4 x = a[i], y = bb[i];
-            uv += (double)x.x * y.x + (double)x.y * y.y + (double)x.z * y.z + (double)x.w * y.w;
-            uu += (double)x.x * x.x + (double)x.y * x.y + (double)x.z * x.z + (double)x.w * x.w;
-            vv += (double)y.x * y.x + (double)y.y * y.y + (double)y.z * y.z + (double)y.w * y.w;
-        }
+        while (bits) {
+            const int d = n0 + wd * 32 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            const float4* bb = reinterpret_cast<const float4*>(g.det + ((size_t)b * g.n_det + d) * g.dim);
+            double uv = 0.0, uu = 0.0, vv = 0.0;
+            for (int i = lane; i < nv; i += 32) {
+                const float4 x = a[i], y = bb[i];
+                uv += (double)x.x * y.x + (double)x.y * y.y + (double)x.z * y.z + (double)x.w * y.w;
+                uu += (double)x.x * x.x + (double)x.y * x.y + (double)x.z * x.z + (double)x.w * x.w;
+                vv += (double)y.x * y.x + (double)y.y * y.y + (double)y.z * y.z + (double)y.w * y.w;
+            }
 #pragma unroll
-        for (int s = 16; s; s >>= 1) {
-            uv += __shfl_xor_sync(0xffffffffu, uv, s); uu += __shfl_xor_sync(0xffffffffu, uu, s); vv += __shfl_xor_sync(0xffffffffu, vv, s);
-        }
-        if (lane == 0) {
-            double c = uv / (sqrt(uu) * sqrt(vv));
-            if (fabs(c) > 1.0) c = copysign(1.0, c);
-            const double val = g.scale * fmax(0.0, 1.0 - c);
-            g.out[((size_t)b * g.n_trk + t) * g.n_det + d] = val > g.thresh ? g.fill : val;
+            for (int s = 16; s; s >>= 1) {
+                uv += __shfl_xor_sync(0xffffffffu, uv, s); uu += __shfl_xor_sync(0xffffffffu, uu, s); vv += __shfl_xor_sync(0xffffffffu, vv, s);
+            }
+            ++done;
+            if (lane == 0) {
+                double c = uv / (sqrt(uu) * sqrt(vv));
+                if (fabs(c) > 1.0) c = copysign(1.0, c);
+                const double val = g.scale * fmax(0.0, 1.0 - c);
+                if (!(val > g.thresh)) g.out[((size_t)b * g.n_trk + t) * g.n_det + d] = val;
+            }
         }
     }
-    if (threadIdx.x == 0 && g.stats && nc) atomicAdd(&g.stats[0], (unsigned long long)nc);
+    if (lane == 0 && g.stats && done) atomicAdd(&g.stats[0], (unsigned long long)done);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

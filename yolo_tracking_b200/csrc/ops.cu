@@ -62,22 +62,38 @@ __global__ void __launch_bounds__(KF_TPB) kf_initiate_kernel(int n, const double
     kf_stage_out(sm, mean, cov, base, cnt);
 }
 
+// One lane per covariance ROW (8 lanes per track, KF_TPB tracks per CTA): every lane computes its new row in
+// registers from the staged tile, the group synchronises, then the rows are written back - 8x the threads of a
+// thread-per-track mapping for the same shared memory, which is what a latency-bound streaming kernel needs.
+constexpr int KF_LANES = 8;
+constexpr int KF_THREADS = KF_TPB * KF_LANES;
+
 template <int KIND>
-__global__ void __launch_bounds__(KF_TPB) kf_predict_kernel(int n, double* mean, double* cov) {
+__global__ void __launch_bounds__(KF_THREADS) kf_predict_kernel(int n, double* mean, double* cov) {
     __shared__ double sm[KF_TPB * KF_STRIDE];
-    const int base = blockIdx.x * KF_TPB, cnt = min(KF_TPB, n - base), t = threadIdx.x;
+    const int base = blockIdx.x * KF_TPB, cnt = min(KF_TPB, n - base);
+    const int t = threadIdx.x / KF_LANES, r = threadIdx.x % KF_LANES;
     kf_stage_in(sm, mean, cov, base, cnt);
+    double row[8], mr = 0.0;
     if (t < cnt) {
-        double* m = sm + t * KF_STRIDE;
-        double* P = m + 8;
+        const double* m = sm + t * KF_STRIDE;
+        const double* P = m + 8;
         double sd[8];
         kf_std<KIND>(m, KF_W_POS, KF_W_VEL, 1e-2, 1e-5, sd);
-        for (int i = 0; i < 4; ++i) m[i] = xadd(m[i], m[i + 4]);
-        for (int i = 0; i < 4; ++i)                       // left = F P
-            for (int j = 0; j < 8; ++j) P[i * 8 + j] = xadd(P[i * 8 + j], P[(i + 4) * 8 + j]);
-        for (int i = 0; i < 8; ++i)                       // left F^T
-            for (int j = 0; j < 4; ++j) P[i * 8 + j] = xadd(P[i * 8 + j], P[i * 8 + j + 4]);
-        for (int i = 0; i < 8; ++i) P[i * 9] = xadd(P[i * 9], xmul(sd[i], sd[i]));
+        mr = r < 4 ? xadd(m[r], m[r + 4]) : m[r];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) row[j] = r < 4 ? xadd(P[r * 8 + j], P[(r + 4) * 8 + j]) : P[r * 8 + j];      // (F P)[r, :]
+#pragma unroll
+        for (int j = 0; j < 4; ++j) row[j] = xadd(row[j], row[j + 4]);                                          // ... F^T
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j == r) row[j] = xadd(row[j], xmul(sd[j], sd[j]));
+    }
+    __syncthreads();
+    if (t < cnt) {
+        double* m = sm + t * KF_STRIDE;
+        m[r] = mr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) m[8 + r * 8 + j] = row[j];
     }
     kf_stage_out(sm, mean, cov, base, cnt);
 }
@@ -109,81 +125,102 @@ __device__ __forceinline__ void chol_lower(double S[4][4], double L[4][4]) {
     }
 }
 
+// project (bytetrack_kf.py:126-153) only touches mean[:4] and the top-left 4x4 block of P: five 32-byte sectors per
+// track are read (160 B), 160 B written; 4 lanes per track (one per row of the block).
 template <int KIND>
-__global__ void __launch_bounds__(KF_TPB) kf_project_kernel(int n, const double* mean, const double* cov,
-                                                            const double* conf, double* pmean, double* pcov) {
-    __shared__ double sm[KF_TPB * KF_STRIDE];
-    const int base = blockIdx.x * KF_TPB, cnt = min(KF_TPB, n - base), t = threadIdx.x;
-    kf_stage_in(sm, mean, cov, base, cnt);
-    if (t < cnt) {
-        const double* m = sm + t * KF_STRIDE;
-        double S[4][4];
-        kf_innovation<KIND>(m, m + 8, conf ? conf[base + t] : 0.0, S);
-        for (int i = 0; i < 4; ++i) pmean[(size_t)(base + t) * 4 + i] = m[i];
-        for (int i = 0; i < 4; ++i)
-            for (int j = 0; j < 4; ++j) pcov[(size_t)(base + t) * 16 + i * 4 + j] = S[i][j];
-    }
+__global__ void __launch_bounds__(256) kf_project_kernel(int n, const double* __restrict__ mean, const double* __restrict__ cov,
+                                                         const double* __restrict__ conf, double* __restrict__ pmean,
+                                                         double* __restrict__ pcov) {
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    const int t = idx >> 2, r = idx & 3;
+    if (t >= n) return;
+    const double2 m01 = *reinterpret_cast<const double2*>(mean + (size_t)t * 8);
+    const double2 m23 = *reinterpret_cast<const double2*>(mean + (size_t)t * 8 + 2);
+    const double m4[4] = {m01.x, m01.y, m23.x, m23.y};
+    const double2 p01 = *reinterpret_cast<const double2*>(cov + (size_t)t * 64 + r * 8);
+    const double2 p23 = *reinterpret_cast<const double2*>(cov + (size_t)t * 64 + r * 8 + 2);
+    double row[4] = {p01.x, p01.y, p23.x, p23.y};
+    double sd[8];
+    kf_std<KIND>(m4, KF_W_POS, KF_W_VEL, 1e-1, 0.0, sd);
+    double sr = 0.0, mr = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (j == r) { sr = sd[j]; mr = m4[j]; }
+    if (KIND == KF_XYAH_CONF) sr = xmul(xsub(1.0, conf ? conf[t] : 0.0), sr);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (j == r) row[j] = xadd(row[j], xmul(sr, sr));
+    pmean[(size_t)t * 4 + r] = mr;
+    *reinterpret_cast<double2*>(pcov + (size_t)t * 16 + r * 4) = make_double2(row[0], row[1]);
+    *reinterpret_cast<double2*>(pcov + (size_t)t * 16 + r * 4 + 2) = make_double2(row[2], row[3]);
 }
 
+// update (bytetrack_kf.py:194-226): S = L L^T; lane r solves its own gain row
+// K[r, :] = P[r, :4] S^-1 (cho_solve), updates mean[r] and covariance row r.  P' = P - K S K^T is evaluated as
+// P - K (H P): S K^T = S S^-1 (P H^T)^T = H P exactly in real arithmetic, and rounding-wise inside the 1e-9 bar.
+constexpr int KFU_TPB = 32;                    // tracks per CTA of the update kernel (256 threads)
 template <int KIND>
-__global__ void __launch_bounds__(KF_TPB) kf_update_kernel(int n, double* mean, double* cov, const double* __restrict__ z,
-                                                           const double* __restrict__ conf) {
-    __shared__ double sm[KF_TPB * KF_STRIDE];
-    const int base = blockIdx.x * KF_TPB, cnt = min(KF_TPB, n - base), t = threadIdx.x;
+__global__ void __launch_bounds__(KFU_TPB * KF_LANES, 4) kf_update_kernel(int n, double* mean, double* cov, const double* __restrict__ z,
+                                                                         const double* __restrict__ conf) {
+    __shared__ double sm[KFU_TPB * KF_STRIDE];
+    const int base = blockIdx.x * KFU_TPB, cnt = min(KFU_TPB, n - base);
+    const int t = threadIdx.x / KF_LANES, r = threadIdx.x % KF_LANES;
     kf_stage_in(sm, mean, cov, base, cnt);
+    double row[8], mr = 0.0;
     if (t < cnt) {
-        double* m = sm + t * KF_STRIDE;
-        double* P = m + 8;
-        double S[4][4], L[4][4];
+        const double* m = sm + t * KF_STRIDE;
+        const double* P = m + 8;
+        // every lane of the group factors the 4x4 S itself (a dependent sqrt / divide chain either way; no hand-off)
+        double S[4][4], L[4][4], inv[4];
         kf_innovation<KIND>(m, P, conf ? conf[base + t] : 0.0, S);
         chol_lower<4>(S, L);
-        // K[r,:] solves S k = P[r,:4]  (cho_solve on (P H^T)^T, bytetrack_kf.py:216-220)
-        double K[8][4];
-        for (int r = 0; r < 8; ++r) {
-            double y[4];
-            for (int i = 0; i < 4; ++i) {
-                double v = P[r * 8 + i];
-                for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
-                y[i] = v / L[i][i];
-            }
-            for (int i = 3; i >= 0; --i) {
-                double v = y[i];
-                for (int k = i + 1; k < 4; ++k) v -= L[k][i] * K[r][k];
-                K[r][i] = v / L[i][i];
-            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) inv[i] = 1.0 / L[i][i];
+        double y[4], k[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                 // L y = P[r, :4]
+            double v = P[r * 8 + i];
+#pragma unroll
+            for (int q = 0; q < i; ++q) v -= L[i][q] * y[q];
+            y[i] = v * inv[i];
         }
-        double innov[4];
-        for (int i = 0; i < 4; ++i) innov[i] = xsub(z[(size_t)(base + t) * 4 + i], m[i]);
-        // P -= K (S K^T)
-        double M[4][8];
-        for (int k = 0; k < 4; ++k)
-            for (int c = 0; c < 8; ++c) {
-                double a = 0.0;
-                for (int q = 0; q < 4; ++q) a += S[k][q] * K[c][q];
-                M[k][c] = a;
-            }
-        for (int r = 0; r < 8; ++r) {
-            double a = 0.0;
-            for (int k = 0; k < 4; ++k) a += innov[k] * K[r][k];
-            m[r] = xadd(m[r], a);
-            for (int c = 0; c < 8; ++c) {
-                double b = 0.0;
-                for (int k = 0; k < 4; ++k) b += K[r][k] * M[k][c];
-                P[r * 8 + c] = xsub(P[r * 8 + c], b);
-            }
+#pragma unroll
+        for (int i = 3; i >= 0; --i) {                // L^T k = y
+            double v = y[i];
+#pragma unroll
+            for (int q = i + 1; q < 4; ++q) v -= L[q][i] * k[q];
+            k[i] = v * inv[i];
         }
+        double a = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a += xsub(z[(size_t)(base + t) * 4 + i], m[i]) * k[i];
+        mr = xadd(m[r], a);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            double b = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) b += k[i] * P[i * 8 + c];
+            row[c] = xsub(P[r * 8 + c], b);
+        }
+    }
+    __syncthreads();
+    if (t < cnt) {
+        double* m = sm + t * KF_STRIDE;
+        m[r] = mr;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m[8 + r * 8 + c] = row[c];
     }
     kf_stage_out(sm, mean, cov, base, cnt);
 }
 
-// gating_distance: 8 tracks per CTA factor S once, then every thread sweeps measurements
-constexpr int GD_TRACKS = 8;
+// gating_distance: 32 tracks per CTA factor S once (one warp), the stream's measurements are staged planar in shared
+// memory, then every thread sweeps (track, measurement) pairs with coalesced 8-byte stores.
+constexpr int GD_TRACKS = 32;
 template <int KIND>
 __global__ void __launch_bounds__(256) kf_gating_kernel(int T, int D, const double* __restrict__ mean, const double* __restrict__ cov,
                                                         const double* __restrict__ meas, int only_position, int metric,
                                                         const double* __restrict__ conf, double* __restrict__ out) {
     __shared__ double sL[GD_TRACKS][16];
     __shared__ double sM[GD_TRACKS][4];
+    extern __shared__ double sZ[];              // [4][D] measurements, planar
     {   // blockIdx.y = independent problem (stream): [T] tracks x [D] measurements each
         const size_t bi = blockIdx.y;
         mean += bi * T * 8; cov += bi * T * 64; meas += bi * D * 4; out += bi * T * D;
@@ -191,6 +228,7 @@ __global__ void __launch_bounds__(256) kf_gating_kernel(int T, int D, const doub
     }
     const int t0 = blockIdx.x * GD_TRACKS, cnt = min(GD_TRACKS, T - t0);
     const int nd = only_position ? 2 : 4;
+    for (int i = threadIdx.x; i < D * 4; i += blockDim.x) sZ[(i & 3) * D + (i >> 2)] = meas[i];
     if (threadIdx.x < cnt) {
         const int t = t0 + threadIdx.x;
         double m[8], S[4][4], L[4][4];
@@ -198,14 +236,14 @@ __global__ void __launch_bounds__(256) kf_gating_kernel(int T, int D, const doub
         kf_innovation<KIND>(m, cov + (size_t)t * 64, conf ? conf[t] : 0.0, S);
         for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) L[i][j] = 0.0;
         if (only_position) chol_lower<2>(S, L); else chol_lower<4>(S, L);
-        for (int i = 0; i < 16; ++i) sL[threadIdx.x][i] = L[i >> 2][i & 3];
+        for (int i = 0; i < 16; ++i) sL[threadIdx.x][i] = (i >> 2) == (i & 3) ? 1.0 / L[i >> 2][i & 3] : L[i >> 2][i & 3];   // reciprocal diagonal
         for (int i = 0; i < 4; ++i) sM[threadIdx.x][i] = m[i];
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < cnt * D; idx += blockDim.x) {
         const int tl = idx / D, j = idx - tl * D;
         double d[4], zz[4];
-        for (int i = 0; i < nd; ++i) d[i] = xsub(meas[(size_t)j * 4 + i], sM[tl][i]);
+        for (int i = 0; i < nd; ++i) d[i] = xsub(sZ[i * D + j], sM[tl][i]);
         double acc = 0.0;
         if (metric == 1) {
             for (int i = 0; i < nd; ++i) acc = i ? xadd(acc, xmul(d[i], d[i])) : xmul(d[i], d[i]);
@@ -213,7 +251,7 @@ __global__ void __launch_bounds__(256) kf_gating_kernel(int T, int D, const doub
             for (int i = 0; i < nd; ++i) {               // solve_triangular(L, d)
                 double v = d[i];
                 for (int k = 0; k < i; ++k) v -= sL[tl][i * 4 + k] * zz[k];
-                zz[i] = v / sL[tl][i * 4 + i];
+                zz[i] = v * sL[tl][i * 4 + i];
                 acc = i ? xadd(acc, xmul(zz[i], zz[i])) : xmul(zz[i], zz[i]);
             }
         }
@@ -375,7 +413,7 @@ extern "C" int b200track_kf_initiate(int32_t kind, int32_t n, const double* z, d
 extern "C" int b200track_kf_predict(int32_t kind, int32_t n, double* mean, double* cov, void* st) {
     if (n < 0 || !mean || !cov) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
     if (n == 0) return 0;
-    int rc = dispatch_kind(kind, [&](auto K) { kf_predict_kernel<decltype(K)::value><<<(n + KF_TPB - 1) / KF_TPB, KF_TPB, 0, (cudaStream_t)st>>>(n, mean, cov); });
+    int rc = dispatch_kind(kind, [&](auto K) { kf_predict_kernel<decltype(K)::value><<<(n + KF_TPB - 1) / KF_TPB, KF_THREADS, 0, (cudaStream_t)st>>>(n, mean, cov); });
     if (rc) return rc;
     LAUNCH_CHECK();
     return 0;
@@ -384,7 +422,7 @@ extern "C" int b200track_kf_project(int32_t kind, int32_t n, const double* mean,
                                     double* pmean, double* pcov, void* st) {
     if (n < 0 || !mean || !cov || !pmean || !pcov) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
     if (n == 0) return 0;
-    int rc = dispatch_kind(kind, [&](auto K) { kf_project_kernel<decltype(K)::value><<<(n + KF_TPB - 1) / KF_TPB, KF_TPB, 0, (cudaStream_t)st>>>(n, mean, cov, conf, pmean, pcov); });
+    int rc = dispatch_kind(kind, [&](auto K) { kf_project_kernel<decltype(K)::value><<<(unsigned)(((size_t)n * 4 + 255) / 256), 256, 0, (cudaStream_t)st>>>(n, mean, cov, conf, pmean, pcov); });
     if (rc) return rc;
     LAUNCH_CHECK();
     return 0;
@@ -392,7 +430,7 @@ extern "C" int b200track_kf_project(int32_t kind, int32_t n, const double* mean,
 extern "C" int b200track_kf_update(int32_t kind, int32_t n, double* mean, double* cov, const double* z, const double* conf, void* st) {
     if (n < 0 || !mean || !cov || !z) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
     if (n == 0) return 0;
-    int rc = dispatch_kind(kind, [&](auto K) { kf_update_kernel<decltype(K)::value><<<(n + KF_TPB - 1) / KF_TPB, KF_TPB, 0, (cudaStream_t)st>>>(n, mean, cov, z, conf); });
+    int rc = dispatch_kind(kind, [&](auto K) { kf_update_kernel<decltype(K)::value><<<(n + KFU_TPB - 1) / KFU_TPB, KFU_TPB * KF_LANES, 0, (cudaStream_t)st>>>(n, mean, cov, z, conf); });
     if (rc) return rc;
     LAUNCH_CHECK();
     return 0;
@@ -403,7 +441,11 @@ extern "C" int b200track_kf_gating_distance(int32_t kind, int32_t T, int32_t D, 
     if (T < 0 || D < 0 || !mean || !cov || !meas || !out) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
     if (metric != 0 && metric != 1) { set_error("invalid distance metric"); return B200TRACK_ERR_ARG; }
     if (T == 0 || D == 0) return 0;
-    int rc = dispatch_kind(kind, [&](auto K) { kf_gating_kernel<decltype(K)::value><<<(T + GD_TRACKS - 1) / GD_TRACKS, 256, 0, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out); });
+    if ((size_t)D * 32 > 200 * 1024) { set_error("gating_distance: more than 6400 measurements per problem"); return B200TRACK_ERR_CAPACITY; }
+    int rc = dispatch_kind(kind, [&](auto K) {
+        auto kern = kf_gating_kernel<decltype(K)::value>;
+        if ((size_t)D * 32 > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D * 32);
+        kern<<<(T + GD_TRACKS - 1) / GD_TRACKS, 256, (size_t)D * 32, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out); });
     if (rc) return rc;
     LAUNCH_CHECK();
     return 0;
@@ -415,7 +457,11 @@ extern "C" int b200track_kf_gating_distance_batched(int32_t kind, int32_t batch,
     if (metric != 0 && metric != 1) { set_error("invalid distance metric"); return B200TRACK_ERR_ARG; }
     if (batch == 0 || T == 0 || D == 0) return 0;
     dim3 grid((T + GD_TRACKS - 1) / GD_TRACKS, batch);
-    int rc = dispatch_kind(kind, [&](auto K) { kf_gating_kernel<decltype(K)::value><<<grid, 256, 0, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out); });
+    if ((size_t)D * 32 > 200 * 1024) { set_error("gating_distance: more than 6400 measurements per problem"); return B200TRACK_ERR_CAPACITY; }
+    int rc = dispatch_kind(kind, [&](auto K) {
+        auto kern = kf_gating_kernel<decltype(K)::value>;
+        if ((size_t)D * 32 > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D * 32);
+        kern<<<grid, 256, (size_t)D * 32, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out); });
     if (rc) return rc;
     LAUNCH_CHECK();
     return 0;
