@@ -157,6 +157,13 @@ int b200track_kf_gating_distance(int32_t kf_kind, int32_t n_tracks, int32_t n_me
 int b200track_kf_gating_distance_batched(int32_t kf_kind, int32_t batch, int32_t n_tracks, int32_t n_meas, const double* d_mean,
                                          const double* d_cov, const double* d_meas, int32_t only_position,
                                          int32_t metric, const double* d_conf, double* d_out, void* stream);
+/* b200track_gate_cost <- gate_cost_matrix (matching.py:170-181; fuse = 0) and fuse_motion (:184-196; fuse = 1) for `batch`
+ * streams: cost[b, t, d] = inf where the squared Mahalanobis distance exceeds chi2inv95[4] (only_position: [2]), then
+ * (fuse) cost = lambda * cost + (1 - lambda) * distance.  In place on d_cost [batch, T, D]; the distance matrix is
+ * never materialised.  d_meas are the detections' xyah (to_xyah()). */
+int b200track_gate_cost(int32_t kf_kind, int32_t batch, int32_t n_tracks, int32_t n_meas, const double* d_mean,
+                        const double* d_cov, const double* d_meas, int32_t only_position, int32_t fuse, double lambda,
+                        const double* d_conf, double* d_cost, void* stream);
 /* b200track_box_similarity <- iou_batch / giou_batch / diou_batch / ciou_batch / centroid_batch
  *     boxmot/utils/iou.py:6-188 ; a[n,4] x b[m,4] -> out[n,m] (img_w, img_h only for centroid)
  * b200track_iou_distance   <- matching.py:94-119 (1 - iou), optional fuse_score :213-221 when

@@ -215,3 +215,38 @@ def test_gating_distance_batched_equals_per_stream_calls():
         assert np.array_equal(got[b], one)
         for t in range(T):
             assert_close(got[b, t], kalman.gating_distance("xyah", mean[b * T + t], cov[b * T + t], meas[b]), what="maha")
+
+
+@pytest.mark.parametrize("only_position", [False, True])
+def test_gate_cost_matrix_and_fuse_motion(only_position):
+    """matching.py:170-196 (gate_cost_matrix, fuse_motion) through the fused kernel vs the oracle's gating_distance."""
+    from oracle import kalman
+    from yolo_tracking_b200.motion.kalman_filters import KalmanFilterXYAH, chi2inv95
+    from yolo_tracking_b200.utils import matching
+    rng = np.random.default_rng(9)
+    T, D = 37, 23
+    z = np.stack([rng.uniform(100, 1800, T), rng.uniform(100, 1000, T), rng.uniform(0.3, 0.8, T), rng.uniform(60, 220, T)], axis=1)
+    mean, cov = kalman.initiate("xyah", z)
+    mean, cov = kalman.predict("xyah", mean, cov)
+    meas = mean[rng.integers(0, T, D), :4] + rng.normal(0, 4, (D, 4)) * np.array([1, 1, 0.005, 1])
+    cost = rng.random((T, D))
+    gd = np.stack([kalman.gating_distance("xyah", mean[t], cov[t], meas, only_position) for t in range(T)])
+    thr = chi2inv95[2 if only_position else 4]
+    ref_gate = np.where(gd > thr, np.inf, cost)
+    ref_fuse = 0.98 * ref_gate + (1 - 0.98) * gd
+
+    class Trk:
+        def __init__(self, m, c): self.mean, self.covariance = m, c
+
+    class Det:
+        def __init__(self, v): self.v = v
+        def to_xyah(self): return self.v
+    kf = KalmanFilterXYAH()
+    trks, dets = [Trk(mean[t], cov[t]) for t in range(T)], [Det(m) for m in meas]
+    got = matching.gate_cost_matrix(kf, cost.copy(), trks, dets, only_position)
+    assert np.array_equal(np.isinf(got), np.isinf(ref_gate)) and 0 < np.isinf(ref_gate).sum() < T * D
+    assert np.array_equal(got[np.isfinite(got)], ref_gate[np.isfinite(ref_gate)])
+    got = matching.fuse_motion(kf, cost.copy(), (mean, cov), meas, only_position)
+    assert np.array_equal(np.isinf(got), np.isinf(ref_fuse))
+    assert_close(got[np.isfinite(got)], ref_fuse[np.isfinite(ref_fuse)], what="fuse_motion")
+    assert matching.gate_cost_matrix(kf, np.zeros((0, 3)), [], dets[:3]).shape == (0, 3)

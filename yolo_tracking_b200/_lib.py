@@ -7,7 +7,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200track.so")
+LIB_PATH = os.environ.get("B200TRACK_LIB") or os.path.join(_HERE, "lib", "libb200track.so")   # override: A/B builds
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200track.h")
 
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
@@ -64,6 +64,7 @@ SIGNATURES = {
     "b200track_kf_update": (C.c_int, [_I, _I, _P, _P, _P, _P, _P]),
     "b200track_kf_gating_distance": (C.c_int, [_I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),
     "b200track_kf_gating_distance_batched": (C.c_int, [_I, _I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "b200track_gate_cost": (C.c_int, [_I, _I, _I, _I, _P, _P, _P, _I, _I, _D, _P, _P, _P]),
     "b200track_box_similarity": (C.c_int, [_I, _I, _I, _P, _P, _D, _D, _P, _P]),
     "b200track_iou_distance": (C.c_int, [_I, _I, _P, _P, _P, _P, _P]),
     "b200track_embedding_distance": (C.c_int, [_I, _I, _I, _P, _P, _P, _P]),

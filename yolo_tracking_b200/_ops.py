@@ -91,6 +91,25 @@ def kf_gating_distance(kind, mean, cov, meas, only_position=False, metric="maha"
     return out.cpu().numpy()
 
 
+def gate_cost(kind, cost, mean, cov, meas, only_position=False, fuse=False, lambda_=0.98, conf=None):
+    """cost [T, D] or [B, T, D] gated (and optionally fused) with the squared Mahalanobis distance, matching.py:170-196."""
+    lib = _lib.load()
+    torch = _torch()
+    cost = np.asarray(cost, dtype=np.float64)
+    single = cost.ndim == 2
+    c3 = cost[None] if single else cost
+    B, T, D = c3.shape
+    m = _dev(np.asarray(mean).reshape(B, T, 8), np.float64)
+    c = _dev(np.asarray(cov).reshape(B, T, 8, 8), np.float64)
+    z = _dev(np.asarray(meas).reshape(B, D, 4), np.float64)
+    cf = _dev(np.broadcast_to(np.asarray(conf, dtype=np.float64), (B, T)), np.float64) if conf is not None else None
+    dc = _dev(c3, np.float64).clone()
+    _sync_check(lib.b200track_gate_cost(kind, B, T, D, _p(m), _p(c), _p(z), int(bool(only_position)), int(bool(fuse)), float(lambda_),
+                                        _p(cf), _p(dc), None))
+    out = dc.cpu().numpy()
+    return out[0] if single else out
+
+
 def box_similarity(name, a, b, w=0.0, h=0.0):
     if name not in _lib.SIM:
         raise ValueError("Invalid function specified. Must be either '(g,d,c, )iou_batch' or 'centroid_batch'.")

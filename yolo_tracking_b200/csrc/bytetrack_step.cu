@@ -48,7 +48,13 @@ constexpr int DF_HIGH = 1, DF_LOW = 2, DF_USED = 4;
 
 constexpr int CAT_NONE = 0, CAT_KEEP = 1, CAT_REFOUND = 2, CAT_LOST_OLD = 3, CAT_LOST_NEW = 4;
 
-constexpr int NCELL = 64;         // cells per axis of the candidate masks
+#ifndef B200_NCX
+#define B200_NCX 64
+#endif
+#ifndef B200_NCY
+#define B200_NCY 64
+#endif
+constexpr int NCX = B200_NCX, NCY = B200_NCY;   // cells per axis of the candidate masks
 
 // row types of one association pass: which detection set / limit / cost a row uses
 constexpr int RT_NONE = 0, RT_A = 1, RT_B = 2;
@@ -85,7 +91,7 @@ struct alignas(16) StepSmem {
     int parent[TMAX + DMAX], head[TMAX], coldeg[DMAX], ncomplex[4];
     uint32_t adj[DW][TMAX];
     uint32_t colbitsA[DWP], colbitsB[DWP];
-    uint32_t xmask[NCELL][DWP], ymask[NCELL][DWP];
+    uint32_t xmask[NCX][DWP], ymask[NCY][DWP];
     float fext[32][4];
     short rnext[TMAX], xr[TMAX], match[TMAX], lostlist[TMAX];
     short yc[DMAX], pred[DMAX], nextc[DMAX], mark[DMAX], scn[DMAX];
@@ -157,10 +163,10 @@ struct PassLimit {
 struct CellMap {
     float x0, y0, sx, sy;
     __device__ __forceinline__ int cx(double x) const {
-        return min(max((int)(((float)x - x0) * sx), 0), NCELL - 1);      // monotone in x
+        return min(max((int)(((float)x - x0) * sx), 0), NCX - 1);      // monotone in x
     }
     __device__ __forceinline__ int cy(double y) const {
-        return min(max((int)(((float)y - y0) * sy), 0), NCELL - 1);
+        return min(max((int)(((float)y - y0) * sy), 0), NCY - 1);
     }
 };
 
@@ -428,7 +434,8 @@ bytetrack_step_kernel(const StepParams p) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + B200_TI_LEN * TMAX + t));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + B200_TI_DET * TMAX + t));
         }
-        for (int i = tid; i < NCELL * DWP; i += NT) { (&sm.xmask[0][0])[i] = 0u; (&sm.ymask[0][0])[i] = 0u; }
+        for (int i = tid; i < NCX * DWP; i += NT) (&sm.xmask[0][0])[i] = 0u;
+        for (int i = tid; i < NCY * DWP; i += NT) (&sm.ymask[0][0])[i] = 0u;
         for (int i = tid; i < TMAX + DMAX; i += NT) sm.drop[i] = 0;
         if constexpr (BOT) sm.bot.rowused[t] = 0;
     }
@@ -506,8 +513,8 @@ bytetrack_step_kernel(const StepParams p) {
             x1 = fmaxf(x1, sm.fext[k][2]); y1 = fmaxf(y1, sm.fext[k][3]);
         }
         cm.x0 = x0; cm.y0 = y0;
-        cm.sx = (x1 > x0) ? (float)NCELL / (x1 - x0) : 0.f;
-        cm.sy = (y1 > y0) ? (float)NCELL / (y1 - y0) : 0.f;
+        cm.sx = (x1 > x0) ? (float)NCX / (x1 - x0) : 0.f;
+        cm.sy = (y1 > y0) ? (float)NCY / (y1 - y0) : 0.f;
     }
     if (mydfl) {
         const int j = tid;

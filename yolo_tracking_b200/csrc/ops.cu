@@ -217,13 +217,17 @@ constexpr int GD_TRACKS = 32;
 template <int KIND>
 __global__ void __launch_bounds__(256) kf_gating_kernel(int T, int D, const double* __restrict__ mean, const double* __restrict__ cov,
                                                         const double* __restrict__ meas, int only_position, int metric,
-                                                        const double* __restrict__ conf, double* __restrict__ out) {
+                                                        const double* __restrict__ conf, double* __restrict__ out,
+                                                        double* __restrict__ cost = nullptr, int fuse = 0, double gate_thr = 0.0,
+                                                        double lambda = 0.0) {
     __shared__ double sL[GD_TRACKS][16];
     __shared__ double sM[GD_TRACKS][4];
     extern __shared__ double sZ[];              // [4][D] measurements, planar
     {   // blockIdx.y = independent problem (stream): [T] tracks x [D] measurements each
         const size_t bi = blockIdx.y;
-        mean += bi * T * 8; cov += bi * T * 64; meas += bi * D * 4; out += bi * T * D;
+        mean += bi * T * 8; cov += bi * T * 64; meas += bi * D * 4;
+        if (out) out += bi * T * D;
+        if (cost) cost += bi * T * D;
         if (conf) conf += bi * T;
     }
     const int t0 = blockIdx.x * GD_TRACKS, cnt = min(GD_TRACKS, T - t0);
@@ -255,7 +259,14 @@ __global__ void __launch_bounds__(256) kf_gating_kernel(int T, int D, const doub
                 acc = i ? xadd(acc, xmul(zz[i], zz[i])) : xmul(zz[i], zz[i]);
             }
         }
-        out[(size_t)(t0 + tl) * D + j] = acc;
+        if (cost) {
+            // gate_cost_matrix / fuse_motion (matching.py:170-196) without the T x D distance matrix ever reaching HBM
+            const size_t o = (size_t)(t0 + tl) * D + j;
+            double c = cost[o];
+            if (acc > gate_thr) c = __longlong_as_double(0x7ff0000000000000LL);
+            if (fuse) c = xadd(xmul(lambda, c), xmul(xsub(1.0, lambda), acc));
+            cost[o] = c;
+        } else out[(size_t)(t0 + tl) * D + j] = acc;
     }
 }
 
@@ -445,7 +456,23 @@ extern "C" int b200track_kf_gating_distance(int32_t kind, int32_t T, int32_t D, 
     int rc = dispatch_kind(kind, [&](auto K) {
         auto kern = kf_gating_kernel<decltype(K)::value>;
         if ((size_t)D * 32 > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D * 32);
-        kern<<<(T + GD_TRACKS - 1) / GD_TRACKS, 256, (size_t)D * 32, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out); });
+        kern<<<(T + GD_TRACKS - 1) / GD_TRACKS, 256, (size_t)D * 32, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out, nullptr, 0, 0.0, 0.0); });
+    if (rc) return rc;
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_gate_cost(int32_t kind, int32_t batch, int32_t T, int32_t D, const double* mean, const double* cov,
+                                   const double* meas, int32_t only_position, int32_t fuse, double lambda, const double* conf,
+                                   double* cost, void* st) {
+    if (batch < 0 || batch > 65535 || T < 0 || D < 0 || !mean || !cov || !meas || !cost) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (batch == 0 || T == 0 || D == 0) return 0;
+    if ((size_t)D * 32 > 200 * 1024) { set_error("gate_cost: more than 6400 measurements per problem"); return B200TRACK_ERR_CAPACITY; }
+    const double thr = only_position ? 5.9915 : 9.4877;            // chi2inv95[2], chi2inv95[4] (matching.py:15-25)
+    dim3 grid((T + GD_TRACKS - 1) / GD_TRACKS, batch);
+    int rc = dispatch_kind(kind, [&](auto K) {
+        auto kern = kf_gating_kernel<decltype(K)::value>;
+        if ((size_t)D * 32 > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D * 32);
+        kern<<<grid, 256, (size_t)D * 32, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, 0, conf, nullptr, cost, fuse ? 1 : 0, thr, lambda); });
     if (rc) return rc;
     LAUNCH_CHECK();
     return 0;
@@ -461,7 +488,7 @@ extern "C" int b200track_kf_gating_distance_batched(int32_t kind, int32_t batch,
     int rc = dispatch_kind(kind, [&](auto K) {
         auto kern = kf_gating_kernel<decltype(K)::value>;
         if ((size_t)D * 32 > 40 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, D * 32);
-        kern<<<grid, 256, (size_t)D * 32, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out); });
+        kern<<<grid, 256, (size_t)D * 32, (cudaStream_t)st>>>(T, D, mean, cov, meas, only_position, metric, conf, out, nullptr, 0, 0.0, 0.0); });
     if (rc) return rc;
     LAUNCH_CHECK();
     return 0;

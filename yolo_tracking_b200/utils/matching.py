@@ -43,3 +43,34 @@ def embedding_distance(track_features, det_features, metric="cosine"):
     if len(a) == 0 or len(b) == 0:
         return np.zeros((len(a), len(b)), dtype=np.float32)
     return _ops.embedding_distance(a, b)
+
+
+def _track_arrays(tracks):
+    if isinstance(tracks, tuple):                      # (means [T, 8], covariances [T, 8, 8])
+        return np.asarray(tracks[0], dtype=np.float64), np.asarray(tracks[1], dtype=np.float64)
+    return (np.asarray([t.mean for t in tracks], dtype=np.float64), np.asarray([t.covariance for t in tracks], dtype=np.float64))
+
+
+def _det_xyah(detections):
+    if isinstance(detections, np.ndarray):
+        return np.asarray(detections, dtype=np.float64).reshape(-1, 4)
+    return np.asarray([d.to_xyah() for d in detections], dtype=np.float64).reshape(-1, 4)
+
+
+def gate_cost_matrix(kf, cost_matrix, tracks, detections, only_position=False):
+    """matching.py:170-181.  `kf` is one of yolo_tracking_b200.motion.kalman_filters; tracks are objects with
+    .mean / .covariance (or a (means, covariances) tuple), detections objects with .to_xyah() (or an [D, 4] array)."""
+    cost_matrix = np.asarray(cost_matrix, dtype=np.float64)
+    if cost_matrix.size == 0:
+        return cost_matrix
+    mean, cov = _track_arrays(tracks)
+    return _ops.gate_cost(kf._kind, cost_matrix, mean, cov, _det_xyah(detections), only_position, fuse=False)
+
+
+def fuse_motion(kf, cost_matrix, tracks, detections, only_position=False, lambda_=0.98):
+    """matching.py:184-196."""
+    cost_matrix = np.asarray(cost_matrix, dtype=np.float64)
+    if cost_matrix.size == 0:
+        return cost_matrix
+    mean, cov = _track_arrays(tracks)
+    return _ops.gate_cost(kf._kind, cost_matrix, mean, cov, _det_xyah(detections), only_position, fuse=True, lambda_=lambda_)
