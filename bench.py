@@ -31,7 +31,7 @@ if ROOT not in sys.path:
 # b_slot: algorithmic HBM bytes of one track slot, in + out; b_feat: embedding bytes per
 # track-update (smoothed row read + detection row read + smoothed row written).
 WORKLOADS = {
-    "bytetrack": dict(kind="bytetrack", config=5, objects=200, streams=4096, max_dets=224, max_tracks=256, emb=0,
+    "bytetrack": dict(kind="bytetrack", config=5, objects=200, streams=4096, max_dets=224, max_tracks=224, emb=0,
                       params=dict(track_thresh=0.5, match_thresh=0.8, track_buffer=30, frame_rate=30),      # bytetrack.yaml
                       b_slot=2 * 200, b_feat=0, kernel="bytetrack_step_kernel", img_hw=(0, 0),
                       label="config5: ByteTrack multi-stream (bytetrack.yaml: track_thresh 0.5, match_thresh 0.8, "
@@ -42,7 +42,7 @@ WORKLOADS = {
                    b_slot=2 * (37 * 8 + 10 * 4), b_feat=0, kernel="ocsort_step_kernel", img_hw=(2160, 3840),
                    label="config2: OC-SORT (ocsort.yaml: giou, det_thresh 0, min_hits 1, max_age 30, delta_t 3, inertia 0.2), "
                          "100 objects/stream with occlusion runs, sharded by stream"),
-    "botsort": dict(kind="botsort", config=3, objects=100, streams=256, max_dets=128, max_tracks=256, emb=512,
+    "botsort": dict(kind="botsort", config=3, objects=100, streams=256, max_dets=128, max_tracks=224, emb=512,
                     params=dict(track_high_thresh=0.33824964456239337, track_low_thresh=0.1,
                                 new_track_thresh=0.21144301345190655, track_buffer=60, match_thresh=0.22734550911325851,
                                 proximity_thresh=0.5945380911899254, appearance_thresh=0.4818211117541298, frame_rate=30),

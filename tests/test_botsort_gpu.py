@@ -76,6 +76,7 @@ def test_botsort_replays_reference_golden(name):
 @pytest.mark.parametrize("n_streams,n_objects,n_frames,emb,kw,params", [
     (6, 40, 60, 128, {}, {}),
     (3, 100, 30, 512, {}, {}),
+    (2, 100, 30, 256, dict(cap=224), {}),
     (4, 16, 120, 128, dict(miss_prob=0.3, fp_rate=3.0), dict(track_high_thresh=0.5, new_track_thresh=0.6, match_thresh=0.8,
                                                              proximity_thresh=0.5, appearance_thresh=0.25, track_buffer=20)),
     (4, 30, 50, 128, dict(miss_prob=0.1), dict(with_reid=False)),
@@ -89,7 +90,8 @@ def test_botsort_multistream_vs_oracle(n_streams, n_objects, n_frames, emb, kw, 
     from oracle.botsort import BoTSORTOracle
     from yolo_tracking_b200.batch import BatchedTracker
     from yolo_tracking_b200.synth import make_batch
-    cap = 256 if n_objects > 60 else 128
+    kw = dict(kw)
+    cap = kw.pop("cap", 256 if n_objects > 60 else 128)
     cfg = dict(BOTSORT_YAML)
     cfg.update(params)
     with_reid = cfg.get("with_reid", True)

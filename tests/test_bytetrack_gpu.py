@@ -85,12 +85,15 @@ def test_bytetrack_known_answer_and_empty():
     (16, 40, 60, {}),
     (8, 20, 120, dict(miss_prob=0.3, fp_rate=3.0)),
     (4, 200, 30, {}),
+    (6, 200, 45, dict(cap=224)),            # the (224, 224) kernel variant bench.py runs (4 CTAs per SM)
+    (3, 150, 40, dict(cap=224, miss_prob=0.2, fp_rate=4.0)),
 ])
 def test_bytetrack_multistream_vs_oracle(n_streams, n_objects, n_frames, kw):
     from oracle.bytetrack import ByteTrackOracle
     from yolo_tracking_b200.batch import BatchedTracker
     from yolo_tracking_b200.synth import make_batch
-    dmax = 256 if n_objects > 100 else 64
+    kw = dict(kw)
+    dmax = kw.pop("cap", 256 if n_objects > 100 else 64)
     dets, nd, _ = make_batch(5, n_streams, n_objects, n_frames, dmax=dmax, **kw)
     trk = BatchedTracker("bytetrack", n_streams, max_tracks=dmax, max_dets=dmax, track_thresh=0.5, match_thresh=0.8,
                          track_buffer=30, frame_rate=30)

@@ -82,6 +82,7 @@ def test_ocsort_reference_known_answers():
     (8, 40, 80, dict(occlusion=True), {}),
     (4, 16, 120, dict(miss_prob=0.3, fp_rate=3.0), dict(min_hits=3, max_age=6)),
     (2, 100, 40, dict(occlusion=True), {}),
+    (2, 100, 40, dict(occlusion=True, cap=224), {}),
     (4, 30, 60, dict(occlusion=True), dict(asso_func="iou", det_thresh=0.3)),
     (2, 30, 50, dict(occlusion=True), dict(asso_func="diou")),
     (4, 40, 80, dict(occlusion=True, miss_prob=0.1), dict(use_byte=True, det_thresh=0.5, min_hits=2)),
@@ -91,7 +92,8 @@ def test_ocsort_multistream_vs_oracle(n_streams, n_objects, n_frames, kw, params
     from oracle.ocsort import OCSortOracle
     from yolo_tracking_b200.batch import BatchedTracker
     from yolo_tracking_b200.synth import make_batch
-    cap = 256 if n_objects > 60 else 128
+    kw = dict(kw)
+    cap = kw.pop("cap", 256 if n_objects > 60 else 128)
     cfg = dict(det_thresh=0, max_age=30, min_hits=1, asso_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2)
     cfg.update(params)
     dets, nd, _ = make_batch(2, n_streams, n_objects, n_frames, dmax=cap, first_stream=50, **kw)

@@ -49,10 +49,10 @@ constexpr int DF_HIGH = 1, DF_LOW = 2, DF_USED = 4;
 constexpr int CAT_NONE = 0, CAT_KEEP = 1, CAT_REFOUND = 2, CAT_LOST_OLD = 3, CAT_LOST_NEW = 4;
 
 #ifndef B200_NCX
-#define B200_NCX 64
+#define B200_NCX 48
 #endif
 #ifndef B200_NCY
-#define B200_NCY 64
+#define B200_NCY 24
 #endif
 constexpr int NCX = B200_NCX, NCY = B200_NCY;   // cells per axis of the candidate masks
 
@@ -81,10 +81,9 @@ struct alignas(16) StepSmem {
     static constexpr int TCAP = TMAX;
     static constexpr int DW = DMAX / 32;
     static constexpr int DWP = (DW + 3) / 4 * 4;      // mask rows padded to 16-byte multiples
-    double mean[8][TMAX];
+    double mean[4][TMAX];                             // position half of the mean; velocities stay in HBM / registers
     double dbox[4][DMAX];                             // raw x1, y1, x2, y2
     double dconf[DMAX];
-    double dcls[DMAX];
     double u[TMAX], v[DMAX], dist[DMAX];
     unsigned long long scratch[40];
     int frame_t[TMAX], start_t[TMAX];
@@ -362,7 +361,7 @@ __device__ __forceinline__ double cls_vote(double* h, double cls, double score, 
 }
 
 template <int NT, int KIND, int TMAX, int DMAX, bool BOT>
-__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : (NT == 256 ? 3 : (NT == 128 ? 6 : 8))))
+__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : (NT == 256 ? 3 : (NT == 224 ? (BOT ? 3 : 4) : (NT == 128 ? 6 : 8)))))
 bytetrack_step_kernel(const StepParams p) {
     static_assert(NT == TMAX && DMAX <= NT, "one thread per track slot; detections fit one pass");
     static_assert(!BOT || KIND == KF_XYWH, "BoT-SORT runs on the XYWH filter");
@@ -391,6 +390,8 @@ bytetrack_step_kernel(const StepParams p) {
 
     // ---- HBM -> shared memory: detections [nd, 6] (planar), means, lifecycle ints ----------
     int fl = 0, frame_t = 0;
+    double vel[4] = {0.0, 0.0, 0.0, 0.0};
+    const double* dets_g = p.dets + (size_t)s * p.max_dets * 6;
     {
         // every global load of this phase is issued before the first value is used (one memory latency, not six)
         const double* g = p.dets + (size_t)s * p.max_dets * 6;
@@ -415,12 +416,14 @@ bytetrack_step_kernel(const StepParams p) {
                 const int j = i / 6, c = i - 6 * j;
                 if (c < 4) sm.dbox[c][j] = dv[k];
                 else if (c == 4) sm.dconf[j] = dv[k];
-                else sm.dcls[j] = dv[k];
+                // the class column is only read for matched / new tracks, straight from the detection row (L2)
             }
         }
         if (t < n) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) sm.mean[c][t] = mv[c];
+            for (int c = 0; c < 4; ++c) vel[c] = mv[4 + c];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) sm.mean[c][t] = mv[c];
             sm.start_t[t] = start_v;
         }
         // the covariance / id / score lines are first used after the association: pull them into L2 now
@@ -481,11 +484,11 @@ bytetrack_step_kernel(const StepParams p) {
         if (role != ROLE_UNCONF) {
             ref_w = sm.mean[2][t]; ref_h = sm.mean[3][t];
             if ((fl & 3) != B200_ST_TRACKED) {          // multi_predict: zero the height (w, h) velocity
-                sm.mean[7][t] = 0.0;
-                if (KIND == KF_XYWH) sm.mean[6][t] = 0.0;
+                vel[3] = 0.0;
+                if (KIND == KF_XYWH) vel[2] = 0.0;
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) sm.mean[i][t] = xadd(sm.mean[i][t], sm.mean[i + 4][t]);
+            for (int i = 0; i < 4; ++i) sm.mean[i][t] = xadd(sm.mean[i][t], vel[i]);
         }
         sm.rowtype[t] = role != ROLE_UNCONF ? RT_A : RT_NONE;
         sm.match[t] = -1;
@@ -624,7 +627,14 @@ bytetrack_step_kernel(const StepParams p) {
         cls = gf[B200_TF_CLS * TMAX + t];
         start = sm.start_t[t];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) ks.m[c] = sm.mean[c][t];
+        for (int c = 0; c < 4; ++c) ks.m[c] = sm.mean[c][t];
+        // velocities: second (L2) read instead of 8 KB of shared memory; same zeroing rule as the motion step
+#pragma unroll
+        for (int c = 0; c < 4; ++c) ks.m[4 + c] = gf[(B200_TF_MEAN + 4 + c) * TMAX + t];
+        if (role != ROLE_UNCONF && (fl & 3) != B200_ST_TRACKED) {
+            ks.m[7] = 0.0;
+            if (KIND == KF_XYWH) ks.m[6] = 0.0;
+        }
         if (role != ROLE_UNCONF) {
             // covariance half of multi_predict; the noise uses the pre-motion w / h
             double ref4[4] = {0.0, 0.0, ref_w, ref_h};
@@ -646,12 +656,12 @@ bytetrack_step_kernel(const StepParams p) {
             det_measurement<KIND>(sm, j, z);
             kf_update<KIND>(ks, z);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) sm.mean[c][t] = ks.m[c];
+            for (int c = 0; c < 4; ++c) sm.mean[c][t] = ks.m[c];
             len = (st0 == B200_ST_TRACKED) ? len + 1 : 0;
             frame_t = frame;
             det_ind = j;
             score = sm.dconf[j];
-            cls = sm.dcls[j];
+            cls = dets_g[j * 6 + 5];
             if constexpr (BOT) {
                 double* h = p.cls_hist + ((size_t)s * TMAX + sm.bot.frow[t]) * 9;
                 cls = cls_vote(h, cls, score, err);
@@ -858,7 +868,7 @@ bytetrack_step_kernel(const StepParams p) {
                 wf[(B200_TF_COV + 3 * a + 2) * TMAX + dst] = kn.vv[a];
             }
             wf[B200_TF_SCORE * TMAX + dst] = sm.dconf[j];
-            wf[B200_TF_CLS * TMAX + dst] = sm.dcls[j];
+            wf[B200_TF_CLS * TMAX + dst] = dets_g[j * 6 + 5];
             wi[B200_TI_ID * TMAX + dst] = id;
             wi[B200_TI_FRAME * TMAX + dst] = frame;
             wi[B200_TI_START * TMAX + dst] = frame;
@@ -874,7 +884,7 @@ bytetrack_step_kernel(const StepParams p) {
             if (stored) {
                 wi[B200_TI_FROW * TMAX + dst] = row;
                 double* h = p.cls_hist + ((size_t)s * TMAX + row) * 9;     // STrack.__init__: cls_hist = [[cls, score]]
-                h[0] = sm.dcls[j]; h[4] = sm.dconf[j]; h[8] = 1.0;
+                h[0] = dets_g[j * 6 + 5]; h[4] = sm.dconf[j]; h[8] = 1.0;
             }
         }
         if (born_active) {
@@ -883,7 +893,7 @@ bytetrack_step_kernel(const StepParams p) {
                 const Box b = mean_to_box<KIND>(z[0], z[1], z[2], z[3]);
                 double* o = gout + (size_t)orow * 8;
                 o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
-                o[4] = (double)id; o[5] = sm.dconf[j]; o[6] = sm.dcls[j]; o[7] = (double)j;
+                o[4] = (double)id; o[5] = sm.dconf[j]; o[6] = dets_g[j * 6 + 5]; o[7] = (double)j;
             }
         }
     }
@@ -916,8 +926,10 @@ bytetrack_step_kernel(const StepParams p) {
 }
 
 #undef PHASE
+// four CTAs of the (224, 224) variant share an SM: 227 KB of shared memory, 1 KB reserved per CTA
+static_assert(sizeof(StepSmem<224, 224>) + 1024 <= 227 * 1024 / 4, "(224, 224) ByteTrack variant must fit 4 CTAs per SM");
 struct Variant { int tmax, dmax; };
-constexpr Variant kVariants[] = {{64, 64}, {128, 128}, {256, 224}, {256, 256}, {512, 512}};
+constexpr Variant kVariants[] = {{64, 64}, {128, 128}, {224, 224}, {256, 256}, {512, 512}};
 
 template <int KIND, int TMAX, int DMAX, bool BOT>
 cudaError_t launch_variant(const StepParams& p, cudaStream_t stream) {
@@ -934,7 +946,7 @@ cudaError_t launch_kind(const StepParams& p, int v, cudaStream_t stream) {
     switch (v) {
         case 0: return launch_variant<KIND, 64, 64, BOT>(p, stream);
         case 1: return launch_variant<KIND, 128, 128, BOT>(p, stream);
-        case 2: return launch_variant<KIND, 256, 224, BOT>(p, stream);
+        case 2: return launch_variant<KIND, 224, 224, BOT>(p, stream);
         case 3: return launch_variant<KIND, 256, 256, BOT>(p, stream);
         case 4: return launch_variant<KIND, 512, 512, BOT>(p, stream);
     }
@@ -954,7 +966,7 @@ size_t bytetrack_step_smem(int variant, bool botsort) {
     switch (variant) {
         case 0: return botsort ? sizeof(StepSmem<64, 64, true>) : sizeof(StepSmem<64, 64>);
         case 1: return botsort ? sizeof(StepSmem<128, 128, true>) : sizeof(StepSmem<128, 128>);
-        case 2: return botsort ? sizeof(StepSmem<256, 224, true>) : sizeof(StepSmem<256, 224>);
+        case 2: return botsort ? sizeof(StepSmem<224, 224, true>) : sizeof(StepSmem<224, 224>);
         case 3: return botsort ? sizeof(StepSmem<256, 256, true>) : sizeof(StepSmem<256, 256>);
         case 4: return botsort ? sizeof(StepSmem<512, 512, true>) : sizeof(StepSmem<512, 512>);
     }

@@ -182,7 +182,7 @@ __device__ __forceinline__ void block_max3(SM& sm, double& d, int& a, int& b) {
 }
 
 template <int NT, int TMAX, int DMAX>
-__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : (NT == 256 ? 2 : (NT == 128 ? 4 : 8))))
+__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : (NT >= 224 ? 2 : (NT == 128 ? 4 : 8))))
 ocsort_step_kernel(const StepParams p) {
     static_assert(NT == TMAX && DMAX <= NT, "one thread per tracker slot; detections fit one pass");
     using SM = OcSmem<TMAX, DMAX>;
@@ -686,7 +686,7 @@ size_t ocsort_step_smem(int variant) {
     switch (variant) {
         case 0: return sizeof(OcSmem<64, 64>);
         case 1: return sizeof(OcSmem<128, 128>);
-        case 2: return sizeof(OcSmem<256, 224>);
+        case 2: return sizeof(OcSmem<224, 224>);
         case 3: return sizeof(OcSmem<256, 256>);
         case 4: return sizeof(OcSmem<512, 512>);
     }
@@ -697,7 +697,7 @@ cudaError_t launch_ocsort_step(const StepParams& p, int variant, cudaStream_t st
     switch (variant) {
         case 0: return launch_oc_variant<64, 64>(p, stream);
         case 1: return launch_oc_variant<128, 128>(p, stream);
-        case 2: return launch_oc_variant<256, 224>(p, stream);
+        case 2: return launch_oc_variant<224, 224>(p, stream);
         case 3: return launch_oc_variant<256, 256>(p, stream);
         case 4: return launch_oc_variant<512, 512>(p, stream);
     }
