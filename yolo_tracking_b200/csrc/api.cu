@@ -76,7 +76,7 @@ extern "C" void b200track_destroy(b200track_ctx* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->p.state_f); cudaFree(ctx->p.state_i); cudaFree(ctx->p.counts);
     cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.dbg); cudaFree(ctx->p.scratch);
-    cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.cls_hist);
+    cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.feat_curr); cudaFree(ctx->p.cls_hist);
     for (auto& s : ctx->slot) {
         cudaFree(s.d_dets); cudaFree(s.d_ndets); cudaFree(s.d_feats); cudaFree(s.d_out); cudaFree(s.d_nout);
         if (s.in_ready) cudaEventDestroy(s.in_ready);
@@ -152,7 +152,10 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         CU_TRY_CTX(cudaMalloc(&p.scratch, S * T * (size_t)b200::step_variant_dmax(ctx->variant) * sizeof(double)));
     if (cfg->kind == B200TRACK_BOTSORT) {
         CU_TRY_CTX(cudaMalloc(&p.cls_hist, S * T * 9 * sizeof(double)));
-        if (cfg->with_reid) CU_TRY_CTX(cudaMalloc(&p.feat_pool, S * T * (size_t)cfg->feat_dim * sizeof(float)));
+        if (cfg->with_reid) {
+            CU_TRY_CTX(cudaMalloc(&p.feat_pool, S * T * (size_t)cfg->feat_dim * sizeof(float)));
+            CU_TRY_CTX(cudaMalloc(&p.feat_curr, S * D * (size_t)cfg->feat_dim * sizeof(float)));
+        }
     }
     CU_TRY_CTX(cudaMalloc(&p.counts, S * 4 * sizeof(int)));
     CU_TRY_CTX(cudaMalloc(&p.track_updates, S * sizeof(unsigned long long)));

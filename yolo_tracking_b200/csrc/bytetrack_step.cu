@@ -67,7 +67,7 @@ struct BotSmem<TMAX, DMAX, true> {
     static constexpr int PCAP = 4 * TMAX;
     double pcost[PCAP];              // iou-side cost of a pair waiting for its appearance distance
     uint32_t epairs[PCAP];           // (row << 16) | det
-    float dn0[DMAX], dn1[DMAX], dn2[DMAX];   // norms of the three in-place normalisations of a detection embedding
+    float dn2[DMAX];                 // norm of a detection's curr_feat (the third in-place normalisation divides by it)
     int nepairs[4];
     short frow[TMAX];                // embedding-pool row of a slot
     short emadet[TMAX];              // detection whose embedding is blended into the slot's, -1 = none
@@ -295,27 +295,33 @@ __device__ __forceinline__ double f4_sq(float4 a) {
 }
 __device__ __forceinline__ float norm_f32(double sumsq) { return sqrtf((float)sumsq); }
 
-// the three successive norms of a detection embedding: get_features row -> STrack.__init__ (feat /= |feat|,
-// then the aliased smooth_feat /= |smooth_feat|) -> update_features of the matched track (feat /= |feat|)
-__device__ __forceinline__ void det_feat_norms(const float4* row, int nv, int lane, float& n0, float& n1, float& n2) {
+// A detection embedding as the reference holds it when costs are computed: get_features row -> STrack.__init__
+// (feat /= |feat|, then the aliased smooth_feat /= |smooth_feat|).  The twice-normalised row (curr_feat) is written
+// to the stream's scratch block once, so pair costs, blends and new tracks read it without redoing the divisions;
+// the return value is its norm, which update_features of a matched track divides by once more.
+__device__ __forceinline__ float det_curr_feat(const float4* row, float4* out, int nv, int lane) {
     double a = 0.0;
     for (int i = lane; i < nv; i += 32) a += f4_sq(row[i]);
-    n0 = norm_f32(warp_sum(a));
+    const float n0 = norm_f32(warp_sum(a));
     a = 0.0;
     for (int i = lane; i < nv; i += 32) a += f4_sq(f4_div(row[i], n0));
-    n1 = norm_f32(warp_sum(a));
+    const float n1 = norm_f32(warp_sum(a));
     a = 0.0;
-    for (int i = lane; i < nv; i += 32) a += f4_sq(f4_div(f4_div(row[i], n0), n1));
-    n2 = norm_f32(warp_sum(a));
+    for (int i = lane; i < nv; i += 32) {
+        const float4 v = f4_div(f4_div(row[i], n0), n1);
+        out[i] = v;
+        a += f4_sq(v);
+    }
+    return norm_f32(warp_sum(a));
 }
 
 // embedding_distance (matching.py:145-167) of one (smoothed track embedding, detection curr_feat) pair:
 // scipy cdist 'cosine' in double on the fp32 values, clamped at 0
-__device__ __forceinline__ double emb_distance(const float4* trk, const float4* det, int nv, int lane, float n0, float n1) {
+__device__ __forceinline__ double emb_distance(const float4* trk, const float4* det, int nv, int lane) {
     double uv = 0.0, uu = 0.0, vv = 0.0;
     for (int i = lane; i < nv; i += 32) {
         const float4 a = trk[i];
-        const float4 b = f4_div(f4_div(det[i], n0), n1);
+        const float4 b = det[i];
         uv += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
         uu += f4_sq(a);
         vv += f4_sq(b);
@@ -336,8 +342,8 @@ __device__ __forceinline__ void graph_phase_emb(SM& sm, const StepParams& p, int
         const uint32_t pr = sm.bot.epairs[k];
         const int t = pr >> 16, j = pr & 0xffff;
         const float4* trk = reinterpret_cast<const float4*>(p.feat_pool + ((size_t)s * SM::TCAP + sm.bot.frow[t]) * p.feat_dim);
-        const float4* det = reinterpret_cast<const float4*>(p.feats + ((size_t)s * p.max_dets + j) * p.feat_dim);
-        double e = xmul(emb_distance(trk, det, nv, lane, sm.bot.dn0[j], sm.bot.dn1[j]), 0.5);
+        const float4* det = reinterpret_cast<const float4*>(p.feat_curr + ((size_t)s * p.max_dets + j) * p.feat_dim);
+        double e = xmul(emb_distance(trk, det, nv, lane), 0.5);
         if (e > p.appearance_thresh) e = 1.0;
         const double c = fmin(sm.bot.pcost[k], e);
         if (lane == 0 && c <= (sm.rowtype[t] == RT_A ? lim.limA : lim.limB)) graph_add_edge<KIND>(sm, t, j, c);
@@ -535,9 +541,9 @@ bytetrack_step_kernel(const StepParams p) {
             const int nv = p.feat_dim >> 2;
             for (int j = warp; j < nd; j += NT / 32) {
                 if (sm.dflag[j] != DF_HIGH) continue;
-                float n0, n1, n2;
-                det_feat_norms(reinterpret_cast<const float4*>(p.feats + ((size_t)s * p.max_dets + j) * p.feat_dim), nv, lane, n0, n1, n2);
-                if (lane == 0) { sm.bot.dn0[j] = n0; sm.bot.dn1[j] = n1; sm.bot.dn2[j] = n2; }
+                const size_t off = ((size_t)s * p.max_dets + j) * p.feat_dim;
+                const float n2 = det_curr_feat(reinterpret_cast<const float4*>(p.feats + off), reinterpret_cast<float4*>(p.feat_curr + off), nv, lane);
+                if (lane == 0) sm.bot.dn2[j] = n2;
             }
         }
         if (tid == 0) sm.bot.nepairs[0] = 0;
@@ -699,10 +705,10 @@ bytetrack_step_kernel(const StepParams p) {
                 const int j = sm.bot.emadet[q];
                 if (j < 0) continue;
                 float4* trk = reinterpret_cast<float4*>(p.feat_pool + ((size_t)s * TMAX + sm.bot.frow[q]) * p.feat_dim);
-                const float4* det = reinterpret_cast<const float4*>(p.feats + ((size_t)s * p.max_dets + j) * p.feat_dim);
-                const float n0 = sm.bot.dn0[j], n1 = sm.bot.dn1[j], n2 = sm.bot.dn2[j];
+                const float4* det = reinterpret_cast<const float4*>(p.feat_curr + ((size_t)s * p.max_dets + j) * p.feat_dim);
+                const float n2 = sm.bot.dn2[j];
                 auto blend = [&](int i) {
-                    const float4 f = f4_div(f4_div(f4_div(det[i], n0), n1), n2);
+                    const float4 f = f4_div(det[i], n2);
                     const float4 a = trk[i];
                     return make_float4(__fadd_rn(__fmul_rn(A, a.x), __fmul_rn(B, f.x)), __fadd_rn(__fmul_rn(A, a.y), __fmul_rn(B, f.y)),
                                        __fadd_rn(__fmul_rn(A, a.z), __fmul_rn(B, f.z)), __fadd_rn(__fmul_rn(A, a.w), __fmul_rn(B, f.w)));
@@ -906,9 +912,8 @@ bytetrack_step_kernel(const StepParams p) {
                 const int j = sm.bot.nbdet[k];
                 if (j < 0) continue;
                 float4* trk = reinterpret_cast<float4*>(p.feat_pool + ((size_t)s * TMAX + sm.bot.nbrow[k]) * p.feat_dim);
-                const float4* det = reinterpret_cast<const float4*>(p.feats + ((size_t)s * p.max_dets + j) * p.feat_dim);
-                const float n0 = sm.bot.dn0[j], n1 = sm.bot.dn1[j];
-                for (int i = lane; i < nv; i += 32) trk[i] = f4_div(f4_div(det[i], n0), n1);
+                const float4* det = reinterpret_cast<const float4*>(p.feat_curr + ((size_t)s * p.max_dets + j) * p.feat_dim);
+                for (int i = lane; i < nv; i += 32) trk[i] = det[i];
             }
         }
     }

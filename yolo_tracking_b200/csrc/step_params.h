@@ -25,6 +25,7 @@ struct StepParams {
     // BoT-SORT
     int with_reid;
     float* feat_pool;         // [S, Tcap, feat_dim] smoothed track embeddings, row-indexed (layout.h)
+    float* feat_curr;         // [S, max_dets, feat_dim] scratch: this frame's twice-normalised detection embeddings
     double* cls_hist;         // [S, Tcap, 9] class-vote tables, row-indexed
     // device state (layout.h)
     double* state_f;
