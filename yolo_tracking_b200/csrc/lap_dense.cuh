@@ -37,27 +37,39 @@ struct DenseLap {
 // which is why the reduction runs over rows (a column reduction would leave free columns with
 // v = colmin != 0).  One warp per row, lanes sweep the columns (coalesced reads of the matrix).
 template <int NT>
-__device__ void dense_lap_init(const DenseLap& w, const double* C, int ld, int R, int Cn, double lambda) {
+__device__ void dense_lap_init(const DenseLap& w, const double* C, int ld, int R, int Cn, double lambda, bool have_rowmin = false) {
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int c = tid; c < Cn; c += NT) { w.v[c] = 0.0; w.yc[c] = -1; w.pred[c] = 0x7fffffff; }
     for (int r = tid; r < R; r += NT) w.xr[r] = -1;
     __syncthreads();
-    for (int r = warp; r < R; r += NT / 32) {
-        double m = INF; int a = -1;
-        const double* row = C + (size_t)r * ld;
-        for (int j = lane; j < Cn; j += 32) { const double x = row[j]; if (x < m) { m = x; a = j; } }
-#pragma unroll
-        for (int d = 16; d; d >>= 1) {
-            const double om = __shfl_xor_sync(0xffffffffu, m, d);
-            const int oa = __shfl_xor_sync(0xffffffffu, a, d);
-            if (om < m || (om == m && oa >= 0 && (a < 0 || oa < a))) { m = om; a = oa; }
-        }
-        if (lane == 0) {
+    if (have_rowmin) {
+        // the caller reduced every row while it filled the matrix: w.u[r] = row minimum, w.claim[r] = its column
+        for (int r = tid; r < R; r += NT) {
+            const double m = w.u[r];
+            const int a = w.claim[r];
             const bool take = a >= 0 && m <= lambda;
             w.u[r] = take ? m : lambda;
             w.claim[r] = take ? a : -1;
             if (take) atomicMin(&w.pred[a], r);
+        }
+    } else {
+        for (int r = warp; r < R; r += NT / 32) {
+            double m = INF; int a = -1;
+            const double* row = C + (size_t)r * ld;
+            for (int j = lane; j < Cn; j += 32) { const double x = row[j]; if (x < m) { m = x; a = j; } }
+#pragma unroll
+            for (int d = 16; d; d >>= 1) {
+                const double om = __shfl_xor_sync(0xffffffffu, m, d);
+                const int oa = __shfl_xor_sync(0xffffffffu, a, d);
+                if (om < m || (om == m && oa >= 0 && (a < 0 || oa < a))) { m = om; a = oa; }
+            }
+            if (lane == 0) {
+                const bool take = a >= 0 && m <= lambda;
+                w.u[r] = take ? m : lambda;
+                w.claim[r] = take ? a : -1;
+                if (take) atomicMin(&w.pred[a], r);
+            }
         }
     }
     __syncthreads();

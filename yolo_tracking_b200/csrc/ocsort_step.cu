@@ -290,26 +290,37 @@ ocsort_step_kernel(const StepParams p) {
         double mx = -1e300;
         if (tid < Cn) sm.colcnt[tid] = 0;
         __syncthreads();
-        {   // all threads share the R x Cn pairs evenly: pair k -> (row k / Cn, column k % Cn), stepped without divisions
-            const int total = R * Cn, dr = NT / Cn, dc = NT - dr * Cn;
-            int r = tid / Cn, c = tid - r * Cn;
-            for (int k = tid; k < total; k += NT) {
-                const int sl = sm.ht[c], j = sm.hd[r];
-                const Box tb = {sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]};
+        {   // one warp per detection row, lanes across the tracker columns: the row minimum (the start of the
+            // assignment, lap_dense.cuh step 1) falls out of the fill as a warp reduction instead of a second pass
+            const int lane = tid & 31, warp = tid >> 5;
+            const double INF = __longlong_as_double(0x7ff0000000000000LL);
+            for (int r = warp; r < R; r += NT / 32) {
+                const int j = sm.hd[r];
                 const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
-                const double sim = oc_sim(func, db, tb, W, H);
-                double ang = 0.0;
-                const double vy = sm.vel[0][sl], vx = sm.vel[1][sl];
-                if (sm.kvalid[sl] && !(vx == 0.0 && vy == 0.0)) {
-                    const double dcx = xdiv(xadd(db.x1, db.x2), 2.0), dcy = xdiv(xadd(db.y1, db.y2), 2.0);
-                    ang = oc_angle(vy, vx, sm.kc[0][sl], sm.kc[1][sl], true, dcx, dcy, p.inertia, sm.dconf[j]);
+                const double dcx = xdiv(xadd(db.x1, db.x2), 2.0), dcy = xdiv(xadd(db.y1, db.y2), 2.0), dconf = sm.dconf[j];
+                double m = INF;
+                int a = -1;
+                for (int c = lane; c < Cn; c += 32) {
+                    const int sl = sm.ht[c];
+                    const Box tb = {sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]};
+                    const double sim = oc_sim(func, db, tb, W, H);
+                    double ang = 0.0;
+                    const double vy = sm.vel[0][sl], vx = sm.vel[1][sl];
+                    if (sm.kvalid[sl] && !(vx == 0.0 && vy == 0.0))
+                        ang = oc_angle(vy, vx, sm.kc[0][sl], sm.kc[1][sl], true, dcx, dcy, p.inertia, dconf);
+                    const double cst = xadd(-xadd(xadd(sim, ang), 0.0), xmul((double)(r * Cn + c), TIE_EPS));
+                    C[(size_t)r * TMAX + c] = cst;
+                    mx = fmax(mx, cst);
+                    if (cst < m) { m = cst; a = c; }
+                    if (sim > thr) { atomicAdd(&sm.colcnt[c], 1); atomicAdd(&sm.rowcnt[r], 1); sm.rowmatch[r] = c; }
                 }
-                const double cst = xadd(-xadd(xadd(sim, ang), 0.0), xmul((double)k, TIE_EPS));      // k == r * Cn + c
-                C[(size_t)r * TMAX + c] = cst;
-                mx = fmax(mx, cst);
-                if (sim > thr) { atomicAdd(&sm.colcnt[c], 1); atomicAdd(&sm.rowcnt[r], 1); sm.rowmatch[r] = c; }
-                r += dr; c += dc;
-                if (c >= Cn) { c -= Cn; ++r; }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    const double om = __shfl_xor_sync(0xffffffffu, m, d);
+                    const int oa = __shfl_xor_sync(0xffffffffu, a, d);
+                    if (om < m || (om == m && oa >= 0 && (a < 0 || oa < a))) { m = om; a = oa; }
+                }
+                if (lane == 0) { sm.u[r] = m; sm.claim[r] = a; }
             }
         }
         __syncthreads();
@@ -323,7 +334,7 @@ ocsort_step_kernel(const StepParams p) {
         } else {
             const DenseLap w = make_dense<NT>(sm);
             const double lambda = 2.0 * (mx + 1.0);
-            dense_lap_init<NT>(w, C, TMAX, R, Cn, lambda);
+            dense_lap_init<NT>(w, C, TMAX, R, Cn, lambda, true);
             dense_lap_augment<NT>(w, C, TMAX, R, Cn, lambda);
         }
         // matched pairs below the similarity threshold fall back to unmatched (association.py:187-193)
