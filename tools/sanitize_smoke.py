@@ -1,0 +1,53 @@
+"""Small end-to-end exercise of every kernel, meant to run under `compute-sanitizer --tool memcheck` (or racecheck /
+initcheck, one tool per gpurun call): a few frames of each tracker on a handful of streams plus every operator."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from yolo_tracking_b200 import _lib, _ops  # noqa: E402
+from yolo_tracking_b200.batch import BatchedTracker  # noqa: E402
+from yolo_tracking_b200.synth import make_batch  # noqa: E402
+
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+for kind, cap, kw, params in (
+        ("bytetrack", 64, dict(miss_prob=0.2, fp_rate=3.0), dict(track_thresh=0.5, match_thresh=0.8, track_buffer=5, frame_rate=30)),
+        ("bytetrack", 224, {}, dict(track_thresh=0.5, match_thresh=0.8, track_buffer=30, frame_rate=30)),
+        ("ocsort", 128, dict(occlusion=True, miss_prob=0.2), dict(det_thresh=0.4, max_age=5, min_hits=1, asso_threshold=0.3, delta_t=3,
+                                                                  asso_func="giou", inertia=0.2, use_byte=True)),
+        ("botsort", 128, dict(miss_prob=0.2, fp_rate=2.0, emb_dim=128), dict(track_high_thresh=0.5, track_low_thresh=0.1, new_track_thresh=0.6,
+                                                                            track_buffer=5, match_thresh=0.8, proximity_thresh=0.5,
+                                                                            appearance_thresh=0.25, frame_rate=30))):
+    n_obj = 150 if cap == 224 else 30
+    dets, nd, embs = make_batch(7, 3, n_obj, F, dmax=cap, **kw)
+    trk = BatchedTracker(kind, 3, max_tracks=cap, max_dets=cap, feat_dim=128 if kind == "botsort" else 0, **params)
+    rows = 0
+    for f in range(F):
+        feats = None
+        if embs is not None:
+            feats = np.ascontiguousarray(embs[f] / 10.0)
+        out, nout = trk.update_batch(np.ascontiguousarray(dets[f]), np.ascontiguousarray(nd[f]), feats=feats, img_hw=(1080, 1920))
+        rows += int(nout.sum())
+    trk.state(1)
+    trk.sync()
+    trk.close()
+    print(kind, cap, "rows", rows, flush=True)
+rng = np.random.default_rng(0)
+z = np.stack([rng.uniform(100, 900, 50), rng.uniform(100, 900, 50), rng.uniform(0.3, 0.8, 50), rng.uniform(60, 220, 50)], axis=1)
+for kind in (_lib.KF_XYAH, _lib.KF_XYWH, _lib.KF_XYAH_CONF):
+    m, c = _ops.kf_initiate(kind, z)
+    m, c = _ops.kf_predict(kind, m, c)
+    _ops.kf_project(kind, m, c, 0.5 if kind == _lib.KF_XYAH_CONF else None)
+    m, c = _ops.kf_update(kind, m, c, z + 1.0, 0.5 if kind == _lib.KF_XYAH_CONF else None)
+    _ops.kf_gating_distance(kind, m, c, z[:17] + 2.0, False, "maha", 0.5 if kind == _lib.KF_XYAH_CONF else None)
+    _ops.gate_cost(kind, rng.random((50, 17)), m, c, z[:17] + 2.0, fuse=True)
+a = np.concatenate([z[:, :2] - 20, z[:, :2] + 30], axis=1)
+for name in ("iou", "giou", "diou", "ciou", "centroid"):
+    _ops.box_similarity(name, a, a[:23] + 3.0, 1920, 1080)
+_ops.iou_distance(a, a[:23] + 3.0)
+_ops.embedding_distance(rng.standard_normal((37, 96)), rng.standard_normal((29, 96)))
+_ops.appearance_cost(rng.standard_normal((2, 150, 128)), rng.standard_normal((2, 70, 128)), 0.5, 0.45, 1.0, gate=rng.random((2, 150, 70)) < 0.3)
+_ops.lapjv(rng.random((3, 40, 55)), 0.6)
+_ops.lapjv(-rng.random((3, 40, 55)))
+print("ops ok", flush=True)
