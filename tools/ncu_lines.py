@@ -48,6 +48,7 @@ for k, r in enumerate(body):
     s = float(r[ci["# Samples"]] or 0)
     agg[key]["samples"] += s
     agg[key]["inst"] += float(r[ci["Instructions Executed"]] or 0)
+    agg[key]["tinst"] += float(r[ci["Thread Instructions Executed"]] or 0)
     tot += s
     for c in stall_cols:
         agg[key][c] += float(r[ci[c]] or 0)
@@ -63,6 +64,18 @@ def src(f, n):
 
 
 print(f"total samples {tot:.0f}")
+if os.environ.get("BY_INST"):
+    ti = sum(a["inst"] for a in agg.values())
+    print(f"total warp instructions {ti / 1e6:.1f} M; by instruction count:")
+    byfile = defaultdict(lambda: [0.0, 0.0])
+    for key, a in agg.items():
+        byfile[key[0]][0] += a["inst"]
+        byfile[key[0]][1] += a["tinst"]
+    for f, (i, t) in sorted(byfile.items(), key=lambda kv: -kv[1][0]):
+        print(f"  {f:32s} {i / 1e6:8.2f} M inst  {100 * i / ti:5.1f} %   avg lanes {t / max(i, 1):5.1f}")
+    for key, a in sorted(agg.items(), key=lambda kv: -kv[1]["inst"])[:top]:
+        print(f"{100 * a['inst'] / ti:5.1f}%  inst {a['inst'] / 1e6:7.2f}M  lanes {a['tinst'] / max(a['inst'], 1):5.1f}  {key[0]}:{key[1]:<4d} {src(*key)}")
+    sys.exit(0)
 for key, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:top]:
     st = sorted(((c[6:], a[c]) for c in stall_cols if a[c] > 0), key=lambda x: -x[1])[:3]
     print(f"{100 * a['samples'] / tot:5.1f}%  inst {a['inst'] / 1e6:7.2f}M  {key[0]}:{key[1]:<4d} {src(*key)}\n        " +

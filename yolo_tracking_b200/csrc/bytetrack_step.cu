@@ -750,6 +750,8 @@ bytetrack_step_kernel(const StepParams p) {
             const Box b = track_box<KIND>(sm, q);
             sm.u[tid] = b.x1; sm.u[LCAP + tid] = b.y1; sm.u[2 * LCAP + tid] = b.x2; sm.u[3 * LCAP + tid] = b.y2;
             sm.coldeg[tid] = sm.frame_t[q] - sm.start_t[q];
+            // conservative fp32 copy (rounded outwards) for the overlap pre-test; dboxf is free after the last graph build
+            sm.dboxf[tid] = make_float4(__double2float_rd(b.x1), __double2float_rd(b.y1), __double2float_ru(b.x2), __double2float_ru(b.y2));
         }
         __syncthreads();
         PHASE(10);
@@ -768,10 +770,15 @@ bytetrack_step_kernel(const StepParams p) {
                 age = 0;
             }
             bool dropme = false;
+            const float ax1 = __double2float_rd(a.x1), ay1 = __double2float_rd(a.y1);
+            const float ax2 = __double2float_ru(a.x2), ay2 = __double2float_ru(a.y2);
             for (int k = 0; k < nLostList; ++k) {
                 Box b;
-                if (lost_cached) { b.x1 = sm.u[k]; b.y1 = sm.u[LCAP + k]; b.x2 = sm.u[2 * LCAP + k]; b.y2 = sm.u[3 * LCAP + k]; }
-                else b = track_box<KIND>(sm, sm.lostlist[k]);
+                if (lost_cached) {
+                    const float4 f = sm.dboxf[k];
+                    if (!(f.x < ax2 && ax1 < f.z && f.y < ay2 && ay1 < f.w)) continue;      // disjoint even after outward rounding
+                    b.x1 = sm.u[k]; b.y1 = sm.u[LCAP + k]; b.x2 = sm.u[2 * LCAP + k]; b.y2 = sm.u[3 * LCAP + k];
+                } else b = track_box<KIND>(sm, sm.lostlist[k]);
                 if (!box_overlap(a, b)) continue;
                 if (xsub(1.0, box_iou(a, b)) < p.dup_thresh) {
                     const int q = sm.lostlist[k];

@@ -152,13 +152,15 @@ template <int NT>
 __device__ __forceinline__ void lap_prepare(const LapWork& w, int nrows, int words) {
     const int tid = threadIdx.x;
     const int ncols = words * 32;
-    for (int t = tid; t < nrows; t += NT) { w.xr[t] = -1; w.u[t] = 0.0; w.parent[t] = t; w.head[t] = -1; w.rnext[t] = -1; }
+    for (int t = tid; t < nrows; t += NT) {
+        w.xr[t] = -1; w.u[t] = 0.0; w.parent[t] = t; w.head[t] = -1; w.rnext[t] = -1;
+        if (w.ehead) w.ehead[t] = -1;
+    }
     for (int j = tid; j < ncols; j += NT) {
         w.yc[j] = -1; w.v[j] = 0.0; w.parent[w.Tmax + j] = w.Tmax + j; w.mark[j] = 0; w.scn[j] = 0; w.coldeg[j] = 0;
         if (w.colxor) w.colxor[j] = 0;
     }
     if (tid == 0) { *w.ncomplex = 0; if (w.ecount) *w.ecount = 0; }
-    if (w.ehead) for (int t = tid; t < nrows; t += NT) w.ehead[t] = -1;
 }
 
 // Whole-CTA solve.  adj[word][row], coldeg[] (and, when used, the edge cache and colxor[]) must be
@@ -178,9 +180,14 @@ __device__ void lap_sparse_solve(const LapWork& w, int nrows, int words, const L
     const bool small_ok = w.ecost != nullptr && w.colxor != nullptr && *w.ecount <= w.ecap;
     for (int t = tid; t < nrows; t += NT) {
         int deg = 0, first = -1;
-        for (int wd = 0; wd < words; ++wd) {
-            const uint32_t bits = w.adj[wd * w.Tmax + t];
-            if (bits) { if (first < 0) first = wd * 32 + __ffs(bits) - 1; deg += __popc(bits); }
+        if (small_ok) {                                   // the edge list mirrors adj: degree 0 / 1 without scanning the mask words
+            const int e0 = w.ehead[t];
+            if (e0 >= 0) { first = w.ecol[e0]; deg = w.enext[e0] < 0 ? 1 : 2; }
+        } else {
+            for (int wd = 0; wd < words; ++wd) {
+                const uint32_t bits = w.adj[wd * w.Tmax + t];
+                if (bits) { if (first < 0) first = wd * 32 + __ffs(bits) - 1; deg += __popc(bits); }
+            }
         }
         if (deg == 0) continue;
         if (deg == 1 && w.coldeg[first] == 1) { w.xr[t] = (short)first; w.yc[first] = (short)t; continue; }
