@@ -26,6 +26,27 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line.  Libraries print there too (NCCL's version banner is a plain printf), so the
+# process's fd 1 is pointed at stderr for its whole life and the result line is written to the saved descriptor.
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 # Workloads (BASELINE.json configs).  The headline (default) is config 5; the others are reported in DESIGN.md.
 # b_slot: algorithmic HBM bytes of one track slot, in + out; b_feat: embedding bytes per
@@ -238,7 +259,7 @@ def run_reference(args, rank, world):
                                    f"cannot travel), one process per core"},
         "e2e": {"value": val, "unit": "track-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_b200(args, rank, world, local_rank):
@@ -367,6 +388,21 @@ def run_b200(args, rank, world, local_rank):
     tu_e2e = trk.track_updates() - tu1
     trk.sync()
 
+    # ---------------- optional final gather of the padded outputs (the only collective; not part of the step) ----
+    gather_ms = None
+    if world > 1:
+        from yolo_tracking_b200.shard import gather_outputs
+        for _ in range(2):
+            gather_outputs(d_out, d_nout)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        all_out, all_nout = gather_outputs(d_out, d_nout)
+        g1.record()
+        torch.cuda.synchronize(dev)
+        assert all_out.shape[0] == S * world and all_nout.shape[0] == S * world
+        gather_ms = g0.elapsed_time(g1)
+
     # ---------------- reduce over ranks ----------------------------------------------------
     from yolo_tracking_b200.shard import reduce_timing
     total_ms_max, (tu_all, tu_e2e_all, launches_all, rows_all, dets_all) = reduce_timing(
@@ -410,6 +446,8 @@ def run_b200(args, rank, world, local_rank):
                     "ms_per_step": e2e_ms_max / args.steps, "pipeline_depth": nslot,
                     "output_rows_per_step": rows_all / args.steps},
             "gpu_launches": int(launches_all),
+            "gather": None if gather_ms is None else {"ms": gather_ms, "bytes_per_rank": S * MAX_TRACKS * 64 + 4 * S,
+                                                       "what": "NCCL all_gather of out[S, max_tracks, 8] + nout[S] after the run (optional, outside the step)"},
             "roofline": {"bound": "hbm", "kernel": W["kernel"], "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
@@ -418,7 +456,7 @@ def run_b200(args, rank, world, local_rank):
             "cpu_baseline": cpu_base,
             "clocks": sampler.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -439,6 +477,7 @@ def main():
     if args.streams <= 0:
         args.streams = STREAMS_PER_GPU
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    _claim_stdout()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
