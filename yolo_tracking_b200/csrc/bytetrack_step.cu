@@ -2,11 +2,12 @@
 // stream, one thread per track slot.
 //
 // Data flow per stream (HBM is touched exactly once in each direction):
-//   * detections [nd, 6] and the 8 Kalman means + 3 lifecycle ints of every slot are staged
-//     in shared memory; the 12 covariance terms of a slot are NOT needed for association
-//     (ByteTrack costs only use boxes), so each thread loads them straight into registers at
-//     the single deferred predict+update point and keeps them there until the final write;
-//   * candidate pairs come from per-frame cell masks (64 x-cells and 64 y-cells, each a
+//   * detections [nd, 6] and the position half of the Kalman mean + 3 lifecycle ints of every
+//     slot are staged in shared memory; velocities and the 12 covariance terms of a slot are NOT
+//     needed for association (ByteTrack costs only use boxes), so each thread loads them straight
+//     into registers at the single deferred predict+update point and keeps them there until the
+//     final write;
+//   * candidate pairs come from per-frame cell masks (48 x-cells and 24 y-cells, each a
 //     bitmask of the detections whose box touches the cell): a track runs the exact IoU test
 //     only against detections sharing a cell range with it in both axes - nothing T x D is
 //     ever computed, let alone written to HBM;

@@ -15,9 +15,10 @@
 // Unlike ByteTrack the assignment is DENSE: lapjv is called without a cost limit on
 // -(similarity + angle cost), every min(D, T) row is matched and pairs are filtered by the
 // similarity threshold afterwards, so nothing can be pruned.  The D x T cost matrix of a stream
-// is written once to a per-stream scratch block (L2 resident) while the column minima are
-// accumulated, then solved by lap_dense.cuh.  Slots are updated in place; a tracker that dies
-// leaves a hole and the stream is compacted only when its slot range runs short.
+// is written once to a per-stream scratch block (L2 resident), one warp per detection row with
+// the row minimum reduced in registers, then solved by lap_dense.cuh.  Slots are updated in
+// place; a tracker that dies leaves a hole and the stream is compacted only when its slot range
+// runs short.
 #include "boxes.cuh"
 #include "lap_dense.cuh"
 #include "layout.h"
