@@ -196,6 +196,15 @@ int b200track_appearance_cost(int32_t batch, int32_t n_tracks, int32_t n_dets, i
 int b200track_lapjv(int32_t batch, int32_t rows, int32_t cols, const double* d_cost, double cost_limit,
                     int32_t* d_x, int32_t* d_y, void* stream);
 
+/* b200track_linear_sum_assignment <- scipy.optimize.linear_sum_assignment as called by StrongSORT
+ *     (strongsort/sort/linear_assignment.py:59-61), bit-faithful including exactly tied costs (the clipped matrix is
+ *     mostly one repeated value and the tie behaviour decides the order of `unmatched_detections`): `batch` problems
+ *     cost[batch, rows, cols] -> d_col4row[batch, min(rows, cols)]: the assignment of the internal problem, which is
+ *     the transposed one when rows > cols exactly like scipy; (row_ind, col_ind) = (arange, col4row) or, transposed,
+ *     (col4row[argsort(col4row)], argsort(col4row)).  *d_err |= 1 when a problem is infeasible (inf / nan). */
+int b200track_linear_sum_assignment(int32_t batch, int32_t rows, int32_t cols, const double* d_cost,
+                                    int32_t* d_col4row, int32_t* d_err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

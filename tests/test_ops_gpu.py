@@ -250,3 +250,32 @@ def test_gate_cost_matrix_and_fuse_motion(only_position):
     assert np.array_equal(np.isinf(got), np.isinf(ref_fuse))
     assert_close(got[np.isfinite(got)], ref_fuse[np.isfinite(ref_fuse)], what="fuse_motion")
     assert matching.gate_cost_matrix(kf, np.zeros((0, 3)), [], dets[:3]).shape == (0, 3)
+
+
+def test_linear_sum_assignment_is_bit_faithful_to_scipy_including_ties():
+    """StrongSORT's solver (strongsort/sort/linear_assignment.py:59-61): clipped matrices are mostly one repeated value,
+    and scipy's tie behaviour decides the order of the unmatched lists.  Same (row_ind, col_ind) as scipy on tie-heavy,
+    constant, integer, tall and wide matrices."""
+    from scipy.optimize import linear_sum_assignment as scipy_lsa
+    from yolo_tracking_b200 import _ops
+    rng = np.random.default_rng(0)
+    for shape in [(1, 1), (3, 7), (7, 3), (12, 12), (40, 55), (55, 40), (130, 200), (200, 130)]:
+        mats = []
+        for kind in range(4):
+            c = rng.random((3,) + shape)
+            if kind == 1:
+                c[c > 0.25] = 0.25 + 1e-5                  # min_cost_matching's clipping
+            elif kind == 2:
+                c = rng.integers(0, 3, (3,) + shape).astype(np.float64)
+            elif kind == 3:
+                c = np.full((3,) + shape, 0.7)
+            mats.append(c)
+        cost = np.concatenate(mats, axis=0)
+        got = _ops.linear_sum_assignment(cost)
+        for b in range(len(cost)):
+            a, c = scipy_lsa(cost[b])
+            assert np.array_equal(got[b][0], a) and np.array_equal(got[b][1], c), (shape, b)
+    a, c = _ops.linear_sum_assignment(np.zeros((0, 4)))
+    assert len(a) == 0 and len(c) == 0
+    with pytest.raises(ValueError):
+        _ops.linear_sum_assignment(np.full((2, 2), np.inf))

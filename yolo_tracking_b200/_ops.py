@@ -175,6 +175,36 @@ def appearance_cost(trk, det, scale=0.5, thresh=0.25, fill=1.0, gate=None, retur
     return (res, int(st[0])) if return_stats else res
 
 
+def linear_sum_assignment(cost):
+    """scipy.optimize.linear_sum_assignment (minimisation), bit-faithful including ties: cost [R, C] -> (row_ind, col_ind),
+    or [B, R, C] -> list of such pairs."""
+    lib = _lib.load()
+    torch = _torch()
+    cost = np.asarray(cost, dtype=np.float64)
+    single = cost.ndim == 2
+    c3 = cost[None] if single else cost
+    B, R, Cc = c3.shape
+    n = min(R, Cc)
+    res = []
+    if n == 0:
+        res = [(np.empty(0, dtype=np.int64), np.empty(0, dtype=np.int64)) for _ in range(B)]
+    else:
+        dc = _dev(c3, np.float64)
+        out = torch.full((B, n), -1, dtype=torch.int32, device=dc.device)
+        err = torch.zeros((1,), dtype=torch.int32, device=dc.device)
+        _sync_check(lib.b200track_linear_sum_assignment(B, R, Cc, _p(dc), _p(out), _p(err), None))
+        if int(err.item()):
+            raise ValueError("cost matrix is infeasible")
+        c4r = out.cpu().numpy().astype(np.int64)
+        for b in range(B):
+            if Cc < R:                                    # scipy solved the transposed problem
+                order = np.argsort(c4r[b], kind="stable")
+                res.append((c4r[b][order], order))
+            else:
+                res.append((np.arange(R, dtype=np.int64), c4r[b]))
+    return res[0] if single else res
+
+
 def lapjv(cost, cost_limit=np.inf):
     """cost [R, C] or [B, R, C] -> x [.., R], y [.., C] (int32, -1 = unmatched)."""
     lib = _lib.load()
