@@ -38,3 +38,18 @@ def botsort_scenario(name):
     assert np.array_equal(nd, g["ndets"]) and np.allclose([dets.sum(), float(np.abs(feats).sum())], g["dets_sum"], rtol=1e-12), \
         "synthetic inputs drifted from the ones the golden was generated on"
     return sc, cfg, dets, nd, feats, g
+
+
+def strongsort_scenario(name):
+    import sys
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    from scenarios import STRONGSORT_SCENARIOS, STRONGSORT_YAML, strongsort_inputs
+    sc = STRONGSORT_SCENARIOS[name]
+    cfg = dict(STRONGSORT_YAML)
+    cfg.update(sc["params"])
+    dets, nd, _, feats = strongsort_inputs(sc)
+    g = load_golden(name)
+    assert np.array_equal(nd, g["ndets"]) and np.allclose([dets.sum(), float(np.abs(feats).sum())], g["dets_sum"], rtol=1e-12), \
+        "synthetic inputs drifted from the ones the golden was generated on"
+    return sc, cfg, dets, nd, feats, g

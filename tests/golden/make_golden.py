@@ -248,7 +248,8 @@ def gen_ocsort():
 
 
 # ----------------------------------------------------------------------------- BoT-SORT
-from scenarios import BOTSORT_SCENARIOS, BOTSORT_YAML, botsort_inputs  # noqa: E402
+from scenarios import (BOTSORT_SCENARIOS, BOTSORT_YAML, STRONGSORT_SCENARIOS, STRONGSORT_YAML, botsort_inputs,  # noqa: E402
+                       strongsort_inputs)
 
 
 def _bs_snapshot(trk):
@@ -341,8 +342,42 @@ def gen_mot():
     _save("mot17_mini", **out)
 
 
+# ----------------------------------------------------------------------------- StrongSORT
+def gen_strongsort():
+    rh.install()
+    from boxmot.trackers.strongsort.strong_sort import StrongSORT
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    for name, sc in STRONGSORT_SCENARIOS.items():
+        dets, nd, embs, feats = strongsort_inputs(sc)
+        cfg = dict(STRONGSORT_YAML)
+        cfg.update(sc["params"])
+        trk = StrongSORT(None, "cpu", False, **cfg)
+        trk.cmc = rh.IdentityCMC()
+        outs, recs, means, covs, cov_frames = [], [], [], [], []
+        for f in range(sc["n_frames"]):
+            if nd[f]:
+                rh.FakeReID.queue.append(embs[f, :nd[f]])
+            o = trk.update(dets[f, :nd[f]], img)
+            outs.append(o)
+            ts = trk.tracker.tracks
+            recs.append(np.array([[t.id, t.state, t.hits, t.age, t.time_since_update, len(trk.tracker.metric.samples.get(t.id, []))]
+                                  for t in ts], dtype=np.int32).reshape(-1, 6))
+            means.append(np.stack([t.mean for t in ts]) if ts else np.zeros((0, 8)))
+            if f % 10 == 9 or f == sc["n_frames"] - 1:
+                covs.append(np.stack([t.covariance.reshape(64) for t in ts]) if ts else np.zeros((0, 64)))
+                cov_frames.append(f)
+        assert not rh.FakeReID.queue
+        ts = trk.tracker.tracks
+        final_feat = np.stack([t.features[-1] for t in ts]).astype(np.float32) if ts else np.zeros((0, sc["emb_dim"]), dtype=np.float32)
+        out_flat, out_offs = _ragged(outs, 8)
+        rec_flat, rec_offs = _ragged(recs, 6)
+        _save(name, ndets=nd, dets_sum=np.array([dets.sum(), float(np.abs(feats).sum())]), out=out_flat, out_offs=out_offs,
+              rec=rec_flat.astype(np.int32), rec_offs=rec_offs, mean=_ragged(means, 8)[0], cov=_ragged(covs, 64)[0],
+              cov_frames=np.array(cov_frames, dtype=np.int32), final_feat=final_feat)
+
+
 GENERATORS = {"kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
-              "mot": gen_mot}
+              "mot": gen_mot, "strongsort": gen_strongsort}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(GENERATORS)

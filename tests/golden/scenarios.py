@@ -46,3 +46,25 @@ BOTSORT_SCENARIOS = {
     "botsort_noreid": dict(stream=904, n_objects=25, n_frames=120, emb_dim=32, kw=dict(miss_prob=0.15, fp_rate=2.0),
                            params=dict(with_reid=False)),
 }
+
+
+# ----------------------------------------------------------------------------- StrongSORT
+STRONGSORT_YAML = dict(max_dist=0.2, max_iou_dist=0.7, max_age=30, n_init=1, nn_budget=100, mc_lambda=0.995,
+                       ema_alpha=0.8)                               # boxmot/configs/strongsort.yaml
+STRONGSORT_SCENARIOS = {
+    "strongsort_c4": dict(stream=0, n_objects=25, n_frames=120, emb_dim=128, kw={}, params={}),
+    # misses and false positives, short memory, confirmation after 3 hits, small gallery
+    "strongsort_churn": dict(stream=906, n_objects=16, n_frames=200, emb_dim=64, kw=dict(miss_prob=0.3, fp_rate=3.0),
+                             params=dict(max_age=8, n_init=3, nn_budget=5, ema_alpha=0.9)),
+}
+
+
+def strongsort_inputs(sc):
+    """dets[F, D, 6], ndets[F], raw embeddings, seam features (every detection row / Frobenius norm of the frame's matrix)."""
+    dets, nd, embs = make_stream(4, sc["stream"], sc["n_objects"], sc["n_frames"], emb_dim=sc["emb_dim"], **sc["kw"])
+    feats = np.zeros_like(embs)
+    for f in range(sc["n_frames"]):
+        if nd[f]:
+            raw = embs[f, :nd[f]]
+            feats[f, :nd[f]] = raw / np.linalg.norm(raw)
+    return dets, nd, embs, feats

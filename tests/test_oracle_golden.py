@@ -204,3 +204,33 @@ def test_botsort_oracle_replays_reference(name):
         assert np.array_equal(s["smooth_feat"], g["final_feat"])       # same numpy float32 operations -> same bits
     if sc.get("classes"):
         assert len(np.unique(g["aux"][:, 1])) > 1
+
+
+# ----------------------------------------------------------------------------- StrongSORT
+@pytest.mark.parametrize("name", ["strongsort_c4", "strongsort_churn"])
+def test_strongsort_oracle_replays_reference(name):
+    from _util import strongsort_scenario
+    from oracle.strongsort import StrongSORTOracle
+    sc, cfg, dets, nd, feats, g = strongsort_scenario(name)
+    trk = StrongSORTOracle(**cfg)
+    cov_frames = {int(f): k for k, f in enumerate(g["cov_frames"])}
+    cov_offs = [0]
+    for f in g["cov_frames"]:
+        cov_offs.append(cov_offs[-1] + int(g["rec_offs"][f + 1] - g["rec_offs"][f]))
+    for f in range(sc["n_frames"]):
+        out = trk.update(dets[f, :nd[f]], feats[f, :nd[f]])
+        ref = g["out"][g["out_offs"][f]:g["out_offs"][f + 1]]
+        assert out.reshape(-1, 8).shape == ref.shape, f"frame {f}"
+        if ref.size:
+            assert np.array_equal(out[:, 4:], ref[:, 4:]), f"frame {f}: id/conf/cls/det_ind"
+            assert_close(out[:, :4], ref[:, :4], what=f"frame {f} boxes")
+        s = trk.snapshot()
+        lo, hi = g["rec_offs"][f], g["rec_offs"][f + 1]
+        mine = np.stack([s["track_id"], s["state"], s["hits"], s["age"], s["time_since_update"], s["gallery"]], axis=1).reshape(-1, 6)
+        assert np.array_equal(mine, g["rec"][lo:hi]), f"frame {f}: track records"
+        assert_close(s["mean"], g["mean"][lo:hi], what=f"frame {f} mean")
+        if f in cov_frames:
+            k = cov_frames[f]
+            assert_close(s["cov"].reshape(-1, 64), g["cov"][cov_offs[k]:cov_offs[k + 1]], abs_=1e-10, what=f"frame {f} cov")
+    assert np.array_equal(s["feature"], g["final_feat"])
+    assert len(np.unique(g["rec"][:, 1])) >= 2
