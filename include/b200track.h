@@ -196,6 +196,11 @@ int b200track_appearance_cost(int32_t batch, int32_t n_tracks, int32_t n_dets, i
 int b200track_lapjv(int32_t batch, int32_t rows, int32_t cols, const double* d_cost, double cost_limit,
                     int32_t* d_x, int32_t* d_y, void* stream);
 
+/* b200track_nn_cosine_distance <- NearestNeighborDistanceMetric.distance, cosine metric (matching.py:247-308, :360-378):
+ *     out[t, d] = min over the gallery rows [d_seg[t], d_seg[t+1]) of track t of 1 - a_hat . b_hat, float32 arithmetic
+ *     like the reference; d_gallery [d_seg[n_tracks], dim], d_det [n_dets, dim] fp32 -> d_out [n_tracks, n_dets] fp64. */
+int b200track_nn_cosine_distance(int32_t n_tracks, int32_t n_dets, int32_t dim, const float* d_gallery, const int32_t* d_seg,
+                                 const float* d_det, double* d_out, void* stream);
 /* b200track_linear_sum_assignment <- scipy.optimize.linear_sum_assignment as called by StrongSORT
  *     (strongsort/sort/linear_assignment.py:59-61), bit-faithful including exactly tied costs (the clipped matrix is
  *     mostly one repeated value and the tie behaviour decides the order of `unmatched_detections`): `batch` problems

@@ -8,7 +8,7 @@ __version__ = "0.1.0"
 
 from .tracker_zoo import create_tracker, get_tracker_config  # noqa: E402,F401
 
-TRACKERS = ["bytetrack", "botsort", "ocsort"]
+TRACKERS = ["bytetrack", "botsort", "ocsort", "strongsort"]
 
 
 def __getattr__(name):          # lazy: BYTETracker / OCSORT / BoTSORT / BatchedTracker
@@ -21,11 +21,14 @@ def __getattr__(name):          # lazy: BYTETracker / OCSORT / BoTSORT / Batched
     if name == "BoTSORT":
         from .trackers.botsort import BoTSORT
         return BoTSORT
+    if name == "StrongSORT":
+        from .trackers.strongsort import StrongSORT
+        return StrongSORT
     if name == "BatchedTracker":
         from .batch import BatchedTracker
         return BatchedTracker
     raise AttributeError(name)
 
 
-__all__ = ("__version__", "BYTETracker", "OCSORT", "BoTSORT", "BatchedTracker", "create_tracker",
+__all__ = ("__version__", "BYTETracker", "OCSORT", "BoTSORT", "StrongSORT", "BatchedTracker", "create_tracker",
            "get_tracker_config", "TRACKERS")

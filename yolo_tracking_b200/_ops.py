@@ -175,6 +175,24 @@ def appearance_cost(trk, det, scale=0.5, thresh=0.25, fill=1.0, gate=None, retur
     return (res, int(st[0])) if return_stats else res
 
 
+def nn_cosine_distance(galleries, det_feats):
+    """galleries: list (one per track) of [n_t, F] float32 arrays; det_feats [D, F] -> cost [T, D] float64
+    (NearestNeighborDistanceMetric.distance, matching.py:360-378)."""
+    lib = _lib.load()
+    torch = _torch()
+    T, det = len(galleries), np.asarray(det_feats, dtype=np.float32)
+    D = det.shape[0]
+    if T == 0 or D == 0:
+        return np.zeros((T, D))
+    seg = np.zeros(T + 1, dtype=np.int32)
+    seg[1:] = np.cumsum([len(g) for g in galleries])
+    gal = _dev(np.concatenate([np.asarray(g, dtype=np.float32).reshape(-1, det.shape[1]) for g in galleries], axis=0), np.float32)
+    dseg, ddet = _dev(seg, np.int32), _dev(det, np.float32)
+    out = torch.empty((T, D), dtype=torch.float64, device=ddet.device)
+    _sync_check(lib.b200track_nn_cosine_distance(T, D, det.shape[1], _p(gal), _p(dseg), _p(ddet), _p(out), None))
+    return out.cpu().numpy()
+
+
 def linear_sum_assignment(cost):
     """scipy.optimize.linear_sum_assignment (minimisation), bit-faithful including ties: cost [R, C] -> (row_ind, col_ind),
     or [B, R, C] -> list of such pairs."""

@@ -395,6 +395,31 @@ __global__ void __launch_bounds__(256) lapjv_dense_kernel(int rows, int cols, co
     for (int j = tid; j < cols; j += NT) y[(size_t)blockIdx.x * cols + j] = w.yc[j];
 }
 
+// NearestNeighborDistanceMetric.distance with the cosine metric (matching.py:247-308, :360-378): per track the smallest
+// 1 - a_hat . b_hat over its gallery rows, float32 arithmetic like the reference (its np.dot is a float32 BLAS call, so
+// the last bits depend on the summation order on both sides).  One thread per (track, detection).
+__global__ void __launch_bounds__(128) nn_cosine_kernel(int T, int D, int dim, const float* __restrict__ gal, const int* __restrict__ seg,
+                                                        const float* __restrict__ det, double* __restrict__ out) {
+    const int idx = blockIdx.x * 128 + threadIdx.x;
+    if (idx >= T * D) return;
+    const int t = idx / D, d = idx - t * D;
+    const float* b = det + (size_t)d * dim;
+    float nb = 0.f;
+    for (int i = 0; i < dim; ++i) nb = fmaf(b[i], b[i], nb);
+    nb = sqrtf(nb);
+    float best = __int_as_float(0x7f800000);
+    for (int g = seg[t]; g < seg[t + 1]; ++g) {
+        const float* a = gal + (size_t)g * dim;
+        float na = 0.f;
+        for (int i = 0; i < dim; ++i) na = fmaf(a[i], a[i], na);
+        na = sqrtf(na);
+        float dot = 0.f;
+        for (int i = 0; i < dim; ++i) dot = fmaf(__fdiv_rn(a[i], na), __fdiv_rn(b[i], nb), dot);
+        best = fminf(best, 1.0f - dot);
+    }
+    out[idx] = (double)best;
+}
+
 template <class F>
 int dispatch_kind(int kind, F&& f) {
     switch (kind) {
@@ -516,6 +541,16 @@ extern "C" int b200track_embedding_distance(int32_t n, int32_t m, int32_t dim, c
     if (n == 0 || m == 0) return 0;
     dim3 grid((m + ED_TILE - 1) / ED_TILE, (n + ED_TILE - 1) / ED_TILE);
     embedding_distance_kernel<<<grid, ED_TILE * ED_TILE, 0, (cudaStream_t)st>>>(n, m, dim, a, b, out);
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_nn_cosine_distance(int32_t n_tracks, int32_t n_dets, int32_t dim, const float* gallery, const int32_t* seg,
+                                            const float* det, double* out, void* st) {
+    if (n_tracks < 0 || n_dets < 0 || dim <= 0 || !seg || !out) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n_tracks == 0 || n_dets == 0) return 0;
+    if (!gallery || !det) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    const int total = n_tracks * n_dets;
+    nn_cosine_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)st>>>(n_tracks, n_dets, dim, gallery, seg, det, out);
     LAUNCH_CHECK();
     return 0;
 }

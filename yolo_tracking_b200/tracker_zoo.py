@@ -39,4 +39,8 @@ def create_tracker(tracker_type, tracker_config, reid_weights=None, device=0, ha
                        track_buffer=cfg.track_buffer, match_thresh=cfg.match_thresh,
                        proximity_thresh=cfg.proximity_thresh, appearance_thresh=cfg.appearance_thresh,
                        cmc_method=cfg.cmc_method, frame_rate=cfg.frame_rate, **capacity)
-    raise ValueError(f"No such tracker: {tracker_type!r} (built: bytetrack, ocsort, botsort)")
+    if tracker_type == "strongsort":
+        from .trackers.strongsort import StrongSORT
+        return StrongSORT(reid_weights, device, half, max_dist=cfg.max_dist, max_iou_dist=cfg.max_iou_dist, max_age=cfg.max_age,
+                          n_init=cfg.n_init, nn_budget=cfg.nn_budget, mc_lambda=cfg.mc_lambda, ema_alpha=cfg.ema_alpha, **capacity)
+    raise ValueError(f"No such tracker: {tracker_type!r} (built: bytetrack, ocsort, botsort, strongsort)")

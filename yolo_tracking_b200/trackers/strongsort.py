@@ -1,0 +1,198 @@
+"""StrongSORT with the reference's constructor and update() contract
+(boxmot/trackers/strongsort/strong_sort.py:13-99), one stream per object like the reference.
+
+Unlike ByteTrack / OC-SORT / BoT-SORT this tracker is not (yet) one fused kernel: the host logic of
+strongsort/sort/tracker.py (track list, confirmation, the two matching rounds and their Python list / set
+orders, which leak into the track ids) runs in Python exactly as in the reference, and every numeric step
+goes through the CUDA operator kernels of the C-ABI:
+  Kalman predict / update with confidence-scaled noise  b200track_kf_predict / _kf_update (strongsort_kf.py:88-189)
+  gallery cosine distance                               b200track_nn_cosine_distance     (matching.py:247-378)
+  Mahalanobis gate + motion fusion                      b200track_gate_cost              (linear_assignment.py:144-200)
+  IoU cost                                              b200track_iou_distance           (iou_matching.py:50-87)
+  assignment on the clipped matrix                      b200track_linear_sum_assignment  (linear_assignment.py:59-61),
+                                                        bit-faithful to scipy including ties.
+The ReID network and the ECC camera-motion estimator are out of scope (BASELINE.json): embeddings come from a
+`model` object with get_features(xyxys, img) or from `update(..., feats=...)`; the warp is the identity.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .. import _lib, _ops
+from .bytetrack import _SingleStreamTracker, _device_index
+
+TENTATIVE, CONFIRMED, DELETED = 1, 2, 3
+KIND = _lib.KF_XYAH_CONF
+INFTY_COST = 1e5
+
+
+class _Track:
+    __slots__ = ("id", "conf", "cls", "det_ind", "hits", "age", "time_since_update", "state", "feature", "mean", "covariance")
+
+    def to_tlwh(self):
+        ret = self.mean[:4].copy()
+        ret[2] *= ret[3]
+        ret[:2] -= ret[2:] / 2
+        return ret
+
+    def to_tlbr(self):
+        ret = self.to_tlwh()
+        ret[2:] = ret[:2] + ret[2:]
+        return ret
+
+
+class StrongSORT:
+    def __init__(self, model_weights=None, device=0, fp16=False, max_dist=0.2, max_iou_dist=0.7, max_age=30, n_init=1,
+                 nn_budget=100, mc_lambda=0.995, ema_alpha=0.9, model=None, **_capacity):
+        self.device = _device_index(device)
+        self.max_dist, self.max_iou_dist, self.max_age, self.n_init = max_dist, max_iou_dist, max_age, n_init
+        self.nn_budget, self.mc_lambda, self.ema_alpha = nn_budget, mc_lambda, ema_alpha
+        self.model = model
+        self.tracks: list[_Track] = []
+        self.samples: dict = {}
+        self._next_id = 1
+        _lib.load()
+        _ops._torch()                                   # fail loudly without a CUDA device: there is no CPU path
+
+    # ------------------------------------------------------------------ matching (linear_assignment.py:14-79)
+    def _min_cost_matching(self, cost_fn, max_distance, track_idx, det_idx):
+        if len(det_idx) == 0 or len(track_idx) == 0:
+            return [], track_idx, det_idx
+        cost = cost_fn(track_idx, det_idx)
+        cost[cost > max_distance] = max_distance + 1e-5
+        rows, cols = _ops.linear_sum_assignment(cost)
+        rows, cols = rows.tolist(), cols.tolist()
+        matches, ut, ud = [], [], []
+        colset, rowset = set(cols), set(rows)
+        for col, d in enumerate(det_idx):
+            if col not in colset:
+                ud.append(d)
+        for row, t in enumerate(track_idx):
+            if row not in rowset:
+                ut.append(t)
+        for row, col in zip(rows, cols):
+            t, d = track_idx[row], det_idx[col]
+            if cost[row, col] > max_distance:
+                ut.append(t)
+                ud.append(d)
+            else:
+                matches.append((t, d))
+        return matches, ut, ud
+
+    def update(self, dets, img, feats=None):
+        _SingleStreamTracker._check(dets)
+        assert isinstance(img, np.ndarray) or img is None or isinstance(img, tuple), "Unsupported 'img' input format"
+        dets = np.asarray(dets, dtype=np.float64)
+        n = len(dets)
+        if feats is None:
+            if n and self.model is None:
+                raise ValueError("StrongSORT needs `feats` or a `model` with get_features(xyxys, img)")
+            feats = self.model.get_features(dets[:, 0:4], img) if n else np.zeros((0, 1), dtype=np.float32)
+        # private copy: a new track normalises its row in place
+        feats = np.array(feats, dtype=np.float32).reshape(n, -1) if n else np.zeros((0, 1), dtype=np.float32)
+        tracks = self.tracks
+        # camera_update with the identity warp (track.py:129-138) - not an exact no-op in floating point
+        for t in tracks:
+            x1, y1, x2, y2 = t.to_tlbr()
+            w, h = x2 - x1, y2 - y1
+            t.mean[:4] = [x1 + w / 2, y1 + h / 2, w / h, h]
+        tlwh = dets[:, :4].copy()
+        tlwh[:, 2] = dets[:, 2] - dets[:, 0]
+        tlwh[:, 3] = dets[:, 3] - dets[:, 1]
+        xyah = tlwh.copy()
+        xyah[:, :2] += xyah[:, 2:] / 2
+        xyah[:, 2] /= xyah[:, 3]
+        # Tracker.predict (tracker.py:59-66)
+        if tracks:
+            mean, cov = _ops.kf_predict(KIND, np.stack([t.mean for t in tracks]), np.stack([t.covariance for t in tracks]))
+            for k, t in enumerate(tracks):
+                t.mean, t.covariance = mean[k], cov[k]
+                t.age += 1
+                t.time_since_update += 1
+
+        def gated_metric(track_idx, det_idx):
+            cost = _ops.nn_cosine_distance([self.samples[tracks[k].id] for k in track_idx], feats[det_idx])
+            cost = _ops.gate_cost(KIND, cost, np.stack([tracks[k].mean for k in track_idx]),
+                                  np.stack([tracks[k].covariance for k in track_idx]), xyah[det_idx], False, fuse=True,
+                                  lambda_=self.mc_lambda)
+            cost[np.isinf(cost)] = INFTY_COST               # the reference gates with 1e5, not inf; both clip to the same value
+            return cost
+
+        def iou_metric(track_idx, det_idx):
+            boxes_t = np.stack([tracks[k].to_tlbr() for k in track_idx])
+            boxes_d = np.concatenate([tlwh[det_idx, :2], tlwh[det_idx, :2] + tlwh[det_idx, 2:]], axis=1)
+            cost = _ops.iou_distance(boxes_t, boxes_d)
+            for r, k in enumerate(track_idx):
+                if tracks[k].time_since_update > 1:
+                    cost[r, :] = INFTY_COST
+            return cost
+
+        # Tracker._match (tracker.py:104-155)
+        confirmed = [i for i, t in enumerate(tracks) if t.state == CONFIRMED]
+        unconfirmed = [i for i, t in enumerate(tracks) if t.state != CONFIRMED]
+        m_a, _, ud = self._min_cost_matching(gated_metric, self.max_dist, list(confirmed), list(range(n)))
+        ut_a = list(set(confirmed) - set(k for k, _ in m_a))            # linear_assignment.py:141 (CPython set order)
+        cand = unconfirmed + [k for k in ut_a if tracks[k].time_since_update == 1]
+        ut_a = [k for k in ut_a if tracks[k].time_since_update != 1]
+        m_b, ut_b, ud = self._min_cost_matching(iou_metric, self.max_iou_dist, cand, ud)
+        matches = m_a + m_b
+        unmatched_tracks = list(set(ut_a + ut_b))
+
+        # Tracker.update (tracker.py:73-102)
+        if matches:
+            ks = [k for k, _ in matches]
+            ds = [d for _, d in matches]
+            mean, cov = _ops.kf_update(KIND, np.stack([tracks[k].mean for k in ks]), np.stack([tracks[k].covariance for k in ks]),
+                                       xyah[ds], dets[ds, 4])
+            for i, (k, d) in enumerate(matches):
+                t = tracks[k]
+                t.mean, t.covariance = mean[i], cov[i]
+                t.conf, t.cls, t.det_ind = dets[d, 4], dets[d, 5], float(d)
+                f = feats[d] / np.linalg.norm(feats[d])                # track.py:166-172, float32
+                smooth = self.ema_alpha * t.feature + (1 - self.ema_alpha) * f
+                smooth /= np.linalg.norm(smooth)
+                t.feature = smooth
+                t.hits += 1
+                t.time_since_update = 0
+                if t.state == TENTATIVE and t.hits >= self.n_init:
+                    t.state = CONFIRMED
+        for k in unmatched_tracks:
+            t = tracks[k]
+            if t.state == TENTATIVE or t.time_since_update > self.max_age:
+                t.state = DELETED
+        if ud:
+            mean, cov = _ops.kf_initiate(KIND, xyah[ud])
+            for i, d in enumerate(ud):
+                t = _Track()
+                t.id = self._next_id
+                self._next_id += 1
+                t.conf, t.cls, t.det_ind = dets[d, 4], dets[d, 5], float(d)
+                t.hits, t.age, t.time_since_update, t.state = 1, 1, 0, TENTATIVE
+                feats[d] /= np.linalg.norm(feats[d])
+                t.feature = feats[d]
+                t.mean, t.covariance = mean[i], cov[i]
+                tracks.append(t)
+        self.tracks = tracks = [t for t in tracks if t.state != DELETED]
+        # NearestNeighborDistanceMetric.partial_fit (matching.py:343-358)
+        active = [t.id for t in tracks if t.state == CONFIRMED]
+        for t in tracks:
+            if t.state == CONFIRMED:
+                g = self.samples.setdefault(t.id, [])
+                g.append(t.feature)
+                if self.nn_budget is not None:
+                    self.samples[t.id] = g[-self.nn_budget:]
+        self.samples = {k: self.samples[k] for k in active}
+        rows = [np.concatenate((t.to_tlbr(), [t.id], [t.conf], [t.cls], [t.det_ind])).reshape(1, -1)
+                for t in tracks if t.state == CONFIRMED and t.time_since_update < 1]
+        return np.concatenate(rows) if rows else np.array([])
+
+    def state(self):
+        ts = self.tracks
+        n = len(ts)
+        return dict(track_id=np.array([t.id for t in ts], dtype=np.int32), state=np.array([t.state for t in ts], dtype=np.int32),
+                    hits=np.array([t.hits for t in ts], dtype=np.int32), age=np.array([t.age for t in ts], dtype=np.int32),
+                    time_since_update=np.array([t.time_since_update for t in ts], dtype=np.int32),
+                    mean=np.stack([t.mean for t in ts]) if n else np.zeros((0, 8)),
+                    cov=np.stack([t.covariance for t in ts]) if n else np.zeros((0, 8, 8)),
+                    gallery=np.array([len(self.samples.get(t.id, [])) for t in ts], dtype=np.int32),
+                    feature=np.stack([t.feature for t in ts]) if n else np.zeros((0, 0), dtype=np.float32))
