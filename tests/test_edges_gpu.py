@@ -152,3 +152,33 @@ def test_reset_pipelined_and_device_apis_agree():
         assert np.array_equal(o[s, :n[s]], ref[F - 1][s]), s
     trk.sync()
     trk.close()
+
+
+@pytest.mark.parametrize("scale, cap", [(0.08, 64), (0.2, 64), (0.35, 64), (0.1, 224), (0.25, 224)])
+def test_crowded_scenes_overflow_the_pair_and_edge_caches(scale, cap):
+    """Objects squeezed into a corner of the canvas: every box overlaps many others, so the candidate pair list and / or
+    the edge cache of the step kernel overflow and the solver runs on the bitmask form of the graph with recomputed
+    costs (large connected components, general shortest-augmenting-path solver).  Results must still equal the oracle's."""
+    from oracle.bytetrack import ByteTrackOracle
+    from yolo_tracking_b200.batch import BatchedTracker
+    from yolo_tracking_b200.synth import make_batch
+    n_obj = 40 if cap == 64 else 150
+    dets, nd, _ = make_batch(7, 2, n_obj, 25, dmax=cap, fp_rate=0.5)
+    dets = dets.copy()
+    ctr = 0.5 * (dets[..., :2] + dets[..., 2:4])
+    half = 0.5 * (dets[..., 2:4] - dets[..., :2])
+    dets[..., :2] = ctr * scale - half                  # centres pulled together, sizes kept
+    dets[..., 2:4] = ctr * scale + half
+    dets[np.arange(cap)[None, None, :] >= nd[:, :, None]] = 0.0
+    trk = BatchedTracker("bytetrack", 2, max_tracks=cap, max_dets=cap, track_thresh=0.5, match_thresh=0.8, track_buffer=30,
+                         frame_rate=30)
+    oracles = [ByteTrackOracle(0.5, 0.8, 30, 30) for _ in range(2)]
+    for f in range(25):
+        out, nout = trk.update_batch(np.ascontiguousarray(dets[f]), np.ascontiguousarray(nd[f]))
+        for s in range(2):
+            ref = oracles[s].update(dets[f, s, :nd[f, s]], None).reshape(-1, 8)
+            o = out[s, :nout[s]]
+            assert o.shape == ref.shape, f"frame {f} stream {s}"
+            assert np.array_equal(o[:, 4:], ref[:, 4:]), f"frame {f} stream {s}: ids"
+            assert_close(o[:, :4], ref[:, :4], what=f"frame {f} stream {s} boxes")
+    trk.close()

@@ -49,13 +49,11 @@ constexpr int DF_HIGH = 1, DF_LOW = 2, DF_USED = 4;
 
 constexpr int CAT_NONE = 0, CAT_KEEP = 1, CAT_REFOUND = 2, CAT_LOST_OLD = 3, CAT_LOST_NEW = 4;
 
-#ifndef B200_NCX
-#define B200_NCX 48
-#endif
-#ifndef B200_NCY
-#define B200_NCY 24
-#endif
-constexpr int NCX = B200_NCX, NCY = B200_NCY;   // cells per axis of the candidate masks
+// Cells per axis of the candidate masks.  A detection covers the cell range [c0, c1] of an axis; instead of one mask
+// per cell, two monotone families are kept per axis: lo[c] = detections with c0 <= c, hi[c] = detections with
+// c1 >= c.  A track covering [t0, t1] then meets exactly lo[t1] & hi[t0]: two loads per axis whatever the range.
+// NCX = 32 = one warp transpose per family; the two 16-cell y families share one transpose.
+constexpr int NCX = 32, NCY = 16;
 
 // row types of one association pass: which detection set / limit / cost a row uses
 constexpr int RT_NONE = 0, RT_A = 1, RT_B = 2;
@@ -86,20 +84,20 @@ struct alignas(16) StepSmem {
     double dbox[4][DMAX];                             // raw x1, y1, x2, y2
     double dconf[DMAX];
     double u[TMAX], v[DMAX], dist[DMAX];
-    unsigned long long scratch[40];
+    unsigned long long scratch[32];
     int frame_t[TMAX], start_t[TMAX];
     int parent[TMAX + DMAX], head[TMAX], coldeg[DMAX], ncomplex[4];
     uint32_t adj[DW][TMAX];
     uint32_t colbitsA[DWP], colbitsB[DWP];
-    uint32_t xmask[NCX][DWP], ymask[NCY][DWP];
-    float fext[32][4];
+    uint32_t xlo[NCX][DWP], xhi[NCX][DWP], ylo[NCY][DWP], yhi[NCY][DWP];
+    float fext[16][4];
     short rnext[TMAX], xr[TMAX], match[TMAX], lostlist[TMAX];
     short yc[DMAX], pred[DMAX], nextc[DMAX], mark[DMAX], scn[DMAX];
     // candidate edge cache (cost computed once, while the graph is built)
     static constexpr int ECAP = 2 * TMAX;
     double ecost[ECAP];
     short ecol[ECAP], enext[ECAP];
-    int ehead[TMAX], colxor[DMAX];
+    int ehead[TMAX];
     int ecount[4];
     // candidate pairs that passed the conservative fp32 overlap filter: (row << 16) | det
     static constexpr int PCAP = 4 * TMAX;
@@ -160,6 +158,18 @@ struct PassLimit {
     __device__ __forceinline__ double operator()(int t) const { return rowtype[t] == RT_A ? limA : limB; }
 };
 
+// 32 x 32 bit-matrix transpose across the lanes of a warp: lane r holds row r, afterwards lane c holds column c
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, int lane) {
+    uint32_t m = 0x0000ffffu;
+#pragma unroll
+    for (int j = 16; j; j >>= 1) {
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+        m ^= m << (j >> 1);
+    }
+    return x;
+}
+
 struct CellMap {
     float x0, y0, sx, sy;
     __device__ __forceinline__ int cx(double x) const {
@@ -181,51 +191,69 @@ struct CellMap {
 template <int KIND, class SM>
 __device__ __forceinline__ void graph_phase_a(SM& sm, int t, int n, int words, const CellMap& cm) {
     constexpr int DWP = SM::DWP;
-    if (t >= n) return;
-    for (int wd = 0; wd < words; ++wd) sm.adj[wd][t] = 0u;
-    const int rt = sm.rowtype[t];
-    if (rt == RT_NONE) return;
-    const Box a = track_box<KIND>(sm, t);
-    const float ax1 = __double2float_rd(a.x1), ay1 = __double2float_rd(a.y1);
-    const float ax2 = __double2float_ru(a.x2), ay2 = __double2float_ru(a.y2);
-    const int cx0 = cm.cx(a.x1), cx1 = cm.cx(a.x2), cy0 = cm.cy(a.y1), cy1 = cm.cy(a.y2);
-    const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
+    const int lane = threadIdx.x & 31;
+    const int rt = t < n ? sm.rowtype[t] : RT_NONE;
+    // survivors of the fp32 test stay in registers (four 16-bit detection ids) and are appended to the shared list
+    // with ONE atomic per warp after the walk; a fifth and later survivor (crowded spot) goes to the list directly
+    unsigned long long packed = 0ull;
+    int cnt = 0;
+    if (rt != RT_NONE) {
+        const Box a = track_box<KIND>(sm, t);
+        const float ax1 = __double2float_rd(a.x1), ay1 = __double2float_rd(a.y1);
+        const float ax2 = __double2float_ru(a.x2), ay2 = __double2float_ru(a.y2);
+        const int cx0 = cm.cx(a.x1), cx1 = cm.cx(a.x2), cy0 = cm.cy(a.y1), cy1 = cm.cy(a.y2);
+        const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
 #pragma unroll
-    for (int q = 0; q < DWP / 4; ++q) {
-        if (q * 4 >= words) break;
-        uint4 mx = make_uint4(0, 0, 0, 0), my = make_uint4(0, 0, 0, 0);
-        for (int c = cx0; c <= cx1; ++c) {
-            const uint4 m = *reinterpret_cast<const uint4*>(&sm.xmask[c][q * 4]);
-            mx.x |= m.x; mx.y |= m.y; mx.z |= m.z; mx.w |= m.w;
-        }
-        for (int c = cy0; c <= cy1; ++c) {
-            const uint4 m = *reinterpret_cast<const uint4*>(&sm.ymask[c][q * 4]);
-            my.x |= m.x; my.y |= m.y; my.z |= m.z; my.w |= m.w;
-        }
-        const uint4 cb = *reinterpret_cast<const uint4*>(&colbits[q * 4]);
-        uint32_t cand4[4] = {mx.x & my.x & cb.x, mx.y & my.y & cb.y, mx.z & my.z & cb.z, mx.w & my.w & cb.w};
+        for (int q = 0; q < DWP / 4; ++q) {
+            if (q * 4 >= words) break;
+            const uint4 xa = *reinterpret_cast<const uint4*>(&sm.xlo[cx1][q * 4]);
+            const uint4 xb = *reinterpret_cast<const uint4*>(&sm.xhi[cx0][q * 4]);
+            const uint4 ya = *reinterpret_cast<const uint4*>(&sm.ylo[cy1][q * 4]);
+            const uint4 yb = *reinterpret_cast<const uint4*>(&sm.yhi[cy0][q * 4]);
+            const uint4 cb = *reinterpret_cast<const uint4*>(&colbits[q * 4]);
+            const unsigned long long cand2[2] = {
+                (unsigned long long)(xa.x & xb.x & ya.x & yb.x & cb.x) | ((unsigned long long)(xa.y & xb.y & ya.y & yb.y & cb.y) << 32),
+                (unsigned long long)(xa.z & xb.z & ya.z & yb.z & cb.z) | ((unsigned long long)(xa.w & xb.w & ya.w & yb.w & cb.w) << 32)};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            uint32_t cand = cand4[k];
-            while (cand) {
-                const int b = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const int j = (q * 4 + k) * 32 + b;
-                const float4 d = sm.dboxf[j];
-                if (d.x < ax2 && ax1 < d.z && d.y < ay2 && ay1 < d.w) {
-                    const int pi = atomicAdd(&sm.npairs[0], 1);
-                    if (pi < SM::PCAP) sm.pairs[pi] = ((uint32_t)t << 16) | (uint32_t)j;
+            for (int k = 0; k < 2; ++k) {
+                unsigned long long cand = cand2[k];
+                while (cand) {
+                    const int j = (q * 2 + k) * 64 + __ffsll((long long)cand) - 1;
+                    cand &= cand - 1;
+                    const float4 d = sm.dboxf[j];
+                    if (d.x < ax2 && ax1 < d.z && d.y < ay2 && ay1 < d.w) {
+                        if (cnt < 4) packed |= (unsigned long long)j << (16 * cnt);
+                        else {
+                            const int pi = atomicAdd(&sm.npairs[0], 1);
+                            if (pi < SM::PCAP) sm.pairs[pi] = ((uint32_t)t << 16) | (uint32_t)j;
+                        }
+                        ++cnt;
+                    }
                 }
             }
         }
     }
+    const int mine = min(cnt, 4);
+    int inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    const int total = __shfl_sync(0xffffffffu, inc, 31);
+    int base = 0;
+    if (lane == 31 && total) base = atomicAdd(&sm.npairs[0], total);
+    base = __shfl_sync(0xffffffffu, base, 31) + inc - mine;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (i < mine && base + i < SM::PCAP) sm.pairs[base + i] = ((uint32_t)t << 16) | (uint32_t)((packed >> (16 * i)) & 0xffffu);
 }
 
+// The bitmask form of the graph (adj) is only read when the edge cache overflowed; it is built on demand
+// (graph_build_adj) instead of on every frame.
 template <int KIND, class SM>
 __device__ __forceinline__ void graph_add_edge(SM& sm, int t, int j, double c) {
-    atomicOr(&sm.adj[j >> 5][t], 1u << (j & 31));
     atomicAdd(&sm.coldeg[j], 1);
-    atomicXor(&sm.colxor[j], t);
     const int e = atomicAdd(&sm.ecount[0], 1);
     if (e < SM::ECAP) {
         sm.ecost[e] = c; sm.ecol[e] = (short)j;
@@ -274,6 +302,30 @@ __device__ __forceinline__ void graph_phase_b(SM& sm, int n, int words, const Pa
                     if (c <= (rt == RT_A ? lim.limA : lim.limB)) graph_add_edge<KIND>(sm, t, j, c);
                 }
             }
+        }
+    }
+}
+
+// Edge cache overflowed (crowded frame): the solver falls back to the bitmask form of the graph and recomputes costs.
+// Thread t owns row t of adj, so no atomics: every row walks its columns once.
+template <int NT, int KIND, class SM>
+__device__ __forceinline__ void graph_build_adj(SM& sm, int n, int words, const PassCost<KIND, SM>& cost, const PassLimit& lim) {
+    for (int t = threadIdx.x; t < n; t += NT) {
+        const int rt = sm.rowtype[t];
+        const Box a = track_box<KIND>(sm, t);
+        const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
+        for (int wd = 0; wd < words; ++wd) {
+            uint32_t bits = 0u;
+            uint32_t cand = rt == RT_NONE ? 0u : colbits[wd];
+            while (cand) {
+                const int b = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const int j = wd * 32 + b;
+                if (!box_overlap(a, det_box(sm, j))) continue;
+                const double c = cost.pair(a, j, rt == RT_A ? cost.fuseA : cost.fuseB);
+                if (c <= (rt == RT_A ? lim.limA : lim.limB)) bits |= 1u << b;
+            }
+            sm.adj[wd][t] = bits;
         }
     }
 }
@@ -383,6 +435,26 @@ bytetrack_step_kernel(const StepParams p) {
     long long ph_last = p.dbg ? clock64() : 0;
 #define PHASE(k) do { if (p.dbg && tid == 0) { const long long now_ = clock64(); atomicAdd(&p.dbg[k], (unsigned long long)(now_ - ph_last)); ph_last = now_; } } while (0)
 
+    // ---- HBM -> shared memory: detections [nd, 6] (planar), means, lifecycle ints ----------
+    // Every global load of this phase is issued before the first value is used, and none of them waits for the
+    // stream's counters: all TMAX slots and max_dets detection rows are fetched (one memory latency instead of
+    // two dependent ones); what lies beyond n / nd is never looked at.
+    const int t = tid;                                   // this thread's track slot
+    const double* gf = p.state_f + (size_t)s * B200_NF * TMAX;
+    const int* gi = p.state_i + (size_t)s * NI * TMAX;
+    const double* dets_g = p.dets + (size_t)s * p.max_dets * 6;
+    constexpr int DITER = (DMAX * 6 + NT - 1) / NT;
+    double dv[DITER], mv[8];
+    const int cap6 = min(DMAX, p.max_dets) * 6;
+#pragma unroll
+    for (int k = 0; k < DITER; ++k) { const int i = tid + k * NT; dv[k] = i < cap6 ? dets_g[i] : 0.0; }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) mv[c] = gf[(B200_TF_MEAN + c) * TMAX + t];
+    int fl = gi[B200_TI_FLAGS * TMAX + t];
+    int frame_t = gi[B200_TI_FRAME * TMAX + t];
+    const int start_v = gi[B200_TI_START * TMAX + t];
+    int frow_v = 0;
+    if constexpr (BOT) frow_v = gi[B200_TI_FROW * TMAX + t];
     int* counts = p.counts + 4 * s;
     const int nT = counts[0], nL = counts[1], id0 = counts[2], frame = counts[3] + 1;
     const int n = nT + nL;
@@ -391,31 +463,11 @@ bytetrack_step_kernel(const StepParams p) {
     if (nd > min(DMAX, p.max_dets)) { nd = min(DMAX, p.max_dets); err |= B200_ERR_DET_OVERFLOW; }
     if (nd < 0) nd = 0;
     const int words = (nd + 31) >> 5;
-    const int t = tid;                                   // this thread's track slot
-    const double* gf = p.state_f + (size_t)s * B200_NF * TMAX;
-    const int* gi = p.state_i + (size_t)s * NI * TMAX;
-
-    // ---- HBM -> shared memory: detections [nd, 6] (planar), means, lifecycle ints ----------
-    int fl = 0, frame_t = 0;
     double vel[4] = {0.0, 0.0, 0.0, 0.0};
-    const double* dets_g = p.dets + (size_t)s * p.max_dets * 6;
+    if (t >= n) { fl = 0; frame_t = 0; }
     {
-        // every global load of this phase is issued before the first value is used (one memory latency, not six)
-        const double* g = p.dets + (size_t)s * p.max_dets * 6;
-        constexpr int DITER = (DMAX * 6 + NT - 1) / NT;
         const int nd6 = nd * 6;
-        double dv[DITER], mv[8];
-        int start_v = 0;
-#pragma unroll
-        for (int k = 0; k < DITER; ++k) { const int i = tid + k * NT; dv[k] = i < nd6 ? g[i] : 0.0; }
-        if (t < n) {
-#pragma unroll
-            for (int c = 0; c < 8; ++c) mv[c] = gf[(B200_TF_MEAN + c) * TMAX + t];
-            fl = gi[B200_TI_FLAGS * TMAX + t];
-            frame_t = gi[B200_TI_FRAME * TMAX + t];
-            start_v = gi[B200_TI_START * TMAX + t];
-            if constexpr (BOT) { sm.bot.frow[t] = (short)gi[B200_TI_FROW * TMAX + t]; sm.bot.emadet[t] = -1; }
-        }
+        if constexpr (BOT) { if (t < n) { sm.bot.frow[t] = (short)frow_v; sm.bot.emadet[t] = -1; } }
 #pragma unroll
         for (int k = 0; k < DITER; ++k) {
             const int i = tid + k * NT;
@@ -444,8 +496,7 @@ bytetrack_step_kernel(const StepParams p) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + B200_TI_LEN * TMAX + t));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + B200_TI_DET * TMAX + t));
         }
-        for (int i = tid; i < NCX * DWP; i += NT) (&sm.xmask[0][0])[i] = 0u;
-        for (int i = tid; i < NCY * DWP; i += NT) (&sm.ymask[0][0])[i] = 0u;
+        if (tid < DWP) { sm.colbitsA[tid] = 0u; sm.colbitsB[tid] = 0u; }    // words beyond the detections stay empty
         for (int i = tid; i < TMAX + DMAX; i += NT) sm.drop[i] = 0;
         if constexpr (BOT) sm.bot.rowused[t] = 0;
     }
@@ -507,7 +558,7 @@ bytetrack_step_kernel(const StepParams p) {
     lw.pred = sm.pred; lw.nextc = sm.nextc; lw.mark = sm.mark; lw.scn = sm.scn;
     lw.coldeg = sm.coldeg; lw.ncomplex = sm.ncomplex;
     lw.ecost = sm.ecost; lw.ecol = sm.ecol; lw.enext = sm.enext; lw.ehead = sm.ehead; lw.ecount = sm.ecount; lw.ecap = SM::ECAP;
-    lw.colxor = sm.colxor;
+    lw.dbg = p.dbg; lw.dbg_last = &ph_last; lw.dbg_slot = 13;
     if (tid == 0) sm.npairs[0] = 0;
     lap_prepare<NT>(lw, n, words);
     __syncthreads();
@@ -526,13 +577,17 @@ bytetrack_step_kernel(const StepParams p) {
         cm.sx = (x1 > x0) ? (float)NCX / (x1 - x0) : 0.f;
         cm.sy = (y1 > y0) ? (float)NCY / (y1 - y0) : 0.f;
     }
-    if (mydfl) {
-        const int j = tid;
-        const uint32_t bit = 1u << (j & 31);
-        const int wd = j >> 5;
-        const int cx0 = cm.cx(mybox.x1), cx1 = cm.cx(mybox.x2), cy0 = cm.cy(mybox.y1), cy1 = cm.cy(mybox.y2);
-        for (int c = cx0; c <= cx1; ++c) atomicOr(&sm.xmask[c][wd], bit);
-        for (int c = cy0; c <= cy1; ++c) atomicOr(&sm.ymask[c][wd], bit);
+    if (tid < words * 32) {                              // warp-uniform; lane = detection of word `warp`
+        uint32_t tlo = 0u, thi = 0u, ty = 0u;             // thermometer codes over the cells, empty for unbanded detections
+        if (mydfl) {
+            const int cx0 = cm.cx(mybox.x1), cx1 = cm.cx(mybox.x2), cy0 = cm.cy(mybox.y1), cy1 = cm.cy(mybox.y2);
+            tlo = 0xffffffffu << cx0;                     // bit c: cx0 <= c
+            thi = 0xffffffffu >> (31 - cx1);              // bit c: cx1 >= c
+            ty = ((0xffffu << cy0) & 0xffffu) | ((0xffffu >> (15 - cy1)) << 16);
+        }
+        tlo = warp_transpose32(tlo, lane); thi = warp_transpose32(thi, lane); ty = warp_transpose32(ty, lane);
+        sm.xlo[lane][warp] = tlo; sm.xhi[lane][warp] = thi;
+        if (lane < 16) sm.ylo[lane][warp] = ty; else sm.yhi[lane - 16][warp] = ty;
     }
     __syncthreads();
     PHASE(3);
@@ -561,11 +616,16 @@ bytetrack_step_kernel(const StepParams p) {
     lim.limA = p.match_thresh; lim.limB = p.match_thresh;
     graph_phase_a<KIND>(sm, t, n, words, cm);
     __syncthreads();
+    PHASE(12);
     graph_phase_b<NT, KIND, BOT>(sm, n, words, cost, lim, p.proximity_thresh);
     __syncthreads();
     if constexpr (BOT) {
         if (sm.npairs[0] > SM::PCAP || sm.ecount[0] > SM::ECAP) err |= B200_ERR_BOT_CAPACITY;
         graph_phase_emb<NT, KIND>(sm, p, s, lim);
+        __syncthreads();
+    }
+    if (sm.ecount[0] > SM::ECAP) {                        // uniform
+        graph_build_adj<NT, KIND>(sm, n, words, cost, lim);
         __syncthreads();
     }
     PHASE(4);
@@ -604,7 +664,12 @@ bytetrack_step_kernel(const StepParams p) {
         graph_phase_emb<NT, KIND>(sm, p, s, lim);
         __syncthreads();
     }
+    if (sm.ecount[0] > SM::ECAP) {                        // uniform
+        graph_build_adj<NT, KIND>(sm, n, words, cost, lim);
+        __syncthreads();
+    }
     PHASE(7);
+    lw.dbg_slot = 14;
     lap_sparse_solve<NT>(lw, n, words, lim, cost);
 
     // ---- deferred Kalman work + lifecycle, thread t (byte_tracker.py:64-98, :222-253) --------
@@ -728,7 +793,7 @@ bytetrack_step_kernel(const StepParams p) {
     {
         const unsigned long long val = (cat == CAT_LOST_OLD ? 1ull : 0ull) | (cat == CAT_LOST_NEW ? (1ull << 16) : 0ull);
         unsigned long long tot;
-        const unsigned long long ex = block_exscan<NT>(val, sm.scratch, tot);
+        const unsigned long long ex = block_exscan1<NT>(val, sm.scratch, tot);
         const int nLostOld = (int)(tot & 0xffff);
         if (cat == CAT_LOST_OLD) sm.lostlist[ex & 0xffff] = (short)t;
         if (cat == CAT_LOST_NEW) sm.lostlist[nLostOld + ((ex >> 16) & 0xffff)] = (short)t;
@@ -773,19 +838,35 @@ bytetrack_step_kernel(const StepParams p) {
             bool dropme = false;
             const float ax1 = __double2float_rd(a.x1), ay1 = __double2float_rd(a.y1);
             const float ax2 = __double2float_ru(a.x2), ay2 = __double2float_ru(a.y2);
-            for (int k = 0; k < nLostList; ++k) {
-                Box b;
-                if (lost_cached) {
-                    const float4 f = sm.dboxf[k];
-                    if (!(f.x < ax2 && ax1 < f.z && f.y < ay2 && ay1 < f.w)) continue;      // disjoint even after outward rounding
-                    b.x1 = sm.u[k]; b.y1 = sm.u[LCAP + k]; b.x2 = sm.u[2 * LCAP + k]; b.y2 = sm.u[3 * LCAP + k];
-                } else b = track_box<KIND>(sm, sm.lostlist[k]);
-                if (!box_overlap(a, b)) continue;
+            auto exact = [&](int k, const Box& b) {
+                if (!box_overlap(a, b)) return;
                 if (xsub(1.0, box_iou(a, b)) < p.dup_thresh) {
                     const int q = sm.lostlist[k];
                     const int ageq = lost_cached ? sm.coldeg[k] : sm.frame_t[q] - sm.start_t[q];
                     if (age > ageq) sm.drop[q] = 1; else dropme = true;
                 }
+            };
+            if (lost_cached) {
+                // branch-free sweep first (the loads of consecutive entries overlap), exact test only on the hits;
+                // nLostList <= LCAP <= 64 (128 for the 512-slot variant: two sweeps)
+                for (int k0 = 0; k0 < nLostList; k0 += 64) {
+                    unsigned long long hits = 0ull;
+                    const int kn = min(64, nLostList - k0);
+#pragma unroll 4
+                    for (int k = 0; k < kn; ++k) {
+                        const float4 f = sm.dboxf[k0 + k];
+                        hits |= (unsigned long long)(f.x < ax2 && ax1 < f.z && f.y < ay2 && ay1 < f.w) << k;   // disjoint even after outward rounding -> 0
+                    }
+                    while (hits) {
+                        const int k = k0 + __ffsll((long long)hits) - 1;
+                        hits &= hits - 1;
+                        Box b;
+                        b.x1 = sm.u[k]; b.y1 = sm.u[LCAP + k]; b.x2 = sm.u[2 * LCAP + k]; b.y2 = sm.u[3 * LCAP + k];
+                        exact(k, b);
+                    }
+                }
+            } else {
+                for (int k = 0; k < nLostList; ++k) exact(k, track_box<KIND>(sm, sm.lostlist[k]));
             }
             if (dropme) sm.drop[pass == 0 ? t : TMAX + tid] = 1;
         }
@@ -811,13 +892,13 @@ bytetrack_step_kernel(const StepParams p) {
         if (val & ((1ull << 40) - 1)) sm.bot.rowused[sm.bot.frow[t]] = 1;      // rows of the tracks that stay listed
     }
     unsigned long long totals;
-    const unsigned long long ex = block_exscan<NT>(val, sm.scratch, totals);
+    const unsigned long long ex = block_exscan1<NT>(val, sm.scratch + 16, totals);
     int nfree = 0;
     if constexpr (BOT) {
         // embedding-pool rows of dead tracks are recycled: the k-th stored newborn takes the k-th free row
         const bool isfree = !sm.bot.rowused[t];
         unsigned long long tf;
-        const int rank = (int)block_exscan<NT>(isfree ? 1ull : 0ull, sm.scratch, tf);
+        const int rank = (int)block_exscan1<NT>(isfree ? 1ull : 0ull, sm.scratch, tf);
         nfree = (int)tf;
         if (isfree) sm.bot.freelist[rank] = (short)t;
         __syncthreads();

@@ -8,10 +8,11 @@
 // so a pair with c_ij > L is never used and can be pruned EXACTLY.  What is left is a sparse
 // bipartite graph that falls apart into many small connected components; each component is
 // an independent assignment problem.  Here:
-//   1. all threads build the candidate bitmask adj[word][row] (caller),
-//   2. components are found with a lock-free union-find in shared memory,
-//   3. the thread that owns a component's root row solves it with the shortest-augmenting-
-//      path (Hungarian / JV augmentation) algorithm over the sparse rows.  Every row owns a
+//   1. all threads build the candidate graph (caller): per-row edge lists with cached costs, or bitmask rows,
+//   2. rows are placed by a greedy tight start (edge lists) or components are found with a lock-free union-find
+//      (bitmask rows),
+//   3. what is left is solved with the shortest-augmenting-path (Hungarian / JV augmentation) algorithm over the
+//      sparse rows.  Every row owns a
 //      private "stay unmatched" column of cost L, real edges keep their cost c_ij (columns
 //      stay unmatched for free): the same objective up to a constant, with the dummy block
 //      of the extended matrix never materialised and no cost ever rescaled.
@@ -25,12 +26,12 @@ namespace b200 {
 
 struct LapWork {
     int Tmax, Dmax;
-    uint32_t* adj;      // [Dmax/32][Tmax]
+    uint32_t* adj;      // [Dmax/32][Tmax]  only read when there is no (valid) edge cache
     double* u;          // [Tmax]
     double* v;          // [Dmax]
     double* dist;       // [Dmax]
     int* parent;        // [Tmax + Dmax]
-    int* head;          // [Tmax]
+    int* head;          // [Tmax]  compact list of the rows sent to the general solver
     short* rnext;       // [Tmax]
     short* xr;          // [Tmax]  column of row, -1 = unmatched
     short* yc;          // [Dmax]  row of column, -1 = free
@@ -48,7 +49,10 @@ struct LapWork {
     int* ehead = nullptr;      // [Tmax]
     int* ecount = nullptr;     // [1]
     int ecap = 0;
-    int* colxor = nullptr;     // [Dmax] XOR of the candidate rows of a column (with coldeg: the other row of a 2-row column)
+    // optional profiling hook: cycles up to the end of the classification stage are added to dbg[dbg_slot] (thread 0)
+    unsigned long long* dbg = nullptr;
+    int dbg_slot = 0;
+    long long* dbg_last = nullptr;
 };
 
 __device__ __forceinline__ int uf_find(volatile int* parent, int x) {
@@ -158,85 +162,61 @@ __device__ __forceinline__ void lap_prepare(const LapWork& w, int nrows, int wor
     }
     for (int j = tid; j < ncols; j += NT) {
         w.yc[j] = -1; w.v[j] = 0.0; w.parent[w.Tmax + j] = w.Tmax + j; w.mark[j] = 0; w.scn[j] = 0; w.coldeg[j] = 0;
-        if (w.colxor) w.colxor[j] = 0;
     }
     if (tid == 0) { *w.ncomplex = 0; if (w.ecount) *w.ecount = 0; }
 }
 
-// Whole-CTA solve.  adj[word][row], coldeg[] (and, when used, the edge cache and colxor[]) must be
-// complete (zero for rows / columns not taking part) and visible (__syncthreads() after the
-// build); rows are 0..nrows-1, columns 0..32*words-1.  lambda(row) is the cost limit of that
-// row's problem.  Results in xr / yc.
+// Whole-CTA solve.  coldeg[] and either the edge cache or adj[word][row] must be complete (zero for rows / columns
+// not taking part) and visible (__syncthreads() after the build); rows are 0..nrows-1, columns 0..32*words-1.
+// lambda(row) is the cost limit of that row's problem.  Results in xr / yc.
 //
-// Small components are solved in place by the thread of their first row, without any barrier:
-//   * 1 row x 1 column: matched directly (c_ij <= limit by construction);
-//   * 1 row with several private columns, and 2-row components (every column touched by the
-//     two rows has no other row): exhaustive enumeration of the partial matchings over the
-//     cached edge costs - the same objective (sum of matched costs + lambda per unmatched row);
-// everything else goes through union-find + shortest augmenting paths.
+// With a valid edge cache (the frame steps):
+//   * a row whose only edge leads to a column nobody else wants is matched directly;
+//   * every other row takes part in a greedy TIGHT start: u[row] = its cheapest edge (never above lambda: dearer edges
+//     were pruned), v = 0, and the row claims that column with a compare-and-swap.  Duals are feasible and every
+//     claimed edge is tight, so rows that got their column are optimally placed unless an augmentation re-routes them;
+//   * the rows that lost the race (two tracks preferring one detection - a handful per frame) are inserted by
+//     shortest augmenting paths, one after the other, by thread 0.  No component analysis is needed: a search never
+//     leaves the component of its row.
+// Without an edge cache (operator kernel, overflowed cache): components by union-find over the bitmask rows, each
+// solved by the thread of its smallest row.
 template <int NT, class Cost, class Lambda>
 __device__ void lap_sparse_solve(const LapWork& w, int nrows, int words, const Lambda& lambda, const Cost& cost) {
     const int tid = threadIdx.x;
-    const bool small_ok = w.ecost != nullptr && w.colxor != nullptr && *w.ecount <= w.ecap;
+    const bool small_ok = w.ecost != nullptr && *w.ecount <= w.ecap;
+    if (small_ok) {
+        for (int t = tid; t < nrows; t += NT) {
+            const int e0 = w.ehead[t];
+            if (e0 < 0) continue;
+            int bj = w.ecol[e0];
+            int e = w.enext[e0];
+            if (e < 0 && w.coldeg[bj] == 1) { w.xr[t] = (short)bj; w.yc[bj] = (short)t; continue; }
+            double best = w.ecost[e0];
+            for (; e >= 0; e = w.enext[e]) {
+                const double c = w.ecost[e];
+                if (c < best) { best = c; bj = w.ecol[e]; }
+            }
+            w.u[t] = best;
+            if (atomicCAS(reinterpret_cast<unsigned short*>(&w.yc[bj]), (unsigned short)0xffffu, (unsigned short)t) == 0xffffu) w.xr[t] = (short)bj;
+            else w.head[atomicAdd(w.ncomplex, 1)] = t;
+        }
+        __syncthreads();
+        if (w.dbg && tid == 0) { const long long now_ = clock64(); atomicAdd(&w.dbg[w.dbg_slot], (unsigned long long)(now_ - *w.dbg_last)); *w.dbg_last = now_; }
+        const int nc = *w.ncomplex;
+        if (nc == 0) return;                              // uniform: every thread reads the same value
+        if (tid == 0)
+            for (int k = 0; k < nc; ++k) lap_insert_row(w, words, lambda, cost, w.head[k]);
+        __syncthreads();
+        return;
+    }
     for (int t = tid; t < nrows; t += NT) {
         int deg = 0, first = -1;
-        if (small_ok) {                                   // the edge list mirrors adj: degree 0 / 1 without scanning the mask words
-            const int e0 = w.ehead[t];
-            if (e0 >= 0) { first = w.ecol[e0]; deg = w.enext[e0] < 0 ? 1 : 2; }
-        } else {
-            for (int wd = 0; wd < words; ++wd) {
-                const uint32_t bits = w.adj[wd * w.Tmax + t];
-                if (bits) { if (first < 0) first = wd * 32 + __ffs(bits) - 1; deg += __popc(bits); }
-            }
+        for (int wd = 0; wd < words; ++wd) {
+            const uint32_t bits = w.adj[wd * w.Tmax + t];
+            if (bits) { if (first < 0) first = wd * 32 + __ffs(bits) - 1; deg += __popc(bits); }
         }
         if (deg == 0) continue;
         if (deg == 1 && w.coldeg[first] == 1) { w.xr[t] = (short)first; w.yc[first] = (short)t; continue; }
-        if (small_ok) {
-            int partner = -1;
-            bool general = false;
-            for (int e = w.ehead[t]; e >= 0; e = w.enext[e]) {
-                const int j = w.ecol[e], cd = w.coldeg[j];
-                if (cd == 1) continue;
-                if (cd == 2) { const int o = w.colxor[j] ^ t; if (partner < 0) partner = o; else if (partner != o) general = true; }
-                else general = true;
-            }
-            if (!general && partner >= 0) {
-                for (int e = w.ehead[partner]; e >= 0; e = w.enext[e]) {
-                    const int j = w.ecol[e], cd = w.coldeg[j];
-                    if (cd == 1) continue;
-                    if (cd != 2 || (w.colxor[j] ^ partner) != t) general = true;
-                }
-            }
-            if (!general) {
-                const double lamA = lambda(t);
-                if (partner < 0) {                        // one row, private columns: cheapest edge or nothing
-                    double best = lamA; int bj = -1;
-                    for (int e = w.ehead[t]; e >= 0; e = w.enext[e])
-                        if (w.ecost[e] < best) { best = w.ecost[e]; bj = w.ecol[e]; }
-                    if (bj >= 0) { w.xr[t] = (short)bj; w.yc[bj] = (short)t; }
-                } else if (t < partner) {                 // two rows: enumerate (col or none) x (col or none)
-                    const double lamB = lambda(partner);
-                    double best = lamA + lamB; int ja = -1, jb = -1;
-                    for (int ea = w.ehead[t]; ; ea = w.enext[ea]) {
-                        const double ca = ea >= 0 ? w.ecost[ea] : lamA;
-                        const int cola = ea >= 0 ? w.ecol[ea] : -1;
-                        for (int eb = w.ehead[partner]; ; eb = w.enext[eb]) {
-                            const double cb = eb >= 0 ? w.ecost[eb] : lamB;
-                            const int colb = eb >= 0 ? w.ecol[eb] : -1;
-                            if (!(cola >= 0 && cola == colb)) {
-                                const double tot = ca + cb;
-                                if (tot < best) { best = tot; ja = cola; jb = colb; }
-                            }
-                            if (eb < 0) break;
-                        }
-                        if (ea < 0) break;
-                    }
-                    if (ja >= 0) { w.xr[t] = (short)ja; w.yc[ja] = (short)t; }
-                    if (jb >= 0) { w.xr[partner] = (short)jb; w.yc[jb] = (short)partner; }
-                }
-                continue;
-            }
-        }
         atomicAdd(w.ncomplex, 1);
         for (int wd = 0; wd < words; ++wd) {
             uint32_t bits = w.adj[wd * w.Tmax + t];
@@ -249,16 +229,14 @@ __device__ void lap_sparse_solve(const LapWork& w, int nrows, int words, const L
         w.rnext[t] = -2;                                  // marks "complex row" for the next phase
     }
     __syncthreads();
-    if (*w.ncomplex == 0) return;                         // uniform: every thread reads the same value
+    if (*w.ncomplex == 0) return;                         // uniform
     for (int t = tid; t < nrows; t += NT) {
         if (w.rnext[t] != -2) continue;
-        const int root = uf_find(w.parent, t);            // smallest row of the component
-        w.rnext[t] = (short)atomicExch(&w.head[root], t);
+        w.rnext[t] = (short)atomicExch(&w.head[uf_find(w.parent, t)], t);   // the root is the component's smallest row
     }
     __syncthreads();
-    for (int t = tid; t < nrows; t += NT) {
+    for (int t = tid; t < nrows; t += NT)
         for (int r = w.head[t]; r >= 0; r = w.rnext[r]) lap_insert_row(w, words, lambda, cost, r);
-    }
     __syncthreads();
 }
 
