@@ -40,7 +40,7 @@ struct LapWork {
     short* mark;        // [Dmax]  stamp when reached
     short* scn;         // [Dmax]  stamp when scanned
     int* coldeg;        // [Dmax]  candidate rows per column (filled while adj is built)
-    int* ncomplex;      // [1]     rows that need the general solver
+    int* ncomplex;      // [2]     rows that need an augmentation; rows whose concurrent search gave up
     // optional edge cache (costs computed while the graph was built): per-row linked lists in a
     // fixed pool.  ecount[0] > ecap means the pool overflowed and costs are recomputed instead.
     double* ecost = nullptr;   // [ecap]
@@ -76,9 +76,16 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
 }
 
 // Insert one row into the matching of its component (one shortest augmenting path).
-template <class Cost, class Lambda>
-__device__ void lap_insert_row(const LapWork& w, int words, const Lambda& lambda, const Cost& cost, int i0) {
-    const short stamp = (short)(i0 + 1);
+// CONCURRENT: several rows are inserted at the same time by different threads.  A search claims every column it
+// touches (compare-and-swap on claim[j], "free" = Tmax + j as left by lap_prepare in parent[Tmax + j]); the rows of
+// its tree are the mates of claimed columns, so two searches that never meet on a column work on edge-disjoint
+// parts of the graph and their dual updates and augmentations commute.  A search that meets a foreign claim gives
+// up WITHOUT having modified the matching or the duals (returns false; the row is inserted afterwards, alone).
+template <bool CONCURRENT = false, class Cost, class Lambda>
+__device__ bool lap_insert_row(const LapWork& w, int words, const Lambda& lambda, const Cost& cost, int i0) {
+    const short stamp = (short)(i0 + 1 + (CONCURRENT ? w.Tmax : 0));       // a retry never sees its own stale marks
+    int* claim = w.parent + w.Tmax;
+    bool conflict = false;
     const bool cached = w.ecost != nullptr && *w.ecount <= w.ecap;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     double minVal = 0.0;
@@ -92,6 +99,10 @@ __device__ void lap_insert_row(const LapWork& w, int words, const Lambda& lambda
         const double dd = minVal + lambda(i) - ui;     // row i may stay unmatched at cost lambda(i)
         if (dd < bestDummy) { bestDummy = dd; bestDummyRow = i; }
         auto relax = [&](int j, double c) {
+            if (CONCURRENT) {
+                const int o = claim[j];
+                if (o != i0 && (o != w.Tmax + j || atomicCAS(&claim[j], w.Tmax + j, i0) != w.Tmax + j)) { conflict = true; return; }
+            }
             if (w.scn[j] == stamp) return;
             const double r = minVal + c - ui - w.v[j];
             if (w.mark[j] != stamp) {
@@ -102,6 +113,7 @@ __device__ void lap_insert_row(const LapWork& w, int words, const Lambda& lambda
         };
         if (cached) {
             for (int e = w.ehead[i]; e >= 0; e = w.enext[e]) relax(w.ecol[e], w.ecost[e]);
+            if (CONCURRENT && conflict) return false;
         } else {
             for (int wd = 0; wd < words; ++wd) {
                 uint32_t bits = w.adj[wd * w.Tmax + i];
@@ -136,7 +148,7 @@ __device__ void lap_insert_row(const LapWork& w, int words, const Lambda& lambda
     int j;
     if (sink >= 0) j = sink;
     else {
-        if (bestDummyRow == i0) return;               // i0 itself stays unmatched
+        if (bestDummyRow == i0) return true;          // i0 itself stays unmatched
         j = w.xr[bestDummyRow];
         w.xr[bestDummyRow] = -1;
     }
@@ -148,6 +160,7 @@ __device__ void lap_insert_row(const LapWork& w, int words, const Lambda& lambda
         j = t;
         if (r == i0) break;
     }
+    return true;
 }
 
 // Zero the per-problem work arrays.  Call (all threads) BEFORE the candidate graph is built:
@@ -163,7 +176,7 @@ __device__ __forceinline__ void lap_prepare(const LapWork& w, int nrows, int wor
     for (int j = tid; j < ncols; j += NT) {
         w.yc[j] = -1; w.v[j] = 0.0; w.parent[w.Tmax + j] = w.Tmax + j; w.mark[j] = 0; w.scn[j] = 0; w.coldeg[j] = 0;
     }
-    if (tid == 0) { *w.ncomplex = 0; if (w.ecount) *w.ecount = 0; }
+    if (tid == 0) { w.ncomplex[0] = 0; w.ncomplex[1] = 0; if (w.ecount) *w.ecount = 0; }
 }
 
 // Whole-CTA solve.  coldeg[] and either the edge cache or adj[word][row] must be complete (zero for rows / columns
@@ -176,8 +189,8 @@ __device__ __forceinline__ void lap_prepare(const LapWork& w, int nrows, int wor
 //     were pruned), v = 0, and the row claims that column with a compare-and-swap.  Duals are feasible and every
 //     claimed edge is tight, so rows that got their column are optimally placed unless an augmentation re-routes them;
 //   * the rows that lost the race (two tracks preferring one detection - a handful per frame) are inserted by
-//     shortest augmenting paths, one after the other, by thread 0.  No component analysis is needed: a search never
-//     leaves the component of its row.
+//     shortest augmenting paths, concurrently (one per warp): a search never leaves the component of its row, and
+//     searches that do meet are detected by column claims and redone one after the other.
 // Without an edge cache (operator kernel, overflowed cache): components by union-find over the bitmask rows, each
 // solved by the thread of its smallest row.
 template <int NT, class Cost, class Lambda>
@@ -204,8 +217,18 @@ __device__ void lap_sparse_solve(const LapWork& w, int nrows, int words, const L
         if (w.dbg && tid == 0) { const long long now_ = clock64(); atomicAdd(&w.dbg[w.dbg_slot], (unsigned long long)(now_ - *w.dbg_last)); *w.dbg_last = now_; }
         const int nc = *w.ncomplex;
         if (nc == 0) return;                              // uniform: every thread reads the same value
+        // concurrent insertions, one per warp at a time (lane 0): searches in different components never meet
+        if ((tid & 31) == 0) {
+            for (int k = tid >> 5; k < nc; k += NT / 32) {
+                const int r = w.head[k];
+                if (!lap_insert_row<true>(w, words, lambda, cost, r)) w.rnext[atomicAdd(w.ncomplex + 1, 1)] = (short)r;
+            }
+        }
+        __syncthreads();
+        const int nretry = w.ncomplex[1];
+        if (nretry == 0) return;                          // uniform
         if (tid == 0)
-            for (int k = 0; k < nc; ++k) lap_insert_row(w, words, lambda, cost, w.head[k]);
+            for (int k = 0; k < nretry; ++k) lap_insert_row(w, words, lambda, cost, w.rnext[k]);
         __syncthreads();
         return;
     }
