@@ -27,9 +27,9 @@ trk.phase_cycles(reset=True)          # enable + zero
 for f in range(warm, F):
     trk.step_device(d_dets[f], d_nd[f], d_out, d_nout)
 c = trk.phase_cycles()
-names = {1: "load dets/means", 2: "det+track prep, lap_prepare", 3: "cell masks", 4: "graph pass 1", 5: "solve pass 1",
-         6: "pass-2 setup", 7: "graph pass 2", 8: "solve pass 2 + deferred KF", 9: "lost-list scan", 10: "lost boxes",
-         11: "dedupe", 12: "graph pass 1: candidate walk", 13: "solve pass 1: classify + small", 14: "solve pass 2: classify + small", 15: "final scan + writes"}
+names = {1: "load dets/means", 2: "det+track prep, lap_prepare", 3: "cell masks", 4: "graph pass 1", 5: "solve pass 1: augmentations",
+         6: "pass-2 setup", 7: "graph pass 2", 8: "deferred KF + lifecycle", 9: "lost-list scan", 10: "solve pass 2: augmentations",
+         11: "lost boxes + dedupe", 12: "graph pass 1: candidate walk", 13: "solve pass 1: classify + small", 14: "solve pass 2: classify + small", 15: "final scan + writes"}
 n = c[0]
 tot = sum(c[1:])
 print(f"CTAs {n}, mean cycles/CTA {tot / n:.0f}")

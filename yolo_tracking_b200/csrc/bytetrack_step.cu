@@ -31,6 +31,8 @@
 // evaluated per candidate pair, one warp per pair, in double on the fp32 values exactly like
 // matching.py:145-167; nothing T x D x F is computed.  Embeddings live in a per-stream pool of
 // rows that never move (a slot carries its row index); rows of dead tracks are recycled.
+#include <cstdlib>
+
 #include "boxes.cuh"
 #include "kf.cuh"
 #include "lap_sparse.cuh"
@@ -80,28 +82,38 @@ struct alignas(16) StepSmem {
     static constexpr int TCAP = TMAX;
     static constexpr int DW = DMAX / 32;
     static constexpr int DWP = (DW + 3) / 4 * 4;      // mask rows padded to 16-byte multiples
+    static constexpr int ECAP = 2 * TMAX;             // candidate edge cache (cost computed once, while the graph is built)
+    static constexpr int PCAP = 4 * TMAX;             // candidate pairs that passed the conservative fp32 overlap filter
     double mean[4][TMAX];                             // position half of the mean; velocities stay in HBM / registers
     double dbox[4][DMAX];                             // raw x1, y1, x2, y2
     double dconf[DMAX];
-    double u[TMAX], v[DMAX], dist[DMAX];
+    double u[TMAX];
     unsigned long long scratch[32];
+    // Everything the association needs and nothing after it does shares its storage with the parking area of the
+    // updated covariances: between the Kalman update and the final write (duplicate removal, scans) the 12 covariance
+    // terms of a slot wait here instead of in registers (at 72 registers per thread they would spill, and with
+    // 4 x 56 KB of shared memory per SM the L1 is too small to hold the spills).
+    union {
+        struct {
+            double v[DMAX], dist[DMAX];
+            double ecost[ECAP];
+            int parent[TMAX + DMAX], head[TMAX];
+            int ehead[TMAX];
+            uint32_t adj[DW][TMAX];
+            uint32_t xlo[NCX][DWP], xhi[NCX][DWP], ylo[NCY][DWP], yhi[NCY][DWP];
+            uint32_t pairs[PCAP];                     // (row << 16) | det
+            short ecol[ECAP], enext[ECAP];
+            short rnext[TMAX];
+            short yc[DMAX], pred[DMAX], nextc[DMAX], mark[DMAX], scn[DMAX];
+        };
+        double park[12][TMAX];
+    };
     int frame_t[TMAX], start_t[TMAX];
-    int parent[TMAX + DMAX], head[TMAX], coldeg[DMAX], ncomplex[4];
-    uint32_t adj[DW][TMAX];
+    int coldeg[DMAX], ncomplex[4];
     uint32_t colbitsA[DWP], colbitsB[DWP];
-    uint32_t xlo[NCX][DWP], xhi[NCX][DWP], ylo[NCY][DWP], yhi[NCY][DWP];
     float fext[16][4];
-    short rnext[TMAX], xr[TMAX], match[TMAX], lostlist[TMAX];
-    short yc[DMAX], pred[DMAX], nextc[DMAX], mark[DMAX], scn[DMAX];
-    // candidate edge cache (cost computed once, while the graph is built)
-    static constexpr int ECAP = 2 * TMAX;
-    double ecost[ECAP];
-    short ecol[ECAP], enext[ECAP];
-    int ehead[TMAX];
+    short xr[TMAX], match[TMAX], lostlist[TMAX];
     int ecount[4];
-    // candidate pairs that passed the conservative fp32 overlap filter: (row << 16) | det
-    static constexpr int PCAP = 4 * TMAX;
-    uint32_t pairs[PCAP];
     int npairs[4];
     float4 dboxf[DMAX];                               // detection boxes rounded outwards to fp32
     unsigned char role[TMAX], rowtype[TMAX], cat[TMAX], drop[TMAX + DMAX], dflag[DMAX];
@@ -190,50 +202,53 @@ struct CellMap {
 //     most a couple of pairs, all lanes busy, one fp64 division each.
 template <int KIND, class SM>
 __device__ __forceinline__ void graph_phase_a(SM& sm, int t, int n, int words, const CellMap& cm) {
-    constexpr int DWP = SM::DWP;
+    constexpr int DW = SM::DW, DWP = SM::DWP;
     const int lane = threadIdx.x & 31;
     const int rt = t < n ? sm.rowtype[t] : RT_NONE;
-    // survivors of the fp32 test stay in registers (four 16-bit detection ids) and are appended to the shared list
-    // with ONE atomic per warp after the walk; a fifth and later survivor (crowded spot) goes to the list directly
-    unsigned long long packed = 0ull;
-    int cnt = 0;
+    // The step is latency bound (few warps, long dependent chains), so the walk is organised for instruction-level
+    // parallelism: every iteration tests ONE candidate of EVERY mask word (DW independent chains) instead of
+    // draining the words one after the other; hits are collected as bitmasks and emitted the same way.
+    uint32_t c[DW], h[DW];
+#pragma unroll
+    for (int w = 0; w < DW; ++w) { c[w] = 0u; h[w] = 0u; }
+    float ax1 = 0.f, ay1 = 0.f, ax2 = 0.f, ay2 = 0.f;
     if (rt != RT_NONE) {
         const Box a = track_box<KIND>(sm, t);
-        const float ax1 = __double2float_rd(a.x1), ay1 = __double2float_rd(a.y1);
-        const float ax2 = __double2float_ru(a.x2), ay2 = __double2float_ru(a.y2);
+        ax1 = __double2float_rd(a.x1); ay1 = __double2float_rd(a.y1);
+        ax2 = __double2float_ru(a.x2); ay2 = __double2float_ru(a.y2);
         const int cx0 = cm.cx(a.x1), cx1 = cm.cx(a.x2), cy0 = cm.cy(a.y1), cy1 = cm.cy(a.y2);
         const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
 #pragma unroll
         for (int q = 0; q < DWP / 4; ++q) {
-            if (q * 4 >= words) break;
             const uint4 xa = *reinterpret_cast<const uint4*>(&sm.xlo[cx1][q * 4]);
             const uint4 xb = *reinterpret_cast<const uint4*>(&sm.xhi[cx0][q * 4]);
             const uint4 ya = *reinterpret_cast<const uint4*>(&sm.ylo[cy1][q * 4]);
             const uint4 yb = *reinterpret_cast<const uint4*>(&sm.yhi[cy0][q * 4]);
             const uint4 cb = *reinterpret_cast<const uint4*>(&colbits[q * 4]);
-            const unsigned long long cand2[2] = {
-                (unsigned long long)(xa.x & xb.x & ya.x & yb.x & cb.x) | ((unsigned long long)(xa.y & xb.y & ya.y & yb.y & cb.y) << 32),
-                (unsigned long long)(xa.z & xb.z & ya.z & yb.z & cb.z) | ((unsigned long long)(xa.w & xb.w & ya.w & yb.w & cb.w) << 32)};
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                unsigned long long cand = cand2[k];
-                while (cand) {
-                    const int j = (q * 2 + k) * 64 + __ffsll((long long)cand) - 1;
-                    cand &= cand - 1;
-                    const float4 d = sm.dboxf[j];
-                    if (d.x < ax2 && ax1 < d.z && d.y < ay2 && ay1 < d.w) {
-                        if (cnt < 4) packed |= (unsigned long long)j << (16 * cnt);
-                        else {
-                            const int pi = atomicAdd(&sm.npairs[0], 1);
-                            if (pi < SM::PCAP) sm.pairs[pi] = ((uint32_t)t << 16) | (uint32_t)j;
-                        }
-                        ++cnt;
-                    }
-                }
-            }
+            if (q * 4 + 0 < DW) c[q * 4 + 0] = xa.x & xb.x & ya.x & yb.x & cb.x;
+            if (q * 4 + 1 < DW) c[q * 4 + 1] = xa.y & xb.y & ya.y & yb.y & cb.y;
+            if (q * 4 + 2 < DW) c[q * 4 + 2] = xa.z & xb.z & ya.z & yb.z & cb.z;
+            if (q * 4 + 3 < DW) c[q * 4 + 3] = xa.w & xb.w & ya.w & yb.w & cb.w;
         }
     }
-    const int mine = min(cnt, 4);
+    while (true) {
+        uint32_t any = 0u;
+#pragma unroll
+        for (int w = 0; w < DW; ++w) any |= c[w];
+        if (!any) break;
+#pragma unroll
+        for (int w = 0; w < DW; ++w) {
+            const uint32_t cw = c[w];
+            const uint32_t low = cw & (0u - cw);              // lowest candidate of this word (0 if none)
+            c[w] = cw ^ low;
+            const int j = w * 32 + (low ? __ffs(low) - 1 : 0);
+            const float4 d = sm.dboxf[j];
+            if (d.x < ax2 && ax1 < d.z && d.y < ay2 && ay1 < d.w) h[w] |= low;
+        }
+    }
+    int mine = 0;
+#pragma unroll
+    for (int w = 0; w < DW; ++w) mine += __popc(h[w]);
     int inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -242,11 +257,27 @@ __device__ __forceinline__ void graph_phase_a(SM& sm, int t, int n, int words, c
     }
     const int total = __shfl_sync(0xffffffffu, inc, 31);
     int base = 0;
-    if (lane == 31 && total) base = atomicAdd(&sm.npairs[0], total);
+    if (lane == 31 && total) base = atomicAdd(&sm.npairs[0], total);      // one list atomic per warp
     base = __shfl_sync(0xffffffffu, base, 31) + inc - mine;
+    int off[DW];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (i < mine && base + i < SM::PCAP) sm.pairs[base + i] = ((uint32_t)t << 16) | (uint32_t)((packed >> (16 * i)) & 0xffffu);
+    for (int w = 0; w < DW; ++w) { off[w] = base; base += __popc(h[w]); }
+    while (true) {
+        uint32_t any = 0u;
+#pragma unroll
+        for (int w = 0; w < DW; ++w) any |= h[w];
+        if (!any) break;
+#pragma unroll
+        for (int w = 0; w < DW; ++w) {
+            const uint32_t hw = h[w];
+            if (hw) {
+                const int j = w * 32 + __ffs(hw) - 1;
+                h[w] = hw & (hw - 1);
+                if (off[w] < SM::PCAP) sm.pairs[off[w]] = ((uint32_t)t << 16) | (uint32_t)j;
+                ++off[w];
+            }
+        }
+    }
 }
 
 // The bitmask form of the graph (adj) is only read when the edge cache overflowed; it is built on demand
@@ -457,8 +488,17 @@ bytetrack_step_kernel(const StepParams p) {
     if constexpr (BOT) frow_v = gi[B200_TI_FROW * TMAX + t];
     int* counts = p.counts + 4 * s;
     const int nT = counts[0], nL = counts[1], id0 = counts[2], frame = counts[3] + 1;
-    const int n = nT + nL;
     int nd = p.ndets[s];
+    LapWork lw;
+    lw.Tmax = TMAX; lw.Dmax = DMAX; lw.adj = &sm.adj[0][0]; lw.u = sm.u; lw.v = sm.v; lw.dist = sm.dist;
+    lw.parent = sm.parent; lw.head = sm.head; lw.rnext = sm.rnext; lw.xr = sm.xr; lw.yc = sm.yc;
+    lw.pred = sm.pred; lw.nextc = sm.nextc; lw.mark = sm.mark; lw.scn = sm.scn;
+    lw.coldeg = sm.coldeg; lw.ncomplex = sm.ncomplex;
+    lw.ecost = sm.ecost; lw.ecol = sm.ecol; lw.enext = sm.enext; lw.ehead = sm.ehead; lw.ecount = sm.ecount; lw.ecap = SM::ECAP;
+    lw.dbg = p.dbg; lw.dbg_last = &ph_last; lw.dbg_slot = 13;
+    if (tid == 0) sm.npairs[0] = 0;
+    lap_prepare<NT>(lw, TMAX, SM::DW);                   // in the shadow of the loads above (does not wait for n / nd)
+    const int n = nT + nL;
     int err = 0;
     if (nd > min(DMAX, p.max_dets)) { nd = min(DMAX, p.max_dets); err |= B200_ERR_DET_OVERFLOW; }
     if (nd < 0) nd = 0;
@@ -552,15 +592,6 @@ bytetrack_step_kernel(const StepParams p) {
         sm.match[t] = -1;
     }
 
-    LapWork lw;
-    lw.Tmax = TMAX; lw.Dmax = DMAX; lw.adj = &sm.adj[0][0]; lw.u = sm.u; lw.v = sm.v; lw.dist = sm.dist;
-    lw.parent = sm.parent; lw.head = sm.head; lw.rnext = sm.rnext; lw.xr = sm.xr; lw.yc = sm.yc;
-    lw.pred = sm.pred; lw.nextc = sm.nextc; lw.mark = sm.mark; lw.scn = sm.scn;
-    lw.coldeg = sm.coldeg; lw.ncomplex = sm.ncomplex;
-    lw.ecost = sm.ecost; lw.ecol = sm.ecol; lw.enext = sm.enext; lw.ehead = sm.ehead; lw.ecount = sm.ecount; lw.ecap = SM::ECAP;
-    lw.dbg = p.dbg; lw.dbg_last = &ph_last; lw.dbg_slot = 13;
-    if (tid == 0) sm.npairs[0] = 0;
-    lap_prepare<NT>(lw, n, words);
     __syncthreads();
     PHASE(2);
 
@@ -671,15 +702,17 @@ bytetrack_step_kernel(const StepParams p) {
     PHASE(7);
     lw.dbg_slot = 14;
     lap_sparse_solve<NT>(lw, n, words, lim, cost);
+    PHASE(10);
 
     // ---- deferred Kalman work + lifecycle, thread t (byte_tracker.py:64-98, :222-253) --------
-    // covariance: HBM -> registers (first and only read), predict, update; it stays in
-    // registers until the final write.
-    KfState ks;
+    // covariance: HBM -> registers (first and only read), predict, update; then parked in shared memory
+    // (sm.park, storage of the solver arrays) until the final write; the position half of the mean lives in sm.mean.
+    double velo[4] = {0.0, 0.0, 0.0, 0.0};
     int tid_id = 0, len = 0, det_ind = 0, start = 0;
     double score = 0.0, cls = 0.0;
     int cat = CAT_NONE;
     if (t < n) {
+        KfState ks;
         bool unmatched2 = false;
         int j = sm.match[t];
         if (sm.rowtype[t] != RT_NONE) {
@@ -742,6 +775,11 @@ bytetrack_step_kernel(const StepParams p) {
             fl = (fl & ~3) | B200_ST_TRACKED | B200_FLAG_ACTIVATED;
         } else if (unmatched2) {
             fl = (fl & ~3) | (role == ROLE_TRACKED ? B200_ST_LOST : B200_ST_REMOVED);   // mark_lost / mark_removed
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            sm.park[3 * i + 0][t] = ks.pp[i]; sm.park[3 * i + 1][t] = ks.pv[i]; sm.park[3 * i + 2][t] = ks.vv[i];
+            velo[i] = ks.m[4 + i];
         }
         int st = fl & 3;
         const bool sticky_old = fl & B200_FLAG_STICKY;      // id already in removed_stracks
@@ -820,7 +858,6 @@ bytetrack_step_kernel(const StepParams p) {
             sm.dboxf[tid] = make_float4(__double2float_rd(b.x1), __double2float_rd(b.y1), __double2float_ru(b.x2), __double2float_ru(b.y2));
         }
         __syncthreads();
-        PHASE(10);
         for (int pass = 0; pass < 2; ++pass) {
             Box a;
             int age;
@@ -920,12 +957,14 @@ bytetrack_step_kernel(const StepParams p) {
         else dst = newT + totLostOld + (int)((ex >> 30) & 1023);
         if (dst < cap) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) wf[(B200_TF_MEAN + c) * TMAX + dst] = ks.m[c];
+            for (int c = 0; c < 4; ++c) wf[(B200_TF_MEAN + c) * TMAX + dst] = sm.mean[c][t];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) wf[(B200_TF_MEAN + 4 + c) * TMAX + dst] = velo[c];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                wf[(B200_TF_COV + 3 * i + 0) * TMAX + dst] = ks.pp[i];
-                wf[(B200_TF_COV + 3 * i + 1) * TMAX + dst] = ks.pv[i];
-                wf[(B200_TF_COV + 3 * i + 2) * TMAX + dst] = ks.vv[i];
+                wf[(B200_TF_COV + 3 * i + 0) * TMAX + dst] = sm.park[3 * i + 0][t];
+                wf[(B200_TF_COV + 3 * i + 1) * TMAX + dst] = sm.park[3 * i + 1][t];
+                wf[(B200_TF_COV + 3 * i + 2) * TMAX + dst] = sm.park[3 * i + 2][t];
             }
             wf[B200_TF_SCORE * TMAX + dst] = score;
             wf[B200_TF_CLS * TMAX + dst] = cls;
@@ -938,7 +977,7 @@ bytetrack_step_kernel(const StepParams p) {
             if constexpr (BOT) wi[B200_TI_FROW * TMAX + dst] = sm.bot.frow[t];
         }
         if (orow >= 0 && orow < out_cap) {
-            const Box b = mean_to_box<KIND>(ks.m[0], ks.m[1], ks.m[2], ks.m[3]);
+            const Box b = track_box<KIND>(sm, t);
             double* o = gout + (size_t)orow * 8;
             o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
             o[4] = (double)tid_id; o[5] = score; o[6] = cls; o[7] = (double)det_ind;
@@ -1028,7 +1067,9 @@ constexpr Variant kVariants[] = {{64, 64}, {128, 128}, {224, 224}, {256, 256}, {
 template <int KIND, int TMAX, int DMAX, bool BOT>
 cudaError_t launch_variant(const StepParams& p, cudaStream_t stream) {
     auto kern = bytetrack_step_kernel<TMAX, KIND, TMAX, DMAX, BOT>;
-    const size_t smem = sizeof(StepSmem<TMAX, DMAX, BOT>);
+    // profiling aid: B200_STEP_SMEM_PAD=<bytes> lowers the number of co-resident CTAs (latency vs throughput experiments)
+    static const size_t pad = [] { const char* v = getenv("B200_STEP_SMEM_PAD"); return v ? (size_t)atol(v) : (size_t)0; }();
+    const size_t smem = sizeof(StepSmem<TMAX, DMAX, BOT>) + pad;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<p.n_streams, TMAX, smem, stream>>>(p);
