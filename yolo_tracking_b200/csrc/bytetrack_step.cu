@@ -474,11 +474,29 @@ bytetrack_step_kernel(const StepParams p) {
     const double* gf = p.state_f + (size_t)s * B200_NF * TMAX;
     const int* gi = p.state_i + (size_t)s * NI * TMAX;
     const double* dets_g = p.dets + (size_t)s * p.max_dets * 6;
-    constexpr int DITER = (DMAX * 6 + NT - 1) / NT;
-    double dv[DITER], mv[8];
-    const int cap6 = min(DMAX, p.max_dets) * 6;
-#pragma unroll
-    for (int k = 0; k < DITER; ++k) { const int i = tid + k * NT; dv[k] = i < cap6 ? dets_g[i] : 0.0; }
+    // thread j fetches detection row j whole (three 16-byte loads: 48-byte rows, 16-byte aligned) - no transposition pass
+    double mv[8];
+    double2 dr0 = make_double2(0.0, 0.0), dr1 = dr0, dr2 = dr0;
+    if (tid < min(DMAX, p.max_dets)) {
+        const double2* row = reinterpret_cast<const double2*>(dets_g + (size_t)tid * 6);
+        dr0 = row[0]; dr1 = row[1]; dr2 = row[2];
+    }
+    // next wave's first-touch lines -> L2 (this grid runs ~4 CTAs on each of 148 SMs; the stream that far ahead starts
+    // when a CTA of the current wave retires): its loads then cost an L2 hit instead of a DRAM round trip
+    {
+        constexpr int AHEAD = 592;
+        const int s2 = s + AHEAD;
+        if (s2 < p.n_streams) {
+            const char* d2 = reinterpret_cast<const char*>(p.dets + (size_t)s2 * p.max_dets * 6);
+            const char* f2 = reinterpret_cast<const char*>(p.state_f + (size_t)s2 * B200_NF * TMAX);
+            const char* i2 = reinterpret_cast<const char*>(p.state_i + (size_t)s2 * NI * TMAX);
+            const int nl_d = (p.max_dets * 48 + 127) >> 7, nl_f = (8 * TMAX * 8 + 127) >> 7, nl_i = (NI * TMAX * 4 + 127) >> 7;   // B200_TF_MEAN == 0
+            for (int l = tid; l < nl_d + nl_f + nl_i; l += NT) {
+                const char* a = l < nl_d ? d2 + ((size_t)l << 7) : (l < nl_d + nl_f ? f2 + ((size_t)(l - nl_d) << 7) : i2 + ((size_t)(l - nl_d - nl_f) << 7));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+        }
+    }
 #pragma unroll
     for (int c = 0; c < 8; ++c) mv[c] = gf[(B200_TF_MEAN + c) * TMAX + t];
     int fl = gi[B200_TI_FLAGS * TMAX + t];
@@ -506,17 +524,11 @@ bytetrack_step_kernel(const StepParams p) {
     double vel[4] = {0.0, 0.0, 0.0, 0.0};
     if (t >= n) { fl = 0; frame_t = 0; }
     {
-        const int nd6 = nd * 6;
         if constexpr (BOT) { if (t < n) { sm.bot.frow[t] = (short)frow_v; sm.bot.emadet[t] = -1; } }
-#pragma unroll
-        for (int k = 0; k < DITER; ++k) {
-            const int i = tid + k * NT;
-            if (i < nd6) {
-                const int j = i / 6, c = i - 6 * j;
-                if (c < 4) sm.dbox[c][j] = dv[k];
-                else if (c == 4) sm.dconf[j] = dv[k];
-                // the class column is only read for matched / new tracks, straight from the detection row (L2)
-            }
+        if (tid < nd) {
+            sm.dbox[0][tid] = dr0.x; sm.dbox[1][tid] = dr0.y; sm.dbox[2][tid] = dr1.x; sm.dbox[3][tid] = dr1.y;
+            sm.dconf[tid] = dr2.x;
+            // the class column is only read for matched / new tracks, straight from the detection row (L2)
         }
         if (t < n) {
 #pragma unroll
@@ -536,12 +548,11 @@ bytetrack_step_kernel(const StepParams p) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + B200_TI_LEN * TMAX + t));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gi + B200_TI_DET * TMAX + t));
         }
-        if (tid < DWP) { sm.colbitsA[tid] = 0u; sm.colbitsB[tid] = 0u; }    // words beyond the detections stay empty
+        if (tid < DWP && tid >= words) { sm.colbitsA[tid] = 0u; sm.colbitsB[tid] = 0u; }    // words beyond the detections stay empty
         for (int i = tid; i < TMAX + DMAX; i += NT) sm.drop[i] = 0;
         if constexpr (BOT) sm.bot.rowused[t] = 0;
     }
-    __syncthreads();
-    PHASE(1);
+    PHASE(1);            // no barrier: up to the frame extents every thread only touches its own detection / slot
 
     // ---- detection side (thread j): confidence bands (byte_tracker.py:151-158, strict
     // inequalities), frame extents for the cell maps -------------------------------------------
