@@ -84,6 +84,9 @@ struct alignas(16) StepSmem {
     static constexpr int DWP = (DW + 3) / 4 * 4;      // mask rows padded to 16-byte multiples
     static constexpr int ECAP = 2 * TMAX;             // candidate edge cache (cost computed once, while the graph is built)
     static constexpr int PCAP = 4 * TMAX;             // candidate pairs that passed the conservative fp32 overlap filter
+    // second-pass candidates found while the first pass is built ((row << 16) | det and cost); they live in the storage
+    // of adj, which is only needed when the edge cache overflows (then the second pass is rebuilt the long way)
+    static constexpr int P2CAP = (DW * TMAX * 4) / 12 < TMAX ? (DW * TMAX * 4) / 12 : TMAX;
     double mean[4][TMAX];                             // position half of the mean; velocities stay in HBM / registers
     double dbox[4][DMAX];                             // raw x1, y1, x2, y2
     double dconf[DMAX];
@@ -115,9 +118,12 @@ struct alignas(16) StepSmem {
     short xr[TMAX], match[TMAX], lostlist[TMAX];
     int ecount[4];
     int npairs[4];
+    int np2[4];                                       // entries of the second-pass candidate list (see P2CAP)
     float4 dboxf[DMAX];                               // detection boxes rounded outwards to fp32
     unsigned char role[TMAX], rowtype[TMAX], cat[TMAX], drop[TMAX + DMAX], dflag[DMAX];
     BotSmem<TMAX, DMAX, BOT> bot;
+    __device__ __forceinline__ double* p2cost() { return reinterpret_cast<double*>(&adj[0][0]); }
+    __device__ __forceinline__ uint32_t* p2pair() { return reinterpret_cast<uint32_t*>(&adj[0][0]) + 2 * P2CAP; }
 };
 
 // STrack.xyxy (byte_tracker.py:100-111): XYAH mean -> (xc, yc, a*h, h) -> corners
@@ -201,7 +207,7 @@ struct CellMap {
 //     lap_sparse.cuh (no overlap => iou = 0 => cost = 1 > limit).  Every thread evaluates at
 //     most a couple of pairs, all lanes busy, one fp64 division each.
 template <int KIND, class SM>
-__device__ __forceinline__ void graph_phase_a(SM& sm, int t, int n, int words, const CellMap& cm) {
+__device__ __forceinline__ void graph_phase_a(SM& sm, int t, int n, int words, const CellMap& cm, bool fused = false) {
     constexpr int DW = SM::DW, DWP = SM::DWP;
     const int lane = threadIdx.x & 31;
     const int rt = t < n ? sm.rowtype[t] : RT_NONE;
@@ -217,14 +223,21 @@ __device__ __forceinline__ void graph_phase_a(SM& sm, int t, int n, int words, c
         ax1 = __double2float_rd(a.x1); ay1 = __double2float_rd(a.y1);
         ax2 = __double2float_ru(a.x2); ay2 = __double2float_ru(a.y2);
         const int cx0 = cm.cx(a.x1), cx1 = cm.cx(a.x2), cy0 = cm.cy(a.y1), cy1 = cm.cy(a.y2);
-        const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
+        // classic: row type A walks colbitsA, B walks colbitsB.  fused first pass (colbitsA = high, colbitsB = low
+        // detections): pool and unconfirmed rows walk the high detections, still-tracked rows the low ones as well
+        const uint32_t* colbits = (fused || rt == RT_A) ? sm.colbitsA : sm.colbitsB;
+        const bool also_low = fused && rt == RT_A && sm.role[t] == ROLE_TRACKED;
 #pragma unroll
         for (int q = 0; q < DWP / 4; ++q) {
             const uint4 xa = *reinterpret_cast<const uint4*>(&sm.xlo[cx1][q * 4]);
             const uint4 xb = *reinterpret_cast<const uint4*>(&sm.xhi[cx0][q * 4]);
             const uint4 ya = *reinterpret_cast<const uint4*>(&sm.ylo[cy1][q * 4]);
             const uint4 yb = *reinterpret_cast<const uint4*>(&sm.yhi[cy0][q * 4]);
-            const uint4 cb = *reinterpret_cast<const uint4*>(&colbits[q * 4]);
+            uint4 cb = *reinterpret_cast<const uint4*>(&colbits[q * 4]);
+            if (also_low) {
+                const uint4 cl = *reinterpret_cast<const uint4*>(&sm.colbitsB[q * 4]);
+                cb.x |= cl.x; cb.y |= cl.y; cb.z |= cl.z; cb.w |= cl.w;
+            }
             if (q * 4 + 0 < DW) c[q * 4 + 0] = xa.x & xb.x & ya.x & yb.x & cb.x;
             if (q * 4 + 1 < DW) c[q * 4 + 1] = xa.y & xb.y & ya.y & yb.y & cb.y;
             if (q * 4 + 2 < DW) c[q * 4 + 2] = xa.z & xb.z & ya.z & yb.z & cb.z;
@@ -294,13 +307,30 @@ __device__ __forceinline__ void graph_add_edge(SM& sm, int t, int j, double c) {
 
 template <int NT, int KIND, bool BOT, class SM>
 __device__ __forceinline__ void graph_phase_b(SM& sm, int n, int words, const PassCost<KIND, SM>& cost, const PassLimit& lim,
-                                              double proximity) {
+                                              double proximity, bool fused = false, double lim2A = 0.0, double lim2B = 0.0) {
     const int np = sm.npairs[0];
     if (np <= SM::PCAP) {
         for (int k = threadIdx.x; k < np; k += NT) {
             const uint32_t pr = sm.pairs[k];
             const int t = pr >> 16, j = pr & 0xffff;
             const bool isA = sm.rowtype[t] == RT_A;
+            if (!BOT && fused) {
+                // one IoU serves both passes: first-pass edge (pool x high, fused score), or a second-pass candidate
+                // (tracked x low, plain IoU distance; unconfirmed x high, fused score) kept for after the first solve
+                const double v = box_iou(track_box<KIND>(sm, t), det_box(sm, j));
+                const bool low = sm.dflag[j] == DF_LOW;
+                if (isA && !low) {
+                    const double c = fused_cost(v, sm.dconf[j]);
+                    if (c <= lim.limA) graph_add_edge<KIND>(sm, t, j, c);
+                } else {
+                    const double c = isA ? xsub(1.0, v) : fused_cost(v, sm.dconf[j]);
+                    if (c <= (isA ? lim2A : lim2B)) {
+                        const int e = atomicAdd(&sm.np2[0], 1);
+                        if (e < SM::P2CAP) { sm.p2pair()[e] = pr; sm.p2cost()[e] = c; }
+                    }
+                }
+                continue;
+            }
             if constexpr (BOT) {
                 // bot_sort.py:298-309 / :356-368: the proximity mask is taken on the plain iou distance
                 const double v = box_iou(track_box<KIND>(sm, t), det_box(sm, j));
@@ -317,9 +347,11 @@ __device__ __forceinline__ void graph_phase_b(SM& sm, int n, int words, const Pa
         }
     } else {
         // pair list overflowed (pathologically crowded frame): every row re-walks its columns
+        // (fused first pass: only the first pass is built here, the second one is rebuilt the long way)
+        if (fused && threadIdx.x == 0) sm.np2[0] = SM::P2CAP + 1;
         for (int t = threadIdx.x; t < n; t += NT) {
             const int rt = sm.rowtype[t];
-            if (rt == RT_NONE) continue;
+            if (rt == RT_NONE || (fused && rt != RT_A)) continue;
             const Box a = track_box<KIND>(sm, t);
             const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
             for (int wd = 0; wd < words; ++wd) {
@@ -340,9 +372,11 @@ __device__ __forceinline__ void graph_phase_b(SM& sm, int n, int words, const Pa
 // Edge cache overflowed (crowded frame): the solver falls back to the bitmask form of the graph and recomputes costs.
 // Thread t owns row t of adj, so no atomics: every row walks its columns once.
 template <int NT, int KIND, class SM>
-__device__ __forceinline__ void graph_build_adj(SM& sm, int n, int words, const PassCost<KIND, SM>& cost, const PassLimit& lim) {
+__device__ __forceinline__ void graph_build_adj(SM& sm, int n, int words, const PassCost<KIND, SM>& cost, const PassLimit& lim, bool fused = false) {
+    if (fused && threadIdx.x == 0) sm.np2[0] = SM::P2CAP + 1;       // adj overwrites the second-pass candidate list
     for (int t = threadIdx.x; t < n; t += NT) {
-        const int rt = sm.rowtype[t];
+        int rt = sm.rowtype[t];
+        if (fused && rt != RT_A) rt = RT_NONE;
         const Box a = track_box<KIND>(sm, t);
         const uint32_t* colbits = rt == RT_A ? sm.colbitsA : sm.colbitsB;
         for (int wd = 0; wd < words; ++wd) {
@@ -457,6 +491,9 @@ bytetrack_step_kernel(const StepParams p) {
     static_assert(!BOT || KIND == KF_XYWH, "BoT-SORT runs on the XYWH filter");
     using SM = StepSmem<TMAX, DMAX, BOT>;
     constexpr int NI = BOT ? B200_NI_BOT : B200_NI;
+    // ByteTrack: the candidates of the second association are collected while the first one is built (one walk, one IoU
+    // per pair for both); BoT-SORT keeps two separate builds (its second pass has its own appearance stage)
+    constexpr bool FUSE2 = !BOT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     constexpr int DWP = SM::DWP;
@@ -514,7 +551,7 @@ bytetrack_step_kernel(const StepParams p) {
     lw.coldeg = sm.coldeg; lw.ncomplex = sm.ncomplex;
     lw.ecost = sm.ecost; lw.ecol = sm.ecol; lw.enext = sm.enext; lw.ehead = sm.ehead; lw.ecount = sm.ecount; lw.ecap = SM::ECAP;
     lw.dbg = p.dbg; lw.dbg_last = &ph_last; lw.dbg_slot = 13;
-    if (tid == 0) sm.npairs[0] = 0;
+    if (tid == 0) { sm.npairs[0] = 0; sm.np2[0] = 0; }
     lap_prepare<NT>(lw, TMAX, SM::DW);                   // in the shadow of the loads above (does not wait for n / nd)
     const int n = nT + nL;
     int err = 0;
@@ -573,7 +610,8 @@ bytetrack_step_kernel(const StepParams p) {
         }
         sm.dflag[j] = (unsigned char)mydfl;
         const uint32_t mh = __ballot_sync(0xffffffffu, mydfl == DF_HIGH);
-        if (lane == 0) sm.colbitsA[j >> 5] = mh;           // first association: all high detections
+        const uint32_t ml = __ballot_sync(0xffffffffu, mydfl == DF_LOW);
+        if (lane == 0) { sm.colbitsA[j >> 5] = mh; sm.colbitsB[j >> 5] = ml; }   // first association: all high detections (+ low for the fused build)
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -599,7 +637,7 @@ bytetrack_step_kernel(const StepParams p) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) sm.mean[i][t] = xadd(sm.mean[i][t], vel[i]);
         }
-        sm.rowtype[t] = role != ROLE_UNCONF ? RT_A : RT_NONE;
+        sm.rowtype[t] = role != ROLE_UNCONF ? RT_A : (FUSE2 ? RT_B : RT_NONE);
         sm.match[t] = -1;
     }
 
@@ -656,10 +694,10 @@ bytetrack_step_kernel(const StepParams p) {
     cost.fuseA = !BOT; cost.fuseB = !BOT;                 // BoT-SORT: fuse_first_associate = False (bot_sort.py:300-301)
     cost.embA = cost.embB = BOT && p.with_reid;
     lim.limA = p.match_thresh; lim.limB = p.match_thresh;
-    graph_phase_a<KIND>(sm, t, n, words, cm);
+    graph_phase_a<KIND>(sm, t, n, words, cm, FUSE2);
     __syncthreads();
     PHASE(12);
-    graph_phase_b<NT, KIND, BOT>(sm, n, words, cost, lim, p.proximity_thresh);
+    graph_phase_b<NT, KIND, BOT>(sm, n, words, cost, lim, p.proximity_thresh, FUSE2, p.second_thresh, p.unconf_thresh);
     __syncthreads();
     if constexpr (BOT) {
         if (sm.npairs[0] > SM::PCAP || sm.ecount[0] > SM::ECAP) err |= B200_ERR_BOT_CAPACITY;
@@ -667,13 +705,13 @@ bytetrack_step_kernel(const StepParams p) {
         __syncthreads();
     }
     if (sm.ecount[0] > SM::ECAP) {                        // uniform
-        graph_build_adj<NT, KIND>(sm, n, words, cost, lim);
+        graph_build_adj<NT, KIND>(sm, n, words, cost, lim, FUSE2);
         __syncthreads();
     }
     PHASE(4);
     lap_sparse_solve<NT>(lw, n, words, lim, cost);
     bool matched1 = false;
-    if (t < n && sm.rowtype[t] != RT_NONE) {
+    if (t < n && sm.rowtype[t] == RT_A) {
         const int j = sm.xr[t];
         if (j >= 0) { matched1 = true; sm.match[t] = (short)j; sm.dflag[j] |= DF_USED; }
     }
@@ -697,14 +735,27 @@ bytetrack_step_kernel(const StepParams p) {
     cost.fuseA = false; cost.fuseB = true;
     cost.embA = false; cost.embB = BOT && p.with_reid;
     lim.limA = p.second_thresh; lim.limB = p.unconf_thresh;
-    graph_phase_a<KIND>(sm, t, n, words, cm);
-    __syncthreads();
-    graph_phase_b<NT, KIND, BOT>(sm, n, words, cost, lim, p.proximity_thresh);
-    __syncthreads();
-    if constexpr (BOT) {
-        if (sm.npairs[0] > SM::PCAP || sm.ecount[0] > SM::ECAP) err |= B200_ERR_BOT_CAPACITY;
-        graph_phase_emb<NT, KIND>(sm, p, s, lim);
+    const int np2 = sm.np2[0];
+    if (FUSE2 && np2 <= SM::P2CAP) {
+        // the candidates were found during the first build: keep those whose row is still unmatched (tracked rows) /
+        // whose detection is still unused (unconfirmed rows); low detections are never used by the first pass
+        for (int k = tid; k < np2; k += NT) {
+            const uint32_t pr = sm.p2pair()[k];
+            const int r = pr >> 16, j = pr & 0xffff;
+            const int rt = sm.rowtype[r];
+            if (rt == RT_A || (rt == RT_B && !(sm.dflag[j] & DF_USED))) graph_add_edge<KIND>(sm, r, j, sm.p2cost()[k]);
+        }
         __syncthreads();
+    } else {
+        graph_phase_a<KIND>(sm, t, n, words, cm);
+        __syncthreads();
+        graph_phase_b<NT, KIND, BOT>(sm, n, words, cost, lim, p.proximity_thresh);
+        __syncthreads();
+        if constexpr (BOT) {
+            if (sm.npairs[0] > SM::PCAP || sm.ecount[0] > SM::ECAP) err |= B200_ERR_BOT_CAPACITY;
+            graph_phase_emb<NT, KIND>(sm, p, s, lim);
+            __syncthreads();
+        }
     }
     if (sm.ecount[0] > SM::ECAP) {                        // uniform
         graph_build_adj<NT, KIND>(sm, n, words, cost, lim);
