@@ -149,6 +149,15 @@ int b200track_kf_project(int32_t kf_kind, int32_t n, const double* d_mean, const
                          const double* d_conf, double* d_pmean, double* d_pcov, void* stream);
 int b200track_kf_update(int32_t kf_kind, int32_t n, double* d_mean, double* d_cov, const double* d_z,
                         const double* d_conf, void* stream);
+/* b200track_kf_apply_warp <- STrack.multi_gmc (bot_sort.py:95-111) / Track.camera_update's matrix form: applies an
+ * externally estimated 2x3 camera-motion warp to dense states: mean <- kron(I4, R) mean (+ t on x, y), cov <- R8 cov R8^T.
+ * d_warp [n_warps, 6] row-major 2x3; d_warp_index [n] picks the warp of each track (NULL: every track uses warp 0). */
+int b200track_kf_apply_warp(int32_t n, double* d_mean, double* d_cov, const double* d_warp, const int32_t* d_warp_index, void* stream);
+/* b200track_aw_max_metric <- compute_aw_max_metric (association.py:79-108, DeepOCSORT's adaptive appearance weight):
+ * emb [batch, rows, cols] similarity matrices -> out = w_assoc * w_row * w_col * emb, the weights from the two largest
+ * entries of every row / column. */
+int b200track_aw_max_metric(int32_t batch, int32_t rows, int32_t cols, const double* d_emb, double w_assoc, double bottom,
+                            double* d_out, void* stream);
 int b200track_kf_gating_distance(int32_t kf_kind, int32_t n_tracks, int32_t n_meas, const double* d_mean,
                                  const double* d_cov, const double* d_meas, int32_t only_position,
                                  int32_t metric, const double* d_conf, double* d_out, void* stream);

@@ -127,3 +127,14 @@ def gating_distance(kind, mean, cov, measurements, only_position=False, metric="
     L = np.linalg.cholesky(pc)
     zz = np.linalg.solve(L, d.T)
     return np.sum(zz * zz, axis=0)
+
+
+def apply_warp(mean, cov, H):
+    """STrack.multi_gmc (boxmot/trackers/botsort/bot_sort.py:95-111) on dense states [n, 8] / [n, 8, 8]:
+    mean <- kron(I4, R) mean, mean[:2] += t, cov <- R8 cov R8^T with R = H[:2, :2], t = H[:2, 2]."""
+    H = np.asarray(H, dtype=np.float64)
+    R8 = np.kron(np.eye(4), H[:2, :2])
+    mean = np.asarray(mean, dtype=np.float64) @ R8.T
+    mean[:, :2] += H[:2, 2]
+    cov = R8 @ np.asarray(cov, dtype=np.float64) @ R8.T
+    return mean, cov

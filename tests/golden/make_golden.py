@@ -129,6 +129,55 @@ def gen_costs():
     _save("costs", **out)
 
 
+# ----------------------------------------------------------------------------- camera-motion warp, adaptive appearance weight
+def gen_aux():
+    """STrack.multi_gmc (bot_sort.py:95-111) on filter states that went through predict / update rounds, and
+    compute_aw_max_metric (association.py:79-108) on similarity matrices with the shapes / degeneracies it branches on."""
+    rh.install()
+    from boxmot.motion.kalman_filters.botsort_kf import KalmanFilter as KFxywh
+    from boxmot.trackers.botsort.bot_sort import STrack
+    from boxmot.utils.association import compute_aw_max_metric
+    rng = np.random.default_rng(21)
+    kf = KFxywh()
+    n = 40
+    mean = np.zeros((n, 8))
+    cov = np.zeros((n, 8, 8))
+    for i in range(n):
+        z = np.array([rng.uniform(100, 1800), rng.uniform(100, 1000), rng.uniform(30, 90), rng.uniform(60, 220)])
+        m, c = kf.initiate(z)
+        for _ in range(3):
+            m, c = kf.predict(m, c)
+            m, c = kf.update(m, c, m[:4] + rng.normal(0, 1.5, 4))
+        mean[i], cov[i] = m, c
+    ang = 0.03
+    warps = np.stack([np.eye(2, 3),
+                      np.array([[np.cos(ang), -np.sin(ang), 3.5], [np.sin(ang), np.cos(ang), -2.25]]),
+                      np.array([[1.02, 0.01, -7.0], [-0.015, 0.98, 4.0]])])
+
+    class _S:                                             # the two attributes multi_gmc reads and writes
+        def __init__(self, m, c): self.mean, self.covariance = m, c
+    out = dict(mean=mean, cov=cov, warps=warps)
+    for k, H in enumerate(warps):
+        ss = [_S(mean[i].copy(), cov[i].copy()) for i in range(n)]
+        STrack.multi_gmc(ss, H)
+        out[f"gmc_mean{k}"] = np.stack([x.mean for x in ss])
+        out[f"gmc_cov{k}"] = np.stack([x.covariance for x in ss])
+    mats = []
+    a = rng.uniform(0.0, 1.0, (17, 23))
+    a[3] = 0.0                                            # a row whose largest entry is 0
+    a[:, 5] = 0.0                                         # a zero column
+    a[7, 2] = a[7, 9] = a[7].max() + 0.1                  # tied top-2 in a row
+    mats.append(a)
+    mats.append(rng.uniform(-0.2, 1.0, (1, 9)))           # a single row: column weights untouched
+    mats.append(rng.uniform(-0.2, 1.0, (6, 1)))           # a single column
+    mats.append(rng.uniform(0.0, 1.0, (96, 120)))
+    for k, m in enumerate(mats):
+        out[f"aw_in{k}"] = m
+        out[f"aw_out{k}"] = compute_aw_max_metric(m.copy(), 0.75, 0.5)
+    out["aw_out0_b"] = compute_aw_max_metric(mats[0].copy(), 0.4, 0.3)
+    _save("aux_ops", **out)
+
+
 # ----------------------------------------------------------------------------- ByteTrack
 def _bt_snapshot(trk):
     ts = trk.tracked_stracks + trk.lost_stracks
@@ -377,7 +426,7 @@ def gen_strongsort():
 
 
 GENERATORS = {"kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
-              "mot": gen_mot, "strongsort": gen_strongsort}
+              "mot": gen_mot, "strongsort": gen_strongsort, "aux": gen_aux}
 
 if __name__ == "__main__":
     names = sys.argv[1:] or list(GENERATORS)

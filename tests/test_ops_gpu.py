@@ -279,3 +279,36 @@ def test_linear_sum_assignment_is_bit_faithful_to_scipy_including_ties():
     assert len(a) == 0 and len(c) == 0
     with pytest.raises(ValueError):
         _ops.linear_sum_assignment(np.full((2, 2), np.inf))
+
+
+def test_camera_warp_operator_matches_reference():
+    """b200track_kf_apply_warp against STrack.multi_gmc of the live reference (golden), one warp for all tracks and a
+    per-track choice of warp."""
+    from yolo_tracking_b200 import _ops
+    g = load_golden("aux_ops")
+    for k, H in enumerate(g["warps"]):
+        m, c = _ops.kf_apply_warp(g["mean"], g["cov"], H)
+        assert_close(m, g[f"gmc_mean{k}"], what=f"warp {k} mean")
+        assert_close(c, g[f"gmc_cov{k}"], abs_=1e-10, what=f"warp {k} cov")
+    idx = np.arange(len(g["mean"])) % 3
+    m, c = _ops.kf_apply_warp(g["mean"], g["cov"], g["warps"], warp_index=idx)
+    for k in range(3):
+        assert_close(m[idx == k], g[f"gmc_mean{k}"][idx == k], what="indexed warp mean")
+        assert_close(c[idx == k], g[f"gmc_cov{k}"][idx == k], abs_=1e-10, what="indexed warp cov")
+    m0, c0 = _ops.kf_apply_warp(g["mean"], g["cov"], np.eye(2, 3))
+    assert np.array_equal(m0, g["mean"]) and np.array_equal(c0, g["cov"])                  # identity warp is exact
+
+
+def test_adaptive_weight_operator_matches_reference():
+    """b200track_aw_max_metric against compute_aw_max_metric of the live reference: zero rows / columns, tied top-2,
+    single row / column, and a batch."""
+    from yolo_tracking_b200 import _ops
+    g = load_golden("aux_ops")
+    for k in range(4):
+        assert_close(_ops.aw_max_metric(g[f"aw_in{k}"], 0.75, 0.5), g[f"aw_out{k}"], what=f"aw {k}")
+    assert_close(_ops.aw_max_metric(g["aw_in0"], 0.4, 0.3), g["aw_out0_b"], what="aw 0 b")
+    batch = np.stack([g["aw_in3"], g["aw_in3"][::-1].copy()])
+    out = _ops.aw_max_metric(batch, 0.75, 0.5)
+    assert_close(out[0], g["aw_out3"], what="batched aw")
+    from oracle.deepocsort import compute_aw_max_metric
+    assert_close(out[1], compute_aw_max_metric(batch[1], 0.75, 0.5), what="batched aw 1")

@@ -234,3 +234,17 @@ def test_strongsort_oracle_replays_reference(name):
             assert_close(s["cov"].reshape(-1, 64), g["cov"][cov_offs[k]:cov_offs[k + 1]], abs_=1e-10, what=f"frame {f} cov")
     assert np.array_equal(s["feature"], g["final_feat"])
     assert len(np.unique(g["rec"][:, 1])) >= 2
+
+
+def test_camera_warp_and_adaptive_weight_match_reference():
+    """STrack.multi_gmc and compute_aw_max_metric restatements against outputs of the live reference."""
+    from oracle import deepocsort, kalman
+    g = load_golden("aux_ops")
+    for k, H in enumerate(g["warps"]):
+        m, c = kalman.apply_warp(g["mean"], g["cov"], H)
+        assert_close(m, g[f"gmc_mean{k}"], what=f"warp {k} mean")
+        assert_close(c, g[f"gmc_cov{k}"], abs_=1e-10, what=f"warp {k} cov")
+    assert np.array_equal(kalman.apply_warp(g["mean"], g["cov"], g["warps"][0])[0], g["mean"])        # identity is exact
+    for k in range(4):
+        assert_close(deepocsort.compute_aw_max_metric(g[f"aw_in{k}"], 0.75, 0.5), g[f"aw_out{k}"], what=f"aw {k}")
+    assert_close(deepocsort.compute_aw_max_metric(g["aw_in0"], 0.4, 0.3), g["aw_out0_b"], what="aw 0 b")

@@ -60,6 +60,8 @@ SIGNATURES = {
     "b200track_get_features": (C.c_int, [_P, _I, _P]),
     "b200track_kf_initiate": (C.c_int, [_I, _I, _P, _P, _P, _P]),
     "b200track_kf_predict": (C.c_int, [_I, _I, _P, _P, _P]),
+    "b200track_kf_apply_warp": (C.c_int, [_I, _P, _P, _P, _P, _P]),
+    "b200track_aw_max_metric": (C.c_int, [_I, _I, _I, _P, _D, _D, _P, _P]),
     "b200track_kf_project": (C.c_int, [_I, _I, _P, _P, _P, _P, _P, _P]),
     "b200track_kf_update": (C.c_int, [_I, _I, _P, _P, _P, _P, _P]),
     "b200track_kf_gating_distance": (C.c_int, [_I, _I, _I, _P, _P, _P, _I, _I, _P, _P, _P]),

@@ -51,6 +51,31 @@ def kf_predict(kind, mean, cov):
     return m.cpu().numpy(), c.cpu().numpy()
 
 
+def kf_apply_warp(mean, cov, warp, warp_index=None):
+    """STrack.multi_gmc (bot_sort.py:95-111): warp [2, 3] (or [W, 2, 3] with warp_index [n]) applied to dense states."""
+    lib = _lib.load()
+    m = _dev(np.asarray(mean).reshape(-1, 8), np.float64)
+    c = _dev(np.asarray(cov).reshape(-1, 8, 8), np.float64)
+    w = _dev(np.asarray(warp, dtype=np.float64).reshape(-1, 6), np.float64)
+    wi = _dev(np.asarray(warp_index, dtype=np.int32).reshape(-1), np.int32) if warp_index is not None else None
+    _sync_check(lib.b200track_kf_apply_warp(m.shape[0], _p(m), _p(c), _p(w), _p(wi) if wi is not None else None, None))
+    return m.cpu().numpy(), c.cpu().numpy()
+
+
+def aw_max_metric(emb_cost, w_association_emb, bottom=0.5):
+    """compute_aw_max_metric (association.py:79-108): emb_cost [R, C] or [B, R, C] float64."""
+    lib = _lib.load()
+    torch = _torch()
+    e = np.asarray(emb_cost, dtype=np.float64)
+    e3 = e.reshape((-1,) + e.shape[-2:])
+    if e3.size == 0:
+        return e.copy()
+    de = _dev(e3, np.float64)
+    out = torch.empty_like(de)
+    _sync_check(lib.b200track_aw_max_metric(e3.shape[0], e3.shape[1], e3.shape[2], _p(de), float(w_association_emb), float(bottom), _p(out), None))
+    return out.cpu().numpy().reshape(e.shape)
+
+
 def kf_project(kind, mean, cov, conf=None):
     lib = _lib.load()
     torch = _torch()

@@ -211,6 +211,87 @@ __global__ void __launch_bounds__(KFU_TPB * KF_LANES, 4) kf_update_kernel(int n,
     kf_stage_out(sm, mean, cov, base, cnt);
 }
 
+// multi_gmc (bot_sort.py:95-111): mean <- R8 mean (+ t on x, y), P <- R8 P R8^T with R8 = kron(I4, R), R = warp[:2, :2],
+// t = warp[:2, 2].  One warp matrix per problem (warp_index[t] picks it, NULL = all tracks use warp 0).  Same staging as
+// predict; lane r owns row r: A[r, :] = R[r&1, 0] P[r&~1, :] + R[r&1, 1] P[r|1, :], then P'[r, 2k+b] = A[r, 2k] R[b, 0] +
+// A[r, 2k+1] R[b, 1].  The product breaks the 2x2 block sparsity the frame steps rely on, hence the dense layout.
+__global__ void __launch_bounds__(KF_THREADS) kf_gmc_kernel(int n, double* mean, double* cov, const double* __restrict__ warp,
+                                                            const int* __restrict__ warp_index) {
+    __shared__ double sm[KF_TPB * KF_STRIDE];
+    const int base = blockIdx.x * KF_TPB, cnt = min(KF_TPB, n - base);
+    const int t = threadIdx.x / KF_LANES, r = threadIdx.x % KF_LANES;
+    kf_stage_in(sm, mean, cov, base, cnt);
+    double row[8], mr = 0.0;
+    if (t < cnt) {
+        const double* m = sm + t * KF_STRIDE;
+        const double* P = m + 8;
+        const double* w = warp + (size_t)(warp_index ? warp_index[base + t] : 0) * 6;
+        const double R[2][2] = {{w[0], w[1]}, {w[3], w[4]}};
+        const int a = r & 1, r0 = r & ~1;
+        mr = xadd(xmul(R[a][0], m[r0]), xmul(R[a][1], m[r0 + 1]));
+        if (r < 2) mr = xadd(mr, w[2 + 3 * r]);
+        double A[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) A[c] = xadd(xmul(R[a][0], P[r0 * 8 + c]), xmul(R[a][1], P[(r0 + 1) * 8 + c]));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            row[2 * k + 0] = xadd(xmul(A[2 * k], R[0][0]), xmul(A[2 * k + 1], R[0][1]));
+            row[2 * k + 1] = xadd(xmul(A[2 * k], R[1][0]), xmul(A[2 * k + 1], R[1][1]));
+        }
+    }
+    __syncthreads();
+    if (t < cnt) {
+        double* m = sm + t * KF_STRIDE;
+        m[r] = mr;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m[8 + r * 8 + c] = row[c];
+    }
+    kf_stage_out(sm, mean, cov, base, cnt);
+}
+
+// compute_aw_max_metric (association.py:79-108, DeepOCSORT): per row and per column of the embedding-similarity matrix
+// the two largest entries decide a weight  w = 1 - max(second / first - bottom, 0) / (1 - bottom)  (0 if the largest
+// entry is 0, untouched if the row / column has fewer than two entries); out = w_assoc * w_row * w_col * emb.
+// One CTA per problem: warp per row for the row weights, thread per column for the column weights, then the product.
+__global__ void __launch_bounds__(256) aw_max_metric_kernel(int R, int C, const double* __restrict__ emb, double w_assoc, double bottom,
+                                                            double* __restrict__ out) {
+    extern __shared__ double wts[];                        // [R] row weights, [C] column weights
+    emb += (size_t)blockIdx.x * R * C;
+    out += (size_t)blockIdx.x * R * C;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double NINF = __longlong_as_double(0xfff0000000000000LL);
+    auto weight = [&](double first, double second) {
+        if (first == 0.0) return 0.0;
+        return xsub(1.0, xdiv(fmax(xsub(xdiv(second, first), bottom), 0.0), xsub(1.0, bottom)));
+    };
+    for (int i = warp; i < R; i += 8) {
+        double a = NINF, b = NINF;                         // largest, second largest of the row
+        for (int j = lane; j < C; j += 32) {
+            const double v = emb[(size_t)i * C + j];
+            if (v > a) { b = a; a = v; } else if (v > b) b = v;
+        }
+#pragma unroll
+        for (int d = 16; d; d >>= 1) {
+            const double oa = __shfl_xor_sync(0xffffffffu, a, d), ob = __shfl_xor_sync(0xffffffffu, b, d);
+            if (oa > a) { b = fmax(a, ob); a = oa; } else b = fmax(b, oa);
+        }
+        if (lane == 0) wts[i] = C < 2 ? 1.0 : weight(a, b);
+    }
+    for (int j = threadIdx.x; j < C; j += 256) {
+        double a = NINF, b = NINF;
+        for (int i = 0; i < R; ++i) {
+            const double v = emb[(size_t)i * C + j];
+            if (v > a) { b = a; a = v; } else if (v > b) b = v;
+        }
+        wts[R + j] = R < 2 ? 1.0 : weight(a, b);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < R * C; k += 256) {
+        const int i = k / C, j = k - i * C;
+        out[k] = xmul(xmul(xmul(w_assoc, wts[i]), wts[R + j]), emb[k]);
+    }
+}
+
 // gating_distance: 32 tracks per CTA factor S once (one warp), the stream's measurements are staged planar in shared
 // memory, then every thread sweeps (track, measurement) pairs with coalesced 8-byte stores.
 constexpr int GD_TRACKS = 32;
@@ -451,6 +532,27 @@ extern "C" int b200track_kf_predict(int32_t kind, int32_t n, double* mean, doubl
     if (n == 0) return 0;
     int rc = dispatch_kind(kind, [&](auto K) { kf_predict_kernel<decltype(K)::value><<<(n + KF_TPB - 1) / KF_TPB, KF_THREADS, 0, (cudaStream_t)st>>>(n, mean, cov); });
     if (rc) return rc;
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_kf_apply_warp(int32_t n, double* mean, double* cov, const double* warp, const int32_t* warp_index, void* st) {
+    if (n < 0 || !mean || !cov || !warp) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n == 0) return 0;
+    kf_gmc_kernel<<<(n + KF_TPB - 1) / KF_TPB, KF_THREADS, 0, (cudaStream_t)st>>>(n, mean, cov, warp, warp_index);
+    LAUNCH_CHECK();
+    return 0;
+}
+extern "C" int b200track_aw_max_metric(int32_t batch, int32_t rows, int32_t cols, const double* emb, double w_assoc, double bottom,
+                                       double* out, void* st) {
+    if (batch < 0 || rows < 0 || cols < 0 || !out || (!emb && batch * rows * cols > 0)) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (batch == 0 || rows == 0 || cols == 0) return 0;
+    if ((size_t)(rows + cols) * 8 > 200 * 1024) { set_error("aw_max_metric: rows + cols too large"); return B200TRACK_ERR_CAPACITY; }
+    const size_t smem = (size_t)(rows + cols) * 8;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(aw_max_metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error(cudaGetErrorString(e)); return B200TRACK_ERR_CUDA; }
+    }
+    aw_max_metric_kernel<<<batch, 256, smem, (cudaStream_t)st>>>(rows, cols, emb, w_assoc, bottom, out);
     LAUNCH_CHECK();
     return 0;
 }

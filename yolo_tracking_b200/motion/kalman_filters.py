@@ -41,6 +41,11 @@ class _KalmanFilterBase:
         """Batched update (no reference analogue: the reference loops over tracks)."""
         return _ops.kf_update(self._kind, mean, covariance, measurement)
 
+    def multi_gmc(self, mean, covariance, H=None):
+        """STrack.multi_gmc (bot_sort.py:95-111) in array form: apply a 2x3 camera-motion warp to [n, 8] / [n, 8, 8] states."""
+        H = np.eye(2, 3) if H is None else H
+        return _ops.kf_apply_warp(mean, covariance, H)
+
     def gating_distance(self, mean, covariance, measurements, only_position=False, metric="maha"):
         return _ops.kf_gating_distance(self._kind, np.asarray(mean).reshape(1, 8), np.asarray(covariance).reshape(1, 8, 8),
                                        measurements, only_position, metric)[0]

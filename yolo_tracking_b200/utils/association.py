@@ -14,3 +14,8 @@ def linear_assignment(cost_matrix):
     x, _ = _ops.lapjv(cost_matrix)
     rows = np.nonzero(x >= 0)[0]
     return np.stack([rows, x[rows]], axis=1).astype(int).reshape(-1, 2)
+
+
+def compute_aw_max_metric(emb_cost, w_association_emb, bottom=0.5):
+    """association.py:79-108 (DeepOCSORT's adaptive appearance weight): emb_cost [R, C] -> w_emb * emb_cost."""
+    return _ops.aw_max_metric(emb_cost, w_association_emb, bottom)
