@@ -202,6 +202,22 @@ int b200track_appearance_cost(int32_t batch, int32_t n_tracks, int32_t n_dets, i
 /* b200track_lapjv <- lap.lapjv(cost, extend_cost=True, cost_limit=L) as called from
  *     matching.py:64 (finite limit) and association.py:23 (cost_limit = +inf): `batch`
  *     independent problems cost[batch, rows, cols] -> x[batch, rows], y[batch, cols] (-1 = unmatched) */
+/* b200track_gallery_cost <- NearestNeighborDistanceMetric.distance with the cosine metric (matching.py:247-308, :360-378)
+ * followed by the clip of min_cost_matching (strongsort/sort/linear_assignment.py:59-78), for `batch` streams in one launch:
+ *     out[b, t, d] = min over g < count[b, t] of 1 - gallery[b, t, g]^ . det[b, d]^   (float32 like the reference)  if <= thresh
+ *                  = fill                                                                                            otherwise
+ * d_gallery [batch, n_tracks, budget, dim] fp32 (budget <= 128 rows per track, rows past count[b, t] are ignored),
+ * d_det [batch, n_dets, dim] fp32 (n_dets <= 256), dim a multiple of 64.  Tensor cores (bf16 tcgen05) pre-filter; every
+ * value that is written was recomputed exactly.  d_gallery_bf16: optional unit-norm bf16 copy of the gallery kept by the
+ * caller (b200track_unit_bf16 on the rows that changed); NULL = converted here into the workspace on every call.
+ * d_stats (3 x uint64, may be NULL): exact row evaluations, protocol errors, surviving pairs. */
+int b200track_gallery_cost_workspace(int32_t batch, int32_t n_tracks, int32_t budget, int32_t n_dets, int32_t dim,
+                                     int32_t with_gallery, uint64_t* h_bytes);
+int b200track_gallery_cost(int32_t batch, int32_t n_tracks, int32_t budget, int32_t n_dets, int32_t dim, const float* d_gallery,
+                           const void* d_gallery_bf16, const int32_t* d_count, const float* d_det, double thresh, double fill,
+                           double* d_out, void* d_workspace, uint64_t workspace_bytes, uint64_t* d_stats, void* stream);
+/* rows of fp32 -> unit-norm bf16 rows (the operand format of the two tensor-core operators) */
+int b200track_unit_bf16(int64_t rows, int32_t dim, const float* d_src, void* d_dst, void* stream);
 int b200track_lapjv(int32_t batch, int32_t rows, int32_t cols, const double* d_cost, double cost_limit,
                     int32_t* d_x, int32_t* d_y, void* stream);
 

@@ -312,3 +312,38 @@ def test_adaptive_weight_operator_matches_reference():
     assert_close(out[0], g["aw_out3"], what="batched aw")
     from oracle.deepocsort import compute_aw_max_metric
     assert_close(out[1], compute_aw_max_metric(batch[1], 0.75, 0.5), what="batched aw 1")
+
+
+@pytest.mark.parametrize("B, T, G, D, F", [(2, 5, 100, 37, 128), (3, 9, 128, 200, 512), (1, 3, 7, 256, 64)])
+def test_gallery_cost_tensor_core_operator(B, T, G, D, F):
+    """b200track_gallery_cost (tcgen05 pre-filter + exact float32 re-evaluation) against the reference arithmetic of
+    NearestNeighborDistanceMetric (matching.py:247-267, float32 numpy) followed by the clip of min_cost_matching: the same
+    entries survive the threshold, surviving values agree to float32 rounding; ragged / empty galleries."""
+    from yolo_tracking_b200 import _ops
+    rng = np.random.default_rng(B * 1000 + T)
+    proto = rng.standard_normal((B, T, F)).astype(np.float32)
+    gal = (proto[:, :, None, :] + 0.25 * rng.standard_normal((B, T, G, F))).astype(np.float32)
+    count = rng.integers(1, G + 1, (B, T)).astype(np.int32)
+    count[0, 0] = 0                                         # a track without stored features: nothing matches
+    count[-1, -1] = G
+    owner = rng.integers(0, T, (B, D))
+    det = (proto[np.arange(B)[:, None], owner] + 0.45 * rng.standard_normal((B, D, F))).astype(np.float32)
+    thresh = 0.2
+    got, st = _ops.gallery_cost(gal, count, det, thresh, return_stats=True)
+    ref = np.full((B, T, D), thresh + 1e-5)
+    raw = np.full((B, T, D), np.inf)
+    for b in range(B):
+        bn = det[b] / np.linalg.norm(det[b], axis=1, keepdims=True)
+        for t in range(T):
+            if count[b, t] == 0:
+                continue
+            a = gal[b, t, :count[b, t]]
+            a = a / np.linalg.norm(a, axis=1, keepdims=True)
+            raw[b, t] = (1.0 - np.dot(a, bn.T)).min(axis=0)
+    keep = raw <= thresh
+    ref[keep] = raw[keep]
+    assert np.abs(raw - thresh).min() > 1e-5, "test data too close to the threshold for a float32 comparison"
+    assert np.array_equal(got <= thresh, keep)
+    assert keep.sum() > 0 and (~keep).sum() > 0
+    assert np.allclose(got, ref, rtol=0, atol=2e-6)
+    assert st[2] >= keep.sum()                              # every surviving pair went through the exact path

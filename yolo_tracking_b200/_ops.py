@@ -200,6 +200,33 @@ def appearance_cost(trk, det, scale=0.5, thresh=0.25, fill=1.0, gate=None, retur
     return (res, int(st[0])) if return_stats else res
 
 
+def gallery_cost(gallery, count, det, thresh=0.2, fill=None, return_stats=False):
+    """Thresholded gallery distance of StrongSORT for a batch of streams (matching.py:247-378 + linear_assignment.py:59-78):
+    gallery [B, T, G, F] float32, count [B, T], det [B, D, F] -> cost [B, T, D] float64 (tensor-core pre-filter, exact values)."""
+    lib = _lib.load()
+    torch = _torch()
+    gal = np.asarray(gallery, dtype=np.float32)
+    dt = np.asarray(det, dtype=np.float32)
+    B, T, G, F = gal.shape
+    D = dt.shape[1]
+    fill = thresh + 1e-5 if fill is None else fill
+    if B * T * D == 0:
+        return np.zeros((B, T, D))
+    dg, dc, dd = _dev(gal, np.float32), _dev(np.asarray(count).reshape(B, T), np.int32), _dev(dt, np.float32)
+    need = C.c_uint64()
+    _lib.check(lib.b200track_gallery_cost_workspace(B, T, G, D, F, 1, C.byref(need)))
+    ws = torch.empty((max(int(need.value), 1),), dtype=torch.uint8, device=dg.device)
+    out = torch.empty((B, T, D), dtype=torch.float64, device=dg.device)
+    st = torch.zeros((3,), dtype=torch.int64, device=dg.device)
+    _sync_check(lib.b200track_gallery_cost(B, T, G, D, F, _p(dg), None, _p(dc), _p(dd), float(thresh), float(fill), _p(out), _p(ws),
+                                           int(need.value), _p(st), None))
+    st = st.cpu().numpy()
+    if st[1]:
+        raise RuntimeError("gallery_cost: tensor-core pipeline protocol error")
+    res = out.cpu().numpy()
+    return (res, st) if return_stats else res
+
+
 def nn_cosine_distance(galleries, det_feats):
     """galleries: list (one per track) of [n_t, F] float32 arrays; det_feats [D, F] -> cost [T, D] float64
     (NearestNeighborDistanceMetric.distance, matching.py:360-378)."""

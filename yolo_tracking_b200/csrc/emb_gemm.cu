@@ -258,6 +258,206 @@ appearance_cost_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (lane == 0 && g.stats && done) atomicAdd(&g.stats[0], (unsigned long long)done);
 }
 
+// ---- kernel 3: StrongSORT's gallery distance -------------------------------------------------------
+//     out[b, t, d] = min over the stored features g < count[b, t] of track t of  1 - a_g^ . b_d^      if that is <= thresh
+//                  = fill                                                                            otherwise
+// (NearestNeighborDistanceMetric.distance with _nn_cosine_distance, boxmot/utils/matching.py:247-308, :360-378, followed
+// by the clip of strongsort/sort/linear_assignment.py:59-78: everything above max_distance becomes one value).
+// This is the GEMM-shaped part of the tracking loop proper: per stream [T x G, F] . [F, D] with G up to 128 stored
+// features per track (2 * T * G * D * F flop, 4.1 GFLOP per stream and frame at T = D = 200, G = 100, F = 512).
+// One CTA per (track, stream): M = 128 gallery rows of that track (TMA zero-fills the rows past the budget), N = the
+// stream's detections (<= 256), K = F through the same 2-stage TMA / tcgen05 ring as above; two CTAs share an SM so
+// one's epilogue runs under the other's MMAs.  Epilogue: column maxima of the cosine tile over the 128 TMEM lanes
+// (register butterfly inside a warp, shared memory across the four warps), threshold test on 1 - max with the bf16
+// band, then the surviving (track, detection) pairs - about one per track - are re-evaluated exactly in float32 on
+// the fp32 gallery, restricted to the rows whose bf16 cosine is within the band of the column maximum.
+struct GalleryArgs {
+    int n_trk, budget, n_det, dim, npad;
+    const float* gallery;                 // [B, n_trk, budget, dim] fp32
+    const int* count;                     // [B, n_trk]
+    const float* det;                     // [B, n_det, dim] fp32
+    double thresh, fill;
+    double* out;                          // [B, n_trk, n_det]
+    unsigned long long* stats;            // [0] exact row evaluations, [1] protocol errors, [2] candidate pairs
+};
+
+__global__ void __launch_bounds__(GEMM_THREADS, 2)
+gallery_cost_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const GalleryArgs g) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int fail_s, ncand_s;
+    __shared__ float colmax[4][BN_MAX];                    // per epilogue warp: max cosine of every column over its 32 rows
+    __shared__ int cand[BN_MAX];                           // surviving detections of this track
+    __shared__ uint32_t rowbits[BN_MAX][4];                // per surviving detection: gallery rows worth an exact evaluation
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x, b = blockIdx.y;
+    const int nk = g.dim / BK;
+    const int ncols = g.n_det, npad = g.npad;
+    const int cnt = min(g.count[(size_t)b * g.n_trk + t], min(g.budget, BM));
+    double* orow = g.out + ((size_t)b * g.n_trk + t) * g.n_det;
+    if (cnt <= 0) {                                        // no stored feature: nothing can match (uniform exit)
+        for (int c = threadIdx.x; c < ncols; c += GEMM_THREADS) orow[c] = g.fill;
+        return;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        fail_s = 0; ncand_s = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(256));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ===== TMA producer =====
+            const uint32_t tx = (uint32_t)(A_BYTES + npad * BK * 2);
+            for (int kb = 0; kb < nk; ++kb) {
+                const int s = kb % STAGES;
+                if (kb >= STAGES && !mbar_wait(&empty_bar[s], ((kb / STAGES) - 1) & 1)) { fail_s = 1; break; }
+                unsigned char* sa = smem + (size_t)s * STAGE_BYTES;
+                mbar_expect_tx(&full_bar[s], tx);
+                tma_load_3d(sa, &map_a, &full_bar[s], kb * BK, 0, b * g.n_trk + t);
+                tma_load_3d(sa + A_BYTES, &map_b, &full_bar[s], kb * BK, 0, b);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                   // ===== MMA issuer =====
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(npad >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            bool ok = true;
+            for (int kb = 0; kb < nk && ok; ++kb) {
+                const int s = kb % STAGES;
+                ok = mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+                if (!ok) { fail_s = 1; break; }
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)s * STAGE_BYTES);
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k)
+                    umma_bf16(tmem_base, umma_desc_sw128(sa + k * 32), umma_desc_sw128(sa + A_BYTES + k * 32), idesc, (kb | k) ? 1u : 0u);
+                umma_commit(&empty_bar[s]);
+            }
+            umma_commit(&acc_bar);
+        }
+    }
+    // ===== epilogue =====
+    bool acc_ok = mbar_wait(&acc_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (!acc_ok) fail_s = 1;
+    __syncthreads();
+    const bool failed = fail_s != 0;
+    const float NEG = -3.0e38f;
+    if (warp >= 2 && !failed) {
+        const int q = warp & 3;                            // TMEM lanes 32 q .. 32 q + 31 = gallery rows
+        const bool row_ok = q * 32 + lane < cnt;
+        for (int c0 = 0; c0 < npad; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = row_ok ? __uint_as_float(v[i]) : NEG;
+            // butterfly with halving: after the 16 / 8 / 4 / 2 steps a lane holds one column's maximum over 16 lanes
+#pragma unroll
+            for (int h = 8, d = 16; h >= 1; h >>= 1, d >>= 1) {
+                const bool up = (lane & d) != 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (i < h) {
+                        const float keep = up ? f[i + h] : f[i];
+                        const float give = up ? f[i] : f[i + h];
+                        f[i] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, give, d));
+                    }
+                }
+            }
+            f[0] = fmaxf(f[0], __shfl_xor_sync(0xffffffffu, f[0], 1));
+            // column held by this lane: bit 4 of the lane chose +8, bit 3 +4, bit 2 +2, bit 1 +1
+            const int col = c0 + ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+            if ((lane & 1) == 0) colmax[q][col] = f[0];
+        }
+    }
+    __syncthreads();
+    // candidate iff 1 - max cos <= thresh + band  (NaN -> candidate); everything else is `fill`
+    const float cos_lim = (float)(1.0 - g.thresh - BAND_COS) - 1e-6f;
+    if (!failed) {
+        for (int c = threadIdx.x; c < ncols; c += GEMM_THREADS) {
+            const float m = fmaxf(fmaxf(colmax[0][c], colmax[1][c]), fmaxf(colmax[2][c], colmax[3][c]));
+            if (!(m < cos_lim)) {
+                const int k = atomicAdd(&ncand_s, 1);
+                cand[k] = c;
+                colmax[0][c] = m;                          // the overall maximum, read back by the row filter
+                rowbits[k][0] = rowbits[k][1] = rowbits[k][2] = rowbits[k][3] = 0u;
+            } else orow[c] = g.fill;
+        }
+    }
+    __syncthreads();
+    const int nc = ncand_s;
+    // rows of a surviving column that can hold the exact maximum: bf16 cosine within twice the band of the column maximum
+    if (warp >= 2 && !failed && nc > 0) {
+        const int q = warp & 3;
+        const bool row_ok = q * 32 + lane < cnt;
+        for (int k = 0; k < nc; ++k) {
+            const int c = cand[k];
+            uint32_t v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c & ~15), v);     // warp-collective
+            float x = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) if (i == (c & 15)) x = __uint_as_float(v[i]);
+            const bool keep = row_ok && !(x < colmax[0][c] - (float)(2.0 * BAND_COS));
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (lane == 0) rowbits[k][q] = m;
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256));
+    if (failed) {
+        if (threadIdx.x == 0 && g.stats) atomicAdd(&g.stats[1], 1ull);
+        return;
+    }
+    // exact float32 re-evaluation (matching.py:247-267: rows normalised, 1 - dot), one warp per surviving detection
+    const int nv = g.dim >> 2;
+    unsigned long long done = 0;
+    for (int k = warp; k < nc; k += GEMM_THREADS / 32) {
+        const int d = cand[k];
+        const float4* bb = reinterpret_cast<const float4*>(g.det + ((size_t)b * g.n_det + d) * g.dim);
+        float vv = 0.f;
+        for (int i = lane; i < nv; i += 32) { const float4 y = bb[i]; vv += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w; }
+#pragma unroll
+        for (int s = 16; s; s >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, s);
+        const float nb = sqrtf(vv);
+        float best = 3.0e38f;
+        for (int w = 0; w < 4; ++w) {
+            uint32_t bits = rowbits[k][w];
+            while (bits) {
+                const int r = w * 32 + __ffs(bits) - 1;
+                bits &= bits - 1;
+                const float4* a = reinterpret_cast<const float4*>(g.gallery + (((size_t)b * g.n_trk + t) * g.budget + r) * g.dim);
+                float uv = 0.f, uu = 0.f;
+                for (int i = lane; i < nv; i += 32) {
+                    const float4 x = a[i], y = bb[i];
+                    uv += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+                    uu += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+                }
+#pragma unroll
+                for (int s = 16; s; s >>= 1) { uv += __shfl_xor_sync(0xffffffffu, uv, s); uu += __shfl_xor_sync(0xffffffffu, uu, s); }
+                best = fminf(best, 1.0f - uv / (sqrtf(uu) * nb));
+                ++done;
+            }
+        }
+        if (lane == 0) orow[d] = ((double)best > g.thresh) ? g.fill : (double)best;
+    }
+    if (lane == 0 && g.stats) {
+        if (done) atomicAdd(&g.stats[0], done);
+        if (warp == 0 && nc) atomicAdd(&g.stats[2], (unsigned long long)nc);
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -283,6 +483,12 @@ bool make_map(CUtensorMap* m, const void* base, int batch, int rows, int dim, in
     const cuuint32_t estr[3] = {1, 1, 1};
     return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t gallery_ws_bytes(int batch, int n_trk, int budget, int n_det, int dim, bool with_gallery) {
+    const size_t a = with_gallery ? (((size_t)batch * n_trk * budget * dim * 2 + 255) & ~size_t(255)) : 0;
+    const size_t b = ((size_t)batch * n_det * dim * 2 + 255) & ~size_t(255);
+    return a + b;
 }
 
 size_t ws_bytes(int batch, int n_trk, int n_det, int dim) {
@@ -331,6 +537,63 @@ extern "C" int b200track_appearance_cost(int32_t batch, int32_t n_tracks, int32_
     B200_CU_TRY(cudaFuncSetAttribute(appearance_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((n_tracks + BM - 1) / BM, (n_dets + BN_MAX - 1) / BN_MAX, batch);
     appearance_cost_kernel<<<grid, GEMM_THREADS, smem, stream>>>(ma, mb, g);
+    B200_CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200track_unit_bf16(int64_t rows, int32_t dim, const float* d_src, void* d_dst, void* st) {
+    if (rows < 0 || dim <= 0 || dim % 4 || !d_dst || (!d_src && rows > 0)) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (rows == 0) return 0;
+    unit_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)st>>>(d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), rows, dim);
+    B200_CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200track_gallery_cost_workspace(int32_t batch, int32_t n_tracks, int32_t budget, int32_t n_dets, int32_t dim,
+                                                int32_t with_gallery, uint64_t* h_bytes) {
+    if (batch < 0 || n_tracks < 0 || budget < 0 || n_dets < 0 || dim <= 0 || !h_bytes) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    *h_bytes = gallery_ws_bytes(batch, n_tracks, budget, n_dets, dim, with_gallery != 0);
+    return 0;
+}
+
+extern "C" int b200track_gallery_cost(int32_t batch, int32_t n_tracks, int32_t budget, int32_t n_dets, int32_t dim,
+                                      const float* d_gallery, const void* d_gallery_bf16, const int32_t* d_count, const float* d_det,
+                                      double thresh, double fill, double* d_out, void* d_workspace, uint64_t workspace_bytes,
+                                      uint64_t* d_stats, void* st) {
+    if (batch < 0 || n_tracks < 0 || n_dets < 0 || budget < 0 || !d_out) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (dim <= 0 || dim % 64) { set_error("dim must be a positive multiple of 64"); return B200TRACK_ERR_ARG; }
+    if (budget > BM) { set_error("gallery budget above 128 rows per track"); return B200TRACK_ERR_CAPACITY; }
+    if (n_dets > BN_MAX) { set_error("more than 256 detections per stream"); return B200TRACK_ERR_CAPACITY; }
+    if (batch == 0 || n_tracks == 0 || n_dets == 0) return 0;
+    if (batch > 65535) { set_error("batch > 65535"); return B200TRACK_ERR_ARG; }
+    if (!d_gallery || !d_count || !d_det || !d_workspace || budget == 0) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    const bool own = d_gallery_bf16 == nullptr;
+    if (workspace_bytes < gallery_ws_bytes(batch, n_tracks, budget, n_dets, dim, own)) { set_error("workspace too small"); return B200TRACK_ERR_ARG; }
+    cudaStream_t stream = (cudaStream_t)st;
+    unsigned char* ws = reinterpret_cast<unsigned char*>(d_workspace);
+    const __nv_bfloat16* ga = reinterpret_cast<const __nv_bfloat16*>(d_gallery_bf16);
+    if (own) {
+        const long long ra = (long long)batch * n_tracks * budget;
+        unit_bf16_kernel<<<(unsigned)((ra + 7) / 8), 256, 0, stream>>>(d_gallery, reinterpret_cast<__nv_bfloat16*>(ws), ra, dim);
+        ga = reinterpret_cast<const __nv_bfloat16*>(ws);
+        ws += ((size_t)ra * dim * 2 + 255) & ~size_t(255);
+    }
+    __nv_bfloat16* wb = reinterpret_cast<__nv_bfloat16*>(ws);
+    const long long rb = (long long)batch * n_dets;
+    unit_bf16_kernel<<<(unsigned)((rb + 7) / 8), 256, 0, stream>>>(d_det, wb, rb, dim);
+    B200_CU_TRY(cudaGetLastError());
+    const int box_n = std::min((n_dets + 15) & ~15, BN_MAX);
+    CUtensorMap ma, mb;
+    if (!make_map(&ma, ga, batch * n_tracks, budget, dim, BM) || !make_map(&mb, wb, batch, n_dets, dim, box_n)) {
+        set_error("cuTensorMapEncodeTiled failed"); return B200TRACK_ERR_CUDA; }
+    GalleryArgs g;
+    g.n_trk = n_tracks; g.budget = budget; g.n_det = n_dets; g.dim = dim; g.npad = box_n;
+    g.gallery = d_gallery; g.count = d_count; g.det = d_det; g.thresh = thresh; g.fill = fill; g.out = d_out;
+    g.stats = reinterpret_cast<unsigned long long*>(d_stats);
+    const size_t smem = (size_t)STAGES * STAGE_BYTES + 1024;
+    B200_CU_TRY(cudaFuncSetAttribute(gallery_cost_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(n_tracks, batch, 1);
+    gallery_cost_kernel<<<grid, GEMM_THREADS, smem, stream>>>(ma, mb, g);
     B200_CU_TRY(cudaGetLastError());
     return 0;
 }
