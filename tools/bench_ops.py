@@ -26,6 +26,8 @@ ap.add_argument("--dim", type=int, default=512)
 ap.add_argument("--iters", type=int, default=20)
 ap.add_argument("--kf-tracks", type=int, default=819200, help="tracks of the Kalman-operator lines (state 4x the L2)")
 ap.add_argument("--only", default="")
+ap.add_argument("--gallery-streams", type=int, default=256, help="streams of the StrongSORT gallery line (21 MB of fp32 gallery per stream at 200 x 100 x 512)")
+ap.add_argument("--budget", type=int, default=100)
 args = ap.parse_args()
 S, T, D, F = args.streams, args.tracks, args.dets, args.dim
 lib = _lib.load()
@@ -166,3 +168,38 @@ if on("config4_pair"):
     ms, best = timeit(both, False)
     report("config 4 back to back: gating_distance + gated cosine cost", ms, best,
            extra={"streams": S, "tracks": T, "dets": D, "dim": F, "track_updates_per_s": S * T / (ms * 1e-3)})
+
+if on("gallery"):
+    # StrongSORT's gallery distance: T tracks x G stored features each against D detections per stream.
+    # The fp32 gallery and its unit-norm bf16 copy are tracker state (one row per confirmed track changes per frame), so
+    # both are resident; the detections are converted inside the timed region.
+    S3, G = args.gallery_streams, args.budget
+    del trk, out, ws, gd, gate
+    torch.cuda.empty_cache()
+    proto3 = torch.randn((S3, max(T, D), F), device=dev)
+    gal = torch.empty((S3, T, G, F), dtype=torch.float32, device=dev)
+    for b0 in range(0, S3, 16):                              # chunked: 16 streams of noise at a time
+        b1 = min(S3, b0 + 16)
+        gal[b0:b1] = proto3[b0:b1, :T, None, :] + 0.25 * torch.randn((b1 - b0, T, G, F), device=dev)
+    det3 = (proto3[:, :D] + 0.45 * torch.randn((S3, D, F), device=dev)).contiguous()
+    cnt3 = torch.full((S3, T), G, dtype=torch.int32, device=dev)
+    gal16 = torch.empty((S3, T, G, F), dtype=torch.bfloat16, device=dev)
+    _lib.check(lib.b200track_unit_bf16(S3 * T * G, F, p(gal), p(gal16), None))
+    out3 = torch.empty((S3, T, D), dtype=torch.float64, device=dev)
+    nb3 = C.c_uint64()
+    _lib.check(lib.b200track_gallery_cost_workspace(S3, T, G, D, F, 0, C.byref(nb3)))
+    ws3 = torch.empty((int(nb3.value),), dtype=torch.uint8, device=dev)
+    st3 = torch.zeros((3,), dtype=torch.int64, device=dev)
+    fn = lambda: _lib.check(lib.b200track_gallery_cost(S3, T, G, D, F, p(gal), p(gal16), p(cnt3), p(det3), 0.2, 0.20001, p(out3), p(ws3),
+                                                       int(nb3.value), p(st3), None))
+    ms, best = timeit(fn, False)
+    n_calls = 3 + args.iters
+    flops3 = 2.0 * S3 * T * G * D * F
+    rows3 = int(st3[0].item()) / n_calls
+    line_bytes = S3 * T * G * F * 2 + S3 * D * F * 4 + S3 * T * D * 8 + rows3 * F * 4
+    report("unit_bf16_kernel (detections) + gallery_cost_kernel (tcgen05): StrongSORT gallery distance, max_dist 0.2", ms, best,
+           flops=flops3, alg_bytes=line_bytes, l2="bf16 gallery %d MB > L2" % ((S3 * T * G * F * 2) >> 20),
+           extra={"streams": S3, "tracks": T, "budget": G, "dets": D, "dim": F, "pairs": S3 * T * D, "pairs_per_s": S3 * T * D / (ms * 1e-3),
+                  "track_updates_per_s": S3 * T / (ms * 1e-3), "surviving_pairs_per_launch": int(st3[2].item()) / n_calls,
+                  "exact_rows_per_launch": rows3, "errors": int(st3[1].item()),
+                  "kept_frac": float((out3 <= 0.2).double().mean().item())})

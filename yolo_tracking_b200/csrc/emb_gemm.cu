@@ -420,10 +420,14 @@ gallery_cost_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (threadIdx.x == 0 && g.stats) atomicAdd(&g.stats[1], 1ull);
         return;
     }
-    // exact float32 re-evaluation (matching.py:247-267: rows normalised, 1 - dot), one warp per surviving detection
+    // exact float32 re-evaluation (matching.py:247-267: rows normalised, 1 - dot).  A surviving pair needs up to `count`
+    // gallery rows of 2 KB each and there is about one pair per CTA, so all six warps share a pair: warp w takes every
+    // sixth kept row, two rows in flight at a time, and the minima meet in shared memory.
+    __shared__ float wbest[GEMM_THREADS / 32];
     const int nv = g.dim >> 2;
     unsigned long long done = 0;
-    for (int k = warp; k < nc; k += GEMM_THREADS / 32) {
+    const float* gbase = g.gallery + ((size_t)b * g.n_trk + t) * g.budget * g.dim;
+    for (int k = 0; k < nc; ++k) {
         const int d = cand[k];
         const float4* bb = reinterpret_cast<const float4*>(g.det + ((size_t)b * g.n_det + d) * g.dim);
         float vv = 0.f;
@@ -432,25 +436,45 @@ gallery_cost_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int s = 16; s; s >>= 1) vv += __shfl_xor_sync(0xffffffffu, vv, s);
         const float nb = sqrtf(vv);
         float best = 3.0e38f;
+        auto eval2 = [&](int r0, int r1) {                 // r1 < 0: single row
+            const float4* a0 = reinterpret_cast<const float4*>(gbase + (size_t)r0 * g.dim);
+            const float4* a1 = reinterpret_cast<const float4*>(gbase + (size_t)(r1 < 0 ? r0 : r1) * g.dim);
+            float uv0 = 0.f, uu0 = 0.f, uv1 = 0.f, uu1 = 0.f;
+            for (int i = lane; i < nv; i += 32) {
+                const float4 x0 = a0[i], x1 = a1[i], y = bb[i];
+                uv0 += x0.x * y.x + x0.y * y.y + x0.z * y.z + x0.w * y.w;
+                uu0 += x0.x * x0.x + x0.y * x0.y + x0.z * x0.z + x0.w * x0.w;
+                uv1 += x1.x * y.x + x1.y * y.y + x1.z * y.z + x1.w * y.w;
+                uu1 += x1.x * x1.x + x1.y * x1.y + x1.z * x1.z + x1.w * x1.w;
+            }
+#pragma unroll
+            for (int s = 16; s; s >>= 1) {
+                uv0 += __shfl_xor_sync(0xffffffffu, uv0, s); uu0 += __shfl_xor_sync(0xffffffffu, uu0, s);
+                uv1 += __shfl_xor_sync(0xffffffffu, uv1, s); uu1 += __shfl_xor_sync(0xffffffffu, uu1, s);
+            }
+            best = fminf(best, fminf(1.0f - uv0 / (sqrtf(uu0) * nb), 1.0f - uv1 / (sqrtf(uu1) * nb)));
+            done += r1 < 0 ? 1 : 2;
+        };
+        int seen = 0, pend = -1;
         for (int w = 0; w < 4; ++w) {
             uint32_t bits = rowbits[k][w];
             while (bits) {
                 const int r = w * 32 + __ffs(bits) - 1;
                 bits &= bits - 1;
-                const float4* a = reinterpret_cast<const float4*>(g.gallery + (((size_t)b * g.n_trk + t) * g.budget + r) * g.dim);
-                float uv = 0.f, uu = 0.f;
-                for (int i = lane; i < nv; i += 32) {
-                    const float4 x = a[i], y = bb[i];
-                    uv += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
-                    uu += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
-                }
-#pragma unroll
-                for (int s = 16; s; s >>= 1) { uv += __shfl_xor_sync(0xffffffffu, uv, s); uu += __shfl_xor_sync(0xffffffffu, uu, s); }
-                best = fminf(best, 1.0f - uv / (sqrtf(uu) * nb));
-                ++done;
+                if (seen++ % (GEMM_THREADS / 32) != warp) continue;
+                if (pend < 0) pend = r; else { eval2(pend, r); pend = -1; }
             }
         }
-        if (lane == 0) orow[d] = ((double)best > g.thresh) ? g.fill : (double)best;
+        if (pend >= 0) eval2(pend, -1);
+        if (lane == 0) wbest[warp] = best;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float m = wbest[0];
+#pragma unroll
+            for (int w = 1; w < GEMM_THREADS / 32; ++w) m = fminf(m, wbest[w]);
+            orow[d] = ((double)m > g.thresh) ? g.fill : (double)m;
+        }
+        __syncthreads();
     }
     if (lane == 0 && g.stats) {
         if (done) atomicAdd(&g.stats[0], done);
