@@ -64,3 +64,43 @@ def test_kalman_and_matching_mirrors():
     cost = matching.iou_distance(a, a)
     assert np.array_equal(matching.fuse_score(cost, np.array([0.9, 0.8])), 1 - (1 - cost) * np.array([0.9, 0.8])[None])
     assert matching.iou_distance(np.zeros((0, 4)), a).shape == (0, 2)
+
+
+def test_per_class_tracker_is_one_stream_per_class():
+    """Per-class tracking: every class is an independent stream of one device context; results equal
+    one oracle tracker per class, ids are unique across classes, det_ind points into the caller's rows."""
+    from oracle.bytetrack import ByteTrackOracle
+    from yolo_tracking_b200.per_class import PerClassTracker
+    from yolo_tracking_b200.synth import make_stream
+    C_ = 3
+    streams = [make_stream(6, 40 + c, 14, 30) for c in range(C_)]
+    trk = PerClassTracker("bytetrack", n_classes=4, max_tracks=64, max_dets=64, track_thresh=0.5, match_thresh=0.8, track_buffer=30,
+                          frame_rate=30)
+    oracles = [ByteTrackOracle(0.5, 0.8, 30, 30) for _ in range(4)]
+    rng = np.random.default_rng(3)
+    for f in range(30):
+        parts = []
+        for c in range(C_):
+            d = streams[c][0][f, :streams[c][1][f]].copy()
+            d[:, 5] = c
+            parts.append(d)
+        dets = np.concatenate(parts, axis=0)
+        perm = rng.permutation(len(dets))
+        dets = dets[perm]
+        out = trk.update(dets, None)
+        ref_rows = []
+        for c in range(4):
+            idx = np.nonzero(dets[:, 5] == c)[0]
+            r = oracles[c].update(dets[idx], None).reshape(-1, 8)
+            if len(r):
+                r = r.copy()
+                r[:, 4] = (r[:, 4] - 1) * 4 + c + 1
+                r[:, 7] = idx[r[:, 7].astype(int)]
+                ref_rows.append(r)
+        ref = np.concatenate(ref_rows, axis=0) if ref_rows else np.empty((0, 8))
+        assert out.shape == ref.shape, f"frame {f}"
+        assert np.array_equal(out[:, 4:], ref[:, 4:]), f"frame {f}"
+        assert np.allclose(out[:, :4], ref[:, :4], rtol=1e-9, atol=1e-9)
+        assert len(set(out[:, 4])) == len(out)
+        assert np.array_equal(dets[out[:, 7].astype(int), 5], out[:, 6])
+    trk.close()

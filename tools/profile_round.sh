@@ -18,7 +18,7 @@ LL="--metrics gpu__time_duration.sum --clock-control none -c 400 --csv"
 BT="python bench.py --steps 20 --warmup 5 --no-cpu-baseline"
 OC="python bench.py --workload ocsort --streams 1024 --steps 20 --warmup 5 --no-cpu-baseline"
 BS="python bench.py --workload botsort --streams 512 --steps 20 --warmup 5 --no-cpu-baseline"
-OP="python tools/bench_ops.py --iters 3"
+OP="python tools/bench_ops.py --iters 3 --gallery-streams 64"
 run ll_bytetrack $LL --log-file $O/${R}_launches_bytetrack.csv -- $BT
 run ll_ocsort $LL --log-file $O/${R}_launches_ocsort.csv -- $OC
 run ll_botsort $LL --log-file $O/${R}_launches_botsort.csv -- $BS
@@ -28,5 +28,6 @@ run full_bytetrack $FULL -k regex:bytetrack_step -s 12 -c 1 -o $O/${R}_full_byte
 run full_ocsort $FULL -k regex:ocsort_step -s 12 -c 1 -o $O/${R}_full_ocsort -f -- $OC
 run full_botsort $FULL -k regex:bytetrack_step -s 12 -c 1 -o $O/${R}_full_botsort -f -- $BS
 run full_appearance $FULL -k regex:appearance_cost -s 1 -c 1 -o $O/${R}_full_appearance -f -- $OP --only appearance
-run full_kf $FULL -k regex:kf_ -c 4 -o $O/${R}_full_kf -f -- $OP --only kf_predict,kf_update,kf_project,gating
+run full_kf $FULL -k regex:"kf_(predict|update|project|gating)" -c 4 -o $O/${R}_full_kf -f -- $OP --only kf_predict,kf_update,kf_project,gating
+run full_gallery $FULL -k regex:gallery_cost -s 1 -c 1 -o $O/${R}_full_gallery -f -- $OP --only gallery --gallery-streams 64 --kf-tracks 1000 --streams 8
 ls -la $O | grep ${R}_

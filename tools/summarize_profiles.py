@@ -19,7 +19,7 @@ os.makedirs(P, exist_ok=True)
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
-        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_registers",
         "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "smsp__average_warp_latency_issue_stalled_barrier.pct",
@@ -67,7 +67,7 @@ try:
     traffic = json.load(open(os.path.join(P, "traffic.json")))
 except Exception:
     pass
-for cap in ("bytetrack", "ocsort", "botsort", "appearance", "kf"):
+for cap in ("bytetrack", "ocsort", "botsort", "appearance", "gallery", "kf"):
     rep = os.path.join(G, f"{R}_full_{cap}.ncu-rep")
     if not os.path.exists(rep):
         continue
