@@ -161,19 +161,41 @@ template <int KIND>
 __global__ void __launch_bounds__(KFU_TPB * KF_LANES, 4) kf_update_kernel(int n, double* mean, double* cov, const double* __restrict__ z,
                                                                          const double* __restrict__ conf) {
     __shared__ double sm[KFU_TPB * KF_STRIDE];
+    __shared__ double sF[KFU_TPB][15];             // per track: L (10 lower-triangle entries), 1 / L[i][i] (4); stride 15 = conflict-free
     const int base = blockIdx.x * KFU_TPB, cnt = min(KFU_TPB, n - base);
     const int t = threadIdx.x / KF_LANES, r = threadIdx.x % KF_LANES;
     kf_stage_in(sm, mean, cov, base, cnt);
+    // The 4x4 factorisation (4 sqrt, 6 divisions, 4 reciprocals: most of the kernel's fp64 instructions) is common to the
+    // eight lanes of a track: the first warp factors all 32 tracks of the CTA, one per lane, instead of every lane for itself.
+    if (threadIdx.x < cnt) {
+        const int q = threadIdx.x;
+        const double* m = sm + q * KF_STRIDE;
+        double S[4][4], L[4][4];
+        kf_innovation<KIND>(m, m + 8, conf ? conf[base + q] : 0.0, S);
+        chol_lower<4>(S, L);
+        int o = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) sF[q][o++] = L[i][j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sF[q][10 + i] = 1.0 / L[i][i];
+    }
+    __syncthreads();
     double row[8], mr = 0.0;
     if (t < cnt) {
         const double* m = sm + t * KF_STRIDE;
         const double* P = m + 8;
-        // every lane of the group factors the 4x4 S itself (a dependent sqrt / divide chain either way; no hand-off)
-        double S[4][4], L[4][4], inv[4];
-        kf_innovation<KIND>(m, P, conf ? conf[base + t] : 0.0, S);
-        chol_lower<4>(S, L);
+        double L[4][4], inv[4];
+        {
+            int o = 0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) inv[i] = 1.0 / L[i][i];
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) L[i][j] = sF[t][o++];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) inv[i] = sF[t][10 + i];
+        }
         double y[4], k[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {                 // L y = P[r, :4]
