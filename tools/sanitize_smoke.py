@@ -50,4 +50,20 @@ _ops.embedding_distance(rng.standard_normal((37, 96)), rng.standard_normal((29, 
 _ops.appearance_cost(rng.standard_normal((2, 150, 128)), rng.standard_normal((2, 70, 128)), 0.5, 0.45, 1.0, gate=rng.random((2, 150, 70)) < 0.3)
 _ops.lapjv(rng.random((3, 40, 55)), 0.6)
 _ops.lapjv(-rng.random((3, 40, 55)))
+_ops.linear_sum_assignment(np.minimum(rng.random((2, 30, 45)), 0.4))
+_ops.kf_apply_warp(m, c, np.array([[1.01, 0.02, 3.0], [-0.02, 0.99, -1.0]]))
+_ops.aw_max_metric(rng.random((2, 33, 47)), 0.75)
+gal = rng.standard_normal((2, 6, 100, 128)).astype(np.float32)
+_ops.gallery_cost(gal, rng.integers(0, 101, (2, 6)), gal[:, :, 3] + 0.1 * rng.standard_normal((2, 6, 128)).astype(np.float32), 0.2)
+_ops.nn_cosine_distance([gal[0, 0, :5], gal[0, 1, :9]], gal[0, :, 3])
+# crowded scene: the pair list and the edge cache of the ByteTrack step overflow (bitmask graph, union-find solver)
+dets, nd, _ = make_batch(7, 2, 40, 8, dmax=64, fp_rate=0.5)
+ctr, half = 0.5 * (dets[..., :2] + dets[..., 2:4]), 0.5 * (dets[..., 2:4] - dets[..., :2])
+dets[..., :2], dets[..., 2:4] = ctr * 0.1 - half, ctr * 0.1 + half
+dets[np.arange(64)[None, None, :] >= nd[:, :, None]] = 0.0
+trk = BatchedTracker("bytetrack", 2, max_tracks=64, max_dets=64, track_thresh=0.5, match_thresh=0.8, track_buffer=30, frame_rate=30)
+for f in range(8):
+    trk.update_batch(np.ascontiguousarray(dets[f]), np.ascontiguousarray(nd[f]))
+trk.sync()
+trk.close()
 print("ops ok", flush=True)
