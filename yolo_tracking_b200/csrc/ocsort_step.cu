@@ -86,6 +86,36 @@ __device__ __forceinline__ double oc_sim(int func, const Box& a, const Box& b, d
     }
 }
 
+// acos for the velocity-direction term, branch-free.  libm's acos takes different paths for small and large |x| and a warp of
+// (track, detection) pairs takes all of them (it was a quarter of the step's instructions at 13 active lanes); here both
+// ranges share one polynomial: asin(s) = s + s z g(z) with z = s^2 <= 1/4, where s = |x| for |x| <= 1/2 and
+// s = sqrt((1 - |x|) / 2) otherwise (acos(|x|) = 2 asin(s)).  g is the degree-12 Chebyshev interpolant of
+// (asin(sqrt z) - sqrt z) / (z sqrt z) on [0, 1/4] (coefficients from a 60-digit fit); the result is within 4.5e-16 of
+// numpy's arccos over [-1, 1] (one ulp at pi) - like libm's own distance from glibc, and the term only has to be exact
+// at exact ties (see oc_angle).
+__device__ __forceinline__ double oc_acos(double x) {
+    const double HALF_PI = 1.5707963267948966, PI = 3.141592653589793;
+    const double ax = fabs(x);
+    const bool big = ax > 0.5;
+    const double z = big ? (1.0 - ax) * 0.5 : x * x;
+    const double s = big ? sqrt(z) : ax;
+    double g = 0.028757851367421566;
+    g = fma(g, z, -0.014851887071247204);
+    g = fma(g, z, 0.01740087944269402);
+    g = fma(g, z, 0.005457506718640358);
+    g = fma(g, z, 0.01032281435018578);
+    g = fma(g, z, 0.011479177415184906);
+    g = fma(g, z, 0.013971212973552933);
+    g = fma(g, z, 0.017352392720869973);
+    g = fma(g, z, 0.02237217294214989);
+    g = fma(g, z, 0.030381944138531247);
+    g = fma(g, z, 0.04464285714635543);
+    g = fma(g, z, 0.07499999999998433);
+    g = fma(g, z, 0.16666666666666669);
+    const double r = fma(s * z, g, s);                     // asin(s)
+    return big ? (x > 0.0 ? 2.0 * r : PI - 2.0 * r) : HALF_PI - copysign(r, x);
+}
+
 // velocity-direction consistency cost of (track, detection), association.py:134-154
 __device__ __forceinline__ double oc_angle(double vy, double vx, double kcx, double kcy, bool valid, double dcx, double dcy,
                                            double inertia, double score) {
@@ -97,7 +127,7 @@ __device__ __forceinline__ double oc_angle(double vy, double vx, double kcx, dou
     const double inv = __drcp_rn(xadd(sqrt(xadd(xmul(dx, dx), xmul(dy, dy))), 1e-6));
     double c = xadd(xmul(vx, xmul(dx, inv)), xmul(vy, xmul(dy, inv)));
     c = fmin(fmax(c, -1.0), 1.0);
-    const double diff = xmul(xsub(HALF_PI, fabs(acos(c))), INV_PI);
+    const double diff = xmul(xsub(HALF_PI, oc_acos(c)), INV_PI);           // acos >= 0: the reference's abs() is a no-op
     return xmul(xmul(xmul(valid ? 1.0 : 0.0, diff), inertia), score);
 }
 
