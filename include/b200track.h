@@ -70,7 +70,7 @@ typedef struct {
     int32_t asso_func;       /* b200track_sim                                               */
     int32_t use_byte;
     int32_t with_reid;       /* BoTSORT: use the embedding cost                             */
-    int32_t reserved;
+    int32_t fuse_first_associate; /* BoTSORT: fuse_score on the first association (bot_sort.py:199,300-301); default 0 */
 } b200track_config;
 
 typedef struct b200track_ctx b200track_ctx;

@@ -316,7 +316,10 @@ def gen_botsort():
     rh.install()
     from boxmot.trackers.botsort.bot_sort import BoTSORT
     img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    only = os.environ.get("GOLDEN_ONLY")
     for name, sc in BOTSORT_SCENARIOS.items():
+        if only and name not in only.split(","):
+            continue
         dets, nd, embs, feats = botsort_inputs(sc)
         cfg = dict(BOTSORT_YAML)
         cfg.update(sc["params"])

@@ -45,6 +45,10 @@ BOTSORT_SCENARIOS = {
     # appearance disabled: IoU-only association with the XYWH filter
     "botsort_noreid": dict(stream=904, n_objects=25, n_frames=120, emb_dim=32, kw=dict(miss_prob=0.15, fp_rate=2.0),
                            params=dict(with_reid=False)),
+    # fuse_first_associate=True (bot_sort.py:300-301): detection scores fused into the first association's IoU cost
+    "botsort_fuse": dict(stream=905, n_objects=20, n_frames=150, emb_dim=128, kw=dict(miss_prob=0.2, fp_rate=2.5),
+                         params=dict(fuse_first_associate=True, track_high_thresh=0.5, new_track_thresh=0.6, match_thresh=0.8,
+                                     proximity_thresh=0.5, appearance_thresh=0.25, track_buffer=30)),
 }
 
 

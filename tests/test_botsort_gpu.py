@@ -13,7 +13,7 @@ FEAT_TOL = 2e-6
 
 def _cfg_kwargs(cfg):
     keys = ("track_high_thresh", "track_low_thresh", "new_track_thresh", "track_buffer", "match_thresh",
-            "proximity_thresh", "appearance_thresh", "frame_rate", "with_reid")
+            "proximity_thresh", "appearance_thresh", "frame_rate", "with_reid", "fuse_first_associate")
     return {k: cfg[k] for k in keys if k in cfg}
 
 
@@ -30,7 +30,7 @@ def _check_state(st, snap, what, with_reid):
         assert np.abs(st["smooth_feat"] - snap["smooth_feat"]).max() < FEAT_TOL, what + " smooth_feat"
 
 
-@pytest.mark.parametrize("name", ["botsort_c3", "botsort_churn", "botsort_noreid"])
+@pytest.mark.parametrize("name", ["botsort_c3", "botsort_churn", "botsort_noreid", "botsort_fuse"])
 def test_botsort_replays_reference_golden(name):
     from yolo_tracking_b200.batch import BatchedTracker
     sc, cfg, dets, nd, feats, g = botsort_scenario(name)

@@ -172,7 +172,7 @@ def test_ocsort_reference_known_answer():
 
 
 # ----------------------------------------------------------------------------- BoT-SORT
-@pytest.mark.parametrize("name", ["botsort_c3", "botsort_churn", "botsort_noreid"])
+@pytest.mark.parametrize("name", ["botsort_c3", "botsort_churn", "botsort_noreid", "botsort_fuse"])
 def test_botsort_oracle_replays_reference(name):
     from _util import botsort_scenario
     from oracle.botsort import BoTSORTOracle

@@ -31,7 +31,7 @@ class Config(C.Structure):
         ("track_buffer", C.c_int32), ("frame_rate", C.c_int32),
         ("det_thresh", C.c_double), ("iou_thresh", C.c_double), ("inertia", C.c_double),
         ("max_age", C.c_int32), ("min_hits", C.c_int32), ("delta_t", C.c_int32), ("asso_func", C.c_int32),
-        ("use_byte", C.c_int32), ("with_reid", C.c_int32), ("reserved", C.c_int32),
+        ("use_byte", C.c_int32), ("with_reid", C.c_int32), ("fuse_first_associate", C.c_int32),
     ]
 
 

@@ -59,6 +59,7 @@ class BatchedTracker:
             cfg.track_buffer = int(params.get("track_buffer", 30))
             cfg.frame_rate = int(params.get("frame_rate", 30))
             cfg.with_reid = int(params.get("with_reid", True))
+            cfg.fuse_first_associate = int(bool(params.get("fuse_first_associate", False)))
         else:
             # OCSort defaults (ocsort.py:191-203)
             cfg.det_thresh = params.get("det_thresh", 0.2)

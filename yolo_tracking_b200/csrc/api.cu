@@ -137,7 +137,7 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     p.det_thresh = cfg->det_thresh; p.iou_thresh = cfg->iou_thresh; p.inertia = cfg->inertia;
     p.max_age = cfg->max_age; p.min_hits = cfg->min_hits; p.delta_t = cfg->delta_t; p.asso_func = cfg->asso_func; p.use_byte = cfg->use_byte ? 1 : 0;
     if (cfg->kind == B200TRACK_OCSORT) { ctx->nf = B200_OC_NF; ctx->ni = B200_OC_NI; }
-    if (cfg->kind == B200TRACK_BOTSORT) { ctx->ni = B200_NI_BOT; p.with_reid = cfg->with_reid ? 1 : 0; }
+    if (cfg->kind == B200TRACK_BOTSORT) { ctx->ni = B200_NI_BOT; p.with_reid = cfg->with_reid ? 1 : 0; p.fuse_first = cfg->fuse_first_associate ? 1 : 0; }
     ctx->kf_kind = cfg->kind == B200TRACK_BOTSORT ? B200TRACK_KF_XYWH : B200TRACK_KF_XYAH;
     ctx->variant = b200::bytetrack_step_variant(cfg->max_tracks, cfg->max_dets);
     if (ctx->variant < 0) { set_error("no kernel variant covers max_tracks / max_dets"); delete ctx; return B200TRACK_ERR_CAPACITY; }

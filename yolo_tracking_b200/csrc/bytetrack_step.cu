@@ -691,7 +691,7 @@ bytetrack_step_kernel(const StepParams p) {
     lim.rowtype = sm.rowtype;
 
     // ---- first association: pool x high detections, fused score, limit match_thresh ----
-    cost.fuseA = !BOT; cost.fuseB = !BOT;                 // BoT-SORT: fuse_first_associate = False (bot_sort.py:300-301)
+    cost.fuseA = cost.fuseB = BOT ? (p.fuse_first != 0) : true;          // BoT-SORT: only with fuse_first_associate (bot_sort.py:300-301)
     cost.embA = cost.embB = BOT && p.with_reid;
     lim.limA = p.match_thresh; lim.limB = p.match_thresh;
     graph_phase_a<KIND>(sm, t, n, words, cm, FUSE2);

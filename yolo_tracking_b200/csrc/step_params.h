@@ -24,6 +24,7 @@ struct StepParams {
     double* scratch;          // [S, Tcap, Dcap] dense cost matrices (OC-SORT)
     // BoT-SORT
     int with_reid;
+    int fuse_first;           // fuse_first_associate (bot_sort.py:300-301)
     float* feat_pool;         // [S, Tcap, feat_dim] smoothed track embeddings, row-indexed (layout.h)
     float* feat_curr;         // [S, max_dets, feat_dim] scratch: this frame's twice-normalised detection embeddings
     double* cls_hist;         // [S, Tcap, 9] class-vote tables, row-indexed

@@ -20,8 +20,7 @@ class BoTSORT(_SingleStreamTracker):
                  new_track_thresh=0.6, track_buffer=30, match_thresh=0.8, proximity_thresh=0.5,
                  appearance_thresh=0.25, cmc_method="sparseOptFlow", frame_rate=30, fuse_first_associate=False,
                  with_reid=True, model=None, feat_dim=512, max_tracks=256, max_dets=256):
-        if fuse_first_associate:
-            raise NotImplementedError("fuse_first_associate=True is not built (reference default: False)")
+        self.fuse_first_associate = fuse_first_associate
         self.track_high_thresh, self.track_low_thresh, self.new_track_thresh = track_high_thresh, track_low_thresh, new_track_thresh
         self.match_thresh, self.proximity_thresh, self.appearance_thresh = match_thresh, proximity_thresh, appearance_thresh
         self.buffer_size = int(frame_rate / 30.0 * track_buffer)
@@ -30,7 +29,7 @@ class BoTSORT(_SingleStreamTracker):
         self._make(device, max_tracks, max_dets, feat_dim=self.feat_dim, track_high_thresh=track_high_thresh,
                    track_low_thresh=track_low_thresh, new_track_thresh=new_track_thresh, track_buffer=track_buffer,
                    match_thresh=match_thresh, proximity_thresh=proximity_thresh, appearance_thresh=appearance_thresh,
-                   frame_rate=frame_rate, with_reid=with_reid)
+                   frame_rate=frame_rate, with_reid=with_reid, fuse_first_associate=fuse_first_associate)
         self._feats = np.zeros((1, max_dets, self.feat_dim), dtype=np.float32) if with_reid else None
 
     def update(self, dets, img, feats=None):
