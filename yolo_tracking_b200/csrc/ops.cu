@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(256) aw_max_metric_kernel(int R, int C, const 
 
 // gating_distance: 32 tracks per CTA factor S once (one warp), the stream's measurements are staged planar in shared
 // memory, then every thread sweeps (track, measurement) pairs with coalesced 8-byte stores.
-constexpr int GD_TRACKS = 32;
+constexpr int GD_TRACKS = 64;
 template <int KIND>
 __global__ void __launch_bounds__(256) kf_gating_kernel(int T, int D, const double* __restrict__ mean, const double* __restrict__ cov,
                                                         const double* __restrict__ meas, int only_position, int metric,
@@ -347,29 +347,40 @@ __global__ void __launch_bounds__(256) kf_gating_kernel(int T, int D, const doub
         for (int i = 0; i < 4; ++i) sM[threadIdx.x][i] = m[i];
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < cnt * D; idx += blockDim.x) {
-        const int tl = idx / D, j = idx - tl * D;
-        double d[4], zz[4];
-        for (int i = 0; i < nd; ++i) d[i] = xsub(sZ[i * D + j], sM[tl][i]);
-        double acc = 0.0;
-        if (metric == 1) {
-            for (int i = 0; i < nd; ++i) acc = i ? xadd(acc, xmul(d[i], d[i])) : xmul(d[i], d[i]);
-        } else {
-            for (int i = 0; i < nd; ++i) {               // solve_triangular(L, d)
-                double v = d[i];
-                for (int k = 0; k < i; ++k) v -= sL[tl][i * 4 + k] * zz[k];
-                zz[i] = v * sL[tl][i * 4 + i];
-                acc = i ? xadd(acc, xmul(zz[i], zz[i])) : xmul(zz[i], zz[i]);
+    // A warp owns 32 consecutive measurements (kept in registers) and walks the CTA's tracks: the factor and the mean of
+    // a track are then the same address for every lane (broadcast shared-memory loads, one wavefront each) - with one
+    // (track, measurement) pair per thread the 18 eight-byte loads per pair made the kernel shared-memory bound.
+    const int lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int ch = threadIdx.x >> 5; ch * 32 < D; ch += nwarps) {
+        const int j = ch * 32 + lane;
+        const bool valid = j < D;
+        double z[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int i = 0; i < nd; ++i) z[i] = valid ? sZ[i * D + j] : 0.0;
+#pragma unroll 2
+        for (int tl = 0; tl < cnt; ++tl) {
+            double d[4], zz[4];
+            for (int i = 0; i < nd; ++i) d[i] = xsub(z[i], sM[tl][i]);
+            double acc = 0.0;
+            if (metric == 1) {
+                for (int i = 0; i < nd; ++i) acc = i ? xadd(acc, xmul(d[i], d[i])) : xmul(d[i], d[i]);
+            } else {
+                for (int i = 0; i < nd; ++i) {               // solve_triangular(L, d)
+                    double v = d[i];
+                    for (int k = 0; k < i; ++k) v -= sL[tl][i * 4 + k] * zz[k];
+                    zz[i] = v * sL[tl][i * 4 + i];
+                    acc = i ? xadd(acc, xmul(zz[i], zz[i])) : xmul(zz[i], zz[i]);
+                }
             }
-        }
-        if (cost) {
-            // gate_cost_matrix / fuse_motion (matching.py:170-196) without the T x D distance matrix ever reaching HBM
+            if (!valid) continue;
             const size_t o = (size_t)(t0 + tl) * D + j;
-            double c = cost[o];
-            if (acc > gate_thr) c = __longlong_as_double(0x7ff0000000000000LL);
-            if (fuse) c = xadd(xmul(lambda, c), xmul(xsub(1.0, lambda), acc));
-            cost[o] = c;
-        } else out[(size_t)(t0 + tl) * D + j] = acc;
+            if (cost) {
+                // gate_cost_matrix / fuse_motion (matching.py:170-196) without the T x D distance matrix ever reaching HBM
+                double c = cost[o];
+                if (acc > gate_thr) c = __longlong_as_double(0x7ff0000000000000LL);
+                if (fuse) c = xadd(xmul(lambda, c), xmul(xsub(1.0, lambda), acc));
+                cost[o] = c;
+            } else out[o] = acc;
+        }
     }
 }
 
