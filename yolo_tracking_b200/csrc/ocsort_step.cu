@@ -334,31 +334,19 @@ ocsort_step_kernel(const StepParams p) {
                 const double dcx = xdiv(xadd(db.x1, db.x2), 2.0), dcy = xdiv(xadd(db.y1, db.y2), 2.0), dconf = sm.dconf[j];
                 double m = INF;
                 int a = -1;
-                // two columns per iteration, the velocity-direction term evaluated unconditionally and selected afterwards: the
-                // pair cost is one long dependent chain (square root, reciprocal, polynomial), two independent ones overlap
-                for (int c0 = lane; c0 < Cn; c0 += 64) {
-                    double simv[2], cstv[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int c = c0 + 32 * u < Cn ? c0 + 32 * u : c0;
-                        const int sl = sm.ht[c];
-                        const Box tb = {sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]};
-                        simv[u] = oc_sim(func, db, tb, W, H);
-                        const double vy = sm.vel[0][sl], vx = sm.vel[1][sl];
-                        const bool use = sm.kvalid[sl] && !(vx == 0.0 && vy == 0.0);
-                        const double ang = oc_angle(vy, vx, sm.kc[0][sl], sm.kc[1][sl], true, dcx, dcy, p.inertia, dconf);
-                        cstv[u] = xadd(-xadd(xadd(simv[u], use ? ang : 0.0), 0.0), xmul((double)(r * Cn + c), TIE_EPS));
-                    }
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int c = c0 + 32 * u;
-                        if (c >= Cn) break;
-                        const double cst = cstv[u];
-                        C[(size_t)r * TMAX + c] = cst;
-                        mx = fmax(mx, cst);
-                        if (cst < m) { m = cst; a = c; }
-                        if (simv[u] > thr) { atomicAdd(&sm.colcnt[c], 1); atomicAdd(&sm.rowcnt[r], 1); sm.rowmatch[r] = c; }
-                    }
+                for (int c = lane; c < Cn; c += 32) {
+                    const int sl = sm.ht[c];
+                    const Box tb = {sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]};
+                    const double sim = oc_sim(func, db, tb, W, H);
+                    double ang = 0.0;
+                    const double vy = sm.vel[0][sl], vx = sm.vel[1][sl];
+                    if (sm.kvalid[sl] && !(vx == 0.0 && vy == 0.0))
+                        ang = oc_angle(vy, vx, sm.kc[0][sl], sm.kc[1][sl], true, dcx, dcy, p.inertia, dconf);
+                    const double cst = xadd(-xadd(xadd(sim, ang), 0.0), xmul((double)(r * Cn + c), TIE_EPS));
+                    C[(size_t)r * TMAX + c] = cst;
+                    mx = fmax(mx, cst);
+                    if (cst < m) { m = cst; a = c; }
+                    if (sim > thr) { atomicAdd(&sm.colcnt[c], 1); atomicAdd(&sm.rowcnt[r], 1); sm.rowmatch[r] = c; }
                 }
 #pragma unroll
                 for (int d = 16; d; d >>= 1) {
