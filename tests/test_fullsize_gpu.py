@@ -84,3 +84,95 @@ def test_config5_shape_determinism_independence_invariants_and_sampled_oracle():
             assert ref.shape == (k, 8), f"frame {f} stream {s}"
             assert np.array_equal(a[f][0][s, :k, 4:], ref[:, 4:]), f"frame {f} stream {s}: ids"
             assert_close(a[f][0][s, :k, :4], ref[:, :4], what=f"frame {f} stream {s} boxes")
+
+
+def test_config2_ocsort_shape_determinism_and_sampled_oracle():
+    """BASELINE config 2 at full size (64 streams x 100 objects with occlusion runs, ocsort.yaml): two runs identical,
+    streams independent of the batch (the three-CTAs-per-SM instantiation used for many streams gives the same rows as
+    the two-CTAs one used for few), sampled streams equal the oracle."""
+    from oracle.ocsort import OCSortOracle
+    from yolo_tracking_b200.batch import BatchedTracker
+    from yolo_tracking_b200.synth import make_batch
+    S2, F2, cap = 64, 40, 128
+    cfg = dict(det_thresh=0, max_age=30, min_hits=1, asso_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2)
+    dets, nd, _ = make_batch(2, S2, 100, F2, dmax=cap, occlusion=True)
+    hw = (2160, 3840)
+
+    def run(streams, copies=1):
+        idx = np.asarray(streams)
+        trk = BatchedTracker("ocsort", len(idx) * copies, max_tracks=cap, max_dets=cap, **cfg)
+        outs = []
+        for f in range(F2):
+            d = np.ascontiguousarray(np.tile(dets[f, idx], (copies, 1, 1)))
+            n = np.ascontiguousarray(np.tile(nd[f, idx], copies))
+            out, nout = trk.update_batch(d, n, img_hw=hw)
+            outs.append((out[:len(idx)].copy(), nout[:len(idx)].copy()))
+        trk.close()
+        return outs
+    a, b = run(range(S2)), run(range(S2))
+    many = run(range(S2), copies=6)                       # 384 streams: the dense instantiation (> 2 streams per SM)
+    sample = [0, 7, 33, 63]
+    alone = run(sample)
+    oracles = [OCSortOracle(False, use_byte=False, **cfg) for _ in sample]
+    for f in range(F2):
+        assert np.array_equal(a[f][1], b[f][1]) and np.array_equal(a[f][1], many[f][1])
+        for s in range(S2):
+            k = a[f][1][s]
+            assert np.array_equal(a[f][0][s, :k], b[f][0][s, :k]), f"frame {f} stream {s}: not deterministic"
+            assert np.array_equal(a[f][0][s, :k], many[f][0][s, :k]), f"frame {f} stream {s}: kernel instantiations differ"
+        for i, s in enumerate(sample):
+            k = a[f][1][s]
+            assert alone[f][1][i] == k and np.array_equal(alone[f][0][i, :k], a[f][0][s, :k])
+            ref = oracles[i].update(dets[f, s, :nd[f, s]], hw).reshape(-1, 8)
+            assert ref.shape == (k, 8), f"frame {f} stream {s}"
+            assert np.array_equal(a[f][0][s, :k, 4:], ref[:, 4:]), f"frame {f} stream {s}: ids"
+            assert_close(a[f][0][s, :k, :4], ref[:, :4], what=f"frame {f} stream {s} boxes")
+
+
+def test_config3_botsort_shape_determinism_and_sampled_oracle():
+    """BASELINE config 3 shape (256 streams x 100 objects, 512-d embeddings through the ReID seam, botsort.yaml): two runs
+    identical bit for bit, sampled streams equal the oracle."""
+    import sys
+    from _util import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    from scenarios import BOTSORT_YAML
+    from oracle.botsort import BoTSORTOracle
+    from yolo_tracking_b200.batch import BatchedTracker
+    from yolo_tracking_b200.synth import make_batch
+    S3, F3, cap, E = 256, 16, 128, 512
+    base_d, base_n, base_e = make_batch(3, 8, 100, F3, dmax=cap, emb_dim=E)
+    feats8 = np.zeros_like(base_e)
+    for f in range(F3):
+        for s in range(8):
+            rows = np.nonzero(base_d[f, s, :base_n[f, s], 4] > BOTSORT_YAML["track_high_thresh"])[0]
+            if len(rows):
+                feats8[f, s, rows] = base_e[f, s, rows] / np.linalg.norm(base_e[f, s, rows])
+    rep = S3 // 8
+    keys = ("track_high_thresh", "track_low_thresh", "new_track_thresh", "track_buffer", "match_thresh", "proximity_thresh",
+            "appearance_thresh", "frame_rate")
+    params = {k: BOTSORT_YAML[k] for k in keys if k in BOTSORT_YAML}
+
+    def run():
+        trk = BatchedTracker("botsort", S3, max_tracks=cap, max_dets=cap, feat_dim=E, **params)
+        outs = []
+        for f in range(F3):
+            out, nout = trk.update_batch(np.ascontiguousarray(np.tile(base_d[f], (rep, 1, 1))), np.ascontiguousarray(np.tile(base_n[f], rep)),
+                                         feats=np.ascontiguousarray(np.tile(feats8[f], (rep, 1, 1))))
+            outs.append((out.copy(), nout.copy()))
+        trk.close()
+        return outs
+    a, b = run(), run()
+    oracles = [BoTSORTOracle(**BOTSORT_YAML) for _ in range(3)]
+    for f in range(F3):
+        assert np.array_equal(a[f][1], b[f][1])
+        for s in range(0, S3, 5):
+            k = a[f][1][s]
+            assert np.array_equal(a[f][0][s, :k], b[f][0][s, :k]), f"frame {f} stream {s}: not deterministic"
+            assert np.array_equal(a[f][0][s, :k], a[f][0][s % 8, :k]), f"frame {f} stream {s}: copies of a stream differ"
+        for i in range(3):
+            ref = oracles[i].update(base_d[f, i, :base_n[f, i]], feats8[f, i, :base_n[f, i]].copy()).reshape(-1, 8)
+            k = a[f][1][i]
+            assert ref.shape == (k, 8), f"frame {f} stream {i}"
+            assert np.array_equal(a[f][0][i, :k, 4:], ref[:, 4:]), f"frame {f} stream {i}: ids"
+            assert_close(a[f][0][i, :k, :4], ref[:, :4], what=f"frame {f} stream {i} boxes")

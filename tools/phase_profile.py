@@ -34,6 +34,9 @@ c = trk.phase_cycles()
 names = {1: "load dets/means", 2: "det+track prep, lap_prepare", 3: "cell masks", 4: "graph pass 1", 5: "solve pass 1: augmentations",
          6: "pass-2 setup", 7: "graph pass 2", 8: "deferred KF + lifecycle", 9: "lost-list scan", 10: "solve pass 2: augmentations",
          11: "lost boxes + dedupe", 12: "graph pass 1: candidate walk", 13: "solve pass 1: classify + small", 14: "solve pass 2: classify + small", 15: "final scan + writes"}
+if KIND == "ocsort":
+    names = {1: "loads, motion step, k-previous observations", 2: "row / column lists", 3: "dense cost fill (similarity + direction term)", 4: "permutation test, row-reduction start",
+             5: "dense augmentations (or shortcut)", 6: "BYTE / recovery rounds", 7: "Kalman update, freeze / unfreeze", 8: "births, output scan"}
 n = c[0]
 tot = sum(c[1:])
 print(f"CTAs {n}, mean cycles/CTA {tot / n:.0f}")

@@ -223,6 +223,9 @@ ocsort_step_kernel(const StepParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SM& sm = *reinterpret_cast<SM*>(smem_raw);
     const int s = blockIdx.x, tid = threadIdx.x, t = tid;
+    // optional per-phase cycle counters (thread 0 of every CTA; b200track_phase_cycles)
+    long long ph_last = p.dbg ? clock64() : 0;
+#define PHASE(k) do { if (p.dbg && tid == 0) { const long long now_ = clock64(); atomicAdd(&p.dbg[k], (unsigned long long)(now_ - ph_last)); ph_last = now_; } } while (0)
     int* counts = p.counts + 4 * s;
     const int n0 = counts[0], id0 = counts[2], frame = counts[3] + 1;
     int nd = p.ndets[s];
@@ -304,6 +307,7 @@ ocsort_step_kernel(const StepParams p) {
     if (t < TMAX) { sm.alive[t] = live; sm.tmatch[t] = -1; }
     if (tid < DMAX) { sm.dmatch[tid] = -1; sm.rowcnt[tid] = 0; sm.rowmatch[tid] = -1; }
     __syncthreads();
+    PHASE(1);
     if (tid < DMAX) sm.dstate[tid] = (tid < nd && sm.dconf[tid] > p.det_thresh) ? DS_FREE0 : DS_NONE;    // ocsort.py:250-251
 
     // compact row (high detections) and column (alive trackers) lists
@@ -318,6 +322,7 @@ ocsort_step_kernel(const StepParams p) {
         R = (int)(tot & 0xffff); Cn = (int)((tot >> 16) & 0xffff);
         __syncthreads();
     }
+    PHASE(2);
 
     // ---- first round: associate(dets, trks, ...) ------------------------------------------------
     if (R > 0 && Cn > 0) {
@@ -358,6 +363,7 @@ ocsort_step_kernel(const StepParams p) {
             }
         }
         __syncthreads();
+        PHASE(3);
         int ccnt = tid < Cn ? sm.colcnt[tid] : 0;
         int rc = tid < R ? sm.rowcnt[tid] : 0;
         block_max3<NT>(sm, mx, ccnt, rc);
@@ -369,8 +375,10 @@ ocsort_step_kernel(const StepParams p) {
             const DenseLap w = make_dense<NT>(sm);
             const double lambda = 2.0 * (mx + 1.0);
             dense_lap_init<NT>(w, C, TMAX, R, Cn, lambda, true);
+            PHASE(4);
             dense_lap_augment<NT>(w, C, TMAX, R, Cn, lambda);
         }
+        PHASE(5);
         // matched pairs below the similarity threshold fall back to unmatched (association.py:187-193)
         if (tid < R) {
             const int c = sm.xr[tid];
@@ -475,6 +483,7 @@ ocsort_step_kernel(const StepParams p) {
         build_lists(false, byte_ran, nr, nc);
         ocr_ran = second_round(nr, nc, true);
     }
+    PHASE(6);
 
     // ---- deferred Kalman work and bookkeeping, thread t = slot t ---------------------------------
     int hits = 0, det_ind = 0, tid_id = 0;
@@ -570,6 +579,7 @@ ocsort_step_kernel(const StepParams p) {
         }
     }
 
+    PHASE(7);
     // ---- new trackers (ocsort.py:351-353) and the reversed output scan (:354-379) -------------------
     // creation order: associate()'s unmatched list order, or ascending when the recovery round ran setdiff1d
     const int ds = tid < DMAX ? sm.dstate[tid] : DS_NONE;
@@ -670,6 +680,7 @@ ocsort_step_kernel(const StepParams p) {
     const int n1 = min(n0 + n_new, tcap);
     const int alive_after = n_keep + min(n_new, tcap - n0 > 0 ? tcap - n0 : 0);
     __syncthreads();
+    PHASE(8);
 
     // ---- compaction, only when the slot range runs short for the next frame ----------------------
     int n_final = n1;
@@ -712,8 +723,10 @@ ocsort_step_kernel(const StepParams p) {
         p.nout[s] = min(E_old + E_new, p.max_tracks);
         p.track_updates[s] += (unsigned long long)Cn;
         if (err) atomicOr(p.err, err);
+        if (p.dbg) atomicAdd(&p.dbg[0], 1ull);
     }
 }
+#undef PHASE
 
 template <int TMAX, int DMAX, bool DENSE>
 cudaError_t launch_oc_kernel(const StepParams& p, cudaStream_t stream) {
