@@ -28,6 +28,6 @@ run full_bytetrack $FULL -k regex:bytetrack_step -s 12 -c 1 -o $O/${R}_full_byte
 run full_ocsort $FULL -k regex:ocsort_step -s 12 -c 1 -o $O/${R}_full_ocsort -f -- $OC
 run full_botsort $FULL -k regex:bytetrack_step -s 12 -c 1 -o $O/${R}_full_botsort -f -- $BS
 run full_appearance $FULL -k regex:appearance_cost -s 1 -c 1 -o $O/${R}_full_appearance -f -- $OP --only appearance
-run full_kf $FULL -k regex:"kf_(predict|update|project|gating)" -c 4 -o $O/${R}_full_kf -f -- $OP --only kf_predict,kf_update,kf_project,gating
+run full_kf $FULL -k regex:"kf_(predict|update|project|gating)" -c 24 -o $O/${R}_full_kf -f -- python tools/bench_ops.py --iters 1 --only kf_predict,kf_update,kf_project,gating
 run full_gallery $FULL -k regex:gallery_cost -s 1 -c 1 -o $O/${R}_full_gallery -f -- $OP --only gallery --gallery-streams 64 --kf-tracks 1000 --streams 8
 ls -la $O | grep ${R}_

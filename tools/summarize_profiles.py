@@ -77,7 +77,10 @@ for cap in ("bytetrack", "ocsort", "botsort", "appearance", "gallery", "kf"):
         continue
     hdr, units = rows[0], rows[1]
     md.append(f"\n## `--set full` capture: {cap} (`gpurun_out/{R}_full_{cap}.ncu-rep`, not tracked)\n")
-    for row in rows[2:]:
+    last = {}
+    for row in rows[2:]:                                  # one entry per kernel: the last captured launch (after the warm-ups)
+        last[dict(zip(hdr, row)).get('Kernel Name', '?')] = row
+    for row in last.values():
         d = dict(zip(hdr, row))
         u = dict(zip(hdr, units))
         md.append(f"\n**`{short(d.get('Kernel Name', '?'))}`** grid {d.get('Grid Size', '?')} block {d.get('Block Size', '?')}\n")

@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(256) kf_project_kernel(int n, const double* __
 // P - K (H P): S K^T = S S^-1 (P H^T)^T = H P exactly in real arithmetic, and rounding-wise inside the 1e-9 bar.
 constexpr int KFU_TPB = 32;                    // tracks per CTA of the update kernel (256 threads)
 template <int KIND>
-__global__ void __launch_bounds__(KFU_TPB * KF_LANES, 4) kf_update_kernel(int n, double* mean, double* cov, const double* __restrict__ z,
+__global__ void __launch_bounds__(KFU_TPB * KF_LANES, 6) kf_update_kernel(int n, double* mean, double* cov, const double* __restrict__ z,
                                                                          const double* __restrict__ conf) {
     __shared__ double sm[KFU_TPB * KF_STRIDE];
     __shared__ double sF[KFU_TPB][15];             // per track: L (10 lower-triangle entries), 1 / L[i][i] (4); stride 15 = conflict-free
