@@ -69,8 +69,12 @@ class _Trk:
         ret[2:] = ret[:2] + ret[2:]
         return ret
 
-    def camera_update_identity(self):                           # track.py:129-138 with warp = eye(2, 3)
+    def camera_update(self, warp=None):                         # track.py:129-138 (warp None = eye(2, 3))
         x1, y1, x2, y2 = self.to_tlbr()
+        if warp is not None:
+            m = np.array([warp[0], warp[1], [0, 0, 1]]).tolist()
+            x1, y1, _ = m @ np.array([x1, y1, 1]).T
+            x2, y2, _ = m @ np.array([x2, y2, 1]).T
         w, h = x2 - x1, y2 - y1
         cx, cy = x1 + w / 2, y1 + h / 2
         self.mean[:4] = [cx, cy, w / h, h]
@@ -179,7 +183,7 @@ class StrongSORTOracle:
         return metric
 
     # ------------------------------------------------------------------ frame step
-    def update(self, dets, feats):
+    def update(self, dets, feats, warp=None):
         assert isinstance(dets, np.ndarray), "dets must be np.ndarray"
         assert dets.ndim == 2, "dets must be two-dimensional"
         assert dets.shape[1] == 6, "dets must have 6 columns"
@@ -187,7 +191,7 @@ class StrongSORTOracle:
         n = len(dets)
         if len(self.tracks) >= 1:
             for t in self.tracks:
-                t.camera_update_identity()
+                t.camera_update(warp)
         tlwh = dets[:, :4].copy()
         tlwh[:, 2] = dets[:, 2] - dets[:, 0]
         tlwh[:, 3] = dets[:, 3] - dets[:, 1]

@@ -44,8 +44,9 @@ def strongsort_scenario(name):
     import sys
     if GOLDEN not in sys.path:
         sys.path.insert(0, GOLDEN)
-    from scenarios import STRONGSORT_SCENARIOS, STRONGSORT_YAML, strongsort_inputs
-    sc = STRONGSORT_SCENARIOS[name]
+    from scenarios import STRONGSORT_SCENARIOS, STRONGSORT_YAML, camera_warps, strongsort_inputs
+    sc = dict(STRONGSORT_SCENARIOS[name])
+    sc["warps"] = camera_warps(sc) if sc.get("camera") else None
     cfg = dict(STRONGSORT_YAML)
     cfg.update(sc["params"])
     dets, nd, _, feats = strongsort_inputs(sc)

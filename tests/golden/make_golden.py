@@ -298,7 +298,7 @@ def gen_ocsort():
 
 # ----------------------------------------------------------------------------- BoT-SORT
 from scenarios import (BOTSORT_SCENARIOS, BOTSORT_YAML, STRONGSORT_SCENARIOS, STRONGSORT_YAML, botsort_inputs,  # noqa: E402
-                       strongsort_inputs)
+                       camera_warps, strongsort_inputs)
 
 
 def _bs_snapshot(trk):
@@ -399,14 +399,18 @@ def gen_strongsort():
     rh.install()
     from boxmot.trackers.strongsort.strong_sort import StrongSORT
     img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    only = os.environ.get("GOLDEN_ONLY")
     for name, sc in STRONGSORT_SCENARIOS.items():
+        if only and name not in only.split(","):
+            continue
         dets, nd, embs, feats = strongsort_inputs(sc)
         cfg = dict(STRONGSORT_YAML)
         cfg.update(sc["params"])
         trk = StrongSORT(None, "cpu", False, **cfg)
-        trk.cmc = rh.IdentityCMC()
+        trk.cmc = rh.ScriptedCMC(camera_warps(sc)) if sc.get("camera") else rh.IdentityCMC()
         outs, recs, means, covs, cov_frames = [], [], [], [], []
         for f in range(sc["n_frames"]):
+            trk.cmc.frame = f
             if nd[f]:
                 rh.FakeReID.queue.append(embs[f, :nd[f]])
             o = trk.update(dets[f, :nd[f]], img)

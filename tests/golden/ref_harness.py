@@ -91,6 +91,15 @@ class IdentityCMC:
         return np.eye(2, 3)
 
 
+class ScriptedCMC:
+    """A camera-motion estimator that returns externally supplied warps: set .frame before every update()."""
+    def __init__(self, warps):
+        self.warps, self.frame = np.asarray(warps, dtype=np.float64), 0
+
+    def apply(self, img, dets):
+        return self.warps[self.frame].copy()
+
+
 _installed = False
 
 

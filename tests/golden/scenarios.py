@@ -60,12 +60,40 @@ STRONGSORT_SCENARIOS = {
     # misses and false positives, short memory, confirmation after 3 hits, small gallery
     "strongsort_churn": dict(stream=906, n_objects=16, n_frames=200, emb_dim=64, kw=dict(miss_prob=0.3, fp_rate=3.0),
                              params=dict(max_age=8, n_init=3, nn_budget=5, ema_alpha=0.9)),
+    # a moving camera: every frame comes with a 2x3 warp (small rotation, zoom, shift) that the detections follow and that
+    # Track.camera_update (track.py:129-138) applies to the tracks before the prediction
+    "strongsort_cam": dict(stream=907, n_objects=14, n_frames=120, emb_dim=64, kw=dict(miss_prob=0.1, fp_rate=1.0), camera=True,
+                           params=dict(n_init=2, nn_budget=20)),
 }
+
+
+def camera_warps(sc):
+    """warps[F, 2, 3]: frame f's camera motion relative to frame f - 1 (identity for frame 0), seeded by the scenario."""
+    rng = np.random.default_rng(70000 + sc["stream"])
+    F = sc["n_frames"]
+    ang = rng.normal(0.0, 0.004, F)
+    zoom = 1.0 + rng.normal(0.0, 0.003, F)
+    shift = rng.normal(0.0, 4.0, (F, 2))
+    w = np.zeros((F, 2, 3))
+    for f in range(F):
+        c, s = np.cos(ang[f]) * zoom[f], np.sin(ang[f]) * zoom[f]
+        w[f] = [[c, -s, shift[f, 0]], [s, c, shift[f, 1]]]
+    w[0] = np.eye(2, 3)
+    return w
 
 
 def strongsort_inputs(sc):
     """dets[F, D, 6], ndets[F], raw embeddings, seam features (every detection row / Frobenius norm of the frame's matrix)."""
     dets, nd, embs = make_stream(4, sc["stream"], sc["n_objects"], sc["n_frames"], emb_dim=sc["emb_dim"], **sc["kw"])
+    if sc.get("camera"):
+        # the scene as the moving camera sees it: box corners pushed through the accumulated warps
+        acc = np.eye(3)
+        for f, w in enumerate(camera_warps(sc)):
+            acc = np.vstack([w, [0.0, 0.0, 1.0]]) @ acc
+            for j in range(nd[f]):
+                x1, y1, x2, y2 = dets[f, j, :4]
+                p = acc[:2, :2] @ np.array([[x1, x2], [y1, y2]]) + acc[:2, 2:3]
+                dets[f, j, :4] = [p[0].min(), p[1].min(), p[0].max(), p[1].max()]
     feats = np.zeros_like(embs)
     for f in range(sc["n_frames"]):
         if nd[f]:

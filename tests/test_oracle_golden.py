@@ -207,7 +207,7 @@ def test_botsort_oracle_replays_reference(name):
 
 
 # ----------------------------------------------------------------------------- StrongSORT
-@pytest.mark.parametrize("name", ["strongsort_c4", "strongsort_churn"])
+@pytest.mark.parametrize("name", ["strongsort_c4", "strongsort_churn", "strongsort_cam"])
 def test_strongsort_oracle_replays_reference(name):
     from _util import strongsort_scenario
     from oracle.strongsort import StrongSORTOracle
@@ -218,7 +218,7 @@ def test_strongsort_oracle_replays_reference(name):
     for f in g["cov_frames"]:
         cov_offs.append(cov_offs[-1] + int(g["rec_offs"][f + 1] - g["rec_offs"][f]))
     for f in range(sc["n_frames"]):
-        out = trk.update(dets[f, :nd[f]], feats[f, :nd[f]])
+        out = trk.update(dets[f, :nd[f]], feats[f, :nd[f]], warp=None if sc["warps"] is None else sc["warps"][f])
         ref = g["out"][g["out_offs"][f]:g["out_offs"][f + 1]]
         assert out.reshape(-1, 8).shape == ref.shape, f"frame {f}"
         if ref.size:

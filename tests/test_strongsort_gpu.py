@@ -9,7 +9,7 @@ from _util import assert_close, strongsort_scenario
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["strongsort_c4", "strongsort_churn"])
+@pytest.mark.parametrize("name", ["strongsort_c4", "strongsort_churn", "strongsort_cam"])
 def test_strongsort_replays_reference_golden(name):
     from yolo_tracking_b200 import StrongSORT
     sc, cfg, dets, nd, feats, g = strongsort_scenario(name)
@@ -20,7 +20,7 @@ def test_strongsort_replays_reference_golden(name):
     for f in g["cov_frames"]:
         cov_offs.append(cov_offs[-1] + int(g["rec_offs"][f + 1] - g["rec_offs"][f]))
     for f in range(sc["n_frames"]):
-        out = trk.update(dets[f, :nd[f]], img, feats=feats[f, :nd[f]])
+        out = trk.update(dets[f, :nd[f]], img, feats=feats[f, :nd[f]], warp=None if sc["warps"] is None else sc["warps"][f])
         ref = g["out"][g["out_offs"][f]:g["out_offs"][f + 1]]
         assert out.reshape(-1, 8).shape == ref.shape, f"{name} frame {f}"
         if ref.size:

@@ -79,7 +79,9 @@ class StrongSORT:
                 matches.append((t, d))
         return matches, ut, ud
 
-    def update(self, dets, img, feats=None):
+    def update(self, dets, img, feats=None, warp=None):
+        """`warp`: externally estimated 2x3 camera-motion matrix of this frame (what self.cmc.apply(img, xyxy) returns in the
+        reference, strong_sort.py:63-65); None = identity.  Estimation itself (OpenCV ECC) is out of scope."""
         _SingleStreamTracker._check(dets)
         assert isinstance(img, np.ndarray) or img is None or isinstance(img, tuple), "Unsupported 'img' input format"
         dets = np.asarray(dets, dtype=np.float64)
@@ -91,9 +93,13 @@ class StrongSORT:
         # private copy: a new track normalises its row in place
         feats = np.array(feats, dtype=np.float32).reshape(n, -1) if n else np.zeros((0, 1), dtype=np.float32)
         tracks = self.tracks
-        # camera_update with the identity warp (track.py:129-138) - not an exact no-op in floating point
+        # Track.camera_update (track.py:129-138) - with the identity warp still not an exact no-op in floating point
+        wm = None if warp is None else np.array([warp[0], warp[1], [0, 0, 1]], dtype=np.float64).tolist()
         for t in tracks:
             x1, y1, x2, y2 = t.to_tlbr()
+            if wm is not None:
+                x1, y1, _ = wm @ np.array([x1, y1, 1]).T
+                x2, y2, _ = wm @ np.array([x2, y2, 1]).T
             w, h = x2 - x1, y2 - y1
             t.mean[:4] = [x1 + w / 2, y1 + h / 2, w / h, h]
         tlwh = dets[:, :4].copy()
