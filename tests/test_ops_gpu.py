@@ -347,3 +347,5 @@ def test_gallery_cost_tensor_core_operator(B, T, G, D, F):
     assert keep.sum() > 0 and (~keep).sum() > 0
     assert np.allclose(got, ref, rtol=0, atol=2e-6)
     assert st[2] >= keep.sum()                              # every surviving pair went through the exact path
+    # the caller-resident bf16 gallery (tracker state, converted once) gives the same matrix
+    assert np.array_equal(_ops.gallery_cost(gal, count, det, thresh, resident_bf16=True), got)

@@ -200,7 +200,7 @@ def appearance_cost(trk, det, scale=0.5, thresh=0.25, fill=1.0, gate=None, retur
     return (res, int(st[0])) if return_stats else res
 
 
-def gallery_cost(gallery, count, det, thresh=0.2, fill=None, return_stats=False):
+def gallery_cost(gallery, count, det, thresh=0.2, fill=None, return_stats=False, resident_bf16=False):
     """Thresholded gallery distance of StrongSORT for a batch of streams (matching.py:247-378 + linear_assignment.py:59-78):
     gallery [B, T, G, F] float32, count [B, T], det [B, D, F] -> cost [B, T, D] float64 (tensor-core pre-filter, exact values)."""
     lib = _lib.load()
@@ -213,12 +213,17 @@ def gallery_cost(gallery, count, det, thresh=0.2, fill=None, return_stats=False)
     if B * T * D == 0:
         return np.zeros((B, T, D))
     dg, dc, dd = _dev(gal, np.float32), _dev(np.asarray(count).reshape(B, T), np.int32), _dev(dt, np.float32)
+    # resident_bf16: the unit-norm bf16 copy of the gallery is built once by the caller (tracker state) instead of per call
+    g16 = None
+    if resident_bf16:
+        g16 = torch.empty((B, T, G, F), dtype=torch.bfloat16, device=dg.device)
+        _lib.check(lib.b200track_unit_bf16(B * T * G, F, _p(dg), _p(g16), None))
     need = C.c_uint64()
-    _lib.check(lib.b200track_gallery_cost_workspace(B, T, G, D, F, 1, C.byref(need)))
+    _lib.check(lib.b200track_gallery_cost_workspace(B, T, G, D, F, 0 if resident_bf16 else 1, C.byref(need)))
     ws = torch.empty((max(int(need.value), 1),), dtype=torch.uint8, device=dg.device)
     out = torch.empty((B, T, D), dtype=torch.float64, device=dg.device)
     st = torch.zeros((3,), dtype=torch.int64, device=dg.device)
-    _sync_check(lib.b200track_gallery_cost(B, T, G, D, F, _p(dg), None, _p(dc), _p(dd), float(thresh), float(fill), _p(out), _p(ws),
+    _sync_check(lib.b200track_gallery_cost(B, T, G, D, F, _p(dg), _p(g16), _p(dc), _p(dd), float(thresh), float(fill), _p(out), _p(ws),
                                            int(need.value), _p(st), None))
     st = st.cpu().numpy()
     if st[1]:
