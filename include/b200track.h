@@ -88,6 +88,7 @@ const char* b200track_last_error(void);
  *   img_h, img_w: frame size (OCSORT reads only img.shape[:2]; ocsort.py:239)
  *   d_out   [n_streams, max_tracks, 8] (x1, y1, x2, y2, id, conf, cls, det_ind) in the
  *           reference's row order; d_nout[s] rows are valid.
+ *   d_dets, d_feats and d_out must be 16-byte aligned (rows are moved with 16-byte accesses).
  * b200track_step_host   same call with HOST buffers: copies in, steps, copies out, waits.
  * b200track_submit_host / b200track_wait_host: pipelined variant - up to
  *   b200track_host_slots() frames in flight (copy-in of frame k+1 and copy-out of frame k-1

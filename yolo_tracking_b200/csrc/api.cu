@@ -206,6 +206,9 @@ extern "C" int b200track_step(b200track_ctx* ctx, const double* d_dets, const in
                               const float* d_feats, int32_t img_h, int32_t img_w,
                               double* d_out, int32_t* d_nout, void* stream) {
     if (!ctx || !d_dets || !d_ndets || !d_out || !d_nout) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    // detection rows are fetched and output rows stored with 16-byte accesses
+    if ((reinterpret_cast<uintptr_t>(d_dets) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_feats)) & 15) {
+        set_error("d_dets / d_out / d_feats must be 16-byte aligned"); return B200TRACK_ERR_ARG; }
     CU_TRY(cudaSetDevice(ctx->cfg.device));
     return launch_step(ctx, d_dets, d_ndets, d_feats, img_h, img_w, d_out, d_nout, (cudaStream_t)stream);
 }

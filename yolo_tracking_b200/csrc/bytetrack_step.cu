@@ -1094,9 +1094,9 @@ bytetrack_step_kernel(const StepParams p) {
         }
         if (orow >= 0 && orow < out_cap) {
             const Box b = track_box<KIND>(sm, t);
-            double* o = gout + (size_t)orow * 8;
-            o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
-            o[4] = (double)tid_id; o[5] = score; o[6] = cls; o[7] = (double)det_ind;
+            double2* o = reinterpret_cast<double2*>(gout + (size_t)orow * 8);      // 64-byte rows: four 16-byte stores
+            o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
+            o[2] = make_double2((double)tid_id, score); o[3] = make_double2(cls, (double)det_ind);
         }
     }
     if (val & (1ull << 40)) {                           // STrack.activate (byte_tracker.py:50-62)
@@ -1141,9 +1141,9 @@ bytetrack_step_kernel(const StepParams p) {
             const int orow = totKeep + k;
             if (orow < out_cap) {
                 const Box b = mean_to_box<KIND>(z[0], z[1], z[2], z[3]);
-                double* o = gout + (size_t)orow * 8;
-                o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
-                o[4] = (double)id; o[5] = sm.dconf[j]; o[6] = dets_g[j * 6 + 5]; o[7] = (double)j;
+                double2* o = reinterpret_cast<double2*>(gout + (size_t)orow * 8);
+                o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
+                o[2] = make_double2((double)id, sm.dconf[j]); o[3] = make_double2(dets_g[j * 6 + 5], (double)j);
             }
         }
     }

@@ -628,9 +628,9 @@ ocsort_step_kernel(const StepParams p) {
                 Box b;
                 if (box_from_obs) { b.x1 = sm.lbox[0][t]; b.y1 = sm.lbox[1][t]; b.x2 = sm.lbox[2][t]; b.y2 = sm.lbox[3][t]; }
                 else b = oc_x_to_box(k.x[0], k.x[1], k.x[2], k.x[3]);
-                double* o = gout + (size_t)row * 8;
-                o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
-                o[4] = (double)(tid_id + 1); o[5] = conf; o[6] = cls; o[7] = (double)det_ind;
+                double2* o = reinterpret_cast<double2*>(gout + (size_t)row * 8);          // 64-byte rows: four 16-byte stores
+                o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
+                o[2] = make_double2((double)(tid_id + 1), conf); o[3] = make_double2(cls, (double)det_ind);
             }
         }
     } else if (t < n0 && (fl & OCF_ALIVE) == 0 && t < TMAX) {
@@ -671,9 +671,9 @@ ocsort_step_kernel(const StepParams p) {
             const int row = n_new - 1 - order;
             if (row < p.max_tracks) {
                 const Box b = oc_x_to_box(z[0], z[1], z[2], z[3]);
-                double* o = gout + (size_t)row * 8;
-                o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
-                o[4] = (double)(id + 1); o[5] = sm.dconf[j]; o[6] = sm.dcls[j]; o[7] = (double)j;
+                double2* o = reinterpret_cast<double2*>(gout + (size_t)row * 8);
+                o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
+                o[2] = make_double2((double)(id + 1), sm.dconf[j]); o[3] = make_double2(sm.dcls[j], (double)j);
             }
         }
     }
