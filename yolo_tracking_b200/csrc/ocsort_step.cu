@@ -239,6 +239,21 @@ ocsort_step_kernel(const StepParams p) {
     const double thr = p.iou_thresh, W = p.img_w, H = p.img_h;
     const int func = p.asso_func;
 
+    // state and detections of a stream a little ahead (one per SM) -> L2: its dependent first loads (flags -> state ->
+    // observation ring) then cost L2 hits instead of DRAM round trips
+    {
+        const int s2 = s + 148;
+        if (s2 < p.n_streams) {
+            const char* d2 = reinterpret_cast<const char*>(p.dets + (size_t)s2 * p.max_dets * 6);
+            const char* f2 = reinterpret_cast<const char*>(p.state_f + (size_t)s2 * B200_OC_NF * TMAX);
+            const char* i2 = reinterpret_cast<const char*>(p.state_i + (size_t)s2 * B200_OC_NI * TMAX);
+            const int nl_d = (p.max_dets * 48 + 127) >> 7, nl_f = (B200_OC_SX * TMAX * 8 + 127) >> 7, nl_i = (B200_OC_NI * TMAX * 4 + 127) >> 7;
+            for (int l = tid; l < nl_d + nl_f + nl_i; l += NT) {
+                const char* a = l < nl_d ? d2 + ((size_t)l << 7) : (l < nl_d + nl_f ? f2 + ((size_t)(l - nl_d) << 7) : i2 + ((size_t)(l - nl_d - nl_f) << 7));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+        }
+    }
     // ---- HBM -> shared memory: detections, hot part of the tracker state --------------------
     {
         const double* g = p.dets + (size_t)s * p.max_dets * 6;
