@@ -2,18 +2,20 @@
 // stream, one thread per track slot.
 //
 // Data flow per stream (HBM is touched exactly once in each direction):
-//   * detections [nd, 6] and the position half of the Kalman mean + 3 lifecycle ints of every
-//     slot are staged in shared memory; velocities and the 12 covariance terms of a slot are NOT
-//     needed for association (ByteTrack costs only use boxes), so each thread loads them straight
-//     into registers at the single deferred predict+update point and keeps them there until the
-//     final write;
-//   * candidate pairs come from per-frame cell masks (48 x-cells and 24 y-cells, each a
-//     bitmask of the detections whose box touches the cell): a track runs the exact IoU test
-//     only against detections sharing a cell range with it in both axes - nothing T x D is
-//     ever computed, let alone written to HBM;
-//   * the assignment is solved on the pruned graph in shared memory (lap_sparse.cuh);
-//   * the state is written back already in the reference's new list order (tracked list, then
-//     lost list), together with the output rows.
+//   * thread j fetches detection row j whole, thread t the mean and 3 lifecycle ints of slot t; boxes and the position
+//     half of the mean are staged in shared memory; velocities and the 12 covariance terms of a slot are NOT needed for
+//     association (ByteTrack costs only use boxes), so each thread loads them at the single deferred predict + update
+//     point and parks the updated covariance in shared memory (storage of the dead solver arrays) until the final write;
+//   * candidate pairs come from per-frame cell masks (32 x-cells, 16 y-cells; per axis two monotone bitmask families
+//     "starts at or before cell c" / "ends at or after cell c", built by warp bit-transposes): a track tests only the
+//     detections whose cell range meets its own in both axes - nothing T x D is ever computed, let alone written to HBM;
+//   * the assignment is solved on the pruned graph in shared memory (lap_sparse.cuh: greedy tight start, concurrent
+//     shortest augmenting paths for the few contested rows); ByteTrack collects the second association's candidates
+//     during the first build;
+//   * the state is written back already in the reference's new list order (tracked list, then lost list), together
+//     with the output rows.
+// The step is latency bound (a CTA alone on an SM needs 35 k cycles, four together 53 k): every phase is organised for
+// short dependent chains and few barriers - see DESIGN.md 4.1 / 6.
 //
 // Replaces BYTETracker.update (boxmot/trackers/bytetrack/byte_tracker.py:132-281) and what it
 // calls: STrack.multi_predict :35-48 -> KalmanFilter.multi_predict (bytetrack_kf.py:155-192),
