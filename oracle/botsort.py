@@ -149,7 +149,7 @@ class BoTSORTOracle:
         emb[mask] = 1.0
         return np.minimum(iou_d, emb)
 
-    def update(self, dets, feats=None):
+    def update(self, dets, feats=None, warp=None):
         assert isinstance(dets, np.ndarray), "dets must be np.ndarray"
         assert dets.ndim == 2, "dets must be two-dimensional"
         assert dets.shape[1] == 6, "dets must have 6 columns"
@@ -180,7 +180,13 @@ class BoTSORTOracle:
             mean, cov = kalman.predict(KIND, mean, cov)
             for k, t in enumerate(pool):
                 t.mean, t.cov = mean[k], cov[k]
-        # multi_gmc with the identity warp is an exact no-op (:94-111)
+        # multi_gmc (:94-111) on the pool, then on the unconfirmed tracks; with the identity warp an exact no-op
+        if warp is not None:
+            for group in (pool, unconfirmed):
+                if group:
+                    mean, cov = kalman.apply_warp(np.stack([t.mean for t in group]), np.stack([t.cov for t in group]), warp)
+                    for k, t in enumerate(group):
+                        t.mean, t.cov = mean[k], cov[k]
 
         activated, refound, newly_lost, newly_removed = [], [], [], []
         m1, ut1, ud1 = assign_with_limit(self._combined(pool, d1, self.fuse_first), self.match_thresh)

@@ -29,8 +29,9 @@ def botsort_scenario(name):
     import sys
     if GOLDEN not in sys.path:
         sys.path.insert(0, GOLDEN)
-    from scenarios import BOTSORT_SCENARIOS, BOTSORT_YAML, botsort_inputs
-    sc = BOTSORT_SCENARIOS[name]
+    from scenarios import BOTSORT_SCENARIOS, BOTSORT_YAML, botsort_inputs, camera_warps
+    sc = dict(BOTSORT_SCENARIOS[name])
+    sc["warps"] = camera_warps(sc) if sc.get("camera") else None
     cfg = dict(BOTSORT_YAML)
     cfg.update(sc["params"])
     dets, nd, _, feats = botsort_inputs(sc)

@@ -325,9 +325,10 @@ def gen_botsort():
         cfg.update(sc["params"])
         rh.reset_counters()
         trk = BoTSORT(None, "cpu", False, **cfg)
-        trk.cmc = rh.IdentityCMC()
+        trk.cmc = rh.ScriptedCMC(camera_warps(sc)) if sc.get("camera") else rh.IdentityCMC()
         outs, ints, counts, means, auxs, covs, cov_frames = [], [], [], [], [], [], []
         for f in range(sc["n_frames"]):
+            trk.cmc.frame = f
             rows = np.nonzero(dets[f, :nd[f], 4] > cfg["track_high_thresh"])[0]
             if cfg.get("with_reid", True) and len(rows):
                 rh.FakeReID.queue.append(embs[f, rows])

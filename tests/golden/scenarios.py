@@ -16,12 +16,25 @@ BOTSORT_YAML = dict(track_high_thresh=0.33824964456239337, track_low_thresh=0.1,
                     appearance_thresh=0.4818211117541298, frame_rate=30)       # boxmot/configs/botsort.yaml
 
 
+def _through_camera(sc, dets, nd):
+    """The scene as the moving camera sees it: box corners pushed through the accumulated warps (in place)."""
+    acc = np.eye(3)
+    for f, w in enumerate(camera_warps(sc)):
+        acc = np.vstack([w, [0.0, 0.0, 1.0]]) @ acc
+        for j in range(nd[f]):
+            x1, y1, x2, y2 = dets[f, j, :4]
+            p = acc[:2, :2] @ np.array([[x1, x2], [y1, y2]]) + acc[:2, 2:3]
+            dets[f, j, :4] = [p[0].min(), p[1].min(), p[0].max(), p[1].max()]
+
+
 def botsort_inputs(sc):
     """Deterministic inputs of a BoT-SORT scenario (shared with the tests, which re-generate them instead
     of storing ~10 MB of embeddings): dets[F, D, 6], ndets[F], seam features[F, D, emb] (what
     ReIDDetectMultiBackend.get_features returns for the first-round rows: raw / Frobenius norm, scattered
     back to detection rows; zero elsewhere)."""
     dets, nd, embs = make_stream(3, sc["stream"], sc["n_objects"], sc["n_frames"], emb_dim=sc["emb_dim"], **sc["kw"])
+    if sc.get("camera"):
+        _through_camera(sc, dets, nd)
     if sc.get("classes"):
         rng = np.random.default_rng(sc["stream"] + 7)
         dets[..., 5] = rng.integers(0, sc["classes"], dets.shape[:2]).astype(np.float64) * (dets[..., 4] > 0)
@@ -49,6 +62,10 @@ BOTSORT_SCENARIOS = {
     "botsort_fuse": dict(stream=905, n_objects=20, n_frames=150, emb_dim=128, kw=dict(miss_prob=0.2, fp_rate=2.5),
                          params=dict(fuse_first_associate=True, track_high_thresh=0.5, new_track_thresh=0.6, match_thresh=0.8,
                                      proximity_thresh=0.5, appearance_thresh=0.25, track_buffer=30)),
+    # a moving camera: STrack.multi_gmc (bot_sort.py:94-111) with a scripted warp per frame; covariances become dense
+    "botsort_cam": dict(stream=908, n_objects=16, n_frames=120, emb_dim=128, kw=dict(miss_prob=0.15, fp_rate=1.5), camera=True,
+                        params=dict(track_high_thresh=0.5, new_track_thresh=0.6, match_thresh=0.8, proximity_thresh=0.5,
+                                    appearance_thresh=0.25, track_buffer=30)),
 }
 
 
@@ -86,14 +103,7 @@ def strongsort_inputs(sc):
     """dets[F, D, 6], ndets[F], raw embeddings, seam features (every detection row / Frobenius norm of the frame's matrix)."""
     dets, nd, embs = make_stream(4, sc["stream"], sc["n_objects"], sc["n_frames"], emb_dim=sc["emb_dim"], **sc["kw"])
     if sc.get("camera"):
-        # the scene as the moving camera sees it: box corners pushed through the accumulated warps
-        acc = np.eye(3)
-        for f, w in enumerate(camera_warps(sc)):
-            acc = np.vstack([w, [0.0, 0.0, 1.0]]) @ acc
-            for j in range(nd[f]):
-                x1, y1, x2, y2 = dets[f, j, :4]
-                p = acc[:2, :2] @ np.array([[x1, x2], [y1, y2]]) + acc[:2, 2:3]
-                dets[f, j, :4] = [p[0].min(), p[1].min(), p[0].max(), p[1].max()]
+        _through_camera(sc, dets, nd)
     feats = np.zeros_like(embs)
     for f in range(sc["n_frames"]):
         if nd[f]:

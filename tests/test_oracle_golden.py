@@ -172,7 +172,7 @@ def test_ocsort_reference_known_answer():
 
 
 # ----------------------------------------------------------------------------- BoT-SORT
-@pytest.mark.parametrize("name", ["botsort_c3", "botsort_churn", "botsort_noreid", "botsort_fuse"])
+@pytest.mark.parametrize("name", ["botsort_c3", "botsort_churn", "botsort_noreid", "botsort_fuse", "botsort_cam"])
 def test_botsort_oracle_replays_reference(name):
     from _util import botsort_scenario
     from oracle.botsort import BoTSORTOracle
@@ -183,7 +183,7 @@ def test_botsort_oracle_replays_reference(name):
     for f in g["cov_frames"]:
         cov_offs.append(cov_offs[-1] + int(g["counts"][f].sum()))
     for f in range(sc["n_frames"]):
-        out = trk.update(dets[f, :nd[f]], feats[f, :nd[f]])
+        out = trk.update(dets[f, :nd[f]], feats[f, :nd[f]], warp=None if sc["warps"] is None else sc["warps"][f])
         ref = g["out"][g["out_offs"][f]:g["out_offs"][f + 1]]
         assert out.reshape(-1, 8).shape == ref.shape, f"frame {f}"
         if ref.size:
