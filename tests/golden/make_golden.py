@@ -433,7 +433,58 @@ def gen_strongsort():
               cov_frames=np.array(cov_frames, dtype=np.int32), final_feat=final_feat)
 
 
-GENERATORS = {"kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
+def _doc_snapshot(trk):
+    ts = trk.trackers
+    ints = np.array([[t.id, t.age, t.time_since_update, t.hits, t.hit_streak, int(t.kf.observed), int(t.frozen)] for t in ts],
+                    dtype=np.int32).reshape(-1, 7)
+    x = np.stack([t.kf.x[:, 0] for t in ts]) if ts else np.zeros((0, 8))
+    P = np.stack([t.kf.P.reshape(64) for t in ts]) if ts else np.zeros((0, 64))
+    vel = np.array([t.velocity if t.velocity is not None else np.zeros(2) for t in ts]).reshape(-1, 2)
+    last = np.array([t.last_observation for t in ts], dtype=np.float64).reshape(-1, 5)
+    return ints, x, P, vel, last
+
+
+def gen_deepocsort():
+    rh.install()
+    from scenarios import DEEPOCSORT_SCENARIOS, DEEPOCSORT_YAML, deepocsort_inputs
+    from boxmot.trackers.deepocsort.deep_ocsort import DeepOCSort
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    only = os.environ.get("GOLDEN_ONLY")
+    for name, sc in DEEPOCSORT_SCENARIOS.items():
+        if only and name not in only.split(","):
+            continue
+        cfg = dict(DEEPOCSORT_YAML)
+        cfg.update(sc["params"])
+        dets, nd, embs, feats = deepocsort_inputs(sc, cfg["det_thresh"])
+        trk = DeepOCSort(None, "cpu", False, False, **cfg)          # resets KalmanBoxTracker.count to 1 (deep_ocsort.py:347)
+        trk.cmc = rh.ScriptedCMC(camera_warps(sc)) if sc.get("camera") else rh.IdentityCMC()
+        outs, ints, xs, Ps, vels, lasts, heavy = [], [], [], [], [], [], []
+        for f in range(sc["n_frames"]):
+            trk.cmc.frame = f
+            keep = dets[f, :nd[f], 4] > cfg["det_thresh"]
+            if keep.any():
+                rh.FakeReID.queue.append(embs[f, :nd[f]][keep])
+            o = trk.update(dets[f, :nd[f]], img)
+            outs.append(o)
+            ii, x, P, vel, last = _doc_snapshot(trk)
+            ints.append(ii)
+            xs.append(x)
+            vels.append(vel)
+            lasts.append(last)
+            if f % 10 == 9 or f == sc["n_frames"] - 1:
+                Ps.append(P)
+                heavy.append(f)
+        assert not rh.FakeReID.queue
+        ts = trk.trackers
+        final_emb = np.stack([np.asarray(t.emb, dtype=np.float64) for t in ts]) if ts else np.zeros((0, sc["emb_dim"]))
+        out_flat, out_offs = _ragged(outs, 8)
+        int_flat, int_offs = _ragged(ints, 7)
+        _save(name, ndets=nd, dets_sum=np.array([dets.sum(), float(sum(np.abs(f).sum() for f in feats))]), out=out_flat,
+              out_offs=out_offs, rec=int_flat.astype(np.int32), rec_offs=int_offs, x=_ragged(xs, 8)[0], vel=_ragged(vels, 2)[0],
+              last=_ragged(lasts, 5)[0], P=_ragged(Ps, 64)[0], heavy_frames=np.array(heavy, dtype=np.int32), final_emb=final_emb)
+
+
+GENERATORS = {"deepocsort": gen_deepocsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
               "mot": gen_mot, "strongsort": gen_strongsort, "aux": gen_aux}
 
 if __name__ == "__main__":

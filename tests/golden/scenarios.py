@@ -110,3 +110,33 @@ def strongsort_inputs(sc):
             raw = embs[f, :nd[f]]
             feats[f, :nd[f]] = raw / np.linalg.norm(raw)
     return dets, nd, embs, feats
+
+
+# ----------------------------------------------------------------------------- DeepOCSORT
+# boxmot/configs/deepocsort.yaml as forwarded by tracker_zoo.py:86-98 (the rest are the constructor defaults,
+# deep_ocsort.py:308-330)
+DEEPOCSORT_YAML = dict(det_thresh=0, max_age=30, min_hits=1, iou_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2)
+DEEPOCSORT_SCENARIOS = {
+    # occlusion runs exercise freeze / the quirky unfreeze (deepocsort_kf.py:433-478) / OCR
+    "deepocsort_c4": dict(stream=0, n_objects=25, n_frames=120, emb_dim=128, kw=dict(occlusion=True), params={}),
+    # misses and false positives, a detection threshold, short memory, output after 3 hits, plain IoU, no adaptive weight
+    "deepocsort_churn": dict(stream=911, n_objects=16, n_frames=160, emb_dim=64, kw=dict(miss_prob=0.3, fp_rate=3.0),
+                             params=dict(det_thresh=0.3, max_age=8, min_hits=3, asso_func="iou", aw_off=True)),
+    # a moving camera: apply_affine_correction (deep_ocsort.py:226-244, deepocsort_kf.py:387-405) on live and frozen state
+    "deepocsort_cam": dict(stream=912, n_objects=14, n_frames=120, emb_dim=64, kw=dict(miss_prob=0.15, fp_rate=1.0, occlusion=True),
+                           camera=True, params={}),
+}
+
+
+def deepocsort_inputs(sc, det_thresh):
+    """dets[F, D, 6], ndets[F], raw embeddings, and per frame the seam features of the detections that pass
+    `conf > det_thresh` (deep_ocsort.py:382-390: the filter runs before get_features, so the Frobenius norm is theirs)."""
+    dets, nd, embs = make_stream(4, sc["stream"], sc["n_objects"], sc["n_frames"], emb_dim=sc["emb_dim"], **sc["kw"])
+    if sc.get("camera"):
+        _through_camera(sc, dets, nd)
+    feats = []
+    for f in range(sc["n_frames"]):
+        keep = dets[f, :nd[f], 4] > det_thresh
+        raw = embs[f, :nd[f]][keep].astype(np.float32)
+        feats.append(raw / np.linalg.norm(raw) if len(raw) else np.zeros((0, sc["emb_dim"]), dtype=np.float32))
+    return dets, nd, embs, feats

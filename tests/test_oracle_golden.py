@@ -248,3 +248,20 @@ def test_camera_warp_and_adaptive_weight_match_reference():
     for k in range(4):
         assert_close(deepocsort.compute_aw_max_metric(g[f"aw_in{k}"], 0.75, 0.5), g[f"aw_out{k}"], what=f"aw {k}")
     assert_close(deepocsort.compute_aw_max_metric(g["aw_in0"], 0.4, 0.3), g["aw_out0_b"], what="aw 0 b")
+
+
+# ----------------------------------------------------------------------------- DeepOCSORT
+@pytest.mark.parametrize("name", ["deepocsort_c4", "deepocsort_churn", "deepocsort_cam"])
+def test_deepocsort_oracle_replays_reference(name):
+    """ids, hit / age counters, observed / frozen flags exact; 8-d filter state, velocities, last observations and boxes to
+    1e-9 against the live reference, through occlusions (the quirky unfreeze), OCR and a moving camera."""
+    from _util import check_deepocsort_frame, deepocsort_scenario, heavy_offsets
+    from oracle.deepocsort import DeepOCSortOracle
+    sc, cfg, dets, nd, feats, g = deepocsort_scenario(name)
+    trk = DeepOCSortOracle(**cfg)
+    heavy = heavy_offsets(g)
+    for f in range(sc["n_frames"]):
+        out = trk.update(dets[f, :nd[f]], feats[f], warp=None if sc["warps"] is None else sc["warps"][f])
+        check_deepocsort_frame(name, f, out, trk.snapshot(), g, heavy)
+    assert_close(trk.snapshot()["emb"], g["final_emb"], rel=1e-6, what="embeddings")
+    assert trk.stats["oru"] > 50 and trk.stats["lap_frames"] > 20 and trk.stats["ocr_frames"] >= 1
