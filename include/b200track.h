@@ -236,6 +236,30 @@ int b200track_nn_cosine_distance(int32_t n_tracks, int32_t n_dets, int32_t dim, 
 int b200track_linear_sum_assignment(int32_t batch, int32_t rows, int32_t cols, const double* d_cost,
                                     int32_t* d_col4row, int32_t* d_err, void* stream);
 
+/* ---- DeepOCSORT operators (csrc/kf8.cu): the 8-d [x, y, w, h, vx, vy, vw, vh] filter the reference configures in
+ * KalmanBoxTracker.__init__ (deep_ocsort.py:103-138), dense [n, 8] / [n, 8, 8] arrays.
+ * b200track_kf8_predict <- KalmanBoxTracker.predict's kf.predict(Q=new_kf_process_noise(w, h)) (deep_ocsort.py:76-80, :263-266,
+ *     deepocsort_kf.py:340-381); unit_q != 0: Q = I, the filter default that unfreeze's own predicts use.
+ * b200track_kf8_update  <- kf.update(z, R=new_kf_measurement_noise(w, h)) (deep_ocsort.py:83-87, :217-218,
+ *     deepocsort_kf.py:549-563: Joseph form, explicit inverse of S); d_wh [n, 2] = the w, h the caller read from the
+ *     state BEFORE a possible unfreeze (as the reference does); NULL: R = I.
+ * b200track_kf8_oru     <- KalmanFilter.unfreeze (deepocsort_kf.py:433-478) on the restored states: d_box1 [n, 4] =
+ *     last_measurement, d_box2 [n, 4] = the new measurement (both read as [x, y, s, r], the reference's quirk), d_gap [n]
+ *     = index2 - index1; the whole virtual trajectory of every track in one launch; d_last_virtual [n, 4] = the last
+ *     virtual box (the final entry of history_obs afterwards).
+ * b200track_ocm_cost    <- associate's cost (association.py:130-172): d_cost[d, t] = -(d_sim[d, t] + angle[d, t] + d_emb[d, t])
+ *     with the velocity-direction term from d_dets5 [D, 5], d_vel [T, 2] (dy, dx), d_prev5 [T, 5] (k_previous_obs; col 4 < 0
+ *     = none); d_emb may be NULL; d_dets5 NULL: no direction term (the OCR round's -iou, deep_ocsort.py:478).  The canonical
+ *     tie-break of the no-limit assignment, + 2^-50 * (d * T + t), is part of the cost.
+ * b200track_dot_matrix  <- dets_embs @ trk_embs.T (deep_ocsort.py:433, :464): a [n, dim], b [m, dim] -> out [n, m], fp64. */
+int b200track_kf8_predict(int32_t n, double* d_mean, double* d_cov, int32_t unit_q, void* stream);
+int b200track_kf8_update(int32_t n, double* d_mean, double* d_cov, const double* d_z, const double* d_wh, void* stream);
+int b200track_kf8_oru(int32_t n, double* d_mean, double* d_cov, const double* d_box1, const double* d_box2, const int32_t* d_gap,
+                      double* d_last_virtual, void* stream);
+int b200track_ocm_cost(int32_t n_dets, int32_t n_tracks, const double* d_dets5, const double* d_vel, const double* d_prev5,
+                       double inertia, const double* d_sim, const double* d_emb, double* d_cost, void* stream);
+int b200track_dot_matrix(int32_t n, int32_t m, int32_t dim, const double* d_a, const double* d_b, double* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -100,3 +100,73 @@ def heavy_offsets(g):
         offs[int(f)] = (pos, pos + n)
         pos += n
     return offs
+
+
+class OracleOps:
+    """The operator namespace of yolo_tracking_b200._ops restated with the CPU oracle - TEST ONLY: it lets the `not gpu`
+    suite replay the host-side list logic of an operator-backed tracker (monkeypatched in, never importable by the
+    product) against the goldens; the GPU suite runs the same replay through the CUDA operators."""
+    @staticmethod
+    def _torch():
+        return None
+
+    @staticmethod
+    def box_similarity(name, a, b, w=0.0, h=0.0):
+        from oracle import boxes
+        return boxes.similarity(name, np.asarray(a, dtype=np.float64).reshape(-1, 4), np.asarray(b, dtype=np.float64).reshape(-1, 4), w, h)
+
+    @staticmethod
+    def dot_matrix(a, b):
+        return np.asarray(a, dtype=np.float64) @ np.asarray(b, dtype=np.float64).T
+
+    @staticmethod
+    def aw_max_metric(emb, w, bottom=0.5):
+        from oracle.deepocsort import compute_aw_max_metric
+        return compute_aw_max_metric(emb, w, bottom)
+
+    @staticmethod
+    def ocm_cost(sim, dets5=None, vel=None, prev5=None, inertia=0.0, emb=None):
+        from oracle.lap import tie_break
+        s = np.array(sim, dtype=np.float64)
+        if dets5 is not None:
+            cx_d, cy_d = (dets5[:, 0] + dets5[:, 2]) / 2.0, (dets5[:, 1] + dets5[:, 3]) / 2.0
+            cx_p, cy_p = (prev5[:, 0] + prev5[:, 2]) / 2.0, (prev5[:, 1] + prev5[:, 3]) / 2.0
+            dx, dy = cx_d[None, :] - cx_p[:, None], cy_d[None, :] - cy_p[:, None]
+            norm = np.sqrt(dx ** 2 + dy ** 2) + 1e-6
+            cosang = np.clip(vel[:, 1:2] * (dx / norm) + vel[:, 0:1] * (dy / norm), -1, 1)
+            diff = (np.pi / 2.0 - np.abs(np.arccos(cosang))) / np.pi
+            valid = (prev5[:, 4] >= 0).astype(np.float64)[:, None]
+            s = s + ((valid * diff) * inertia).T * dets5[:, 4:5]
+        if emb is not None:
+            s = s + emb
+        return tie_break(-s)
+
+    @staticmethod
+    def lapjv(cost, cost_limit=np.inf):
+        from oracle.lap import lapjv_extended
+        _, x, y = lapjv_extended(cost, cost_limit)
+        return x, y
+
+    @staticmethod
+    def kf8_predict(mean, cov, unit_q=False):
+        from oracle import deepocsort as o
+        out = [o.kf8_predict(m, c, np.eye(8) if unit_q else o.process_noise(m[2], m[3])) for m, c in zip(mean, cov)]
+        return np.stack([a for a, _ in out]), np.stack([b for _, b in out])
+
+    @staticmethod
+    def kf8_update(mean, cov, z, wh=None):
+        from oracle import deepocsort as o
+        out = [o.kf8_correct(m, c, zz, np.eye(4) if wh is None else o.measurement_noise(wh[i][0], wh[i][1]))
+               for i, (m, c, zz) in enumerate(zip(mean, cov, z))]
+        return np.stack([a for a, _ in out]), np.stack([b for _, b in out])
+
+    @staticmethod
+    def kf8_oru(mean, cov, box1, box2, gap):
+        from oracle import deepocsort as o
+        out = [o.kf8_virtual_trajectory(m, c, b1, b2, int(g)) for m, c, b1, b2, g in zip(mean, cov, box1, box2, gap)]
+        return np.stack([a for a, _, _ in out]), np.stack([b for _, b, _ in out]), np.stack([v[-1] for _, _, v in out])
+
+    @staticmethod
+    def kf_apply_warp(mean, cov, warp, warp_index=None):
+        from oracle import kalman
+        return kalman.apply_warp(np.asarray(mean), np.asarray(cov), np.asarray(warp))

@@ -78,6 +78,11 @@ SIGNATURES = {
     "b200track_nn_cosine_distance": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P]),
     "b200track_linear_sum_assignment": (C.c_int, [_I, _I, _I, _P, _P, _P, _P]),
     "b200track_lapjv": (C.c_int, [_I, _I, _I, _P, _D, _P, _P, _P]),
+    "b200track_kf8_predict": (C.c_int, [_I, _P, _P, _I, _P]),
+    "b200track_kf8_update": (C.c_int, [_I, _P, _P, _P, _P, _P]),
+    "b200track_kf8_oru": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P]),
+    "b200track_ocm_cost": (C.c_int, [_I, _I, _P, _P, _P, _D, _P, _P, _P, _P]),
+    "b200track_dot_matrix": (C.c_int, [_I, _I, _I, _P, _P, _P, _P]),
 }
 
 _lib = None

@@ -294,3 +294,68 @@ def lapjv(cost, cost_limit=np.inf):
     _sync_check(lib.b200track_lapjv(B, R, Cc, _p(dc) if R * Cc else None, float(cost_limit), _p(x), _p(y), None))
     x, y = x.cpu().numpy()[:, :R], y.cpu().numpy()[:, :Cc]
     return (x[0], y[0]) if single else (x, y)
+
+
+# ---------------------------------------------------------------------------------- DeepOCSORT operators (csrc/kf8.cu)
+def kf8_predict(mean, cov, unit_q=False):
+    """kf.predict(Q=new_kf_process_noise(w, h)) of DeepOCSORT's 8-d filter (deep_ocsort.py:76-80, :263-266)."""
+    lib = _lib.load()
+    m = _dev(np.asarray(mean).reshape(-1, 8), np.float64)
+    c = _dev(np.asarray(cov).reshape(-1, 8, 8), np.float64)
+    _sync_check(lib.b200track_kf8_predict(m.shape[0], _p(m), _p(c), int(bool(unit_q)), None))
+    return m.cpu().numpy(), c.cpu().numpy()
+
+
+def kf8_update(mean, cov, z, wh=None):
+    """kf.update(z, R=new_kf_measurement_noise(w, h)) (deepocsort_kf.py:549-563); wh [n, 2] or None (R = I)."""
+    lib = _lib.load()
+    m = _dev(np.asarray(mean).reshape(-1, 8), np.float64)
+    c = _dev(np.asarray(cov).reshape(-1, 8, 8), np.float64)
+    dz = _dev(np.asarray(z).reshape(-1, 4), np.float64)
+    dwh = _dev(np.asarray(wh).reshape(-1, 2), np.float64) if wh is not None else None
+    _sync_check(lib.b200track_kf8_update(m.shape[0], _p(m), _p(c), _p(dz), _p(dwh), None))
+    return m.cpu().numpy(), c.cpu().numpy()
+
+
+def kf8_oru(mean, cov, box1, box2, gap):
+    """KalmanFilter.unfreeze's virtual trajectory (deepocsort_kf.py:433-478) -> mean, cov, last virtual box [n, 4]."""
+    lib = _lib.load()
+    torch = _torch()
+    m = _dev(np.asarray(mean).reshape(-1, 8), np.float64)
+    c = _dev(np.asarray(cov).reshape(-1, 8, 8), np.float64)
+    b1 = _dev(np.asarray(box1).reshape(-1, 4), np.float64)
+    b2 = _dev(np.asarray(box2).reshape(-1, 4), np.float64)
+    g = _dev(np.asarray(gap).reshape(-1), np.int32)
+    last = torch.empty((m.shape[0], 4), dtype=torch.float64, device=m.device)
+    _sync_check(lib.b200track_kf8_oru(m.shape[0], _p(m), _p(c), _p(b1), _p(b2), _p(g), _p(last), None))
+    return m.cpu().numpy(), c.cpu().numpy(), last.cpu().numpy()
+
+
+def ocm_cost(sim, dets5=None, vel=None, prev5=None, inertia=0.0, emb=None):
+    """-(sim + velocity-direction term + emb) + the canonical tie-break (association.py:130-172); sim [D, T]."""
+    lib = _lib.load()
+    torch = _torch()
+    sim = np.asarray(sim, dtype=np.float64)
+    D, T = sim.shape
+    if D == 0 or T == 0:
+        return np.zeros((D, T))
+    ds = _dev(sim, np.float64)
+    dd = _dev(np.asarray(dets5).reshape(D, 5), np.float64) if dets5 is not None else None
+    dv = _dev(np.asarray(vel).reshape(T, 2), np.float64) if dets5 is not None else None
+    dp = _dev(np.asarray(prev5).reshape(T, 5), np.float64) if dets5 is not None else None
+    de = _dev(np.asarray(emb).reshape(D, T), np.float64) if emb is not None else None
+    out = torch.empty_like(ds)
+    _sync_check(lib.b200track_ocm_cost(D, T, _p(dd), _p(dv), _p(dp), float(inertia), _p(ds), _p(de), _p(out), None))
+    return out.cpu().numpy()
+
+
+def dot_matrix(a, b):
+    """a @ b.T with fp64 accumulation (deep_ocsort.py:433): a [n, dim], b [m, dim] -> [n, m]."""
+    lib = _lib.load()
+    torch = _torch()
+    da = _dev(np.asarray(a, dtype=np.float64), np.float64)
+    db = _dev(np.asarray(b, dtype=np.float64), np.float64)
+    out = torch.empty((da.shape[0], db.shape[0]), dtype=torch.float64, device=da.device)
+    if out.numel():
+        _sync_check(lib.b200track_dot_matrix(da.shape[0], db.shape[0], da.shape[1], _p(da), _p(db), _p(out), None))
+    return out.cpu().numpy()

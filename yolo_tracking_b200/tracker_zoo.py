@@ -43,4 +43,9 @@ def create_tracker(tracker_type, tracker_config, reid_weights=None, device=0, ha
         from .trackers.strongsort import StrongSORT
         return StrongSORT(reid_weights, device, half, max_dist=cfg.max_dist, max_iou_dist=cfg.max_iou_dist, max_age=cfg.max_age,
                           n_init=cfg.n_init, nn_budget=cfg.nn_budget, mc_lambda=cfg.mc_lambda, ema_alpha=cfg.ema_alpha, **capacity)
-    raise ValueError(f"No such tracker: {tracker_type!r} (built: bytetrack, ocsort, botsort, strongsort)")
+    if tracker_type == "deepocsort":
+        from .trackers.deepocsort import DeepOCSort
+        return DeepOCSort(reid_weights, device, half, per_class, det_thresh=cfg.det_thresh, max_age=cfg.max_age,
+                          min_hits=cfg.min_hits, iou_threshold=cfg.iou_thresh, delta_t=cfg.delta_t, asso_func=cfg.asso_func,
+                          inertia=cfg.inertia, **capacity)
+    raise ValueError(f"No such tracker: {tracker_type!r} (built: bytetrack, ocsort, botsort, strongsort, deepocsort)")
