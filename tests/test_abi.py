@@ -56,7 +56,7 @@ def test_no_cpu_fallback(has_cuda):
 def test_factory_names_and_configs():
     import yaml
     import yolo_tracking_b200 as pkg
-    assert pkg.TRACKERS == ["bytetrack", "botsort", "ocsort", "strongsort"]
+    assert pkg.TRACKERS == ["bytetrack", "botsort", "ocsort", "strongsort", "deepocsort"]
     for name in pkg.TRACKERS:
         path = pkg.get_tracker_config(name)
         assert path.name == name + ".yaml" and path.exists()
