@@ -117,6 +117,21 @@ if on("kf_project"):
     report("kf_project_kernel (reads mean[:4] + the 4x4 block: 160 B, writes 160 B per track)", ms, best, alg_bytes=N * 320, l2=l2note,
            extra={"tracks": N, "bytes_per_track": 320})
 
+if on("kf8"):
+    # DeepOCSORT's 8-d filter (csrc/kf8.cu): same dense layout and bytes as the lines above, one thread per track
+    m8 = mean.clone()
+    m8[:, 2] = torch.from_numpy(rng.uniform(30, 90, N)).to(dev)
+    c8 = cov.clone()
+    z8 = (m8[:, :4] + torch.randn((N, 4), device=dev, dtype=torch.float64) * 2).contiguous()
+    wh8 = m8[:, 2:4].contiguous()
+    ms, best = timeit(lambda: _lib.check(lib.b200track_kf8_predict(N, p(m8), p(c8), 0, None)), not big)
+    report("kf8_predict_kernel (DeepOCSORT filter, Q from w, h)", ms, best, alg_bytes=2 * state_bytes, l2=l2note,
+           extra={"tracks": N, "bytes_per_track": 2 * 576})
+    ms, best = timeit(lambda: _lib.check(lib.b200track_kf8_update(N, p(m8), p(c8), p(z8), p(wh8), None)), not big)
+    report("kf8_update_kernel (Joseph form, 4x4 inverse, R from w, h)", ms, best, alg_bytes=2 * state_bytes + N * 48, l2=l2note,
+           extra={"tracks": N, "bytes_per_track": 2 * 576 + 48})
+    del m8, c8, z8, wh8
+
 # ---- config 4 ------------------------------------------------------------------------------------------
 mean4 = mean[:S * T].view(S, T, 8)
 meas = (mean4[:, torch.randint(0, T, (D,), device=dev), :4] + torch.randn((S, D, 4), device=dev, dtype=torch.float64) * 4).contiguous()
