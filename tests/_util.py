@@ -170,3 +170,35 @@ class OracleOps:
     def kf_apply_warp(mean, cov, warp, warp_index=None):
         from oracle import kalman
         return kalman.apply_warp(np.asarray(mean), np.asarray(cov), np.asarray(warp))
+
+
+def deepocsort_known_answer(make_tracker):
+    """The reference's own DeepOCSORT test (tests/test_python.py:51-95): two boxes in, two rows out in reversed order
+    within atol=1 / rtol=7e-3; nothing before min_hits consecutive hits once frame_count > min_hits."""
+    from numpy.testing import assert_allclose
+    rgb = np.random.default_rng(0).integers(0, 255, size=(640, 640, 3), dtype=np.uint8)
+    det = np.array([[144, 212, 578, 480, 0.82, 0], [425, 281, 576, 472, 0.56, 65]], dtype=np.float64)
+    trk = make_tracker()
+    trk.asso_func = "centroid"
+    out = trk.update(det, rgb)
+    assert out.shape == (2, 8)
+    assert_allclose(det, np.flip(np.delete(out, [4, 7], axis=1), axis=0), atol=1, rtol=7e-3)
+    trk = make_tracker()
+    trk.min_hits = 2
+    sizes = [trk.update(d, rgb).size for d in (np.empty((0, 6)), np.empty((0, 6)), det, det)]
+    assert sizes == [0, 0, 0, 0]
+    out = trk.update(det, rgb)
+    assert out.shape == (2, 8)
+    out = trk.update(det, rgb)
+    assert out.shape == (2, 8)
+    assert_allclose(det, np.flip(np.delete(out, [4, 7], axis=1), axis=0), atol=1, rtol=7e-3)
+
+
+class RandomReID:
+    """get_features seam with seeded random embeddings through the reference's whole-matrix normalisation."""
+    def __init__(self, dim=32):
+        self.rng, self.dim = np.random.default_rng(5), dim
+
+    def get_features(self, xyxys, img):
+        f = self.rng.normal(0, 1, (len(xyxys), self.dim)).astype(np.float32)
+        return f / np.linalg.norm(f)

@@ -133,3 +133,10 @@ def test_deepocsort_factory_and_seam():
             assert_close(out[:, :4], ref[:, :4])
     with pytest.raises(AssertionError):
         trk.update(np.zeros((2, 5)), img)
+
+
+def test_deepocsort_reference_known_answer():
+    from _util import RandomReID, deepocsort_known_answer
+    import yolo_tracking_b200 as pkg
+    deepocsort_known_answer(lambda: pkg.create_tracker("deepocsort", pkg.get_tracker_config("deepocsort"), None, 0, False, False,
+                                                       model=RandomReID()))

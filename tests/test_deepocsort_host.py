@@ -33,3 +33,13 @@ def test_deepocsort_without_cuda_fails_loudly():
     from yolo_tracking_b200 import create_tracker, get_tracker_config
     with pytest.raises((RuntimeError, ImportError)):
         create_tracker("deepocsort", get_tracker_config("deepocsort"), None, 0, False, False)
+
+
+def test_deepocsort_reference_known_answer_host(monkeypatch):
+    from _util import RandomReID, deepocsort_known_answer
+    from yolo_tracking_b200.trackers import deepocsort as mod
+    import yolo_tracking_b200 as pkg
+    monkeypatch.setattr(mod, "_ops", OracleOps)
+    monkeypatch.setattr(mod, "_lib", types.SimpleNamespace(load=lambda: None, SIM=mod._lib.SIM))
+    deepocsort_known_answer(lambda: pkg.create_tracker("deepocsort", pkg.get_tracker_config("deepocsort"), None, 0, False, False,
+                                                       model=RandomReID()))
