@@ -127,21 +127,115 @@ __global__ void __launch_bounds__(K8_TPB) kf8_predict_kernel(int n, double* mean
 
 // kf.update(z, R) (deepocsort_kf.py:480-569, the observed branch): R = new_kf_measurement_noise(w, h) with the caller's
 // w, h (deep_ocsort.py:218: the state BEFORE a possible unfreeze), or R = I when wh is NULL.
-__global__ void __launch_bounds__(K8_TPB) kf8_update_kernel(int n, double* mean, double* cov, const double* __restrict__ z,
-                                                            const double* __restrict__ wh) {
-    __shared__ double sm[K8_TPB * K8_STRIDE];
-    const int base = blockIdx.x * K8_TPB, cnt = min(K8_TPB, n - base);
+// 32 tracks per CTA, 8 lanes per track - lane r owns row r of K, of (I - K H) P and of the result (one thread per track
+// needed 210 registers and ran at 0.34 of the HBM roofline).  The first warp factors the 32 innovation matrices, one
+// per lane, every lane then solves its own gain row; the gain rows are exchanged through shared memory inside the warp (a track's 8 lanes share a warp).
+constexpr int K8U_TPB = 32;
+__global__ void __launch_bounds__(K8U_TPB * 8, 5) kf8_update_kernel(int n, double* mean, double* cov, const double* __restrict__ z,
+                                                                   const double* __restrict__ wh) {
+    __shared__ double sm[K8U_TPB * K8_STRIDE];
+    __shared__ double sS[K8U_TPB][19];            // per track: L of S = L L^T (10), 1 / L[i][i] (4), diag R (4); odd stride
+    __shared__ double sK[K8U_TPB][33];            // per track: K (8 x 4)
+    const int base = blockIdx.x * K8U_TPB, cnt = min(K8U_TPB, n - base);
+    const int t = threadIdx.x >> 3, r = threadIdx.x & 7;
     k8_in(sm, mean, cov, base, cnt);
     if ((int)threadIdx.x < cnt) {
-        const int t = base + threadIdx.x;
-        double* x = sm + threadIdx.x * K8_STRIDE;
-        double r[4] = {1.0, 1.0, 1.0, 1.0}, zz[4];
+        const int q = threadIdx.x;
+        const double* P = sm + q * K8_STRIDE + 8;
+        double rr[4] = {1.0, 1.0, 1.0, 1.0}, L[4][4];
         if (wh) {
-            const double mw = xmul(1.0 / 20, wh[t * 2]), mh = xmul(1.0 / 20, wh[t * 2 + 1]);
-            r[0] = r[2] = xmul(mw, mw); r[1] = r[3] = xmul(mh, mh);
+            const double mw = xmul(1.0 / 20, wh[(size_t)(base + q) * 2]), mh = xmul(1.0 / 20, wh[(size_t)(base + q) * 2 + 1]);
+            rr[0] = rr[2] = xmul(mw, mw); rr[1] = rr[3] = xmul(mh, mh);
         }
-        for (int k = 0; k < 4; ++k) zz[k] = z[(size_t)t * 4 + k];
-        k8_update(x, x + 8, zz, r);
+        // S = P[:4, :4] + R is symmetric positive definite: the reference's explicit inverse (np.linalg.inv) times
+        // P H^T equals the two triangular solves below to rounding (the 1e-9 bar leaves ~6 digits of room)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            double d = xadd(P[j * 8 + j], rr[j]);
+#pragma unroll
+            for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+            L[j][j] = sqrt(d);
+            const double inv = 1.0 / L[j][j];
+            sS[q][10 + j] = inv;
+#pragma unroll
+            for (int i = j + 1; i < 4; ++i) {
+                double v = P[i * 8 + j];
+#pragma unroll
+                for (int k = 0; k < j; ++k) v -= L[i][k] * L[j][k];
+                L[i][j] = v * inv;
+            }
+        }
+        int o = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) sS[q][o++] = L[i][j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sS[q][14 + i] = rr[i];
+    }
+    __syncthreads();
+    double row[8], mr = 0.0, K[4], M[8];
+    if (t < cnt) {
+        const double* m = sm + t * K8_STRIDE;
+        const double* P = m + 8;
+        {
+            double L[4][4], inv[4], y[4];
+            int o = 0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) L[i][j] = sS[t][o++];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) inv[i] = sS[t][10 + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {                 // L y = P[r, :4]
+                double v = P[r * 8 + i];
+#pragma unroll
+                for (int q = 0; q < i; ++q) v -= L[i][q] * y[q];
+                y[i] = v * inv[i];
+            }
+#pragma unroll
+            for (int i = 3; i >= 0; --i) {                // L^T K[r, :] = y
+                double v = y[i];
+#pragma unroll
+                for (int q = i + 1; q < 4; ++q) v -= L[q][i] * K[q];
+                K[i] = v * inv[i];
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) sK[t][r * 4 + j] = K[j];
+        }
+        double a = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a = xadd(a, xmul(K[k], xsub(z[(size_t)(base + t) * 4 + k], m[k])));
+        mr = xadd(m[r], a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                                 // row r of (I - K H) P
+            double b = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) b = xadd(b, xmul(K[k], P[k * 8 + j]));
+            M[j] = xsub(P[r * 8 + j], b);
+        }
+    }
+    __syncwarp();                                                     // the track's gain rows are in sK (its 8 lanes share a warp)
+    if (t < cnt) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            double b = 0.0, c = 0.0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double kj = sK[t][j * 4 + k];
+                b = xadd(b, xmul(M[k], kj));
+                c = xadd(c, xmul(xmul(K[k], sS[t][14 + k]), kj));
+            }
+            row[j] = xadd(xsub(M[j], b), c);
+        }
+    }
+    __syncthreads();
+    if (t < cnt) {
+        double* m = sm + t * K8_STRIDE;
+        m[r] = mr;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) m[8 + r * 8 + c] = row[c];
     }
     k8_out(sm, mean, cov, base, cnt);
 }
@@ -244,7 +338,7 @@ extern "C" int b200track_kf8_predict(int32_t n, double* mean, double* cov, int32
 extern "C" int b200track_kf8_update(int32_t n, double* mean, double* cov, const double* z, const double* wh, void* st) {
     if (n < 0 || !mean || !cov || !z) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
     if (n == 0) return 0;
-    kf8_update_kernel<<<(n + K8_TPB - 1) / K8_TPB, K8_TPB, 0, (cudaStream_t)st>>>(n, mean, cov, z, wh);
+    kf8_update_kernel<<<(n + K8U_TPB - 1) / K8U_TPB, K8U_TPB * 8, 0, (cudaStream_t)st>>>(n, mean, cov, z, wh);
     LAUNCH_CHECK();
     return 0;
 }
