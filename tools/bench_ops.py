@@ -128,7 +128,7 @@ if on("kf8"):
     report("kf8_predict_kernel (DeepOCSORT filter, Q from w, h)", ms, best, alg_bytes=2 * state_bytes, l2=l2note,
            extra={"tracks": N, "bytes_per_track": 2 * 576})
     ms, best = timeit(lambda: _lib.check(lib.b200track_kf8_update(N, p(m8), p(c8), p(z8), p(wh8), None)), not big)
-    report("kf8_update_kernel (Joseph form, 4x4 inverse, R from w, h)", ms, best, alg_bytes=2 * state_bytes + N * 48, l2=l2note,
+    report("kf8_update_kernel (Joseph form, Cholesky solves per lane, R from w, h)", ms, best, alg_bytes=2 * state_bytes + N * 48, l2=l2note,
            extra={"tracks": N, "bytes_per_track": 2 * 576 + 48})
     del m8, c8, z8, wh8
 

@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(K8U_TPB * 8, 5) kf8_update_kernel(int n, doubl
         for (int i = 0; i < 4; ++i) sS[q][14 + i] = rr[i];
     }
     __syncthreads();
-    double row[8], mr = 0.0, K[4], M[8];
+    double mr = 0.0, K[4], M[8];
     if (t < cnt) {
         const double* m = sm + t * K8_STRIDE;
         const double* P = m + 8;
@@ -218,16 +218,16 @@ __global__ void __launch_bounds__(K8U_TPB * 8, 5) kf8_update_kernel(int n, doubl
     }
     __syncwarp();                                                     // the track's gain rows are in sK (its 8 lanes share a warp)
     if (t < cnt) {
+        // row r of M (I - K H)^T + K R K^T = M[r, j] - sum_k (M[r, k] - K[r, k] R_k) K[j, k]
+        double W[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) W[k] = xsub(M[k], xmul(K[k], sS[t][14 + k]));
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            double b = 0.0, c = 0.0;
+            double b = 0.0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const double kj = sK[t][j * 4 + k];
-                b = xadd(b, xmul(M[k], kj));
-                c = xadd(c, xmul(xmul(K[k], sS[t][14 + k]), kj));
-            }
-            row[j] = xadd(xsub(M[j], b), c);
+            for (int k = 0; k < 4; ++k) b = xadd(b, xmul(W[k], sK[t][j * 4 + k]));
+            M[j] = xsub(M[j], b);
         }
     }
     __syncthreads();
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(K8U_TPB * 8, 5) kf8_update_kernel(int n, doubl
         double* m = sm + t * K8_STRIDE;
         m[r] = mr;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) m[8 + r * 8 + c] = row[c];
+        for (int c = 0; c < 8; ++c) m[8 + r * 8 + c] = M[c];
     }
     k8_out(sm, mean, cov, base, cnt);
 }
