@@ -202,3 +202,29 @@ class RandomReID:
     def get_features(self, xyxys, img):
         f = self.rng.normal(0, 1, (len(xyxys), self.dim)).astype(np.float32)
         return f / np.linalg.norm(f)
+
+
+def deepocsort_edge_replay(make_tracker, make_oracle):
+    """Edges of DeepOCSort.update against the oracle: appearance switched off, empty frames in the middle of a run,
+    frames whose detections all fall under det_thresh, tracks that age out."""
+    from yolo_tracking_b200.synth import make_stream
+    dets, nd, embs = make_stream(4, 90, 9, 60, emb_dim=16, occlusion=True, miss_prob=0.1)
+    for cfg in (dict(embedding_off=True), dict(det_thresh=0.45, max_age=4, min_hits=2, asso_func="diou"), dict(aw_off=True, asso_func="ciou")):
+        base = dict(det_thresh=0, max_age=30, min_hits=1, iou_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2)
+        base.update(cfg)
+        trk, orc = make_tracker(**base), make_oracle(**base)
+        for f in range(60):
+            d = dets[f, :nd[f]].copy()
+            if f in (7, 8, 30):
+                d = np.empty((0, 6))
+            if f in (15, 16, 17, 18, 19, 20):
+                d[:, 4] = 0.01 * (1 + np.arange(len(d)))           # nothing passes a threshold of 0.45
+            keep = d[:, 4] > base["det_thresh"]
+            raw = embs[f, :len(d)][keep].astype(np.float32)
+            feats = raw / np.linalg.norm(raw) if len(raw) else np.zeros((0, 16), dtype=np.float32)
+            got = trk.update(d, (1080, 1920), feats=feats).reshape(-1, 8)
+            ref = orc.update(d, feats).reshape(-1, 8)
+            assert got.shape == ref.shape, (cfg, f)
+            assert np.array_equal(got[:, 4:], ref[:, 4:]), (cfg, f)
+            assert_close(got[:, :4], ref[:, :4], what=f"{cfg} frame {f}")
+        assert [t.id for t in trk.trackers] == [t.id for t in orc.trackers]

@@ -140,3 +140,10 @@ def test_deepocsort_reference_known_answer():
     import yolo_tracking_b200 as pkg
     deepocsort_known_answer(lambda: pkg.create_tracker("deepocsort", pkg.get_tracker_config("deepocsort"), None, 0, False, False,
                                                        model=RandomReID()))
+
+
+def test_deepocsort_edges():
+    from _util import deepocsort_edge_replay
+    from oracle.deepocsort import DeepOCSortOracle
+    from yolo_tracking_b200 import DeepOCSORT
+    deepocsort_edge_replay(lambda **kw: DeepOCSORT(None, 0, False, False, **kw), lambda **kw: DeepOCSortOracle(**kw))

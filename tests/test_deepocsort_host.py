@@ -43,3 +43,12 @@ def test_deepocsort_reference_known_answer_host(monkeypatch):
     monkeypatch.setattr(mod, "_lib", types.SimpleNamespace(load=lambda: None, SIM=mod._lib.SIM))
     deepocsort_known_answer(lambda: pkg.create_tracker("deepocsort", pkg.get_tracker_config("deepocsort"), None, 0, False, False,
                                                        model=RandomReID()))
+
+
+def test_deepocsort_edges_host(monkeypatch):
+    from _util import deepocsort_edge_replay
+    from oracle.deepocsort import DeepOCSortOracle
+    from yolo_tracking_b200.trackers import deepocsort as mod
+    monkeypatch.setattr(mod, "_ops", OracleOps)
+    monkeypatch.setattr(mod, "_lib", types.SimpleNamespace(load=lambda: None, SIM=mod._lib.SIM))
+    deepocsort_edge_replay(lambda **kw: mod.DeepOCSort(None, 0, False, False, **kw), lambda **kw: DeepOCSortOracle(**kw))
