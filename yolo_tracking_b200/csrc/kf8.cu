@@ -106,21 +106,34 @@ __device__ void k8_update(double* x, double* P, const double* z, const double* r
 
 // KalmanBoxTracker.predict's filter part (deep_ocsort.py:263-266 + deepocsort_kf.py:340-381): Q from the state's w, h
 // BEFORE the motion (new_kf_process_noise :76-80), or Q = I (the filter's default, used inside unfreeze).
-__global__ void __launch_bounds__(K8_TPB) kf8_predict_kernel(int n, double* mean, double* cov, int unit_q) {
+// 64 tracks per CTA, 8 lanes per track: lane r owns row r of P (one thread per track was latency-bound at 18 % of the
+// warp slots: 106 registers, 64-thread CTAs).
+__global__ void __launch_bounds__(K8_TPB * 8) kf8_predict_kernel(int n, double* mean, double* cov, int unit_q) {
     __shared__ double sm[K8_TPB * K8_STRIDE];
     const int base = blockIdx.x * K8_TPB, cnt = min(K8_TPB, n - base);
+    const int t = threadIdx.x >> 3, r = threadIdx.x & 7;
     k8_in(sm, mean, cov, base, cnt);
-    if ((int)threadIdx.x < cnt) {
-        double* x = sm + threadIdx.x * K8_STRIDE;
-        double q[8];
-        if (unit_q) {
-            for (int i = 0; i < 8; ++i) q[i] = 1.0;
-        } else {
-            const double pw = xmul(1.0 / 20, x[2]), ph = xmul(1.0 / 20, x[3]), vw = xmul(1.0 / 160, x[2]), vh = xmul(1.0 / 160, x[3]);
-            q[0] = q[2] = xmul(pw, pw); q[1] = q[3] = xmul(ph, ph);
-            q[4] = q[6] = xmul(vw, vw); q[5] = q[7] = xmul(vh, vh);
-        }
-        k8_predict(x, x + 8, q);
+    double row[8], mr = 0.0;
+    if (t < cnt) {
+        const double* x = sm + t * K8_STRIDE;
+        const double* P = x + 8;
+        const double ref = x[2 + (r & 1)];                                  // w for the x / w axes, h for y / h
+        const double sd = xmul(r < 4 ? 1.0 / 20 : 1.0 / 160, ref);
+        const double q = unit_q ? 1.0 : xmul(sd, sd);
+        mr = r < 4 ? xadd(x[r], x[r + 4]) : x[r];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) row[j] = r < 4 ? xadd(P[r * 8 + j], P[(r + 4) * 8 + j]) : P[r * 8 + j];      // F P
+#pragma unroll
+        for (int j = 0; j < 4; ++j) row[j] = xadd(row[j], row[j + 4]);                                            // (F P) F^T
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (j == r) row[j] = xadd(row[j], q);
+    }
+    __syncthreads();
+    if (t < cnt) {
+        double* x = sm + t * K8_STRIDE;
+        x[r] = mr;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[8 + r * 8 + c] = row[c];
     }
     k8_out(sm, mean, cov, base, cnt);
 }
@@ -331,7 +344,7 @@ using namespace b200;
 extern "C" int b200track_kf8_predict(int32_t n, double* mean, double* cov, int32_t unit_q, void* st) {
     if (n < 0 || !mean || !cov) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
     if (n == 0) return 0;
-    kf8_predict_kernel<<<(n + K8_TPB - 1) / K8_TPB, K8_TPB, 0, (cudaStream_t)st>>>(n, mean, cov, unit_q);
+    kf8_predict_kernel<<<(n + K8_TPB - 1) / K8_TPB, K8_TPB * 8, 0, (cudaStream_t)st>>>(n, mean, cov, unit_q);
     LAUNCH_CHECK();
     return 0;
 }
