@@ -462,7 +462,7 @@ def gen_deepocsort():
         for f in range(sc["n_frames"]):
             trk.cmc.frame = f
             keep = dets[f, :nd[f], 4] > cfg["det_thresh"]
-            if keep.any():
+            if keep.any() and not cfg.get("embedding_off"):
                 rh.FakeReID.queue.append(embs[f, :nd[f]][keep])
             o = trk.update(dets[f, :nd[f]], img)
             outs.append(o)
@@ -476,7 +476,7 @@ def gen_deepocsort():
                 heavy.append(f)
         assert not rh.FakeReID.queue
         ts = trk.trackers
-        final_emb = np.stack([np.asarray(t.emb, dtype=np.float64) for t in ts]) if ts else np.zeros((0, sc["emb_dim"]))
+        final_emb = np.stack([np.asarray(t.emb, dtype=np.float64).reshape(-1) for t in ts]) if ts else np.zeros((0, sc["emb_dim"]))
         out_flat, out_offs = _ragged(outs, 8)
         int_flat, int_offs = _ragged(ints, 7)
         _save(name, ndets=nd, dets_sum=np.array([dets.sum(), float(sum(np.abs(f).sum() for f in feats))]), out=out_flat,

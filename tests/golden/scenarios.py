@@ -125,6 +125,14 @@ DEEPOCSORT_SCENARIOS = {
     # a moving camera: apply_affine_correction (deep_ocsort.py:226-244, deepocsort_kf.py:387-405) on live and frozen state
     "deepocsort_cam": dict(stream=912, n_objects=14, n_frames=120, emb_dim=64, kw=dict(miss_prob=0.15, fp_rate=1.0, occlusion=True),
                            camera=True, params={}),
+    # appearance switched off (dets_embs = ones, deep_ocsort.py:386-387), DIoU, output after two hits
+    "deepocsort_noemb": dict(stream=913, n_objects=18, n_frames=100, emb_dim=16, kw=dict(miss_prob=0.1, fp_rate=2.0, occlusion=True),
+                             params=dict(embedding_off=True, asso_func="diou", min_hits=2)),
+    # CIoU, the yaml's appearance weight (never forwarded by the reference's factory), another adaptive-weight floor, a
+    # moving camera.  (The centroid similarity cannot be pinned this way: the reference's OCR round calls it without the
+    # image size, deep_ocsort.py:463, and raises TypeError as soon as a detection and a track are left over.)
+    "deepocsort_ciou": dict(stream=914, n_objects=12, n_frames=100, emb_dim=32, kw=dict(miss_prob=0.1, fp_rate=1.0, occlusion=True),
+                            camera=True, params=dict(asso_func="ciou", w_association_emb=0.75, aw_param=0.4)),
 }
 
 

@@ -91,7 +91,7 @@ def test_ocm_cost_and_dot_matrix_match_oracle():
     assert _ops.dot_matrix(a[:0], b).shape == (0, T)
 
 
-@pytest.mark.parametrize("name", ["deepocsort_c4", "deepocsort_churn", "deepocsort_cam"])
+@pytest.mark.parametrize("name", ["deepocsort_c4", "deepocsort_churn", "deepocsort_cam", "deepocsort_noemb", "deepocsort_ciou"])
 def test_deepocsort_replays_reference_golden(name):
     from yolo_tracking_b200 import DeepOCSORT
     sc, cfg, dets, nd, feats, g = deepocsort_scenario(name)

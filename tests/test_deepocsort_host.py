@@ -11,7 +11,7 @@ import pytest
 from _util import OracleOps, assert_close, check_deepocsort_frame, deepocsort_scenario, heavy_offsets
 
 
-@pytest.mark.parametrize("name", ["deepocsort_c4", "deepocsort_churn", "deepocsort_cam"])
+@pytest.mark.parametrize("name", ["deepocsort_c4", "deepocsort_churn", "deepocsort_cam", "deepocsort_noemb", "deepocsort_ciou"])
 def test_deepocsort_host_logic_replays_reference(name, monkeypatch):
     from yolo_tracking_b200.trackers import deepocsort as mod
     monkeypatch.setattr(mod, "_ops", OracleOps)

@@ -251,7 +251,7 @@ def test_camera_warp_and_adaptive_weight_match_reference():
 
 
 # ----------------------------------------------------------------------------- DeepOCSORT
-@pytest.mark.parametrize("name", ["deepocsort_c4", "deepocsort_churn", "deepocsort_cam"])
+@pytest.mark.parametrize("name", ["deepocsort_c4", "deepocsort_churn", "deepocsort_cam", "deepocsort_noemb", "deepocsort_ciou"])
 def test_deepocsort_oracle_replays_reference(name):
     """ids, hit / age counters, observed / frozen flags exact; 8-d filter state, velocities, last observations and boxes to
     1e-9 against the live reference, through occlusions (the quirky unfreeze), OCR and a moving camera."""
