@@ -56,6 +56,19 @@ _ops.aw_max_metric(rng.random((2, 33, 47)), 0.75)
 gal = rng.standard_normal((2, 6, 100, 128)).astype(np.float32)
 _ops.gallery_cost(gal, rng.integers(0, 101, (2, 6)), gal[:, :, 3] + 0.1 * rng.standard_normal((2, 6, 128)).astype(np.float32), 0.2)
 _ops.nn_cosine_distance([gal[0, 0, :5], gal[0, 1, :9]], gal[0, :, 3])
+# DeepOCSORT operators (csrc/kf8.cu): a track count that is not a multiple of the 32 / 64 tracks a CTA stages
+x8 = np.concatenate([rng.uniform(100, 900, (77, 2)), rng.uniform(30, 200, (77, 2)), rng.normal(0, 2, (77, 4))], axis=1)
+P8 = np.stack([np.diag(rng.uniform(1, 30, 8)) for _ in range(77)])
+x8, P8 = _ops.kf8_predict(x8, P8)
+x8, P8 = _ops.kf8_predict(x8, P8, unit_q=True)
+x8, P8 = _ops.kf8_update(x8, P8, x8[:, :4] + 1.0, x8[:, 2:4])
+x8, P8 = _ops.kf8_update(x8, P8, x8[:, :4] + 1.0)
+_ops.kf8_oru(x8, P8, x8[:, :4], x8[:, :4] + 5.0, rng.integers(1, 31, 77))
+d5 = np.concatenate([a[:23] + 3.0, rng.uniform(0.1, 1, (23, 1))], axis=1)
+p5 = np.concatenate([a, rng.uniform(-1, 1, (50, 1))], axis=1)
+_ops.ocm_cost(rng.random((23, 50)), d5, rng.normal(0, 1, (50, 2)), p5, 0.2, rng.random((23, 50)))
+_ops.ocm_cost(rng.random((23, 50)))
+_ops.dot_matrix(rng.standard_normal((23, 96)), rng.standard_normal((50, 96)))
 # crowded scene: the pair list and the edge cache of the ByteTrack step overflow (bitmask graph, union-find solver)
 dets, nd, _ = make_batch(7, 2, 40, 8, dmax=64, fp_rate=0.5)
 ctr, half = 0.5 * (dets[..., :2] + dets[..., 2:4]), 0.5 * (dets[..., 2:4] - dets[..., :2])
