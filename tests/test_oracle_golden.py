@@ -265,3 +265,16 @@ def test_deepocsort_oracle_replays_reference(name):
         check_deepocsort_frame(name, f, out, trk.snapshot(), g, heavy)
     assert_close(trk.snapshot()["emb"], g["final_emb"], rel=1e-6, what="embeddings")
     assert trk.stats["oru"] > 50 and trk.stats["lap_frames"] > 20 and trk.stats["ocr_frames"] >= 1
+
+
+def test_camera_warp_leaves_two_independent_4x4_blocks():
+    """Structure the fused frame steps can rely on when they take a camera warp (DESIGN.md performance plan): on the live
+    reference's moving-camera runs the covariance couples x with y (and w with h) but the (x, y, vx, vy) and (w, h, vw, vh)
+    groups stay EXACTLY uncorrelated - kron(I4, R) maps each group to itself, F, H and the diagonal Q, R never mix them.
+    So a warped 8-d filter is two 4x4 symmetric blocks (20 numbers), not a dense 8x8 (36)."""
+    A, B = [0, 1, 4, 5], [2, 3, 6, 7]
+    for name, key in (("botsort_cam", "cov"), ("deepocsort_cam", "P"), ("deepocsort_ciou", "P")):
+        cov = load_golden(name)[key].reshape(-1, 8, 8)
+        assert len(cov) > 100
+        assert np.abs(cov[:, A][:, :, B]).max() == 0.0 and np.abs(cov[:, B][:, :, A]).max() == 0.0, name
+        assert np.abs(cov[:, 0, 1]).max() > 0.1, name                  # the warp did break the 2x2 sparsity
