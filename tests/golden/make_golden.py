@@ -395,6 +395,36 @@ def gen_mot():
     _save("mot17_mini", **out)
 
 
+def gen_mot_deepocsort():
+    """The same three MOT17-mini detection streams (rows taken from tests/golden/mot17_mini.npz) through the reference's
+    DeepOCSORT with seeded stand-in embeddings (scenarios.mot_feats): integer MOT rows per sequence."""
+    rh.install()
+    from scenarios import DEEPOCSORT_YAML, mot_feats
+    from yolo_tracking_b200 import mot_io
+    from yolo_tracking_b200.replay import dense_frames
+    from boxmot.trackers.deepocsort.deep_ocsort import DeepOCSort
+    g = np.load(os.path.join(HERE, "mot17_mini.npz"))
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    out = {}
+    for si, name in enumerate(MOT_SEQS):
+        frames, dets = mot_io.split_det_rows(g[name + "_det"])
+        seq = dense_frames(frames, dets, int(g[name + "_len"]))
+        trk = DeepOCSort(None, "cpu", False, False, **DEEPOCSORT_YAML)
+        trk.cmc = rh.IdentityCMC()
+        rows = []
+        for f, d in enumerate(seq):
+            keep = d[:, 4] > DEEPOCSORT_YAML["det_thresh"]
+            if keep.any():
+                rh.FakeReID.queue.append(mot_feats(si, f, int(keep.sum())))
+            o = trk.update(d, img)
+            if o.size:
+                rows.append(mot_io.mot_rows(o, f))
+        assert not rh.FakeReID.queue
+        out[name] = mot_io.as_int_rows(np.concatenate(rows, axis=0))
+        print(name, "deepocsort", len(out[name]), "rows")
+    _save("mot17_mini_deepocsort", **out)
+
+
 # ----------------------------------------------------------------------------- StrongSORT
 def gen_strongsort():
     rh.install()
@@ -484,7 +514,7 @@ def gen_deepocsort():
               last=_ragged(lasts, 5)[0], P=_ragged(Ps, 64)[0], heavy_frames=np.array(heavy, dtype=np.int32), final_emb=final_emb)
 
 
-GENERATORS = {"deepocsort": gen_deepocsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
+GENERATORS = {"deepocsort": gen_deepocsort, "mot_deepocsort": gen_mot_deepocsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
               "mot": gen_mot, "strongsort": gen_strongsort, "aux": gen_aux}
 
 if __name__ == "__main__":

@@ -148,3 +148,9 @@ def deepocsort_inputs(sc, det_thresh):
         raw = embs[f, :nd[f]][keep].astype(np.float32)
         feats.append(raw / np.linalg.norm(raw) if len(raw) else np.zeros((0, sc["emb_dim"]), dtype=np.float32))
     return dets, nd, embs, feats
+
+
+def mot_feats(seq_index, frame, n, dim=32):
+    """Seeded stand-in embeddings for the detections of frame `frame` of MOT17-mini sequence `seq_index` (raw, before the
+    seam's whole-matrix normalisation)."""
+    return np.random.default_rng(50000 + 1000 * seq_index + frame).normal(0.0, 1.0, (n, dim)).astype(np.float32)

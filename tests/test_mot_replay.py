@@ -83,3 +83,40 @@ def test_replay_cli_writes_result_files(tmp_path):
     for name in SEQS[1:]:
         got = np.loadtxt(tmp_path / "out" / (name + ".txt"), dtype=np.int64, ndmin=2)
         assert np.array_equal(got, g[f"{name}_bytetrack"]), name
+
+
+def _deepocsort_replay(make, update):
+    import sys
+    from _util import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    from scenarios import DEEPOCSORT_YAML, mot_feats
+    g, ref = load_golden("mot17_mini"), load_golden("mot17_mini_deepocsort")
+    for si, (name, seq) in enumerate(zip(SEQS, _sequences(g))):
+        trk = make(**DEEPOCSORT_YAML)
+        rows = []
+        for f, d in enumerate(seq):
+            raw = mot_feats(si, f, int((d[:, 4] > DEEPOCSORT_YAML["det_thresh"]).sum()))
+            feats = raw / np.linalg.norm(raw) if len(raw) else raw
+            o = update(trk, d, feats)
+            if o.size:
+                rows.append(mot_io.mot_rows(o, f))
+        assert np.array_equal(mot_io.as_int_rows(np.concatenate(rows)), ref[name]), name
+
+
+def test_deepocsort_oracle_replay_matches_reference_files():
+    """Real MOT17 public detections (duplicate boxes, confidences down to 0.05) with seeded stand-in embeddings through the
+    DeepOCSORT oracle: the result rows equal the live reference's (tests/golden/mot17_mini_deepocsort.npz)."""
+    from oracle.deepocsort import DeepOCSortOracle
+    _deepocsort_replay(lambda **kw: DeepOCSortOracle(**kw), lambda t, d, f: t.update(d, f, (1080, 1920)))
+
+
+def test_deepocsort_host_logic_replay_matches_reference_files(monkeypatch):
+    """The drop-in's host list logic on the same streams, the operators patched with the oracle's arithmetic (test-only,
+    tests/_util.py::OracleOps)."""
+    import types
+    from _util import OracleOps
+    from yolo_tracking_b200.trackers import deepocsort as mod
+    monkeypatch.setattr(mod, "_ops", OracleOps)
+    monkeypatch.setattr(mod, "_lib", types.SimpleNamespace(load=lambda: None, SIM=mod._lib.SIM))
+    _deepocsort_replay(lambda **kw: mod.DeepOCSort(None, 0, False, False, **kw), lambda t, d, f: t.update(d, (1080, 1920), feats=f))
