@@ -120,3 +120,24 @@ def test_deepocsort_host_logic_replay_matches_reference_files(monkeypatch):
     monkeypatch.setattr(mod, "_ops", OracleOps)
     monkeypatch.setattr(mod, "_lib", types.SimpleNamespace(load=lambda: None, SIM=mod._lib.SIM))
     _deepocsort_replay(lambda **kw: mod.DeepOCSort(None, 0, False, False, **kw), lambda t, d, f: t.update(d, (1080, 1920), feats=f))
+
+
+def test_strongsort_oracle_replay_matches_reference_files():
+    """The same streams through the StrongSORT oracle (every detection row gets a stand-in embedding; scipy's tie
+    behaviour on the clipped cost matrix decides ids on real data too): rows equal the live reference's."""
+    import sys
+    from _util import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    from oracle.strongsort import StrongSORTOracle
+    from scenarios import STRONGSORT_YAML, mot_feats
+    g, ref = load_golden("mot17_mini"), load_golden("mot17_mini_strongsort")
+    for si, (name, seq) in enumerate(zip(SEQS, _sequences(g))):
+        trk = StrongSORTOracle(**STRONGSORT_YAML)
+        rows = []
+        for f, d in enumerate(seq):
+            raw = mot_feats(si, f, len(d))
+            o = trk.update(d, raw / np.linalg.norm(raw) if len(raw) else raw)
+            if o.size:
+                rows.append(mot_io.mot_rows(o, f))
+        assert np.array_equal(mot_io.as_int_rows(np.concatenate(rows)), ref[name]), name
