@@ -425,6 +425,37 @@ def gen_mot_deepocsort():
     _save("mot17_mini_deepocsort", **out)
 
 
+def gen_mot_botsort():
+    """The three MOT17-mini detection streams through the reference's BoT-SORT (botsort.yaml, identity camera, seeded
+    stand-in embeddings for the detections above track_high_thresh): integer MOT rows per sequence."""
+    rh.install()
+    from scenarios import mot_feats
+    from yolo_tracking_b200 import mot_io
+    from yolo_tracking_b200.replay import dense_frames
+    from boxmot.trackers.botsort.bot_sort import BoTSORT
+    g = np.load(os.path.join(HERE, "mot17_mini.npz"))
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    out = {}
+    for si, name in enumerate(MOT_SEQS):
+        frames, dets = mot_io.split_det_rows(g[name + "_det"])
+        seq = dense_frames(frames, dets, int(g[name + "_len"]))
+        rh.reset_counters()
+        trk = BoTSORT(None, "cpu", False, **BOTSORT_YAML)
+        trk.cmc = rh.IdentityCMC()
+        rows = []
+        for f, d in enumerate(seq):
+            hi = np.nonzero(d[:, 4] > BOTSORT_YAML["track_high_thresh"])[0]
+            if len(hi):
+                rh.FakeReID.queue.append(mot_feats(si, f, len(d))[hi])
+            o = trk.update(d, img)
+            if o.size:
+                rows.append(mot_io.mot_rows(o, f))
+        assert not rh.FakeReID.queue
+        out[name] = mot_io.as_int_rows(np.concatenate(rows, axis=0))
+        print(name, "botsort", len(out[name]), "rows")
+    _save("mot17_mini_botsort", **out)
+
+
 def gen_mot_strongsort():
     """The three MOT17-mini detection streams through the reference's StrongSORT (identity camera, seeded stand-in
     embeddings for every detection row): integer MOT rows per sequence."""
@@ -543,7 +574,7 @@ def gen_deepocsort():
               last=_ragged(lasts, 5)[0], P=_ragged(Ps, 64)[0], heavy_frames=np.array(heavy, dtype=np.int32), final_emb=final_emb)
 
 
-GENERATORS = {"deepocsort": gen_deepocsort, "mot_deepocsort": gen_mot_deepocsort, "mot_strongsort": gen_mot_strongsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
+GENERATORS = {"deepocsort": gen_deepocsort, "mot_deepocsort": gen_mot_deepocsort, "mot_strongsort": gen_mot_strongsort, "mot_botsort": gen_mot_botsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
               "mot": gen_mot, "strongsort": gen_strongsort, "aux": gen_aux}
 
 if __name__ == "__main__":

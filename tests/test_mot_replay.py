@@ -141,3 +141,28 @@ def test_strongsort_oracle_replay_matches_reference_files():
             if o.size:
                 rows.append(mot_io.mot_rows(o, f))
         assert np.array_equal(mot_io.as_int_rows(np.concatenate(rows)), ref[name]), name
+
+
+def test_botsort_oracle_replay_matches_reference_files():
+    """The same streams through the BoT-SORT oracle (botsort.yaml; stand-in embeddings for the detections above
+    track_high_thresh, normalised like the seam): rows equal the live reference's."""
+    import sys
+    from _util import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    from oracle.botsort import BoTSORTOracle
+    from scenarios import BOTSORT_YAML, mot_feats
+    g, ref = load_golden("mot17_mini"), load_golden("mot17_mini_botsort")
+    for si, (name, seq) in enumerate(zip(SEQS, _sequences(g))):
+        trk = BoTSORTOracle(**BOTSORT_YAML)
+        rows = []
+        for f, d in enumerate(seq):
+            raw = mot_feats(si, f, len(d))
+            hi = np.nonzero(d[:, 4] > BOTSORT_YAML["track_high_thresh"])[0]
+            feats = np.zeros_like(raw)
+            if len(hi):
+                feats[hi] = raw[hi] / np.linalg.norm(raw[hi])
+            o = trk.update(d, feats)
+            if o.size:
+                rows.append(mot_io.mot_rows(o, f))
+        assert np.array_equal(mot_io.as_int_rows(np.concatenate(rows)), ref[name]), name
