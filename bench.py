@@ -6,7 +6,11 @@ config 5: 4096 streams x 200 objects per GPU, sharded by stream, weak scaling).
 
 A "step" is one frame over every stream of the rank.  `value` is measured with the
 detections of all frames already resident in HBM; `e2e` drives the same frames through the
-host-buffer C-ABI (pinned host memory -> H2D -> step -> D2H) with a 3-deep pipeline.
+packed host interface of the C-ABI (b200track_submit_packed: one pinned input block -> ONE H2D
+copy -> step -> ONE D2H copy of the compact result block) with a 3-deep pipeline.  Both legs
+start from the same steady state: PREROLL untimed frames (track_buffer ages out lost tracks
+from frame 31 on) run before the --warmup frames.  Detections are fp32-representable (what a
+detector emits), so the fp32 packed path, the fp64 padded path and the CPU arm see identical values.
 `--impl reference` times the CPU oracle port of the reference on the host cores.
 One JSON line on stdout (rank 0).
 """
@@ -85,11 +89,15 @@ def select_workload(name):
     MAX_DETS, MAX_TRACKS, PARAMS = W["max_dets"], W["max_tracks"], W["params"]
 
 
+PREROLL = 40      # untimed frames before the warm-up: the timed window then holds lost, re-found and aged-out tracks
+
+
 def _stream_inputs(stream, n_frames):
     """dets[F, MAX_DETS, 6], ndets[F], seam features[F, MAX_DETS, emb] or None for one stream of the workload."""
     from yolo_tracking_b200.synth import make_stream
     kw = dict(occlusion=True) if W.get("occlusion") else {}
     d, n, e = make_stream(CONFIG_ID, stream, N_OBJECTS, n_frames, dmax=MAX_DETS, emb_dim=W["emb"], **kw)
+    d = d.astype(np.float32).astype(np.float64)          # detector output precision; every consumer sees these values
     if e is not None:
         # the ReID seam (reid_multibackend.py:304-311): first-round rows / Frobenius norm of their matrix
         high = PARAMS["track_high_thresh"]
@@ -126,11 +134,11 @@ def _gen_worker(args):
 
 
 def generate(n_streams, stream0, n_frames, workers):
-    """dets[F, S, MAX_DETS, 6] f64, ndets[F, S] i32 (and feats[F, S, MAX_DETS, emb] f32) in fork-shared anonymous memory."""
-    nbytes = n_frames * n_streams * MAX_DETS * 6 * 8
+    """dets[F, S, MAX_DETS, 6] f32, ndets[F, S] i32 (and feats[F, S, MAX_DETS, emb] f32) in fork-shared anonymous memory."""
+    nbytes = n_frames * n_streams * MAX_DETS * 6 * 4
     buf = mmap.mmap(-1, nbytes)
     buf2 = mmap.mmap(-1, n_frames * n_streams * 4)
-    dets = np.frombuffer(buf, dtype=np.float64).reshape(n_frames, n_streams, MAX_DETS, 6)
+    dets = np.frombuffer(buf, dtype=np.float32).reshape(n_frames, n_streams, MAX_DETS, 6)
     nd = np.frombuffer(buf2, dtype=np.int32).reshape(n_frames, n_streams)
     _shared["dets"], _shared["nd"] = dets, nd
     _shared.pop("feats", None)
@@ -171,7 +179,7 @@ def _oracle_worker(args):
             d, n, e = data[k]
             second = W["img_hw"] if W["kind"] == "ocsort" else (e[f, :n[f]] if e is not None else None)
             t.update(d[f, :n[f]], second)
-    for f in range(warm):
+    for f in range(warm):                         # pre-roll + warm-up frames, untimed
         step(f)
     base = sum(t.track_updates for t in trks)
     t0 = time.perf_counter()
@@ -185,7 +193,7 @@ def cpu_oracle_run(n_workers, streams_per_worker, steps, warmup):
     """The oracle port (oracle/<tracker>.py) on `n_workers` processes; returns
     (track_updates, wall_seconds = slowest worker)."""
     os.environ.setdefault("OMP_NUM_THREADS", "1")
-    tasks = [([100000 + w * streams_per_worker + k for k in range(streams_per_worker)], steps + warmup, warmup)
+    tasks = [([100000 + w * streams_per_worker + k for k in range(streams_per_worker)], steps + warmup + PREROLL, warmup + PREROLL)
              for w in range(n_workers)]
     if n_workers == 1:
         res = [_oracle_worker(tasks[0])]
@@ -254,7 +262,7 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": W["label"], "streams_per_gpu": args.streams, "sample_streams": cores * spw, "objects": N_OBJECTS},
         "cpu_baseline": {"value": val, "unit": "track-updates/s", "cores": cores, "kind": "port",
-                         "sample": f"{cores * spw} streams x {args.steps} frames after {args.warmup} warm-up frames, "
+                         "sample": f"{cores * spw} streams x {args.steps} frames after {PREROLL} pre-roll + {args.warmup} warm-up frames, "
                                    f"oracle/{W['kind']}.py (numpy port of the reference; /root/reference is Python and "
                                    f"cannot travel), one process per core"},
         "e2e": {"value": val, "unit": "track-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -264,21 +272,22 @@ def run_reference(args, rank, world):
 
 def run_b200(args, rank, world, local_rank):
     S = args.streams
-    F = args.steps + args.warmup
+    W0 = PREROLL + args.warmup                   # first timed frame
+    F = W0 + args.steps
     cores = host_cores()
     gen_workers = max(1, cores // max(1, world))
     t_gen = time.time()
     from yolo_tracking_b200.shard import shard_bounds
     stream0, stream1 = shard_bounds(S * world, rank, world)          # weak scaling: S streams per GPU, block-sharded
     assert stream1 - stream0 == S
-    dets_h, nd_h, feats_h = generate(S, stream0, F, gen_workers)
+    dets_h, nd_h, feats_h = generate(S, stream0, F, gen_workers)     # fp32 [F, S, D, 6]
     t_gen = time.time() - t_gen
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         tu, dt = cpu_oracle_run(cores, 1, 40, 10)
         cpu_base = {"value": tu / dt, "unit": "track-updates/s", "cores": cores, "kind": "port",
-                    "sample": f"{cores} streams x 40 frames after 10 warm-up frames of the same workload, "
+                    "sample": f"{cores} streams x 40 frames after {PREROLL} pre-roll + 10 warm-up frames of the same workload, "
                               f"oracle/{W['kind']}.py, one process per core"}
 
     import torch
@@ -289,27 +298,15 @@ def run_b200(args, rank, world, local_rank):
     from yolo_tracking_b200.batch import BatchedTracker
 
     dev = torch.device("cuda", local_rank)
-    # page-locked copies of the generated frames: source of the per-step H2D copies of the e2e leg
-    pin_all = torch.empty(dets_h.shape, dtype=torch.float64, pin_memory=True)
-    pin_all.numpy()[...] = dets_h
-    pin_nd_all = torch.empty(nd_h.shape, dtype=torch.int32, pin_memory=True)
-    pin_nd_all.numpy()[...] = nd_h
-    dets_h, nd_h = pin_all.numpy(), pin_nd_all.numpy()
-    d_dets = pin_all.to(dev)                            # all frames resident in HBM for the device leg
-    d_nd = pin_nd_all.to(dev)
-    d_feats = None
-    if feats_h is not None:
-        pin_feats = torch.empty(feats_h.shape, dtype=torch.float32, pin_memory=True)
-        pin_feats.numpy()[...] = feats_h
-        feats_h = pin_feats.numpy()
-        d_feats = pin_feats.to(dev)
+    # device leg: all frames resident in HBM as the padded fp64 [S, max_dets, 6] blocks of b200track_step
+    d_dets = torch.from_numpy(dets_h).to(dev).to(torch.float64)
+    d_nd = torch.from_numpy(nd_h).to(dev)
+    d_feats = torch.from_numpy(feats_h).to(dev) if feats_h is not None else None
     hw = W["img_hw"]
 
     def feats_dev(f):
         return d_feats[f] if d_feats is not None else None
 
-    def feats_host(f):
-        return feats_h[f] if feats_h is not None else None
     d_out = torch.empty((S, MAX_TRACKS, 8), dtype=torch.float64, device=dev)
     d_nout = torch.empty((S,), dtype=torch.int32, device=dev)
     trk = BatchedTracker(W["kind"], S, max_tracks=MAX_TRACKS, max_dets=MAX_DETS, device=local_rank, feat_dim=W["emb"], **PARAMS)
@@ -321,13 +318,15 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def preroll(upto):
+        with torch.cuda.stream(stream):
+            for f in range(upto):
+                trk.step_device(d_dets[f], d_nd[f], d_out, d_nout, d_feats=feats_dev(f), img_hw=hw, stream=stream.cuda_stream)
+
     # ---------------- device-resident leg -------------------------------------------------
-    with torch.cuda.stream(stream):
-        for f in range(args.warmup):
-            trk.step_device(d_dets[f], d_nd[f], d_out, d_nout, d_feats=feats_dev(f), img_hw=hw, stream=stream.cuda_stream)
+    preroll(W0)                                  # PREROLL + warm-up frames, untimed
     barrier()
     tu0, l0 = trk.track_updates(), trk.launches()
-    rows = 0
     sampler = ClockSampler(local_rank)
     sampler.start()
     # L2 hygiene: config 5's per-step working set is several times the 126 MB L2 and every step reads new
@@ -340,7 +339,7 @@ def run_b200(args, rank, world, local_rank):
     barrier()
     with torch.cuda.stream(stream):
         for k in range(args.steps):
-            f = args.warmup + k
+            f = W0 + k
             if flush is not None:
                 flush.sum()                       # read 256 MB: L2 ends up holding clean lines of another buffer
             ev0[k].record(stream)
@@ -353,40 +352,62 @@ def run_b200(args, rank, world, local_rank):
     total_ms = ev0[0].elapsed_time(ev1[-1]) if flush is None else float(step_ms.sum())
     tu_dev = trk.track_updates() - tu0
     launches = trk.launches() - l0
-    dets_timed = int(nd_h[args.warmup:].sum())
-    # output rows of the timed region are re-counted in the e2e leg (same frames, same results)
+    dets_timed = int(nd_h[W0:].sum())
 
-    # ---------------- end-to-end leg: pinned host buffers through the C-ABI ----------------
+    # ---------------- end-to-end leg: pinned host blocks through the packed C-ABI ----------------
+    # Every timed frame is one pinned input block (offsets + fp32 detection rows [+ fp32 embeddings]) prepared before the
+    # clock starts - the form a detector hands frames over in; per step: ONE H2D copy, the step, ONE D2H copy of the result
+    # block (header, per-stream row counts, compact rows), and the host reads the row counts of the finished frame.
     trk.reset()
+    preroll(PREROLL)
+    torch.cuda.synchronize(dev)
     nslot = trk.host_slots
-    pin_out = [torch.empty((S, MAX_TRACKS, 8), dtype=torch.float64).pin_memory() for _ in range(nslot)]
-    pin_nout = [torch.empty((S,), dtype=torch.int32).pin_memory() for _ in range(nslot)]
+    n_e2e = args.warmup + args.steps
+    rows_of, flags_of, in_blocks = [], [], []
+    max_rows = int(nd_h[PREROLL:].sum(axis=1).max())
+    for k in range(n_e2e):
+        f = PREROLL + k
+        blk, _ = trk.frame_buffers(max_rows=int(nd_h[f].sum()))
+        r, fl = trk.pack(blk, dets_h[f], ndets=nd_h[f], feats=None if feats_h is None else feats_h[f], dtype=np.float32)
+        in_blocks.append(blk); rows_of.append(r); flags_of.append(fl)
+    out_blocks = [trk.frame_buffers(max_rows=max_rows)[1] for _ in range(nslot)]
+    del dets_h
 
-    def submit(f, slot):
-        trk.submit(slot, dets_h[f], nd_h[f], pin_out[slot].numpy(), pin_nout[slot].numpy(), feats=feats_host(f), img_hw=hw)
+    def submit(k, slot):
+        trk.submit_packed(slot, in_blocks[k], out_blocks[slot], np.float32, flags_of[k], img_hw=hw)
 
-    for f in range(args.warmup):
-        submit(f, f % nslot)
-        trk.wait(f % nslot)
+    def collect(k, slot):
+        trk.wait_packed(slot)
+        v = trk.frame_views(None, out_blocks[slot], rows_of[k], np.float32)
+        return int(v["nout"].sum())               # device->host read of the step's result
+
+    for k in range(args.warmup):
+        submit(k, k % nslot)
+        collect(k, k % nslot)
     barrier()
     tu1 = trk.track_updates()
-    h2d = d2h = 0
+    h2d = d2h = rows = 0
+    sampler_e2e = ClockSampler(local_rank)
+    sampler_e2e.start()
     t0 = time.perf_counter()
     for k in range(args.steps):
         slot = k % nslot
         if k >= nslot:
-            trk.wait(slot)
-            rows += int(pin_nout[slot].numpy().sum())      # device->host read of the step's result
+            rows += collect(args.warmup + k - nslot, slot)
         submit(args.warmup + k, slot)
-        h2d += int(nd_h[args.warmup + k].max()) * (48 + 4 * W["emb"]) * S + 4 * S
-        d2h += min(int(nd_h[args.warmup + k].max()), MAX_TRACKS) * 64 * S + 4 * S
     for k in range(max(0, args.steps - nslot), args.steps):
-        trk.wait(k % nslot)
-        rows += int(pin_nout[k % nslot].numpy().sum())
+        rows += collect(args.warmup + k, k % nslot)
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    sampler_e2e.stop_flag = True
+    sampler_e2e.join()
+    for k in range(args.warmup, n_e2e):
+        L = trk.frame_layout(rows_of[k], np.float32)
+        h2d += int(L.in_bytes); d2h += int(L.out_bytes)
+    row_bytes = int(trk.frame_layout(0, np.float32).row_bytes)
     tu_e2e = trk.track_updates() - tu1
     trk.sync()
+    assert tu_e2e == tu_dev, "the two legs ran different work"
 
     # ---------------- optional final gather of the padded outputs (the only collective; not part of the step) ----
     gather_ms = None
@@ -416,15 +437,19 @@ def run_b200(args, rank, world, local_rank):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
+        # DRAM bytes per launch cannot be measured outside a profiler: the number comes from the ncu --set full capture of
+        # this same command committed under profiles/ (tools/summarize_profiles.py writes the file), null if none matches
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
                 tr = json.load(fh)[W["kernel"]]
             if tr["streams"] == S:
                 traffic = tr["dram_bytes_per_launch"]
+                traffic_src = tr.get("source", "profiles/traffic.json")
         except Exception:
             pass
-        # rank-0 kernel: algorithmic bytes per launch / mean launch duration (events on the launch stream)
+        # rank-0 kernel: algorithmic bytes per launch / mean launch duration (events on the launch stream); the device leg
+        # reads padded fp64 detection rows (48 B) and writes the reference's 64-byte result rows
         alg_bytes = (tu_dev * (W["b_slot"] + W["b_feat"]) + dets_timed * B_DET + rows * B_ROW) / args.steps     # rank-0 shard
         mean_ms = float(step_ms.mean())
         achieved = alg_bytes / (mean_ms * 1e-3) / 1e9
@@ -439,17 +464,23 @@ def run_b200(args, rank, world, local_rank):
                               "new detections" % (working_set / 1e6)) if flush is None else
                              ("per-step working set ~%.0f MB: a 256 MB buffer is read between steps (L2 flush), outside "
                               "the per-step event pairs; value = units / sum of step times" % (working_set / 1e6)),
+                       "preroll_frames": PREROLL, "detections": "fp32-representable values (detector precision)",
                        "data_gen_s": round(t_gen, 1)},
             "p50_step_ms": float(np.percentile(step_ms, 50)), "p99_step_ms": float(np.percentile(step_ms, 99)),
             "e2e": {"value": tu_e2e_all / (e2e_ms_max * 1e-3), "unit": "track-updates/s",
                     "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                     "ms_per_step": e2e_ms_max / args.steps, "pipeline_depth": nslot,
-                    "output_rows_per_step": rows_all / args.steps},
+                    "output_rows_per_step": rows_all / args.steps / world,
+                    "interface": "b200track_submit_packed / wait_packed: one pinned input block per frame (int32 offsets + fp32 "
+                                 "detection rows%s), one linear cudaMemcpyAsync per direction, compact %d-byte result rows; "
+                                 "the host reads the per-stream row counts of every finished frame"
+                                 % (" + fp32 embeddings" if W["emb"] else "", row_bytes),
+                    "clocks": sampler_e2e.summary()},
             "gpu_launches": int(launches_all),
             "gather": None if gather_ms is None else {"ms": gather_ms, "bytes_per_rank": S * MAX_TRACKS * 64 + 4 * S,
                                                        "what": "NCCL all_gather of out[S, max_tracks, 8] + nout[S] after the run (optional, outside the step)"},
             "roofline": {"bound": "hbm", "kernel": W["kernel"], "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650",
                          "alg_bytes_per_launch": alg_bytes, "mean_launch_ms": mean_ms,
                          "bytes_per_track_update": alg_bytes * args.steps / max(1, tu_dev)},

@@ -107,7 +107,46 @@ int b200track_host_slots(b200track_ctx* ctx);
 int b200track_submit_host(b200track_ctx* ctx, int32_t slot, const double* h_dets,
                           const int32_t* h_ndets, const float* h_feats, int32_t img_h,
                           int32_t img_w, double* h_out, int32_t* h_nout);
-int b200track_wait_host(b200track_ctx* ctx, int32_t slot);
+int b200track_wait_host(b200track_ctx* ctx, int32_t slot);   /* B200TRACK_ERR_CAPACITY if that step overflowed */
+
+/* ---- packed frames: the same step with the bytes a detector produces and a consumer needs --------------------------
+ * The padded interface above moves max_dets-row blocks and 64-byte result rows of which conf / cls (and, for OC-SORT,
+ * the box) are copies of the caller's own detection row det_ind (byte_tracker.py:270-279, ocsort.py:354-363).  Here a
+ * frame is ONE input block and ONE result block, so the host interface is one linear copy per direction:
+ *   input block  (b200track_layout.in_*):  int32 offsets[n_streams + 1] (stream s owns detection rows
+ *       [offsets[s], offsets[s + 1]) - the exclusive scan of the per-stream counts), double warps[n_streams][6]
+ *       (BoT-SORT contexts only; read when flags has B200TRACK_FRAME_HAS_WARPS: the 2x3 camera-motion warp per stream,
+ *       bot_sort.py:293-295), the detection rows [n_rows][6] (x1, y1, x2, y2, conf, cls) back to back as fp32
+ *       (B200TRACK_F32: what detectors emit; widened on the device, which is exact, so the result equals the padded
+ *       interface's on dets.astype(float64)) or fp64, and for BoT-SORT with_reid the embeddings [n_rows][feat_dim] fp32;
+ *   result block (b200track_layout.out_*): int32 header[4] ([0] = capacity bits of this step, 0 = fine),
+ *       int32 nout[n_streams], then compact rows: stream s owns rows [offsets[s], offsets[s] + nout[s]) (a result row
+ *       carries a distinct detection of its frame, so nout[s] <= its detection count), in the reference's row order:
+ *         ByteTrack b200track_row    40 B  x1, y1, x2, y2 (fp64), id, det_ind
+ *         BoT-SORT  b200track_row_bot 48 B  + cls (the voted class, bot_sort.py:50-67), conf as fp32
+ *         OC-SORT   b200track_row_oc   8 B  id, det_ind; det_ind bit 30 set = tracker created this frame (its box is
+ *                   convert_x_to_bbox(convert_bbox_to_z(det)), otherwise the detection's own box)
+ * b200track_frame_layout   offsets / sizes of both blocks for n_rows detection rows.
+ * b200track_step_packed    device blocks, asynchronous on `stream`.
+ * b200track_submit_packed / b200track_wait_packed   HOST blocks through the 3-deep copy / step / copy pipeline (slots are
+ *   shared with b200track_submit_host); wait returns B200TRACK_ERR_CAPACITY if that step overflowed. */
+typedef enum { B200TRACK_F32 = 0, B200TRACK_F64 = 1 } b200track_dtype;
+#define B200TRACK_FRAME_HAS_WARPS 1
+#define B200TRACK_ROW_OC_NEW (1 << 30)
+typedef struct { double x1, y1, x2, y2; int32_t id; int32_t det_ind; } b200track_row;
+typedef struct { double x1, y1, x2, y2; int32_t id; int32_t det_ind; float cls; float conf; } b200track_row_bot;
+typedef struct { int32_t id; int32_t det_ind; } b200track_row_oc;
+typedef struct {
+    uint64_t in_bytes, in_off_offsets, in_off_warps, in_off_dets, in_off_feats;
+    uint64_t out_bytes, out_off_nout, out_off_rows;
+    int32_t row_bytes, reserved;
+} b200track_layout;
+int b200track_frame_layout(b200track_ctx* ctx, int64_t n_rows, int32_t det_dtype, b200track_layout* out);
+int b200track_step_packed(b200track_ctx* ctx, const void* d_in, int64_t n_rows, int32_t det_dtype, int32_t flags,
+                          int32_t img_h, int32_t img_w, void* d_result, void* stream);
+int b200track_submit_packed(b200track_ctx* ctx, int32_t slot, const void* h_in, int32_t det_dtype, int32_t flags,
+                            int32_t img_h, int32_t img_w, void* h_result);
+int b200track_wait_packed(b200track_ctx* ctx, int32_t slot);
 /* Waits for all work of the context, then reports capacity overflows seen since the last call. */
 int b200track_sync(b200track_ctx* ctx);
 /* Sum over streams of the tracks that entered association so far (SURVEY.md 8(d) metric). */

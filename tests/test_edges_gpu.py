@@ -63,14 +63,20 @@ def test_capacity_overflow_is_reported_not_silent():
     trk = BatchedTracker("bytetrack", 1, max_tracks=cap, max_dets=cap, **BT)
     d = np.zeros((1, cap, 6))
     d[0] = boxes(cap)
-    trk.update_batch(d, np.array([cap + 5], dtype=np.int32))          # claims more detections than the buffer holds
+    # the step that overflowed reports it when its results are collected (b200track_wait_host), and b200track_sync repeats
+    # it for callers of the asynchronous device interface
+    with pytest.raises(_lib.B200TrackError) as e:
+        trk.update_batch(d, np.array([cap + 5], dtype=np.int32))      # claims more detections than the buffer holds
+    assert e.value.code == _lib.ERR_CAPACITY and "detections" in str(e.value)
     with pytest.raises(_lib.B200TrackError) as e:
         trk.sync()
     assert e.value.code == _lib.ERR_CAPACITY and "detections" in str(e.value)
     trk.reset()
-    for _ in range(3):                                                # 3 x 32 well separated boxes -> > 32 tracks (lost + new)
-        d[0] = boxes(cap)
-        trk.update_batch(d, np.array([cap], dtype=np.int32))
+    with pytest.raises(_lib.B200TrackError) as e:
+        for _ in range(3):                                            # 3 x 32 well separated boxes -> > 32 tracks (lost + new)
+            d[0] = boxes(cap)
+            trk.update_batch(d, np.array([cap], dtype=np.int32))
+    assert e.value.code == _lib.ERR_CAPACITY and "tracks" in str(e.value)
     with pytest.raises(_lib.B200TrackError) as e:
         trk.sync()
     assert e.value.code == _lib.ERR_CAPACITY and "tracks" in str(e.value)

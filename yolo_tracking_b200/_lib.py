@@ -35,6 +35,17 @@ class Config(C.Structure):
     ]
 
 
+class Layout(C.Structure):
+    _fields_ = [("in_bytes", C.c_uint64), ("in_off_offsets", C.c_uint64), ("in_off_warps", C.c_uint64),
+                ("in_off_dets", C.c_uint64), ("in_off_feats", C.c_uint64),
+                ("out_bytes", C.c_uint64), ("out_off_nout", C.c_uint64), ("out_off_rows", C.c_uint64),
+                ("row_bytes", C.c_int32), ("reserved", C.c_int32)]
+
+
+F32, F64 = 0, 1
+FRAME_HAS_WARPS = 1
+ROW_OC_NEW = 1 << 30
+
 _P = C.c_void_p
 _I = C.c_int32
 _D = C.c_double
@@ -51,6 +62,10 @@ SIGNATURES = {
     "b200track_host_slots": (C.c_int, [_P]),
     "b200track_submit_host": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _P, _P]),
     "b200track_wait_host": (C.c_int, [_P, _I]),
+    "b200track_frame_layout": (C.c_int, [_P, C.c_int64, _I, C.POINTER(Layout)]),
+    "b200track_step_packed": (C.c_int, [_P, _P, C.c_int64, _I, _I, _I, _I, _P, _P]),
+    "b200track_submit_packed": (C.c_int, [_P, _I, _P, _I, _I, _I, _I, _P]),
+    "b200track_wait_packed": (C.c_int, [_P, _I]),
     "b200track_sync": (C.c_int, [_P]),
     "b200track_track_updates": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
     "b200track_launch_count": (C.c_int, [_P, C.POINTER(C.c_uint64)]),

@@ -133,6 +133,144 @@ class BatchedTracker:
     def sync(self):
         _lib.check(self._lib.b200track_sync(self._ctx))
 
+    # ------------------------------------------------------------------ packed frames (one copy per direction)
+    _ROW_DTYPES = {
+        "bytetrack": np.dtype([("box", "<f8", 4), ("id", "<i4"), ("det_ind", "<i4")]),
+        "botsort": np.dtype([("box", "<f8", 4), ("id", "<i4"), ("det_ind", "<i4"), ("cls", "<f4"), ("conf", "<f4")]),
+        "ocsort": np.dtype([("id", "<i4"), ("det_ind", "<i4")]),
+    }
+
+    def frame_layout(self, n_rows: int, dtype=np.float32):
+        L = _lib.Layout()
+        _lib.check(self._lib.b200track_frame_layout(self._ctx, int(n_rows), _lib.F32 if np.dtype(dtype) == np.float32 else _lib.F64,
+                                                    C.byref(L)))
+        return L
+
+    def frame_buffers(self, max_rows: int | None = None, pinned: bool = True):
+        """(input block, result block) as uint8 arrays big enough for ``max_rows`` detection rows in either dtype."""
+        L = self.frame_layout(self.n_streams * self.max_dets if max_rows is None else max_rows, np.float64)
+        if pinned:
+            import torch
+            keep = (torch.empty(int(L.in_bytes), dtype=torch.uint8, pin_memory=True),
+                    torch.empty(int(L.out_bytes), dtype=torch.uint8, pin_memory=True))
+            bufs = tuple(t.numpy() for t in keep)
+            self._pinned = getattr(self, "_pinned", []) + [keep]          # the arrays borrow the tensors' memory
+            return bufs
+        return np.empty(int(L.in_bytes), dtype=np.uint8), np.empty(int(L.out_bytes), dtype=np.uint8)
+
+    def pack(self, block, dets, ndets=None, feats=None, warps=None, dtype=np.float32):
+        """Fill an input block.  ``dets``: a list of per-stream [n_s, 6] arrays, or a padded [S, D, 6] array with
+        ``ndets`` [S].  ``feats`` likewise ([n_s, F] per stream or [S, D, F]); ``warps`` [S, 2, 3].  Returns
+        ``(n_rows, flags)``; the views ``offsets``, ``dets`` of the block come from ``frame_views``."""
+        S = self.n_streams
+        dtype = np.dtype(dtype)
+        if ndets is None:
+            counts = np.fromiter((len(d) for d in dets), dtype=np.int64, count=S)
+        else:
+            counts = np.asarray(ndets, dtype=np.int64)
+        if counts.max(initial=0) > self.max_dets:
+            raise ValueError(f"{int(counts.max())} detections exceed max_dets={self.max_dets}")
+        off = np.zeros(S + 1, dtype=np.int32)
+        np.cumsum(counts, out=off[1:])
+        R = int(off[S])
+        v = self.frame_views(block, None, R, dtype)
+        v["offsets"][:] = off
+        if ndets is None:
+            if R:
+                np.concatenate([np.asarray(d).reshape(-1, 6) for d in dets], axis=0, out=v["dets"], dtype=dtype, casting="same_kind")
+            if feats is not None and v["feats"] is not None and R:
+                np.concatenate([np.asarray(f).reshape(-1, self.feat_dim) for f in feats], axis=0, out=v["feats"], dtype=np.float32, casting="same_kind")
+        else:
+            mask = np.arange(self.max_dets)[None, :] < counts[:, None]
+            v["dets"][:] = np.asarray(dets)[mask]
+            if feats is not None and v["feats"] is not None:
+                v["feats"][:] = np.asarray(feats)[mask]
+        flags = 0
+        if warps is not None:
+            if v["warps"] is None:
+                raise ValueError("only BoT-SORT contexts take camera-motion warps")
+            v["warps"][:] = np.asarray(warps, dtype=np.float64).reshape(S, 6)
+            flags |= _lib.FRAME_HAS_WARPS
+        return R, flags
+
+    def frame_views(self, in_block, out_block, n_rows: int, dtype=np.float32):
+        """Typed views into the blocks of a frame with ``n_rows`` detection rows."""
+        dtype = np.dtype(dtype)
+        L = self.frame_layout(n_rows, dtype)
+        S, R = self.n_streams, int(n_rows)
+        v = {"layout": L}
+        if in_block is not None:
+            v["offsets"] = in_block[L.in_off_offsets:L.in_off_offsets + 4 * (S + 1)].view(np.int32)
+            v["dets"] = in_block[L.in_off_dets:L.in_off_dets + R * 6 * dtype.itemsize].view(dtype).reshape(R, 6)
+            v["warps"] = (in_block[L.in_off_warps:L.in_off_warps + 48 * S].view(np.float64).reshape(S, 6)
+                          if self.kind == "botsort" else None)
+            v["feats"] = (in_block[L.in_off_feats:L.in_off_feats + R * self.feat_dim * 4].view(np.float32).reshape(R, self.feat_dim)
+                          if self.kind == "botsort" and self._cfg.with_reid else None)
+        if out_block is not None:
+            v["header"] = out_block[0:16].view(np.int32)
+            v["nout"] = out_block[L.out_off_nout:L.out_off_nout + 4 * S].view(np.int32)
+            v["rows"] = out_block[L.out_off_rows:L.out_off_rows + R * L.row_bytes].view(self._ROW_DTYPES[self.kind])
+        return v
+
+    def submit_packed(self, slot, in_block, out_block, dtype=np.float32, flags=0, img_hw=(0, 0)):
+        _lib.check(self._lib.b200track_submit_packed(self._ctx, slot, _ptr(in_block), _lib.F32 if np.dtype(dtype) == np.float32 else _lib.F64,
+                                                     int(flags), int(img_hw[0]), int(img_hw[1]), _ptr(out_block)))
+
+    def wait_packed(self, slot):
+        _lib.check(self._lib.b200track_wait_packed(self._ctx, slot))
+
+    def step_packed_device(self, d_in, n_rows, d_result, dtype=np.float32, flags=0, img_hw=(0, 0), stream=None):
+        """Asynchronous step on DEVICE blocks (torch uint8 tensors laid out like the host blocks)."""
+        st = C.c_void_p(stream) if stream else None
+        _lib.check(self._lib.b200track_step_packed(self._ctx, _ptr(d_in), int(n_rows), _lib.F32 if np.dtype(dtype) == np.float32 else _lib.F64,
+                                                   int(flags), int(img_hw[0]), int(img_hw[1]), _ptr(d_result), st))
+
+    def expand(self, in_block, out_block, n_rows: int, dtype=np.float32):
+        """The reference's result arrays rebuilt from a finished frame: ``(rows[M, 8] f64, stream_of_row[M])`` with
+        rows = [x1, y1, x2, y2, id, conf, cls, det_ind] in stream order, each stream in the reference's row order."""
+        v = self.frame_views(in_block, out_block, n_rows, dtype)
+        off, nout, rows, dets = v["offsets"], v["nout"], v["rows"], v["dets"]
+        S = self.n_streams
+        stream_of = np.repeat(np.arange(S, dtype=np.int32), nout)
+        first = np.repeat(off[:S].astype(np.int64), nout)
+        within = np.arange(len(stream_of), dtype=np.int64) - np.repeat(np.cumsum(nout, dtype=np.int64) - nout, nout)
+        r = rows[first + within]
+        di = r["det_ind"] & ~_lib.ROW_OC_NEW
+        src = dets[first + di].astype(np.float64, copy=False)
+        out = np.empty((len(r), 8), dtype=np.float64)
+        if self.kind == "ocsort":
+            out[:, 0:4] = src[:, 0:4]
+            new = (r["det_ind"] & _lib.ROW_OC_NEW) != 0
+            if new.any():                               # KalmanBoxTracker.get_state of a fresh tracker (ocsort.py:24-62)
+                b = src[new, 0:4]
+                w, h = b[:, 2] - b[:, 0], b[:, 3] - b[:, 1]
+                x, y, s_, r_ = b[:, 0] + w / 2.0, b[:, 1] + h / 2.0, w * h, w / (h + 1e-6)
+                w2 = np.sqrt(s_ * r_)
+                h2 = s_ / w2
+                out[new, 0], out[new, 1], out[new, 2], out[new, 3] = x - w2 / 2.0, y - h2 / 2.0, x + w2 / 2.0, y + h2 / 2.0
+        else:
+            out[:, 0:4] = r["box"]
+        out[:, 4] = r["id"]
+        out[:, 5] = src[:, 4]
+        out[:, 6] = r["cls"] if self.kind == "botsort" else src[:, 5]
+        out[:, 7] = di
+        return out, stream_of
+
+    def update_frames(self, dets, feats=None, warps=None, img_hw=(0, 0), dtype=None):
+        """Synchronous step on a list of per-stream detection arrays -> list of per-stream result arrays [M_s, 8]
+        (the reference's ``tracker.update`` output for every stream).  fp32 detections travel as fp32."""
+        if dtype is None:
+            dtype = np.float32 if all(np.asarray(d).dtype == np.float32 for d in dets) else np.float64
+        if not hasattr(self, "_frame_bufs"):
+            self._frame_bufs = self.frame_buffers()
+        bi, bo = self._frame_bufs
+        R, flags = self.pack(bi, dets, feats=feats, warps=warps, dtype=dtype)
+        self.submit_packed(0, bi, bo, dtype, flags, img_hw)
+        self.wait_packed(0)
+        out, stream_of = self.expand(bi, bo, R, dtype)
+        cuts = np.cumsum(self.frame_views(None, bo, R, dtype)["nout"])[:-1]
+        return np.split(out, cuts)
+
     # ------------------------------------------------------------------ probes
     def track_updates(self) -> int:
         v = C.c_uint64()

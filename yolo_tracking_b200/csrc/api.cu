@@ -31,6 +31,18 @@ using b200::set_error;
 namespace {
 constexpr int NSLOT = 3;
 
+// every entry point runs on the context's device and leaves the caller's current device as it found it
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev); else if (err == cudaSuccess) prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(ctx) DeviceGuard _guard((ctx)->cfg.device); CU_TRY(_guard.err)
+
 struct HostSlot {
     double* d_dets = nullptr;
     int32_t* d_ndets = nullptr;
@@ -39,6 +51,12 @@ struct HostSlot {
     int32_t* d_nout = nullptr;
     cudaEvent_t in_ready = nullptr, done = nullptr, out_ready = nullptr;
     bool used = false;
+    int32_t* h_err = nullptr;           // pinned: capacity bits of the step this slot carried (b200track_wait_host)
+    // packed frames: one input block, one result block (b200track_frame_layout)
+    unsigned char* d_in = nullptr;
+    unsigned char* d_res = nullptr;
+    const int32_t* h_res = nullptr;     // the caller's result block of the step in flight (header read by wait_packed)
+    bool packed = false;
 };
 }  // namespace
 
@@ -72,13 +90,15 @@ extern "C" const char* b200track_last_error(void) { return b200::g_last_error.c_
 
 extern "C" void b200track_destroy(b200track_ctx* ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->cfg.device);
+    DeviceGuard _guard(ctx->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(ctx->p.state_f); cudaFree(ctx->p.state_i); cudaFree(ctx->p.counts);
-    cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.dbg); cudaFree(ctx->p.scratch);
+    cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.err_slot); cudaFree(ctx->p.dbg); cudaFree(ctx->p.scratch);
     cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.feat_curr); cudaFree(ctx->p.cls_hist);
     for (auto& s : ctx->slot) {
         cudaFree(s.d_dets); cudaFree(s.d_ndets); cudaFree(s.d_feats); cudaFree(s.d_out); cudaFree(s.d_nout);
+        cudaFree(s.d_in); cudaFree(s.d_res);
+        if (s.h_err) cudaFreeHost(s.h_err);
         if (s.in_ready) cudaEventDestroy(s.in_ready);
         if (s.done) cudaEventDestroy(s.done);
         if (s.out_ready) cudaEventDestroy(s.out_ready);
@@ -92,7 +112,7 @@ extern "C" void b200track_destroy(b200track_ctx* ctx) {
 
 extern "C" int b200track_reset(b200track_ctx* ctx) {
     if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
-    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
     const size_t S = ctx->cfg.n_streams, T = ctx->tcap;
     CU_TRY(cudaMemset(ctx->p.state_f, 0, S * ctx->nf * T * sizeof(double)));
@@ -118,7 +138,8 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     int ndev = 0;
     CU_TRY(cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) { set_error("no such CUDA device"); return B200TRACK_ERR_CUDA; }
-    CU_TRY(cudaSetDevice(cfg->device));
+    DeviceGuard _guard(cfg->device);
+    CU_TRY(_guard.err);
     b200track_ctx* ctx = new b200track_ctx();
     ctx->cfg = *cfg;
     b200::StepParams& p = ctx->p;
@@ -160,16 +181,16 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     CU_TRY_CTX(cudaMalloc(&p.counts, S * 4 * sizeof(int)));
     CU_TRY_CTX(cudaMalloc(&p.track_updates, S * sizeof(unsigned long long)));
     CU_TRY_CTX(cudaMalloc(&p.err, sizeof(int)));
+    CU_TRY_CTX(cudaMalloc(&p.err_slot, NSLOT * sizeof(int)));
+    CU_TRY_CTX(cudaMemset(p.err_slot, 0, NSLOT * sizeof(int)));
     CU_TRY_CTX(cudaMallocHost(&ctx->h_err, sizeof(int32_t)));
     CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->s_compute, cudaStreamNonBlocking));
     CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
     CU_TRY_CTX(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
     for (auto& s : ctx->slot) {
-        CU_TRY_CTX(cudaMalloc(&s.d_dets, S * D * 6 * sizeof(double)));
-        CU_TRY_CTX(cudaMalloc(&s.d_ndets, S * sizeof(int32_t)));
-        if (cfg->feat_dim > 0) CU_TRY_CTX(cudaMalloc(&s.d_feats, S * D * (size_t)cfg->feat_dim * sizeof(float)));
-        CU_TRY_CTX(cudaMalloc(&s.d_out, S * (size_t)cfg->max_tracks * 8 * sizeof(double)));
-        CU_TRY_CTX(cudaMalloc(&s.d_nout, S * sizeof(int32_t)));
+        // the device staging buffers of a slot are allocated on first use (padded or packed form)
+        CU_TRY_CTX(cudaMallocHost(&s.h_err, sizeof(int32_t)));
+        *s.h_err = 0;
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.in_ready, cudaEventDisableTiming));
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.out_ready, cudaEventDisableTiming));
@@ -189,9 +210,9 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
 }
 
 static int launch_step(b200track_ctx* ctx, const double* d_dets, const int32_t* d_ndets, const float* d_feats,
-                       int32_t img_h, int32_t img_w, double* d_out, int32_t* d_nout, cudaStream_t st) {
+                       int32_t img_h, int32_t img_w, double* d_out, int32_t* d_nout, cudaStream_t st, int* d_err_step = nullptr) {
     b200::StepParams p = ctx->p;
-    p.dets = d_dets; p.ndets = d_ndets; p.feats = d_feats; p.out = d_out; p.nout = d_nout;
+    p.dets = d_dets; p.ndets = d_ndets; p.feats = d_feats; p.out = d_out; p.nout = d_nout; p.err_out = d_err_step;
     p.img_h = img_h; p.img_w = img_w;
     if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
     else if (ctx->cfg.kind == B200TRACK_BOTSORT) {
@@ -209,19 +230,41 @@ extern "C" int b200track_step(b200track_ctx* ctx, const double* d_dets, const in
     // detection rows are fetched and output rows stored with 16-byte accesses
     if ((reinterpret_cast<uintptr_t>(d_dets) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_feats)) & 15) {
         set_error("d_dets / d_out / d_feats must be 16-byte aligned"); return B200TRACK_ERR_ARG; }
-    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    ON_DEVICE(ctx);
     return launch_step(ctx, d_dets, d_ndets, d_feats, img_h, img_w, d_out, d_nout, (cudaStream_t)stream);
 }
 
 extern "C" int b200track_host_slots(b200track_ctx* ctx) { return ctx ? NSLOT : B200TRACK_ERR_ARG; }
+
+static std::string capacity_message(int e) {
+    return std::string("capacity overflow:") + ((e & B200_ERR_DET_OVERFLOW) ? " detections > max_dets" : "") +
+           ((e & B200_ERR_TRACK_OVERFLOW) ? " tracks > max_tracks" : "") +
+           ((e & B200_ERR_BOT_CAPACITY) ? " BoT-SORT candidate graph or class history (> 4 classes on a track)" : "") +
+           ((e & B200_ERR_PACKED_ROW) ? " OC-SORT compact row cannot carry a filter-state box (use b200track_step)" : "") +
+           "; the context's state is truncated - b200track_reset before reuse";
+}
+
+static int ensure_padded_slot(b200track_ctx* ctx, HostSlot& s) {
+    if (s.d_dets) return 0;
+    const size_t S = ctx->cfg.n_streams, D = ctx->cfg.max_dets;
+    CU_TRY(cudaMalloc(&s.d_dets, S * D * 6 * sizeof(double)));
+    CU_TRY(cudaMalloc(&s.d_ndets, S * sizeof(int32_t)));
+    if (ctx->cfg.feat_dim > 0) CU_TRY(cudaMalloc(&s.d_feats, S * D * (size_t)ctx->cfg.feat_dim * sizeof(float)));
+    CU_TRY(cudaMalloc(&s.d_out, S * (size_t)ctx->cfg.max_tracks * 8 * sizeof(double)));
+    CU_TRY(cudaMalloc(&s.d_nout, S * sizeof(int32_t)));
+    return 0;
+}
 
 extern "C" int b200track_submit_host(b200track_ctx* ctx, int32_t slot, const double* h_dets,
                                      const int32_t* h_ndets, const float* h_feats, int32_t img_h,
                                      int32_t img_w, double* h_out, int32_t* h_nout) {
     if (!ctx || !h_dets || !h_ndets || !h_out || !h_nout) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
     if (slot < 0 || slot >= NSLOT) { set_error("slot out of range"); return B200TRACK_ERR_ARG; }
-    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    if (ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid && !h_feats) {
+        set_error("BoT-SORT with_reid: h_feats is NULL"); return B200TRACK_ERR_ARG; }
+    ON_DEVICE(ctx);
     HostSlot& s = ctx->slot[slot];
+    if (int rc = ensure_padded_slot(ctx, s)) return rc;
     const size_t S = ctx->cfg.n_streams, T = ctx->cfg.max_tracks, D = ctx->cfg.max_dets;
     if (s.used) {
         CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.done, 0));        // previous step on this slot consumed its inputs
@@ -241,26 +284,35 @@ extern "C" int b200track_submit_host(b200track_ctx* ctx, int32_t slot, const dou
     }
     CU_TRY(cudaEventRecord(s.in_ready, ctx->s_h2d));
     CU_TRY(cudaStreamWaitEvent(ctx->s_compute, s.in_ready, 0));
-    if (int rc = launch_step(ctx, s.d_dets, s.d_ndets, ctx->cfg.feat_dim > 0 ? s.d_feats : nullptr, img_h, img_w,
-                             s.d_out, s.d_nout, ctx->s_compute)) return rc;
+    // capacity overflows of THIS step come back with its outputs (b200track_wait_host reports them)
+    CU_TRY(cudaMemsetAsync(ctx->p.err_slot + slot, 0, sizeof(int), ctx->s_compute));
+    if (int rc = launch_step(ctx, s.d_dets, s.d_ndets, ctx->cfg.feat_dim > 0 && h_feats ? s.d_feats : nullptr, img_h, img_w,
+                             s.d_out, s.d_nout, ctx->s_compute, ctx->p.err_slot + slot)) return rc;
     CU_TRY(cudaEventRecord(s.done, ctx->s_compute));
     CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, s.done, 0));
     CU_TRY(cudaMemcpyAsync(h_nout, s.d_nout, S * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU_TRY(cudaMemcpyAsync(s.h_err, ctx->p.err_slot + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->s_d2h));
     // every output row carries a distinct detection of this frame (a track is only listed as tracked in the frame it
     // was matched or born), so at most maxnd rows per stream are valid: copy that prefix of each stream's block
     if (maxnd > 0)
         CU_TRY(cudaMemcpy2DAsync(h_out, T * 8 * sizeof(double), s.d_out, T * 8 * sizeof(double),
                                  (size_t)(maxnd < (int)T ? maxnd : (int)T) * 8 * sizeof(double), S, cudaMemcpyDeviceToHost, ctx->s_d2h));
     CU_TRY(cudaEventRecord(s.out_ready, ctx->s_d2h));
-    s.used = true;
+    s.used = true; s.packed = false;
+    return 0;
+}
+
+static int finish_slot(HostSlot& s) {
+    if (!s.used) return 0;
+    CU_TRY(cudaEventSynchronize(s.out_ready));
+    const int e = s.packed ? (s.h_res ? s.h_res[0] : 0) : *s.h_err;
+    if (e) { set_error(capacity_message(e)); return B200TRACK_ERR_CAPACITY; }
     return 0;
 }
 
 extern "C" int b200track_wait_host(b200track_ctx* ctx, int32_t slot) {
     if (!ctx || slot < 0 || slot >= NSLOT) { set_error("bad ctx / slot"); return B200TRACK_ERR_ARG; }
-    if (!ctx->slot[slot].used) return 0;
-    CU_TRY(cudaEventSynchronize(ctx->slot[slot].out_ready));
-    return 0;
+    return finish_slot(ctx->slot[slot]);
 }
 
 extern "C" int b200track_step_host(b200track_ctx* ctx, const double* h_dets, const int32_t* h_ndets,
@@ -270,17 +322,122 @@ extern "C" int b200track_step_host(b200track_ctx* ctx, const double* h_dets, con
     return b200track_wait_host(ctx, 0);
 }
 
+// ---- packed frames ------------------------------------------------------------------------------------------------
+static inline uint64_t align16(uint64_t v) { return (v + 15) & ~(uint64_t)15; }
+
+static int row_bytes_of(const b200track_ctx* ctx) {
+    return ctx->cfg.kind == B200TRACK_OCSORT ? B200_ROW_OC : (ctx->cfg.kind == B200TRACK_BOTSORT ? B200_ROW_BOT : B200_ROW_BYTE);
+}
+
+extern "C" int b200track_frame_layout(b200track_ctx* ctx, int64_t n_rows, int32_t det_dtype, b200track_layout* out) {
+    if (!ctx || !out) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    if (n_rows < 0 || (det_dtype != B200TRACK_F32 && det_dtype != B200TRACK_F64)) { set_error("bad n_rows / det_dtype"); return B200TRACK_ERR_ARG; }
+    const uint64_t S = ctx->cfg.n_streams, R = (uint64_t)n_rows;
+    const uint64_t det_row = det_dtype == B200TRACK_F32 ? 24 : 48;
+    const bool feats = ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid;
+    const bool warps = ctx->cfg.kind == B200TRACK_BOTSORT;
+    out->in_off_offsets = 0;
+    out->in_off_warps = align16(4 * (S + 1));
+    out->in_off_dets = align16(out->in_off_warps + (warps ? 48 * S : 0));
+    out->in_off_feats = align16(out->in_off_dets + det_row * R);
+    out->in_bytes = align16(out->in_off_feats + (feats ? R * (uint64_t)ctx->cfg.feat_dim * 4 : 0));
+    out->row_bytes = row_bytes_of(ctx);
+    out->out_off_nout = 16;
+    out->out_off_rows = align16(16 + 4 * S);
+    out->out_bytes = align16(out->out_off_rows + R * (uint64_t)out->row_bytes);
+    return 0;
+}
+
+// validates the offsets of a host-side input block and returns its row count
+static int64_t packed_rows(const b200track_ctx* ctx, const int32_t* off) {
+    const int S = ctx->cfg.n_streams;
+    if (off[0] != 0) return -1;
+    for (int i = 0; i < S; ++i) if (off[i + 1] < off[i]) return -1;
+    if ((int64_t)off[S] > (int64_t)S * ctx->cfg.max_dets) return -2;
+    return off[S];
+}
+
+static int launch_packed(b200track_ctx* ctx, const unsigned char* d_in, int64_t R, int32_t det_dtype, int32_t flags,
+                         int32_t img_h, int32_t img_w, unsigned char* d_res, cudaStream_t st) {
+    b200track_layout L;
+    if (int rc = b200track_frame_layout(ctx, R, det_dtype, &L)) return rc;
+    b200::StepParams p = ctx->p;
+    p.det_off = reinterpret_cast<const int*>(d_in + L.in_off_offsets);
+    p.dets32 = det_dtype == B200TRACK_F32 ? reinterpret_cast<const float*>(d_in + L.in_off_dets) : nullptr;
+    p.dets = det_dtype == B200TRACK_F64 ? reinterpret_cast<const double*>(d_in + L.in_off_dets) : nullptr;
+    p.ndets = nullptr;
+    p.feats = (ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid) ? reinterpret_cast<const float*>(d_in + L.in_off_feats) : nullptr;
+    p.warps = (ctx->cfg.kind == B200TRACK_BOTSORT && (flags & B200TRACK_FRAME_HAS_WARPS)) ? reinterpret_cast<const double*>(d_in + L.in_off_warps) : nullptr;
+    p.out = nullptr;
+    p.nout = reinterpret_cast<int*>(d_res + L.out_off_nout);
+    p.rows = d_res + L.out_off_rows;
+    p.err_out = reinterpret_cast<int*>(d_res);
+    p.img_h = img_h; p.img_w = img_w;
+    CU_TRY(cudaMemsetAsync(d_res, 0, 16, st));                  // header: [0] capacity bits of this step
+    if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
+    else if (ctx->cfg.kind == B200TRACK_BOTSORT) CU_TRY(b200::launch_botsort_step(p, ctx->variant, st));
+    else CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, ctx->variant, st));
+    ctx->launches += 1;
+    return 0;
+}
+
+extern "C" int b200track_step_packed(b200track_ctx* ctx, const void* d_in, int64_t n_rows, int32_t det_dtype, int32_t flags,
+                                     int32_t img_h, int32_t img_w, void* d_result, void* stream) {
+    if (!ctx || !d_in || !d_result) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    if ((reinterpret_cast<uintptr_t>(d_in) | reinterpret_cast<uintptr_t>(d_result)) & 15) { set_error("blocks must be 16-byte aligned"); return B200TRACK_ERR_ARG; }
+    if (n_rows < 0 || n_rows > (int64_t)ctx->cfg.n_streams * ctx->cfg.max_dets) { set_error("n_rows out of range"); return B200TRACK_ERR_ARG; }
+    ON_DEVICE(ctx);
+    return launch_packed(ctx, static_cast<const unsigned char*>(d_in), n_rows, det_dtype, flags, img_h, img_w,
+                         static_cast<unsigned char*>(d_result), (cudaStream_t)stream);
+}
+
+extern "C" int b200track_submit_packed(b200track_ctx* ctx, int32_t slot, const void* h_in, int32_t det_dtype, int32_t flags,
+                                       int32_t img_h, int32_t img_w, void* h_result) {
+    if (!ctx || !h_in || !h_result) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    if (slot < 0 || slot >= NSLOT) { set_error("slot out of range"); return B200TRACK_ERR_ARG; }
+    const int64_t R = packed_rows(ctx, static_cast<const int32_t*>(h_in));
+    if (R == -1) { set_error("offsets must start at 0 and be non-decreasing"); return B200TRACK_ERR_ARG; }
+    if (R == -2) { set_error("more detection rows than n_streams * max_dets"); return B200TRACK_ERR_CAPACITY; }
+    ON_DEVICE(ctx);
+    HostSlot& s = ctx->slot[slot];
+    b200track_layout L, Lmax;
+    if (int rc = b200track_frame_layout(ctx, R, det_dtype, &L)) return rc;
+    if (!s.d_in) {
+        if (int rc = b200track_frame_layout(ctx, (int64_t)ctx->cfg.n_streams * ctx->cfg.max_dets, B200TRACK_F64, &Lmax)) return rc;
+        CU_TRY(cudaMalloc(&s.d_in, Lmax.in_bytes));
+        CU_TRY(cudaMalloc(&s.d_res, Lmax.out_bytes));
+    }
+    if (s.used) {
+        CU_TRY(cudaStreamWaitEvent(ctx->s_h2d, s.done, 0));
+        CU_TRY(cudaStreamWaitEvent(ctx->s_compute, s.out_ready, 0));
+    }
+    // ONE linear copy per direction: the input block in, the result block (header, counts, compact rows) out
+    CU_TRY(cudaMemcpyAsync(s.d_in, h_in, L.in_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CU_TRY(cudaEventRecord(s.in_ready, ctx->s_h2d));
+    CU_TRY(cudaStreamWaitEvent(ctx->s_compute, s.in_ready, 0));
+    if (int rc = launch_packed(ctx, s.d_in, R, det_dtype, flags, img_h, img_w, s.d_res, ctx->s_compute)) return rc;
+    CU_TRY(cudaEventRecord(s.done, ctx->s_compute));
+    CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, s.done, 0));
+    CU_TRY(cudaMemcpyAsync(h_result, s.d_res, L.out_bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CU_TRY(cudaEventRecord(s.out_ready, ctx->s_d2h));
+    s.used = true; s.packed = true; s.h_res = static_cast<const int32_t*>(h_result);
+    return 0;
+}
+
+extern "C" int b200track_wait_packed(b200track_ctx* ctx, int32_t slot) {
+    if (!ctx || slot < 0 || slot >= NSLOT) { set_error("bad ctx / slot"); return B200TRACK_ERR_ARG; }
+    return finish_slot(ctx->slot[slot]);
+}
+
 extern "C" int b200track_sync(b200track_ctx* ctx) {
     if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
-    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
     CU_TRY(cudaMemcpy(ctx->h_err, ctx->p.err, sizeof(int), cudaMemcpyDeviceToHost));
     const int e = *ctx->h_err;
     if (e) {
         CU_TRY(cudaMemset(ctx->p.err, 0, sizeof(int)));
-        set_error(std::string("capacity overflow:") + ((e & B200_ERR_DET_OVERFLOW) ? " detections > max_dets" : "") +
-                  ((e & B200_ERR_TRACK_OVERFLOW) ? " tracks > max_tracks" : "") +
-                  ((e & B200_ERR_BOT_CAPACITY) ? " BoT-SORT candidate graph or class history (> 4 classes on a track)" : ""));
+        set_error(capacity_message(e));
         return B200TRACK_ERR_CAPACITY;
     }
     return 0;
@@ -288,7 +445,7 @@ extern "C" int b200track_sync(b200track_ctx* ctx) {
 
 extern "C" int b200track_track_updates(b200track_ctx* ctx, uint64_t* h_total) {
     if (!ctx || !h_total) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
-    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
     std::vector<unsigned long long> h(ctx->cfg.n_streams);
     CU_TRY(cudaMemcpy(h.data(), ctx->p.track_updates, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
@@ -306,7 +463,7 @@ extern "C" int b200track_launch_count(b200track_ctx* ctx, uint64_t* h_launches) 
 
 extern "C" int b200track_phase_cycles(b200track_ctx* ctx, uint64_t* h_out16, int32_t reset) {
     if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
-    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
     if (!ctx->p.dbg) {
         CU_TRY(cudaMalloc(&ctx->p.dbg, 16 * sizeof(unsigned long long)));
@@ -329,7 +486,7 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
                                    int32_t* h_rec, double* h_mean, double* h_cov, double* h_aux) {
     if (!ctx || !h_counts) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
     if (stream_index < 0 || stream_index >= ctx->cfg.n_streams) { set_error("stream_index out of range"); return B200TRACK_ERR_ARG; }
-    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
     const size_t T = ctx->tcap, s = stream_index;
     std::vector<double> f((size_t)ctx->nf * T);
@@ -410,7 +567,7 @@ extern "C" int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, 
     if (!ctx || !h_feat) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
     if (ctx->cfg.kind != B200TRACK_BOTSORT || !ctx->p.feat_pool) { set_error("context holds no embeddings"); return B200TRACK_ERR_STATE; }
     if (stream_index < 0 || stream_index >= ctx->cfg.n_streams) { set_error("stream_index out of range"); return B200TRACK_ERR_ARG; }
-    CU_TRY(cudaSetDevice(ctx->cfg.device));
+    ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
     const size_t T = ctx->tcap, s = stream_index, F = ctx->cfg.feat_dim;
     int counts[4];

@@ -552,11 +552,29 @@ bytetrack_step_kernel(const StepParams p) {
     const int t = tid;                                   // this thread's track slot
     const double* gf = p.state_f + (size_t)s * B200_NF * TMAX;
     const int* gi = p.state_i + (size_t)s * NI * TMAX;
-    const double* dets_g = p.dets + (size_t)s * p.max_dets * 6;
+    // packed frames: the rows of all streams lie back to back, fp32 or fp64 (step_params.h); the row offset of the stream
+    // is one more dependent load, which the stream ahead prefetched to L2
+    const bool packed = p.det_off != nullptr;
+    int roff = 0, nd_in = 0;
+    if (packed) { roff = p.det_off[s]; nd_in = p.det_off[s + 1] - roff; }
+    const double* dets_g = packed ? p.dets + (size_t)roff * 6 : p.dets + (size_t)s * p.max_dets * 6;
+    const float* dets32_g = p.dets32 ? p.dets32 + (size_t)roff * 6 : nullptr;
+    auto det_cls = [&](int j) -> double { return dets32_g ? (double)dets32_g[j * 6 + 5] : dets_g[j * 6 + 5]; };
     // thread j fetches detection row j whole (three 16-byte loads: 48-byte rows, 16-byte aligned) - no transposition pass
     double mv[8];
     double2 dr0 = make_double2(0.0, 0.0), dr1 = dr0, dr2 = dr0;
-    if (tid < min(DMAX, p.max_dets)) {
+    if (packed) {
+        if (tid < min(min(DMAX, p.max_dets), nd_in)) {
+            if (dets32_g) {                              // 24-byte rows, 8-byte aligned; widening is exact
+                const float2* row = reinterpret_cast<const float2*>(dets32_g + (size_t)tid * 6);
+                const float2 a = row[0], b = row[1], c = row[2];
+                dr0 = make_double2((double)a.x, (double)a.y); dr1 = make_double2((double)b.x, (double)b.y); dr2 = make_double2((double)c.x, (double)c.y);
+            } else {
+                const double2* row = reinterpret_cast<const double2*>(dets_g + (size_t)tid * 6);
+                dr0 = row[0]; dr1 = row[1]; dr2 = row[2];
+            }
+        }
+    } else if (tid < min(DMAX, p.max_dets)) {
         const double2* row = reinterpret_cast<const double2*>(dets_g + (size_t)tid * 6);
         dr0 = row[0]; dr1 = row[1]; dr2 = row[2];
     }
@@ -569,9 +587,16 @@ bytetrack_step_kernel(const StepParams p) {
         const int s2 = s + AHEAD;
         if (s2 < p.n_streams) {
             const char* d2 = reinterpret_cast<const char*>(p.dets + (size_t)s2 * p.max_dets * 6);
+            int nl_d = (p.max_dets * 48 + 127) >> 7;
+            if (packed) {
+                const int o2 = p.det_off[s2], n2 = p.det_off[s2 + 1] - o2, rb = p.dets32 ? 24 : 48;
+                d2 = p.dets32 ? reinterpret_cast<const char*>(p.dets32 + (size_t)o2 * 6) : reinterpret_cast<const char*>(p.dets + (size_t)o2 * 6);
+                nl_d = (n2 * rb + 127) >> 7;
+                if (tid == 0 && s2 + AHEAD < p.n_streams) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.det_off + s2 + AHEAD));
+            }
             const char* f2 = reinterpret_cast<const char*>(p.state_f + (size_t)s2 * B200_NF * TMAX);
             const char* i2 = reinterpret_cast<const char*>(p.state_i + (size_t)s2 * NI * TMAX);
-            const int nl_d = (p.max_dets * 48 + 127) >> 7, nl_f = (8 * TMAX * 8 + 127) >> 7, nl_i = (NI * TMAX * 4 + 127) >> 7;   // B200_TF_MEAN == 0
+            const int nl_f = (8 * TMAX * 8 + 127) >> 7, nl_i = (NI * TMAX * 4 + 127) >> 7;   // B200_TF_MEAN == 0
             for (int l = tid; l < nl_d + nl_f + nl_i; l += NT) {
                 const char* a = l < nl_d ? d2 + ((size_t)l << 7) : (l < nl_d + nl_f ? f2 + ((size_t)(l - nl_d) << 7) : i2 + ((size_t)(l - nl_d - nl_f) << 7));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
@@ -587,7 +612,7 @@ bytetrack_step_kernel(const StepParams p) {
     if constexpr (BOT) frow_v = gi[B200_TI_FROW * TMAX + t];
     int* counts = p.counts + 4 * s;
     const int nT = counts[0], nL = counts[1], id0 = counts[2], frame = counts[3] + 1;
-    int nd = p.ndets[s];
+    int nd = packed ? nd_in : p.ndets[s];
     LapWork lw;
     lw.Tmax = TMAX; lw.Dmax = DMAX; lw.adj = &sm.adj[0][0]; lw.u = sm.u; lw.v = sm.v; lw.dist = sm.dist;
     lw.parent = sm.parent; lw.head = sm.head; lw.rnext = sm.rnext; lw.xr = sm.xr; lw.yc = sm.yc;
@@ -722,7 +747,8 @@ bytetrack_step_kernel(const StepParams p) {
             for (int j = warp; j < nd; j += NT / 32) {
                 if (sm.dflag[j] != DF_HIGH) continue;
                 const size_t off = ((size_t)s * p.max_dets + j) * p.feat_dim;
-                const float n2 = det_curr_feat(reinterpret_cast<const float4*>(p.feats + off), reinterpret_cast<float4*>(p.feat_curr + off), nv, lane);
+                const size_t off_in = packed ? ((size_t)roff + j) * p.feat_dim : off;
+                const float n2 = det_curr_feat(reinterpret_cast<const float4*>(p.feats + off_in), reinterpret_cast<float4*>(p.feat_curr + off), nv, lane);
                 if (lane == 0) sm.bot.dn2[j] = n2;
             }
         }
@@ -872,7 +898,7 @@ bytetrack_step_kernel(const StepParams p) {
             frame_t = frame;
             det_ind = j;
             score = sm.dconf[j];
-            cls = dets_g[j * 6 + 5];
+            cls = det_cls(j);
             if constexpr (BOT) {
                 double* h = p.cls_hist + ((size_t)s * TMAX + sm.bot.frow[t]) * 9;
                 cls = cls_vote(h, cls, score, err);
@@ -1037,8 +1063,25 @@ bytetrack_step_kernel(const StepParams p) {
     const bool born_active = frame == 1;                 // STrack.activate: is_activated only on frame 1
     double* wf = p.state_f + (size_t)s * B200_NF * TMAX;
     int* wi = p.state_i + (size_t)s * NI * TMAX;
-    double* gout = p.out + (size_t)s * p.max_tracks * 8;
-    const int out_cap = p.max_tracks;
+    double* gout = packed ? nullptr : p.out + (size_t)s * p.max_tracks * 8;
+    const int out_cap = packed ? min(p.max_tracks, nd_in) : p.max_tracks;
+    // result row: the reference's [x1, y1, x2, y2, id, conf, cls, det_ind] (64 bytes, four 16-byte stores), or the compact
+    // row of the packed interface (layout.h: 40 bytes, BoT-SORT 48) - conf / cls there are the caller's own input columns
+    auto write_row = [&](int orow, const Box& b, int id, double conf, double cl, int di) {
+        if (!packed) {
+            double2* o = reinterpret_cast<double2*>(gout + (size_t)orow * 8);
+            o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
+            o[2] = make_double2((double)id, conf); o[3] = make_double2(cl, (double)di);
+        } else if constexpr (BOT) {
+            double2* o = reinterpret_cast<double2*>(p.rows + (size_t)(roff + orow) * B200_ROW_BOT);
+            o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
+            reinterpret_cast<int4*>(o)[2] = make_int4(id, di, __float_as_int((float)cl), __float_as_int((float)conf));
+        } else {
+            double* o = reinterpret_cast<double*>(p.rows + (size_t)(roff + orow) * B200_ROW_BYTE);
+            o[0] = b.x1; o[1] = b.y1; o[2] = b.x2; o[3] = b.y2;
+            reinterpret_cast<int2*>(o)[4] = make_int2(id, di);
+        }
+    };
     unsigned long long val = 0ull;
     if (cat != CAT_NONE && !sm.drop[t]) val = 1ull << (10 * (cat - 1));
     if (born) {
@@ -1096,12 +1139,7 @@ bytetrack_step_kernel(const StepParams p) {
             wi[B200_TI_FLAGS * TMAX + dst] = fl;
             if constexpr (BOT) wi[B200_TI_FROW * TMAX + dst] = sm.bot.frow[t];
         }
-        if (orow >= 0 && orow < out_cap) {
-            const Box b = track_box<KIND>(sm, t);
-            double2* o = reinterpret_cast<double2*>(gout + (size_t)orow * 8);      // 64-byte rows: four 16-byte stores
-            o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
-            o[2] = make_double2((double)tid_id, score); o[3] = make_double2(cls, (double)det_ind);
-        }
+        if (orow >= 0 && orow < out_cap) write_row(orow, track_box<KIND>(sm, t), tid_id, score, cls, det_ind);
     }
     if (val & (1ull << 40)) {                           // STrack.activate (byte_tracker.py:50-62)
         const int j = tid;
@@ -1122,7 +1160,7 @@ bytetrack_step_kernel(const StepParams p) {
                 wf[(B200_TF_COV + 3 * a + 2) * TMAX + dst] = kn.vv[a];
             }
             wf[B200_TF_SCORE * TMAX + dst] = sm.dconf[j];
-            wf[B200_TF_CLS * TMAX + dst] = dets_g[j * 6 + 5];
+            wf[B200_TF_CLS * TMAX + dst] = det_cls(j);
             wi[B200_TI_ID * TMAX + dst] = id;
             wi[B200_TI_FRAME * TMAX + dst] = frame;
             wi[B200_TI_START * TMAX + dst] = frame;
@@ -1138,17 +1176,12 @@ bytetrack_step_kernel(const StepParams p) {
             if (stored) {
                 wi[B200_TI_FROW * TMAX + dst] = row;
                 double* h = p.cls_hist + ((size_t)s * TMAX + row) * 9;     // STrack.__init__: cls_hist = [[cls, score]]
-                h[0] = dets_g[j * 6 + 5]; h[4] = sm.dconf[j]; h[8] = 1.0;
+                h[0] = det_cls(j); h[4] = sm.dconf[j]; h[8] = 1.0;
             }
         }
         if (born_active) {
             const int orow = totKeep + k;
-            if (orow < out_cap) {
-                const Box b = mean_to_box<KIND>(z[0], z[1], z[2], z[3]);
-                double2* o = reinterpret_cast<double2*>(gout + (size_t)orow * 8);
-                o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
-                o[2] = make_double2((double)id, sm.dconf[j]); o[3] = make_double2(dets_g[j * 6 + 5], (double)j);
-            }
+            if (orow < out_cap) write_row(orow, mean_to_box<KIND>(z[0], z[1], z[2], z[3]), id, sm.dconf[j], det_cls(j), j);
         }
     }
     if constexpr (BOT) {
@@ -1171,7 +1204,7 @@ bytetrack_step_kernel(const StepParams p) {
         }
     }
     PHASE(15);
-    if (err) atomicOr(p.err, err);
+    if (err) { atomicOr(p.err, err); if (p.err_out) atomicOr(p.err_out, err); }
     if (tid == 0) {
         if (p.dbg) atomicAdd(&p.dbg[0], 1ull);
         counts[0] = min(newT, cap);

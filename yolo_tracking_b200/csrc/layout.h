@@ -34,12 +34,25 @@
 #define B200_ERR_DET_OVERFLOW 1
 #define B200_ERR_TRACK_OVERFLOW 2
 #define B200_ERR_BOT_CAPACITY 4     // BoT-SORT: candidate graph overflow or more than 4 classes voted on one track
+#define B200_ERR_PACKED_ROW 8       // OC-SORT compact rows: a matched tracker whose last observation sums below zero reports its
+                                    // filter box (ocsort.py:355-358), which an (id, det_ind) row cannot carry - use b200track_step
 
 // BoT-SORT contexts carry one more int32 component per slot: the row of the track in the stream's
 // embedding pool feat_pool[(s * Tmax + row) * feat_dim] (fp32) and class-vote table
 // cls_hist[(s * Tmax + row) * 9] = {cls[4], score sum[4], n}.  Rows never move; slots do.
 #define B200_NI_BOT 7
 #define B200_TI_FROW 6
+
+// Compact result rows of the packed frame interface (b200track_step_packed):
+//   ByteTrack 40 B: double x1, y1, x2, y2; int32 id; int32 det_ind    (conf / cls are the caller's own dets[det_ind, 4:6])
+//   BoT-SORT  48 B: double x1, y1, x2, y2; int32 id; int32 det_ind; float cls (the voted class); float conf
+//   OC-SORT    8 B: int32 id; int32 det_ind                            (the box is the caller's own dets[det_ind, 0:4])
+#define B200_ROW_BYTE 40
+#define B200_ROW_BOT 48
+#define B200_ROW_OC 8
+// OC-SORT compact rows: det_ind bit 30 = row of a tracker created this frame (its box is the detection's round trip
+// convert_x_to_bbox(convert_bbox_to_z(det)), ocsort.py:354-360 with the placeholder last_observation)
+#define B200_ROW_OC_NEW (1 << 30)
 
 // bytes a track slot occupies in HBM (one direction)
 #define B200_SLOT_BYTES (B200_NF * 8 + B200_NI * 4)

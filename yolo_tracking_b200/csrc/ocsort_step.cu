@@ -228,7 +228,11 @@ ocsort_step_kernel(const StepParams p) {
 #define PHASE(k) do { if (p.dbg && tid == 0) { const long long now_ = clock64(); atomicAdd(&p.dbg[k], (unsigned long long)(now_ - ph_last)); ph_last = now_; } } while (0)
     int* counts = p.counts + 4 * s;
     const int n0 = counts[0], id0 = counts[2], frame = counts[3] + 1;
-    int nd = p.ndets[s];
+    const bool packed = p.det_off != nullptr;          // packed frames (step_params.h)
+    int roff = 0;
+    if (packed) roff = p.det_off[s];
+    const int nd_in = packed ? p.det_off[s + 1] - roff : p.ndets[s];
+    int nd = nd_in;
     int err = 0;
     const int dcap = min(DMAX, p.max_dets), tcap = min(TMAX, p.max_tracks);
     if (nd > dcap) { nd = dcap; err |= B200_ERR_DET_OVERFLOW; }
@@ -245,9 +249,15 @@ ocsort_step_kernel(const StepParams p) {
         const int s2 = s + 148;
         if (s2 < p.n_streams) {
             const char* d2 = reinterpret_cast<const char*>(p.dets + (size_t)s2 * p.max_dets * 6);
+            int nl_d = (p.max_dets * 48 + 127) >> 7;
+            if (packed) {
+                const int o2 = p.det_off[s2], n2 = p.det_off[s2 + 1] - o2;
+                d2 = p.dets32 ? reinterpret_cast<const char*>(p.dets32 + (size_t)o2 * 6) : reinterpret_cast<const char*>(p.dets + (size_t)o2 * 6);
+                nl_d = (n2 * (p.dets32 ? 24 : 48) + 127) >> 7;
+            }
             const char* f2 = reinterpret_cast<const char*>(p.state_f + (size_t)s2 * B200_OC_NF * TMAX);
             const char* i2 = reinterpret_cast<const char*>(p.state_i + (size_t)s2 * B200_OC_NI * TMAX);
-            const int nl_d = (p.max_dets * 48 + 127) >> 7, nl_f = (B200_OC_SX * TMAX * 8 + 127) >> 7, nl_i = (B200_OC_NI * TMAX * 4 + 127) >> 7;
+            const int nl_f = (B200_OC_SX * TMAX * 8 + 127) >> 7, nl_i = (B200_OC_NI * TMAX * 4 + 127) >> 7;
             for (int l = tid; l < nl_d + nl_f + nl_i; l += NT) {
                 const char* a = l < nl_d ? d2 + ((size_t)l << 7) : (l < nl_d + nl_f ? f2 + ((size_t)(l - nl_d) << 7) : i2 + ((size_t)(l - nl_d - nl_f) << 7));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
@@ -256,9 +266,10 @@ ocsort_step_kernel(const StepParams p) {
     }
     // ---- HBM -> shared memory: detections, hot part of the tracker state --------------------
     {
-        const double* g = p.dets + (size_t)s * p.max_dets * 6;
+        const double* g = packed ? p.dets + (size_t)roff * 6 : p.dets + (size_t)s * p.max_dets * 6;
+        const float* g32 = p.dets32 ? p.dets32 + (size_t)roff * 6 : nullptr;
         for (int i = tid; i < nd * 6; i += NT) {
-            const double val = g[i];
+            const double val = g32 ? (double)g32[i] : g[i];
             const int j = i / 6, c = i - 6 * j;
             if (c < 4) sm.dbox[c][j] = val;
             else if (c == 4) sm.dconf[j] = val;
@@ -615,8 +626,17 @@ ocsort_step_kernel(const StepParams p) {
     const int E_old = (int)(tot & 1023), E_new = (int)((tot >> 10) & 1023);
     const int n_free0 = (int)((tot >> 20) & 1023), n_free1 = (int)((tot >> 30) & 1023), n_keep = (int)((tot >> 40) & 1023);
     const int n_new = n_free0 + n_free1;
-    double* gout = p.out + (size_t)s * p.max_tracks * 8;
+    double* gout = packed ? nullptr : p.out + (size_t)s * p.max_tracks * 8;
+    const int out_cap = packed ? min(p.max_tracks, nd_in) : p.max_tracks;
     if (n0 + n_new > tcap) err |= B200_ERR_TRACK_OVERFLOW;
+    // result row: the reference's [x1, y1, x2, y2, id, conf, cls, det_ind], or - packed frames - just (id, det_ind): an
+    // OC-SORT row's box / conf / cls are the caller's own detection row det_ind (ocsort.py:356-363: last_observation)
+    auto write_row = [&](int row, const Box& b, int id, double cf, double cl, int di) {
+        if (packed) { reinterpret_cast<int2*>(p.rows)[(size_t)roff + row] = make_int2(id, di); return; }
+        double2* o = reinterpret_cast<double2*>(gout + (size_t)row * 8);          // 64-byte rows: four 16-byte stores
+        o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
+        o[2] = make_double2((double)id, cf); o[3] = make_double2(cl, (double)di);
+    };
 
     if (live) {
         // write the slot back in place
@@ -639,13 +659,11 @@ ocsort_step_kernel(const StepParams p) {
         gi[B200_OCI_FLAGS * TMAX + t] = die ? (fl & ~OCF_ALIVE) : fl;
         if (emit_old) {
             const int row = E_new + (E_old - 1 - (int)(ex & 1023));
-            if (row < p.max_tracks) {
+            if (row < out_cap) {
                 Box b;
                 if (box_from_obs) { b.x1 = sm.lbox[0][t]; b.y1 = sm.lbox[1][t]; b.x2 = sm.lbox[2][t]; b.y2 = sm.lbox[3][t]; }
-                else b = oc_x_to_box(k.x[0], k.x[1], k.x[2], k.x[3]);
-                double2* o = reinterpret_cast<double2*>(gout + (size_t)row * 8);          // 64-byte rows: four 16-byte stores
-                o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
-                o[2] = make_double2((double)(tid_id + 1), conf); o[3] = make_double2(cls, (double)det_ind);
+                else { b = oc_x_to_box(k.x[0], k.x[1], k.x[2], k.x[3]); if (packed) err |= B200_ERR_PACKED_ROW; }
+                write_row(row, b, tid_id + 1, conf, cls, det_ind);
             }
         }
     } else if (t < n0 && (fl & OCF_ALIVE) == 0 && t < TMAX) {
@@ -684,12 +702,8 @@ ocsort_step_kernel(const StepParams p) {
         if (emit_new) {
             // reversed list order: the newest tracker first; rows of the new trackers precede the old ones
             const int row = n_new - 1 - order;
-            if (row < p.max_tracks) {
-                const Box b = oc_x_to_box(z[0], z[1], z[2], z[3]);
-                double2* o = reinterpret_cast<double2*>(gout + (size_t)row * 8);
-                o[0] = make_double2(b.x1, b.y1); o[1] = make_double2(b.x2, b.y2);
-                o[2] = make_double2((double)(id + 1), sm.dconf[j]); o[3] = make_double2(sm.dcls[j], (double)j);
-            }
+            // packed: bit 30 marks a new tracker - its box is the detection's round trip through the filter state
+            if (row < out_cap) write_row(row, oc_x_to_box(z[0], z[1], z[2], z[3]), id + 1, sm.dconf[j], sm.dcls[j], packed ? (j | B200_ROW_OC_NEW) : j);
         }
     }
     const int n1 = min(n0 + n_new, tcap);
@@ -735,11 +749,11 @@ ocsort_step_kernel(const StepParams p) {
         counts[1] = alive_after;
         counts[2] = id0 + n_new;
         counts[3] = frame;
-        p.nout[s] = min(E_old + E_new, p.max_tracks);
+        p.nout[s] = min(E_old + E_new, out_cap);
         p.track_updates[s] += (unsigned long long)Cn;
-        if (err) atomicOr(p.err, err);
         if (p.dbg) atomicAdd(&p.dbg[0], 1ull);
     }
+    if (err) { atomicOr(p.err, err); if (p.err_out) atomicOr(p.err_out, err); }
 }
 #undef PHASE
 

@@ -34,6 +34,7 @@ struct StepParams {
     int* counts;
     unsigned long long* track_updates;
     int* err;
+    int* err_slot;            // [host slots] per-step capacity words of the padded host interface
     unsigned long long* dbg;  // [16] optional phase cycle counters, null = off
     // per-step inputs / outputs (device)
     const double* dets;       // [S, max_dets, 6]
@@ -41,6 +42,16 @@ struct StepParams {
     const float* feats;       // [S, max_dets, feat_dim] or null
     double* out;              // [S, max_tracks, 8]
     int* nout;                // [S]
+    // packed frame interface (b200track_step_packed, include/b200track.h): det_off != null selects it.  The detection
+    // rows of all streams lie back to back (stream s owns rows [det_off[s], det_off[s + 1])), as fp32 (dets32) or fp64
+    // (dets) rows of 6; embeddings, if any, are packed the same way (feats[row]); the result rows of stream s are
+    // written compactly (layout.h: B200_ROW_*) at the same row offsets - every result row carries a distinct detection
+    // of its frame, so a stream never has more result rows than detections.
+    const float* dets32;      // [R, 6] or null
+    const int* det_off;       // [S + 1]
+    unsigned char* rows;      // [R] compact result rows
+    int* err_out;             // header word of the result block: capacity overflow bits of this step
+    const double* warps;      // [S, 6] row-major 2x3 camera-motion warp per stream (BoT-SORT), null = identity
 };
 
 // The step kernel is compiled for a few (slot capacity, detection capacity) pairs; a context
