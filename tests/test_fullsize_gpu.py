@@ -100,7 +100,9 @@ def test_config2_ocsort_shape_determinism_and_sampled_oracle():
 
     def run(streams, copies=1):
         idx = np.asarray(streams)
-        trk = BatchedTracker("ocsort", len(idx) * copies, max_tracks=cap, max_dets=cap, **cfg)
+        # det_thresh 0 turns every false positive into a tracker that lives max_age frames: ~130 live trackers per stream,
+        # so 256 slots like bench.py's config-2 workload (128 overflowed on a few streams - reported by wait_host now)
+        trk = BatchedTracker("ocsort", len(idx) * copies, max_tracks=256, max_dets=cap, **cfg)
         outs = []
         for f in range(F2):
             d = np.ascontiguousarray(np.tile(dets[f, idx], (copies, 1, 1)))

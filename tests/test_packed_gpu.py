@@ -31,8 +31,9 @@ def test_packed_rows_equal_padded_rows(kind, cfg, fp32):
     S, N, F, D = 5, 30, 40, 64
     dets, nd, feats = _inputs(kind, S, N, F, D, fp32)
     fd = 128 if kind == "botsort" else 0
-    a = BatchedTracker(kind, S, max_tracks=D, max_dets=D, feat_dim=fd, **cfg)
-    b = BatchedTracker(kind, S, max_tracks=D, max_dets=D, feat_dim=fd, **cfg)
+    T = 128 if kind == "ocsort" else D          # false positives live max_age frames as OC-SORT trackers
+    a = BatchedTracker(kind, S, max_tracks=T, max_dets=D, feat_dim=fd, **cfg)
+    b = BatchedTracker(kind, S, max_tracks=T, max_dets=D, feat_dim=fd, **cfg)
     hw = (1080, 1920)
     for f in range(F):
         out, nout = a.update_batch(np.ascontiguousarray(dets[f]), np.ascontiguousarray(nd[f]),

@@ -18,7 +18,7 @@ import torch  # noqa: E402
 from yolo_tracking_b200.batch import BatchedTracker  # noqa: E402
 
 dev = torch.device("cuda", 0)
-d_dets = torch.from_numpy(dets).to(dev)
+d_dets = torch.from_numpy(dets).to(dev).to(torch.float64)
 d_nd = torch.from_numpy(nd).to(dev)
 d_out = torch.empty((S, bench.MAX_TRACKS, 8), dtype=torch.float64, device=dev)
 d_nout = torch.empty((S,), dtype=torch.int32, device=dev)
@@ -26,10 +26,10 @@ d_feats = torch.from_numpy(feats).to(dev) if feats is not None else None
 trk = BatchedTracker(KIND, S, max_tracks=bench.MAX_TRACKS, max_dets=bench.MAX_DETS, feat_dim=bench.W["emb"], **bench.PARAMS)
 warm = F // 2
 for f in range(warm):
-    trk.step_device(d_dets[f], d_nd[f], d_out, d_nout, d_feats=d_feats[f] if d_feats is not None else None)
+    trk.step_device(d_dets[f], d_nd[f], d_out, d_nout, d_feats=d_feats[f] if d_feats is not None else None, img_hw=bench.W['img_hw'])
 trk.phase_cycles(reset=True)          # enable + zero
 for f in range(warm, F):
-    trk.step_device(d_dets[f], d_nd[f], d_out, d_nout, d_feats=d_feats[f] if d_feats is not None else None)
+    trk.step_device(d_dets[f], d_nd[f], d_out, d_nout, d_feats=d_feats[f] if d_feats is not None else None, img_hw=bench.W['img_hw'])
 c = trk.phase_cycles()
 names = {1: "load dets/means", 2: "det+track prep, lap_prepare", 3: "cell masks", 4: "graph pass 1", 5: "solve pass 1: augmentations",
          6: "pass-2 setup", 7: "graph pass 2", 8: "deferred KF + lifecycle", 9: "lost-list scan", 10: "solve pass 2: augmentations",

@@ -177,9 +177,9 @@ class BatchedTracker:
         v["offsets"][:] = off
         if ndets is None:
             if R:
-                np.concatenate([np.asarray(d).reshape(-1, 6) for d in dets], axis=0, out=v["dets"], dtype=dtype, casting="same_kind")
+                np.concatenate([np.asarray(d).reshape(-1, 6) for d in dets], axis=0, out=v["dets"], casting="same_kind")
             if feats is not None and v["feats"] is not None and R:
-                np.concatenate([np.asarray(f).reshape(-1, self.feat_dim) for f in feats], axis=0, out=v["feats"], dtype=np.float32, casting="same_kind")
+                np.concatenate([np.asarray(f).reshape(-1, self.feat_dim) for f in feats], axis=0, out=v["feats"], casting="same_kind")
         else:
             mask = np.arange(self.max_dets)[None, :] < counts[:, None]
             v["dets"][:] = np.asarray(dets)[mask]

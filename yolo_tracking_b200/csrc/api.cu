@@ -375,8 +375,8 @@ static int launch_packed(b200track_ctx* ctx, const unsigned char* d_in, int64_t 
     p.img_h = img_h; p.img_w = img_w;
     CU_TRY(cudaMemsetAsync(d_res, 0, 16, st));                  // header: [0] capacity bits of this step
     if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
-    else if (ctx->cfg.kind == B200TRACK_BOTSORT) CU_TRY(b200::launch_botsort_step(p, ctx->variant, st));
-    else CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, ctx->variant, st));
+    else if (ctx->cfg.kind == B200TRACK_BOTSORT) CU_TRY(b200::launch_botsort_step_packed(p, ctx->variant, st));
+    else CU_TRY(b200::launch_bytetrack_step_packed(p, ctx->kf_kind, ctx->variant, st));
     ctx->launches += 1;
     return 0;
 }

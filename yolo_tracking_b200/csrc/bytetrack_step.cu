@@ -33,7 +33,14 @@
 // evaluated per candidate pair, one warp per pair, in double on the fp32 values exactly like
 // matching.py:145-167; nothing T x D x F is computed.  Embeddings live in a per-stream pool of
 // rows that never move (a slot carries its row index); rows of dead tracks are recycled.
+// This file is compiled twice: as is for the padded interface (b200track_step), and through bytetrack_step_packed.cu with
+// B200_STEP_PACKED = 1 for the packed frame interface (b200track_step_packed) - the input / output addressing is a
+// compile-time choice, so neither instantiation carries the other's registers.
 #include <cstdlib>
+
+#ifndef B200_STEP_PACKED
+#define B200_STEP_PACKED 0
+#endif
 
 #include "boxes.cuh"
 #include "kf.cuh"
@@ -554,7 +561,7 @@ bytetrack_step_kernel(const StepParams p) {
     const int* gi = p.state_i + (size_t)s * NI * TMAX;
     // packed frames: the rows of all streams lie back to back, fp32 or fp64 (step_params.h); the row offset of the stream
     // is one more dependent load, which the stream ahead prefetched to L2
-    const bool packed = p.det_off != nullptr;
+    constexpr bool packed = B200_STEP_PACKED != 0;
     int roff = 0, nd_in = 0;
     if (packed) { roff = p.det_off[s]; nd_in = p.det_off[s + 1] - roff; }
     const double* dets_g = packed ? p.dets + (size_t)roff * 6 : p.dets + (size_t)s * p.max_dets * 6;
@@ -1248,6 +1255,7 @@ cudaError_t launch_kind(const StepParams& p, int v, cudaStream_t stream) {
 
 }  // namespace
 
+#if !B200_STEP_PACKED
 int bytetrack_step_variant(int max_tracks, int max_dets) {
     for (int v = 0; v < (int)(sizeof(kVariants) / sizeof(kVariants[0])); ++v)
         if (max_tracks <= kVariants[v].tmax && max_dets <= kVariants[v].dmax) return v;
@@ -1273,5 +1281,14 @@ cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, int variant,
 cudaError_t launch_botsort_step(const StepParams& p, int variant, cudaStream_t stream) {
     return launch_kind<KF_XYWH, true>(p, variant, stream);
 }
+#else
+cudaError_t launch_bytetrack_step_packed(const StepParams& p, int kf_kind, int variant, cudaStream_t stream) {
+    return kf_kind == KF_XYWH ? launch_kind<KF_XYWH, false>(p, variant, stream) : launch_kind<KF_XYAH, false>(p, variant, stream);
+}
+
+cudaError_t launch_botsort_step_packed(const StepParams& p, int variant, cudaStream_t stream) {
+    return launch_kind<KF_XYWH, true>(p, variant, stream);
+}
+#endif
 
 }  // namespace b200

@@ -62,6 +62,9 @@ int bytetrack_step_tmax(int variant);
 size_t bytetrack_step_smem(int variant, bool botsort = false);
 cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, int variant, cudaStream_t stream);
 cudaError_t launch_botsort_step(const StepParams& p, int variant, cudaStream_t stream);
+// the same steps on packed frames (bytetrack_step_packed.cu)
+cudaError_t launch_bytetrack_step_packed(const StepParams& p, int kf_kind, int variant, cudaStream_t stream);
+cudaError_t launch_botsort_step_packed(const StepParams& p, int variant, cudaStream_t stream);
 size_t ocsort_step_smem(int variant);
 cudaError_t launch_ocsort_step(const StepParams& p, int variant, cudaStream_t stream);
 int step_variant_dmax(int variant);

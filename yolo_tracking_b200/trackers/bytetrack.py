@@ -28,8 +28,6 @@ class _SingleStreamTracker:
         self._max_dets = max_dets
         self._batch = BatchedTracker(self.kind, 1, max_tracks=max_tracks, max_dets=max_dets,
                                      device=_device_index(device), feat_dim=feat_dim, **params)
-        self._dets = np.zeros((1, max_dets, 6), dtype=np.float64)
-        self._nd = np.zeros((1,), dtype=np.int32)
         self.frame_id = 0
 
     @staticmethod
@@ -38,16 +36,22 @@ class _SingleStreamTracker:
         assert len(dets.shape) == 2, "Unsupported 'dets' dimensions, valid number of dimensions is two"
         assert dets.shape[1] == 6, "Unsupported 'dets' 2nd dimension lenght, valid lenghts is 6"
 
-    def _step(self, dets, img_hw=(0, 0), feats=None):
+    @staticmethod
+    def _as_rows(dets):
+        """float32 detections travel as float32 (widened on the device, exact); everything else as float64."""
+        return dets if dets.dtype == np.float32 else np.asarray(dets, dtype=np.float64)
+
+    def _step(self, dets, img_hw=(0, 0), feats=None, warp=None):
+        """One frame through the packed host interface: one copy in, the step, one copy of the compact rows out; a
+        capacity overflow of this very step raises here."""
         n = len(dets)
         if n > self._max_dets:
             raise ValueError(f"{n} detections exceed max_dets={self._max_dets}")
-        self._dets[0, :n] = dets
-        self._nd[0] = n
-        out, nout = self._batch.update_batch(self._dets, self._nd, feats=feats, img_hw=img_hw)
-        self._batch.sync()
+        rows = self._batch.update_frames([dets], feats=None if feats is None else [feats],
+                                         warps=None if warp is None else np.asarray(warp, dtype=np.float64).reshape(1, 6),
+                                         img_hw=img_hw, dtype=dets.dtype)[0]
         self.frame_id += 1
-        return out[0, :nout[0]].copy()
+        return rows
 
     def state(self):
         return self._batch.state(0)
@@ -69,5 +73,5 @@ class BYTETracker(_SingleStreamTracker):
 
     def update(self, dets, _=None):
         self._check(dets)
-        rows = self._step(np.asarray(dets, dtype=np.float64))
+        rows = self._step(self._as_rows(dets))
         return rows if len(rows) else np.asarray([])        # byte_tracker.py:280: empty -> shape (0,)

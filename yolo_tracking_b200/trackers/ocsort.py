@@ -23,6 +23,6 @@ class OCSort(_SingleStreamTracker):
     def update(self, dets, img):
         self._check(dets)
         h, w = img.shape[0:2] if hasattr(img, "shape") else img       # only the frame size is used (ocsort.py:239)
-        rows = self._step(np.asarray(dets, dtype=np.float64), img_hw=(h, w))
+        rows = self._step(self._as_rows(dets), img_hw=(h, w))
         self.frame_count += 1
         return rows if len(rows) else np.array([])                   # ocsort.py:379
