@@ -125,7 +125,10 @@ int b200track_wait_host(b200track_ctx* ctx, int32_t slot);   /* B200TRACK_ERR_CA
  *         ByteTrack b200track_row    40 B  x1, y1, x2, y2 (fp64), id, det_ind
  *         BoT-SORT  b200track_row_bot 48 B  + cls (the voted class, bot_sort.py:50-67), conf as fp32
  *         OC-SORT   b200track_row_oc   8 B  id, det_ind; det_ind bit 30 set = tracker created this frame (its box is
- *                   convert_x_to_bbox(convert_bbox_to_z(det)), otherwise the detection's own box)
+ *                   convert_x_to_bbox(convert_bbox_to_z(det)), otherwise the detection's own box); bit 29 set = the row
+ *                   reports the filter's box (a matched tracker whose observation sums below zero, ocsort.py:355-358):
+ *                   header[1] such rows have an entry b200track_exc_oc {row, box} in the exception area that follows
+ *                   the rows (out_off_exc, exc_capacity entries; more than that sets a capacity bit)
  * b200track_frame_layout   offsets / sizes of both blocks for n_rows detection rows.
  * b200track_step_packed    device blocks, asynchronous on `stream`.
  * b200track_submit_packed / b200track_wait_packed   HOST blocks through the 3-deep copy / step / copy pipeline (slots are
@@ -133,13 +136,15 @@ int b200track_wait_host(b200track_ctx* ctx, int32_t slot);   /* B200TRACK_ERR_CA
 typedef enum { B200TRACK_F32 = 0, B200TRACK_F64 = 1 } b200track_dtype;
 #define B200TRACK_FRAME_HAS_WARPS 1
 #define B200TRACK_ROW_OC_NEW (1 << 30)
+#define B200TRACK_ROW_OC_STATE (1 << 29)
 typedef struct { double x1, y1, x2, y2; int32_t id; int32_t det_ind; } b200track_row;
 typedef struct { double x1, y1, x2, y2; int32_t id; int32_t det_ind; float cls; float conf; } b200track_row_bot;
 typedef struct { int32_t id; int32_t det_ind; } b200track_row_oc;
+typedef struct { int32_t row; int32_t reserved; double x1, y1, x2, y2; } b200track_exc_oc;   /* row = index into the rows */
 typedef struct {
     uint64_t in_bytes, in_off_offsets, in_off_warps, in_off_dets, in_off_feats;
-    uint64_t out_bytes, out_off_nout, out_off_rows;
-    int32_t row_bytes, reserved;
+    uint64_t out_bytes, out_off_nout, out_off_rows, out_off_exc;
+    int32_t row_bytes, exc_capacity;
 } b200track_layout;
 int b200track_frame_layout(b200track_ctx* ctx, int64_t n_rows, int32_t det_dtype, b200track_layout* out);
 int b200track_step_packed(b200track_ctx* ctx, const void* d_in, int64_t n_rows, int32_t det_dtype, int32_t flags,

@@ -54,6 +54,28 @@ def test_packed_rows_equal_padded_rows(kind, cfg, fp32):
     a.close(); b.close()
 
 
+def test_packed_ocsort_rows_that_report_the_filter_box():
+    """Boxes in negative coordinates: last_observation sums below zero, so a matched tracker reports the filter's box
+    (ocsort.py:355-358) - it travels in the exception area of the result block."""
+    from yolo_tracking_b200.batch import BatchedTracker
+    S, N, F, D = 3, 20, 25, 64
+    dets, nd, _ = _inputs("ocsort", S, N, F, D, False)
+    dets = dets.copy()
+    dets[..., 0:4] -= 5000.0
+    dets[..., 0:4] *= (np.arange(D)[None, None, :, None] < nd[:, :, None, None])
+    a = BatchedTracker("ocsort", S, max_tracks=128, max_dets=D, **OC)
+    b = BatchedTracker("ocsort", S, max_tracks=128, max_dets=D, **OC)
+    flagged = 0
+    for f in range(F):
+        out, nout = a.update_batch(np.ascontiguousarray(dets[f]), np.ascontiguousarray(nd[f]), img_hw=(1080, 1920))
+        got = b.update_frames([dets[f, s, :nd[f, s]] for s in range(S)], img_hw=(1080, 1920))
+        flagged += int(b.frame_views(None, b._frame_bufs[1], int(nd[f].sum()), np.float64)["header"][1])
+        for s in range(S):
+            assert np.array_equal(got[s], out[s, :nout[s]]), (f, s)
+    assert flagged > 50
+    a.close(); b.close()
+
+
 def test_packed_bytetrack_replays_reference_golden():
     from yolo_tracking_b200.batch import BatchedTracker
     g = load_golden("bytetrack_churn")

@@ -32,7 +32,9 @@ class _HostOnly(BatchedTracker):
         L.row_bytes = {"bytetrack": 40, "botsort": 48, "ocsort": 8}[self.kind]
         L.out_off_nout = 16
         L.out_off_rows = a16(16 + 4 * S)
-        L.out_bytes = a16(L.out_off_rows + R * L.row_bytes)
+        L.out_off_exc = a16(L.out_off_rows + R * L.row_bytes)
+        L.exc_capacity = 64 + R // 128 if self.kind == "ocsort" else 0
+        L.out_bytes = a16(L.out_off_exc + L.exc_capacity * 40)
         return L
 
     def __del__(self):
@@ -43,7 +45,7 @@ def test_row_structs_match_the_header():
     assert BatchedTracker._ROW_DTYPES["bytetrack"].itemsize == 40
     assert BatchedTracker._ROW_DTYPES["botsort"].itemsize == 48
     assert BatchedTracker._ROW_DTYPES["ocsort"].itemsize == 8
-    assert C.sizeof(_lib.Layout) == 8 * 8 + 8
+    assert C.sizeof(_lib.Layout) == 9 * 8 + 8
     with open(_lib.HEADER_PATH) as f:
         text = f.read()
     for needle in ("b200track_row;", "b200track_row_bot;", "b200track_row_oc;", "B200TRACK_FRAME_HAS_WARPS 1", "(1 << 30)"):

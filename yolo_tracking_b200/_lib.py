@@ -39,12 +39,13 @@ class Layout(C.Structure):
     _fields_ = [("in_bytes", C.c_uint64), ("in_off_offsets", C.c_uint64), ("in_off_warps", C.c_uint64),
                 ("in_off_dets", C.c_uint64), ("in_off_feats", C.c_uint64),
                 ("out_bytes", C.c_uint64), ("out_off_nout", C.c_uint64), ("out_off_rows", C.c_uint64),
-                ("row_bytes", C.c_int32), ("reserved", C.c_int32)]
+                ("out_off_exc", C.c_uint64), ("row_bytes", C.c_int32), ("exc_capacity", C.c_int32)]
 
 
 F32, F64 = 0, 1
 FRAME_HAS_WARPS = 1
 ROW_OC_NEW = 1 << 30
+ROW_OC_STATE = 1 << 29
 
 _P = C.c_void_p
 _I = C.c_int32

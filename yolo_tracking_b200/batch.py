@@ -140,6 +140,8 @@ class BatchedTracker:
         "ocsort": np.dtype([("id", "<i4"), ("det_ind", "<i4")]),
     }
 
+    _EXC_DTYPE = np.dtype([("row", "<i4"), ("reserved", "<i4"), ("box", "<f8", 4)])
+
     def frame_layout(self, n_rows: int, dtype=np.float32):
         L = _lib.Layout()
         _lib.check(self._lib.b200track_frame_layout(self._ctx, int(n_rows), _lib.F32 if np.dtype(dtype) == np.float32 else _lib.F64,
@@ -210,6 +212,7 @@ class BatchedTracker:
             v["header"] = out_block[0:16].view(np.int32)
             v["nout"] = out_block[L.out_off_nout:L.out_off_nout + 4 * S].view(np.int32)
             v["rows"] = out_block[L.out_off_rows:L.out_off_rows + R * L.row_bytes].view(self._ROW_DTYPES[self.kind])
+            v["exc"] = out_block[L.out_off_exc:L.out_off_exc + L.exc_capacity * 40].view(self._EXC_DTYPE)
         return v
 
     def submit_packed(self, slot, in_block, out_block, dtype=np.float32, flags=0, img_hw=(0, 0)):
@@ -235,7 +238,7 @@ class BatchedTracker:
         first = np.repeat(off[:S].astype(np.int64), nout)
         within = np.arange(len(stream_of), dtype=np.int64) - np.repeat(np.cumsum(nout, dtype=np.int64) - nout, nout)
         r = rows[first + within]
-        di = r["det_ind"] & ~_lib.ROW_OC_NEW
+        di = r["det_ind"] & ~(_lib.ROW_OC_NEW | _lib.ROW_OC_STATE)
         src = dets[first + di].astype(np.float64, copy=False)
         out = np.empty((len(r), 8), dtype=np.float64)
         if self.kind == "ocsort":
@@ -248,6 +251,12 @@ class BatchedTracker:
                 w2 = np.sqrt(s_ * r_)
                 h2 = s_ / w2
                 out[new, 0], out[new, 1], out[new, 2], out[new, 3] = x - w2 / 2.0, y - h2 / 2.0, x + w2 / 2.0, y + h2 / 2.0
+            state = np.nonzero(r["det_ind"] & _lib.ROW_OC_STATE)[0]
+            if len(state):                              # rows that report the filter's box (ocsort.py:355-358): exception area
+                exc = v["exc"][:int(v["header"][1])]
+                where = {int(e["row"]): e["box"] for e in exc}
+                for k in state:
+                    out[k, 0:4] = where[int(first[k] + within[k])]
         else:
             out[:, 0:4] = r["box"]
         out[:, 4] = r["id"]

@@ -169,8 +169,6 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
 #define CU_TRY_CTX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return fail(B200TRACK_ERR_CUDA); } } while (0)
     CU_TRY_CTX(cudaMalloc(&p.state_f, S * ctx->nf * T * sizeof(double)));
     CU_TRY_CTX(cudaMalloc(&p.state_i, S * ctx->ni * T * sizeof(int)));
-    if (cfg->kind == B200TRACK_OCSORT)
-        CU_TRY_CTX(cudaMalloc(&p.scratch, S * T * (size_t)b200::step_variant_dmax(ctx->variant) * sizeof(double)));
     if (cfg->kind == B200TRACK_BOTSORT) {
         CU_TRY_CTX(cudaMalloc(&p.cls_hist, S * T * 9 * sizeof(double)));
         if (cfg->with_reid) {
@@ -240,7 +238,7 @@ static std::string capacity_message(int e) {
     return std::string("capacity overflow:") + ((e & B200_ERR_DET_OVERFLOW) ? " detections > max_dets" : "") +
            ((e & B200_ERR_TRACK_OVERFLOW) ? " tracks > max_tracks" : "") +
            ((e & B200_ERR_BOT_CAPACITY) ? " BoT-SORT candidate graph or class history (> 4 classes on a track)" : "") +
-           ((e & B200_ERR_PACKED_ROW) ? " OC-SORT compact row cannot carry a filter-state box (use b200track_step)" : "") +
+           ((e & B200_ERR_PACKED_ROW) ? " OC-SORT exception area of the result block is full (rows that report the filter's box)" : "") +
            "; the context's state is truncated - b200track_reset before reuse";
 }
 
@@ -344,7 +342,9 @@ extern "C" int b200track_frame_layout(b200track_ctx* ctx, int64_t n_rows, int32_
     out->row_bytes = row_bytes_of(ctx);
     out->out_off_nout = 16;
     out->out_off_rows = align16(16 + 4 * S);
-    out->out_bytes = align16(out->out_off_rows + R * (uint64_t)out->row_bytes);
+    out->out_off_exc = align16(out->out_off_rows + R * (uint64_t)out->row_bytes);
+    out->exc_capacity = ctx->cfg.kind == B200TRACK_OCSORT ? (int32_t)(64 + R / 128) : 0;
+    out->out_bytes = align16(out->out_off_exc + (uint64_t)out->exc_capacity * B200_EXC_OC_BYTES);
     return 0;
 }
 
@@ -372,6 +372,8 @@ static int launch_packed(b200track_ctx* ctx, const unsigned char* d_in, int64_t 
     p.nout = reinterpret_cast<int*>(d_res + L.out_off_nout);
     p.rows = d_res + L.out_off_rows;
     p.err_out = reinterpret_cast<int*>(d_res);
+    p.exc = d_res + L.out_off_exc;
+    p.exc_cap = L.exc_capacity;
     p.img_h = img_h; p.img_w = img_w;
     CU_TRY(cudaMemsetAsync(d_res, 0, 16, st));                  // header: [0] capacity bits of this step
     if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));

@@ -1,15 +1,27 @@
 // Dense linear assignment with lap.lapjv(cost, extend_cost=True) semantics (no cost_limit), one
-// CTA per problem.  Reference call site: boxmot/utils/association.py:20-24 (OC-SORT family).
+// CTA per problem, MATRIX-FREE: the cost of a pair is a functor evaluated from shared-memory
+// resident boxes whenever the solver needs it, the R x C matrix is never stored (at 100 x 130
+// fp64 it would be 104 KB per stream - more than a CTA's share of shared memory, and as a global
+// scratch block it was 40 % of the OC-SORT step's DRAM traffic).
+// Reference call site: boxmot/utils/association.py:20-24 (OC-SORT family).
 //
 // Without a limit lapjv pads with max(cost)+1, so an unmatched (row, column) pair costs
-// lambda = 2 * (max + 1): every min(R, C) row is matched - nothing can be pruned.  The solver
-// keeps a private "stay unmatched" column of cost lambda per row (the extended matrix without
-// its dummy block) and runs
-//   1. row reduction: u[r] = min_c cost[r][c]; the row takes its arg-min column unless a lower
+// lambda = 2 * (max + 1): every min(R, C) row is matched - nothing can be pruned from the
+// problem.  Which pairs are matched does not depend on the value of lambda once it exceeds
+// every cost by more than 2 (leaving a matchable pair unmatched can then never pay), so callers
+// may pass any upper bound of 2 * (max + 1).  The solver keeps a private "stay unmatched" column
+// of cost lambda per row (the extended matrix without its dummy block) and runs
+//   1. row reduction: u[r] = min_c cost(r, c); the row takes its arg-min column unless a lower
 //      row claimed it (dual feasible, complementary slack, free columns keep v = 0) - on
-//      tracking matrices this assigns almost every real pair at once;
-//   2. shortest augmenting paths for the rows still free: threads own columns, one block-wide
-//      arg-min per Dijkstra step.
+//      tracking matrices this assigns almost every real pair at once.  The caller computes the
+//      row minima (it can prune: see ocsort_step.cu);
+//   2. shortest augmenting paths for the rows still free (under one per frame on tracking
+//      data): thread j owns column j (distance, scanned flag and v[j] in registers), one
+//      block-wide arg-min with ONE barrier per Dijkstra step - the per-warp minima are
+//      double-buffered and every thread reduces them itself, so there is no serial section.
+//      A column whose cheap lower bound cannot improve its distance is not evaluated: after the
+//      first step of a search that is nearly every column (a matched row's dual sits ~0.9 below
+//      the bound of its non-overlapping columns).
 // On tie-free inputs the optimum is unique, hence identical to lapjv's x, y.
 #pragma once
 #include "common.cuh"
@@ -19,58 +31,32 @@ namespace b200 {
 struct DenseLap {
     double* u;              // [R]
     double* v;              // [C]
-    double* dist;           // [C]
     int* pred;              // [C]
     int* xr;                // [R]  column of row, -1 = unmatched
     int* yc;                // [C]  row of column, -1 = free
     int* claim;             // [R]
-    unsigned char* scn;     // [C]
-    double* red_v;          // [32]
-    int* red_i;             // [32]
-    double* sh_d;           // [4]  s_min, s_bestDummy
-    int* sh_i;              // [4]  s_cur, s_sink, s_bestRow
+    double* red_v;          // [2][32]
+    int* red_i;             // [2][32]
+    int* freerow;           // [R]  rows left free by the row reduction, ascending
+    unsigned long long* dbg;   // optional counters (profiling aid): [9] += searches, [10] += Dijkstra steps, [11] += cost evaluations
 };
 
-// Step 1, row reduction: u[r] = min_c cost[r][c] (capped by lambda), v = 0; a row takes its
-// arg-min column unless a lower row claimed it.  Rows are the side that must be matched or pay
-// lambda; columns may stay free, so a free column must keep v = 0 for the optimality proof -
-// which is why the reduction runs over rows (a column reduction would leave free columns with
-// v = colmin != 0).  One warp per row, lanes sweep the columns (coalesced reads of the matrix).
+// Step 1.  The caller reduced every row: w.u[r] = row minimum, w.claim[r] = its column (-1: none).
+// Rows are the side that must be matched or pay lambda; columns may stay free, so a free column must
+// keep v = 0 for the optimality proof - which is why the reduction runs over rows.
 template <int NT>
-__device__ void dense_lap_init(const DenseLap& w, const double* C, int ld, int R, int Cn, double lambda, bool have_rowmin = false) {
-    const double INF = __longlong_as_double(0x7ff0000000000000LL);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ void dense_lap_init(const DenseLap& w, int R, int Cn, double lambda) {
+    const int tid = threadIdx.x;
     for (int c = tid; c < Cn; c += NT) { w.v[c] = 0.0; w.yc[c] = -1; w.pred[c] = 0x7fffffff; }
     for (int r = tid; r < R; r += NT) w.xr[r] = -1;
     __syncthreads();
-    if (have_rowmin) {
-        // the caller reduced every row while it filled the matrix: w.u[r] = row minimum, w.claim[r] = its column
-        for (int r = tid; r < R; r += NT) {
-            const double m = w.u[r];
-            const int a = w.claim[r];
-            const bool take = a >= 0 && m <= lambda;
-            w.u[r] = take ? m : lambda;
-            w.claim[r] = take ? a : -1;
-            if (take) atomicMin(&w.pred[a], r);
-        }
-    } else {
-        for (int r = warp; r < R; r += NT / 32) {
-            double m = INF; int a = -1;
-            const double* row = C + (size_t)r * ld;
-            for (int j = lane; j < Cn; j += 32) { const double x = row[j]; if (x < m) { m = x; a = j; } }
-#pragma unroll
-            for (int d = 16; d; d >>= 1) {
-                const double om = __shfl_xor_sync(0xffffffffu, m, d);
-                const int oa = __shfl_xor_sync(0xffffffffu, a, d);
-                if (om < m || (om == m && oa >= 0 && (a < 0 || oa < a))) { m = om; a = oa; }
-            }
-            if (lane == 0) {
-                const bool take = a >= 0 && m <= lambda;
-                w.u[r] = take ? m : lambda;
-                w.claim[r] = take ? a : -1;
-                if (take) atomicMin(&w.pred[a], r);
-            }
-        }
+    for (int r = tid; r < R; r += NT) {
+        const double m = w.u[r];
+        const int a = w.claim[r];
+        const bool take = a >= 0 && m <= lambda;
+        w.u[r] = take ? m : lambda;
+        w.claim[r] = take ? a : -1;
+        if (take) atomicMin(&w.pred[a], r);
     }
     __syncthreads();
     for (int r = tid; r < R; r += NT) {
@@ -80,73 +66,101 @@ __device__ void dense_lap_init(const DenseLap& w, const double* C, int ld, int R
     __syncthreads();
 }
 
-// Step 2 for every row that is still free.
-template <int NT>
-__device__ void dense_lap_augment(const DenseLap& w, const double* C, int ld, int R, int Cn, double lambda) {
+// Step 2 for every row that is still free.  cost(r, c) must return the same bits the row reduction saw;
+// cost.lower(r, c) <= cost(r, c).
+// Needs Cn <= NT (one column per thread).
+template <int NT, class CostFn>
+__device__ void dense_lap_augment(const DenseLap& w, const CostFn& cost, int R, int Cn, double lambda) {
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i0 = 0; i0 < R; ++i0) {
-        if (w.xr[i0] >= 0) continue;            // uniform: shared memory, read after a barrier
-        for (int j = tid; j < Cn; j += NT) { w.dist[j] = INF; w.scn[j] = 0; w.pred[j] = -1; }
-        if (tid == 0) { w.sh_d[0] = 0.0; w.sh_i[0] = i0; w.sh_d[1] = INF; w.sh_i[2] = -1; w.sh_i[1] = -2; }
-        __syncthreads();
+    const int j = tid;
+    const bool mine = j < Cn;
+    int par = 0;
+    // the rows the row reduction left free, ascending (warp 0 compacts them; usually none or one)
+    int nfree = 0;
+    if (warp == 0) {
+        for (int r0 = 0; r0 < R; r0 += 32) {
+            const int r = r0 + lane;
+            const bool fr = r < R && w.xr[r] < 0;
+            const uint32_t m = __ballot_sync(0xffffffffu, fr);
+            if (fr) w.freerow[nfree + __popc(m & ((1u << lane) - 1u))] = r;
+            nfree += __popc(m);
+        }
+        if (lane == 0) w.red_i[63] = nfree;
+    }
+    __syncthreads();
+    nfree = w.red_i[63];
+    for (int f = 0; f < nfree; ++f) {
+        const int i0 = w.freerow[f];
+        if (w.dbg && tid == 0) atomicAdd(&w.dbg[9], 1ull);
+        double dist = INF;
+        bool scn = false;
+        const double vj = mine ? w.v[j] : 0.0;
+        if (mine) w.pred[j] = -1;
+        int i = i0, bestRow = -1, sink = -2;
+        double minVal = 0.0, bestDummy = INF;
         while (true) {
-            const int i = w.sh_i[0];
-            const double minVal = w.sh_d[0], ui = w.u[i];
-            double best = INF; int bj = -1;
-            for (int j = tid; j < Cn; j += NT) {
-                if (w.scn[j]) continue;
-                const double r = minVal + C[(size_t)i * ld + j] - ui - w.v[j];
-                double dj = w.dist[j];
-                if (r < dj) { dj = r; w.dist[j] = r; w.pred[j] = i; }
-                if (dj < best) { best = dj; bj = j; }
+            const double ui = w.u[i];
+            double cand = INF;
+            int cj = -1;
+            if (mine && !scn) {
+                // cost.lower(i, j) <= cost(i, j) is cheap (a bound for pairs that provably do not overlap); fp addition is
+                // monotone, so the bound below never exceeds the value it stands for and skipping is exact
+                if (minVal + cost.lower(i, j) - ui - vj < dist) {
+                    if (w.dbg) atomicAdd(&w.dbg[11], 1ull);
+                    const double r = minVal + cost(i, j) - ui - vj;
+                    if (r < dist) { dist = r; w.pred[j] = i; }
+                }
+                cand = dist; cj = j;
             }
 #pragma unroll
             for (int d = 16; d; d >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, d);
-                const int oj = __shfl_xor_sync(0xffffffffu, bj, d);
-                if (ob < best || (ob == best && oj >= 0 && (bj < 0 || oj < bj))) { best = ob; bj = oj; }
+                const double ob = __shfl_xor_sync(0xffffffffu, cand, d);
+                const int oj = __shfl_xor_sync(0xffffffffu, cj, d);
+                if (ob < cand || (ob == cand && oj >= 0 && (cj < 0 || oj < cj))) { cand = ob; cj = oj; }
             }
-            if (lane == 0) { w.red_v[warp] = best; w.red_i[warp] = bj; }
+            if (lane == 0) { w.red_v[par * 32 + warp] = cand; w.red_i[par * 32 + warp] = cj; }
+            if (w.dbg && tid == 0) atomicAdd(&w.dbg[10], 1ull);
             __syncthreads();
-            if (tid == 0) {
-                double b = w.red_v[0]; int j = w.red_i[0];
-                for (int k = 1; k < NT / 32; ++k)
-                    if (w.red_v[k] < b || (w.red_v[k] == b && w.red_i[k] >= 0 && (j < 0 || w.red_i[k] < j))) { b = w.red_v[k]; j = w.red_i[k]; }
-                const double dd = minVal + lambda - ui;         // row i may stay unmatched
-                if (dd < w.sh_d[1]) { w.sh_d[1] = dd; w.sh_i[2] = i; }
-                if (j < 0 || w.sh_d[1] <= b) { w.sh_i[1] = -1; w.sh_d[0] = w.sh_d[1]; }
-                else {
-                    w.sh_d[0] = b; w.scn[j] = 1;
-                    if (w.yc[j] < 0) w.sh_i[1] = j; else w.sh_i[0] = w.yc[j];
-                }
+            double b = w.red_v[par * 32];
+            int bj = w.red_i[par * 32];
+#pragma unroll
+            for (int k = 1; k < NW; ++k) {
+                const double ob = w.red_v[par * 32 + k];
+                const int oj = w.red_i[par * 32 + k];
+                if (ob < b || (ob == b && oj >= 0 && (bj < 0 || oj < bj))) { b = ob; bj = oj; }
             }
-            __syncthreads();
-            if (w.sh_i[1] != -2) break;
+            par ^= 1;
+            const double dd = minVal + lambda - ui;         // row i may stay unmatched
+            if (dd < bestDummy) { bestDummy = dd; bestRow = i; }
+            if (bj < 0 || bestDummy <= b) { sink = -1; minVal = bestDummy; break; }
+            minVal = b;
+            if (j == bj) scn = true;
+            const int owner = w.yc[bj];                     // not modified during a search
+            if (owner < 0) { sink = bj; break; }
+            i = owner;
         }
-        const double minVal = w.sh_d[0];
-        const int sink = w.sh_i[1];
-        for (int j = tid; j < Cn; j += NT) {
-            if (!w.scn[j]) continue;
-            const double delta = minVal - w.dist[j];
+        if (mine && scn) {
+            const double delta = minVal - dist;
             const int r = w.yc[j];
             if (r >= 0) w.u[r] += delta;
-            w.v[j] -= delta;
+            w.v[j] = vj - delta;
         }
         __syncthreads();
         if (tid == 0) {
             w.u[i0] += minVal;
-            int j = -1;
+            int c = -1;
             bool go = true;
-            if (sink >= 0) j = sink;
-            else if (w.sh_i[2] == i0) go = false;
-            else { j = w.xr[w.sh_i[2]]; w.xr[w.sh_i[2]] = -1; }
+            if (sink >= 0) c = sink;
+            else if (bestRow == i0) go = false;
+            else { c = w.xr[bestRow]; w.xr[bestRow] = -1; }
             while (go) {
-                const int r = w.pred[j];
-                w.yc[j] = r;
+                const int r = w.pred[c];
+                w.yc[c] = r;
                 const int t = w.xr[r];
-                w.xr[r] = j;
-                j = t;
+                w.xr[r] = c;
+                c = t;
                 if (r == i0) break;
             }
         }

@@ -34,8 +34,7 @@
 #define B200_ERR_DET_OVERFLOW 1
 #define B200_ERR_TRACK_OVERFLOW 2
 #define B200_ERR_BOT_CAPACITY 4     // BoT-SORT: candidate graph overflow or more than 4 classes voted on one track
-#define B200_ERR_PACKED_ROW 8       // OC-SORT compact rows: a matched tracker whose last observation sums below zero reports its
-                                    // filter box (ocsort.py:355-358), which an (id, det_ind) row cannot carry - use b200track_step
+#define B200_ERR_PACKED_ROW 8       // OC-SORT compact rows: more filter-box rows than the exception area of the result block holds
 
 // BoT-SORT contexts carry one more int32 component per slot: the row of the track in the stream's
 // embedding pool feat_pool[(s * Tmax + row) * feat_dim] (fp32) and class-vote table
@@ -53,6 +52,10 @@
 // OC-SORT compact rows: det_ind bit 30 = row of a tracker created this frame (its box is the detection's round trip
 // convert_x_to_bbox(convert_bbox_to_z(det)), ocsort.py:354-360 with the placeholder last_observation)
 #define B200_ROW_OC_NEW (1 << 30)
+// det_ind bit 29 = the row reports the filter's box, carried by an entry {int32 row, int32 0, double box[4]} of the
+// exception area behind the rows (ocsort.py:355-358: last_observation sums below zero)
+#define B200_ROW_OC_STATE (1 << 29)
+#define B200_EXC_OC_BYTES 40
 
 // bytes a track slot occupies in HBM (one direction)
 #define B200_SLOT_BYTES (B200_NF * 8 + B200_NI * 4)

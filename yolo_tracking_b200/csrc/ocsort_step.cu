@@ -14,11 +14,17 @@
 //
 // Unlike ByteTrack the assignment is DENSE: lapjv is called without a cost limit on
 // -(similarity + angle cost), every min(D, T) row is matched and pairs are filtered by the
-// similarity threshold afterwards, so nothing can be pruned.  The D x T cost matrix of a stream
-// is written once to a per-stream scratch block (L2 resident), one warp per detection row with
-// the row minimum reduced in registers, then solved by lap_dense.cuh.  Slots are updated in
-// place; a tracker that dies leaves a hole and the stream is compacted only when its slot range
-// runs short.
+// similarity threshold afterwards, so no pair can be dropped from the problem.  But the matrix
+// is never stored (lap_dense.cuh is matrix-free: a cost is re-evaluated from the shared-memory
+// resident boxes when the solver asks for it), and the row reduction that starts the solver
+// does not evaluate it in full either: for iou / giou a disjoint pair has similarity exactly 0
+// and the direction term is bounded by |inertia| * conf / 2, so once the best cost among the
+// OVERLAPPING columns of a row (one to three, found by a conservative fp32 test) lies below
+// that bound no other column can be the row minimum; only rows without such a column (new
+// objects, false positives) are evaluated in full.  Slots are updated in place; a tracker
+// that dies leaves a hole and the stream is compacted only when its slot range runs short.
+#include <cstdlib>
+
 #include "boxes.cuh"
 #include "lap_dense.cuh"
 #include "layout.h"
@@ -34,23 +40,37 @@ constexpr double TIE_EPS = 8.8817841970012523e-16;
 
 template <int TMAX, int DMAX>
 struct alignas(16) OcSmem {
-    double x[7][TMAX];
     double tbox[4][TMAX];           // predicted box, convert_x_to_bbox
     double lbox[4][TMAX];           // last_observation box (placeholder -1)
     double kc[2][TMAX];             // centre of k_previous_obs
     double vel[2][TMAX];            // (vy, vx)
     double dbox[4][DMAX];
-    double dconf[DMAX], dcls[DMAX];
-    double u[DMAX], v[TMAX], dist[TMAX];
-    double red_v[32], sh_d[4];
+    double dconf[DMAX];
+    double u[DMAX], v[TMAX];
+    double red_v[64];
     unsigned long long scratch[40];
+    // candidate pairs of the first association (boxes that overlap): row-major segments, exact cost per pair
+    static constexpr int PCAP = 3 * DMAX;
+    double pcost[PCAP];
+    uint32_t ppair[PCAP];           // (row << 16) | column
+    int segstart[DMAX];
+    short segcnt[DMAX];             // -1: the row's candidates did not fit (evaluated in full instead)
     int pred[TMAX], xr[DMAX], yc[TMAX], claim[DMAX], partner[TMAX];
-    int red_i[32], sh_i[4];
+    int red_i[64];
     int rowcnt[DMAX], rowmatch[DMAX], colcnt[TMAX];
     int misc[8];
     short hd[DMAX], ht[TMAX], dmatch[DMAX], tmatch[TMAX], ud[DMAX], ut[TMAX];
-    unsigned char scn[TMAX], kvalid[TMAX], alive[TMAX], dstate[DMAX];
+    float4 cboxf[TMAX];             // predicted box of COLUMN c rounded outwards to fp32 (irregular boxes: everything), step A
+    double dred[8 * (TMAX / 32)];   // per (row, column chunk) minima of the rows evaluated in full
+    int ired[8 * (TMAX / 32)];
+    unsigned char kvalid[TMAX], alive[TMAX], dstate[DMAX], tdeg[TMAX], ddeg[DMAX], rowfull[DMAX];
 };
+
+// a box the pruning rules may reason about: positive, finite extent (everything else is evaluated in full)
+__device__ __forceinline__ bool oc_regular_box(double x1, double y1, double x2, double y2) {
+    const double w = x2 - x1, h = y2 - y1;
+    return w > 0.0 && h > 0.0 && w < 1e100 && h < 1e100 && fabs(x1) < 1e100 && fabs(y1) < 1e100;
+}
 
 __device__ __forceinline__ Box oc_x_to_box(double x, double y, double s, double r) {
     const double w = sqrt(xmul(s, r));
@@ -99,19 +119,18 @@ __device__ __forceinline__ double oc_acos(double x) {
     const bool big = ax > 0.5;
     const double z = big ? (1.0 - ax) * 0.5 : x * x;
     const double s = big ? sqrt(z) : ax;
-    double g = 0.028757851367421566;
-    g = fma(g, z, -0.014851887071247204);
-    g = fma(g, z, 0.01740087944269402);
-    g = fma(g, z, 0.005457506718640358);
-    g = fma(g, z, 0.01032281435018578);
-    g = fma(g, z, 0.011479177415184906);
-    g = fma(g, z, 0.013971212973552933);
-    g = fma(g, z, 0.017352392720869973);
-    g = fma(g, z, 0.02237217294214989);
-    g = fma(g, z, 0.030381944138531247);
-    g = fma(g, z, 0.04464285714635543);
-    g = fma(g, z, 0.07499999999998433);
-    g = fma(g, z, 0.16666666666666669);
+    // degree-12 polynomial in z, Estrin's scheme: 5 dependent fma levels instead of Horner's 12 (a cost evaluation is
+    // latency bound: the solver and the row reduction wait for single evaluations)
+    const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    const double p01 = fma(0.07499999999998433, z, 0.16666666666666669);
+    const double p23 = fma(0.030381944138531247, z, 0.04464285714635543);
+    const double p45 = fma(0.017352392720869973, z, 0.02237217294214989);
+    const double p67 = fma(0.011479177415184906, z, 0.013971212973552933);
+    const double p89 = fma(0.005457506718640358, z, 0.01032281435018578);
+    const double pab = fma(-0.014851887071247204, z, 0.01740087944269402);
+    const double q0 = fma(p23, z2, p01), q1 = fma(p67, z2, p45), q2 = fma(pab, z2, p89);
+    const double h0 = fma(q1, z4, q0), h1 = fma(0.028757851367421566, z4, q2);
+    const double g = fma(h1, z8, h0);
     const double r = fma(s * z, g, s);                     // asin(s)
     return big ? (x > 0.0 ? 2.0 * r : PI - 2.0 * r) : HALF_PI - copysign(r, x);
 }
@@ -186,11 +205,57 @@ __device__ __forceinline__ void oc_correct(OcKf& k, const double* z) {
     }
 }
 
+// Cost of (row r = high detection hd[r], column c = live tracker ht[c]) in the first association,
+// association.py:130-172: -(similarity + direction term) plus the canonical tie-break.  The row reduction and the
+// solver evaluate it through this one object, so they see the same bits.
+template <class SM>
+struct OcCost1 {
+    const SM& sm;
+    int func, Cn;
+    double W, H, inertia;
+    bool sparse;                    // iou / giou with a non-negative threshold: a disjoint pair has similarity exactly +0.0
+    __device__ __forceinline__ Box dbox(int j) const { return Box{sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]}; }
+    __device__ __forceinline__ Box tbox(int sl) const { return Box{sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]}; }
+    // |direction term| + ties of a row, rounded up
+    __device__ __forceinline__ double bound(int j) const { return xmul(0.5, fabs(xmul(inertia, sm.dconf[j]))) + 1e-6; }
+    // provably similarity-free pair: regular boxes that do not overlap
+    __device__ __forceinline__ bool free_pair(int j, int sl) const {
+        return sparse && !sm.ddeg[j] && !sm.tdeg[sl] && !box_overlap(dbox(j), tbox(sl));
+    }
+    __device__ __forceinline__ double sim(int r, int c) const { return oc_sim(func, dbox(sm.hd[r]), tbox(sm.ht[c]), W, H); }
+    __device__ __forceinline__ double from_sim(int r, int c, double sv) const {
+        const int j = sm.hd[r], sl = sm.ht[c];
+        double ang = 0.0;
+        const double vy = sm.vel[0][sl], vx = sm.vel[1][sl];
+        if (sm.kvalid[sl] && !(vx == 0.0 && vy == 0.0))
+            ang = oc_angle(vy, vx, sm.kc[0][sl], sm.kc[1][sl], true, xdiv(xadd(sm.dbox[0][j], sm.dbox[2][j]), 2.0),
+                           xdiv(xadd(sm.dbox[1][j], sm.dbox[3][j]), 2.0), inertia, sm.dconf[j]);
+        return xadd(-xadd(xadd(sv, ang), 0.0), xmul((double)(r * Cn + c), TIE_EPS));
+    }
+    // A pair that is not similarity-free went through the pair list (same test) unless its row overflowed it: the
+    // solver then reads the cost the row reduction computed instead of paying a second ~3000-cycle evaluation - after
+    // the first step of a search every evaluation is such a pair.
+    __device__ __forceinline__ double operator()(int r, int c) const {
+        const int j = sm.hd[r], sl = sm.ht[c];
+        if (free_pair(j, sl)) return from_sim(r, c, 0.0);
+        if (sparse) {
+            const int n = sm.segcnt[r], b0 = sm.segstart[r];
+            for (int k = 0; k < n; ++k)
+                if ((int)(sm.ppair[b0 + k] & 0xffff) == c) return sm.pcost[b0 + k];
+        }
+        return from_sim(r, c, sim(r, c));
+    }
+    __device__ __forceinline__ double lower(int r, int c) const {
+        const int j = sm.hd[r];
+        return free_pair(j, sm.ht[c]) ? -bound(j) : -__longlong_as_double(0x7ff0000000000000LL);
+    }
+};
+
 template <int NT, class SM>
 __device__ __forceinline__ DenseLap make_dense(SM& sm) {
     DenseLap w;
-    w.u = sm.u; w.v = sm.v; w.dist = sm.dist; w.pred = sm.pred; w.xr = sm.xr; w.yc = sm.yc; w.claim = sm.claim;
-    w.scn = sm.scn; w.red_v = sm.red_v; w.red_i = sm.red_i; w.sh_d = sm.sh_d; w.sh_i = sm.sh_i;
+    w.u = sm.u; w.v = sm.v; w.pred = sm.pred; w.xr = sm.xr; w.yc = sm.yc; w.claim = sm.claim;
+    w.red_v = sm.red_v; w.red_i = sm.red_i; w.freerow = sm.rowmatch; w.dbg = nullptr;
     return w;
 }
 
@@ -227,7 +292,8 @@ ocsort_step_kernel(const StepParams p) {
     long long ph_last = p.dbg ? clock64() : 0;
 #define PHASE(k) do { if (p.dbg && tid == 0) { const long long now_ = clock64(); atomicAdd(&p.dbg[k], (unsigned long long)(now_ - ph_last)); ph_last = now_; } } while (0)
     int* counts = p.counts + 4 * s;
-    const int n0 = counts[0], id0 = counts[2], frame = counts[3] + 1;
+    int n0 = counts[0];
+    const int alive0 = counts[1], id0 = counts[2], frame = counts[3] + 1;
     const bool packed = p.det_off != nullptr;          // packed frames (step_params.h)
     int roff = 0;
     if (packed) roff = p.det_off[s];
@@ -239,7 +305,40 @@ ocsort_step_kernel(const StepParams p) {
     if (nd < 0) nd = 0;
     double* gf = p.state_f + (size_t)s * B200_OC_NF * TMAX;
     int* gi = p.state_i + (size_t)s * B200_OC_NI * TMAX;
-    double* C = p.scratch + (size_t)s * TMAX * DMAX;
+    // ---- compaction on demand: dead trackers leave holes in the slot range; the live ones move down (order kept) only
+    // when this frame's detections - an upper bound of its new trackers - might not fit behind the range otherwise
+    // (every ~10-20 frames at config 2; doing it whenever the range passed max_tracks - max_dets meant every frame)
+    if (n0 > alive0 && n0 + nd > tcap) {                 // uniform
+        bool lv = false;
+        if (t < n0) lv = gi[B200_OCI_FLAGS * TMAX + t] & OCF_ALIVE;
+        unsigned long long tt;
+        const int dst = (int)block_exscan<NT>(lv ? 1ull : 0ull, sm.scratch, tt);
+        for (int c0 = 0; c0 < B200_OC_NF; c0 += 8) {
+            double tmp[8];
+            if (lv && dst != t) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c0 + c < B200_OC_NF) tmp[c] = gf[(c0 + c) * TMAX + t];
+            }
+            __syncthreads();
+            if (lv && dst != t) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c0 + c < B200_OC_NF) gf[(c0 + c) * TMAX + dst] = tmp[c];
+            }
+            __syncthreads();
+        }
+        int itmp[B200_OC_NI];
+        if (lv && dst != t) {
+#pragma unroll
+            for (int c = 0; c < B200_OC_NI; ++c) itmp[c] = gi[c * TMAX + t];
+        }
+        __syncthreads();
+        if (lv && dst != t) {
+#pragma unroll
+            for (int c = 0; c < B200_OC_NI; ++c) gi[c * TMAX + dst] = itmp[c];
+        }
+        __syncthreads();
+        n0 = (int)tt;
+    }
     const double thr = p.iou_thresh, W = p.img_w, H = p.img_h;
     const int func = p.asso_func;
 
@@ -257,9 +356,16 @@ ocsort_step_kernel(const StepParams p) {
             }
             const char* f2 = reinterpret_cast<const char*>(p.state_f + (size_t)s2 * B200_OC_NF * TMAX);
             const char* i2 = reinterpret_cast<const char*>(p.state_i + (size_t)s2 * B200_OC_NI * TMAX);
-            const int nl_f = (B200_OC_SX * TMAX * 8 + 127) >> 7, nl_i = (B200_OC_NI * TMAX * 4 + 127) >> 7;
+            // only the slot range in use of every hot component row (a row is TMAX slots long; prefetching whole rows read
+            // twice the state from DRAM)
+            const int r2 = min(p.counts[4 * s2], TMAX);
+            const int lf = (r2 * 8 + 127) >> 7, li = (r2 * 4 + 127) >> 7;            // lines per fp64 / int32 component row
+            const int nl_f = B200_OC_SX * lf, nl_i = B200_OC_NI * li;
             for (int l = tid; l < nl_d + nl_f + nl_i; l += NT) {
-                const char* a = l < nl_d ? d2 + ((size_t)l << 7) : (l < nl_d + nl_f ? f2 + ((size_t)(l - nl_d) << 7) : i2 + ((size_t)(l - nl_d - nl_f) << 7));
+                const char* a;
+                if (l < nl_d) a = d2 + ((size_t)l << 7);
+                else if (l < nl_d + nl_f) { const int q = l - nl_d, c = q / lf; a = f2 + (size_t)c * TMAX * 8 + ((size_t)(q - c * lf) << 7); }
+                else { const int q = l - nl_d - nl_f, c = q / li; a = i2 + (size_t)c * TMAX * 4 + ((size_t)(q - c * li) << 7); }
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
             }
         }
@@ -273,9 +379,12 @@ ocsort_step_kernel(const StepParams p) {
             const int j = i / 6, c = i - 6 * j;
             if (c < 4) sm.dbox[c][j] = val;
             else if (c == 4) sm.dconf[j] = val;
-            else sm.dcls[j] = val;
         }
     }
+    // the class column is only read for matched / new trackers, straight from the detection row (L2)
+    const double* dets_g = packed ? p.dets + (size_t)roff * 6 : p.dets + (size_t)s * p.max_dets * 6;
+    const float* dets32_g = p.dets32 ? p.dets32 + (size_t)roff * 6 : nullptr;
+    auto det_cls = [&](int j) -> double { return dets32_g ? (double)dets32_g[j * 6 + 5] : dets_g[j * 6 + 5]; };
     int fl = 0, age = 0, tsu = 0, streak = 0;
     bool live = false;
     if (t < n0) {
@@ -296,10 +405,11 @@ ocsort_step_kernel(const StepParams p) {
         age += 1;
         if (tsu > 0) streak = 0;
         tsu += 1;
-#pragma unroll
-        for (int c = 0; c < 7; ++c) sm.x[c][t] = x[c];
+        // the predicted state itself is only needed again by this thread after the association: it is re-derived from
+        // the same (L2-resident) loads there instead of occupying 7 x TMAX doubles of shared memory
         const Box b = oc_x_to_box(x[0], x[1], x[2], x[3]);
         sm.tbox[0][t] = b.x1; sm.tbox[1][t] = b.y1; sm.tbox[2][t] = b.x2; sm.tbox[3][t] = b.y2;
+        sm.tdeg[t] = !oc_regular_box(b.x1, b.y1, b.x2, b.y2);
         if (isnan(b.x1) || isnan(b.y1) || isnan(b.x2) || isnan(b.y2)) { live = false; fl &= ~OCF_ALIVE; }   // :260-264
         const bool hasobs = fl & B200_OCF_HASOBS;
         double l[4] = {-1.0, -1.0, -1.0, -1.0};
@@ -351,33 +461,135 @@ ocsort_step_kernel(const StepParams p) {
     PHASE(2);
 
     // ---- first round: associate(dets, trks, ...) ------------------------------------------------
+    if (tid < DMAX && tid < nd) sm.ddeg[tid] = !oc_regular_box(sm.dbox[0][tid], sm.dbox[1][tid], sm.dbox[2][tid], sm.dbox[3][tid]);
+    OcCost1<SM> cost1{sm, func, Cn, W, H, p.inertia, func <= 1 && thr >= 0.0};
     if (R > 0 && Cn > 0) {
-        double mx = -1e300;
-        if (tid < Cn) sm.colcnt[tid] = 0;
+        const int lane = tid & 31, warp = tid >> 5;
+        const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        constexpr int NCH = TMAX / 32;
+        double amax = 0.0;                           // bound of the direction term over the rows
+        if (tid < Cn) {
+            sm.colcnt[tid] = 0;
+            const int sl = sm.ht[tid];
+            const float FINF = __int_as_float(0x7f800000);
+            sm.cboxf[tid] = sm.tdeg[sl] ? make_float4(-FINF, -FINF, FINF, FINF)
+                                        : make_float4(__double2float_rd(sm.tbox[0][sl]), __double2float_rd(sm.tbox[1][sl]),
+                                                      __double2float_ru(sm.tbox[2][sl]), __double2float_ru(sm.tbox[3][sl]));
+        }
+        if (tid == 0) { sm.misc[0] = 0; sm.misc[1] = SM::PCAP; }
         __syncthreads();
-        {   // one warp per detection row, lanes across the tracker columns: the row minimum (the start of the
-            // assignment, lap_dense.cuh step 1) falls out of the fill as a warp reduction instead of a second pass
-            const int lane = tid & 31, warp = tid >> 5;
-            const double INF = __longlong_as_double(0x7ff0000000000000LL);
+        // Row reduction (lap_dense.cuh step 1) without evaluating the matrix:
+        //   A. one warp per row marks the columns whose box may overlap the row's and appends them to the pair list (one
+        //      segment per row);
+        //   B. one thread per pair: similarity, threshold counts for the permutation shortcut, exact cost;
+        //   C. one thread per row: minimum over its segment; if it is below -bound(row) no column outside the segment
+        //      (similarity exactly 0, |direction term| <= bound) can be the row minimum;
+        //   D. the remaining rows (new objects, false positives; or every row for diou / ciou / centroid, whose similarity
+        //      is dense) are evaluated in full, one warp per row.
+        if (cost1.sparse) {
             for (int r = warp; r < R; r += NT / 32) {
                 const int j = sm.hd[r];
-                const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
-                const double dcx = xdiv(xadd(db.x1, db.x2), 2.0), dcy = xdiv(xadd(db.y1, db.y2), 2.0), dconf = sm.dconf[j];
+                // conservative fp32 test (boxes rounded outwards; an irregular box overlaps everything): a superset of the
+                // pairs the exact test of free_pair() keeps - a pair listed needlessly is evaluated exactly all the same
+                const float FINF = __int_as_float(0x7f800000);
+                const bool ddeg = sm.ddeg[j];
+                const float dx1 = ddeg ? -FINF : __double2float_rd(sm.dbox[0][j]), dy1 = ddeg ? -FINF : __double2float_rd(sm.dbox[1][j]);
+                const float dx2 = ddeg ? FINF : __double2float_ru(sm.dbox[2][j]), dy2 = ddeg ? FINF : __double2float_ru(sm.dbox[3][j]);
+                uint32_t bits[NCH];
+                int total = 0;
+#pragma unroll
+                for (int k = 0; k < NCH; ++k) {
+                    const int c = k * 32 + lane;
+                    bool cand = false;
+                    if (k * 32 < Cn && c < Cn) {
+                        const float4 tf = sm.cboxf[c];
+                        cand = (tf.x < dx2) & (dx1 < tf.z) & (tf.y < dy2) & (dy1 < tf.w);
+                    }
+                    bits[k] = __ballot_sync(0xffffffffu, cand);
+                    total += __popc(bits[k]);
+                }
+                int base = 0;
+                if (lane == 0 && total) base = atomicAdd(&sm.misc[0], total);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const bool fits = base + total <= SM::PCAP;
+                if (fits) {
+#pragma unroll
+                    for (int k = 0; k < NCH; ++k) {
+                        if (bits[k]) {                        // uniform
+                            if (bits[k] & (1u << lane)) sm.ppair[base + __popc(bits[k] & ((1u << lane) - 1u))] = ((uint32_t)r << 16) | (uint32_t)(k * 32 + lane);
+                            base += __popc(bits[k]);
+                        }
+                    }
+                    base -= total;
+                }
+                if (lane == 0) {
+                    sm.segstart[r] = base; sm.segcnt[r] = fits ? (short)total : (short)-1;
+                    if (!fits) atomicMin(&sm.misc[1], base);      // bases only grow: every entry below the first overflow is written
+                }
+            }
+            __syncthreads();
+            const int np = min(sm.misc[0], sm.misc[1]);
+            for (int k = tid; k < np; k += NT) {
+                const uint32_t pr = sm.ppair[k];
+                const int r = pr >> 16, c = pr & 0xffff;
+                const double sv = cost1.sim(r, c);
+                if (sv > thr) { atomicAdd(&sm.colcnt[c], 1); atomicAdd(&sm.rowcnt[r], 1); sm.rowmatch[r] = c; }
+                sm.pcost[k] = cost1.from_sim(r, c, sv);
+            }
+            __syncthreads();
+            if (tid < R) {
+                const int r = tid, n = sm.segcnt[r], b0 = sm.segstart[r];
+                const double bound = cost1.bound(sm.hd[r]);
+                amax = bound;
                 double m = INF;
                 int a = -1;
-                for (int c = lane; c < Cn; c += 32) {
+                for (int k = 0; k < n; ++k) {
+                    const double cst = sm.pcost[b0 + k];
+                    const int c = sm.ppair[b0 + k] & 0xffff;
+                    if (cst < m || (cst == m && c < a)) { m = cst; a = c; }
+                }
+                sm.u[r] = m; sm.claim[r] = a;
+                sm.rowfull[r] = n < 0 ? 2 : (m < -bound ? 0 : 1);     // 2: nothing of the row was evaluated yet
+            }
+        } else if (tid < R) {
+            sm.rowfull[tid] = 2;
+            amax = cost1.bound(sm.hd[tid]);
+        }
+        __syncthreads();
+        // D: tasks = (row to evaluate in full, chunk of 32 columns), dealt over the warps - an evaluation is ~3000 cycles of
+        // dependent fp64 work, so a warp walking all chunks of its row would serialise them.  Task results meet in pcost /
+        // ppair (the pair list is dead for these rows: mode 1 rows keep theirs, and their tasks skip the listed columns).
+        int nfull = 0;
+        if (warp == 0) {
+            for (int r0 = 0; r0 < R; r0 += 32) {
+                const int r = r0 + lane;
+                const bool fr = r < R && sm.rowfull[r] != 0;
+                const uint32_t mk = __ballot_sync(0xffffffffu, fr);
+                if (fr) sm.partner[nfull + __popc(mk & ((1u << lane) - 1u))] = r;
+                nfull += __popc(mk);
+            }
+            if (lane == 0) sm.misc[2] = nfull;
+        }
+        __syncthreads();
+        nfull = sm.misc[2];
+        const int nch = (Cn + 31) >> 5;
+        for (int f0 = 0; f0 < nfull; f0 += 8) {           // 8 rows per round: their chunk results fit the scratch below
+            const int nf = min(8, nfull - f0);
+            for (int task = warp; task < nf * nch; task += NT / 32) {
+                const int fi = task / nch, k = task - fi * nch;
+                const int r = sm.partner[f0 + fi], mode = sm.rowfull[r], j = sm.hd[r];
+                const int c = k * 32 + lane;
+                double m = INF;
+                int a = -1;
+                if (c < Cn) {
                     const int sl = sm.ht[c];
-                    const Box tb = {sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]};
-                    const double sim = oc_sim(func, db, tb, W, H);
-                    double ang = 0.0;
-                    const double vy = sm.vel[0][sl], vx = sm.vel[1][sl];
-                    if (sm.kvalid[sl] && !(vx == 0.0 && vy == 0.0))
-                        ang = oc_angle(vy, vx, sm.kc[0][sl], sm.kc[1][sl], true, dcx, dcy, p.inertia, dconf);
-                    const double cst = xadd(-xadd(xadd(sim, ang), 0.0), xmul((double)(r * Cn + c), TIE_EPS));
-                    C[(size_t)r * TMAX + c] = cst;
-                    mx = fmax(mx, cst);
-                    if (cst < m) { m = cst; a = c; }
-                    if (sim > thr) { atomicAdd(&sm.colcnt[c], 1); atomicAdd(&sm.rowcnt[r], 1); sm.rowmatch[r] = c; }
+                    const bool fp = cost1.free_pair(j, sl);
+                    if (mode == 2 || fp) {                // mode 1: the other columns went through the pair list
+                        const double sv = fp ? 0.0 : cost1.sim(r, c);
+                        if (sv > thr) { atomicAdd(&sm.colcnt[c], 1); atomicAdd(&sm.rowcnt[r], 1); sm.rowmatch[r] = c; }
+                        m = cost1.from_sim(r, c, sv);
+                        a = c;
+                    }
                 }
 #pragma unroll
                 for (int d = 16; d; d >>= 1) {
@@ -385,24 +597,38 @@ ocsort_step_kernel(const StepParams p) {
                     const int oa = __shfl_xor_sync(0xffffffffu, a, d);
                     if (om < m || (om == m && oa >= 0 && (a < 0 || oa < a))) { m = om; a = oa; }
                 }
-                if (lane == 0) { sm.u[r] = m; sm.claim[r] = a; }
+                if (lane == 0) { sm.dred[fi * NCH + k] = m; sm.ired[fi * NCH + k] = a; }
             }
+            __syncthreads();
+            if (tid < nf) {
+                const int r = sm.partner[f0 + tid], mode = sm.rowfull[r];
+                double m = mode == 1 ? sm.u[r] : INF;
+                int a = mode == 1 ? sm.claim[r] : -1;
+                for (int k = 0; k < nch; ++k) {
+                    const double om = sm.dred[tid * NCH + k];
+                    const int oa = sm.ired[tid * NCH + k];
+                    if (oa >= 0 && (om < m || (om == m && (a < 0 || oa < a)))) { m = om; a = oa; }
+                }
+                sm.u[r] = m; sm.claim[r] = a;
+            }
+            __syncthreads();
         }
         __syncthreads();
         PHASE(3);
         int ccnt = tid < Cn ? sm.colcnt[tid] : 0;
         int rc = tid < R ? sm.rowcnt[tid] : 0;
-        block_max3<NT>(sm, mx, ccnt, rc);
+        block_max3<NT>(sm, amax, ccnt, rc);
         const bool shortcut = (rc == 1 && ccnt == 1);                          // association.py:157-159
         if (shortcut) {
             if (tid < R) sm.xr[tid] = sm.rowcnt[tid] == 1 ? sm.rowmatch[tid] : -1;
             __syncthreads();
         } else {
-            const DenseLap w = make_dense<NT>(sm);
-            const double lambda = 2.0 * (mx + 1.0);
-            dense_lap_init<NT>(w, C, TMAX, R, Cn, lambda, true);
+            DenseLap w = make_dense<NT>(sm);
+            w.dbg = p.dbg;
+            const double lambda = 2.0 * (amax + 1.0);          // >= lapjv's 2 * (max cost + 1): same assignment (lap_dense.cuh)
+            dense_lap_init<NT>(w, R, Cn, lambda);
             PHASE(4);
-            dense_lap_augment<NT>(w, C, TMAX, R, Cn, lambda);
+            dense_lap_augment<NT>(w, cost1, R, Cn, lambda);
         }
         PHASE(5);
         // matched pairs below the similarity threshold fall back to unmatched (association.py:187-193)
@@ -426,36 +652,55 @@ ocsort_step_kernel(const StepParams p) {
     // rows = sm.ud[0..nr), columns = sm.ut[0..nc) (slot indices); boxes of the columns: predicted or last observed.
     auto second_round = [&](int nr, int nc, bool last_boxes) -> bool {
         if (nr <= 0 || nc <= 0) return false;                        // uniform
-        double mx = -1e300, smax = -1e300;
-        int d1 = 0, d2 = 0;
         const double (*bx)[TMAX] = last_boxes ? sm.lbox : sm.tbox;
-        if (tid < nc) {
-            const int sl = sm.ut[tid];
+        auto sim2 = [&](int r, int c) -> double {
+            const int j = sm.ud[r], sl = sm.ut[c];
             const Box tb = {bx[0][sl], bx[1][sl], bx[2][sl], bx[3][sl]};
-            for (int r = 0; r < nr; ++r) {
-                const int j = sm.ud[r];
-                const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
-                const double sim = oc_sim(func, db, tb, W, H);
-                const double c = xadd(-sim, xmul((double)(r * nc + tid), TIE_EPS));
-                C[(size_t)r * TMAX + tid] = c;
-                mx = fmax(mx, c);
-                smax = fmax(smax, sim);
+            const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
+            return oc_sim(func, db, tb, W, H);
+        };
+        struct Cost2 {
+            decltype(sim2)& sim;
+            int nc;
+            __device__ __forceinline__ double operator()(int r, int c) const { return xadd(-sim(r, c), xmul((double)(r * nc + c), TIE_EPS)); }
+            __device__ __forceinline__ double lower(int, int) const { return -__longlong_as_double(0x7ff0000000000000LL); }
+        } cost2{sim2, nc};
+        // row reduction in full (these problems are small and rare), one warp per row
+        double smax = -1e300;
+        {
+            const int lane = tid & 31, warp = tid >> 5;
+            const double INF = __longlong_as_double(0x7ff0000000000000LL);
+            for (int r = warp; r < nr; r += NT / 32) {
+                double m = INF;
+                int a = -1;
+                for (int c = lane; c < nc; c += 32) {
+                    const double sv = sim2(r, c);
+                    const double cst = xadd(-sv, xmul((double)(r * nc + c), TIE_EPS));
+                    smax = fmax(smax, sv);
+                    if (cst < m) { m = cst; a = c; }
+                }
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    const double om = __shfl_xor_sync(0xffffffffu, m, d);
+                    const int oa = __shfl_xor_sync(0xffffffffu, a, d);
+                    if (om < m || (om == m && oa >= 0 && (a < 0 || oa < a))) { m = om; a = oa; }
+                }
+                if (lane == 0) { sm.u[r] = m; sm.claim[r] = a; }
             }
         }
+        int d1 = 0, d2 = 0;
         block_max3<NT>(sm, smax, d1, d2);
-        block_max3<NT>(sm, mx, d1, d2);
         if (!(smax > thr)) return false;
         const DenseLap w = make_dense<NT>(sm);
-        const double lambda = 2.0 * (mx + 1.0);
-        dense_lap_init<NT>(w, C, TMAX, nr, nc, lambda);
-        dense_lap_augment<NT>(w, C, TMAX, nr, nc, lambda);
+        // costs are -similarity (+ ties): at most 1e-6 for every similarity whose range starts at 0, else bounded by 1 + 1e-6
+        const double lambda = 2.0 * ((func <= 1 ? 0.0 : 1.0) + 1e-6 + 1.0);
+        dense_lap_init<NT>(w, nr, nc, lambda);
+        dense_lap_augment<NT>(w, cost2, nr, nc, lambda);
         if (tid < nr) {
             const int c = sm.xr[tid];
             if (c >= 0) {
                 const int j = sm.ud[tid], sl = sm.ut[c];
-                const Box tb = {bx[0][sl], bx[1][sl], bx[2][sl], bx[3][sl]};
-                const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
-                if (!(oc_sim(func, db, tb, W, H) < thr)) {
+                if (!(sim2(tid, c) < thr)) {
                     if (sm.dstate[j] != DS_NONE) sm.dstate[j] = DS_MATCHED;
                     sm.dmatch[j] = (short)sl; sm.tmatch[sl] = (short)j;
                 }
@@ -517,7 +762,10 @@ ocsort_step_kernel(const StepParams p) {
     OcKf k;
     if (live) {
 #pragma unroll
-        for (int c = 0; c < 7; ++c) k.x[c] = sm.x[c][t];
+        for (int c = 0; c < 7; ++c) k.x[c] = gf[(B200_OC_X + c) * TMAX + t];
+        if (xadd(k.x[6], k.x[2]) <= 0.0) k.x[6] = xmul(k.x[6], 0.0);          // the motion step of phase 1, same operations
+#pragma unroll
+        for (int c = 0; c < 3; ++c) k.x[c] = xadd(k.x[c], k.x[c + 4]);
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             k.pp[i] = gf[(B200_OC_P + 3 * i + 0) * TMAX + t];
@@ -543,7 +791,7 @@ ocsort_step_kernel(const StepParams p) {
                 gf[(B200_OC_VEL + 0) * TMAX + t] = xdiv(dy, norm);
                 gf[(B200_OC_VEL + 1) * TMAX + t] = xdiv(dx, norm);
             }
-            conf = sm.dconf[j]; cls = sm.dcls[j]; det_ind = j;
+            conf = sm.dconf[j]; cls = det_cls(j); det_ind = j;
             gf[(B200_OC_LAST + 0) * TMAX + t] = b0; gf[(B200_OC_LAST + 1) * TMAX + t] = b1;
             gf[(B200_OC_LAST + 2) * TMAX + t] = b2; gf[(B200_OC_LAST + 3) * TMAX + t] = b3;
             const int rs = age % 3;
@@ -662,8 +910,19 @@ ocsort_step_kernel(const StepParams p) {
             if (row < out_cap) {
                 Box b;
                 if (box_from_obs) { b.x1 = sm.lbox[0][t]; b.y1 = sm.lbox[1][t]; b.x2 = sm.lbox[2][t]; b.y2 = sm.lbox[3][t]; }
-                else { b = oc_x_to_box(k.x[0], k.x[1], k.x[2], k.x[3]); if (packed) err |= B200_ERR_PACKED_ROW; }
-                write_row(row, b, tid_id + 1, conf, cls, det_ind);
+                else b = oc_x_to_box(k.x[0], k.x[1], k.x[2], k.x[3]);
+                int di = det_ind;
+                if (packed && !box_from_obs) {            // the filter's box travels in the exception area
+                    const int e = atomicAdd(p.err_out + 1, 1);
+                    if (e < p.exc_cap) {
+                        unsigned char* x = p.exc + (size_t)e * B200_EXC_OC_BYTES;
+                        reinterpret_cast<int2*>(x)[0] = make_int2(roff + row, 0);
+                        double* xb = reinterpret_cast<double*>(x + 8);
+                        xb[0] = b.x1; xb[1] = b.y1; xb[2] = b.x2; xb[3] = b.y2;
+                    } else err |= B200_ERR_PACKED_ROW;
+                    di |= B200_ROW_OC_STATE;
+                }
+                write_row(row, b, tid_id + 1, conf, cls, di);
             }
         }
     } else if (t < n0 && (fl & OCF_ALIVE) == 0 && t < TMAX) {
@@ -688,7 +947,7 @@ ocsort_step_kernel(const StepParams p) {
 #pragma unroll
             for (int c = 0; c < 10; ++c) gf[(B200_OC_P + c) * TMAX + dst] = P0[c];
             gf[B200_OC_CONF * TMAX + dst] = sm.dconf[j];
-            gf[B200_OC_CLS * TMAX + dst] = sm.dcls[j];
+            gf[B200_OC_CLS * TMAX + dst] = det_cls(j);
             gf[(B200_OC_VEL + 0) * TMAX + dst] = 0.0; gf[(B200_OC_VEL + 1) * TMAX + dst] = 0.0;
             gi[B200_OCI_ID * TMAX + dst] = id;
             gi[B200_OCI_AGE * TMAX + dst] = 0;
@@ -703,7 +962,7 @@ ocsort_step_kernel(const StepParams p) {
             // reversed list order: the newest tracker first; rows of the new trackers precede the old ones
             const int row = n_new - 1 - order;
             // packed: bit 30 marks a new tracker - its box is the detection's round trip through the filter state
-            if (row < out_cap) write_row(row, oc_x_to_box(z[0], z[1], z[2], z[3]), id + 1, sm.dconf[j], sm.dcls[j], packed ? (j | B200_ROW_OC_NEW) : j);
+            if (row < out_cap) write_row(row, oc_x_to_box(z[0], z[1], z[2], z[3]), id + 1, sm.dconf[j], det_cls(j), packed ? (j | B200_ROW_OC_NEW) : j);
         }
     }
     const int n1 = min(n0 + n_new, tcap);
@@ -711,39 +970,7 @@ ocsort_step_kernel(const StepParams p) {
     __syncthreads();
     PHASE(8);
 
-    // ---- compaction, only when the slot range runs short for the next frame ----------------------
-    int n_final = n1;
-    if (n1 > alive_after && n1 + dcap > tcap) {
-        bool lv = false;
-        if (t < n1) lv = gi[B200_OCI_FLAGS * TMAX + t] & OCF_ALIVE;
-        unsigned long long tt;
-        const int dst = (int)block_exscan<NT>(lv ? 1ull : 0ull, sm.scratch, tt);
-        n_final = (int)tt;
-        for (int c0 = 0; c0 < B200_OC_NF; c0 += 8) {
-            double tmp[8];
-            if (lv && dst != t) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) if (c0 + c < B200_OC_NF) tmp[c] = gf[(c0 + c) * TMAX + t];
-            }
-            __syncthreads();
-            if (lv && dst != t) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) if (c0 + c < B200_OC_NF) gf[(c0 + c) * TMAX + dst] = tmp[c];
-            }
-            __syncthreads();
-        }
-        int itmp[B200_OC_NI];
-        if (lv && dst != t) {
-#pragma unroll
-            for (int c = 0; c < B200_OC_NI; ++c) itmp[c] = gi[c * TMAX + t];
-        }
-        __syncthreads();
-        if (lv && dst != t) {
-#pragma unroll
-            for (int c = 0; c < B200_OC_NI; ++c) gi[c * TMAX + dst] = itmp[c];
-        }
-        __syncthreads();
-    }
+    const int n_final = n1;
     if (tid == 0) {
         counts[0] = n_final;
         counts[1] = alive_after;
@@ -771,7 +998,8 @@ template <int TMAX, int DMAX>
 cudaError_t launch_oc_variant(const StepParams& p, cudaStream_t stream) {
     if constexpr (TMAX >= 224 && TMAX < 512) {
         static const int sms = [] { int d = 0, n = 148; cudaGetDevice(&d); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d); return n; }();
-        if (p.n_streams > 2 * sms) return launch_oc_kernel<TMAX, DMAX, true>(p, stream);
+        static const int force = [] { const char* v = getenv("B200_OC_DENSE"); return v ? atoi(v) : -1; }();     // A/B experiments
+        if (force == 1 || (force < 0 && p.n_streams > 2 * sms)) return launch_oc_kernel<TMAX, DMAX, true>(p, stream);
     }
     return launch_oc_kernel<TMAX, DMAX, false>(p, stream);
 }

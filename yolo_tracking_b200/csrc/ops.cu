@@ -11,7 +11,7 @@
 #include "api_util.h"
 #include "boxes.cuh"
 #include "kf.cuh"
-#include "lap_dense.cuh"
+#include "lap_dense_matrix.cuh"
 #include "lap_sparse.cuh"
 
 namespace b200 {
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(256) lapjv_dense_kernel(int rows, int cols, co
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     size_t off = 0;
     auto take = [&](size_t bytes) { unsigned char* p = raw + off; off = (off + bytes + 15) & ~size_t(15); return p; };
-    DenseLap w;
+    DenseLapM w;
     w.u = (double*)take(8 * rows); w.v = (double*)take(8 * cols); w.dist = (double*)take(8 * cols);
     w.red_v = (double*)take(8 * 32); w.sh_d = (double*)take(8 * 4);
     w.red_i = (int*)take(4 * 32); w.sh_i = (int*)take(4 * 4);
@@ -503,8 +503,8 @@ __global__ void __launch_bounds__(256) lapjv_dense_kernel(int rows, int cols, co
     for (int k = 1; k < NT / 32; ++k) m2 = fmax(m2, w.red_v[k]);
     const double lambda = 2.0 * (m2 + 1.0);
     __syncthreads();
-    dense_lap_init<NT>(w, c, cols, rows, cols, lambda);
-    dense_lap_augment<NT>(w, c, cols, rows, cols, lambda);
+    dense_lapm_init<NT>(w, c, cols, rows, cols, lambda);
+    dense_lapm_augment<NT>(w, c, cols, rows, cols, lambda);
     for (int t = tid; t < rows; t += NT) x[(size_t)blockIdx.x * rows + t] = w.xr[t];
     for (int j = tid; j < cols; j += NT) y[(size_t)blockIdx.x * cols + j] = w.yc[j];
 }

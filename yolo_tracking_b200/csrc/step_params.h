@@ -50,7 +50,9 @@ struct StepParams {
     const float* dets32;      // [R, 6] or null
     const int* det_off;       // [S + 1]
     unsigned char* rows;      // [R] compact result rows
-    int* err_out;             // header word of the result block: capacity overflow bits of this step
+    int* err_out;             // header of the result block: [0] capacity overflow bits of this step, [1] exception entries
+    unsigned char* exc;       // OC-SORT: exception area of the result block (layout.h: B200_ROW_OC_STATE)
+    int exc_cap;
     const double* warps;      // [S, 6] row-major 2x3 camera-motion warp per stream (BoT-SORT), null = identity
 };
 
