@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define B200TRACK_ABI_VERSION 1
+#define B200TRACK_ABI_VERSION 2
 
 typedef enum {
     B200TRACK_OK = 0,
@@ -34,7 +34,8 @@ typedef enum {
 typedef enum {
     B200TRACK_BYTETRACK = 0,      /* boxmot/trackers/bytetrack/byte_tracker.py:114 BYTETracker */
     B200TRACK_OCSORT = 1,         /* boxmot/trackers/ocsort/ocsort.py:190 OCSort               */
-    B200TRACK_BOTSORT = 2         /* boxmot/trackers/botsort/bot_sort.py:184 BoTSORT           */
+    B200TRACK_BOTSORT = 2,        /* boxmot/trackers/botsort/bot_sort.py:184 BoTSORT           */
+    B200TRACK_DEEPOCSORT = 3      /* boxmot/trackers/deepocsort/deep_ocsort.py:308 DeepOCSort  */
 } b200track_kind;
 
 typedef enum { B200TRACK_KF_XYAH = 0, B200TRACK_KF_XYWH = 1, B200TRACK_KF_XYAH_CONF = 2 } b200track_kf_kind;
@@ -71,6 +72,17 @@ typedef struct {
     int32_t use_byte;
     int32_t with_reid;       /* BoTSORT: use the embedding cost                             */
     int32_t fuse_first_associate; /* BoTSORT: fuse_score on the first association (bot_sort.py:199,300-301); default 0 */
+    /* DeepOCSORT (deep_ocsort.py:309-330); it also reads det_thresh, iou_thresh, inertia, max_age, min_hits, delta_t,
+     * asso_func and feat_dim above.  embedding_off != 0: no appearance term (feat_dim may be 0). */
+    double w_association_emb;
+    double alpha_fixed_emb;
+    double aw_param;
+    int32_t embedding_off;
+    int32_t aw_off;
+    /* BoTSORT: camera_motion != 0 keeps the filter in the form a camera warp needs (two 4x4 covariance blocks instead of
+     * four 2x2) so that per-stream warps can be applied (bot_sort.py:293-295); DeepOCSORT contexts always accept warps */
+    int32_t camera_motion;
+    int32_t reserved;
 } b200track_config;
 
 typedef struct b200track_ctx b200track_ctx;
@@ -89,6 +101,11 @@ const char* b200track_last_error(void);
  *   d_out   [n_streams, max_tracks, 8] (x1, y1, x2, y2, id, conf, cls, det_ind) in the
  *           reference's row order; d_nout[s] rows are valid.
  *   d_dets, d_feats and d_out must be 16-byte aligned (rows are moved with 16-byte accesses).
+ * b200track_step_cam    the same with one externally estimated 2x3 camera-motion warp per stream, d_warps
+ *                          [n_streams, 6] row-major (NULL = identity): BoT-SORT contexts created with camera_motion
+ *                          (STrack.multi_gmc, bot_sort.py:95-111, :293-295) and DeepOCSORT contexts
+ *                          (apply_affine_correction, deep_ocsort.py:222-241, :393-396).  For DeepOCSORT d_feats holds the
+ *                          embedding of every detection row with conf > det_thresh (deep_ocsort.py:382-390).
  * b200track_step_host   same call with HOST buffers: copies in, steps, copies out, waits.
  * b200track_submit_host / b200track_wait_host: pipelined variant - up to
  *   b200track_host_slots() frames in flight (copy-in of frame k+1 and copy-out of frame k-1
@@ -100,6 +117,9 @@ int b200track_reset(b200track_ctx* ctx);
 int b200track_step(b200track_ctx* ctx, const double* d_dets, const int32_t* d_ndets,
                    const float* d_feats, int32_t img_h, int32_t img_w,
                    double* d_out, int32_t* d_nout, void* stream);
+int b200track_step_cam(b200track_ctx* ctx, const double* d_dets, const int32_t* d_ndets,
+                       const float* d_feats, const double* d_warps, int32_t img_h, int32_t img_w,
+                       double* d_out, int32_t* d_nout, void* stream);
 int b200track_step_host(b200track_ctx* ctx, const double* h_dets, const int32_t* h_ndets,
                         const float* h_feats, int32_t img_h, int32_t img_w,
                         double* h_out, int32_t* h_nout);
@@ -116,13 +136,13 @@ int b200track_wait_host(b200track_ctx* ctx, int32_t slot);   /* B200TRACK_ERR_CA
  *   input block  (b200track_layout.in_*):  int32 offsets[n_streams + 1] (stream s owns detection rows
  *       [offsets[s], offsets[s + 1]) - the exclusive scan of the per-stream counts), double warps[n_streams][6]
  *       (BoT-SORT contexts only; read when flags has B200TRACK_FRAME_HAS_WARPS: the 2x3 camera-motion warp per stream,
- *       bot_sort.py:293-295), the detection rows [n_rows][6] (x1, y1, x2, y2, conf, cls) back to back as fp32
+ *       bot_sort.py:293-295; DeepOCSORT contexts likewise), the detection rows [n_rows][6] (x1, y1, x2, y2, conf, cls) back to back as fp32
  *       (B200TRACK_F32: what detectors emit; widened on the device, which is exact, so the result equals the padded
- *       interface's on dets.astype(float64)) or fp64, and for BoT-SORT with_reid the embeddings [n_rows][feat_dim] fp32;
+ *       interface's on dets.astype(float64)) or fp64, and for BoT-SORT with_reid / DeepOCSORT the embeddings [n_rows][feat_dim] fp32;
  *   result block (b200track_layout.out_*): int32 header[4] ([0] = capacity bits of this step, 0 = fine),
  *       int32 nout[n_streams], then compact rows: stream s owns rows [offsets[s], offsets[s] + nout[s]) (a result row
  *       carries a distinct detection of its frame, so nout[s] <= its detection count), in the reference's row order:
- *         ByteTrack b200track_row    40 B  x1, y1, x2, y2 (fp64), id, det_ind
+ *         ByteTrack, DeepOCSORT b200track_row    40 B  x1, y1, x2, y2 (fp64), id, det_ind
  *         BoT-SORT  b200track_row_bot 48 B  + cls (the voted class, bot_sort.py:50-67), conf as fp32
  *         OC-SORT   b200track_row_oc   8 B  id, det_ind; det_ind bit 30 set = tracker created this frame (its box is
  *                   convert_x_to_bbox(convert_bbox_to_z(det)), otherwise the detection's own box); bit 29 set = the row
@@ -178,6 +198,15 @@ int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int32_t* h_cou
 /* BoT-SORT contexts (with_reid): STrack.smooth_feat (bot_sort.py:40-48) of every listed track of one
  * stream, in the same list order as b200track_get_state; h_feat[max_tracks, feat_dim] fp32. */
 int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, float* h_feat);
+/* DeepOCSORT contexts: KalmanBoxTracker fields like the OC-SORT form of b200track_get_state (h_rec[.., 5] = kf.observed +
+ * 2 * frozen; h_mean = x[8]; h_cov = dense 8x8 kf.P; h_aux = conf, cls, det_ind) plus, in b200track_get_track_extras,
+ * h_extra[max_tracks, 8] = velocity[2], last_observation[5] (placeholder -1), unused; h_emb[max_tracks, feat_dim] = the
+ * smoothed embedding (fp64), NULL to skip. */
+int b200track_get_track_extras(b200track_ctx* ctx, int32_t stream_index, double* h_extra, double* h_emb);
+/* Event counters summed over all streams since create / reset (DeepOCSORT contexts): h_out8[0] = first associations solved
+ * as an assignment problem (not by the permutation shortcut, association.py:157-159), [1] = recovery rounds that ran an
+ * assignment (deep_ocsort.py:466), [2] = observation-centric re-updates (deepocsort_kf.py:433-478); the rest reserved. */
+int b200track_counters(b200track_ctx* ctx, uint64_t* h_out8);
 
 /* ---- operator level: the reference's functional API, batched, device pointers -----------
  * Dense [n, 8] means / [n, 8, 8] covariances in the reference's memory layout.

@@ -111,15 +111,45 @@ def test_deepocsort_oracle_replay_matches_reference_files():
     _deepocsort_replay(lambda **kw: DeepOCSortOracle(**kw), lambda t, d, f: t.update(d, f, (1080, 1920)))
 
 
-def test_deepocsort_host_logic_replay_matches_reference_files(monkeypatch):
-    """The drop-in's host list logic on the same streams, the operators patched with the oracle's arithmetic (test-only,
-    tests/_util.py::OracleOps)."""
-    import types
-    from _util import OracleOps
-    from yolo_tracking_b200.trackers import deepocsort as mod
-    monkeypatch.setattr(mod, "_ops", OracleOps)
-    monkeypatch.setattr(mod, "_lib", types.SimpleNamespace(load=lambda: None, SIM=mod._lib.SIM))
-    _deepocsort_replay(lambda **kw: mod.DeepOCSort(None, 0, False, False, **kw), lambda t, d, f: t.update(d, (1080, 1920), feats=f))
+@pytest.mark.gpu
+def test_deepocsort_cuda_replay_matches_reference_files():
+    """GPU twin: the same streams through the fused CUDA DeepOCSORT step (the drop-in is a one-stream context of it)."""
+    import yolo_tracking_b200 as pkg
+    _deepocsort_replay(lambda **kw: pkg.DeepOCSORT(None, 0, False, False, **kw), lambda t, d, f: t.update(d, (1080, 1920), feats=f))
+
+
+@pytest.mark.gpu
+def test_deepocsort_cuda_replay_batched_streams():
+    """The three sequences as three streams of ONE batched DeepOCSORT context (ragged frame counts: a finished sequence
+    keeps sending empty frames), through the packed interface."""
+    import sys
+    from _util import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    from scenarios import DEEPOCSORT_YAML, mot_feats
+    from yolo_tracking_b200.batch import BatchedTracker
+    g, ref = load_golden("mot17_mini"), load_golden("mot17_mini_deepocsort")
+    seqs = _sequences(g)
+    trk = BatchedTracker("deepocsort", len(seqs), max_tracks=256, max_dets=256, feat_dim=32, **DEEPOCSORT_YAML)
+    rows = [[] for _ in seqs]
+    for f in range(max(len(q) for q in seqs)):
+        dets, feats = [], []
+        for si, seq in enumerate(seqs):
+            d = seq[f] if f < len(seq) else np.zeros((0, 6))
+            keep = d[:, 4] > DEEPOCSORT_YAML["det_thresh"]
+            raw = mot_feats(si, f, int(keep.sum()))
+            full = np.zeros((len(d), 32), dtype=np.float32)
+            if len(raw):
+                full[keep] = raw / np.linalg.norm(raw)
+            dets.append(d)
+            feats.append(full)
+        outs = trk.update_frames(dets, feats=feats, img_hw=(1080, 1920))
+        for si, o in enumerate(outs):
+            if o.size and f < len(seqs[si]):
+                rows[si].append(mot_io.mot_rows(o, f))
+    for name, r in zip(SEQS, rows):
+        assert np.array_equal(mot_io.as_int_rows(np.concatenate(r)), ref[name]), name
+    trk.close()
 
 
 def test_strongsort_oracle_replay_matches_reference_files():
@@ -163,6 +193,53 @@ def test_botsort_oracle_replay_matches_reference_files():
             if len(hi):
                 feats[hi] = raw[hi] / np.linalg.norm(raw[hi])
             o = trk.update(d, feats)
+            if o.size:
+                rows.append(mot_io.mot_rows(o, f))
+        assert np.array_equal(mot_io.as_int_rows(np.concatenate(rows)), ref[name]), name
+
+
+@pytest.mark.gpu
+def test_botsort_cuda_replay_matches_reference_files():
+    """GPU twin of the BoT-SORT replay: the fused CUDA step on the MOT17-mini public detections."""
+    import sys
+    from _util import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    import yolo_tracking_b200 as pkg
+    from scenarios import BOTSORT_YAML, mot_feats
+    g, ref = load_golden("mot17_mini"), load_golden("mot17_mini_botsort")
+    for si, (name, seq) in enumerate(zip(SEQS, _sequences(g))):
+        kw = {k: v for k, v in BOTSORT_YAML.items() if k != "cmc_method"}
+        trk = pkg.BoTSORT(None, 0, False, feat_dim=128, max_tracks=256, max_dets=256, **kw)
+        rows = []
+        for f, d in enumerate(seq):
+            raw = mot_feats(si, f, len(d))
+            hi = np.nonzero(d[:, 4] > BOTSORT_YAML["track_high_thresh"])[0]
+            feats = np.zeros((len(d), 128), dtype=np.float32)          # the 32-d stand-ins zero-padded to the kernel's row granularity
+            if len(hi):
+                feats[hi, :32] = raw[hi] / np.linalg.norm(raw[hi])
+            o = trk.update(d, None, feats=feats)
+            if o.size:
+                rows.append(mot_io.mot_rows(o, f))
+        assert np.array_equal(mot_io.as_int_rows(np.concatenate(rows)), ref[name]), name
+
+
+@pytest.mark.gpu
+def test_strongsort_cuda_replay_matches_reference_files():
+    """GPU twin of the StrongSORT replay: the operator-backed drop-in on the MOT17-mini public detections."""
+    import sys
+    from _util import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    import yolo_tracking_b200 as pkg
+    from scenarios import STRONGSORT_YAML, mot_feats
+    g, ref = load_golden("mot17_mini"), load_golden("mot17_mini_strongsort")
+    for si, (name, seq) in enumerate(zip(SEQS, _sequences(g))):
+        trk = pkg.StrongSORT(None, 0, False, **STRONGSORT_YAML)
+        rows = []
+        for f, d in enumerate(seq):
+            raw = mot_feats(si, f, len(d))
+            o = trk.update(d, np.zeros((1080, 1920, 3), dtype=np.uint8), feats=raw / np.linalg.norm(raw) if len(raw) else raw)
             if o.size:
                 rows.append(mot_io.mot_rows(o, f))
         assert np.array_equal(mot_io.as_int_rows(np.concatenate(rows)), ref[name]), name

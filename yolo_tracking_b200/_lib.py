@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("B200TRACK_LIB") or os.path.join(_HERE, "lib", "libb20
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200track.h")
 
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
-BYTETRACK, OCSORT, BOTSORT = 0, 1, 2
+BYTETRACK, OCSORT, BOTSORT, DEEPOCSORT = 0, 1, 2, 3
 KF_XYAH, KF_XYWH, KF_XYAH_CONF = 0, 1, 2
 SIM = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3, "centroid": 4}
 
@@ -32,6 +32,8 @@ class Config(C.Structure):
         ("det_thresh", C.c_double), ("iou_thresh", C.c_double), ("inertia", C.c_double),
         ("max_age", C.c_int32), ("min_hits", C.c_int32), ("delta_t", C.c_int32), ("asso_func", C.c_int32),
         ("use_byte", C.c_int32), ("with_reid", C.c_int32), ("fuse_first_associate", C.c_int32),
+        ("w_association_emb", C.c_double), ("alpha_fixed_emb", C.c_double), ("aw_param", C.c_double),
+        ("embedding_off", C.c_int32), ("aw_off", C.c_int32), ("camera_motion", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -59,6 +61,9 @@ SIGNATURES = {
     "b200track_destroy": (None, [_P]),
     "b200track_reset": (C.c_int, [_P]),
     "b200track_step": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "b200track_step_cam": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
+    "b200track_get_track_extras": (C.c_int, [_P, _I, _P, _P]),
+    "b200track_counters": (C.c_int, [_P, C.POINTER(C.c_uint64 * 8)]),
     "b200track_step_host": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _P]),
     "b200track_host_slots": (C.c_int, [_P]),
     "b200track_submit_host": (C.c_int, [_P, _I, _P, _P, _P, _I, _I, _P, _P]),

@@ -13,7 +13,7 @@ import numpy as np
 
 from . import _lib
 
-_KINDS = {"bytetrack": _lib.BYTETRACK, "ocsort": _lib.OCSORT, "botsort": _lib.BOTSORT}
+_KINDS = {"bytetrack": _lib.BYTETRACK, "ocsort": _lib.OCSORT, "botsort": _lib.BOTSORT, "deepocsort": _lib.DEEPOCSORT}
 
 
 def _ptr(a):
@@ -60,6 +60,23 @@ class BatchedTracker:
             cfg.frame_rate = int(params.get("frame_rate", 30))
             cfg.with_reid = int(params.get("with_reid", True))
             cfg.fuse_first_associate = int(bool(params.get("fuse_first_associate", False)))
+            cfg.camera_motion = int(bool(params.get("camera_motion", False)))
+        elif kind == "deepocsort":
+            # DeepOCSort defaults (deep_ocsort.py:309-330)
+            cfg.det_thresh = params.get("det_thresh", 0.3)
+            cfg.max_age = int(params.get("max_age", 30))
+            cfg.min_hits = int(params.get("min_hits", 3))
+            cfg.iou_thresh = params.get("iou_threshold", params.get("iou_thresh", 0.3))
+            cfg.delta_t = int(params.get("delta_t", 3))
+            cfg.asso_func = _lib.SIM[params.get("asso_func", "iou")]
+            cfg.inertia = params.get("inertia", 0.2)
+            cfg.w_association_emb = params.get("w_association_emb", 0.5)
+            cfg.alpha_fixed_emb = params.get("alpha_fixed_emb", 0.95)
+            cfg.aw_param = params.get("aw_param", 0.5)
+            cfg.embedding_off = int(bool(params.get("embedding_off", False)))
+            cfg.aw_off = int(bool(params.get("aw_off", False)))
+            if cfg.embedding_off:
+                self.feat_dim = cfg.feat_dim = 0
         else:
             # OCSort defaults (ocsort.py:191-203)
             cfg.det_thresh = params.get("det_thresh", 0.2)
@@ -91,10 +108,14 @@ class BatchedTracker:
         _lib.check(self._lib.b200track_reset(self._ctx))
 
     # ------------------------------------------------------------------ frame step
-    def step_device(self, d_dets, d_ndets, d_out, d_nout, d_feats=None, img_hw=(0, 0), stream=None):
+    def step_device(self, d_dets, d_ndets, d_out, d_nout, d_feats=None, img_hw=(0, 0), stream=None, d_warps=None):
         """Asynchronous step on device tensors (torch, contiguous): dets [S, max_dets, 6] f64,
-        ndets [S] i32 -> out [S, max_tracks, 8] f64, nout [S] i32."""
+        ndets [S] i32 -> out [S, max_tracks, 8] f64, nout [S] i32; d_warps [S, 6] f64 camera motion (optional)."""
         st = C.c_void_p(stream) if stream else None
+        if d_warps is not None:
+            _lib.check(self._lib.b200track_step_cam(self._ctx, _ptr(d_dets), _ptr(d_ndets), _ptr(d_feats), _ptr(d_warps),
+                                                    int(img_hw[0]), int(img_hw[1]), _ptr(d_out), _ptr(d_nout), st))
+            return
         _lib.check(self._lib.b200track_step(self._ctx, _ptr(d_dets), _ptr(d_ndets), _ptr(d_feats),
                                             int(img_hw[0]), int(img_hw[1]), _ptr(d_out), _ptr(d_nout), st))
 
@@ -139,8 +160,17 @@ class BatchedTracker:
         "botsort": np.dtype([("box", "<f8", 4), ("id", "<i4"), ("det_ind", "<i4"), ("cls", "<f4"), ("conf", "<f4")]),
         "ocsort": np.dtype([("id", "<i4"), ("det_ind", "<i4")]),
     }
+    _ROW_DTYPES["deepocsort"] = _ROW_DTYPES["bytetrack"]
 
     _EXC_DTYPE = np.dtype([("row", "<i4"), ("reserved", "<i4"), ("box", "<f8", 4)])
+
+    @property
+    def _has_feats(self):
+        return (self.kind == "botsort" and bool(self._cfg.with_reid)) or (self.kind == "deepocsort" and not self._cfg.embedding_off)
+
+    @property
+    def _has_warps(self):
+        return self.kind in ("botsort", "deepocsort")
 
     def frame_layout(self, n_rows: int, dtype=np.float32):
         L = _lib.Layout()
@@ -190,7 +220,7 @@ class BatchedTracker:
         flags = 0
         if warps is not None:
             if v["warps"] is None:
-                raise ValueError("only BoT-SORT contexts take camera-motion warps")
+                raise ValueError("only BoT-SORT and DeepOCSORT contexts take camera-motion warps")
             v["warps"][:] = np.asarray(warps, dtype=np.float64).reshape(S, 6)
             flags |= _lib.FRAME_HAS_WARPS
         return R, flags
@@ -204,10 +234,9 @@ class BatchedTracker:
         if in_block is not None:
             v["offsets"] = in_block[L.in_off_offsets:L.in_off_offsets + 4 * (S + 1)].view(np.int32)
             v["dets"] = in_block[L.in_off_dets:L.in_off_dets + R * 6 * dtype.itemsize].view(dtype).reshape(R, 6)
-            v["warps"] = (in_block[L.in_off_warps:L.in_off_warps + 48 * S].view(np.float64).reshape(S, 6)
-                          if self.kind == "botsort" else None)
+            v["warps"] = in_block[L.in_off_warps:L.in_off_warps + 48 * S].view(np.float64).reshape(S, 6) if self._has_warps else None
             v["feats"] = (in_block[L.in_off_feats:L.in_off_feats + R * self.feat_dim * 4].view(np.float32).reshape(R, self.feat_dim)
-                          if self.kind == "botsort" and self._cfg.with_reid else None)
+                          if self._has_feats else None)
         if out_block is not None:
             v["header"] = out_block[0:16].view(np.int32)
             v["nout"] = out_block[L.out_off_nout:L.out_off_nout + 4 * S].view(np.int32)
@@ -286,6 +315,12 @@ class BatchedTracker:
         _lib.check(self._lib.b200track_track_updates(self._ctx, C.byref(v)))
         return v.value
 
+    def counters(self):
+        """Event counters over all streams (DeepOCSORT): assignment-solved first associations, recovery rounds, re-updates."""
+        buf = (C.c_uint64 * 8)()
+        _lib.check(self._lib.b200track_counters(self._ctx, C.byref(buf)))
+        return dict(lap_frames=int(buf[0]), ocr_frames=int(buf[1]), oru=int(buf[2]))
+
     def launches(self) -> int:
         v = C.c_uint64()
         _lib.check(self._lib.b200track_launch_count(self._ctx, C.byref(v)))
@@ -313,6 +348,17 @@ class BatchedTracker:
         _lib.check(self._lib.b200track_get_state(self._ctx, int(stream), _ptr(counts), _ptr(rec), _ptr(mean),
                                                  _ptr(cov), _ptr(aux)))
         n = int(counts[0] + counts[1])
+        if self.kind == "deepocsort":
+            extra = np.zeros((T, 8))
+            F = self.feat_dim
+            emb = np.zeros((T, max(F, 1)))
+            _lib.check(self._lib.b200track_get_track_extras(self._ctx, int(stream), _ptr(extra), _ptr(emb) if F else None))
+            return dict(n=n, id_count=int(counts[2]), frame_count=int(counts[3]),
+                        track_id=rec[:n, 0].copy(), age=rec[:n, 1].copy(), time_since_update=rec[:n, 2].copy(),
+                        hits=rec[:n, 3].copy(), hit_streak=rec[:n, 4].copy(), observed=rec[:n, 5] & 1, frozen=(rec[:n, 5] >> 1) & 1,
+                        x=mean[:n].copy(), P=cov[:n].reshape(n, 8, 8).copy(), velocity=extra[:n, 0:2].copy(),
+                        last_observation=extra[:n, 2:7].copy(), conf=aux[:n, 0].copy(), cls=aux[:n, 1].copy(),
+                        det_ind=aux[:n, 2].copy(), emb=emb[:n].copy() if F else np.ones((n, 1)))
         if self.kind == "ocsort":
             c = cov[:n]
             return dict(n=n, id_count=int(counts[2]), frame_count=int(counts[3]),

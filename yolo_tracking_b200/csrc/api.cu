@@ -80,7 +80,7 @@ static int check_cfg(const b200track_config* c) {
         set_error("max_tracks must be a multiple of 32 in [32, 512]"); return B200TRACK_ERR_ARG; }
     if (c->max_dets <= 0 || c->max_dets % 32 || c->max_dets > 512) {
         set_error("max_dets must be a multiple of 32 in [32, 512]"); return B200TRACK_ERR_ARG; }
-    if (c->kind != B200TRACK_BYTETRACK && c->kind != B200TRACK_OCSORT && c->kind != B200TRACK_BOTSORT) {
+    if (c->kind != B200TRACK_BYTETRACK && c->kind != B200TRACK_OCSORT && c->kind != B200TRACK_BOTSORT && c->kind != B200TRACK_DEEPOCSORT) {
         set_error("unknown tracker kind"); return B200TRACK_ERR_ARG; }
     return 0;
 }
@@ -93,8 +93,8 @@ extern "C" void b200track_destroy(b200track_ctx* ctx) {
     DeviceGuard _guard(ctx->cfg.device);
     cudaDeviceSynchronize();
     cudaFree(ctx->p.state_f); cudaFree(ctx->p.state_i); cudaFree(ctx->p.counts);
-    cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.err_slot); cudaFree(ctx->p.dbg); cudaFree(ctx->p.scratch);
-    cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.feat_curr); cudaFree(ctx->p.cls_hist);
+    cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.stats); cudaFree(ctx->p.err_slot); cudaFree(ctx->p.dbg); cudaFree(ctx->p.scratch);
+    cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.feat_curr); cudaFree(ctx->p.cls_hist); cudaFree(ctx->p.emb_pool);
     for (auto& s : ctx->slot) {
         cudaFree(s.d_dets); cudaFree(s.d_ndets); cudaFree(s.d_feats); cudaFree(s.d_out); cudaFree(s.d_nout);
         cudaFree(s.d_in); cudaFree(s.d_res);
@@ -120,6 +120,7 @@ extern "C" int b200track_reset(b200track_ctx* ctx) {
     CU_TRY(cudaMemset(ctx->p.counts, 0, S * 4 * sizeof(int)));
     CU_TRY(cudaMemset(ctx->p.track_updates, 0, S * sizeof(unsigned long long)));
     CU_TRY(cudaMemset(ctx->p.err, 0, sizeof(int)));
+    CU_TRY(cudaMemset(ctx->p.stats, 0, 8 * sizeof(unsigned long long)));
     return 0;
 }
 
@@ -131,9 +132,13 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         if (cfg->feat_dim <= 0 || cfg->feat_dim % 128 || cfg->feat_dim > 4096) {
             set_error("BoT-SORT with_reid needs feat_dim to be a multiple of 128 in [128, 4096]"); return B200TRACK_ERR_ARG; }
     }
-    if (cfg->kind == B200TRACK_OCSORT) {
-        if (cfg->delta_t < 1 || cfg->delta_t > 3) { set_error("OC-SORT delta_t must be in [1, 3]"); return B200TRACK_ERR_ARG; }
+    if (cfg->kind == B200TRACK_OCSORT || cfg->kind == B200TRACK_DEEPOCSORT) {
+        if (cfg->delta_t < 1 || cfg->delta_t > 3) { set_error("OC-SORT / DeepOCSORT delta_t must be in [1, 3]"); return B200TRACK_ERR_ARG; }
         if (cfg->asso_func < 0 || cfg->asso_func > B200TRACK_SIM_CENTROID) { set_error("unknown asso_func"); return B200TRACK_ERR_ARG; }
+    }
+    if (cfg->kind == B200TRACK_DEEPOCSORT && !cfg->embedding_off) {
+        if (cfg->feat_dim <= 0 || cfg->feat_dim % 4 || cfg->feat_dim > 4096) {
+            set_error("DeepOCSORT needs feat_dim to be a multiple of 4 in [4, 4096] (or embedding_off)"); return B200TRACK_ERR_ARG; }
     }
     int ndev = 0;
     CU_TRY(cudaGetDeviceCount(&ndev));
@@ -158,6 +163,12 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     p.det_thresh = cfg->det_thresh; p.iou_thresh = cfg->iou_thresh; p.inertia = cfg->inertia;
     p.max_age = cfg->max_age; p.min_hits = cfg->min_hits; p.delta_t = cfg->delta_t; p.asso_func = cfg->asso_func; p.use_byte = cfg->use_byte ? 1 : 0;
     if (cfg->kind == B200TRACK_OCSORT) { ctx->nf = B200_OC_NF; ctx->ni = B200_OC_NI; }
+    if (cfg->kind == B200TRACK_DEEPOCSORT) {
+        ctx->nf = B200_DO_NF; ctx->ni = B200_DO_NI;
+        p.w_assoc_emb = cfg->w_association_emb; p.alpha_fixed_emb = cfg->alpha_fixed_emb; p.aw_param = cfg->aw_param;
+        p.embedding_off = cfg->embedding_off ? 1 : 0; p.aw_off = cfg->aw_off ? 1 : 0;
+        if (p.embedding_off) p.feat_dim = 0;
+    }
     if (cfg->kind == B200TRACK_BOTSORT) { ctx->ni = B200_NI_BOT; p.with_reid = cfg->with_reid ? 1 : 0; p.fuse_first = cfg->fuse_first_associate ? 1 : 0; }
     ctx->kf_kind = cfg->kind == B200TRACK_BOTSORT ? B200TRACK_KF_XYWH : B200TRACK_KF_XYAH;
     ctx->variant = b200::bytetrack_step_variant(cfg->max_tracks, cfg->max_dets);
@@ -169,6 +180,12 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
 #define CU_TRY_CTX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return fail(B200TRACK_ERR_CUDA); } } while (0)
     CU_TRY_CTX(cudaMalloc(&p.state_f, S * ctx->nf * T * sizeof(double)));
     CU_TRY_CTX(cudaMalloc(&p.state_i, S * ctx->ni * T * sizeof(int)));
+    if (cfg->kind == B200TRACK_DEEPOCSORT && !p.embedding_off) {
+        CU_TRY_CTX(cudaMalloc(&p.emb_pool, S * T * (size_t)cfg->feat_dim * sizeof(double)));
+        // diou / ciou / centroid have a similarity - hence an appearance term - for every pair: per-stream scratch matrix
+        if (!(cfg->asso_func <= B200TRACK_SIM_GIOU && cfg->iou_thresh >= 0.0))
+            CU_TRY_CTX(cudaMalloc(&p.scratch, S * T * (size_t)b200::step_variant_dmax(ctx->variant) * sizeof(double)));
+    }
     if (cfg->kind == B200TRACK_BOTSORT) {
         CU_TRY_CTX(cudaMalloc(&p.cls_hist, S * T * 9 * sizeof(double)));
         if (cfg->with_reid) {
@@ -179,6 +196,7 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     CU_TRY_CTX(cudaMalloc(&p.counts, S * 4 * sizeof(int)));
     CU_TRY_CTX(cudaMalloc(&p.track_updates, S * sizeof(unsigned long long)));
     CU_TRY_CTX(cudaMalloc(&p.err, sizeof(int)));
+    CU_TRY_CTX(cudaMalloc(&p.stats, 8 * sizeof(unsigned long long)));
     CU_TRY_CTX(cudaMalloc(&p.err_slot, NSLOT * sizeof(int)));
     CU_TRY_CTX(cudaMemset(p.err_slot, 0, NSLOT * sizeof(int)));
     CU_TRY_CTX(cudaMallocHost(&ctx->h_err, sizeof(int32_t)));
@@ -194,7 +212,8 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.out_ready, cudaEventDisableTiming));
     }
     const size_t smem = cfg->kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
-                                                      : b200::bytetrack_step_smem(ctx->variant, cfg->kind == B200TRACK_BOTSORT);
+                        : cfg->kind == B200TRACK_DEEPOCSORT ? b200::deepocsort_step_smem(ctx->variant)
+                        : b200::bytetrack_step_smem(ctx->variant, cfg->kind == B200TRACK_BOTSORT);
     int max_smem = 0;
     CU_TRY_CTX(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     if (smem > (size_t)max_smem) {
@@ -208,11 +227,17 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
 }
 
 static int launch_step(b200track_ctx* ctx, const double* d_dets, const int32_t* d_ndets, const float* d_feats,
-                       int32_t img_h, int32_t img_w, double* d_out, int32_t* d_nout, cudaStream_t st, int* d_err_step = nullptr) {
+                       int32_t img_h, int32_t img_w, double* d_out, int32_t* d_nout, cudaStream_t st, int* d_err_step = nullptr,
+                       const double* d_warps = nullptr) {
     b200::StepParams p = ctx->p;
     p.dets = d_dets; p.ndets = d_ndets; p.feats = d_feats; p.out = d_out; p.nout = d_nout; p.err_out = d_err_step;
-    p.img_h = img_h; p.img_w = img_w;
-    if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
+    p.img_h = img_h; p.img_w = img_w; p.warps = d_warps;
+    if (d_warps && !(ctx->cfg.kind == B200TRACK_DEEPOCSORT || (ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.camera_motion))) {
+        set_error("camera-motion warps need a DeepOCSORT context or a BoT-SORT context created with camera_motion"); return B200TRACK_ERR_STATE; }
+    if (ctx->cfg.kind == B200TRACK_DEEPOCSORT) {
+        if (!ctx->p.embedding_off && !d_feats) { set_error("DeepOCSORT: the embedding buffer is NULL"); return B200TRACK_ERR_ARG; }
+        CU_TRY(b200::launch_deepocsort_step(p, ctx->variant, st));
+    } else if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
     else if (ctx->cfg.kind == B200TRACK_BOTSORT) {
         if (p.with_reid && !d_feats) { set_error("BoT-SORT with_reid: the embedding buffer is NULL"); return B200TRACK_ERR_ARG; }
         CU_TRY(b200::launch_botsort_step(p, ctx->variant, st));
@@ -232,6 +257,16 @@ extern "C" int b200track_step(b200track_ctx* ctx, const double* d_dets, const in
     return launch_step(ctx, d_dets, d_ndets, d_feats, img_h, img_w, d_out, d_nout, (cudaStream_t)stream);
 }
 
+extern "C" int b200track_step_cam(b200track_ctx* ctx, const double* d_dets, const int32_t* d_ndets,
+                                  const float* d_feats, const double* d_warps, int32_t img_h, int32_t img_w,
+                                  double* d_out, int32_t* d_nout, void* stream) {
+    if (!ctx || !d_dets || !d_ndets || !d_out || !d_nout) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    if ((reinterpret_cast<uintptr_t>(d_dets) | reinterpret_cast<uintptr_t>(d_out) | reinterpret_cast<uintptr_t>(d_feats)) & 15) {
+        set_error("d_dets / d_out / d_feats must be 16-byte aligned"); return B200TRACK_ERR_ARG; }
+    ON_DEVICE(ctx);
+    return launch_step(ctx, d_dets, d_ndets, d_feats, img_h, img_w, d_out, d_nout, (cudaStream_t)stream, nullptr, d_warps);
+}
+
 extern "C" int b200track_host_slots(b200track_ctx* ctx) { return ctx ? NSLOT : B200TRACK_ERR_ARG; }
 
 static std::string capacity_message(int e) {
@@ -247,7 +282,7 @@ static int ensure_padded_slot(b200track_ctx* ctx, HostSlot& s) {
     const size_t S = ctx->cfg.n_streams, D = ctx->cfg.max_dets;
     CU_TRY(cudaMalloc(&s.d_dets, S * D * 6 * sizeof(double)));
     CU_TRY(cudaMalloc(&s.d_ndets, S * sizeof(int32_t)));
-    if (ctx->cfg.feat_dim > 0) CU_TRY(cudaMalloc(&s.d_feats, S * D * (size_t)ctx->cfg.feat_dim * sizeof(float)));
+    if (ctx->p.feat_dim > 0) CU_TRY(cudaMalloc(&s.d_feats, S * D * (size_t)ctx->p.feat_dim * sizeof(float)));
     CU_TRY(cudaMalloc(&s.d_out, S * (size_t)ctx->cfg.max_tracks * 8 * sizeof(double)));
     CU_TRY(cudaMalloc(&s.d_nout, S * sizeof(int32_t)));
     return 0;
@@ -258,8 +293,8 @@ extern "C" int b200track_submit_host(b200track_ctx* ctx, int32_t slot, const dou
                                      int32_t img_w, double* h_out, int32_t* h_nout) {
     if (!ctx || !h_dets || !h_ndets || !h_out || !h_nout) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
     if (slot < 0 || slot >= NSLOT) { set_error("slot out of range"); return B200TRACK_ERR_ARG; }
-    if (ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid && !h_feats) {
-        set_error("BoT-SORT with_reid: h_feats is NULL"); return B200TRACK_ERR_ARG; }
+    if (((ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid) || (ctx->cfg.kind == B200TRACK_DEEPOCSORT && !ctx->p.embedding_off)) && !h_feats) {
+        set_error("this context needs embeddings: h_feats is NULL"); return B200TRACK_ERR_ARG; }
     ON_DEVICE(ctx);
     HostSlot& s = ctx->slot[slot];
     if (int rc = ensure_padded_slot(ctx, s)) return rc;
@@ -276,15 +311,15 @@ extern "C" int b200track_submit_host(b200track_ctx* ctx, int32_t slot, const dou
     if (maxnd > 0)
         CU_TRY(cudaMemcpy2DAsync(s.d_dets, D * 6 * sizeof(double), h_dets, D * 6 * sizeof(double),
                                  (size_t)maxnd * 6 * sizeof(double), S, cudaMemcpyHostToDevice, ctx->s_h2d));
-    if (ctx->cfg.feat_dim > 0 && h_feats && maxnd > 0) {
-        const size_t row = (size_t)ctx->cfg.feat_dim * sizeof(float);
+    if (ctx->p.feat_dim > 0 && h_feats && maxnd > 0) {
+        const size_t row = (size_t)ctx->p.feat_dim * sizeof(float);
         CU_TRY(cudaMemcpy2DAsync(s.d_feats, D * row, h_feats, D * row, maxnd * row, S, cudaMemcpyHostToDevice, ctx->s_h2d));
     }
     CU_TRY(cudaEventRecord(s.in_ready, ctx->s_h2d));
     CU_TRY(cudaStreamWaitEvent(ctx->s_compute, s.in_ready, 0));
     // capacity overflows of THIS step come back with its outputs (b200track_wait_host reports them)
     CU_TRY(cudaMemsetAsync(ctx->p.err_slot + slot, 0, sizeof(int), ctx->s_compute));
-    if (int rc = launch_step(ctx, s.d_dets, s.d_ndets, ctx->cfg.feat_dim > 0 && h_feats ? s.d_feats : nullptr, img_h, img_w,
+    if (int rc = launch_step(ctx, s.d_dets, s.d_ndets, ctx->p.feat_dim > 0 && h_feats ? s.d_feats : nullptr, img_h, img_w,
                              s.d_out, s.d_nout, ctx->s_compute, ctx->p.err_slot + slot)) return rc;
     CU_TRY(cudaEventRecord(s.done, ctx->s_compute));
     CU_TRY(cudaStreamWaitEvent(ctx->s_d2h, s.done, 0));
@@ -324,7 +359,7 @@ extern "C" int b200track_step_host(b200track_ctx* ctx, const double* h_dets, con
 static inline uint64_t align16(uint64_t v) { return (v + 15) & ~(uint64_t)15; }
 
 static int row_bytes_of(const b200track_ctx* ctx) {
-    return ctx->cfg.kind == B200TRACK_OCSORT ? B200_ROW_OC : (ctx->cfg.kind == B200TRACK_BOTSORT ? B200_ROW_BOT : B200_ROW_BYTE);
+    return ctx->cfg.kind == B200TRACK_OCSORT ? B200_ROW_OC : (ctx->cfg.kind == B200TRACK_BOTSORT ? B200_ROW_BOT : B200_ROW_BYTE);   // DeepOCSORT: 40-byte rows
 }
 
 extern "C" int b200track_frame_layout(b200track_ctx* ctx, int64_t n_rows, int32_t det_dtype, b200track_layout* out) {
@@ -332,13 +367,13 @@ extern "C" int b200track_frame_layout(b200track_ctx* ctx, int64_t n_rows, int32_
     if (n_rows < 0 || (det_dtype != B200TRACK_F32 && det_dtype != B200TRACK_F64)) { set_error("bad n_rows / det_dtype"); return B200TRACK_ERR_ARG; }
     const uint64_t S = ctx->cfg.n_streams, R = (uint64_t)n_rows;
     const uint64_t det_row = det_dtype == B200TRACK_F32 ? 24 : 48;
-    const bool feats = ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid;
-    const bool warps = ctx->cfg.kind == B200TRACK_BOTSORT;
+    const bool feats = (ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid) || (ctx->cfg.kind == B200TRACK_DEEPOCSORT && !ctx->p.embedding_off);
+    const bool warps = ctx->cfg.kind == B200TRACK_BOTSORT || ctx->cfg.kind == B200TRACK_DEEPOCSORT;
     out->in_off_offsets = 0;
     out->in_off_warps = align16(4 * (S + 1));
     out->in_off_dets = align16(out->in_off_warps + (warps ? 48 * S : 0));
     out->in_off_feats = align16(out->in_off_dets + det_row * R);
-    out->in_bytes = align16(out->in_off_feats + (feats ? R * (uint64_t)ctx->cfg.feat_dim * 4 : 0));
+    out->in_bytes = align16(out->in_off_feats + (feats ? R * (uint64_t)ctx->p.feat_dim * 4 : 0));
     out->row_bytes = row_bytes_of(ctx);
     out->out_off_nout = 16;
     out->out_off_rows = align16(16 + 4 * S);
@@ -366,8 +401,11 @@ static int launch_packed(b200track_ctx* ctx, const unsigned char* d_in, int64_t 
     p.dets32 = det_dtype == B200TRACK_F32 ? reinterpret_cast<const float*>(d_in + L.in_off_dets) : nullptr;
     p.dets = det_dtype == B200TRACK_F64 ? reinterpret_cast<const double*>(d_in + L.in_off_dets) : nullptr;
     p.ndets = nullptr;
-    p.feats = (ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid) ? reinterpret_cast<const float*>(d_in + L.in_off_feats) : nullptr;
-    p.warps = (ctx->cfg.kind == B200TRACK_BOTSORT && (flags & B200TRACK_FRAME_HAS_WARPS)) ? reinterpret_cast<const double*>(d_in + L.in_off_warps) : nullptr;
+    const bool has_feats = (ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid) || (ctx->cfg.kind == B200TRACK_DEEPOCSORT && !ctx->p.embedding_off);
+    p.feats = has_feats ? reinterpret_cast<const float*>(d_in + L.in_off_feats) : nullptr;
+    p.warps = (flags & B200TRACK_FRAME_HAS_WARPS) ? reinterpret_cast<const double*>(d_in + L.in_off_warps) : nullptr;
+    if (p.warps && !(ctx->cfg.kind == B200TRACK_DEEPOCSORT || (ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.camera_motion))) {
+        set_error("camera-motion warps need a DeepOCSORT context or a BoT-SORT context created with camera_motion"); return B200TRACK_ERR_STATE; }
     p.out = nullptr;
     p.nout = reinterpret_cast<int*>(d_res + L.out_off_nout);
     p.rows = d_res + L.out_off_rows;
@@ -377,6 +415,7 @@ static int launch_packed(b200track_ctx* ctx, const unsigned char* d_in, int64_t 
     p.img_h = img_h; p.img_w = img_w;
     CU_TRY(cudaMemsetAsync(d_res, 0, 16, st));                  // header: [0] capacity bits of this step
     if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
+    else if (ctx->cfg.kind == B200TRACK_DEEPOCSORT) CU_TRY(b200::launch_deepocsort_step(p, ctx->variant, st));
     else if (ctx->cfg.kind == B200TRACK_BOTSORT) CU_TRY(b200::launch_botsort_step_packed(p, ctx->variant, st));
     else CU_TRY(b200::launch_bytetrack_step_packed(p, ctx->kf_kind, ctx->variant, st));
     ctx->launches += 1;
@@ -480,7 +519,8 @@ extern "C" int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state, uint64
     if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
     if (h_state) *h_state = (uint64_t)ctx->tcap * (ctx->nf * 8 + ctx->ni * 4) + 4 * sizeof(int) + sizeof(unsigned long long);
     if (h_smem) *h_smem = ctx->cfg.kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
-                                                            : b200::bytetrack_step_smem(ctx->variant, ctx->cfg.kind == B200TRACK_BOTSORT);
+                          : ctx->cfg.kind == B200TRACK_DEEPOCSORT ? b200::deepocsort_step_smem(ctx->variant)
+                          : b200::bytetrack_step_smem(ctx->variant, ctx->cfg.kind == B200TRACK_BOTSORT);
     return 0;
 }
 
@@ -496,6 +536,44 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
     CU_TRY(cudaMemcpy(h_counts, ctx->p.counts + 4 * s, 4 * sizeof(int), cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(f.data(), ctx->p.state_f + s * ctx->nf * T, f.size() * sizeof(double), cudaMemcpyDeviceToHost));
     CU_TRY(cudaMemcpy(iv.data(), ctx->p.state_i + s * ctx->ni * T, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    if (ctx->cfg.kind == B200TRACK_DEEPOCSORT) {
+        // alive slots in list order; h_rec = id (1-based like KalmanBoxTracker.count), age, time_since_update, hits, hit_streak,
+        // observed + 2 * frozen; h_mean = x[8]; h_cov = dense 8x8 P from the two 4x4 groups; h_aux = conf, cls, det_ind
+        static const int gidx[2][4] = {{0, 1, 4, 5}, {2, 3, 6, 7}};
+        int k = 0;
+        for (int t = 0; t < h_counts[0] && t < ctx->cfg.max_tracks; ++t) {
+            const int fl = iv[B200_OCI_FLAGS * T + t];
+            if (!(fl & 8)) continue;
+            if (h_rec) {
+                int32_t* r = h_rec + 6 * k;
+                r[0] = iv[B200_OCI_ID * T + t] + 1; r[1] = iv[B200_OCI_AGE * T + t]; r[2] = iv[B200_OCI_TSU * T + t];
+                r[3] = iv[B200_OCI_HITS * T + t]; r[4] = iv[B200_OCI_STREAK * T + t];
+                r[5] = (fl & B200_OCF_OBSERVED) | ((fl & B200_DOF_FROZEN) ? 2 : 0);
+            }
+            if (h_mean) for (int c = 0; c < 8; ++c) h_mean[8 * k + c] = f[(B200_DO_X + c) * T + t];
+            if (h_cov) {
+                double* c = h_cov + 64 * k;
+                for (int q = 0; q < 64; ++q) c[q] = 0.0;
+                for (int g = 0; g < 2; ++g) {
+                    int q = 0;
+                    for (int a = 0; a < 4; ++a)
+                        for (int b = a; b < 4; ++b) {
+                            const double v = f[((g ? B200_DO_PB : B200_DO_PA) + q) * T + t];
+                            c[gidx[g][a] * 8 + gidx[g][b]] = v; c[gidx[g][b] * 8 + gidx[g][a]] = v;
+                            ++q;
+                        }
+                }
+            }
+            if (h_aux) {
+                h_aux[3 * k + 0] = f[B200_DO_CONF * T + t];
+                h_aux[3 * k + 1] = f[B200_DO_CLS * T + t];
+                h_aux[3 * k + 2] = (double)iv[B200_OCI_DET * T + t];
+            }
+            ++k;
+        }
+        h_counts[0] = k; h_counts[1] = 0;
+        return 0;
+    }
     if (ctx->cfg.kind == B200TRACK_OCSORT) {
         // alive slots in list order; h_rec = id, age, time_since_update, hits, hit_streak, observed;
         // h_mean[8] = x[7], has-observation flag; h_cov = dense 7x7 P in the first 49 entries;
@@ -579,5 +657,45 @@ extern "C" int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, 
     const int n = counts[0] + counts[1];
     for (int t = 0; t < n && t < ctx->cfg.max_tracks; ++t)
         CU_TRY(cudaMemcpy(h_feat + (size_t)t * F, ctx->p.feat_pool + (s * T + rows[t]) * F, F * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int b200track_get_track_extras(b200track_ctx* ctx, int32_t stream_index, double* h_extra, double* h_emb) {
+    if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
+    if (ctx->cfg.kind != B200TRACK_DEEPOCSORT) { set_error("not a DeepOCSORT context"); return B200TRACK_ERR_STATE; }
+    if (stream_index < 0 || stream_index >= ctx->cfg.n_streams) { set_error("stream_index out of range"); return B200TRACK_ERR_ARG; }
+    ON_DEVICE(ctx);
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t T = ctx->tcap, s = stream_index, F = ctx->p.feat_dim;
+    int counts[4];
+    CU_TRY(cudaMemcpy(counts, ctx->p.counts + 4 * s, sizeof(counts), cudaMemcpyDeviceToHost));
+    std::vector<double> f((size_t)ctx->nf * T);
+    std::vector<int> iv((size_t)ctx->ni * T);
+    CU_TRY(cudaMemcpy(f.data(), ctx->p.state_f + s * ctx->nf * T, f.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(iv.data(), ctx->p.state_i + s * ctx->ni * T, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    int k = 0;
+    for (int t = 0; t < counts[0] && t < ctx->cfg.max_tracks; ++t) {
+        const int fl = iv[B200_OCI_FLAGS * T + t];
+        if (!(fl & 8)) continue;
+        if (h_extra) {
+            double* e = h_extra + 8 * k;
+            e[0] = f[(B200_DO_VEL + 0) * T + t]; e[1] = f[(B200_DO_VEL + 1) * T + t];
+            const bool has = fl & B200_OCF_HASOBS;
+            for (int q = 0; q < 4; ++q) e[2 + q] = has ? f[(B200_DO_LAST + q) * T + t] : -1.0;
+            e[6] = has ? f[B200_DO_CONF * T + t] : -1.0;
+            e[7] = 0.0;
+        }
+        if (h_emb && F > 0 && ctx->p.emb_pool)
+            CU_TRY(cudaMemcpy(h_emb + (size_t)k * F, ctx->p.emb_pool + (s * T + iv[B200_DOI_EROW * T + t]) * F, F * sizeof(double), cudaMemcpyDeviceToHost));
+        ++k;
+    }
+    return 0;
+}
+
+extern "C" int b200track_counters(b200track_ctx* ctx, uint64_t* h_out8) {
+    if (!ctx || !h_out8) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    ON_DEVICE(ctx);
+    CU_TRY(cudaDeviceSynchronize());
+    CU_TRY(cudaMemcpy(h_out8, ctx->p.stats, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return 0;
 }

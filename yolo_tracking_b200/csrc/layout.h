@@ -89,3 +89,28 @@
 #define B200_OCF_HASOBS 4
 // regular per-step traffic of a slot: x, P, last, conf, cls, vel, ring (37 doubles) + 10 ints
 #define B200_OC_SLOT_BYTES (37 * 8 + B200_OC_NI * 4)
+
+// ---- DeepOCSORT slot (deepocsort_step.cu) ---------------------------------------------------------
+// Same arrangement as the OC-SORT slot; the 8-d filter [x, y, w, h, vx, vy, vw, vh] keeps its covariance as the two
+// independent 4x4 blocks a camera warp leaves (kf44.cuh): group A = (x, y, vx, vy), group B = (w, h, vw, vh), each 10
+// numbers in upper-triangle order 00 01 02 03 11 12 13 22 23 33.  fp64 components:
+#define B200_DO_NF 80
+#define B200_DO_X 0          // x[8]
+#define B200_DO_PA 8         // group A covariance (10)
+#define B200_DO_PB 18        // group B covariance (10)
+#define B200_DO_LAST 28      // last_observation box
+#define B200_DO_CONF 32
+#define B200_DO_CLS 33
+#define B200_DO_VEL 34       // (dy, dx) / norm, zeros while None
+#define B200_DO_RING 36      // observations of the last 3 ages: ring[age % 3][4]
+#define B200_DO_HOT 48       // components touched every frame
+#define B200_DO_SX 48        // frozen x (8), frozen PA (10), frozen PB (10): attr_saved of the filter
+#define B200_DO_SPA 56
+#define B200_DO_SPB 66
+#define B200_DO_LASTZ 76     // last entry of the filter's observation history [4] (a measurement or a virtual box)
+// int32 components: the OC-SORT ones (B200_OCI_*) plus the row of the track in the stream's embedding pool
+// emb_pool[(s * Tmax + row) * feat_dim] (fp64: the reference's smoothed embedding is float64 after its first blend)
+#define B200_DO_NI 11
+#define B200_DOI_EROW 10
+#define B200_DOF_FROZEN 16   // flag bit 4: KalmanBoxTracker.frozen
+#define B200_DO_SLOT_BYTES (B200_DO_HOT * 8 + B200_DO_NI * 4)

@@ -28,6 +28,10 @@ struct StepParams {
     float* feat_pool;         // [S, Tcap, feat_dim] smoothed track embeddings, row-indexed (layout.h)
     float* feat_curr;         // [S, max_dets, feat_dim] scratch: this frame's twice-normalised detection embeddings
     double* cls_hist;         // [S, Tcap, 9] class-vote tables, row-indexed
+    // DeepOCSORT (deepocsort.yaml keys)
+    double w_assoc_emb, alpha_fixed_emb, aw_param;
+    int embedding_off, aw_off;
+    double* emb_pool;         // [S, Tcap, feat_dim] fp64 smoothed track embeddings, row-indexed (layout.h)
     // device state (layout.h)
     double* state_f;
     int* state_i;
@@ -36,6 +40,8 @@ struct StepParams {
     int* err;
     int* err_slot;            // [host slots] per-step capacity words of the padded host interface
     unsigned long long* dbg;  // [16] optional phase cycle counters, null = off
+    unsigned long long* stats;   // [8] event counters over all streams (b200track_counters): [0] first associations solved as an
+                                 // assignment problem, [1] recovery rounds that ran theirs, [2] observation-centric re-updates
     // per-step inputs / outputs (device)
     const double* dets;       // [S, max_dets, 6]
     const int* ndets;         // [S]
@@ -70,5 +76,7 @@ cudaError_t launch_botsort_step_packed(const StepParams& p, int variant, cudaStr
 size_t ocsort_step_smem(int variant);
 cudaError_t launch_ocsort_step(const StepParams& p, int variant, cudaStream_t stream);
 int step_variant_dmax(int variant);
+size_t deepocsort_step_smem(int variant);
+cudaError_t launch_deepocsort_step(const StepParams& p, int variant, cudaStream_t stream);
 
 }  // namespace b200
