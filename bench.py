@@ -74,6 +74,16 @@ WORKLOADS = {
                     b_slot=2 * (22 * 8 + 7 * 4 + 72), b_feat=3 * 512 * 4, kernel="bytetrack_step_kernel<BOT>", img_hw=(0, 0),
                     label="config3: BoT-SORT (botsort.yaml, identity camera motion, 512-d appearance embeddings), "
                           "100 objects/stream, sharded by stream"),
+    # config 4 as a TRACKER run: DeepOCSORT (Mahalanobis-free, appearance-weighted association) at 1024 streams.  det_thresh 0
+    # (deepocsort.yaml) keeps every false positive alive for max_age frames, so 190 objects give ~220 live trackers per stream
+    # in 256 slots and ~182 detections per frame.
+    "deepocsort": dict(kind="deepocsort", config=4, objects=190, streams=1024, max_dets=224, max_tracks=256, emb=512, distinct=128,
+                       steps=20, warmup=5,
+                       params=dict(det_thresh=0, max_age=30, min_hits=1, iou_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2,
+                                   w_association_emb=0.5, alpha_fixed_emb=0.95, aw_param=0.5),      # deepocsort.yaml through the factory
+                       b_slot=2 * (48 * 8 + 11 * 4), b_feat=512 * (8 + 8 + 4), kernel="deepocsort_step_kernel", img_hw=(2160, 3840),
+                       label="config4 as a tracker: DeepOCSORT (deepocsort.yaml: giou, det_thresh 0, min_hits 1, max_age 30, adaptive "
+                             "appearance weight, 512-d embeddings), 190 objects + ~30 false-positive trackers per stream, sharded by stream"),
 }
 W = dict(WORKLOADS["bytetrack"])          # the active workload (set in main)
 CONFIG_ID, N_OBJECTS, STREAMS_PER_GPU = W["config"], W["objects"], W["streams"]
@@ -100,7 +110,7 @@ def _stream_inputs(stream, n_frames):
     d = d.astype(np.float32).astype(np.float64)          # detector output precision; every consumer sees these values
     if e is not None:
         # the ReID seam (reid_multibackend.py:304-311): first-round rows / Frobenius norm of their matrix
-        high = PARAMS["track_high_thresh"]
+        high = PARAMS["track_high_thresh"] if W["kind"] == "botsort" else PARAMS["det_thresh"]
         feats = np.zeros_like(e)
         for f in range(n_frames):
             rows = np.nonzero(d[f, :n[f], 4] > high)[0]
@@ -165,6 +175,9 @@ def _make_oracle():
     if W["kind"] == "ocsort":
         from oracle.ocsort import OCSortOracle
         return OCSortOracle(False, use_byte=False, **PARAMS)
+    if W["kind"] == "deepocsort":
+        from oracle.deepocsort import DeepOCSortOracle
+        return DeepOCSortOracle(**PARAMS)
     from oracle.botsort import BoTSORTOracle
     return BoTSORTOracle(**PARAMS)
 
@@ -177,6 +190,10 @@ def _oracle_worker(args):
     def step(f):
         for k, t in enumerate(trks):
             d, n, e = data[k]
+            if W["kind"] == "deepocsort":
+                rows = d[f, :n[f], 4] > PARAMS["det_thresh"]
+                t.update(d[f, :n[f]], e[f, :n[f]][rows], W["img_hw"])
+                continue
             second = W["img_hw"] if W["kind"] == "ocsort" else (e[f, :n[f]] if e is not None else None)
             t.update(d[f, :n[f]], second)
     for f in range(warm):                         # pre-roll + warm-up frames, untimed
@@ -280,7 +297,12 @@ def run_b200(args, rank, world, local_rank):
     from yolo_tracking_b200.shard import shard_bounds
     stream0, stream1 = shard_bounds(S * world, rank, world)          # weak scaling: S streams per GPU, block-sharded
     assert stream1 - stream0 == S
-    dets_h, nd_h, feats_h = generate(S, stream0, F, gen_workers)     # fp32 [F, S, D, 6]
+    # workloads with large embeddings generate `distinct` streams and replicate them (physically: separate copies in HBM
+    # and in the pinned blocks, so nothing is shared between replicas but the values)
+    Sd = min(S, W.get("distinct", S))
+    assert S % Sd == 0
+    reps = S // Sd
+    dets_h, nd_h, feats_h = generate(Sd, rank * Sd if reps > 1 else stream0, F, gen_workers)     # fp32 [F, Sd, D, 6]
     t_gen = time.time() - t_gen
 
     cpu_base = None
@@ -299,9 +321,11 @@ def run_b200(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     # device leg: all frames resident in HBM as the padded fp64 [S, max_dets, 6] blocks of b200track_step
-    d_dets = torch.from_numpy(dets_h).to(dev).to(torch.float64)
-    d_nd = torch.from_numpy(nd_h).to(dev)
-    d_feats = torch.from_numpy(feats_h).to(dev) if feats_h is not None else None
+    d_dets = torch.from_numpy(dets_h).to(dev).to(torch.float64).repeat(1, reps, 1, 1)
+    d_nd = torch.from_numpy(nd_h).to(dev).repeat(1, reps)
+    d_feats = torch.from_numpy(feats_h).to(dev).repeat(1, reps, 1, 1) if feats_h is not None else None
+    if reps > 1:
+        nd_h = np.tile(nd_h, (1, reps))
     hw = W["img_hw"]
 
     def feats_dev(f):
@@ -368,7 +392,8 @@ def run_b200(args, rank, world, local_rank):
     for k in range(n_e2e):
         f = PREROLL + k
         blk, _ = trk.frame_buffers(max_rows=int(nd_h[f].sum()))
-        r, fl = trk.pack(blk, dets_h[f], ndets=nd_h[f], feats=None if feats_h is None else feats_h[f], dtype=np.float32)
+        r, fl = trk.pack(blk, np.tile(dets_h[f], (reps, 1, 1)) if reps > 1 else dets_h[f], ndets=nd_h[f],
+                         feats=None if feats_h is None else (np.tile(feats_h[f], (reps, 1, 1)) if reps > 1 else feats_h[f]), dtype=np.float32)
         in_blocks.append(blk); rows_of.append(r); flags_of.append(fl)
     out_blocks = [trk.frame_buffers(max_rows=max_rows)[1] for _ in range(nslot)]
     del dets_h
@@ -465,6 +490,7 @@ def run_b200(args, rank, world, local_rank):
                              ("per-step working set ~%.0f MB: a 256 MB buffer is read between steps (L2 flush), outside "
                               "the per-step event pairs; value = units / sum of step times" % (working_set / 1e6)),
                        "preroll_frames": PREROLL, "detections": "fp32-representable values (detector precision)",
+                       "distinct_streams_per_gpu": Sd,
                        "data_gen_s": round(t_gen, 1)},
             "p50_step_ms": float(np.percentile(step_ms, 50)), "p99_step_ms": float(np.percentile(step_ms, 99)),
             "e2e": {"value": tu_e2e_all / (e2e_ms_max * 1e-3), "unit": "track-updates/s",
@@ -496,17 +522,21 @@ def run_b200(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=None, help="default 100 (20 for the embedding-heavy deepocsort workload)")
+    ap.add_argument("--warmup", type=int, default=None, help="default 20 (5 for deepocsort)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="bytetrack", choices=sorted(WORKLOADS),
-                    help="bytetrack = BASELINE config 5 (the headline); ocsort = config 2; botsort = config 3")
+                    help="bytetrack = BASELINE config 5 (the headline); ocsort = config 2; botsort = config 3; deepocsort = config 4 as a tracker")
     ap.add_argument("--streams", type=int, default=0, help="streams per GPU (default: the workload's own count)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     select_workload(args.workload)
     if args.streams <= 0:
         args.streams = STREAMS_PER_GPU
+    if args.steps is None:
+        args.steps = W.get("steps", 100)
+    if args.warmup is None:
+        args.warmup = W.get("warmup", 20)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     _claim_stdout()
     rank = int(os.environ.get("RANK", 0))

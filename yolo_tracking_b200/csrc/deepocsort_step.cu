@@ -189,8 +189,26 @@ deepocsort_step_kernel(const StepParams p) {
     const float* dfeat = !emb_on ? nullptr : (packed ? p.feats + (size_t)roff * F : p.feats + (size_t)s * p.max_dets * F);
     const double* wp = p.warps ? p.warps + 6 * s : nullptr;
 
+
+    // ---- HBM -> shared memory: detections ------------------------------------------------------------
+    {
+        const double* g = packed ? p.dets + (size_t)roff * 6 : p.dets + (size_t)s * p.max_dets * 6;
+        const float* g32 = p.dets32 ? p.dets32 + (size_t)roff * 6 : nullptr;
+        for (int i = tid; i < nd * 6; i += NT) {
+            const double val = g32 ? (double)g32[i] : g[i];
+            const int j = i / 6, c = i - 6 * j;
+            if (c < 4) sm.dbox[c][j] = val;
+            else if (c == 4) sm.dconf[j] = val;
+        }
+    }
+    const double* dets_g = packed ? p.dets + (size_t)roff * 6 : p.dets + (size_t)s * p.max_dets * 6;
+    const float* dets32_g = p.dets32 ? p.dets32 + (size_t)roff * 6 : nullptr;
+    auto det_cls = [&](int j) -> double { return dets32_g ? (double)dets32_g[j * 6 + 5] : dets_g[j * 6 + 5]; };
+    // detections above det_thresh: the only ones that can start a tracker this frame
+    __syncthreads();
+    const int nhigh = __syncthreads_count(tid < nd && sm.dconf[tid] > p.det_thresh);
     // ---- compaction on demand (see ocsort_step.cu) ------------------------------------------------
-    if (n0 > alive0 && n0 + nd > tcap) {                 // uniform
+    if (n0 > alive0 && n0 + nhigh > tcap) {              // uniform
         bool lv = false;
         if (t < n0) lv = gi[B200_OCI_FLAGS * TMAX + t] & OCF_ALIVE;
         unsigned long long tt;
@@ -221,21 +239,6 @@ deepocsort_step_kernel(const StepParams p) {
         __syncthreads();
         n0 = (int)tt;
     }
-
-    // ---- HBM -> shared memory: detections ------------------------------------------------------------
-    {
-        const double* g = packed ? p.dets + (size_t)roff * 6 : p.dets + (size_t)s * p.max_dets * 6;
-        const float* g32 = p.dets32 ? p.dets32 + (size_t)roff * 6 : nullptr;
-        for (int i = tid; i < nd * 6; i += NT) {
-            const double val = g32 ? (double)g32[i] : g[i];
-            const int j = i / 6, c = i - 6 * j;
-            if (c < 4) sm.dbox[c][j] = val;
-            else if (c == 4) sm.dconf[j] = val;
-        }
-    }
-    const double* dets_g = packed ? p.dets + (size_t)roff * 6 : p.dets + (size_t)s * p.max_dets * 6;
-    const float* dets32_g = p.dets32 ? p.dets32 + (size_t)roff * 6 : nullptr;
-    auto det_cls = [&](int j) -> double { return dets32_g ? (double)dets32_g[j * 6 + 5] : dets_g[j * 6 + 5]; };
 
     // ---- tracker side, thread t = slot t: camera correction, predict -----------------------------
     int fl = 0, age = 0, tsu = 0, streak = 0;

@@ -199,40 +199,6 @@ ocsort_step_kernel(const StepParams p) {
     if (nd < 0) nd = 0;
     double* gf = p.state_f + (size_t)s * B200_OC_NF * TMAX;
     int* gi = p.state_i + (size_t)s * B200_OC_NI * TMAX;
-    // ---- compaction on demand: dead trackers leave holes in the slot range; the live ones move down (order kept) only
-    // when this frame's detections - an upper bound of its new trackers - might not fit behind the range otherwise
-    // (every ~10-20 frames at config 2; doing it whenever the range passed max_tracks - max_dets meant every frame)
-    if (n0 > alive0 && n0 + nd > tcap) {                 // uniform
-        bool lv = false;
-        if (t < n0) lv = gi[B200_OCI_FLAGS * TMAX + t] & OCF_ALIVE;
-        unsigned long long tt;
-        const int dst = (int)block_exscan<NT>(lv ? 1ull : 0ull, sm.scratch, tt);
-        for (int c0 = 0; c0 < B200_OC_NF; c0 += 8) {
-            double tmp[8];
-            if (lv && dst != t) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) if (c0 + c < B200_OC_NF) tmp[c] = gf[(c0 + c) * TMAX + t];
-            }
-            __syncthreads();
-            if (lv && dst != t) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) if (c0 + c < B200_OC_NF) gf[(c0 + c) * TMAX + dst] = tmp[c];
-            }
-            __syncthreads();
-        }
-        int itmp[B200_OC_NI];
-        if (lv && dst != t) {
-#pragma unroll
-            for (int c = 0; c < B200_OC_NI; ++c) itmp[c] = gi[c * TMAX + t];
-        }
-        __syncthreads();
-        if (lv && dst != t) {
-#pragma unroll
-            for (int c = 0; c < B200_OC_NI; ++c) gi[c * TMAX + dst] = itmp[c];
-        }
-        __syncthreads();
-        n0 = (int)tt;
-    }
     const double thr = p.iou_thresh, W = p.img_w, H = p.img_h;
     const int func = p.asso_func;
 
@@ -279,6 +245,43 @@ ocsort_step_kernel(const StepParams p) {
     const double* dets_g = packed ? p.dets + (size_t)roff * 6 : p.dets + (size_t)s * p.max_dets * 6;
     const float* dets32_g = p.dets32 ? p.dets32 + (size_t)roff * 6 : nullptr;
     auto det_cls = [&](int j) -> double { return dets32_g ? (double)dets32_g[j * 6 + 5] : dets_g[j * 6 + 5]; };
+    // detections above det_thresh: the only ones that can start a tracker this frame
+    __syncthreads();
+    const int nhigh = __syncthreads_count(tid < nd && sm.dconf[tid] > p.det_thresh);
+    // ---- compaction on demand: dead trackers leave holes in the slot range; the live ones move down (order kept) only
+    // when this frame's detections above det_thresh - an upper bound of its new trackers - might not fit behind the range otherwise
+    // (every ~10-20 frames at config 2; doing it whenever the range passed max_tracks - max_dets meant every frame)
+    if (n0 > alive0 && n0 + nhigh > tcap) {              // uniform
+        bool lv = false;
+        if (t < n0) lv = gi[B200_OCI_FLAGS * TMAX + t] & OCF_ALIVE;
+        unsigned long long tt;
+        const int dst = (int)block_exscan<NT>(lv ? 1ull : 0ull, sm.scratch, tt);
+        for (int c0 = 0; c0 < B200_OC_NF; c0 += 8) {
+            double tmp[8];
+            if (lv && dst != t) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c0 + c < B200_OC_NF) tmp[c] = gf[(c0 + c) * TMAX + t];
+            }
+            __syncthreads();
+            if (lv && dst != t) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) if (c0 + c < B200_OC_NF) gf[(c0 + c) * TMAX + dst] = tmp[c];
+            }
+            __syncthreads();
+        }
+        int itmp[B200_OC_NI];
+        if (lv && dst != t) {
+#pragma unroll
+            for (int c = 0; c < B200_OC_NI; ++c) itmp[c] = gi[c * TMAX + t];
+        }
+        __syncthreads();
+        if (lv && dst != t) {
+#pragma unroll
+            for (int c = 0; c < B200_OC_NI; ++c) gi[c * TMAX + dst] = itmp[c];
+        }
+        __syncthreads();
+        n0 = (int)tt;
+    }
     int fl = 0, age = 0, tsu = 0, streak = 0;
     bool live = false;
     if (t < n0) {
