@@ -30,8 +30,10 @@ def _check_state(st, snap, what, with_reid):
         assert np.abs(st["smooth_feat"] - snap["smooth_feat"]).max() < FEAT_TOL, what + " smooth_feat"
 
 
-@pytest.mark.parametrize("name", ["botsort_c3", "botsort_churn", "botsort_noreid", "botsort_fuse"])
-def test_botsort_replays_reference_golden(name):
+@pytest.mark.parametrize("name,cam", [("botsort_c3", False), ("botsort_churn", False), ("botsort_noreid", False), ("botsort_fuse", False),
+                                      ("botsort_cam", True),          # a scripted moving camera: warps applied inside the fused step
+                                      ("botsort_churn", True)])       # the camera-motion form of the filter without warps = identity
+def test_botsort_replays_reference_golden(name, cam):
     from yolo_tracking_b200.batch import BatchedTracker
     sc, cfg, dets, nd, feats, g = botsort_scenario(name)
     with_reid = cfg.get("with_reid", True)
@@ -39,7 +41,7 @@ def test_botsort_replays_reference_golden(name):
     cap = 64 if D <= 64 else 128
     F = sc["emb_dim"] if with_reid else 0
     Fpad = (F + 127) // 128 * 128
-    trk = BatchedTracker("botsort", 1, max_tracks=cap, max_dets=cap, feat_dim=Fpad, **_cfg_kwargs(cfg))
+    trk = BatchedTracker("botsort", 1, max_tracks=cap, max_dets=cap, feat_dim=Fpad, camera_motion=cam, **_cfg_kwargs(cfg))
     cov_frames = {int(f): k for k, f in enumerate(g["cov_frames"])}
     cov_offs = [0]
     for f in g["cov_frames"]:
@@ -50,7 +52,12 @@ def test_botsort_replays_reference_golden(name):
         d[0, :D] = dets[f]
         if with_reid:
             ft[0, :D, :F] = feats[f]
-        out, nout = trk.update_batch(d, np.array([nd[f]], dtype=np.int32), feats=ft)
+        if cam:     # packed frames carry the warp of every stream (b200track_submit_packed)
+            rows = trk.update_frames([dets[f, :nd[f]]], feats=None if ft is None else [ft[0, :nd[f]]],
+                                     warps=None if sc["warps"] is None else sc["warps"][f].reshape(1, 6))[0]
+            out, nout = rows[None], np.array([len(rows)])
+        else:
+            out, nout = trk.update_batch(d, np.array([nd[f]], dtype=np.int32), feats=ft)
         ref = g["out"][g["out_offs"][f]:g["out_offs"][f + 1]]
         assert nout[0] == len(ref), f"{name} frame {f}: {nout[0]} rows vs {len(ref)}"
         o = out[0, :nout[0]]
@@ -162,3 +169,34 @@ def test_botsort_reference_shaped_api():
             assert_close(out[:, :4], ref[:, :4])
     with pytest.raises(AssertionError):
         trk.update(np.zeros((2, 5)), img)
+
+
+def test_botsort_camera_warp_needs_the_camera_form():
+    """A context created without camera_motion refuses warps (error, not silently wrong tracks); the device interface
+    b200track_step_cam applies them like the packed one."""
+    import torch
+    from yolo_tracking_b200 import _lib
+    from yolo_tracking_b200.batch import BatchedTracker
+    sc, cfg, dets, nd, feats, g = botsort_scenario("botsort_cam")
+    kw = _cfg_kwargs(cfg)
+    plain = BatchedTracker("botsort", 1, max_tracks=64, max_dets=64, feat_dim=128, **kw)
+    with pytest.raises(_lib.B200TrackError) as e:
+        plain.update_frames([dets[0, :nd[0]]], feats=[np.zeros((nd[0], 128), dtype=np.float32)], warps=sc["warps"][0].reshape(1, 6))
+    assert e.value.code == _lib.ERR_STATE
+    plain.close()
+    a = BatchedTracker("botsort", 1, max_tracks=64, max_dets=64, feat_dim=128, camera_motion=True, **kw)
+    b = BatchedTracker("botsort", 1, max_tracks=64, max_dets=64, feat_dim=128, camera_motion=True, **kw)
+    D, F = dets.shape[1], sc["emb_dim"]
+    d_out = torch.zeros((1, 64, 8), dtype=torch.float64, device="cuda")
+    d_nout = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    for f in range(30):
+        ft = np.zeros((nd[f], 128), dtype=np.float32)
+        ft[:, :F] = feats[f][:nd[f]]
+        ref = a.update_frames([dets[f, :nd[f]]], feats=[ft], warps=sc["warps"][f].reshape(1, 6))[0]
+        dd = np.zeros((1, 64, 6)); dd[0, :nd[f]] = dets[f, :nd[f]]
+        df = np.zeros((1, 64, 128), dtype=np.float32); df[0, :nd[f]] = ft
+        b.step_device(torch.from_numpy(dd).cuda(), torch.tensor([nd[f]], dtype=torch.int32, device="cuda"), d_out, d_nout,
+                      d_feats=torch.from_numpy(df).cuda(), d_warps=torch.from_numpy(sc["warps"][f].reshape(1, 6).copy()).cuda())
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out[0, :int(d_nout[0])].cpu().numpy(), ref), f
+    a.close(); b.close()

@@ -169,7 +169,10 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         p.embedding_off = cfg->embedding_off ? 1 : 0; p.aw_off = cfg->aw_off ? 1 : 0;
         if (p.embedding_off) p.feat_dim = 0;
     }
-    if (cfg->kind == B200TRACK_BOTSORT) { ctx->ni = B200_NI_BOT; p.with_reid = cfg->with_reid ? 1 : 0; p.fuse_first = cfg->fuse_first_associate ? 1 : 0; }
+    if (cfg->kind == B200TRACK_BOTSORT) {
+        ctx->ni = B200_NI_BOT; p.with_reid = cfg->with_reid ? 1 : 0; p.fuse_first = cfg->fuse_first_associate ? 1 : 0;
+        if (cfg->camera_motion) ctx->nf = B200_NF_CAM;
+    }
     ctx->kf_kind = cfg->kind == B200TRACK_BOTSORT ? B200TRACK_KF_XYWH : B200TRACK_KF_XYAH;
     ctx->variant = b200::bytetrack_step_variant(cfg->max_tracks, cfg->max_dets);
     if (ctx->variant < 0) { set_error("no kernel variant covers max_tracks / max_dets"); delete ctx; return B200TRACK_ERR_CAPACITY; }
@@ -213,7 +216,7 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     }
     const size_t smem = cfg->kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
                         : cfg->kind == B200TRACK_DEEPOCSORT ? b200::deepocsort_step_smem(ctx->variant)
-                        : b200::bytetrack_step_smem(ctx->variant, cfg->kind == B200TRACK_BOTSORT);
+                        : b200::bytetrack_step_smem(ctx->variant, cfg->kind == B200TRACK_BOTSORT, cfg->kind == B200TRACK_BOTSORT && cfg->camera_motion);
     int max_smem = 0;
     CU_TRY_CTX(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
     if (smem > (size_t)max_smem) {
@@ -240,7 +243,7 @@ static int launch_step(b200track_ctx* ctx, const double* d_dets, const int32_t* 
     } else if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
     else if (ctx->cfg.kind == B200TRACK_BOTSORT) {
         if (p.with_reid && !d_feats) { set_error("BoT-SORT with_reid: the embedding buffer is NULL"); return B200TRACK_ERR_ARG; }
-        CU_TRY(b200::launch_botsort_step(p, ctx->variant, st));
+        CU_TRY(b200::launch_botsort_step(p, ctx->variant, st, ctx->cfg.camera_motion != 0));
     } else CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, ctx->variant, st));
     ctx->launches += 1;
     return 0;
@@ -416,7 +419,7 @@ static int launch_packed(b200track_ctx* ctx, const unsigned char* d_in, int64_t 
     CU_TRY(cudaMemsetAsync(d_res, 0, 16, st));                  // header: [0] capacity bits of this step
     if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
     else if (ctx->cfg.kind == B200TRACK_DEEPOCSORT) CU_TRY(b200::launch_deepocsort_step(p, ctx->variant, st));
-    else if (ctx->cfg.kind == B200TRACK_BOTSORT) CU_TRY(b200::launch_botsort_step_packed(p, ctx->variant, st));
+    else if (ctx->cfg.kind == B200TRACK_BOTSORT) CU_TRY(b200::launch_botsort_step_packed(p, ctx->variant, st, ctx->cfg.camera_motion != 0));
     else CU_TRY(b200::launch_bytetrack_step_packed(p, ctx->kf_kind, ctx->variant, st));
     ctx->launches += 1;
     return 0;
@@ -520,7 +523,7 @@ extern "C" int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state, uint64
     if (h_state) *h_state = (uint64_t)ctx->tcap * (ctx->nf * 8 + ctx->ni * 4) + 4 * sizeof(int) + sizeof(unsigned long long);
     if (h_smem) *h_smem = ctx->cfg.kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
                           : ctx->cfg.kind == B200TRACK_DEEPOCSORT ? b200::deepocsort_step_smem(ctx->variant)
-                          : b200::bytetrack_step_smem(ctx->variant, ctx->cfg.kind == B200TRACK_BOTSORT);
+                          : b200::bytetrack_step_smem(ctx->variant, ctx->cfg.kind == B200TRACK_BOTSORT, ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.camera_motion);
     return 0;
 }
 
@@ -625,9 +628,22 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
             r[3] = iv[B200_TI_FRAME * T + t]; r[4] = iv[B200_TI_START * T + t]; r[5] = iv[B200_TI_LEN * T + t];
         }
         if (h_mean) for (int c = 0; c < 8; ++c) h_mean[8 * t + c] = f[(B200_TF_MEAN + c) * T + t];
+        const bool cam = ctx->nf == B200_NF_CAM;
         if (h_cov) {
             double* c = h_cov + 64 * t;
             for (int k = 0; k < 64; ++k) c[k] = 0.0;
+            if (cam) {
+                static const int gidx[2][4] = {{0, 1, 4, 5}, {2, 3, 6, 7}};
+                for (int g = 0; g < 2; ++g) {
+                    int q = 0;
+                    for (int a = 0; a < 4; ++a)
+                        for (int b = a; b < 4; ++b) {
+                            const double v = f[((g ? B200_TFC_COVB : B200_TFC_COVA) + q) * T + t];
+                            c[gidx[g][a] * 8 + gidx[g][b]] = v; c[gidx[g][b] * 8 + gidx[g][a]] = v;
+                            ++q;
+                        }
+                }
+            } else
             for (int a = 0; a < 4; ++a) {
                 c[a * 8 + a] = f[(B200_TF_COV + 3 * a + 0) * T + t];
                 c[a * 8 + a + 4] = c[(a + 4) * 8 + a] = f[(B200_TF_COV + 3 * a + 1) * T + t];
@@ -635,8 +651,8 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
             }
         }
         if (h_aux) {
-            h_aux[3 * t + 0] = f[B200_TF_SCORE * T + t];
-            h_aux[3 * t + 1] = f[B200_TF_CLS * T + t];
+            h_aux[3 * t + 0] = f[(cam ? B200_TFC_SCORE : B200_TF_SCORE) * T + t];
+            h_aux[3 * t + 1] = f[(cam ? B200_TFC_CLS : B200_TF_CLS) * T + t];
             h_aux[3 * t + 2] = (double)iv[B200_TI_DET * T + t];
         }
     }

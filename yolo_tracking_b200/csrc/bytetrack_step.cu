@@ -44,6 +44,7 @@
 
 #include "boxes.cuh"
 #include "kf.cuh"
+#include "kf44.cuh"
 #include "lap_sparse.cuh"
 #include "layout.h"
 #include "step_params.h"
@@ -86,7 +87,7 @@ struct BotSmem<TMAX, DMAX, true> {
     unsigned char rowused[TMAX];
 };
 
-template <int TMAX, int DMAX, bool BOT = false>
+template <int TMAX, int DMAX, bool BOT = false, bool CAM = false>
 struct alignas(16) StepSmem {
     static constexpr int TCAP = TMAX;
     static constexpr int DW = DMAX / 32;
@@ -118,7 +119,7 @@ struct alignas(16) StepSmem {
             short rnext[TMAX];
             short yc[DMAX], pred[DMAX], nextc[DMAX], mark[DMAX], scn[DMAX];
         };
-        double park[12][TMAX];
+        double park[CAM ? 20 : 12][TMAX];       // CAM: the two 4x4 covariance blocks of a camera-corrected filter
     };
     int frame_t[TMAX], start_t[TMAX];
     int coldeg[DMAX], ncomplex[4];
@@ -533,12 +534,16 @@ __device__ __forceinline__ double cls_vote(double* h, double cls, double score, 
     return out;
 }
 
-template <int NT, int KIND, int TMAX, int DMAX, bool BOT>
-__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : (NT == 256 ? 3 : (NT == 224 ? (BOT ? 3 : 4) : (NT == 128 ? 6 : 8)))))
+template <int NT, int KIND, int TMAX, int DMAX, bool BOT, bool CAM = false>
+__global__ void __launch_bounds__(NT, (NT >= 512 ? 1 : (NT == 256 ? (CAM ? 2 : 3) : (NT == 224 ? (BOT ? (CAM ? 2 : 3) : 4) : (NT == 128 ? (CAM ? 4 : 6) : 8)))))
 bytetrack_step_kernel(const StepParams p) {
     static_assert(NT == TMAX && DMAX <= NT, "one thread per track slot; detections fit one pass");
     static_assert(!BOT || KIND == KF_XYWH, "BoT-SORT runs on the XYWH filter");
-    using SM = StepSmem<TMAX, DMAX, BOT>;
+    static_assert(!CAM || BOT, "camera-motion warps belong to BoT-SORT (bot_sort.py:293-295)");
+    using SM = StepSmem<TMAX, DMAX, BOT, CAM>;
+    // CAM: the covariance is two 4x4 blocks (layout.h: B200_NF_CAM) and the frame's warp is applied after the motion step
+    constexpr int NFk = CAM ? B200_NF_CAM : B200_NF, TF_SCORE = CAM ? B200_TFC_SCORE : B200_TF_SCORE, TF_CLS = CAM ? B200_TFC_CLS : B200_TF_CLS;
+    const double* wp = (CAM && p.warps) ? p.warps + 6 * blockIdx.x : nullptr;
     constexpr int NI = BOT ? B200_NI_BOT : B200_NI;
     // ByteTrack: the candidates of the second association are collected while the first one is built (one walk, one IoU
     // per pair for both); BoT-SORT keeps two separate builds (its second pass has its own appearance stage)
@@ -557,7 +562,7 @@ bytetrack_step_kernel(const StepParams p) {
     // stream's counters: all TMAX slots and max_dets detection rows are fetched (one memory latency instead of
     // two dependent ones); what lies beyond n / nd is never looked at.
     const int t = tid;                                   // this thread's track slot
-    const double* gf = p.state_f + (size_t)s * B200_NF * TMAX;
+    const double* gf = p.state_f + (size_t)s * NFk * TMAX;
     const int* gi = p.state_i + (size_t)s * NI * TMAX;
     // packed frames: the rows of all streams lie back to back, fp32 or fp64 (step_params.h); the row offset of the stream
     // is one more dependent load, which the stream ahead prefetched to L2
@@ -601,7 +606,7 @@ bytetrack_step_kernel(const StepParams p) {
                 nl_d = (n2 * rb + 127) >> 7;
                 if (tid == 0 && s2 + AHEAD < p.n_streams) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.det_off + s2 + AHEAD));
             }
-            const char* f2 = reinterpret_cast<const char*>(p.state_f + (size_t)s2 * B200_NF * TMAX);
+            const char* f2 = reinterpret_cast<const char*>(p.state_f + (size_t)s2 * NFk * TMAX);
             const char* i2 = reinterpret_cast<const char*>(p.state_i + (size_t)s2 * NI * TMAX);
             const int nl_f = (8 * TMAX * 8 + 127) >> 7, nl_i = (NI * TMAX * 4 + 127) >> 7;   // B200_TF_MEAN == 0
             for (int l = tid; l < nl_d + nl_f + nl_i; l += NT) {
@@ -653,7 +658,7 @@ bytetrack_step_kernel(const StepParams p) {
         // the covariance / id / score lines are first used after the association: pull them into L2 now
         if (t < n && (t & 15) == 0) {
 #pragma unroll
-            for (int c = B200_TF_COV; c < B200_NF; ++c)
+            for (int c = B200_TF_COV; c < NFk; ++c)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(gf + c * TMAX + t));
         }
         if (t < n && (t & 31) == 0) {
@@ -712,6 +717,17 @@ bytetrack_step_kernel(const StepParams p) {
             }
 #pragma unroll
             for (int i = 0; i < 4; ++i) sm.mean[i][t] = xadd(sm.mean[i][t], vel[i]);
+        }
+        if constexpr (CAM) {
+            // STrack.multi_gmc (bot_sort.py:95-111) on the pool AND the unconfirmed tracks: the position half here (the
+            // association sees the corrected boxes), velocities and covariance in the Kalman phase with the same operations
+            if (wp) {
+                const double M[4] = {wp[0], wp[1], wp[3], wp[4]}, tv[2] = {wp[2], wp[5]};
+                double x = sm.mean[0][t], y = sm.mean[1][t], w = sm.mean[2][t], h = sm.mean[3][t];
+                g4_warp_pair(M, tv, x, y);
+                g4_warp_pair(M, nullptr, w, h);
+                sm.mean[0][t] = x; sm.mean[1][t] = y; sm.mean[2][t] = w; sm.mean[3][t] = h;
+            }
         }
         sm.rowtype[t] = role != ROLE_UNCONF ? RT_A : (FUSE2 ? RT_B : RT_NONE);
         sm.match[t] = -1;
@@ -858,17 +874,23 @@ bytetrack_step_kernel(const StepParams p) {
             j = sm.xr[t];
             if (j >= 0) sm.dflag[j] |= DF_USED; else unmatched2 = true;
         }
+        G4 gA, gB;                                      // CAM only
+        if constexpr (!CAM) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             ks.pp[i] = gf[(B200_TF_COV + 3 * i + 0) * TMAX + t];
             ks.pv[i] = gf[(B200_TF_COV + 3 * i + 1) * TMAX + t];
             ks.vv[i] = gf[(B200_TF_COV + 3 * i + 2) * TMAX + t];
         }
+        } else {
+            g4_load(gA, gf + (size_t)B200_TFC_COVA * TMAX + t, TMAX);
+            g4_load(gB, gf + (size_t)B200_TFC_COVB * TMAX + t, TMAX);
+        }
         tid_id = gi[B200_TI_ID * TMAX + t];
         len = gi[B200_TI_LEN * TMAX + t];
         det_ind = gi[B200_TI_DET * TMAX + t];
-        score = gf[B200_TF_SCORE * TMAX + t];
-        cls = gf[B200_TF_CLS * TMAX + t];
+        score = gf[TF_SCORE * TMAX + t];
+        cls = gf[TF_CLS * TMAX + t];
         start = sm.start_t[t];
 #pragma unroll
         for (int c = 0; c < 4; ++c) ks.m[c] = sm.mean[c][t];
@@ -879,7 +901,26 @@ bytetrack_step_kernel(const StepParams p) {
             ks.m[7] = 0.0;
             if (KIND == KF_XYWH) ks.m[6] = 0.0;
         }
-        if (role != ROLE_UNCONF) {
+        if constexpr (CAM) {
+            // the whole filter step again from the stored state, with the operations of the motion step above: predict
+            // (pool only), camera correction, so that the positions equal sm.mean bit for bit
+            double m8[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) m8[c] = gf[(B200_TF_MEAN + c) * TMAX + t];
+            gA.m[0] = m8[0]; gA.m[1] = m8[1]; gA.m[2] = ks.m[4]; gA.m[3] = ks.m[5];
+            gB.m[0] = m8[2]; gB.m[1] = m8[3]; gB.m[2] = ks.m[6]; gB.m[3] = ks.m[7];
+            if (role != ROLE_UNCONF) {
+                const double spw = xmul(KF_W_POS, ref_w), sph = xmul(KF_W_POS, ref_h), svw = xmul(KF_W_VEL, ref_w), svh = xmul(KF_W_VEL, ref_h);
+                const double q[4] = {xmul(spw, spw), xmul(sph, sph), xmul(svw, svw), xmul(svh, svh)};
+                g4_predict(gA, q);
+                g4_predict(gB, q);
+            }
+            if (wp) {
+                const double M[4] = {wp[0], wp[1], wp[3], wp[4]}, tv[2] = {wp[2], wp[5]};
+                g4_warp(gA, M, tv);
+                g4_warp(gB, M, nullptr);
+            }
+        } else if (role != ROLE_UNCONF) {
             // covariance half of multi_predict; the noise uses the pre-motion w / h
             double ref4[4] = {0.0, 0.0, ref_w, ref_h};
 #pragma unroll
@@ -898,9 +939,18 @@ bytetrack_step_kernel(const StepParams p) {
         if (j >= 0) {                                   // STrack.update / re_activate
             double z[4];
             det_measurement<KIND>(sm, j, z);
+            if constexpr (CAM) {
+                // botsort_kf.py:193-225 on the two blocks: measurement noise from the (corrected) state's w, h
+                const double sw = xmul(KF_W_POS, gB.m[0]), sh = xmul(KF_W_POS, gB.m[1]);
+                const double r[2] = {xmul(sw, sw), xmul(sh, sh)};
+                g4_update_chol(gA, z, r);
+                g4_update_chol(gB, z + 2, r);
+                sm.mean[0][t] = gA.m[0]; sm.mean[1][t] = gA.m[1]; sm.mean[2][t] = gB.m[0]; sm.mean[3][t] = gB.m[1];
+            } else {
             kf_update<KIND>(ks, z);
 #pragma unroll
             for (int c = 0; c < 4; ++c) sm.mean[c][t] = ks.m[c];
+            }
             len = (st0 == B200_ST_TRACKED) ? len + 1 : 0;
             frame_t = frame;
             det_ind = j;
@@ -915,10 +965,16 @@ bytetrack_step_kernel(const StepParams p) {
         } else if (unmatched2) {
             fl = (fl & ~3) | (role == ROLE_TRACKED ? B200_ST_LOST : B200_ST_REMOVED);   // mark_lost / mark_removed
         }
+        if constexpr (CAM) {
+            g4_store(gA, &sm.park[0][t], TMAX);
+            g4_store(gB, &sm.park[10][t], TMAX);
+            velo[0] = gA.m[2]; velo[1] = gA.m[3]; velo[2] = gB.m[2]; velo[3] = gB.m[3];
+        } else {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             sm.park[3 * i + 0][t] = ks.pp[i]; sm.park[3 * i + 1][t] = ks.pv[i]; sm.park[3 * i + 2][t] = ks.vv[i];
             velo[i] = ks.m[4 + i];
+        }
         }
         int st = fl & 3;
         const bool sticky_old = fl & B200_FLAG_STICKY;      // id already in removed_stracks
@@ -1068,7 +1124,7 @@ bytetrack_step_kernel(const StepParams p) {
     //   slots: [0) keep, [10) refound, [20) lostOld, [30) lostNew ; dets: [40) born kept, [50) born (all)
     // Every CAT_KEEP / CAT_REFOUND entry is activated, so output rows = keep ++ born (frame 1 only) ++ refound.
     const bool born_active = frame == 1;                 // STrack.activate: is_activated only on frame 1
-    double* wf = p.state_f + (size_t)s * B200_NF * TMAX;
+    double* wf = p.state_f + (size_t)s * NFk * TMAX;
     int* wi = p.state_i + (size_t)s * NI * TMAX;
     double* gout = packed ? nullptr : p.out + (size_t)s * p.max_tracks * 8;
     const int out_cap = packed ? min(p.max_tracks, nd_in) : p.max_tracks;
@@ -1130,14 +1186,19 @@ bytetrack_step_kernel(const StepParams p) {
             for (int c = 0; c < 4; ++c) wf[(B200_TF_MEAN + c) * TMAX + dst] = sm.mean[c][t];
 #pragma unroll
             for (int c = 0; c < 4; ++c) wf[(B200_TF_MEAN + 4 + c) * TMAX + dst] = velo[c];
+            if constexpr (CAM) {
+#pragma unroll
+                for (int i = 0; i < 20; ++i) wf[(B200_TFC_COVA + i) * TMAX + dst] = sm.park[i][t];
+            } else {
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 wf[(B200_TF_COV + 3 * i + 0) * TMAX + dst] = sm.park[3 * i + 0][t];
                 wf[(B200_TF_COV + 3 * i + 1) * TMAX + dst] = sm.park[3 * i + 1][t];
                 wf[(B200_TF_COV + 3 * i + 2) * TMAX + dst] = sm.park[3 * i + 2][t];
             }
-            wf[B200_TF_SCORE * TMAX + dst] = score;
-            wf[B200_TF_CLS * TMAX + dst] = cls;
+            }
+            wf[TF_SCORE * TMAX + dst] = score;
+            wf[TF_CLS * TMAX + dst] = cls;
             wi[B200_TI_ID * TMAX + dst] = tid_id;
             wi[B200_TI_FRAME * TMAX + dst] = frame_t;
             wi[B200_TI_START * TMAX + dst] = start;
@@ -1160,14 +1221,24 @@ bytetrack_step_kernel(const StepParams p) {
         if (dst < cap) {
 #pragma unroll
             for (int c = 0; c < 8; ++c) wf[(B200_TF_MEAN + c) * TMAX + dst] = kn.m[c];
+            if constexpr (CAM) {
+                // diagonal start: (x, y, vx, vy) and (w, h, vw, vh) blocks, entries 00 11 22 33 at triangle positions 0 4 7 9
+#pragma unroll
+                for (int i = 0; i < 20; ++i) wf[(B200_TFC_COVA + i) * TMAX + dst] = 0.0;
+                wf[(B200_TFC_COVA + 0) * TMAX + dst] = kn.pp[0]; wf[(B200_TFC_COVA + 4) * TMAX + dst] = kn.pp[1];
+                wf[(B200_TFC_COVA + 7) * TMAX + dst] = kn.vv[0]; wf[(B200_TFC_COVA + 9) * TMAX + dst] = kn.vv[1];
+                wf[(B200_TFC_COVB + 0) * TMAX + dst] = kn.pp[2]; wf[(B200_TFC_COVB + 4) * TMAX + dst] = kn.pp[3];
+                wf[(B200_TFC_COVB + 7) * TMAX + dst] = kn.vv[2]; wf[(B200_TFC_COVB + 9) * TMAX + dst] = kn.vv[3];
+            } else {
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
                 wf[(B200_TF_COV + 3 * a + 0) * TMAX + dst] = kn.pp[a];
                 wf[(B200_TF_COV + 3 * a + 1) * TMAX + dst] = kn.pv[a];
                 wf[(B200_TF_COV + 3 * a + 2) * TMAX + dst] = kn.vv[a];
             }
-            wf[B200_TF_SCORE * TMAX + dst] = sm.dconf[j];
-            wf[B200_TF_CLS * TMAX + dst] = det_cls(j);
+            }
+            wf[TF_SCORE * TMAX + dst] = sm.dconf[j];
+            wf[TF_CLS * TMAX + dst] = det_cls(j);
             wi[B200_TI_ID * TMAX + dst] = id;
             wi[B200_TI_FRAME * TMAX + dst] = frame;
             wi[B200_TI_START * TMAX + dst] = frame;
@@ -1229,26 +1300,26 @@ static_assert(sizeof(StepSmem<224, 224>) + 1024 <= 227 * 1024 / 4, "(224, 224) B
 struct Variant { int tmax, dmax; };
 constexpr Variant kVariants[] = {{64, 64}, {128, 128}, {224, 224}, {256, 256}, {512, 512}};
 
-template <int KIND, int TMAX, int DMAX, bool BOT>
+template <int KIND, int TMAX, int DMAX, bool BOT, bool CAM = false>
 cudaError_t launch_variant(const StepParams& p, cudaStream_t stream) {
-    auto kern = bytetrack_step_kernel<TMAX, KIND, TMAX, DMAX, BOT>;
+    auto kern = bytetrack_step_kernel<TMAX, KIND, TMAX, DMAX, BOT, CAM>;
     // profiling aid: B200_STEP_SMEM_PAD=<bytes> lowers the number of co-resident CTAs (latency vs throughput experiments)
     static const size_t pad = [] { const char* v = getenv("B200_STEP_SMEM_PAD"); return v ? (size_t)atol(v) : (size_t)0; }();
-    const size_t smem = sizeof(StepSmem<TMAX, DMAX, BOT>) + pad;
+    const size_t smem = sizeof(StepSmem<TMAX, DMAX, BOT, CAM>) + pad;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<p.n_streams, TMAX, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-template <int KIND, bool BOT>
+template <int KIND, bool BOT, bool CAM = false>
 cudaError_t launch_kind(const StepParams& p, int v, cudaStream_t stream) {
     switch (v) {
-        case 0: return launch_variant<KIND, 64, 64, BOT>(p, stream);
-        case 1: return launch_variant<KIND, 128, 128, BOT>(p, stream);
-        case 2: return launch_variant<KIND, 224, 224, BOT>(p, stream);
-        case 3: return launch_variant<KIND, 256, 256, BOT>(p, stream);
-        case 4: return launch_variant<KIND, 512, 512, BOT>(p, stream);
+        case 0: return launch_variant<KIND, 64, 64, BOT, CAM>(p, stream);
+        case 1: return launch_variant<KIND, 128, 128, BOT, CAM>(p, stream);
+        case 2: return launch_variant<KIND, 224, 224, BOT, CAM>(p, stream);
+        case 3: return launch_variant<KIND, 256, 256, BOT, CAM>(p, stream);
+        case 4: return launch_variant<KIND, 512, 512, BOT, CAM>(p, stream);
     }
     return cudaErrorInvalidValue;
 }
@@ -1263,13 +1334,13 @@ int bytetrack_step_variant(int max_tracks, int max_dets) {
 }
 int bytetrack_step_tmax(int variant) { return kVariants[variant].tmax; }
 int step_variant_dmax(int variant) { return kVariants[variant].dmax; }
-size_t bytetrack_step_smem(int variant, bool botsort) {
+size_t bytetrack_step_smem(int variant, bool botsort, bool cam) {
     switch (variant) {
-        case 0: return botsort ? sizeof(StepSmem<64, 64, true>) : sizeof(StepSmem<64, 64>);
-        case 1: return botsort ? sizeof(StepSmem<128, 128, true>) : sizeof(StepSmem<128, 128>);
-        case 2: return botsort ? sizeof(StepSmem<224, 224, true>) : sizeof(StepSmem<224, 224>);
-        case 3: return botsort ? sizeof(StepSmem<256, 256, true>) : sizeof(StepSmem<256, 256>);
-        case 4: return botsort ? sizeof(StepSmem<512, 512, true>) : sizeof(StepSmem<512, 512>);
+        case 0: return cam ? sizeof(StepSmem<64, 64, true, true>) : botsort ? sizeof(StepSmem<64, 64, true>) : sizeof(StepSmem<64, 64>);
+        case 1: return cam ? sizeof(StepSmem<128, 128, true, true>) : botsort ? sizeof(StepSmem<128, 128, true>) : sizeof(StepSmem<128, 128>);
+        case 2: return cam ? sizeof(StepSmem<224, 224, true, true>) : botsort ? sizeof(StepSmem<224, 224, true>) : sizeof(StepSmem<224, 224>);
+        case 3: return cam ? sizeof(StepSmem<256, 256, true, true>) : botsort ? sizeof(StepSmem<256, 256, true>) : sizeof(StepSmem<256, 256>);
+        case 4: return cam ? sizeof(StepSmem<512, 512, true, true>) : botsort ? sizeof(StepSmem<512, 512, true>) : sizeof(StepSmem<512, 512>);
     }
     return 0;
 }
@@ -1278,16 +1349,16 @@ cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, int variant,
     return kf_kind == KF_XYWH ? launch_kind<KF_XYWH, false>(p, variant, stream) : launch_kind<KF_XYAH, false>(p, variant, stream);
 }
 
-cudaError_t launch_botsort_step(const StepParams& p, int variant, cudaStream_t stream) {
-    return launch_kind<KF_XYWH, true>(p, variant, stream);
+cudaError_t launch_botsort_step(const StepParams& p, int variant, cudaStream_t stream, bool cam) {
+    return cam ? launch_kind<KF_XYWH, true, true>(p, variant, stream) : launch_kind<KF_XYWH, true>(p, variant, stream);
 }
 #else
 cudaError_t launch_bytetrack_step_packed(const StepParams& p, int kf_kind, int variant, cudaStream_t stream) {
     return kf_kind == KF_XYWH ? launch_kind<KF_XYWH, false>(p, variant, stream) : launch_kind<KF_XYAH, false>(p, variant, stream);
 }
 
-cudaError_t launch_botsort_step_packed(const StepParams& p, int variant, cudaStream_t stream) {
-    return launch_kind<KF_XYWH, true>(p, variant, stream);
+cudaError_t launch_botsort_step_packed(const StepParams& p, int variant, cudaStream_t stream, bool cam) {
+    return cam ? launch_kind<KF_XYWH, true, true>(p, variant, stream) : launch_kind<KF_XYWH, true>(p, variant, stream);
 }
 #endif
 

@@ -116,12 +116,20 @@ __device__ __forceinline__ void g4_update_chol(G4& g, const double* z, const dou
         }
 }
 
+// (u, v) <- M (u, v) (+ t), every operation rounded on its own
+__device__ __forceinline__ void g4_warp_pair(const double* M, const double* t, double& u, double& v) {
+    const double nu = xadd(xmul(M[0], u), xmul(M[1], v)), nv = xadd(xmul(M[2], u), xmul(M[3], v));
+    u = t ? xadd(nu, t[0]) : nu;
+    v = t ? xadd(nv, t[1]) : nv;
+}
+
 // m <- kron(I2, M) m (+ t on the position pair), P <- B P B^T with B = kron(I2, M); M row-major 2x2
 __device__ __forceinline__ void g4_warp(G4& g, const double* M, const double* t) {
     const double a = M[0], b = M[1], c = M[2], d = M[3];
-    const double p0 = a * g.m[0] + b * g.m[1], p1 = c * g.m[0] + d * g.m[1];
-    const double v0 = a * g.m[2] + b * g.m[3], v1 = c * g.m[2] + d * g.m[3];
-    g.m[0] = t ? p0 + t[0] : p0; g.m[1] = t ? p1 + t[1] : p1; g.m[2] = v0; g.m[3] = v1;
+    // the mean with separately rounded operations: callers that need the warped position elsewhere (association boxes)
+    // evaluate g4_warp_pair and must get the same bits
+    g4_warp_pair(M, t, g.m[0], g.m[1]);
+    g4_warp_pair(M, nullptr, g.m[2], g.m[3]);
     double A[4][4];                                       // B P
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

@@ -36,6 +36,14 @@
 #define B200_ERR_BOT_CAPACITY 4     // BoT-SORT: candidate graph overflow or more than 4 classes voted on one track
 #define B200_ERR_PACKED_ROW 8       // OC-SORT compact rows: more filter-box rows than the exception area of the result block holds
 
+// BoT-SORT contexts created with camera_motion keep the covariance as the two 4x4 blocks a camera warp leaves (kf44.cuh):
+// 8 mean + group A (x, y, vx, vy) 10 + group B (w, h, vw, vh) 10 + score + cls
+#define B200_NF_CAM 30
+#define B200_TFC_COVA 8
+#define B200_TFC_COVB 18
+#define B200_TFC_SCORE 28
+#define B200_TFC_CLS 29
+
 // BoT-SORT contexts carry one more int32 component per slot: the row of the track in the stream's
 // embedding pool feat_pool[(s * Tmax + row) * feat_dim] (fp32) and class-vote table
 // cls_hist[(s * Tmax + row) * 9] = {cls[4], score sum[4], n}.  Rows never move; slots do.

@@ -67,12 +67,12 @@ struct StepParams {
 // with the variant's slot capacity as stride.
 int bytetrack_step_variant(int max_tracks, int max_dets);   // -1: nothing large enough
 int bytetrack_step_tmax(int variant);
-size_t bytetrack_step_smem(int variant, bool botsort = false);
+size_t bytetrack_step_smem(int variant, bool botsort = false, bool cam = false);
 cudaError_t launch_bytetrack_step(const StepParams& p, int kf_kind, int variant, cudaStream_t stream);
-cudaError_t launch_botsort_step(const StepParams& p, int variant, cudaStream_t stream);
+cudaError_t launch_botsort_step(const StepParams& p, int variant, cudaStream_t stream, bool cam = false);
 // the same steps on packed frames (bytetrack_step_packed.cu)
 cudaError_t launch_bytetrack_step_packed(const StepParams& p, int kf_kind, int variant, cudaStream_t stream);
-cudaError_t launch_botsort_step_packed(const StepParams& p, int variant, cudaStream_t stream);
+cudaError_t launch_botsort_step_packed(const StepParams& p, int variant, cudaStream_t stream, bool cam = false);
 size_t ocsort_step_smem(int variant);
 cudaError_t launch_ocsort_step(const StepParams& p, int variant, cudaStream_t stream);
 int step_variant_dmax(int variant);
