@@ -574,7 +574,62 @@ def gen_deepocsort():
               last=_ragged(lasts, 5)[0], P=_ragged(Ps, 64)[0], heavy_frames=np.array(heavy, dtype=np.int32), final_emb=final_emb)
 
 
-GENERATORS = {"deepocsort": gen_deepocsort, "mot_deepocsort": gen_mot_deepocsort, "mot_strongsort": gen_mot_strongsort, "mot_botsort": gen_mot_botsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
+def gen_fullsize():
+    """Rows-only goldens at the BASELINE config sizes (scenarios.FULLSIZE)."""
+    rh.install()
+    from scenarios import (BOTSORT_YAML, DEEPOCSORT_YAML, FULLSIZE, STRONGSORT_YAML, fullsize_inputs)
+    img = np.zeros((2160, 3840, 3), dtype=np.uint8)
+    only = os.environ.get("GOLDEN_ONLY")
+    for name, sc in FULLSIZE.items():
+        if only and name not in only.split(","):
+            continue
+        dets, nd, embs = fullsize_inputs(sc)
+        kind = sc["kind"]
+        rh.reset_counters()
+        if kind == "bytetrack":
+            trk = rh.make_tracker("bytetrack")
+        elif kind == "ocsort":
+            from boxmot.trackers.ocsort.ocsort import OCSort
+            trk = OCSort(det_thresh=0, max_age=30, min_hits=1, asso_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2, use_byte=False)
+        elif kind == "botsort":
+            from boxmot.trackers.botsort.bot_sort import BoTSORT
+            trk = BoTSORT(None, "cpu", False, **BOTSORT_YAML)
+            trk.cmc = rh.IdentityCMC()
+        elif kind == "deepocsort":
+            from boxmot.trackers.deepocsort.deep_ocsort import DeepOCSort
+            trk = DeepOCSort(None, "cpu", False, False, **DEEPOCSORT_YAML)
+            trk.cmc = rh.IdentityCMC()
+        else:
+            from boxmot.trackers.strongsort.strong_sort import StrongSORT
+            trk = StrongSORT(None, "cpu", False, **STRONGSORT_YAML)
+            trk.cmc = rh.IdentityCMC()
+        ids, dis, offs, boxes, box_frames = [], [], [0], [], []
+        for f in range(sc["n_frames"]):
+            d = dets[f, :nd[f]]
+            if kind == "botsort":
+                rows = np.nonzero(d[:, 4] > BOTSORT_YAML["track_high_thresh"])[0]
+                if len(rows):
+                    rh.FakeReID.queue.append(embs[f, rows])
+            elif kind == "deepocsort":
+                keep = d[:, 4] > DEEPOCSORT_YAML["det_thresh"]
+                if keep.any():
+                    rh.FakeReID.queue.append(embs[f, :nd[f]][keep])
+            elif kind == "strongsort" and nd[f]:
+                rh.FakeReID.queue.append(embs[f, :nd[f]])
+            o = np.asarray(trk.update(d, None if kind == "bytetrack" else img), dtype=np.float64).reshape(-1, 8)
+            ids.append(o[:, 4].astype(np.int32))
+            dis.append(o[:, 7].astype(np.int32))
+            offs.append(offs[-1] + len(o))
+            if f % sc["box_every"] == sc["box_every"] - 1 or f == sc["n_frames"] - 1:
+                boxes.append(o[:, :4])
+                box_frames.append(f)
+        assert not rh.FakeReID.queue
+        _save(name, ndets=nd, dets_sum=np.array([dets.sum(), 0.0 if embs is None else float(np.abs(embs.astype(np.float64)).sum())]),
+              ids=np.concatenate(ids), det_ind=np.concatenate(dis).astype(np.int16), offs=np.array(offs, dtype=np.int64),
+              boxes=np.concatenate(boxes), box_frames=np.array(box_frames, dtype=np.int32))
+
+
+GENERATORS = {"fullsize": gen_fullsize, "deepocsort": gen_deepocsort, "mot_deepocsort": gen_mot_deepocsort, "mot_strongsort": gen_mot_strongsort, "mot_botsort": gen_mot_botsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
               "mot": gen_mot, "strongsort": gen_strongsort, "aux": gen_aux}
 
 if __name__ == "__main__":

@@ -154,3 +154,24 @@ def mot_feats(seq_index, frame, n, dim=32):
     """Seeded stand-in embeddings for the detections of frame `frame` of MOT17-mini sequence `seq_index` (raw, before the
     seam's whole-matrix normalisation)."""
     return np.random.default_rng(50000 + 1000 * seq_index + frame).normal(0.0, 1.0, (n, dim)).astype(np.float32)
+
+
+# ----------------------------------------------------------------------------- BASELINE config sizes (rows-only fixtures)
+# One stream per BASELINE.json config at its stated size, run through the live reference; the fixtures (full_*.npz) keep
+# the result rows only - ids and det_ind of every frame, boxes of every `box_every`-th frame - so they stay small.
+FULLSIZE = {
+    # config 1: ByteTrack, 1 stream, 1000 frames x ~50 detections (53 objects)
+    "full_bytetrack_c1": dict(kind="bytetrack", config=1, stream=0, n_objects=53, n_frames=1000, emb_dim=0, kw={}, box_every=10),
+    # config 2: OC-SORT, 100 objects with occlusion runs (one of the 64 streams)
+    "full_ocsort_c2": dict(kind="ocsort", config=2, stream=7, n_objects=100, n_frames=200, emb_dim=0, kw=dict(occlusion=True), box_every=5),
+    # config 3: BoT-SORT, 100 objects, 512-d embeddings (one of the 256 streams)
+    "full_botsort_c3": dict(kind="botsort", config=3, stream=11, n_objects=100, n_frames=200, emb_dim=512, kw={}, box_every=5),
+    # config 4: 200 tracks x 200 detections with 512-d embeddings through DeepOCSORT and StrongSORT
+    "full_deepocsort_c4": dict(kind="deepocsort", config=4, stream=3, n_objects=190, n_frames=100, emb_dim=512, kw={}, box_every=5),
+    "full_strongsort_c4": dict(kind="strongsort", config=4, stream=3, n_objects=200, n_frames=60, emb_dim=512, kw={}, box_every=5),
+}
+
+
+def fullsize_inputs(sc):
+    """dets[F, D, 6], ndets[F], raw embeddings (or None) of a full-size scenario."""
+    return make_stream(sc["config"], sc["stream"], sc["n_objects"], sc["n_frames"], emb_dim=sc["emb_dim"], **sc["kw"])
