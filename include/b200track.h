@@ -290,6 +290,19 @@ int b200track_gallery_cost_workspace(int32_t batch, int32_t n_tracks, int32_t bu
 int b200track_gallery_cost(int32_t batch, int32_t n_tracks, int32_t budget, int32_t n_dets, int32_t dim, const float* d_gallery,
                            const void* d_gallery_bf16, const int32_t* d_count, const float* d_det, double thresh, double fill,
                            double* d_out, void* d_workspace, uint64_t workspace_bytes, uint64_t* d_stats, void* stream);
+/* b200track_gallery_append <- NearestNeighborDistanceMetric.partial_fit (matching.py:343-358) on a device-resident gallery
+ * [n_slots, budget, dim]: row r goes to gallery[d_slot[r], d_pos[r]] as fp32 and, unit-normalised, as bf16 (the operand
+ * formats of b200track_gallery_cost); the caller keeps the ring position of every slot.
+ * b200track_ema_unit_features <- Track.update's feature smoothing (strongsort/sort/track.py:166-172), float32 in place:
+ * trk <- unit(alpha * trk + (1 - alpha) * unit(det)) for n rows.
+ * b200track_camera_update_xyah <- Track.camera_update (track.py:129-138) on n xyah means [n, 8] (in place): the box corners
+ * through the 2x3 warp d_warp[6] (NULL: the identity, which is still not an exact no-op in floating point). */
+int b200track_gallery_append(int32_t n, int32_t dim, int32_t budget, const float* d_rows, const int32_t* d_slot, const int32_t* d_pos,
+                             float* d_gallery, void* d_gallery_bf16, void* stream);
+int b200track_ema_unit_features(int32_t n, int32_t dim, float* d_trk, const float* d_det, double alpha, void* stream);
+/* rows /= |row| in float32, in place (the first feature of a new StrongSORT track, strongsort/sort/tracker.py:170-172) */
+int b200track_unit_features(int32_t n, int32_t dim, float* d_rows, void* stream);
+int b200track_camera_update_xyah(int32_t n, double* d_mean, const double* d_warp, void* stream);
 /* rows of fp32 -> unit-norm bf16 rows (the operand format of the two tensor-core operators) */
 int b200track_unit_bf16(int64_t rows, int32_t dim, const float* d_src, void* d_dst, void* stream);
 int b200track_lapjv(int32_t batch, int32_t rows, int32_t cols, const double* d_cost, double cost_limit,

@@ -1,6 +1,7 @@
 """GPU parity of the StrongSORT drop-in (host logic of strongsort/sort/tracker.py in Python, every numeric step through the
 CUDA operator kernels) against the goldens of the live reference: ids, confirmation / deletion, gallery sizes exact; boxes
-and Kalman state to 1e-9; smoothed embeddings bit-exact (same float32 numpy operations on the host side)."""
+and Kalman state to 1e-9; smoothed embeddings (unit-norm float32, smoothed on the device) to 1e-6 absolute: the reference's
+norms come from a BLAS float32 dot product whose summation order is unspecified, the kernel accumulates them in double."""
 import numpy as np
 import pytest
 
@@ -34,7 +35,8 @@ def test_strongsort_replays_reference_golden(name):
         if f in cov_frames:
             k = cov_frames[f]
             assert_close(s["cov"].reshape(-1, 64), g["cov"][cov_offs[k]:cov_offs[k + 1]], abs_=1e-10, what=f"{name} frame {f} cov")
-    assert np.array_equal(s["feature"], g["final_feat"])
+    assert s["feature"].shape == g["final_feat"].shape and s["feature"].dtype == np.float32
+    assert np.abs(s["feature"] - g["final_feat"]).max() < 1e-6, f"{name}: smoothed embeddings"
 
 
 def test_strongsort_factory_and_seam():
@@ -69,3 +71,62 @@ def test_strongsort_factory_and_seam():
             assert_close(out[:, :4], ref[:, :4])
     with pytest.raises(AssertionError):
         trk.update(np.zeros((2, 5)), img)
+
+
+def test_new_strongsort_operators_match_numpy():
+    """b200track_ema_unit_features / _unit_features / _camera_update_xyah against the reference's numpy arithmetic
+    (strongsort/sort/track.py:129-138, :166-172)."""
+    from yolo_tracking_b200 import _ops
+    rng = np.random.default_rng(3)
+    trk = rng.normal(0, 1, (37, 96)).astype(np.float32)
+    trk /= np.linalg.norm(trk, axis=1, keepdims=True)
+    det = rng.normal(0, 1, (37, 96)).astype(np.float32)
+    for alpha in (0.9, 0.8):
+        f = det / np.linalg.norm(det, axis=1, keepdims=True)
+        ref = alpha * trk + (1 - alpha) * f
+        ref /= np.linalg.norm(ref, axis=1, keepdims=True)
+        assert np.abs(_ops.ema_unit_features(trk, det, alpha) - ref).max() < 2e-7
+    assert np.abs(_ops.unit_features(det) - det / np.linalg.norm(det, axis=1, keepdims=True)).max() < 2e-7
+    mean = np.concatenate([rng.uniform(100, 1800, (50, 2)), rng.uniform(0.3, 0.8, (50, 1)), rng.uniform(60, 220, (50, 1)),
+                           rng.normal(0, 2, (50, 4))], axis=1)
+    warp = np.array([[1.002, -0.004, 3.5], [0.004, 0.998, -2.25]])
+    for w in (None, warp):
+        ref = mean.copy()
+        for m in ref:
+            tl = m[:4].copy(); tl[2] *= tl[3]; tl[:2] -= tl[2:] / 2
+            x1, y1, x2, y2 = tl[0], tl[1], tl[0] + tl[2], tl[1] + tl[3]
+            if w is not None:
+                wm = np.array([w[0], w[1], [0, 0, 1]])
+                x1, y1, _ = wm @ np.array([x1, y1, 1.0])
+                x2, y2, _ = wm @ np.array([x2, y2, 1.0])
+            ww, hh = x2 - x1, y2 - y1
+            m[:4] = [x1 + ww / 2, y1 + hh / 2, ww / hh, hh]
+        assert_close(_ops.camera_update_xyah(mean, w), ref, what="camera_update")
+
+
+def test_strongsort_runs_the_tensor_core_gallery_distance():
+    """The drop-in's appearance cost goes through b200track_gallery_cost (device-resident gallery, tcgen05 pre-filter)."""
+    import yolo_tracking_b200 as pkg
+    sc, cfg, dets, nd, feats, g = strongsort_scenario("strongsort_c4")
+    trk = pkg.StrongSORT(None, 0, False, **cfg)
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    for f in range(12):
+        trk.update(dets[f, :nd[f]], img, feats=feats[f, :nd[f]])
+    assert trk._store is not None and not trk.samples
+    st = trk.state()
+    assert st["gallery"].max() >= 10
+
+
+@pytest.mark.skipif("__import__('torch').cuda.device_count() < 2")
+def test_operator_backed_tracker_on_second_device():
+    """StrongSORT(device=1): operator kernels and buffers follow the tracker's device."""
+    import torch
+    import yolo_tracking_b200 as pkg
+    sc, cfg, dets, nd, feats, g = strongsort_scenario("strongsort_churn")
+    a, b = pkg.StrongSORT(None, 0, False, **cfg), pkg.StrongSORT(None, 1, False, **cfg)
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    for f in range(40):
+        ra = a.update(dets[f, :nd[f]], img, feats=feats[f, :nd[f]])
+        rb = b.update(dets[f, :nd[f]], img, feats=feats[f, :nd[f]])
+        assert np.array_equal(ra, rb), f
+    assert torch.cuda.current_device() == 0

@@ -17,6 +17,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
 
 from yolo_tracking_b200 import _lib  # noqa: E402
+from bench import ClockSampler  # noqa: E402  (NVML SM clock / throttle-reason sampler of the headline bench)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--streams", type=int, default=1024)
@@ -48,10 +49,15 @@ def p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+LAST_CLOCKS = {}
+
+
 def timeit(fn, flush_l2):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
+    sampler = ClockSampler(0)                     # every line carries the clocks sampled while IT was timed
+    sampler.start()
     ms = []
     for _ in range(args.iters):
         if flush_l2:
@@ -63,6 +69,10 @@ def timeit(fn, flush_l2):
         e1.record()
         torch.cuda.synchronize()
         ms.append(e0.elapsed_time(e1))
+    sampler.stop_flag = True
+    sampler.join()
+    LAST_CLOCKS.clear()
+    LAST_CLOCKS.update(sampler.summary())
     return float(np.median(ms)), float(np.min(ms))
 
 
@@ -77,6 +87,7 @@ def report(name, ms, best, alg_bytes=None, flops=None, extra=None, l2=""):
         line["tensor"] = {"achieved": ach, "peak": TF, "unit": "TFLOP/s", "frac": ach / TF, "flops_per_launch": flops, "peak_source": src}
     if extra:
         line.update(extra)
+    line["clocks"] = dict(LAST_CLOCKS)
     print(json.dumps(line), flush=True)
 
 

@@ -16,10 +16,19 @@ def _torch():
     return torch
 
 
-def _dev(a, dtype, device=0):
+def _dev(a, dtype):
+    """Host array -> tensor on the CURRENT CUDA device: the operator entry points launch on the current device, so callers
+    that own a device (the drop-in trackers) run their operator calls inside `on_device(index)`."""
     torch = _torch()
     arr = np.ascontiguousarray(a, dtype=dtype)
-    return torch.from_numpy(arr).to(f"cuda:{device}")
+    if not arr.flags.writeable:
+        arr = arr.copy()
+    return torch.from_numpy(arr).to("cuda")
+
+
+def on_device(index):
+    """Context manager: operator calls inside run on (and allocate on) CUDA device `index`."""
+    return _torch().cuda.device(int(index))
 
 
 def _p(t):
@@ -359,3 +368,104 @@ def dot_matrix(a, b):
     if out.numel():
         _sync_check(lib.b200track_dot_matrix(da.shape[0], db.shape[0], da.shape[1], _p(da), _p(db), _p(out), None))
     return out.cpu().numpy()
+
+
+def ema_unit_features(trk, det, alpha):
+    """Track.update's feature smoothing (strongsort/sort/track.py:166-172) for n rows, float32:
+    unit(alpha * trk + (1 - alpha) * unit(det))."""
+    lib = _lib.load()
+    a = _dev(np.asarray(trk, dtype=np.float32), np.float32)
+    b = _dev(np.asarray(det, dtype=np.float32), np.float32)
+    n, F = a.shape
+    _sync_check(lib.b200track_ema_unit_features(n, F, _p(a), _p(b), float(alpha), None))
+    return a.cpu().numpy()
+
+
+def unit_features(rows):
+    """rows / |row| in float32 (a new StrongSORT track's first feature)."""
+    lib = _lib.load()
+    a = _dev(np.asarray(rows, dtype=np.float32), np.float32)
+    _sync_check(lib.b200track_unit_features(a.shape[0], a.shape[1], _p(a), None))
+    return a.cpu().numpy()
+
+
+def camera_update_xyah(mean, warp=None):
+    """Track.camera_update (strongsort/sort/track.py:129-138) on xyah means [n, 8]; warp [2, 3] or None (identity)."""
+    lib = _lib.load()
+    m = _dev(np.asarray(mean, dtype=np.float64).reshape(-1, 8), np.float64)
+    w = _dev(np.asarray(warp, dtype=np.float64).reshape(6), np.float64) if warp is not None else None
+    _sync_check(lib.b200track_camera_update_xyah(m.shape[0], _p(m), _p(w), None))
+    return m.cpu().numpy()
+
+
+class GalleryStore:
+    """Device-resident StrongSORT gallery (NearestNeighborDistanceMetric.samples, matching.py:311-378): per slot the last
+    `budget` features of a track as fp32 rows and as unit-norm bf16 rows, the operand formats of the tensor-core gallery
+    distance (b200track_gallery_cost: tcgen05 pre-filter, exact float32 values).  The host keeps which slot belongs to which
+    track and how many rows it holds; features are appended on the device (b200track_gallery_append)."""
+
+    def __init__(self, n_slots, budget, dim):
+        torch = _torch()
+        self.lib = _lib.load()
+        self.n_slots, self.budget, self.dim = int(n_slots), int(budget), int(dim)
+        self.gal32 = torch.zeros((1, self.n_slots, self.budget, self.dim), dtype=torch.float32, device="cuda")
+        self.gal16 = torch.zeros((1, self.n_slots, self.budget, self.dim), dtype=torch.bfloat16, device="cuda")
+        self.appended = np.zeros(self.n_slots, dtype=np.int64)         # rows ever appended per slot
+        self.slot_of = {}                                              # track id -> slot
+        self.free = list(range(self.n_slots - 1, -1, -1))
+        self._ws = None
+
+    def count(self, track_id):
+        s = self.slot_of.get(track_id)
+        return 0 if s is None else int(min(self.appended[s], self.budget))
+
+    def append(self, track_ids, rows):
+        """One new feature row per listed track (a slot is allocated on a track's first row)."""
+        if not len(track_ids):
+            return
+        slots, pos = [], []
+        for tid in track_ids:
+            s = self.slot_of.get(tid)
+            if s is None:
+                if not self.free:
+                    raise RuntimeError(f"more than {self.n_slots} confirmed tracks (max_tracks)")
+                s = self.slot_of[tid] = self.free.pop()
+                self.appended[s] = 0
+            slots.append(s)
+            pos.append(int(self.appended[s] % self.budget))
+            self.appended[s] += 1
+        d_rows = _dev(np.asarray(rows, dtype=np.float32).reshape(len(slots), self.dim), np.float32)
+        d_slot, d_pos = _dev(slots, np.int32), _dev(pos, np.int32)
+        _sync_check(self.lib.b200track_gallery_append(len(slots), self.dim, self.budget, _p(d_rows), _p(d_slot), _p(d_pos),
+                                                      _p(self.gal32), _p(self.gal16), None))
+
+    def keep_only(self, track_ids):
+        """samples = {k: samples[k] for k in active_targets}: slots of every other track are released."""
+        keep = set(track_ids)
+        for tid in [t for t in self.slot_of if t not in keep]:
+            self.free.append(self.slot_of.pop(tid))
+
+    def distance(self, track_ids, det, thresh, fill):
+        """min over a track's rows of 1 - cos(row, det) where that is <= thresh, else `fill`: [len(track_ids), D] float64."""
+        torch = _torch()
+        det = np.asarray(det, dtype=np.float32)
+        D = det.shape[0]
+        if not len(track_ids) or D == 0:
+            return np.zeros((len(track_ids), D))
+        cnt = np.zeros(self.n_slots, dtype=np.int32)
+        for tid, s in self.slot_of.items():
+            cnt[s] = min(self.appended[s], self.budget)
+        dc, dd = _dev(cnt.reshape(1, -1), np.int32), _dev(det.reshape(1, D, self.dim), np.float32)
+        need = C.c_uint64()
+        _lib.check(self.lib.b200track_gallery_cost_workspace(1, self.n_slots, self.budget, D, self.dim, 0, C.byref(need)))
+        if self._ws is None or self._ws.numel() < int(need.value):
+            self._ws = torch.empty((max(int(need.value), 1),), dtype=torch.uint8, device="cuda")
+        out = torch.empty((1, self.n_slots, D), dtype=torch.float64, device="cuda")
+        st = torch.zeros((3,), dtype=torch.int64, device="cuda")
+        _sync_check(self.lib.b200track_gallery_cost(1, self.n_slots, self.budget, D, self.dim, _p(self.gal32), _p(self.gal16), _p(dc),
+                                                    _p(dd), float(thresh), float(fill), _p(out), _p(self._ws), int(need.value),
+                                                    _p(st), None))
+        if int(st[1]):
+            raise RuntimeError("gallery_cost: tensor-core pipeline protocol error")
+        full = out[0].cpu().numpy()
+        return full[[self.slot_of[t] for t in track_ids]]

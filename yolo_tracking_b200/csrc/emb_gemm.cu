@@ -104,6 +104,32 @@ __global__ void __launch_bounds__(256) unit_bf16_kernel(const float* __restrict_
     }
 }
 
+// ---- gallery maintenance: append one feature row per track to a device-resident gallery (fp32 row + unit-norm bf16
+// row, the operand formats of gallery_cost_kernel); one warp per row.  NearestNeighborDistanceMetric.partial_fit keeps the
+// last `budget` features of a track (matching.py:343-358): the caller passes the ring position.
+__global__ void __launch_bounds__(256) gallery_append_kernel(int n, int dim, int budget, const float* __restrict__ rows,
+                                                             const int* __restrict__ slot, const int* __restrict__ pos,
+                                                             float* __restrict__ gal32, __nv_bfloat16* __restrict__ gal16) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    const float4* s = reinterpret_cast<const float4*>(rows + (size_t)r * dim);
+    const size_t dst = ((size_t)slot[r] * budget + pos[r]) * dim;
+    float4* o32 = reinterpret_cast<float4*>(gal32 + dst);
+    __nv_bfloat162* o16 = reinterpret_cast<__nv_bfloat162*>(gal16 + dst);
+    const int nv = dim >> 2;
+    float acc = 0.f;
+    for (int i = lane; i < nv; i += 32) { const float4 v = s[i]; o32[i] = v; acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    const float inv = acc > 0.f ? rsqrtf(acc) : 0.f;
+    for (int i = lane; i < nv; i += 32) {
+        const float4 v = s[i];
+        o16[2 * i] = __floats2bfloat162_rn(v.x * inv, v.y * inv);
+        o16[2 * i + 1] = __floats2bfloat162_rn(v.z * inv, v.w * inv);
+    }
+}
+
 struct CostArgs {
     int n_trk, n_det, dim, npad;          // npad: detections of one N tile rounded up to 16
     const float* trk;                     // [B, n_trk, dim]
@@ -569,6 +595,17 @@ extern "C" int b200track_unit_bf16(int64_t rows, int32_t dim, const float* d_src
     if (rows < 0 || dim <= 0 || dim % 4 || !d_dst || (!d_src && rows > 0)) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
     if (rows == 0) return 0;
     unit_bf16_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, (cudaStream_t)st>>>(d_src, reinterpret_cast<__nv_bfloat16*>(d_dst), rows, dim);
+    B200_CU_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int b200track_gallery_append(int32_t n, int32_t dim, int32_t budget, const float* d_rows, const int32_t* d_slot,
+                                        const int32_t* d_pos, float* d_gallery, void* d_gallery_bf16, void* st) {
+    if (n < 0 || dim <= 0 || dim % 4 || budget <= 0 || !d_gallery || !d_gallery_bf16 || (n > 0 && (!d_rows || !d_slot || !d_pos))) {
+        set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n == 0) return 0;
+    gallery_append_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)st>>>(n, dim, budget, d_rows, d_slot, d_pos, d_gallery,
+                                                                      reinterpret_cast<__nv_bfloat16*>(d_gallery_bf16));
     B200_CU_TRY(cudaGetLastError());
     return 0;
 }

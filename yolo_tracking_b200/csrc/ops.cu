@@ -534,6 +534,67 @@ __global__ void __launch_bounds__(128) nn_cosine_kernel(int T, int D, int dim, c
     out[idx] = (double)best;
 }
 
+// Track.update's feature smoothing (strongsort/sort/track.py:166-172), float32 like the reference: f = det / |det|,
+// s = alpha * trk + (1 - alpha) * f, trk = s / |s|; separately rounded operations, norms accumulated in double (the
+// reference's come from BLAS, whose summation order is unspecified).  One warp per row.
+__global__ void __launch_bounds__(256) ema_unit_kernel(int n, int dim, float* __restrict__ trk, const float* __restrict__ det, float alpha, float beta) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    float* a = trk + (size_t)r * dim;
+    const float* b = det + (size_t)r * dim;
+    double acc = 0.0;
+    for (int i = lane; i < dim; i += 32) acc += (double)b[i] * b[i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    const float nb = sqrtf((float)acc);
+    acc = 0.0;
+    for (int i = lane; i < dim; i += 32) {
+        const float v = __fadd_rn(__fmul_rn(alpha, a[i]), __fmul_rn(beta, __fdiv_rn(b[i], nb)));
+        a[i] = v;
+        acc += (double)v * v;
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    const float ns = sqrtf((float)acc);
+    for (int i = lane; i < dim; i += 32) a[i] = __fdiv_rn(a[i], ns);
+}
+
+// rows /= |row| in float32 (a new StrongSORT track's first feature, tracker.py:170-172 + track.py:88-90)
+__global__ void __launch_bounds__(256) unit_rows_kernel(int n, int dim, float* __restrict__ rows) {
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= n) return;
+    float* a = rows + (size_t)r * dim;
+    double acc = 0.0;
+    for (int i = lane; i < dim; i += 32) acc += (double)a[i] * a[i];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    const float nb = sqrtf((float)acc);
+    for (int i = lane; i < dim; i += 32) a[i] = __fdiv_rn(a[i], nb);
+}
+
+// Track.camera_update (strongsort/sort/track.py:129-138): tlbr of the state, both corners through the 3x3 warp, back to
+// xyah - the reference's operation order (with the identity warp this is still not an exact no-op in floating point).
+__global__ void camera_update_xyah_kernel(int n, double* __restrict__ mean, const double* __restrict__ warp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* m = mean + (size_t)i * 8;
+    // to_tlwh: ret[2] *= ret[3]; ret[:2] -= ret[2:] / 2; to_tlbr: ret[2:] = ret[:2] + ret[2:]
+    const double w0 = xmul(m[2], m[3]), h0 = m[3];
+    double x1 = xsub(m[0], xdiv(w0, 2.0)), y1 = xsub(m[1], xdiv(h0, 2.0));
+    double x2 = xadd(x1, w0), y2 = xadd(y1, h0);
+    if (warp) {
+        // warp_matrix @ [x, y, 1]: three-term dot products, accumulated left to right
+        const double a = warp[0], b = warp[1], c = warp[2], d = warp[3], e = warp[4], f = warp[5];
+        const double nx1 = xadd(xadd(xmul(a, x1), xmul(b, y1)), c), ny1 = xadd(xadd(xmul(d, x1), xmul(e, y1)), f);
+        const double nx2 = xadd(xadd(xmul(a, x2), xmul(b, y2)), c), ny2 = xadd(xadd(xmul(d, x2), xmul(e, y2)), f);
+        x1 = nx1; y1 = ny1; x2 = nx2; y2 = ny2;
+    }
+    const double w = xsub(x2, x1), h = xsub(y2, y1);
+    m[0] = xadd(x1, xdiv(w, 2.0)); m[1] = xadd(y1, xdiv(h, 2.0)); m[2] = xdiv(w, h); m[3] = h;
+}
+
 template <class F>
 int dispatch_kind(int kind, F&& f) {
     switch (kind) {
@@ -711,6 +772,31 @@ extern "C" int b200track_lapjv(int32_t batch, int32_t rows, int32_t cols, const 
         B200_CU_TRY(cudaFuncSetAttribute(lapjv_dense_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         lapjv_dense_kernel<<<batch, 256, smem, (cudaStream_t)st>>>(rows, cols, cost, x, y);
     }
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200track_ema_unit_features(int32_t n, int32_t dim, float* d_trk, const float* d_det, double alpha, void* st) {
+    if (n < 0 || dim <= 0 || (n > 0 && (!d_trk || !d_det))) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n == 0) return 0;
+    // alpha * feature with a Python float alpha and a float32 array is a float32 product with float32(alpha) (numpy)
+    ema_unit_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)st>>>(n, dim, d_trk, d_det, (float)alpha, (float)(1.0 - alpha));
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200track_camera_update_xyah(int32_t n, double* d_mean, const double* d_warp, void* st) {
+    if (n < 0 || (n > 0 && !d_mean)) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n == 0) return 0;
+    camera_update_xyah_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)st>>>(n, d_mean, d_warp);
+    LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200track_unit_features(int32_t n, int32_t dim, float* d_rows, void* st) {
+    if (n < 0 || dim <= 0 || (n > 0 && !d_rows)) { set_error("bad argument"); return B200TRACK_ERR_ARG; }
+    if (n == 0) return 0;
+    unit_rows_kernel<<<(n + 7) / 8, 256, 0, (cudaStream_t)st>>>(n, dim, d_rows);
     LAUNCH_CHECK();
     return 0;
 }

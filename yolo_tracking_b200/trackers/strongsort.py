@@ -6,7 +6,13 @@ strongsort/sort/tracker.py (track list, confirmation, the two matching rounds an
 orders, which leak into the track ids) runs in Python exactly as in the reference, and every numeric step
 goes through the CUDA operator kernels of the C-ABI:
   Kalman predict / update with confidence-scaled noise  b200track_kf_predict / _kf_update (strongsort_kf.py:88-189)
-  gallery cosine distance                               b200track_nn_cosine_distance     (matching.py:247-378)
+  gallery cosine distance                               b200track_gallery_cost           (matching.py:247-378): the gallery
+                                                        lives on the device (fp32 + unit-norm bf16 rows, appended by
+                                                        b200track_gallery_append); a bf16 tcgen05 GEMM pre-filters, every value
+                                                        that can survive the threshold is recomputed exactly in float32.
+                                                        (b200track_nn_cosine_distance, plain, when the shape does not fit the
+                                                        tensor-core kernel: budget > 128, > 256 detections, dim % 64 != 0)
+  feature smoothing, first features, camera correction  b200track_ema_unit_features / _unit_features / _camera_update_xyah
   Mahalanobis gate + motion fusion                      b200track_gate_cost              (linear_assignment.py:144-200)
   IoU cost                                              b200track_iou_distance           (iou_matching.py:50-87)
   assignment on the clipped matrix                      b200track_linear_sum_assignment  (linear_assignment.py:59-61),
@@ -43,13 +49,15 @@ class _Track:
 
 class StrongSORT:
     def __init__(self, model_weights=None, device=0, fp16=False, max_dist=0.2, max_iou_dist=0.7, max_age=30, n_init=1,
-                 nn_budget=100, mc_lambda=0.995, ema_alpha=0.9, model=None, **_capacity):
+                 nn_budget=100, mc_lambda=0.995, ema_alpha=0.9, model=None, max_tracks=256, **_capacity):
         self.device = _device_index(device)
         self.max_dist, self.max_iou_dist, self.max_age, self.n_init = max_dist, max_iou_dist, max_age, n_init
         self.nn_budget, self.mc_lambda, self.ema_alpha = nn_budget, mc_lambda, ema_alpha
         self.model = model
         self.tracks: list[_Track] = []
-        self.samples: dict = {}
+        self.samples: dict = {}                            # plain path only (see _gallery_ok)
+        self._store = None                                 # device-resident gallery of the tensor-core path
+        self._max_tracks = max_tracks
         self._next_id = 1
         _lib.load()
         _ops._torch()                                   # fail loudly without a CUDA device: there is no CPU path
@@ -79,7 +87,16 @@ class StrongSORT:
                 matches.append((t, d))
         return matches, ut, ud
 
+    def _gallery_ok(self, dim):
+        """The tensor-core gallery distance needs budget <= 128 rows per track, dim % 64 == 0 and a positive mc_lambda (its
+        threshold is max_dist / mc_lambda: a larger cosine distance cannot survive the fused, clipped cost)."""
+        return self.nn_budget is not None and 0 < self.nn_budget <= 128 and dim % 64 == 0 and self.mc_lambda > 0
+
     def update(self, dets, img, feats=None, warp=None):
+        with _ops.on_device(self.device):
+            return self._update(dets, img, feats, warp)
+
+    def _update(self, dets, img, feats=None, warp=None):
         """`warp`: externally estimated 2x3 camera-motion matrix of this frame (what self.cmc.apply(img, xyxy) returns in the
         reference, strong_sort.py:63-65); None = identity.  Estimation itself (OpenCV ECC) is out of scope."""
         _SingleStreamTracker._check(dets)
@@ -94,14 +111,14 @@ class StrongSORT:
         feats = np.array(feats, dtype=np.float32).reshape(n, -1) if n else np.zeros((0, 1), dtype=np.float32)
         tracks = self.tracks
         # Track.camera_update (track.py:129-138) - with the identity warp still not an exact no-op in floating point
-        wm = None if warp is None else np.array([warp[0], warp[1], [0, 0, 1]], dtype=np.float64).tolist()
-        for t in tracks:
-            x1, y1, x2, y2 = t.to_tlbr()
-            if wm is not None:
-                x1, y1, _ = wm @ np.array([x1, y1, 1]).T
-                x2, y2, _ = wm @ np.array([x2, y2, 1]).T
-            w, h = x2 - x1, y2 - y1
-            t.mean[:4] = [x1 + w / 2, y1 + h / 2, w / h, h]
+        if tracks:
+            moved = _ops.camera_update_xyah(np.stack([t.mean for t in tracks]), warp)
+            for k, t in enumerate(tracks):
+                t.mean = moved[k]
+        use_store = n > 0 and n <= 256 and self._gallery_ok(feats.shape[1])
+        if use_store and self._store is None and not self.samples:
+            self._store = _ops.GalleryStore(self._max_tracks, self.nn_budget, feats.shape[1])
+        use_store = use_store and self._store is not None
         tlwh = dets[:, :4].copy()
         tlwh[:, 2] = dets[:, 2] - dets[:, 0]
         tlwh[:, 3] = dets[:, 3] - dets[:, 1]
@@ -117,7 +134,14 @@ class StrongSORT:
                 t.time_since_update += 1
 
         def gated_metric(track_idx, det_idx):
-            cost = _ops.nn_cosine_distance([self.samples[tracks[k].id] for k in track_idx], feats[det_idx])
+            if self._store is not None and use_store:
+                # a cosine distance above max_dist / mc_lambda cannot survive the fused cost's clip at max_dist
+                thr = self.max_dist / self.mc_lambda * (1.0 + 1e-12)
+                cost = self._store.distance([tracks[k].id for k in track_idx], feats[det_idx], thr, thr + 1e-5)
+            elif self._store is not None:
+                raise RuntimeError("StrongSORT: a frame with more than 256 detections after the device-resident gallery was set up")
+            else:
+                cost = _ops.nn_cosine_distance([self.samples[tracks[k].id] for k in track_idx], feats[det_idx])
             cost = _ops.gate_cost(KIND, cost, np.stack([tracks[k].mean for k in track_idx]),
                                   np.stack([tracks[k].covariance for k in track_idx]), xyah[det_idx], False, fuse=True,
                                   lambda_=self.mc_lambda)
@@ -150,14 +174,12 @@ class StrongSORT:
             ds = [d for _, d in matches]
             mean, cov = _ops.kf_update(KIND, np.stack([tracks[k].mean for k in ks]), np.stack([tracks[k].covariance for k in ks]),
                                        xyah[ds], dets[ds, 4])
+            smooth = _ops.ema_unit_features(np.stack([tracks[k].feature for k in ks]), feats[ds], self.ema_alpha)   # track.py:166-172
             for i, (k, d) in enumerate(matches):
                 t = tracks[k]
                 t.mean, t.covariance = mean[i], cov[i]
                 t.conf, t.cls, t.det_ind = dets[d, 4], dets[d, 5], float(d)
-                f = feats[d] / np.linalg.norm(feats[d])                # track.py:166-172, float32
-                smooth = self.ema_alpha * t.feature + (1 - self.ema_alpha) * f
-                smooth /= np.linalg.norm(smooth)
-                t.feature = smooth
+                t.feature = smooth[i]
                 t.hits += 1
                 t.time_since_update = 0
                 if t.state == TENTATIVE and t.hits >= self.n_init:
@@ -168,26 +190,32 @@ class StrongSORT:
                 t.state = DELETED
         if ud:
             mean, cov = _ops.kf_initiate(KIND, xyah[ud])
+            first = _ops.unit_features(feats[ud])
             for i, d in enumerate(ud):
                 t = _Track()
                 t.id = self._next_id
                 self._next_id += 1
                 t.conf, t.cls, t.det_ind = dets[d, 4], dets[d, 5], float(d)
                 t.hits, t.age, t.time_since_update, t.state = 1, 1, 0, TENTATIVE
-                feats[d] /= np.linalg.norm(feats[d])
-                t.feature = feats[d]
+                t.feature = first[i]
                 t.mean, t.covariance = mean[i], cov[i]
                 tracks.append(t)
         self.tracks = tracks = [t for t in tracks if t.state != DELETED]
         # NearestNeighborDistanceMetric.partial_fit (matching.py:343-358)
         active = [t.id for t in tracks if t.state == CONFIRMED]
-        for t in tracks:
-            if t.state == CONFIRMED:
-                g = self.samples.setdefault(t.id, [])
-                g.append(t.feature)
-                if self.nn_budget is not None:
-                    self.samples[t.id] = g[-self.nn_budget:]
-        self.samples = {k: self.samples[k] for k in active}
+        if self._store is None and active and self._gallery_ok(len(tracks[0].feature)) and not self.samples:
+            self._store = _ops.GalleryStore(self._max_tracks, self.nn_budget, len(tracks[0].feature))
+        if self._store is not None:
+            self._store.append(active, np.stack([t.feature for t in tracks if t.state == CONFIRMED]) if active else np.zeros((0, 1)))
+            self._store.keep_only(active)
+        else:
+            for t in tracks:
+                if t.state == CONFIRMED:
+                    g = self.samples.setdefault(t.id, [])
+                    g.append(t.feature)
+                    if self.nn_budget is not None:
+                        self.samples[t.id] = g[-self.nn_budget:]
+            self.samples = {k: self.samples[k] for k in active}
         rows = [np.concatenate((t.to_tlbr(), [t.id], [t.conf], [t.cls], [t.det_ind])).reshape(1, -1)
                 for t in tracks if t.state == CONFIRMED and t.time_since_update < 1]
         return np.concatenate(rows) if rows else np.array([])
@@ -200,5 +228,6 @@ class StrongSORT:
                     time_since_update=np.array([t.time_since_update for t in ts], dtype=np.int32),
                     mean=np.stack([t.mean for t in ts]) if n else np.zeros((0, 8)),
                     cov=np.stack([t.covariance for t in ts]) if n else np.zeros((0, 8, 8)),
-                    gallery=np.array([len(self.samples.get(t.id, [])) for t in ts], dtype=np.int32),
+                    gallery=np.array([self._store.count(t.id) if self._store is not None else len(self.samples.get(t.id, []))
+                                      for t in ts], dtype=np.int32),
                     feature=np.stack([t.feature for t in ts]) if n else np.zeros((0, 0), dtype=np.float32))
