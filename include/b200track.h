@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define B200TRACK_ABI_VERSION 2
+#define B200TRACK_ABI_VERSION 3
 
 typedef enum {
     B200TRACK_OK = 0,
@@ -35,7 +35,8 @@ typedef enum {
     B200TRACK_BYTETRACK = 0,      /* boxmot/trackers/bytetrack/byte_tracker.py:114 BYTETracker */
     B200TRACK_OCSORT = 1,         /* boxmot/trackers/ocsort/ocsort.py:190 OCSort               */
     B200TRACK_BOTSORT = 2,        /* boxmot/trackers/botsort/bot_sort.py:184 BoTSORT           */
-    B200TRACK_DEEPOCSORT = 3      /* boxmot/trackers/deepocsort/deep_ocsort.py:308 DeepOCSort  */
+    B200TRACK_DEEPOCSORT = 3,     /* boxmot/trackers/deepocsort/deep_ocsort.py:308 DeepOCSort  */
+    B200TRACK_STRONGSORT = 4      /* boxmot/trackers/strongsort/strong_sort.py:13 StrongSORT   */
 } b200track_kind;
 
 typedef enum { B200TRACK_KF_XYAH = 0, B200TRACK_KF_XYWH = 1, B200TRACK_KF_XYAH_CONF = 2 } b200track_kf_kind;
@@ -83,6 +84,15 @@ typedef struct {
      * four 2x2) so that per-stream warps can be applied (bot_sort.py:293-295); DeepOCSORT contexts always accept warps */
     int32_t camera_motion;
     int32_t reserved;
+    /* StrongSORT (strong_sort.py:14-41; it also reads max_age above): feat_dim a multiple of 64, nn_budget in [1, 128],
+     * max_tracks and max_dets <= 256 (the shapes of the tensor-core gallery distance), mc_lambda > 0.  Padded interface
+     * only (b200track_step / _step_cam / _step_host / _submit_host); every context accepts warps (Track.camera_update). */
+    double max_dist;
+    double max_iou_dist;
+    double mc_lambda;
+    double ema_alpha;
+    int32_t n_init;
+    int32_t nn_budget;
 } b200track_config;
 
 typedef struct b200track_ctx b200track_ctx;
@@ -101,6 +111,8 @@ const char* b200track_last_error(void);
  *   d_out   [n_streams, max_tracks, 8] (x1, y1, x2, y2, id, conf, cls, det_ind) in the
  *           reference's row order; d_nout[s] rows are valid.
  *   d_dets, d_feats and d_out must be 16-byte aligned (rows are moved with 16-byte accesses).
+ *   StrongSORT contexts (StrongSORT.update, strong_sort.py:43-99): d_feats holds one appearance row per detection row
+ *           (what the ReID seam returns); one step is a fixed sequence of eight launches for all streams (strongsort_step.cu).
  * b200track_step_cam    the same with one externally estimated 2x3 camera-motion warp per stream, d_warps
  *                          [n_streams, 6] row-major (NULL = identity): BoT-SORT contexts created with camera_motion
  *                          (STrack.multi_gmc, bot_sort.py:95-111, :293-295) and DeepOCSORT contexts
@@ -190,12 +202,15 @@ int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state_bytes_per_stream, 
  *   h_counts[4] = n_tracked, n_lost, id counter, frame_id
  *   h_rec [max_tracks, 6] = track_id, state, is_activated, frame_id, start_frame, tracklet_len
  *   h_mean[max_tracks, 8], h_cov[max_tracks, 64], h_aux[max_tracks, 3] = score, cls, det_ind
+ * StrongSORT contexts (Track fields, strongsort/sort/track.py:72-99): h_counts = list length, 0, next id, frame count;
+ *   h_rec = track_id, state (1 tentative, 2 confirmed), hits, age, time_since_update, stored gallery rows; h_aux = conf,
+ *   cls, det_ind; b200track_get_features gives the smoothed feature (Track.features[-1]) of every listed track.
  * OC-SORT contexts (KalmanBoxTracker fields, ocsort.py:65-128): h_counts[0] = live trackers;
  *   h_rec = id, age, time_since_update, hits, hit_streak, kf.observed; h_mean = kf.x[7], has-observation;
  *   h_cov[0:49] = dense 7x7 kf.P, [49:51] = velocity, [51:56] = last_observation. */
 int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int32_t* h_counts,
                         int32_t* h_rec, double* h_mean, double* h_cov, double* h_aux);
-/* BoT-SORT contexts (with_reid): STrack.smooth_feat (bot_sort.py:40-48) of every listed track of one
+/* BoT-SORT contexts (with_reid) and StrongSORT contexts: STrack.smooth_feat (bot_sort.py:40-48) / Track.features[-1] of every listed track of one
  * stream, in the same list order as b200track_get_state; h_feat[max_tracks, feat_dim] fp32. */
 int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, float* h_feat);
 /* DeepOCSORT contexts: KalmanBoxTracker fields like the OC-SORT form of b200track_get_state (h_rec[.., 5] = kf.observed +

@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/b200track.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature in _lib.py"
     assert set(_lib.SIGNATURES) == set(declared)
-    assert lib.b200track_abi_version() == 2
+    assert lib.b200track_abi_version() == 3
 
 
 def test_config_struct_matches_header_field_order():

@@ -1,5 +1,6 @@
-"""GPU parity of the StrongSORT drop-in (host logic of strongsort/sort/tracker.py in Python, every numeric step through the
-CUDA operator kernels) against the goldens of the live reference: ids, confirmation / deletion, gallery sizes exact; boxes
+"""GPU parity of StrongSORT - the batched frame step (csrc/strongsort_step.cu; the drop-in is a one-stream context of it) and
+the operator-backed fallback (host logic of strongsort/sort/tracker.py in Python, every numeric step through the CUDA
+operator kernels) - against the goldens of the live reference: ids, confirmation / deletion, gallery sizes exact; boxes
 and Kalman state to 1e-9; smoothed embeddings (unit-norm float32, smoothed on the device) to 1e-6 absolute: the reference's
 norms come from a BLAS float32 dot product whose summation order is unspecified, the kernel accumulates them in double."""
 import numpy as np
@@ -10,11 +11,12 @@ from _util import assert_close, strongsort_scenario
 pytestmark = pytest.mark.gpu
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "operators"])
 @pytest.mark.parametrize("name", ["strongsort_c4", "strongsort_churn", "strongsort_cam"])
-def test_strongsort_replays_reference_golden(name):
+def test_strongsort_replays_reference_golden(name, fused):
     from yolo_tracking_b200 import StrongSORT
     sc, cfg, dets, nd, feats, g = strongsort_scenario(name)
-    trk = StrongSORT(None, 0, False, **cfg)
+    trk = StrongSORT(None, 0, False, fused=fused, **cfg)
     img = np.zeros((4, 4, 3), dtype=np.uint8)
     cov_frames = {int(f): k for k, f in enumerate(g["cov_frames"])}
     cov_offs = [0]
@@ -35,6 +37,7 @@ def test_strongsort_replays_reference_golden(name):
         if f in cov_frames:
             k = cov_frames[f]
             assert_close(s["cov"].reshape(-1, 64), g["cov"][cov_offs[k]:cov_offs[k + 1]], abs_=1e-10, what=f"{name} frame {f} cov")
+    assert (trk._fused is not None) == fused
     assert s["feature"].shape == g["final_feat"].shape and s["feature"].dtype == np.float32
     assert np.abs(s["feature"] - g["final_feat"]).max() < 1e-6, f"{name}: smoothed embeddings"
 
@@ -105,16 +108,56 @@ def test_new_strongsort_operators_match_numpy():
 
 
 def test_strongsort_runs_the_tensor_core_gallery_distance():
-    """The drop-in's appearance cost goes through b200track_gallery_cost (device-resident gallery, tcgen05 pre-filter)."""
+    """The appearance cost of both forms goes through b200track_gallery_cost (device-resident gallery, tcgen05 pre-filter)."""
     import yolo_tracking_b200 as pkg
     sc, cfg, dets, nd, feats, g = strongsort_scenario("strongsort_c4")
-    trk = pkg.StrongSORT(None, 0, False, **cfg)
     img = np.zeros((1080, 1920, 3), dtype=np.uint8)
-    for f in range(12):
-        trk.update(dets[f, :nd[f]], img, feats=feats[f, :nd[f]])
-    assert trk._store is not None and not trk.samples
-    st = trk.state()
-    assert st["gallery"].max() >= 10
+    for fused in (True, False):
+        trk = pkg.StrongSORT(None, 0, False, fused=fused, **cfg)
+        for f in range(12):
+            trk.update(dets[f, :nd[f]], img, feats=feats[f, :nd[f]])
+        assert (trk._fused is not None) if fused else (trk._store is not None and not trk.samples)
+        st = trk.state()
+        assert st["gallery"].max() >= 10
+
+
+def test_batched_strongsort_streams_are_independent_and_match_the_oracle():
+    """BatchedTracker("strongsort", S): S different streams in one context, every stream against its own oracle; ragged
+    detection counts, an empty stream, streams that start late."""
+    from oracle.strongsort import StrongSORTOracle
+    from yolo_tracking_b200.batch import BatchedTracker
+    from yolo_tracking_b200.synth import make_stream
+    S, F, D, T, frames = 5, 64, 64, 96, 45
+    cfg = dict(max_dist=0.2, max_iou_dist=0.7, max_age=6, n_init=2, nn_budget=5, mc_lambda=0.995, ema_alpha=0.8)
+    streams = [make_stream(20 + s, 7 * s, 6 + 7 * s, frames, emb_dim=F, occlusion=True) for s in range(S)]
+    trk = BatchedTracker("strongsort", S, max_tracks=T, max_dets=D, feat_dim=F, **cfg)
+    orcs = [StrongSORTOracle(**cfg) for _ in range(S)]
+    dets = np.zeros((S, D, 6))
+    feats = np.zeros((S, D, F), dtype=np.float32)
+    for f in range(frames):
+        nd = np.zeros(S, dtype=np.int32)
+        for s in range(S):
+            d, n, e = streams[s]
+            k = 0 if (s == 1 or f < 3 * s) else int(n[f])          # stream 1 never sees a detection; others start late
+            nd[s] = k
+            dets[s, :k] = d[f, :k]
+            if k:
+                feats[s, :k] = (e[f, :k] / np.linalg.norm(e[f, :k])).astype(np.float32)
+        out, nout = trk.update_batch(np.ascontiguousarray(dets), nd, feats=np.ascontiguousarray(feats))
+        for s in range(S):
+            ref = orcs[s].update(dets[s, :nd[s]].copy(), feats[s, :nd[s]].copy()).reshape(-1, 8)
+            got = out[s, :nout[s]]
+            assert got.shape == ref.shape, (f, s)
+            if ref.size:
+                assert np.array_equal(got[:, 4:], ref[:, 4:]), (f, s)
+                assert_close(got[:, :4], ref[:, :4], what=f"frame {f} stream {s}")
+            st, snap = trk.state(s), orcs[s].snapshot()
+            for key in ("track_id", "state", "hits", "age", "time_since_update", "gallery"):
+                assert np.array_equal(st[key], snap[key]), (f, s, key)
+            assert_close(st["mean"], snap["mean"], what=f"frame {f} stream {s} mean")
+    trk.sync()
+    assert trk.launches() == 8 * frames
+    trk.close()
 
 
 @pytest.mark.skipif("__import__('torch').cuda.device_count() < 2")

@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("B200TRACK_LIB") or os.path.join(_HERE, "lib", "libb20
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200track.h")
 
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
-BYTETRACK, OCSORT, BOTSORT, DEEPOCSORT = 0, 1, 2, 3
+BYTETRACK, OCSORT, BOTSORT, DEEPOCSORT, STRONGSORT = 0, 1, 2, 3, 4
 KF_XYAH, KF_XYWH, KF_XYAH_CONF = 0, 1, 2
 SIM = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3, "centroid": 4}
 
@@ -34,6 +34,8 @@ class Config(C.Structure):
         ("use_byte", C.c_int32), ("with_reid", C.c_int32), ("fuse_first_associate", C.c_int32),
         ("w_association_emb", C.c_double), ("alpha_fixed_emb", C.c_double), ("aw_param", C.c_double),
         ("embedding_off", C.c_int32), ("aw_off", C.c_int32), ("camera_motion", C.c_int32), ("reserved", C.c_int32),
+        ("max_dist", C.c_double), ("max_iou_dist", C.c_double), ("mc_lambda", C.c_double), ("ema_alpha", C.c_double),
+        ("n_init", C.c_int32), ("nn_budget", C.c_int32),
     ]
 
 

@@ -13,7 +13,8 @@ import numpy as np
 
 from . import _lib
 
-_KINDS = {"bytetrack": _lib.BYTETRACK, "ocsort": _lib.OCSORT, "botsort": _lib.BOTSORT, "deepocsort": _lib.DEEPOCSORT}
+_KINDS = {"bytetrack": _lib.BYTETRACK, "ocsort": _lib.OCSORT, "botsort": _lib.BOTSORT, "deepocsort": _lib.DEEPOCSORT,
+          "strongsort": _lib.STRONGSORT}
 
 
 def _ptr(a):
@@ -77,6 +78,15 @@ class BatchedTracker:
             cfg.aw_off = int(bool(params.get("aw_off", False)))
             if cfg.embedding_off:
                 self.feat_dim = cfg.feat_dim = 0
+        elif kind == "strongsort":
+            # StrongSORT defaults (strong_sort.py:14-25)
+            cfg.max_dist = params.get("max_dist", 0.2)
+            cfg.max_iou_dist = params.get("max_iou_dist", 0.7)
+            cfg.max_age = int(params.get("max_age", 30))
+            cfg.n_init = int(params.get("n_init", 1))
+            cfg.nn_budget = int(params.get("nn_budget", 100))
+            cfg.mc_lambda = params.get("mc_lambda", 0.995)
+            cfg.ema_alpha = params.get("ema_alpha", 0.9)
         else:
             # OCSort defaults (ocsort.py:191-203)
             cfg.det_thresh = params.get("det_thresh", 0.2)
@@ -348,6 +358,14 @@ class BatchedTracker:
         _lib.check(self._lib.b200track_get_state(self._ctx, int(stream), _ptr(counts), _ptr(rec), _ptr(mean),
                                                  _ptr(cov), _ptr(aux)))
         n = int(counts[0] + counts[1])
+        if self.kind == "strongsort":
+            feat = np.zeros((T, self.feat_dim), dtype=np.float32)
+            _lib.check(self._lib.b200track_get_features(self._ctx, int(stream), _ptr(feat)))
+            return dict(n=n, next_id=int(counts[2]), frame_count=int(counts[3]),
+                        track_id=rec[:n, 0].copy(), state=rec[:n, 1].copy(), hits=rec[:n, 2].copy(), age=rec[:n, 3].copy(),
+                        time_since_update=rec[:n, 4].copy(), gallery=rec[:n, 5].copy(), mean=mean[:n].copy(),
+                        cov=cov[:n].reshape(n, 8, 8).copy(), conf=aux[:n, 0].copy(), cls=aux[:n, 1].copy(),
+                        det_ind=aux[:n, 2].copy(), feature=feat[:n].copy())
         if self.kind == "deepocsort":
             extra = np.zeros((T, 8))
             F = self.feat_dim

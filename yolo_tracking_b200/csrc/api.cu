@@ -11,6 +11,7 @@
 #include "api_util.h"
 #include "layout.h"
 #include "step_params.h"
+#include "strongsort_step.h"
 
 namespace b200 {
 thread_local std::string g_last_error;
@@ -71,6 +72,7 @@ struct b200track_ctx {
     HostSlot slot[NSLOT];
     uint64_t launches = 0;
     int32_t* h_err = nullptr;   // pinned
+    b200::SSParams ss{};         // StrongSORT contexts: state + scratch of the multi-launch step (strongsort_step.cu)
 };
 
 static int check_cfg(const b200track_config* c) {
@@ -80,7 +82,8 @@ static int check_cfg(const b200track_config* c) {
         set_error("max_tracks must be a multiple of 32 in [32, 512]"); return B200TRACK_ERR_ARG; }
     if (c->max_dets <= 0 || c->max_dets % 32 || c->max_dets > 512) {
         set_error("max_dets must be a multiple of 32 in [32, 512]"); return B200TRACK_ERR_ARG; }
-    if (c->kind != B200TRACK_BYTETRACK && c->kind != B200TRACK_OCSORT && c->kind != B200TRACK_BOTSORT && c->kind != B200TRACK_DEEPOCSORT) {
+    if (c->kind != B200TRACK_BYTETRACK && c->kind != B200TRACK_OCSORT && c->kind != B200TRACK_BOTSORT && c->kind != B200TRACK_DEEPOCSORT &&
+        c->kind != B200TRACK_STRONGSORT) {
         set_error("unknown tracker kind"); return B200TRACK_ERR_ARG; }
     return 0;
 }
@@ -95,6 +98,12 @@ extern "C" void b200track_destroy(b200track_ctx* ctx) {
     cudaFree(ctx->p.state_f); cudaFree(ctx->p.state_i); cudaFree(ctx->p.counts);
     cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.stats); cudaFree(ctx->p.err_slot); cudaFree(ctx->p.dbg); cudaFree(ctx->p.scratch);
     cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.feat_curr); cudaFree(ctx->p.cls_hist); cudaFree(ctx->p.emb_pool);
+    {
+        b200::SSParams& q = ctx->ss;
+        cudaFree(q.mean); cudaFree(q.cov); cudaFree(q.conf); cudaFree(q.cls); cudaFree(q.ti); cudaFree(q.order); cudaFree(q.feat);
+        cudaFree(q.gal32); cudaFree(q.gal16); cudaFree(q.cost); cudaFree(q.gcount); cudaFree(q.meas); cudaFree(q.tlwh); cudaFree(q.dconf);
+        cudaFree(q.match); cudaFree(q.iou); cudaFree(q.ud); cudaFree(q.nud); cudaFree(q.ws); cudaFree(q.gstats);
+    }
     for (auto& s : ctx->slot) {
         cudaFree(s.d_dets); cudaFree(s.d_ndets); cudaFree(s.d_feats); cudaFree(s.d_out); cudaFree(s.d_nout);
         cudaFree(s.d_in); cudaFree(s.d_res);
@@ -115,9 +124,22 @@ extern "C" int b200track_reset(b200track_ctx* ctx) {
     ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
     const size_t S = ctx->cfg.n_streams, T = ctx->tcap;
-    CU_TRY(cudaMemset(ctx->p.state_f, 0, S * ctx->nf * T * sizeof(double)));
-    CU_TRY(cudaMemset(ctx->p.state_i, 0, S * ctx->ni * T * sizeof(int)));
-    CU_TRY(cudaMemset(ctx->p.counts, 0, S * 4 * sizeof(int)));
+    if (ctx->cfg.kind == B200TRACK_STRONGSORT) {
+        b200::SSParams& q = ctx->ss;
+        CU_TRY(cudaMemset(q.mean, 0, S * T * 8 * sizeof(double)));
+        CU_TRY(cudaMemset(q.cov, 0, S * T * 64 * sizeof(double)));
+        CU_TRY(cudaMemset(q.ti, 0, S * b200::SS_NI * T * sizeof(int)));
+        CU_TRY(cudaMemset(q.order, 0, S * T * sizeof(int)));
+        CU_TRY(cudaMemset(q.feat, 0, S * T * (size_t)q.F * sizeof(float)));
+        CU_TRY(cudaMemset(q.gstats, 0, 3 * sizeof(unsigned long long)));
+        std::vector<int> c(S * 4, 0);
+        for (size_t i = 0; i < S; ++i) c[4 * i + 1] = 1;                // Tracker._next_id = 1 (tracker.py:57)
+        CU_TRY(cudaMemcpy(ctx->p.counts, c.data(), c.size() * sizeof(int), cudaMemcpyHostToDevice));
+    } else {
+        CU_TRY(cudaMemset(ctx->p.state_f, 0, S * ctx->nf * T * sizeof(double)));
+        CU_TRY(cudaMemset(ctx->p.state_i, 0, S * ctx->ni * T * sizeof(int)));
+        CU_TRY(cudaMemset(ctx->p.counts, 0, S * 4 * sizeof(int)));
+    }
     CU_TRY(cudaMemset(ctx->p.track_updates, 0, S * sizeof(unsigned long long)));
     CU_TRY(cudaMemset(ctx->p.err, 0, sizeof(int)));
     CU_TRY(cudaMemset(ctx->p.stats, 0, 8 * sizeof(unsigned long long)));
@@ -139,6 +161,13 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     if (cfg->kind == B200TRACK_DEEPOCSORT && !cfg->embedding_off) {
         if (cfg->feat_dim <= 0 || cfg->feat_dim % 4 || cfg->feat_dim > 4096) {
             set_error("DeepOCSORT needs feat_dim to be a multiple of 4 in [4, 4096] (or embedding_off)"); return B200TRACK_ERR_ARG; }
+    }
+    if (cfg->kind == B200TRACK_STRONGSORT) {
+        if (cfg->feat_dim <= 0 || cfg->feat_dim % 64 || cfg->feat_dim > 4096) {
+            set_error("StrongSORT needs feat_dim to be a multiple of 64 in [64, 4096]"); return B200TRACK_ERR_ARG; }
+        if (cfg->nn_budget < 1 || cfg->nn_budget > 128) { set_error("StrongSORT nn_budget must be in [1, 128]"); return B200TRACK_ERR_ARG; }
+        if (cfg->max_tracks > 256 || cfg->max_dets > 256) { set_error("StrongSORT contexts take at most 256 tracks / detections per stream"); return B200TRACK_ERR_CAPACITY; }
+        if (!(cfg->mc_lambda > 0.0) || cfg->n_streams > 65535) { set_error("StrongSORT needs mc_lambda > 0 and at most 65535 streams"); return B200TRACK_ERR_ARG; }
     }
     int ndev = 0;
     CU_TRY(cudaGetDeviceCount(&ndev));
@@ -181,8 +210,43 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     int rc = 0;
     auto fail = [&](int code) { b200track_destroy(ctx); return code; };
 #define CU_TRY_CTX(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(std::string(#expr) + ": " + cudaGetErrorString(_e)); return fail(B200TRACK_ERR_CUDA); } } while (0)
+    if (cfg->kind == B200TRACK_STRONGSORT) {
+        ctx->tcap = cfg->max_tracks;
+        const size_t Ts = cfg->max_tracks, F = cfg->feat_dim, G = cfg->nn_budget;
+        b200::SSParams& q = ctx->ss;
+        q.n_streams = cfg->n_streams; q.T = (int)Ts; q.D = cfg->max_dets; q.F = cfg->feat_dim; q.budget = cfg->nn_budget;
+        q.max_dist = cfg->max_dist; q.max_iou_dist = cfg->max_iou_dist; q.mc_lambda = cfg->mc_lambda;
+        q.ema_alpha = (float)cfg->ema_alpha; q.ema_beta = (float)(1.0 - cfg->ema_alpha);
+        q.max_age = cfg->max_age; q.n_init = cfg->n_init;
+        CU_TRY_CTX(cudaMalloc(&q.mean, S * Ts * 8 * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&q.cov, S * Ts * 64 * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&q.conf, S * Ts * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&q.cls, S * Ts * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&q.ti, S * b200::SS_NI * Ts * sizeof(int)));
+        CU_TRY_CTX(cudaMalloc(&q.order, S * Ts * sizeof(int)));
+        CU_TRY_CTX(cudaMalloc(&q.feat, S * Ts * F * sizeof(float)));
+        CU_TRY_CTX(cudaMalloc(&q.gal32, S * Ts * G * F * sizeof(float)));
+        CU_TRY_CTX(cudaMalloc(&q.gal16, S * Ts * G * F * 2));
+        CU_TRY_CTX(cudaMemset(q.gal32, 0, S * Ts * G * F * sizeof(float)));
+        CU_TRY_CTX(cudaMemset(q.gal16, 0, S * Ts * G * F * 2));
+        CU_TRY_CTX(cudaMalloc(&q.cost, S * Ts * D * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&q.iou, S * Ts * D * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&q.gcount, S * Ts * sizeof(int)));
+        CU_TRY_CTX(cudaMalloc(&q.match, S * Ts * sizeof(int)));
+        CU_TRY_CTX(cudaMalloc(&q.meas, S * D * 4 * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&q.tlwh, S * D * 4 * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&q.dconf, S * D * sizeof(double)));
+        CU_TRY_CTX(cudaMalloc(&q.ud, S * D * sizeof(int)));
+        CU_TRY_CTX(cudaMalloc(&q.nud, S * sizeof(int)));
+        CU_TRY_CTX(cudaMalloc(&q.gstats, 3 * sizeof(unsigned long long)));
+        uint64_t wsb = 0;
+        if (b200track_gallery_cost_workspace(cfg->n_streams, (int)Ts, cfg->nn_budget, cfg->max_dets, cfg->feat_dim, 0, &wsb)) return fail(B200TRACK_ERR_ARG);
+        q.ws_bytes = wsb;
+        CU_TRY_CTX(cudaMalloc(&q.ws, wsb ? wsb : 16));
+    } else {
     CU_TRY_CTX(cudaMalloc(&p.state_f, S * ctx->nf * T * sizeof(double)));
     CU_TRY_CTX(cudaMalloc(&p.state_i, S * ctx->ni * T * sizeof(int)));
+    }
     if (cfg->kind == B200TRACK_DEEPOCSORT && !p.embedding_off) {
         CU_TRY_CTX(cudaMalloc(&p.emb_pool, S * T * (size_t)cfg->feat_dim * sizeof(double)));
         // diou / ciou / centroid have a similarity - hence an appearance term - for every pair: per-stream scratch matrix
@@ -214,7 +278,11 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.out_ready, cudaEventDisableTiming));
     }
-    const size_t smem = cfg->kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
+    if (cfg->kind == B200TRACK_STRONGSORT) {
+        ctx->ss.counts = p.counts; ctx->ss.track_updates = p.track_updates; ctx->ss.err = p.err;
+    }
+    const size_t smem = cfg->kind == B200TRACK_STRONGSORT ? b200::strongsort_match_smem()
+                        : cfg->kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
                         : cfg->kind == B200TRACK_DEEPOCSORT ? b200::deepocsort_step_smem(ctx->variant)
                         : b200::bytetrack_step_smem(ctx->variant, cfg->kind == B200TRACK_BOTSORT, cfg->kind == B200TRACK_BOTSORT && cfg->camera_motion);
     int max_smem = 0;
@@ -235,6 +303,12 @@ static int launch_step(b200track_ctx* ctx, const double* d_dets, const int32_t* 
     b200::StepParams p = ctx->p;
     p.dets = d_dets; p.ndets = d_ndets; p.feats = d_feats; p.out = d_out; p.nout = d_nout; p.err_out = d_err_step;
     p.img_h = img_h; p.img_w = img_w; p.warps = d_warps;
+    if (ctx->cfg.kind == B200TRACK_STRONGSORT) {
+        if (!d_feats) { set_error("StrongSORT: the embedding buffer is NULL"); return B200TRACK_ERR_ARG; }
+        if (int rc = b200::launch_strongsort_step(ctx->ss, d_dets, d_ndets, d_feats, d_warps, d_out, d_nout, d_err_step, st)) return rc;
+        ctx->launches += 8;
+        return 0;
+    }
     if (d_warps && !(ctx->cfg.kind == B200TRACK_DEEPOCSORT || (ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.camera_motion))) {
         set_error("camera-motion warps need a DeepOCSORT context or a BoT-SORT context created with camera_motion"); return B200TRACK_ERR_STATE; }
     if (ctx->cfg.kind == B200TRACK_DEEPOCSORT) {
@@ -276,6 +350,7 @@ static std::string capacity_message(int e) {
     return std::string("capacity overflow:") + ((e & B200_ERR_DET_OVERFLOW) ? " detections > max_dets" : "") +
            ((e & B200_ERR_TRACK_OVERFLOW) ? " tracks > max_tracks" : "") +
            ((e & B200_ERR_BOT_CAPACITY) ? " BoT-SORT candidate graph or class history (> 4 classes on a track)" : "") +
+           ((e & B200_ERR_LSA) ? " StrongSORT: cost matrix contains invalid numeric entries" : "") +
            ((e & B200_ERR_PACKED_ROW) ? " OC-SORT exception area of the result block is full (rows that report the filter's box)" : "") +
            "; the context's state is truncated - b200track_reset before reuse";
 }
@@ -296,7 +371,8 @@ extern "C" int b200track_submit_host(b200track_ctx* ctx, int32_t slot, const dou
                                      int32_t img_w, double* h_out, int32_t* h_nout) {
     if (!ctx || !h_dets || !h_ndets || !h_out || !h_nout) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
     if (slot < 0 || slot >= NSLOT) { set_error("slot out of range"); return B200TRACK_ERR_ARG; }
-    if (((ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid) || (ctx->cfg.kind == B200TRACK_DEEPOCSORT && !ctx->p.embedding_off)) && !h_feats) {
+    if (((ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid) || (ctx->cfg.kind == B200TRACK_DEEPOCSORT && !ctx->p.embedding_off) ||
+         ctx->cfg.kind == B200TRACK_STRONGSORT) && !h_feats) {
         set_error("this context needs embeddings: h_feats is NULL"); return B200TRACK_ERR_ARG; }
     ON_DEVICE(ctx);
     HostSlot& s = ctx->slot[slot];
@@ -367,6 +443,7 @@ static int row_bytes_of(const b200track_ctx* ctx) {
 
 extern "C" int b200track_frame_layout(b200track_ctx* ctx, int64_t n_rows, int32_t det_dtype, b200track_layout* out) {
     if (!ctx || !out) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    if (ctx->cfg.kind == B200TRACK_STRONGSORT) { set_error("StrongSORT contexts use the padded interface (b200track_step / _submit_host)"); return B200TRACK_ERR_STATE; }
     if (n_rows < 0 || (det_dtype != B200TRACK_F32 && det_dtype != B200TRACK_F64)) { set_error("bad n_rows / det_dtype"); return B200TRACK_ERR_ARG; }
     const uint64_t S = ctx->cfg.n_streams, R = (uint64_t)n_rows;
     const uint64_t det_row = det_dtype == B200TRACK_F32 ? 24 : 48;
@@ -520,6 +597,12 @@ extern "C" int b200track_phase_cycles(b200track_ctx* ctx, uint64_t* h_out16, int
 
 extern "C" int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state, uint64_t* h_smem) {
     if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
+    if (ctx->cfg.kind == B200TRACK_STRONGSORT) {
+        const uint64_t F = ctx->ss.F, G = ctx->ss.budget;
+        if (h_state) *h_state = (uint64_t)ctx->tcap * (72 * 8 + 2 * 8 + b200::SS_NI * 4 + 4 + F * 4 + G * F * 6) + 4 * sizeof(int) + sizeof(unsigned long long);
+        if (h_smem) *h_smem = b200::strongsort_match_smem();
+        return 0;
+    }
     if (h_state) *h_state = (uint64_t)ctx->tcap * (ctx->nf * 8 + ctx->ni * 4) + 4 * sizeof(int) + sizeof(unsigned long long);
     if (h_smem) *h_smem = ctx->cfg.kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
                           : ctx->cfg.kind == B200TRACK_DEEPOCSORT ? b200::deepocsort_step_smem(ctx->variant)
@@ -534,6 +617,34 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
     ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
     const size_t T = ctx->tcap, s = stream_index;
+    if (ctx->cfg.kind == B200TRACK_STRONGSORT) {
+        const b200::SSParams& q = ctx->ss;
+        int c4[4];
+        CU_TRY(cudaMemcpy(c4, ctx->p.counts + 4 * s, sizeof(c4), cudaMemcpyDeviceToHost));
+        std::vector<int> iv((size_t)b200::SS_NI * T), order(T);
+        std::vector<double> mean(T * 8), cov(T * 64), conf(T), cls(T);
+        CU_TRY(cudaMemcpy(iv.data(), q.ti + s * b200::SS_NI * T, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(order.data(), q.order + s * T, T * sizeof(int), cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(mean.data(), q.mean + s * T * 8, mean.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(cov.data(), q.cov + s * T * 64, cov.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(conf.data(), q.conf + s * T, T * sizeof(double), cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(cls.data(), q.cls + s * T, T * sizeof(double), cudaMemcpyDeviceToHost));
+        const int n = c4[0];
+        for (int k = 0; k < n && k < (int)T; ++k) {
+            const int t = order[k];
+            if (h_rec) {
+                int32_t* r = h_rec + 6 * k;
+                r[0] = iv[b200::SSI_ID * T + t]; r[1] = iv[b200::SSI_STATE * T + t]; r[2] = iv[b200::SSI_HITS * T + t];
+                r[3] = iv[b200::SSI_AGE * T + t]; r[4] = iv[b200::SSI_TSU * T + t];
+                r[5] = iv[b200::SSI_STATE * T + t] == b200::SS_CONFIRMED ? std::min(iv[b200::SSI_APPENDED * T + t], q.budget) : 0;
+            }
+            if (h_mean) for (int c = 0; c < 8; ++c) h_mean[8 * k + c] = mean[(size_t)t * 8 + c];
+            if (h_cov) for (int c = 0; c < 64; ++c) h_cov[64 * k + c] = cov[(size_t)t * 64 + c];
+            if (h_aux) { h_aux[3 * k] = conf[t]; h_aux[3 * k + 1] = cls[t]; h_aux[3 * k + 2] = (double)iv[b200::SSI_DET * T + t]; }
+        }
+        h_counts[0] = n; h_counts[1] = 0; h_counts[2] = c4[1]; h_counts[3] = c4[2];
+        return 0;
+    }
     std::vector<double> f((size_t)ctx->nf * T);
     std::vector<int> iv((size_t)ctx->ni * T);
     CU_TRY(cudaMemcpy(h_counts, ctx->p.counts + 4 * s, 4 * sizeof(int), cudaMemcpyDeviceToHost));
@@ -661,8 +772,21 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
 
 extern "C" int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, float* h_feat) {
     if (!ctx || !h_feat) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
-    if (ctx->cfg.kind != B200TRACK_BOTSORT || !ctx->p.feat_pool) { set_error("context holds no embeddings"); return B200TRACK_ERR_STATE; }
     if (stream_index < 0 || stream_index >= ctx->cfg.n_streams) { set_error("stream_index out of range"); return B200TRACK_ERR_ARG; }
+    if (ctx->cfg.kind == B200TRACK_STRONGSORT) {
+        ON_DEVICE(ctx);
+        CU_TRY(cudaDeviceSynchronize());
+        const b200::SSParams& q = ctx->ss;
+        const size_t T = ctx->tcap, s = stream_index, F = q.F;
+        int c4[4];
+        CU_TRY(cudaMemcpy(c4, ctx->p.counts + 4 * s, sizeof(c4), cudaMemcpyDeviceToHost));
+        std::vector<int> order(T);
+        CU_TRY(cudaMemcpy(order.data(), q.order + s * T, T * sizeof(int), cudaMemcpyDeviceToHost));
+        for (int k = 0; k < c4[0] && k < (int)T; ++k)
+            CU_TRY(cudaMemcpy(h_feat + (size_t)k * F, q.feat + (s * T + order[k]) * F, F * sizeof(float), cudaMemcpyDeviceToHost));
+        return 0;
+    }
+    if (ctx->cfg.kind != B200TRACK_BOTSORT || !ctx->p.feat_pool) { set_error("context holds no embeddings"); return B200TRACK_ERR_STATE; }
     ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
     const size_t T = ctx->tcap, s = stream_index, F = ctx->cfg.feat_dim;

@@ -34,6 +34,7 @@
 #define B200_ERR_DET_OVERFLOW 1
 #define B200_ERR_TRACK_OVERFLOW 2
 #define B200_ERR_BOT_CAPACITY 4     // BoT-SORT: candidate graph overflow or more than 4 classes voted on one track
+#define B200_ERR_LSA 16             // StrongSORT: an assignment problem with nan / inf costs (scipy raises ValueError there)
 #define B200_ERR_PACKED_ROW 8       // OC-SORT compact rows: more filter-box rows than the exception area of the result block holds
 
 // BoT-SORT contexts created with camera_motion keep the covariance as the two 4x4 blocks a camera warp leaves (kf44.cuh):

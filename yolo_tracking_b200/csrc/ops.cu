@@ -157,21 +157,36 @@ __global__ void __launch_bounds__(256) kf_project_kernel(int n, const double* __
 // K[r, :] = P[r, :4] S^-1 (cho_solve), updates mean[r] and covariance row r.  P' = P - K S K^T is evaluated as
 // P - K (H P): S K^T = S S^-1 (P H^T)^T = H P exactly in real arithmetic, and rounding-wise inside the 1e-9 bar.
 constexpr int KFU_TPB = 32;                    // tracks per CTA of the update kernel (256 threads)
-template <int KIND>
+// MASKED (the batched StrongSORT step, strongsort_step.cu): the n tracks are the slots of all streams ([streams, T]); only
+// the slots with sel[slot] >= 0 are updated, with measurement / confidence row sel[slot] of their stream's [D, 4] / [D]
+// blocks; tiles without a selected slot leave at once.
+template <int KIND, bool MASKED = false>
 __global__ void __launch_bounds__(KFU_TPB * KF_LANES, 6) kf_update_kernel(int n, double* mean, double* cov, const double* __restrict__ z,
-                                                                         const double* __restrict__ conf) {
+                                                                         const double* __restrict__ conf, const int* __restrict__ sel = nullptr,
+                                                                         int T = 1, int D = 1) {
     __shared__ double sm[KFU_TPB * KF_STRIDE];
     __shared__ double sF[KFU_TPB][15];             // per track: L (10 lower-triangle entries), 1 / L[i][i] (4); stride 15 = conflict-free
     const int base = blockIdx.x * KFU_TPB, cnt = min(KFU_TPB, n - base);
     const int t = threadIdx.x / KF_LANES, r = threadIdx.x % KF_LANES;
+    int zrow = base + t;                           // row of z / conf this thread's track reads
+    bool mine = t < cnt;
+    if (MASKED) {
+        const int j = t < cnt ? sel[base + t] : -1;
+        mine = j >= 0;
+        zrow = ((base + t) / T) * D + j;
+        if (!__syncthreads_or(mine)) return;
+    }
     kf_stage_in(sm, mean, cov, base, cnt);
     // The 4x4 factorisation (4 sqrt, 6 divisions, 4 reciprocals: most of the kernel's fp64 instructions) is common to the
     // eight lanes of a track: the first warp factors all 32 tracks of the CTA, one per lane, instead of every lane for itself.
-    if (threadIdx.x < cnt) {
+    int qrow = base + threadIdx.x;
+    bool qsel = threadIdx.x < cnt;
+    if (MASKED && qsel) { const int j = sel[base + threadIdx.x]; qsel = j >= 0; qrow = ((base + threadIdx.x) / T) * D + j; }
+    if (qsel) {
         const int q = threadIdx.x;
         const double* m = sm + q * KF_STRIDE;
         double S[4][4], L[4][4];
-        kf_innovation<KIND>(m, m + 8, conf ? conf[base + q] : 0.0, S);
+        kf_innovation<KIND>(m, m + 8, conf ? conf[qrow] : 0.0, S);
         chol_lower<4>(S, L);
         int o = 0;
 #pragma unroll
@@ -183,7 +198,7 @@ __global__ void __launch_bounds__(KFU_TPB * KF_LANES, 6) kf_update_kernel(int n,
     }
     __syncthreads();
     double row[8], mr = 0.0;
-    if (t < cnt) {
+    if (mine) {
         const double* m = sm + t * KF_STRIDE;
         const double* P = m + 8;
         double L[4][4], inv[4];
@@ -213,7 +228,7 @@ __global__ void __launch_bounds__(KFU_TPB * KF_LANES, 6) kf_update_kernel(int n,
         }
         double a = 0.0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) a += xsub(z[(size_t)(base + t) * 4 + i], m[i]) * k[i];
+        for (int i = 0; i < 4; ++i) a += xsub(z[(size_t)zrow * 4 + i], m[i]) * k[i];
         mr = xadd(m[r], a);
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
@@ -224,7 +239,7 @@ __global__ void __launch_bounds__(KFU_TPB * KF_LANES, 6) kf_update_kernel(int n,
         }
     }
     __syncthreads();
-    if (t < cnt) {
+    if (mine) {
         double* m = sm + t * KF_STRIDE;
         m[r] = mr;
 #pragma unroll
@@ -667,6 +682,18 @@ extern "C" int b200track_kf_update(int32_t kind, int32_t n, double* mean, double
     LAUNCH_CHECK();
     return 0;
 }
+// internal (strongsort_step.cu): Track.update's filter step for the matched slots of all streams, in place
+namespace b200 {
+cudaError_t launch_kf_update_masked(int kind, int n_streams, int T, int D, double* mean, double* cov, const double* meas,
+                                    const double* conf, const int* sel, cudaStream_t st) {
+    const int n = n_streams * T;
+    if (n == 0) return cudaSuccess;
+    if (dispatch_kind(kind, [&](auto K) {
+            kf_update_kernel<decltype(K)::value, true><<<(n + KFU_TPB - 1) / KFU_TPB, KFU_TPB * KF_LANES, 0, st>>>(n, mean, cov, meas, conf, sel, T, D); }))
+        return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+}  // namespace b200
 extern "C" int b200track_kf_gating_distance(int32_t kind, int32_t T, int32_t D, const double* mean, const double* cov,
                                             const double* meas, int32_t only_position, int32_t metric, const double* conf,
                                             double* out, void* st) {

@@ -1,30 +1,30 @@
 """StrongSORT with the reference's constructor and update() contract
 (boxmot/trackers/strongsort/strong_sort.py:13-99), one stream per object like the reference.
 
-Unlike ByteTrack / OC-SORT / BoT-SORT this tracker is not (yet) one fused kernel: the host logic of
-strongsort/sort/tracker.py (track list, confirmation, the two matching rounds and their Python list / set
-orders, which leak into the track ids) runs in Python exactly as in the reference, and every numeric step
-goes through the CUDA operator kernels of the C-ABI:
+Default path: a one-stream context of the batched StrongSORT frame step (csrc/strongsort_step.cu, kind "strongsort" of
+`BatchedTracker`): camera correction, Kalman predict, the tensor-core gallery distance, Mahalanobis gate + motion fusion,
+both assignment rounds (scipy's linear_sum_assignment restated bit-faithfully including ties, the unmatched set in CPython's
+set order), Kalman update, feature smoothing, lifecycle, gallery ring and the result rows all run on the device - eight
+launches per frame, the host only hands buffers over.  Track many streams with one `BatchedTracker("strongsort", S, ...)`.
+
+Shapes the tensor-core gallery distance does not take (feature size not a multiple of 64, nn_budget above 128 or None, more
+than 256 tracks / detections, mc_lambda <= 0) fall back to the operator-backed form: the list logic of
+strongsort/sort/tracker.py in Python, every numeric step a CUDA operator of the C-ABI
   Kalman predict / update with confidence-scaled noise  b200track_kf_predict / _kf_update (strongsort_kf.py:88-189)
-  gallery cosine distance                               b200track_gallery_cost           (matching.py:247-378): the gallery
-                                                        lives on the device (fp32 + unit-norm bf16 rows, appended by
-                                                        b200track_gallery_append); a bf16 tcgen05 GEMM pre-filters, every value
-                                                        that can survive the threshold is recomputed exactly in float32.
-                                                        (b200track_nn_cosine_distance, plain, when the shape does not fit the
-                                                        tensor-core kernel: budget > 128, > 256 detections, dim % 64 != 0)
+  gallery cosine distance                               b200track_nn_cosine_distance     (matching.py:247-378)
   feature smoothing, first features, camera correction  b200track_ema_unit_features / _unit_features / _camera_update_xyah
   Mahalanobis gate + motion fusion                      b200track_gate_cost              (linear_assignment.py:144-200)
   IoU cost                                              b200track_iou_distance           (iou_matching.py:50-87)
-  assignment on the clipped matrix                      b200track_linear_sum_assignment  (linear_assignment.py:59-61),
-                                                        bit-faithful to scipy including ties.
+  assignment on the clipped matrix                      b200track_linear_sum_assignment  (linear_assignment.py:59-61)
 The ReID network and the ECC camera-motion estimator are out of scope (BASELINE.json): embeddings come from a
-`model` object with get_features(xyxys, img) or from `update(..., feats=...)`; the warp is the identity.
+`model` object with get_features(xyxys, img) or from `update(..., feats=...)`; the warp is passed in (None = identity).
 """
 from __future__ import annotations
 
 import numpy as np
 
 from .. import _lib, _ops
+from ..batch import BatchedTracker
 from .bytetrack import _SingleStreamTracker, _device_index
 
 TENTATIVE, CONFIRMED, DELETED = 1, 2, 3
@@ -47,10 +47,51 @@ class _Track:
         return ret
 
 
+class _FusedStream:
+    """One-stream context of the batched StrongSORT step, device buffers held as torch tensors."""
+
+    def __init__(self, device, max_tracks, max_dets, dim, **cfg):
+        torch = _ops._torch()
+        self.torch = torch
+        self.D, self.T, self.F = max_dets, max_tracks, dim
+        self.batch = BatchedTracker("strongsort", 1, max_tracks=max_tracks, max_dets=max_dets, device=device, feat_dim=dim, **cfg)
+        dev = f"cuda:{device}"
+        self.h_dets = torch.zeros((1, max_dets, 6), dtype=torch.float64, pin_memory=True)
+        self.h_feats = torch.zeros((1, max_dets, dim), dtype=torch.float32, pin_memory=True)
+        self.d_dets = torch.zeros((1, max_dets, 6), dtype=torch.float64, device=dev)
+        self.d_feats = torch.zeros((1, max_dets, dim), dtype=torch.float32, device=dev)
+        self.d_nd = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.d_warp = torch.zeros((1, 6), dtype=torch.float64, device=dev)
+        self.d_out = torch.zeros((1, max_tracks, 8), dtype=torch.float64, device=dev)
+        self.d_nout = torch.zeros((2,), dtype=torch.int32, device=dev)
+
+    def step(self, dets, feats, warp):
+        torch = self.torch
+        n = len(dets)
+        if n > self.D:
+            raise ValueError(f"{n} detections exceed max_dets={self.D}")
+        self.h_dets[0, :n] = torch.from_numpy(np.ascontiguousarray(dets, dtype=np.float64))
+        self.d_dets.copy_(self.h_dets, non_blocking=True)
+        if n:
+            self.h_feats[0, :n] = torch.from_numpy(np.ascontiguousarray(feats, dtype=np.float32))
+            self.d_feats.copy_(self.h_feats, non_blocking=True)
+        self.d_nd.fill_(n)
+        if warp is not None:
+            self.d_warp.copy_(torch.from_numpy(np.asarray(warp, dtype=np.float64).reshape(1, 6)))
+        stream = torch.cuda.current_stream().cuda_stream
+        self.batch.step_device(self.d_dets, self.d_nd, self.d_out, self.d_nout, d_feats=self.d_feats, stream=stream,
+                               d_warps=self.d_warp if warp is not None else None)
+        m = int(self.d_nout[0].item())
+        self.batch.sync()                                   # capacity overflows of this step raise here
+        return self.d_out[0, :m].cpu().numpy() if m else np.array([])
+
+
 class StrongSORT:
     def __init__(self, model_weights=None, device=0, fp16=False, max_dist=0.2, max_iou_dist=0.7, max_age=30, n_init=1,
-                 nn_budget=100, mc_lambda=0.995, ema_alpha=0.9, model=None, max_tracks=256, **_capacity):
+                 nn_budget=100, mc_lambda=0.995, ema_alpha=0.9, model=None, max_tracks=256, max_dets=256, fused=True, **_capacity):
         self.device = _device_index(device)
+        self._fused = None                                 # one-stream context of the batched step (default path)
+        self._want_fused, self._max_dets = bool(fused), max_dets
         self.max_dist, self.max_iou_dist, self.max_age, self.n_init = max_dist, max_iou_dist, max_age, n_init
         self.nn_budget, self.mc_lambda, self.ema_alpha = nn_budget, mc_lambda, ema_alpha
         self.model = model
@@ -110,6 +151,15 @@ class StrongSORT:
         # private copy: a new track normalises its row in place
         feats = np.array(feats, dtype=np.float32).reshape(n, -1) if n else np.zeros((0, 1), dtype=np.float32)
         tracks = self.tracks
+        if self._fused is None and self._want_fused and not tracks and not self.samples and self._store is None:
+            if n == 0:
+                return np.array([])                         # nothing tracked, nothing seen
+            if self._gallery_ok(feats.shape[1]) and self._max_tracks <= 256 and self._max_dets <= 256:
+                self._fused = _FusedStream(self.device, self._max_tracks, self._max_dets, feats.shape[1], max_dist=self.max_dist,
+                                           max_iou_dist=self.max_iou_dist, max_age=self.max_age, n_init=self.n_init,
+                                           nn_budget=self.nn_budget, mc_lambda=self.mc_lambda, ema_alpha=self.ema_alpha)
+        if self._fused is not None:
+            return self._fused.step(dets, feats, warp)
         # Track.camera_update (track.py:129-138) - with the identity warp still not an exact no-op in floating point
         if tracks:
             moved = _ops.camera_update_xyah(np.stack([t.mean for t in tracks]), warp)
@@ -221,6 +271,8 @@ class StrongSORT:
         return np.concatenate(rows) if rows else np.array([])
 
     def state(self):
+        if self._fused is not None:
+            return self._fused.batch.state(0)
         ts = self.tracks
         n = len(ts)
         return dict(track_id=np.array([t.id for t in ts], dtype=np.int32), state=np.array([t.state for t in ts], dtype=np.int32),
