@@ -84,6 +84,16 @@ WORKLOADS = {
                        b_slot=2 * (48 * 8 + 11 * 4), b_feat=512 * (8 + 8 + 4), kernel="deepocsort_step_kernel", img_hw=(2160, 3840),
                        label="config4 as a tracker: DeepOCSORT (deepocsort.yaml: giou, det_thresh 0, min_hits 1, max_age 30, adaptive "
                              "appearance weight, 512-d embeddings), 190 objects + ~30 false-positive trackers per stream, sharded by stream"),
+    # config 4 in its StrongSORT form: Mahalanobis gate + gallery cosine cost (100 stored features per track) at 200 x 200;
+    # the batched step is eight launches per frame, dominated by the tensor-core gallery distance.  256 streams: the gallery
+    # ring alone is 256 x 256 x 100 x 512 x 6 B = 20 GB of HBM.  Padded host interface (the context takes no packed frames).
+    "strongsort": dict(kind="strongsort", config=4, objects=190, streams=256, max_dets=224, max_tracks=256, emb=512, distinct=64,
+                       steps=10, warmup=3, padded_e2e=True, cpu_sample=(6, 2),
+                       params=dict(max_dist=0.2, max_iou_dist=0.7, max_age=30, n_init=1, nn_budget=100, mc_lambda=0.995, ema_alpha=0.8),  # strongsort.yaml
+                       b_slot=2 * (72 * 8 + 2 * 8 + 7 * 4) + 2 * 576, b_feat=512 * (4 + 4 + 4 + 4 + 2), kernel="gallery_cost_kernel (+ 7 smaller launches)",
+                       img_hw=(2160, 3840),
+                       label="config4 as a tracker: StrongSORT (strongsort.yaml: max_dist 0.2, nn_budget 100, mc_lambda 0.995, ema_alpha 0.8; "
+                             "Mahalanobis gate + gallery cosine cost, 512-d embeddings), 190 objects per stream, sharded by stream"),
 }
 W = dict(WORKLOADS["bytetrack"])          # the active workload (set in main)
 CONFIG_ID, N_OBJECTS, STREAMS_PER_GPU = W["config"], W["objects"], W["streams"]
@@ -110,7 +120,7 @@ def _stream_inputs(stream, n_frames):
     d = d.astype(np.float32).astype(np.float64)          # detector output precision; every consumer sees these values
     if e is not None:
         # the ReID seam (reid_multibackend.py:304-311): first-round rows / Frobenius norm of their matrix
-        high = PARAMS["track_high_thresh"] if W["kind"] == "botsort" else PARAMS["det_thresh"]
+        high = PARAMS["track_high_thresh"] if W["kind"] == "botsort" else PARAMS.get("det_thresh", -1.0)    # StrongSORT: every row
         feats = np.zeros_like(e)
         for f in range(n_frames):
             rows = np.nonzero(d[f, :n[f], 4] > high)[0]
@@ -178,12 +188,20 @@ def _make_oracle():
     if W["kind"] == "deepocsort":
         from oracle.deepocsort import DeepOCSortOracle
         return DeepOCSortOracle(**PARAMS)
+    if W["kind"] == "strongsort":
+        from oracle.strongsort import StrongSORTOracle
+        return StrongSORTOracle(**PARAMS)
     from oracle.botsort import BoTSORTOracle
     return BoTSORTOracle(**PARAMS)
 
 
 def _oracle_worker(args):
     streams, n_frames, warm = args
+    try:                                          # one BLAS thread per worker process: the workers already fill the cores
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
     data = [_stream_inputs(s, n_frames) for s in streams]
     trks = [_make_oracle() for _ in streams]
 
@@ -307,9 +325,10 @@ def run_b200(args, rank, world, local_rank):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        tu, dt = cpu_oracle_run(cores, 1, 40, 10)
+        cs, cw = W.get("cpu_sample", (40, 10))
+        tu, dt = cpu_oracle_run(cores, 1, cs, cw)
         cpu_base = {"value": tu / dt, "unit": "track-updates/s", "cores": cores, "kind": "port",
-                    "sample": f"{cores} streams x 40 frames after {PREROLL} pre-roll + 10 warm-up frames of the same workload, "
+                    "sample": f"{cores} streams x {cs} frames after {PREROLL} pre-roll + {cw} warm-up frames of the same workload, "
                               f"oracle/{W['kind']}.py, one process per core"}
 
     import torch
@@ -351,6 +370,7 @@ def run_b200(args, rank, world, local_rank):
     preroll(W0)                                  # PREROLL + warm-up frames, untimed
     barrier()
     tu0, l0 = trk.track_updates(), trk.launches()
+    gal0 = trk.counters()["gallery_rows"] if W["kind"] == "strongsort" else 0
     sampler = ClockSampler(local_rank)
     sampler.start()
     # L2 hygiene: config 5's per-step working set is several times the 126 MB L2 and every step reads new
@@ -377,6 +397,7 @@ def run_b200(args, rank, world, local_rank):
     tu_dev = trk.track_updates() - tu0
     launches = trk.launches() - l0
     dets_timed = int(nd_h[W0:].sum())
+    gal_rows = (trk.counters()["gallery_rows"] - gal0) if W["kind"] == "strongsort" else 0
 
     # ---------------- end-to-end leg: pinned host blocks through the packed C-ABI ----------------
     # Every timed frame is one pinned input block (offsets + fp32 detection rows [+ fp32 embeddings]) prepared before the
@@ -389,19 +410,43 @@ def run_b200(args, rank, world, local_rank):
     n_e2e = args.warmup + args.steps
     rows_of, flags_of, in_blocks = [], [], []
     max_rows = int(nd_h[PREROLL:].sum(axis=1).max())
-    for k in range(n_e2e):
+    padded = bool(W.get("padded_e2e"))
+    if padded:
+        # contexts without packed frames (StrongSORT): pinned padded blocks dets [S, D, 6] f64 + feats [S, D, F] f32 in,
+        # out [S, T, 8] + nout [S] back through b200track_submit_host / wait_host (pitched copies of the used rows)
+        def pinned(shape, dtype):
+            t = torch.empty(shape, dtype=dtype, pin_memory=True)
+            return t, t.numpy()
+        keep = []
+        for k in range(n_e2e):
+            f = PREROLL + k
+            td, a = pinned((S, MAX_DETS, 6), torch.float64)
+            a[:] = np.tile(dets_h[f], (reps, 1, 1))
+            tf, b = pinned((S, MAX_DETS, W["emb"]), torch.float32)
+            b[:] = np.tile(feats_h[f], (reps, 1, 1))
+            keep.append((td, tf))
+            in_blocks.append((a, b, np.ascontiguousarray(nd_h[f])))
+        outs = [pinned((S, MAX_TRACKS, 8), torch.float64) + pinned((S,), torch.int32) for _ in range(nslot)]
+    for k in range(0 if padded else n_e2e):
         f = PREROLL + k
         blk, _ = trk.frame_buffers(max_rows=int(nd_h[f].sum()))
         r, fl = trk.pack(blk, np.tile(dets_h[f], (reps, 1, 1)) if reps > 1 else dets_h[f], ndets=nd_h[f],
                          feats=None if feats_h is None else (np.tile(feats_h[f], (reps, 1, 1)) if reps > 1 else feats_h[f]), dtype=np.float32)
         in_blocks.append(blk); rows_of.append(r); flags_of.append(fl)
-    out_blocks = [trk.frame_buffers(max_rows=max_rows)[1] for _ in range(nslot)]
+    out_blocks = [] if padded else [trk.frame_buffers(max_rows=max_rows)[1] for _ in range(nslot)]
     del dets_h
 
     def submit(k, slot):
+        if padded:
+            a, b, n = in_blocks[k]
+            trk.submit(slot, a, n, outs[slot][1], outs[slot][3], feats=b, img_hw=hw)
+            return
         trk.submit_packed(slot, in_blocks[k], out_blocks[slot], np.float32, flags_of[k], img_hw=hw)
 
     def collect(k, slot):
+        if padded:
+            trk.wait(slot)
+            return int(outs[slot][3].sum())
         trk.wait_packed(slot)
         v = trk.frame_views(None, out_blocks[slot], rows_of[k], np.float32)
         return int(v["nout"].sum())               # device->host read of the step's result
@@ -427,9 +472,13 @@ def run_b200(args, rank, world, local_rank):
     sampler_e2e.stop_flag = True
     sampler_e2e.join()
     for k in range(args.warmup, n_e2e):
+        if padded:
+            mx = int(in_blocks[k][2].max())
+            h2d += S * 4 + S * mx * (48 + 4 * W["emb"]); d2h += S * 4 + 4 + S * min(mx, MAX_TRACKS) * 64
+            continue
         L = trk.frame_layout(rows_of[k], np.float32)
         h2d += int(L.in_bytes); d2h += int(L.out_bytes)
-    row_bytes = int(trk.frame_layout(0, np.float32).row_bytes)
+    row_bytes = 64 if padded else int(trk.frame_layout(0, np.float32).row_bytes)
     tu_e2e = trk.track_updates() - tu1
     trk.sync()
     assert tu_e2e == tu_dev, "the two legs ran different work"
@@ -476,6 +525,10 @@ def run_b200(args, rank, world, local_rank):
         # rank-0 kernel: algorithmic bytes per launch / mean launch duration (events on the launch stream); the device leg
         # reads padded fp64 detection rows (48 B) and writes the reference's 64-byte result rows
         alg_bytes = (tu_dev * (W["b_slot"] + W["b_feat"]) + dets_timed * B_DET + rows * B_ROW) / args.steps     # rank-0 shard
+        if W["kind"] == "strongsort":
+            # + the stored gallery rows every confirmed track is compared against (bf16 operand of the tensor-core distance)
+            # and the detection embeddings (fp32 read + bf16 copy written and read)
+            alg_bytes += (gal_rows * W["emb"] * 2 + dets_timed * W["emb"] * (4 + 2 + 2)) / args.steps
         mean_ms = float(step_ms.mean())
         achieved = alg_bytes / (mean_ms * 1e-3) / 1e9
         line = {
@@ -497,7 +550,10 @@ def run_b200(args, rank, world, local_rank):
                     "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
                     "ms_per_step": e2e_ms_max / args.steps, "pipeline_depth": nslot,
                     "output_rows_per_step": rows_all / args.steps / world,
-                    "interface": "b200track_submit_packed / wait_packed: one pinned input block per frame (int32 offsets + fp32 "
+                    "interface": ("b200track_submit_host / wait_host: pinned padded blocks (fp64 detection rows + fp32 embeddings), pitched "
+                                  "copies of the used rows, 64-byte result rows; the host reads the per-stream row counts of every "
+                                  "finished frame") if padded else
+                                 "b200track_submit_packed / wait_packed: one pinned input block per frame (int32 offsets + fp32 "
                                  "detection rows%s), one linear cudaMemcpyAsync per direction, compact %d-byte result rows; "
                                  "the host reads the per-stream row counts of every finished frame"
                                  % (" + fp32 embeddings" if W["emb"] else "", row_bytes),
@@ -513,6 +569,12 @@ def run_b200(args, rank, world, local_rank):
             "cpu_baseline": cpu_base,
             "clocks": sampler.summary(),
         }
+        if W["kind"] == "strongsort":
+            # the GEMM-shaped part: every stored gallery row against every detection of its stream (2 F flop per pair)
+            flops = 2.0 * gal_rows * W["emb"] * (dets_timed / max(1, S * args.steps)) / args.steps
+            line["tensor"] = {"what": "gallery rows x detections x 2 F per step, over the whole step time (eight launches)",
+                              "gallery_rows_per_step": gal_rows / args.steps, "tflops_over_step": flops / (mean_ms * 1e-3) / 1e12,
+                              "peak_bf16_tflops": peaks.get("bf16_tflops")}
         emit(line)
     if world > 1:
         dist.barrier()

@@ -220,7 +220,8 @@ int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, float* h_fe
 int b200track_get_track_extras(b200track_ctx* ctx, int32_t stream_index, double* h_extra, double* h_emb);
 /* Event counters summed over all streams since create / reset (DeepOCSORT contexts): h_out8[0] = first associations solved
  * as an assignment problem (not by the permutation shortcut, association.py:157-159), [1] = recovery rounds that ran an
- * assignment (deep_ocsort.py:466), [2] = observation-centric re-updates (deepocsort_kf.py:433-478); the rest reserved. */
+ * assignment (deep_ocsort.py:466), [2] = observation-centric re-updates (deepocsort_kf.py:433-478); StrongSORT contexts: [3] = stored gallery rows the
+ * distance metric compared against (sum over frames and confirmed tracks); the rest reserved. */
 int b200track_counters(b200track_ctx* ctx, uint64_t* h_out8);
 
 /* ---- operator level: the reference's functional API, batched, device pointers -----------

@@ -2,7 +2,7 @@
 BYTETracker, OCSort, BoTSORT at BASELINE config 1 (1 stream, ~50 detections per frame) and for DeepOCSORT / StrongSORT at
 100 objects with 512-d embeddings, next to the oracle port of the reference on one host core (same synthetic stream, seam
 features passed in, identity camera).  One call = pack -> one H2D copy -> one fused step -> one D2H copy -> rebuild the
-reference's [M, 8] rows (StrongSORT: operator-backed, see its module).  This is a latency figure; the multi-stream
+reference's [M, 8] rows (StrongSORT: the eight-launch batched step on one stream).  This is a latency figure; the multi-stream
 throughput is bench.py.  Every line carries the SM clocks sampled while it ran.
 usage: python tools/bench_dropins.py [--frames 300] > profiles/rNN_dropins.jsonl"""
 import argparse
@@ -96,7 +96,7 @@ def main():
         sampler.join()
         line = {"tracker": name, "objects": objects, "dets_per_frame": float(nd.mean()), "frames": frames, "emb_dim": dim,
                 "update_ms_p50": p50, "update_ms_p99": p99, "update_ms_mean": mean, "frames_per_s": 1e3 / mean,
-                "path": "operator-backed drop-in (host list logic over CUDA operators)" if name == "strongsort" else
+                "path": "one-stream context of the batched StrongSORT step (eight launches per frame, device buffers via torch)" if name == "strongsort" else
                         "one-stream context of the fused frame step through the packed host interface",
                 "clocks": sampler.summary()}
         if not args.no_cpu:

@@ -329,7 +329,7 @@ class BatchedTracker:
         """Event counters over all streams (DeepOCSORT): assignment-solved first associations, recovery rounds, re-updates."""
         buf = (C.c_uint64 * 8)()
         _lib.check(self._lib.b200track_counters(self._ctx, C.byref(buf)))
-        return dict(lap_frames=int(buf[0]), ocr_frames=int(buf[1]), oru=int(buf[2]))
+        return dict(lap_frames=int(buf[0]), ocr_frames=int(buf[1]), oru=int(buf[2]), gallery_rows=int(buf[3]))
 
     def launches(self) -> int:
         v = C.c_uint64()

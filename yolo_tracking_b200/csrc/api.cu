@@ -279,7 +279,7 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         CU_TRY_CTX(cudaEventCreateWithFlags(&s.out_ready, cudaEventDisableTiming));
     }
     if (cfg->kind == B200TRACK_STRONGSORT) {
-        ctx->ss.counts = p.counts; ctx->ss.track_updates = p.track_updates; ctx->ss.err = p.err;
+        ctx->ss.counts = p.counts; ctx->ss.track_updates = p.track_updates; ctx->ss.err = p.err; ctx->ss.stats = p.stats;
     }
     const size_t smem = cfg->kind == B200TRACK_STRONGSORT ? b200::strongsort_match_smem()
                         : cfg->kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
@@ -554,6 +554,11 @@ extern "C" int b200track_sync(b200track_ctx* ctx) {
     if (!ctx) { set_error("ctx is NULL"); return B200TRACK_ERR_ARG; }
     ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
+    if (ctx->cfg.kind == B200TRACK_STRONGSORT) {
+        unsigned long long g[3];
+        CU_TRY(cudaMemcpy(g, ctx->ss.gstats, sizeof(g), cudaMemcpyDeviceToHost));
+        if (g[1]) { set_error("StrongSORT: tensor-core pipeline protocol error in the gallery distance"); return B200TRACK_ERR_CUDA; }
+    }
     CU_TRY(cudaMemcpy(ctx->h_err, ctx->p.err, sizeof(int), cudaMemcpyDeviceToHost));
     const int e = *ctx->h_err;
     if (e) {

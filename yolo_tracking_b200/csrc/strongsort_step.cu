@@ -89,11 +89,17 @@ __global__ void __launch_bounds__(NT) ss_pre_kernel(const SSParams p, const doub
         ti[SSI_AGE * T + slot] += 1;                   // Track.predict (track.py:144-150)
         ti[SSI_TSU * T + slot] += 1;
     }
+    int grows = 0;
     for (int t = tid; t < T; t += NT) {
         const int st = ti[SSI_STATE * T + t];
-        p.gcount[(size_t)s * T + t] = st == SS_CONFIRMED ? min(ti[SSI_APPENDED * T + t], p.budget) : 0;
+        const int g = st == SS_CONFIRMED ? min(ti[SSI_APPENDED * T + t], p.budget) : 0;
+        p.gcount[(size_t)s * T + t] = g;
         p.match[(size_t)s * T + t] = -1;
+        grows += g;
     }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) grows += __shfl_xor_sync(0xffffffffu, grows, d);
+    if ((tid & 31) == 0 && grows && p.stats) atomicAdd(&p.stats[3], (unsigned long long)grows);
     int nd = ndets[s];
     if (nd > D) { nd = D; if (tid == 0) { atomicOr(p.err, B200_ERR_DET_OVERFLOW); if (err_step) atomicOr(err_step, B200_ERR_DET_OVERFLOW); } }
     for (int j = tid; j < D; j += NT) {

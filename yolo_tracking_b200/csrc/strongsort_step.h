@@ -40,6 +40,7 @@ struct SSParams {
     void* ws;                            // workspace of the gallery distance
     uint64_t ws_bytes;
     unsigned long long* gstats;          // [3] counters of the gallery distance ([1] = protocol errors)
+    unsigned long long* stats;           // context counters (b200track_counters): [3] += gallery rows compared this step
     unsigned long long* track_updates;   // [S]
     int* err;
 };
