@@ -338,6 +338,24 @@ int b200track_nn_cosine_distance(int32_t n_tracks, int32_t n_dets, int32_t dim, 
 int b200track_linear_sum_assignment(int32_t batch, int32_t rows, int32_t cols, const double* d_cost,
                                     int32_t* d_col4row, int32_t* d_err, void* stream);
 
+/* ---- OC-SORT's XYSR filter at operator level (csrc/kf_xysr.cu): the 7-d [x, y, s, r, vx, vy, vs] filter KalmanBoxTracker
+ * configures (ocsort.py:79-106) on dense d_x [n, 7] / d_P [n, 7, 7] arrays, in place, with the same device functions the fused
+ * OC-SORT step runs.  *d_err |= 1 (may be NULL) if a covariance does not have the structure of this filter (three
+ * (position, velocity) 2x2 blocks + P_rr).
+ * b200track_kf_xysr_predict         <- KalmanFilter.predict (ocsort_kf.py:339-379); the tracker-level guards of
+ *                                      KalmanBoxTracker.predict (ocsort.py:168-181) stay with the caller
+ * b200track_kf_xysr_update          <- KalmanFilter.update(z) (ocsort_kf.py:437-526: Joseph form), d_z [n, 4]
+ * b200track_kf_xysr_unfreeze_update <- KalmanFilter.update(z) on a frozen filter: unfreeze() (:383-434) replays a
+ *                                      straight-line virtual trajectory from the last measurement d_last_z [n, 4] to d_z over
+ *                                      d_gap [n] frames starting from the state saved by freeze() (freeze is a copy: the
+ *                                      caller passes that copy as d_x / d_P), then the real measurement is applied on top;
+ *                                      d_virtual_last [n, 4] (may be NULL) receives the last virtual box, which the
+ *                                      reference leaves at the end of history_obs. */
+int b200track_kf_xysr_predict(int32_t n, double* d_x, double* d_P, int32_t* d_err, void* stream);
+int b200track_kf_xysr_update(int32_t n, double* d_x, double* d_P, const double* d_z, int32_t* d_err, void* stream);
+int b200track_kf_xysr_unfreeze_update(int32_t n, double* d_x, double* d_P, const double* d_last_z, const int32_t* d_gap,
+                                      const double* d_z, double* d_virtual_last, int32_t* d_err, void* stream);
+
 /* ---- DeepOCSORT operators (csrc/kf8.cu): the 8-d [x, y, w, h, vx, vy, vw, vh] filter the reference configures in
  * KalmanBoxTracker.__init__ (deep_ocsort.py:103-138), dense [n, 8] / [n, 8, 8] arrays.
  * b200track_kf8_predict <- KalmanBoxTracker.predict's kf.predict(Q=new_kf_process_noise(w, h)) (deep_ocsort.py:76-80, :263-266,

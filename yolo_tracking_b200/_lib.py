@@ -98,6 +98,9 @@ SIGNATURES = {
     "b200track_gallery_cost_workspace": (C.c_int, [_I, _I, _I, _I, _I, _I, C.POINTER(C.c_uint64)]),
     "b200track_gallery_cost": (C.c_int, [_I, _I, _I, _I, _I, _P, _P, _P, _P, _D, _D, _P, _P, C.c_uint64, _P, _P]),
     "b200track_unit_bf16": (C.c_int, [C.c_int64, _I, _P, _P, _P]),
+    "b200track_kf_xysr_predict": (C.c_int, [_I, _P, _P, _P, _P]),
+    "b200track_kf_xysr_update": (C.c_int, [_I, _P, _P, _P, _P, _P]),
+    "b200track_kf_xysr_unfreeze_update": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200track_gallery_append": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "b200track_ema_unit_features": (C.c_int, [_I, _I, _P, _P, _D, _P]),
     "b200track_unit_features": (C.c_int, [_I, _I, _P, _P]),

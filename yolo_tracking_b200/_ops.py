@@ -469,3 +469,45 @@ class GalleryStore:
             raise RuntimeError("gallery_cost: tensor-core pipeline protocol error")
         full = out[0].cpu().numpy()
         return full[[self.slot_of[t] for t in track_ids]]
+
+
+# ---- OC-SORT's XYSR filter at operator level (csrc/kf_xysr.cu) -------------------------------------------------------
+def _xysr(mode, x, P, z=None, last_z=None, gap=None):
+    lib = _lib.load()
+    torch = _torch()
+    dx = _dev(np.asarray(x, dtype=np.float64).reshape(-1, 7), np.float64)
+    dP = _dev(np.asarray(P, dtype=np.float64).reshape(-1, 7, 7), np.float64)
+    n = dx.shape[0]
+    err = torch.zeros((1,), dtype=torch.int32, device=dx.device)
+    vl = None
+    if mode == 0:
+        _sync_check(lib.b200track_kf_xysr_predict(n, _p(dx), _p(dP), _p(err), None))
+    else:
+        dz = _dev(np.asarray(z, dtype=np.float64).reshape(n, 4), np.float64)
+        if mode == 1:
+            _sync_check(lib.b200track_kf_xysr_update(n, _p(dx), _p(dP), _p(dz), _p(err), None))
+        else:
+            dl = _dev(np.asarray(last_z, dtype=np.float64).reshape(n, 4), np.float64)
+            dg = _dev(np.asarray(gap).reshape(n), np.int32)
+            vl = torch.zeros((n, 4), dtype=torch.float64, device=dx.device)
+            _sync_check(lib.b200track_kf_xysr_unfreeze_update(n, _p(dx), _p(dP), _p(dl), _p(dg), _p(dz), _p(vl), _p(err), None))
+    if int(err.item()):
+        raise ValueError("covariance does not have the structure of OC-SORT's XYSR filter")
+    out = (dx.cpu().numpy(), dP.cpu().numpy())
+    return out + (vl.cpu().numpy(),) if vl is not None else out
+
+
+def kf_xysr_predict(x, P):
+    """KalmanFilter.predict of OC-SORT's 7-d filter (ocsort_kf.py:339-379, ocsort.py:79-106): x [n, 7], P [n, 7, 7]."""
+    return _xysr(0, x, P)
+
+
+def kf_xysr_update(x, P, z):
+    """KalmanFilter.update(z) (ocsort_kf.py:437-526), z [n, 4] = [x, y, s, r]."""
+    return _xysr(1, x, P, z)
+
+
+def kf_xysr_unfreeze_update(x_saved, P_saved, last_z, gap, z):
+    """update(z) on a frozen filter: the virtual trajectory of unfreeze() (ocsort_kf.py:383-434) from the saved state, then
+    the real measurement; returns (x, P, last virtual box)."""
+    return _xysr(2, x_saved, P_saved, z, last_z, gap)

@@ -28,6 +28,7 @@
 #include "boxes.cuh"
 #include "lap_dense.cuh"
 #include "oc_common.cuh"
+#include "kf_xysr.cuh"
 #include "layout.h"
 #include "step_params.h"
 
@@ -61,61 +62,6 @@ struct alignas(16) OcSmem {
     int ired[8 * (TMAX / 32)];
     unsigned char kvalid[TMAX], alive[TMAX], dstate[DMAX], tdeg[TMAX], ddeg[DMAX], rowfull[DMAX];
 };
-
-struct OcKf {
-    double x[7];
-    double pp[3], pv[3], vv[3], prr;
-};
-
-__device__ __forceinline__ void oc_predict_cov(OcKf& k) {
-    const double qv[3] = {0.01, 0.01, 0.0001};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double a = xadd(k.pp[i], k.pv[i]);
-        const double b = xadd(k.pv[i], k.vv[i]);
-        k.pp[i] = xadd(xadd(a, b), 1.0);
-        k.pv[i] = b;
-        k.vv[i] = xadd(k.vv[i], qv[i]);
-    }
-    k.prr = xadd(k.prr, 1.0);
-}
-__device__ __forceinline__ void oc_predict_full(OcKf& k) {          // kf.predict (no tracker-level guard)
-#pragma unroll
-    for (int i = 0; i < 3; ++i) k.x[i] = xadd(k.x[i], k.x[i + 4]);
-    oc_predict_cov(k);
-}
-// Joseph-form update, ocsort_kf.py:496-521, on the block-sparse covariance
-__device__ __forceinline__ void oc_correct(OcKf& k, const double* z) {
-    const double R[4] = {1.0, 1.0, 10.0, 10.0};
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-        const double S = xadd(k.pp[i], R[i]);
-        const double si = xdiv(1.0, S);
-        const double kp = xmul(k.pp[i], si), kv = xmul(k.pv[i], si);
-        const double y = xsub(z[i], k.x[i]);
-        k.x[i] = xadd(k.x[i], xmul(kp, y));
-        k.x[i + 4] = xadd(k.x[i + 4], xmul(kv, y));
-        const double a = xsub(1.0, kp);
-        const double ap00 = xmul(a, k.pp[i]), ap01 = xmul(a, k.pv[i]);
-        const double ap10 = xadd(xmul(-kv, k.pp[i]), k.pv[i]), ap11 = xadd(xmul(-kv, k.pv[i]), k.vv[i]);
-        const double n00 = xmul(ap00, a);
-        const double n01 = xadd(xmul(ap00, -kv), ap01);
-        const double n11 = xadd(xmul(ap10, -kv), ap11);
-        const double krp = xmul(kp, R[i]), krv = xmul(kv, R[i]);
-        k.pp[i] = xadd(n00, xmul(krp, kp));
-        k.pv[i] = xadd(n01, xmul(krp, kv));
-        k.vv[i] = xadd(n11, xmul(krv, kv));
-    }
-    {
-        const double S = xadd(k.prr, R[3]);
-        const double si = xdiv(1.0, S);
-        const double kr = xmul(k.prr, si);
-        const double y = xsub(z[3], k.x[3]);
-        k.x[3] = xadd(k.x[3], xmul(kr, y));
-        const double a = xsub(1.0, kr);
-        k.prr = xadd(xmul(xmul(a, k.prr), a), xmul(xmul(kr, R[3]), kr));
-    }
-}
 
 // Cost of (row r = high detection hd[r], column c = live tracker ht[c]) in the first association,
 // association.py:130-172: -(similarity + direction term) plus the canonical tie-break.  The row reduction and the
@@ -709,22 +655,9 @@ ocsort_step_kernel(const StepParams p) {
                     k.vv[i] = gf[(B200_OC_SP + 3 * i + 2) * TMAX + t];
                 }
                 k.prr = gf[(B200_OC_SP + 9) * TMAX + t];
-                const double x1 = gf[(B200_OC_LASTZ + 0) * TMAX + t], y1 = gf[(B200_OC_LASTZ + 1) * TMAX + t];
-                const double s1 = gf[(B200_OC_LASTZ + 2) * TMAX + t], r1 = gf[(B200_OC_LASTZ + 3) * TMAX + t];
-                const double w1 = sqrt(xmul(s1, r1)), h1 = sqrt(xdiv(s1, r1));
-                const double w2 = sqrt(xmul(z[2], z[3])), h2 = sqrt(xdiv(z[2], z[3]));
-                const int g = tsu;                                      // index2 - index1 of history_obs
-                const double gd = (double)g;
-                const double dx = xdiv(xsub(z[0], x1), gd), dy = xdiv(xsub(z[1], y1), gd);
-                const double dw = xdiv(xsub(w2, w1), gd), dh = xdiv(xsub(h2, h1), gd);
-                for (int i = 0; i < g; ++i) {
-                    const double f = (double)(i + 1);
-                    const double w = xadd(w1, xmul(f, dw)), h = xadd(h1, xmul(f, dh));
-                    vz[0] = xadd(x1, xmul(f, dx)); vz[1] = xadd(y1, xmul(f, dy)); vz[2] = xmul(w, h); vz[3] = xdiv(w, h);
-                    oc_correct(k, vz);
-                    if (i != g - 1) oc_predict_full(k);
-                }
-                virt = g > 0;
+                const double lz[4] = {gf[(B200_OC_LASTZ + 0) * TMAX + t], gf[(B200_OC_LASTZ + 1) * TMAX + t],
+                                      gf[(B200_OC_LASTZ + 2) * TMAX + t], gf[(B200_OC_LASTZ + 3) * TMAX + t]};
+                virt = oc_virtual_trajectory(k, lz, z, tsu, vz);       // gap = index2 - index1 of history_obs
                 fl &= ~B200_OCF_SAVED;
             }
             fl |= B200_OCF_OBSERVED | B200_OCF_HASOBS;
