@@ -38,7 +38,7 @@ def short(name):
     return name[:110]
 
 
-for wl in ("bytetrack", "ocsort", "botsort", "ops"):
+for wl in ("bytetrack", "ocsort", "botsort", "deepocsort", "strongsort", "ops"):
     src = os.path.join(G, f"{R}_launches_{wl}.csv")
     if not os.path.exists(src):
         continue
@@ -67,7 +67,7 @@ try:
     traffic = json.load(open(os.path.join(P, "traffic.json")))
 except Exception:
     pass
-for cap in ("bytetrack", "ocsort", "botsort", "appearance", "gallery", "kf"):
+for cap in ("bytetrack", "ocsort", "botsort", "deepocsort", "strongsort", "appearance", "gallery", "kf"):
     rep = os.path.join(G, f"{R}_full_{cap}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -94,7 +94,8 @@ for cap in ("bytetrack", "ocsort", "botsort", "appearance", "gallery", "kf"):
             wr = float(d["dram__bytes_write.sum"].replace(",", ""))
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             tot_b = rd * scale.get(u["dram__bytes_read.sum"], 1) + wr * scale.get(u["dram__bytes_write.sum"], 1)
-            key = {"bytetrack": "bytetrack_step_kernel", "ocsort": "ocsort_step_kernel", "botsort": "bytetrack_step_kernel<BOT>"}.get(cap)
+            key = {"bytetrack": "bytetrack_step_kernel", "ocsort": "ocsort_step_kernel", "botsort": "bytetrack_step_kernel<BOT>",
+                   "deepocsort": "deepocsort_step_kernel"}.get(cap)
             if key:
                 traffic[key] = {"streams": int(d.get("Grid Size", "0").replace(",", "").split()[0].strip("()")) if d.get("Grid Size") else 0,
                                 "dram_bytes_per_launch": int(tot_b),
