@@ -93,6 +93,41 @@ def check_deepocsort_frame(name, f, out, s, g, heavy):
         assert_close(s["P"].reshape(-1, 64), g["P"][a:b], abs_=1e-10, what=f"{name} frame {f} P")
 
 
+def hybridsort_scenario(name):
+    """(scenario, params, dets, ndets, per-frame seam features of the detections above det_thresh, golden)."""
+    import sys
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    from scenarios import HYBRIDSORT_SCENARIOS, HYBRIDSORT_YAML, hybridsort_inputs
+    sc = dict(HYBRIDSORT_SCENARIOS[name])
+    cfg = dict(HYBRIDSORT_YAML)
+    cfg.update(sc["params"])
+    dets, nd, _, feats = hybridsort_inputs(sc, cfg["det_thresh"])
+    g = load_golden(name)
+    assert np.array_equal(nd, g["ndets"]) and np.allclose([dets.sum(), float(sum(np.abs(f).sum() for f in feats))], g["dets_sum"],
+                                                          rtol=1e-12), "synthetic inputs drifted from the ones the golden was generated on"
+    return sc, cfg, dets, nd, feats, g
+
+
+def check_hybridsort_frame(name, f, out, s, g, heavy):
+    """One frame of a HybridSORT replay against the live reference's golden: output rows (the last column is the SCORE of
+    the input row the reference indexes, hybridsort.py:396), track records, 9-d filter state, four corner velocities."""
+    ref = g["out"][g["out_offs"][f]:g["out_offs"][f + 1]]
+    assert out.reshape(-1, 8).shape == ref.shape, f"{name} frame {f}"
+    if ref.size:
+        assert np.array_equal(out[:, 4:], ref[:, 4:]), f"{name} frame {f}: id/conf/cls/last column"
+        assert_close(out[:, :4], ref[:, :4], what=f"{name} frame {f} boxes")
+    lo, hi = g["rec_offs"][f], g["rec_offs"][f + 1]
+    mine = np.stack([s["track_id"], s["age"], s["time_since_update"], s["hits"], s["hit_streak"], s["observed"]], axis=1).reshape(-1, 6)
+    assert np.array_equal(mine, g["rec"][lo:hi]), f"{name} frame {f}: track records"
+    assert_close(s["x"], g["x"][lo:hi], what=f"{name} frame {f} x")
+    assert_close(s["velocity"].reshape(-1, 8), g["vel"][lo:hi], what=f"{name} frame {f} velocity")
+    assert_close(s["last_observation"], g["last"][lo:hi], what=f"{name} frame {f} last observation")
+    if f in heavy:
+        a, b = heavy[f]
+        assert_close(s["P"].reshape(-1, 81), g["P"][a:b], abs_=1e-10, what=f"{name} frame {f} P")
+
+
 def heavy_offsets(g):
     offs, pos = {}, 0
     for f in g["heavy_frames"]:

@@ -574,6 +574,55 @@ def gen_deepocsort():
               last=_ragged(lasts, 5)[0], P=_ragged(Ps, 64)[0], heavy_frames=np.array(heavy, dtype=np.int32), final_emb=final_emb)
 
 
+def _hyb_snapshot(trk):
+    ts = trk.trackers
+    ints = np.array([[t.id, t.age, t.time_since_update, t.hits, t.hit_streak, int(t.kf.observed)] for t in ts],
+                    dtype=np.int32).reshape(-1, 6)
+    x = np.stack([t.kf.x[:, 0] for t in ts]) if ts else np.zeros((0, 9))
+    P = np.stack([t.kf.P.reshape(81) for t in ts]) if ts else np.zeros((0, 81))
+    vel = np.array([[v if v is not None else np.zeros(2) for v in (t.velocity_lt, t.velocity_rt, t.velocity_lb, t.velocity_rb)]
+                    for t in ts], dtype=np.float64).reshape(-1, 8)
+    last = np.array([t.last_observation for t in ts], dtype=np.float64).reshape(-1, 5)
+    return ints, x, P, vel, last
+
+
+def gen_hybridsort():
+    rh.install()
+    from scenarios import HYBRIDSORT_SCENARIOS, HYBRIDSORT_YAML, hybridsort_inputs
+    from boxmot.trackers.hybridsort.hybridsort import HybridSORT
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    only = os.environ.get("GOLDEN_ONLY")
+    for name, sc in HYBRIDSORT_SCENARIOS.items():
+        if only and name not in only.split(","):
+            continue
+        cfg = dict(HYBRIDSORT_YAML)
+        cfg.update(sc["params"])
+        dets, nd, embs, feats = hybridsort_inputs(sc, cfg["det_thresh"])
+        trk = HybridSORT(None, "cpu", False, **cfg)                 # resets KalmanBoxTracker.count (hybridsort.py:364)
+        outs, ints, xs, Ps, vels, lasts, heavy = [], [], [], [], [], [], []
+        for f in range(sc["n_frames"]):
+            if nd[f]:
+                rh.FakeReID.queue.append(embs[f, :nd[f]])            # features of every detection (hybridsort.py:394)
+            o = trk.update(dets[f, :nd[f]], img)                     # through PerClassDecorator (one class: one call)
+            outs.append(o)
+            ii, x, P, vel, last = _hyb_snapshot(trk)
+            ints.append(ii)
+            xs.append(x)
+            vels.append(vel)
+            lasts.append(last)
+            if f % 10 == 9 or f == sc["n_frames"] - 1:
+                Ps.append(P)
+                heavy.append(f)
+        assert not rh.FakeReID.queue
+        ts = trk.trackers
+        final_emb = np.stack([np.asarray(t.smooth_feat, dtype=np.float32).reshape(-1) for t in ts]) if ts else np.zeros((0, sc["emb_dim"]), dtype=np.float32)
+        out_flat, out_offs = _ragged(outs, 8)
+        int_flat, int_offs = _ragged(ints, 6)
+        _save(name, ndets=nd, dets_sum=np.array([dets.sum(), float(sum(np.abs(f).sum() for f in feats))]), out=out_flat,
+              out_offs=out_offs, rec=int_flat.astype(np.int32), rec_offs=int_offs, x=_ragged(xs, 9)[0], vel=_ragged(vels, 8)[0],
+              last=_ragged(lasts, 5)[0], P=_ragged(Ps, 81)[0], heavy_frames=np.array(heavy, dtype=np.int32), final_emb=final_emb)
+
+
 def gen_fullsize():
     """Rows-only goldens at the BASELINE config sizes (scenarios.FULLSIZE)."""
     rh.install()
@@ -629,7 +678,7 @@ def gen_fullsize():
               boxes=np.concatenate(boxes), box_frames=np.array(box_frames, dtype=np.int32))
 
 
-GENERATORS = {"fullsize": gen_fullsize, "deepocsort": gen_deepocsort, "mot_deepocsort": gen_mot_deepocsort, "mot_strongsort": gen_mot_strongsort, "mot_botsort": gen_mot_botsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
+GENERATORS = {"fullsize": gen_fullsize, "hybridsort": gen_hybridsort, "deepocsort": gen_deepocsort, "mot_deepocsort": gen_mot_deepocsort, "mot_strongsort": gen_mot_strongsort, "mot_botsort": gen_mot_botsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
               "mot": gen_mot, "strongsort": gen_strongsort, "aux": gen_aux}
 
 if __name__ == "__main__":

@@ -150,6 +150,36 @@ def deepocsort_inputs(sc, det_thresh):
     return dets, nd, embs, feats
 
 
+# ----------------------------------------------------------------------------- HybridSORT
+# boxmot/configs/hybridsort.yaml as forwarded by tracker_zoo.py:100-115 (use_byte is not forwarded; everything else is
+# fixed in HybridSORT.__init__, hybridsort.py:337-364)
+HYBRIDSORT_YAML = dict(det_thresh=0, max_age=30, min_hits=1, iou_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2)
+HYBRIDSORT_SCENARIOS = {
+    # occlusion runs exercise freeze / unfreeze (hybridsort_kf.py:390-436, score read as aspect ratio) / OCR
+    "hybridsort_c4": dict(stream=0, n_objects=25, n_frames=120, emb_dim=128, kw=dict(occlusion=True), params={}),
+    # misses and false positives, a detection threshold (the class / last column then come from the UNFILTERED row of the
+    # same index, hybridsort.py:396-404), short memory, output after 3 hits, plain IoU
+    "hybridsort_churn": dict(stream=921, n_objects=16, n_frames=160, emb_dim=64, kw=dict(miss_prob=0.3, fp_rate=3.0),
+                             params=dict(det_thresh=0.3, max_age=8, min_hits=3, asso_func="iou")),
+    # crowded, long occlusions, DIoU, a two-frame velocity window
+    "hybridsort_diou": dict(stream=922, n_objects=40, n_frames=100, emb_dim=32, kw=dict(miss_prob=0.1, fp_rate=2.0, occlusion=True),
+                            params=dict(asso_func="diou", delta_t=2, min_hits=2)),
+}
+
+
+def hybridsort_inputs(sc, det_thresh):
+    """dets[F, D, 6], ndets[F], raw embeddings, and per frame the seam features of the detections that pass
+    `conf > det_thresh`.  The reference extracts features for EVERY detection (hybridsort.py:394) and the seam divides by
+    the Frobenius norm of that whole matrix; only the rows above det_thresh are used (:403)."""
+    dets, nd, embs = make_stream(4, sc["stream"], sc["n_objects"], sc["n_frames"], emb_dim=sc["emb_dim"], **sc["kw"])
+    feats = []
+    for f in range(sc["n_frames"]):
+        keep = dets[f, :nd[f], 4] > det_thresh
+        raw = embs[f, :nd[f]].astype(np.float32)
+        feats.append((raw / np.linalg.norm(raw))[keep] if len(raw) else np.zeros((0, sc["emb_dim"]), dtype=np.float32))
+    return dets, nd, embs, feats
+
+
 def mot_feats(seq_index, frame, n, dim=32):
     """Seeded stand-in embeddings for the detections of frame `frame` of MOT17-mini sequence `seq_index` (raw, before the
     seam's whole-matrix normalisation)."""

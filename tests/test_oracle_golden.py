@@ -267,6 +267,25 @@ def test_deepocsort_oracle_replays_reference(name):
     assert trk.stats["oru"] > 50 and trk.stats["lap_frames"] > 20 and trk.stats["ocr_frames"] >= 1
 
 
+# ----------------------------------------------------------------------------- HybridSORT
+@pytest.mark.parametrize("name", ["hybridsort_c4", "hybridsort_churn", "hybridsort_diou"])
+def test_hybridsort_oracle_replays_reference(name):
+    """ids, hit / age counters, observed flags and the reference's odd last column exact; 9-d filter state, the four corner
+    velocities, last observations and boxes to 1e-9, smoothed float32 embeddings to 2e-6 against the live reference, through
+    occlusions (unfreeze with the score read as aspect ratio), the long-term-ReID correction and OCR."""
+    from _util import check_hybridsort_frame, heavy_offsets, hybridsort_scenario
+    from oracle.hybridsort import HybridSortOracle
+    sc, cfg, dets, nd, feats, g = hybridsort_scenario(name)
+    trk = HybridSortOracle(**cfg)
+    heavy = heavy_offsets(g)
+    for f in range(sc["n_frames"]):
+        out = trk.update(dets[f, :nd[f]], feats[f])
+        check_hybridsort_frame(name, f, out, trk.snapshot(), g, heavy)
+    assert_close(trk.snapshot()["smooth_feat"], g["final_emb"], rel=2e-6, abs_=2e-6, what="embeddings")
+    assert trk.stats["oru"] > 10 and trk.stats["corrections"] > 20
+    assert name != "hybridsort_c4" or trk.stats["ocr_frames"] >= 1
+
+
 def test_camera_warp_leaves_two_independent_4x4_blocks():
     """Structure the fused frame steps can rely on when they take a camera warp (DESIGN.md performance plan): on the live
     reference's moving-camera runs the covariance couples x with y (and w with h) but the (x, y, vx, vy) and (w, h, vw, vh)
