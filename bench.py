@@ -94,6 +94,15 @@ WORKLOADS = {
                        img_hw=(2160, 3840),
                        label="config4 as a tracker: StrongSORT (strongsort.yaml: max_dist 0.2, nn_budget 100, mc_lambda 0.995, ema_alpha 0.8; "
                              "Mahalanobis gate + gallery cosine cost, 512-d embeddings), 190 objects per stream, sharded by stream"),
+    # config 4 through HybridSORT: every (detection, tracker) pair carries an appearance term (a dense 512-d cosine matrix per
+    # stream and frame) next to the four-corner direction cost; padded host interface (the context takes no packed frames).
+    "hybridsort": dict(kind="hybridsort", config=4, objects=190, streams=512, max_dets=224, max_tracks=256, emb=512, distinct=128,
+                       steps=20, warmup=5, padded_e2e=True, cpu_sample=(10, 3),
+                       params=dict(det_thresh=0, max_age=30, min_hits=1, iou_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2),  # hybridsort.yaml
+                       b_slot=2 * (48 * 8 + 11 * 4), b_feat=512 * (4 + 4 + 4), kernel="hybridsort_step_kernel", img_hw=(2160, 3840),
+                       label="config4 as a tracker: HybridSORT (hybridsort.yaml: giou, det_thresh 0, min_hits 1, max_age 30; four-corner "
+                             "direction cost + 1.3 x cosine distance on 512-d embeddings for every pair), 190 objects + ~30 false-positive "
+                             "trackers per stream, sharded by stream"),
 }
 W = dict(WORKLOADS["bytetrack"])          # the active workload (set in main)
 CONFIG_ID, N_OBJECTS, STREAMS_PER_GPU = W["config"], W["objects"], W["streams"]
@@ -191,6 +200,9 @@ def _make_oracle():
     if W["kind"] == "strongsort":
         from oracle.strongsort import StrongSORTOracle
         return StrongSORTOracle(**PARAMS)
+    if W["kind"] == "hybridsort":
+        from oracle.hybridsort import HybridSortOracle
+        return HybridSortOracle(**PARAMS)
     from oracle.botsort import BoTSORTOracle
     return BoTSORTOracle(**PARAMS)
 
@@ -208,7 +220,7 @@ def _oracle_worker(args):
     def step(f):
         for k, t in enumerate(trks):
             d, n, e = data[k]
-            if W["kind"] == "deepocsort":
+            if W["kind"] in ("deepocsort", "hybridsort"):
                 rows = d[f, :n[f], 4] > PARAMS["det_thresh"]
                 t.update(d[f, :n[f]], e[f, :n[f]][rows], W["img_hw"])
                 continue

@@ -36,7 +36,8 @@ typedef enum {
     B200TRACK_OCSORT = 1,         /* boxmot/trackers/ocsort/ocsort.py:190 OCSort               */
     B200TRACK_BOTSORT = 2,        /* boxmot/trackers/botsort/bot_sort.py:184 BoTSORT           */
     B200TRACK_DEEPOCSORT = 3,     /* boxmot/trackers/deepocsort/deep_ocsort.py:308 DeepOCSort  */
-    B200TRACK_STRONGSORT = 4      /* boxmot/trackers/strongsort/strong_sort.py:13 StrongSORT   */
+    B200TRACK_STRONGSORT = 4,     /* boxmot/trackers/strongsort/strong_sort.py:13 StrongSORT   */
+    B200TRACK_HYBRIDSORT = 5      /* boxmot/trackers/hybridsort/hybridsort.py:336 HybridSORT   */
 } b200track_kind;
 
 typedef enum { B200TRACK_KF_XYAH = 0, B200TRACK_KF_XYWH = 1, B200TRACK_KF_XYAH_CONF = 2 } b200track_kf_kind;
@@ -93,6 +94,11 @@ typedef struct {
     double ema_alpha;
     int32_t n_init;
     int32_t nn_budget;
+    /* HybridSORT (hybridsort.py:337-364) reads det_thresh, iou_thresh, inertia, max_age, min_hits, delta_t, asso_func and
+     * feat_dim (a multiple of 4) above; everything else the reference's constructor fixes is compiled in.  use_byte must
+     * be 0 (tracker_zoo.py:100-115 never forwards it; the branch cannot produce a result row).  Padded interface only;
+     * d_feats holds one appearance row per detection row (get_features of every box, hybridsort.py:394).  The last column
+     * of a result row is what the reference writes there: the score of the input row the match indexes (:396-404). */
 } b200track_config;
 
 typedef struct b200track_ctx b200track_ctx;
@@ -218,6 +224,13 @@ int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, float* h_fe
  * h_extra[max_tracks, 8] = velocity[2], last_observation[5] (placeholder -1), unused; h_emb[max_tracks, feat_dim] = the
  * smoothed embedding (fp64), NULL to skip. */
 int b200track_get_track_extras(b200track_ctx* ctx, int32_t stream_index, double* h_extra, double* h_emb);
+/* HybridSORT contexts: the KalmanBoxTracker list of one stream (hybridsort.py:106-334) in list order.  h_counts[4] as
+ * b200track_get_state; h_rec[max_tracks, 6] = id, age, time_since_update, hits, hit_streak, kf.observed; h_x[max_tracks, 9]
+ * = kf.x; h_P[max_tracks, 81] = dense kf.P; h_vel[max_tracks, 8] = velocity_lt, _rt, _lb, _rb as (dy, dx), zeros while
+ * None; h_last[max_tracks, 5] = last_observation (-1 placeholder); h_aux[max_tracks, 3] = conf, cls, matched input row.
+ * Any output pointer may be NULL.  The smoothed embeddings come from b200track_get_features (same order). */
+int b200track_get_state_hybridsort(b200track_ctx* ctx, int32_t stream_index, int32_t* h_counts, int32_t* h_rec, double* h_x,
+                                   double* h_P, double* h_vel, double* h_last, double* h_aux);
 /* Event counters summed over all streams since create / reset (DeepOCSORT contexts): h_out8[0] = first associations solved
  * as an assignment problem (not by the permutation shortcut, association.py:157-159), [1] = recovery rounds that ran an
  * assignment (deep_ocsort.py:466), [2] = observation-centric re-updates (deepocsort_kf.py:433-478); StrongSORT contexts: [3] = stored gallery rows the

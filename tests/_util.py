@@ -93,8 +93,9 @@ def check_deepocsort_frame(name, f, out, s, g, heavy):
         assert_close(s["P"].reshape(-1, 64), g["P"][a:b], abs_=1e-10, what=f"{name} frame {f} P")
 
 
-def hybridsort_scenario(name):
-    """(scenario, params, dets, ndets, per-frame seam features of the detections above det_thresh, golden)."""
+def hybridsort_scenario(name, full=False):
+    """(scenario, params, dets, ndets, per-frame seam features of the detections above det_thresh - `full`: of every
+    detection, as the device path takes them -, golden)."""
     import sys
     if GOLDEN not in sys.path:
         sys.path.insert(0, GOLDEN)
@@ -106,6 +107,8 @@ def hybridsort_scenario(name):
     g = load_golden(name)
     assert np.array_equal(nd, g["ndets"]) and np.allclose([dets.sum(), float(sum(np.abs(f).sum() for f in feats))], g["dets_sum"],
                                                           rtol=1e-12), "synthetic inputs drifted from the ones the golden was generated on"
+    if full:
+        feats = hybridsort_inputs(sc, cfg["det_thresh"], full=True)[3]
     return sc, cfg, dets, nd, feats, g
 
 

@@ -167,16 +167,18 @@ HYBRIDSORT_SCENARIOS = {
 }
 
 
-def hybridsort_inputs(sc, det_thresh):
+def hybridsort_inputs(sc, det_thresh, full=False):
     """dets[F, D, 6], ndets[F], raw embeddings, and per frame the seam features of the detections that pass
     `conf > det_thresh`.  The reference extracts features for EVERY detection (hybridsort.py:394) and the seam divides by
-    the Frobenius norm of that whole matrix; only the rows above det_thresh are used (:403)."""
+    the Frobenius norm of that whole matrix; only the rows above det_thresh are used (:403).  `full`: the rows of all
+    detections instead (what the device path is handed)."""
     dets, nd, embs = make_stream(4, sc["stream"], sc["n_objects"], sc["n_frames"], emb_dim=sc["emb_dim"], **sc["kw"])
     feats = []
     for f in range(sc["n_frames"]):
         keep = dets[f, :nd[f], 4] > det_thresh
         raw = embs[f, :nd[f]].astype(np.float32)
-        feats.append((raw / np.linalg.norm(raw))[keep] if len(raw) else np.zeros((0, sc["emb_dim"]), dtype=np.float32))
+        rows = raw / np.linalg.norm(raw) if len(raw) else np.zeros((0, sc["emb_dim"]), dtype=np.float32)
+        feats.append(rows if full else rows[keep])
     return dets, nd, embs, feats
 
 

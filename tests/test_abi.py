@@ -56,7 +56,7 @@ def test_no_cpu_fallback(has_cuda):
 def test_factory_names_and_configs():
     import yaml
     import yolo_tracking_b200 as pkg
-    assert pkg.TRACKERS == ["bytetrack", "botsort", "ocsort", "strongsort", "deepocsort"]
+    assert pkg.TRACKERS == ["bytetrack", "botsort", "ocsort", "strongsort", "deepocsort", "hybridsort"]     # boxmot/__init__.py:14
     for name in pkg.TRACKERS:
         path = pkg.get_tracker_config(name)
         assert path.name == name + ".yaml" and path.exists()
@@ -65,3 +65,5 @@ def test_factory_names_and_configs():
     assert (bt["track_thresh"], bt["match_thresh"], bt["track_buffer"], bt["frame_rate"]) == (0.5, 0.8, 30, 30)
     with pytest.raises(ValueError):
         pkg.create_tracker("nosuch", pkg.get_tracker_config("bytetrack"), None, 0, False, False)
+    hy = yaml.safe_load(open(pkg.get_tracker_config("hybridsort")))
+    assert (hy["det_thresh"], hy["iou_thresh"], hy["asso_func"], hy["min_hits"], hy["use_byte"]) == (0, 0.3, "giou", 1, False)

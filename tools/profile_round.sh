@@ -13,6 +13,16 @@ run() {   # name, ncu args..., -- , command...
     shift
     "$@" > $O/${R}_${name}_plain.log 2>&1 || { echo "$name: plain run failed"; tail -5 $O/${R}_${name}_plain.log; return 1; }
     ncu "${ncu_args[@]}" "$@" > $O/${R}_${name}_ncu.log 2>&1 || { echo "$name: ncu failed"; tail -5 $O/${R}_${name}_ncu.log; }
+    # gpurun brings back at most 64 MiB: a --set full report is exported to its raw-metric page (what
+    # tools/summarize_profiles.py reads) and the per-line source page of the step kernels (tools/ncu_lines.py) on the box,
+    # and the .ncu-rep itself is dropped unless KEEP_REP=1
+    local rep=$O/${R}_${name#full_}.ncu-rep
+    [ "${name#full_}" != "$name" ] && rep=$O/${R}_${name}.ncu-rep
+    if [ -f "$rep" ]; then
+        ncu -i "$rep" --page raw --csv > "${rep%.ncu-rep}.raw.csv" 2>/dev/null
+        case "$name" in full_bytetrack|full_ocsort|full_botsort|full_deepocsort|full_hybridsort) ncu -i "$rep" --page source --csv > "${rep%.ncu-rep}.source.csv" 2>/dev/null; gzip -f "${rep%.ncu-rep}.source.csv";; esac
+        [ -z "${KEEP_REP:-}" ] && rm -f "$rep"
+    fi
 }
 LL="--metrics gpu__time_duration.sum --clock-control none -c 400 --csv"
 BT="python bench.py --steps 20 --warmup 5 --no-cpu-baseline"

@@ -69,9 +69,13 @@ except Exception:
     pass
 for cap in ("bytetrack", "ocsort", "botsort", "deepocsort", "strongsort", "appearance", "gallery", "kf"):
     rep = os.path.join(G, f"{R}_full_{cap}.ncu-rep")
-    if not os.path.exists(rep):
+    raw = os.path.join(G, f"{R}_full_{cap}.raw.csv")          # exported on the GPU box by tools/profile_round.sh
+    if os.path.exists(raw):
+        txt = open(raw).read()
+    elif os.path.exists(rep):
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
         continue
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     if len(rows) < 3:
         continue

@@ -8,7 +8,7 @@ __version__ = "0.1.0"
 
 from .tracker_zoo import create_tracker, get_tracker_config  # noqa: E402,F401
 
-TRACKERS = ["bytetrack", "botsort", "ocsort", "strongsort", "deepocsort"]
+TRACKERS = ["bytetrack", "botsort", "ocsort", "strongsort", "deepocsort", "hybridsort"]
 
 
 def __getattr__(name):          # lazy: BYTETracker / OCSORT / BoTSORT / BatchedTracker
@@ -27,11 +27,14 @@ def __getattr__(name):          # lazy: BYTETracker / OCSORT / BoTSORT / Batched
     if name in ("DeepOCSORT", "DeepOCSort"):
         from .trackers.deepocsort import DeepOCSort
         return DeepOCSort
+    if name == "HybridSORT":
+        from .trackers.hybridsort import HybridSORT
+        return HybridSORT
     if name == "BatchedTracker":
         from .batch import BatchedTracker
         return BatchedTracker
     raise AttributeError(name)
 
 
-__all__ = ("__version__", "BYTETracker", "OCSORT", "BoTSORT", "StrongSORT", "DeepOCSORT", "BatchedTracker", "create_tracker",
+__all__ = ("__version__", "BYTETracker", "OCSORT", "BoTSORT", "StrongSORT", "DeepOCSORT", "HybridSORT", "BatchedTracker", "create_tracker",
            "get_tracker_config", "TRACKERS")

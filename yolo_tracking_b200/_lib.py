@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("B200TRACK_LIB") or os.path.join(_HERE, "lib", "libb20
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "b200track.h")
 
 OK, ERR_ARG, ERR_CUDA, ERR_CAPACITY, ERR_STATE = 0, -1, -2, -3, -4
-BYTETRACK, OCSORT, BOTSORT, DEEPOCSORT, STRONGSORT = 0, 1, 2, 3, 4
+BYTETRACK, OCSORT, BOTSORT, DEEPOCSORT, STRONGSORT, HYBRIDSORT = 0, 1, 2, 3, 4, 5
 KF_XYAH, KF_XYWH, KF_XYAH_CONF = 0, 1, 2
 SIM = {"iou": 0, "giou": 1, "diou": 2, "ciou": 3, "centroid": 4}
 
@@ -65,6 +65,7 @@ SIGNATURES = {
     "b200track_step": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "b200track_step_cam": (C.c_int, [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P]),
     "b200track_get_track_extras": (C.c_int, [_P, _I, _P, _P]),
+    "b200track_get_state_hybridsort": (C.c_int, [_P, _I, _P, _P, _P, _P, _P, _P, _P]),
     "b200track_counters": (C.c_int, [_P, C.POINTER(C.c_uint64 * 8)]),
     "b200track_step_host": (C.c_int, [_P, _P, _P, _P, _I, _I, _P, _P]),
     "b200track_host_slots": (C.c_int, [_P]),

@@ -14,7 +14,7 @@ import numpy as np
 from . import _lib
 
 _KINDS = {"bytetrack": _lib.BYTETRACK, "ocsort": _lib.OCSORT, "botsort": _lib.BOTSORT, "deepocsort": _lib.DEEPOCSORT,
-          "strongsort": _lib.STRONGSORT}
+          "strongsort": _lib.STRONGSORT, "hybridsort": _lib.HYBRIDSORT}
 
 
 def _ptr(a):
@@ -78,6 +78,16 @@ class BatchedTracker:
             cfg.aw_off = int(bool(params.get("aw_off", False)))
             if cfg.embedding_off:
                 self.feat_dim = cfg.feat_dim = 0
+        elif kind == "hybridsort":
+            # HybridSORT defaults (hybridsort.py:337-338); everything else is fixed by its constructor
+            cfg.det_thresh = params["det_thresh"]
+            cfg.max_age = int(params.get("max_age", 30))
+            cfg.min_hits = int(params.get("min_hits", 3))
+            cfg.iou_thresh = params.get("iou_threshold", params.get("iou_thresh", 0.3))
+            cfg.delta_t = int(params.get("delta_t", 3))
+            cfg.asso_func = _lib.SIM[params.get("asso_func", "iou")]
+            cfg.inertia = params.get("inertia", 0.2)
+            cfg.use_byte = int(bool(params.get("use_byte", False)))
         elif kind == "strongsort":
             # StrongSORT defaults (strong_sort.py:14-25)
             cfg.max_dist = params.get("max_dist", 0.2)
@@ -352,6 +362,19 @@ class BatchedTracker:
         T = self.max_tracks
         counts = np.zeros(4, dtype=np.int32)
         rec = np.zeros((T, 6), dtype=np.int32)
+        if self.kind == "hybridsort":
+            x, P, vel, last, aux = np.zeros((T, 9)), np.zeros((T, 81)), np.zeros((T, 8)), np.zeros((T, 5)), np.zeros((T, 3))
+            feat = np.zeros((T, self.feat_dim), dtype=np.float32)
+            _lib.check(self._lib.b200track_get_state_hybridsort(self._ctx, int(stream), _ptr(counts), _ptr(rec), _ptr(x), _ptr(P),
+                                                                _ptr(vel), _ptr(last), _ptr(aux)))
+            _lib.check(self._lib.b200track_get_features(self._ctx, int(stream), _ptr(feat)))
+            n = int(counts[0])
+            return dict(n=n, id_count=int(counts[2]), frame_count=int(counts[3]),
+                        track_id=rec[:n, 0].copy(), age=rec[:n, 1].copy(), time_since_update=rec[:n, 2].copy(),
+                        hits=rec[:n, 3].copy(), hit_streak=rec[:n, 4].copy(), observed=rec[:n, 5].copy(),
+                        x=x[:n].copy(), P=P[:n].reshape(n, 9, 9).copy(), velocity=vel[:n].reshape(n, 4, 2).copy(),
+                        last_observation=last[:n].copy(), conf=aux[:n, 0].copy(), cls=aux[:n, 1].copy(),
+                        det_ind=aux[:n, 2].copy(), smooth_feat=feat[:n].copy())
         mean = np.zeros((T, 8))
         cov = np.zeros((T, 64))
         aux = np.zeros((T, 3))

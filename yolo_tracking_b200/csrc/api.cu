@@ -83,7 +83,7 @@ static int check_cfg(const b200track_config* c) {
     if (c->max_dets <= 0 || c->max_dets % 32 || c->max_dets > 512) {
         set_error("max_dets must be a multiple of 32 in [32, 512]"); return B200TRACK_ERR_ARG; }
     if (c->kind != B200TRACK_BYTETRACK && c->kind != B200TRACK_OCSORT && c->kind != B200TRACK_BOTSORT && c->kind != B200TRACK_DEEPOCSORT &&
-        c->kind != B200TRACK_STRONGSORT) {
+        c->kind != B200TRACK_STRONGSORT && c->kind != B200TRACK_HYBRIDSORT) {
         set_error("unknown tracker kind"); return B200TRACK_ERR_ARG; }
     return 0;
 }
@@ -97,7 +97,7 @@ extern "C" void b200track_destroy(b200track_ctx* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->p.state_f); cudaFree(ctx->p.state_i); cudaFree(ctx->p.counts);
     cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.stats); cudaFree(ctx->p.err_slot); cudaFree(ctx->p.dbg); cudaFree(ctx->p.scratch);
-    cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.cls_hist); cudaFree(ctx->p.emb_pool);
+    cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.feat_curr); cudaFree(ctx->p.cls_hist); cudaFree(ctx->p.emb_pool);
     {
         b200::SSParams& q = ctx->ss;
         cudaFree(q.mean); cudaFree(q.cov); cudaFree(q.conf); cudaFree(q.cls); cudaFree(q.ti); cudaFree(q.order); cudaFree(q.feat);
@@ -154,13 +154,18 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         if (cfg->feat_dim <= 0 || cfg->feat_dim % 128 || cfg->feat_dim > 4096) {
             set_error("BoT-SORT with_reid needs feat_dim to be a multiple of 128 in [128, 4096]"); return B200TRACK_ERR_ARG; }
     }
-    if (cfg->kind == B200TRACK_OCSORT || cfg->kind == B200TRACK_DEEPOCSORT) {
-        if (cfg->delta_t < 1 || cfg->delta_t > 3) { set_error("OC-SORT / DeepOCSORT delta_t must be in [1, 3]"); return B200TRACK_ERR_ARG; }
+    if (cfg->kind == B200TRACK_OCSORT || cfg->kind == B200TRACK_DEEPOCSORT || cfg->kind == B200TRACK_HYBRIDSORT) {
+        if (cfg->delta_t < 1 || cfg->delta_t > 3) { set_error("OC-SORT / DeepOCSORT / HybridSORT delta_t must be in [1, 3]"); return B200TRACK_ERR_ARG; }
         if (cfg->asso_func < 0 || cfg->asso_func > B200TRACK_SIM_CENTROID) { set_error("unknown asso_func"); return B200TRACK_ERR_ARG; }
     }
     if (cfg->kind == B200TRACK_DEEPOCSORT && !cfg->embedding_off) {
         if (cfg->feat_dim <= 0 || cfg->feat_dim % 4 || cfg->feat_dim > 4096) {
             set_error("DeepOCSORT needs feat_dim to be a multiple of 4 in [4, 4096] (or embedding_off)"); return B200TRACK_ERR_ARG; }
+    }
+    if (cfg->kind == B200TRACK_HYBRIDSORT) {
+        if (cfg->feat_dim <= 0 || cfg->feat_dim % 4 || cfg->feat_dim > 4096) {
+            set_error("HybridSORT needs feat_dim to be a multiple of 4 in [4, 4096]"); return B200TRACK_ERR_ARG; }
+        if (cfg->use_byte) { set_error("HybridSORT: use_byte is not supported (the reference's branch cannot produce a result row)"); return B200TRACK_ERR_ARG; }
     }
     if (cfg->kind == B200TRACK_STRONGSORT) {
         if (cfg->feat_dim <= 0 || cfg->feat_dim % 64 || cfg->feat_dim > 4096) {
@@ -192,6 +197,7 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     p.det_thresh = cfg->det_thresh; p.iou_thresh = cfg->iou_thresh; p.inertia = cfg->inertia;
     p.max_age = cfg->max_age; p.min_hits = cfg->min_hits; p.delta_t = cfg->delta_t; p.asso_func = cfg->asso_func; p.use_byte = cfg->use_byte ? 1 : 0;
     if (cfg->kind == B200TRACK_OCSORT) { ctx->nf = B200_OC_NF; ctx->ni = B200_OC_NI; }
+    if (cfg->kind == B200TRACK_HYBRIDSORT) { ctx->nf = B200_HY_NF; ctx->ni = B200_HY_NI; }
     if (cfg->kind == B200TRACK_DEEPOCSORT) {
         ctx->nf = B200_DO_NF; ctx->ni = B200_DO_NI;
         p.w_assoc_emb = cfg->w_association_emb; p.alpha_fixed_emb = cfg->alpha_fixed_emb; p.aw_param = cfg->aw_param;
@@ -253,10 +259,17 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         if (!(cfg->asso_func <= B200TRACK_SIM_GIOU && cfg->iou_thresh >= 0.0))
             CU_TRY_CTX(cudaMalloc(&p.scratch, S * T * (size_t)b200::step_variant_dmax(ctx->variant) * sizeof(double)));
     }
+    if (cfg->kind == B200TRACK_HYBRIDSORT) {
+        CU_TRY_CTX(cudaMalloc(&p.feat_pool, S * T * (size_t)cfg->feat_dim * sizeof(float)));
+        CU_TRY_CTX(cudaMemset(p.feat_pool, 0, S * T * (size_t)cfg->feat_dim * sizeof(float)));
+        // every pair has an appearance term: per-stream cost matrix [detection capacity of the variant][slot capacity]
+        CU_TRY_CTX(cudaMalloc(&p.scratch, S * T * (size_t)b200::step_variant_dmax(ctx->variant) * sizeof(double)));
+    }
     if (cfg->kind == B200TRACK_BOTSORT) {
         CU_TRY_CTX(cudaMalloc(&p.cls_hist, S * T * 9 * sizeof(double)));
         if (cfg->with_reid) {
             CU_TRY_CTX(cudaMalloc(&p.feat_pool, S * T * (size_t)cfg->feat_dim * sizeof(float)));
+            CU_TRY_CTX(cudaMalloc(&p.feat_curr, S * D * (size_t)cfg->feat_dim * sizeof(float)));
         }
     }
     CU_TRY_CTX(cudaMalloc(&p.counts, S * 4 * sizeof(int)));
@@ -283,6 +296,7 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
     const size_t smem = cfg->kind == B200TRACK_STRONGSORT ? b200::strongsort_match_smem()
                         : cfg->kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
                         : cfg->kind == B200TRACK_DEEPOCSORT ? b200::deepocsort_step_smem(ctx->variant)
+                        : cfg->kind == B200TRACK_HYBRIDSORT ? b200::hybridsort_step_smem(ctx->variant)
                         : b200::bytetrack_step_smem(ctx->variant, cfg->kind == B200TRACK_BOTSORT, cfg->kind == B200TRACK_BOTSORT && cfg->camera_motion);
     int max_smem = 0;
     CU_TRY_CTX(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device));
@@ -314,7 +328,10 @@ static int launch_step(b200track_ctx* ctx, const double* d_dets, const int32_t* 
         if (!ctx->p.embedding_off && !d_feats) { set_error("DeepOCSORT: the embedding buffer is NULL"); return B200TRACK_ERR_ARG; }
         CU_TRY(b200::launch_deepocsort_step(p, ctx->variant, st));
     } else if (ctx->cfg.kind == B200TRACK_OCSORT) CU_TRY(b200::launch_ocsort_step(p, ctx->variant, st));
-    else if (ctx->cfg.kind == B200TRACK_BOTSORT) {
+    else if (ctx->cfg.kind == B200TRACK_HYBRIDSORT) {
+        if (!d_feats) { set_error("HybridSORT: the embedding buffer is NULL"); return B200TRACK_ERR_ARG; }
+        CU_TRY(b200::launch_hybridsort_step(p, ctx->variant, st));
+    } else if (ctx->cfg.kind == B200TRACK_BOTSORT) {
         if (p.with_reid && !d_feats) { set_error("BoT-SORT with_reid: the embedding buffer is NULL"); return B200TRACK_ERR_ARG; }
         CU_TRY(b200::launch_botsort_step(p, ctx->variant, st, ctx->cfg.camera_motion != 0));
     } else CU_TRY(b200::launch_bytetrack_step(p, ctx->kf_kind, ctx->variant, st));
@@ -371,7 +388,7 @@ extern "C" int b200track_submit_host(b200track_ctx* ctx, int32_t slot, const dou
     if (!ctx || !h_dets || !h_ndets || !h_out || !h_nout) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
     if (slot < 0 || slot >= NSLOT) { set_error("slot out of range"); return B200TRACK_ERR_ARG; }
     if (((ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.with_reid) || (ctx->cfg.kind == B200TRACK_DEEPOCSORT && !ctx->p.embedding_off) ||
-         ctx->cfg.kind == B200TRACK_STRONGSORT) && !h_feats) {
+         ctx->cfg.kind == B200TRACK_STRONGSORT || ctx->cfg.kind == B200TRACK_HYBRIDSORT) && !h_feats) {
         set_error("this context needs embeddings: h_feats is NULL"); return B200TRACK_ERR_ARG; }
     ON_DEVICE(ctx);
     HostSlot& s = ctx->slot[slot];
@@ -442,7 +459,8 @@ static int row_bytes_of(const b200track_ctx* ctx) {
 
 extern "C" int b200track_frame_layout(b200track_ctx* ctx, int64_t n_rows, int32_t det_dtype, b200track_layout* out) {
     if (!ctx || !out) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
-    if (ctx->cfg.kind == B200TRACK_STRONGSORT) { set_error("StrongSORT contexts use the padded interface (b200track_step / _submit_host)"); return B200TRACK_ERR_STATE; }
+    if (ctx->cfg.kind == B200TRACK_STRONGSORT || ctx->cfg.kind == B200TRACK_HYBRIDSORT) {
+        set_error("StrongSORT / HybridSORT contexts use the padded interface (b200track_step / _submit_host)"); return B200TRACK_ERR_STATE; }
     if (n_rows < 0 || (det_dtype != B200TRACK_F32 && det_dtype != B200TRACK_F64)) { set_error("bad n_rows / det_dtype"); return B200TRACK_ERR_ARG; }
     const uint64_t S = ctx->cfg.n_streams, R = (uint64_t)n_rows;
     const uint64_t det_row = det_dtype == B200TRACK_F32 ? 24 : 48;
@@ -610,6 +628,7 @@ extern "C" int b200track_footprint(b200track_ctx* ctx, uint64_t* h_state, uint64
     if (h_state) *h_state = (uint64_t)ctx->tcap * (ctx->nf * 8 + ctx->ni * 4) + 4 * sizeof(int) + sizeof(unsigned long long);
     if (h_smem) *h_smem = ctx->cfg.kind == B200TRACK_OCSORT ? b200::ocsort_step_smem(ctx->variant)
                           : ctx->cfg.kind == B200TRACK_DEEPOCSORT ? b200::deepocsort_step_smem(ctx->variant)
+                          : ctx->cfg.kind == B200TRACK_HYBRIDSORT ? b200::hybridsort_step_smem(ctx->variant)
                           : b200::bytetrack_step_smem(ctx->variant, ctx->cfg.kind == B200TRACK_BOTSORT, ctx->cfg.kind == B200TRACK_BOTSORT && ctx->cfg.camera_motion);
     return 0;
 }
@@ -621,6 +640,7 @@ extern "C" int b200track_get_state(b200track_ctx* ctx, int32_t stream_index, int
     ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
     const size_t T = ctx->tcap, s = stream_index;
+    if (ctx->cfg.kind == B200TRACK_HYBRIDSORT) { set_error("HybridSORT contexts are read with b200track_get_state_hybridsort"); return B200TRACK_ERR_STATE; }
     if (ctx->cfg.kind == B200TRACK_STRONGSORT) {
         const b200::SSParams& q = ctx->ss;
         int c4[4];
@@ -790,6 +810,22 @@ extern "C" int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, 
             CU_TRY(cudaMemcpy(h_feat + (size_t)k * F, q.feat + (s * T + order[k]) * F, F * sizeof(float), cudaMemcpyDeviceToHost));
         return 0;
     }
+    if (ctx->cfg.kind == B200TRACK_HYBRIDSORT) {
+        ON_DEVICE(ctx);
+        CU_TRY(cudaDeviceSynchronize());
+        const size_t T = ctx->tcap, s = stream_index, F = ctx->cfg.feat_dim;
+        int counts[4];
+        CU_TRY(cudaMemcpy(counts, ctx->p.counts + 4 * s, sizeof(counts), cudaMemcpyDeviceToHost));
+        std::vector<int> iv((size_t)ctx->ni * T);
+        CU_TRY(cudaMemcpy(iv.data(), ctx->p.state_i + s * ctx->ni * T, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        int k = 0;
+        for (int t = 0; t < counts[0] && t < ctx->cfg.max_tracks; ++t) {
+            if (!(iv[B200_OCI_FLAGS * T + t] & 8)) continue;
+            CU_TRY(cudaMemcpy(h_feat + (size_t)k * F, ctx->p.feat_pool + (s * T + iv[B200_HYI_FROW * T + t]) * F, F * sizeof(float), cudaMemcpyDeviceToHost));
+            ++k;
+        }
+        return 0;
+    }
     if (ctx->cfg.kind != B200TRACK_BOTSORT || !ctx->p.feat_pool) { set_error("context holds no embeddings"); return B200TRACK_ERR_STATE; }
     ON_DEVICE(ctx);
     CU_TRY(cudaDeviceSynchronize());
@@ -833,6 +869,56 @@ extern "C" int b200track_get_track_extras(b200track_ctx* ctx, int32_t stream_ind
             CU_TRY(cudaMemcpy(h_emb + (size_t)k * F, ctx->p.emb_pool + (s * T + iv[B200_DOI_EROW * T + t]) * F, F * sizeof(double), cudaMemcpyDeviceToHost));
         ++k;
     }
+    return 0;
+}
+
+extern "C" int b200track_get_state_hybridsort(b200track_ctx* ctx, int32_t stream_index, int32_t* h_counts, int32_t* h_rec, double* h_x,
+                                              double* h_P, double* h_vel, double* h_last, double* h_aux) {
+    if (!ctx || !h_counts) { set_error("NULL argument"); return B200TRACK_ERR_ARG; }
+    if (ctx->cfg.kind != B200TRACK_HYBRIDSORT) { set_error("not a HybridSORT context"); return B200TRACK_ERR_STATE; }
+    if (stream_index < 0 || stream_index >= ctx->cfg.n_streams) { set_error("stream_index out of range"); return B200TRACK_ERR_ARG; }
+    ON_DEVICE(ctx);
+    CU_TRY(cudaDeviceSynchronize());
+    const size_t T = ctx->tcap, s = stream_index;
+    std::vector<double> f((size_t)ctx->nf * T);
+    std::vector<int> iv((size_t)ctx->ni * T);
+    CU_TRY(cudaMemcpy(h_counts, ctx->p.counts + 4 * s, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(f.data(), ctx->p.state_f + s * ctx->nf * T, f.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    CU_TRY(cudaMemcpy(iv.data(), ctx->p.state_i + s * ctx->ni * T, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    int k = 0;
+    for (int t = 0; t < h_counts[0] && t < ctx->cfg.max_tracks; ++t) {
+        const int fl = iv[B200_OCI_FLAGS * T + t];
+        if (!(fl & 8)) continue;
+        const bool has = fl & B200_OCF_HASOBS;
+        if (h_rec) {
+            int32_t* r = h_rec + 6 * k;
+            r[0] = iv[B200_OCI_ID * T + t]; r[1] = iv[B200_OCI_AGE * T + t]; r[2] = iv[B200_OCI_TSU * T + t];
+            r[3] = iv[B200_OCI_HITS * T + t]; r[4] = iv[B200_OCI_STREAK * T + t]; r[5] = fl & B200_OCF_OBSERVED;
+        }
+        if (h_x) for (int c = 0; c < 9; ++c) h_x[9 * k + c] = f[(B200_HY_X + c) * T + t];
+        if (h_P) {
+            double* c = h_P + 81 * k;
+            for (int q = 0; q < 81; ++q) c[q] = 0.0;
+            for (int a = 0; a < 4; ++a) {
+                c[a * 9 + a] = f[(B200_HY_P + 3 * a + 0) * T + t];
+                c[a * 9 + a + 5] = c[(a + 5) * 9 + a] = f[(B200_HY_P + 3 * a + 1) * T + t];
+                c[(a + 5) * 9 + a + 5] = f[(B200_HY_P + 3 * a + 2) * T + t];
+            }
+            c[4 * 9 + 4] = f[(B200_HY_P + 12) * T + t];
+        }
+        if (h_vel) for (int c = 0; c < 8; ++c) h_vel[8 * k + c] = f[(B200_HY_VEL + c) * T + t];
+        if (h_last) {
+            for (int c = 0; c < 4; ++c) h_last[5 * k + c] = has ? f[(B200_HY_LAST + c) * T + t] : -1.0;
+            h_last[5 * k + 4] = has ? f[B200_HY_CONF * T + t] : -1.0;
+        }
+        if (h_aux) {
+            h_aux[3 * k + 0] = f[B200_HY_CONF * T + t];
+            h_aux[3 * k + 1] = f[B200_HY_CLS * T + t];
+            h_aux[3 * k + 2] = (double)iv[B200_OCI_DET * T + t];
+        }
+        ++k;
+    }
+    h_counts[0] = k; h_counts[1] = 0;
     return 0;
 }
 

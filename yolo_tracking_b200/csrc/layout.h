@@ -123,3 +123,24 @@
 #define B200_DOI_EROW 10
 #define B200_DOF_FROZEN 16   // flag bit 4: KalmanBoxTracker.frozen
 #define B200_DO_SLOT_BYTES (B200_DO_HOT * 8 + B200_DO_NI * 4)
+
+// ---- HybridSORT slot (hybridsort_step.cu) ---------------------------------------------------------
+// Same arrangement as the OC-SORT slot; the 9-d filter [u, v, s, c, r, du, dv, ds, dc] keeps four (position, velocity)
+// 2x2 blocks and P_rr (kf_hybrid.cuh).  fp64 components:
+#define B200_HY_NF 75
+#define B200_HY_X 0          // x[9]
+#define B200_HY_P 9          // 4 x (pp, pv, vv) for (u,du) (v,dv) (s,ds) (c,dc), then P_rr                        (13)
+#define B200_HY_LAST 22      // last_observation box (valid when the has-observation flag is set)
+#define B200_HY_CONF 26
+#define B200_HY_CLS 27
+#define B200_HY_VEL 28       // velocity_lt, _rt, _lb, _rb as (dy, dx) sums of unit vectors, zeros while None       (8)
+#define B200_HY_RING 36      // observations of the last 3 ages: ring[age % 3][4]
+#define B200_HY_HOT 48       // components touched every frame
+#define B200_HY_SX 48        // frozen x (9)
+#define B200_HY_SP 57        // frozen P (13, same order as B200_HY_P)
+#define B200_HY_LASTZ 70     // last entry of the filter's observation history [x, y, s, score, r] (measurement or virtual box)
+// int32 components: the OC-SORT ones (B200_OCI_*) plus the row of the track in the stream's embedding pool
+// feat_pool[(s * Tmax + row) * feat_dim] (fp32: every embedding operation of the reference is float32, hybridsort.py:188-205)
+#define B200_HY_NI 11
+#define B200_HYI_FROW 10
+#define B200_HY_SLOT_BYTES (B200_HY_HOT * 8 + B200_HY_NI * 4)

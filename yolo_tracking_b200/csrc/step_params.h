@@ -21,11 +21,12 @@ struct StepParams {
     // OC-SORT (ocsort.yaml keys)
     double det_thresh, iou_thresh, inertia, img_w, img_h;
     int max_age, min_hits, delta_t, asso_func, use_byte;
-    double* scratch;          // [S, Tcap, Dcap] dense cost matrices (OC-SORT)
+    double* scratch;          // [S, Dcap, Tcap] dense cost / appearance matrices (DeepOCSORT with a dense similarity, HybridSORT)
     // BoT-SORT
     int with_reid;
     int fuse_first;           // fuse_first_associate (bot_sort.py:300-301)
     float* feat_pool;         // [S, Tcap, feat_dim] smoothed track embeddings, row-indexed (layout.h)
+    float* feat_curr;         // [S, max_dets, feat_dim] scratch: this frame's twice-normalised detection embeddings
     double* cls_hist;         // [S, Tcap, 9] class-vote tables, row-indexed
     // DeepOCSORT (deepocsort.yaml keys)
     double w_assoc_emb, alpha_fixed_emb, aw_param;
@@ -77,5 +78,7 @@ cudaError_t launch_ocsort_step(const StepParams& p, int variant, cudaStream_t st
 int step_variant_dmax(int variant);
 size_t deepocsort_step_smem(int variant);
 cudaError_t launch_deepocsort_step(const StepParams& p, int variant, cudaStream_t stream);
+size_t hybridsort_step_smem(int variant);
+cudaError_t launch_hybridsort_step(const StepParams& p, int variant, cudaStream_t stream);
 
 }  // namespace b200

@@ -48,4 +48,8 @@ def create_tracker(tracker_type, tracker_config, reid_weights=None, device=0, ha
         return DeepOCSort(reid_weights, device, half, per_class, det_thresh=cfg.det_thresh, max_age=cfg.max_age,
                           min_hits=cfg.min_hits, iou_threshold=cfg.iou_thresh, delta_t=cfg.delta_t, asso_func=cfg.asso_func,
                           inertia=cfg.inertia, **capacity)
-    raise ValueError(f"No such tracker: {tracker_type!r} (built: bytetrack, ocsort, botsort, strongsort, deepocsort)")
+    if tracker_type == "hybridsort":
+        from .trackers.hybridsort import HybridSORT
+        return HybridSORT(reid_weights, device, half, det_thresh=cfg.det_thresh, max_age=cfg.max_age, min_hits=cfg.min_hits,
+                          iou_threshold=cfg.iou_thresh, delta_t=cfg.delta_t, asso_func=cfg.asso_func, inertia=cfg.inertia, **capacity)
+    raise ValueError(f"No such tracker: {tracker_type!r} (built: bytetrack, ocsort, botsort, strongsort, deepocsort, hybridsort)")
