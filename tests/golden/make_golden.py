@@ -601,9 +601,17 @@ def gen_hybridsort():
         trk = HybridSORT(None, "cpu", False, **cfg)                 # resets KalmanBoxTracker.count (hybridsort.py:364)
         outs, ints, xs, Ps, vels, lasts, heavy = [], [], [], [], [], [], []
         for f in range(sc["n_frames"]):
+            d = dets[f, :nd[f]]
             if nd[f]:
-                rh.FakeReID.queue.append(embs[f, :nd[f]])            # features of every detection (hybridsort.py:394)
-            o = trk.update(dets[f, :nd[f]], img)                     # through PerClassDecorator (one class: one call)
+                # features of every detection of a call (hybridsort.py:394); the PerClassDecorator makes one call per class, in
+                # the iteration order of these very expressions (boxmot/utils/__init__.py:33-45)
+                by_cls = {class_id: np.array([i for i, det in enumerate(d) if det[5] == class_id]) for class_id in set(det[5] for det in d)}
+                relevant = set([t.cls for t in trk.trackers]).union(set(by_cls.keys()))
+                for class_id in relevant:
+                    idx = by_cls.get(int(class_id))
+                    if idx is not None and len(idx):
+                        rh.FakeReID.queue.append(embs[f, :nd[f]][idx])
+            o = trk.update(d, img)                                   # through PerClassDecorator
             outs.append(o)
             ii, x, P, vel, last = _hyb_snapshot(trk)
             ints.append(ii)

@@ -164,6 +164,10 @@ HYBRIDSORT_SCENARIOS = {
     # crowded, long occlusions, DIoU, a two-frame velocity window
     "hybridsort_diou": dict(stream=922, n_objects=40, n_frames=100, emb_dim=32, kw=dict(miss_prob=0.1, fp_rate=2.0, occlusion=True),
                             params=dict(asso_func="diou", delta_t=2, min_hits=2)),
+    # two classes (wide boxes are class 1): HybridSORT is the one tracker whose update runs under the PerClassDecorator with
+    # per_class = True (hybridsort.py:346, :372; boxmot/utils/__init__.py:22-61) - one full update per class and frame
+    "hybridsort_2cls": dict(stream=923, n_objects=14, n_frames=90, emb_dim=32, kw=dict(miss_prob=0.1, fp_rate=1.0, occlusion=True),
+                            two_classes=True, params=dict(max_age=10)),
 }
 
 
@@ -173,11 +177,16 @@ def hybridsort_inputs(sc, det_thresh, full=False):
     the Frobenius norm of that whole matrix; only the rows above det_thresh are used (:403).  `full`: the rows of all
     detections instead (what the device path is handed)."""
     dets, nd, embs = make_stream(4, sc["stream"], sc["n_objects"], sc["n_frames"], emb_dim=sc["emb_dim"], **sc["kw"])
+    if sc.get("two_classes"):
+        dets[:, :, 5] = (dets[:, :, 2] - dets[:, :, 0] > 60.0).astype(np.float64)
     feats = []
     for f in range(sc["n_frames"]):
         keep = dets[f, :nd[f], 4] > det_thresh
         raw = embs[f, :nd[f]].astype(np.float32)
-        rows = raw / np.linalg.norm(raw) if len(raw) else np.zeros((0, sc["emb_dim"]), dtype=np.float32)
+        rows = np.zeros((nd[f], sc["emb_dim"]), dtype=np.float32)
+        for c in np.unique(dets[f, :nd[f], 5]):               # the seam normalises the matrix of ONE get_features call: one class
+            m = dets[f, :nd[f], 5] == c
+            rows[m] = raw[m] / np.linalg.norm(raw[m])
         feats.append(rows if full else rows[keep])
     return dets, nd, embs, feats
 
