@@ -112,6 +112,16 @@ def hybridsort_scenario(name, full=False):
     return sc, cfg, dets, nd, feats, g
 
 
+def per_class_calls(dets, tracker_classes):
+    """The calls the reference's PerClassDecorator makes for one frame (boxmot/utils/__init__.py:33-52), as index arrays into
+    `dets` in call order: one per class that has detections or live trackers, in the iteration order of the same set / dict
+    expressions."""
+    by_cls = {class_id: np.array([i for i, det in enumerate(dets) if det[5] == class_id], dtype=np.int64)
+              for class_id in set(det[5] for det in dets)}
+    relevant = set([np.float64(c) for c in tracker_classes]).union(set(by_cls.keys()))
+    return [by_cls.get(int(class_id), np.zeros(0, dtype=np.int64)) for class_id in relevant]
+
+
 def check_hybridsort_frame(name, f, out, s, g, heavy):
     """One frame of a HybridSORT replay against the live reference's golden: output rows (the last column is the SCORE of
     the input row the reference indexes, hybridsort.py:396), track records, 9-d filter state, four corner velocities."""

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 IMG = (1080, 1920)
 
 
-@pytest.mark.parametrize("name", ["hybridsort_c4", "hybridsort_churn", "hybridsort_diou"])
+@pytest.mark.parametrize("name", ["hybridsort_c4", "hybridsort_churn", "hybridsort_diou", "hybridsort_2cls"])
 def test_hybridsort_dropin_replays_reference(name):
     from yolo_tracking_b200.trackers.hybridsort import HybridSORT
     sc, cfg, dets, nd, feats, g = hybridsort_scenario(name, full=True)
@@ -25,7 +25,8 @@ def test_hybridsort_dropin_replays_reference(name):
         check_hybridsort_frame(name, f, out, trk.state(), g, heavy)
     assert_close(trk.state()["smooth_feat"], g["final_emb"], rel=2e-6, abs_=2e-6, what="embeddings")
     st = trk.stats
-    assert st["oru"] > 10 and st["corrections"] > 20 and st["lap_frames"] > 50
+    assert st["oru"] > 10 and st["lap_frames"] > 50 and (name == "hybridsort_2cls" or st["corrections"] > 20)
+    assert name != "hybridsort_2cls" or trk.frame_count > 1.8 * sc["n_frames"]      # one update per class and frame
 
 
 def test_hybridsort_multi_stream_matches_oracle():

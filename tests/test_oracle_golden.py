@@ -286,6 +286,34 @@ def test_hybridsort_oracle_replays_reference(name):
     assert name != "hybridsort_c4" or trk.stats["ocr_frames"] >= 1
 
 
+def test_hybridsort_oracle_two_classes_through_the_per_class_wrapper():
+    """The live reference ran `hybridsort_2cls` through its PerClassDecorator (per_class = True, hybridsort.py:346): one full
+    update per class and frame.  The oracle restates the undecorated update; driven by the same calls it reproduces the rows
+    and the track records."""
+    from _util import check_hybridsort_frame, heavy_offsets, hybridsort_scenario, per_class_calls
+    from oracle.hybridsort import HybridSortOracle
+    name = "hybridsort_2cls"
+    sc, cfg, dets, nd, feats, g = hybridsort_scenario(name, full=True)
+    trk = HybridSortOracle(**cfg)
+    heavy = heavy_offsets(g)
+    calls = 0
+    for f in range(sc["n_frames"]):
+        d = dets[f, :nd[f]]
+        out = np.empty((0, 8))
+        if d.size:
+            for idx in per_class_calls(d, [t.cls for t in trk.trackers]):
+                keep = d[idx, 4] > cfg["det_thresh"]
+                o = trk.update(d[idx].reshape(-1, 6), feats[f][idx][keep])
+                calls += 1
+                if o.size:
+                    out = np.append(out, o.reshape(-1, 8), axis=0)
+        else:
+            out = trk.update(d, feats[f]).reshape(-1, 8)
+            calls += 1
+        check_hybridsort_frame(name, f, out, trk.snapshot(), g, heavy)
+    assert calls > 1.8 * sc["n_frames"] and len(set(t.cls for t in trk.trackers)) == 2
+
+
 def test_camera_warp_leaves_two_independent_4x4_blocks():
     """Structure the fused frame steps can rely on when they take a camera warp (DESIGN.md performance plan): on the live
     reference's moving-camera runs the covariance couples x with y (and w with h) but the (x, y, vx, vy) and (w, h, vw, vh)
