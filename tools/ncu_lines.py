@@ -1,6 +1,6 @@
 """Attribute the warp-stall samples of an ncu --set full capture to CUDA source lines.
 ncu's CSV source page is SASS-only, so the line table comes from `nvdisasm -g` of the same cubin and is joined by
-instruction order.  usage: python tools/ncu_lines.py <rep> <cubin-name-substring> <mangled-kernel-substring> [top]"""
+instruction order.  usage: python tools/ncu_lines.py <rep | source.csv[.gz]> <cubin-name-substring> <mangled-kernel-substring> [top]"""
 import csv
 import io
 import os
@@ -32,7 +32,13 @@ for l in dis:
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,}\*/", l):
         lines.append((cur, l.strip()))
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+if rep.endswith(".csv.gz"):                       # the source page exported on the GPU box (tools/profile_round.sh)
+    import gzip
+    txt = gzip.open(rep, "rt").read()
+elif rep.endswith(".csv"):
+    txt = open(rep).read()
+else:
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 hdr = rows[1]
 ci = {n: i for i, n in enumerate(hdr)}

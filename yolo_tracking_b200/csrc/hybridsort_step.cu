@@ -59,7 +59,17 @@ struct alignas(16) HySmem {
     short hd[DMAX], ht[TMAX], drow[DMAX], dmatch[DMAX], tmatch[TMAX], ud[DMAX], ut[TMAX], frow[TMAX], freelist[TMAX];
     short nbrow[DMAX], nbdet[DMAX];
     unsigned char kvalid[TMAX], alive[TMAX], dstate[DMAX], rowused[TMAX], ema[TMAX];
+    // staging of the smoothed track embeddings for the dense cosine matrix: two tiles of eight fp32 rows (up to 512 values)
+    float4 etile[2][8][128];
 };
+
+__device__ __forceinline__ void hy_cp_async16(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void hy_cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
+template <int N>
+__device__ __forceinline__ void hy_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // the stored cost matrix behind the solver's functor interface
 struct HyMatCost {
@@ -103,6 +113,74 @@ __device__ __forceinline__ double hy_cosine(double uv, double nu, double nv) {
     double c = uv / (nu * nv);
     if (fabs(c) > 1.0) c = copysign(1.0, c);
     return fmax(0.0, 1.0 - c);
+}
+
+// Embedding dot products.  A detection row lives in registers as 16 doubles per lane (value 4 k + e of lane l is element
+// 4 (l + 32 k) + e of the row); a lane accumulates its share of a pair with a fixed chain of fused multiply-adds (the
+// product of two fp32 values is exact in fp64, so the chain only fixes the ORDER of the additions), and eight such
+// per-lane partials - eight pairs - are reduced TOGETHER: three exchange steps that halve the number of values a lane
+// still carries (bits 4, 3, 2 of the lane index pick the half it keeps) and two plain steps, 9 shuffles of a double
+// instead of 40; afterwards lane 4 q holds the sum of value q and eight lanes finalise their pairs in parallel.  Every
+// value is summed over the lanes in the same pairing order, so a pair's bits do not depend on its position in the
+// group: the correction pass recomputes single pairs with the same chain and the same tree.
+__device__ __forceinline__ double hy_chain(const double (&d)[16], const float4 (&v)[4]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        acc = fma(d[4 * k], (double)v[k].x, acc); acc = fma(d[4 * k + 1], (double)v[k].y, acc);
+        acc = fma(d[4 * k + 2], (double)v[k].z, acc); acc = fma(d[4 * k + 3], (double)v[k].w, acc);
+    }
+    return acc;
+}
+__device__ __forceinline__ double hy_reduce8(double (&p)[8], int lane) {
+    const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double recv = __shfl_xor_sync(0xffffffffu, h4 ? p[i] : p[i + 4], 16);
+        p[i] = (h4 ? p[i + 4] : p[i]) + recv;
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double recv = __shfl_xor_sync(0xffffffffu, h3 ? p[i] : p[i + 2], 8);
+        p[i] = (h3 ? p[i + 2] : p[i]) + recv;
+    }
+    {
+        const double recv = __shfl_xor_sync(0xffffffffu, h2 ? p[0] : p[1], 4);
+        p[0] = (h2 ? p[1] : p[0]) + recv;
+    }
+    p[0] += __shfl_xor_sync(0xffffffffu, p[0], 2);
+    p[0] += __shfl_xor_sync(0xffffffffu, p[0], 1);
+    return p[0];                                           // lanes 4 q + {0..3}: value q = 4 * bit4 + 2 * bit3 + bit2
+}
+// two detection rows x four smoothed rows resident in shared memory (zero padded to 128 float4): value q < 4 is
+// (row 0, column q), value 4 + q is (row 1, column q) - a loaded, converted element serves two pairs
+__device__ __forceinline__ double hy_dot2x4(const double (&d0)[16], const double (&d1)[16], const float4 (*tile)[128], int lane) {
+    double p[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = tile[q][lane + 32 * k];
+        p[q] = hy_chain(d0, v);
+        p[q + 4] = hy_chain(d1, v);
+    }
+    return hy_reduce8(p, lane);
+}
+// one pair, the smoothed row read from global memory: lane 0 holds the sum
+__device__ __forceinline__ double hy_dot1(const double (&d)[16], const float4* b, int nv, int lane) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = lane + 32 * k < nv ? b[lane + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+    double p[8] = {hy_chain(d, v), 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    return hy_reduce8(p, lane);
+}
+// the detection row in that register form
+__device__ __forceinline__ void hy_load_row16(double (&d)[16], const float4* a, int nv, int lane) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float4 v = lane + 32 * k < nv ? a[lane + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+        d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+    }
 }
 
 template <int NT, int TMAX, int DMAX>
@@ -272,39 +350,49 @@ hybridsort_step_kernel(const StepParams p) {
         __syncthreads();
         // embedding distances -> Cm: one warp per detection row, the row in registers as doubles (rows of up to 512 values)
         if (nv <= 128) {
-            for (int r = warp; r < R; r += NW) {
-                const int j = sm.hd[r];
-                const float4* a = reinterpret_cast<const float4*>(dfeat + (size_t)j * F);
-                double d[16];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float4 v = lane + 32 * k < nv ? a[lane + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    d[4 * k] = v.x; d[4 * k + 1] = v.y; d[4 * k + 2] = v.z; d[4 * k + 3] = v.w;
+            // Every warp holds TWO detection rows in registers; the smoothed rows of the trackers pass through shared memory
+            // in tiles of eight (cp.async, double buffered), so a tile fetched once from L2 serves all 2 NW detection rows of
+            // the round - read per pair from L2 instead, the 2 KB rows made the step L2-bandwidth bound (83 MB per stream
+            // and frame at config 4).
+            for (int i = tid; i < 2 * 8 * 128; i += NT) (&sm.etile[0][0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // padding stays zero
+            __syncthreads();
+            const int ntile = (Cn + 7) >> 3;
+            auto issue_tile = [&](int ti, int buf) {
+                const int c0 = ti * 8, ncols = min(8, Cn - c0);
+                for (int i = tid; i < ncols * 128; i += NT) {
+                    const int qq = i >> 7, e = i & 127;
+                    if (e < nv) hy_cp_async16(&sm.etile[buf][qq][e], reinterpret_cast<const float4*>(pool + (size_t)sm.frow[sm.ht[c0 + qq]] * F) + e);
                 }
-                const double nj = sm.dnorm[j];
-                for (int c0 = 0; c0 < Cn; c0 += 2) {                  // two columns in flight
-                    const int c1 = min(c0 + 1, Cn - 1);
-                    const int sl0 = sm.ht[c0], sl1 = sm.ht[c1];
-                    const float4* b0 = reinterpret_cast<const float4*>(pool + (size_t)sm.frow[sl0] * F);
-                    const float4* b1 = reinterpret_cast<const float4*>(pool + (size_t)sm.frow[sl1] * F);
-                    float4 v0[4], v1[4];
+                hy_cp_async_commit();
+            };
+            const int qi = lane >> 2;                                 // the value of a group this lane finalises
+            for (int r0 = 0; r0 < R; r0 += 2 * NW) {
+                const int rA = r0 + 2 * warp, rB = rA + 1;
+                const bool actA = rA < R, actB = rB < R;              // warp-uniform; idle warps still copy and synchronise
+                const int jA = actA ? sm.hd[rA] : 0, jB = actB ? sm.hd[rB] : jA;
+                double d0[16], d1[16];
+                hy_load_row16(d0, reinterpret_cast<const float4*>(dfeat + (size_t)jA * F), nv, lane);
+                hy_load_row16(d1, reinterpret_cast<const float4*>(dfeat + (size_t)jB * F), nv, lane);
+                const int myr = (qi & 4) ? rB : rA;
+                const bool myact = (lane & 3) == 0 && ((qi & 4) ? actB : actA);
+                const double nj = sm.dnorm[(qi & 4) ? jB : jA];
+                issue_tile(0, 0);
+                for (int ti = 0; ti < ntile; ++ti) {
+                    const int buf = ti & 1;
+                    if (ti + 1 < ntile) { issue_tile(ti + 1, buf ^ 1); hy_cp_async_wait<1>(); } else hy_cp_async_wait<0>();
+                    __syncthreads();
+                    if (actA) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const bool in = lane + 32 * k < nv;
-                        v0[k] = in ? b0[lane + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        v1[k] = in ? b1[lane + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int g = 0; g < 2; ++g) {
+                            const int c0 = ti * 8 + 4 * g;
+                            if (c0 < Cn) {                            // uniform
+                                const double uv = hy_dot2x4(d0, d1, &sm.etile[buf][4 * g], lane);
+                                const int c = c0 + (qi & 3);
+                                if (myact && c < Cn) Cm[(size_t)myr * TMAX + c] = hy_cosine(uv, sm.tnorm[sm.ht[c]], nj);
+                            }
+                        }
                     }
-                    double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        a0 += d[4 * k] * v0[k].x + d[4 * k + 1] * v0[k].y + d[4 * k + 2] * v0[k].z + d[4 * k + 3] * v0[k].w;
-                        a1 += d[4 * k] * v1[k].x + d[4 * k + 1] * v1[k].y + d[4 * k + 2] * v1[k].z + d[4 * k + 3] * v1[k].w;
-                    }
-                    a0 = hy_warp_sum(a0); a1 = hy_warp_sum(a1);
-                    if (lane == 0) {
-                        Cm[(size_t)r * TMAX + c0] = hy_cosine(a0, sm.tnorm[sl0], nj);
-                        if (c1 != c0) Cm[(size_t)r * TMAX + c1] = hy_cosine(a1, sm.tnorm[sl1], nj);
-                    }
+                    __syncthreads();                                  // the next iteration's prefetch overwrites this tile's twin
                 }
             }
         } else {
@@ -372,12 +460,17 @@ hybridsort_step_kernel(const StepParams p) {
             dense_lap_init<NT>(w, R, Cn, lambda);
             dense_lap_augment<NT>(w, cost, R, Cn, lambda);
         }
-        // embedding distance of every assigned pair again (the matrix now holds costs), one warp per row
+        // embedding distance of every assigned pair again (the matrix now holds costs), one warp per row, same routine
         for (int r = warp; r < R; r += NW) {
             const int c = sm.xr[r];
             if (c < 0) continue;
             const int j = sm.hd[r], sl = sm.ht[c];
-            const double uv = emb_dot(j, sl);
+            double uv;
+            if (nv <= 128) {
+                double d[16];
+                hy_load_row16(d, reinterpret_cast<const float4*>(dfeat + (size_t)j * F), nv, lane);
+                uv = hy_dot1(d, reinterpret_cast<const float4*>(pool + (size_t)sm.frow[sl] * F), nv, lane);
+            } else uv = emb_dot(j, sl);
             if (lane == 0) sm.remb[r] = hy_cosine(uv, sm.tnorm[sl], sm.dnorm[j]);
         }
         __syncthreads();
