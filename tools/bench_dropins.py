@@ -1,5 +1,5 @@
 """Single-stream latency of the reference-shaped drop-ins on one B200: `tracker.update(dets, img)` p50 / p99 per frame for
-BYTETracker, OCSort, BoTSORT at BASELINE config 1 (1 stream, ~50 detections per frame) and for DeepOCSORT / StrongSORT at
+BYTETracker, OCSort, BoTSORT at BASELINE config 1 (1 stream, ~50 detections per frame) and for DeepOCSORT / StrongSORT / HybridSORT at
 100 objects with 512-d embeddings, next to the oracle port of the reference on one host core (same synthetic stream, seam
 features passed in, identity camera).  One call = pack -> one H2D copy -> one fused step -> one D2H copy -> rebuild the
 reference's [M, 8] rows (StrongSORT: the eight-launch batched step on one stream).  This is a latency figure; the multi-stream
@@ -39,6 +39,7 @@ def main():
     from oracle.botsort import BoTSORTOracle
     from oracle.bytetrack import ByteTrackOracle
     from oracle.deepocsort import DeepOCSortOracle
+    from oracle.hybridsort import HybridSortOracle
     from oracle.ocsort import OCSortOracle
     from oracle.strongsort import StrongSORTOracle
     F = args.frames
@@ -55,10 +56,11 @@ def main():
         ("botsort", 53, args.dim, lambda: pkg.BoTSORT(None, 0, False, feat_dim=args.dim, **bs), lambda: BoTSORTOracle(**bs)),
         ("deepocsort", 100, args.dim, lambda: pkg.DeepOCSORT(None, 0, False, False, **do), lambda: DeepOCSortOracle(**do)),
         ("strongsort", 100, args.dim, lambda: pkg.StrongSORT(None, 0, False, **ss), lambda: StrongSORTOracle(**ss)),
+        ("hybridsort", 100, args.dim, lambda: pkg.HybridSORT(None, 0, False, **do), lambda: HybridSortOracle(**do)),
     ]
     for name, objects, dim, mk, mk_orc in cases:
         frames = F if name != "strongsort" else min(F, 120)
-        dets, nd, embs = make_stream(1 if objects <= 64 else 4, 1, objects, frames, emb_dim=dim, occlusion=(name in ("ocsort", "deepocsort")))
+        dets, nd, embs = make_stream(1 if objects <= 64 else 4, 1, objects, frames, emb_dim=dim, occlusion=(name in ("ocsort", "deepocsort", "hybridsort")))
         dets = dets.astype(np.float32).astype(np.float64)
 
         def seam(f, kind):
@@ -87,6 +89,8 @@ def main():
                 return lambda f: orc.update(dets[f, :nd[f]], (1080, 1920))
             if name == "deepocsort":
                 return lambda f: orc.update(dets[f, :nd[f]], feats[f], (1080, 1920))
+            if name == "hybridsort":
+                return lambda f: orc.update(dets[f, :nd[f]], feats[f][dets[f, :nd[f], 4] > 0], (1080, 1920))
             return lambda f: orc.update(dets[f, :nd[f]], feats[f])
         trk = mk()
         sampler = ClockSampler(0)
@@ -97,7 +101,9 @@ def main():
         line = {"tracker": name, "objects": objects, "dets_per_frame": float(nd.mean()), "frames": frames, "emb_dim": dim,
                 "update_ms_p50": p50, "update_ms_p99": p99, "update_ms_mean": mean, "frames_per_s": 1e3 / mean,
                 "path": "one-stream context of the batched StrongSORT step (eight launches per frame, device buffers via torch)" if name == "strongsort" else
-                        "one-stream context of the fused frame step through the packed host interface",
+                        ("one-stream context of the fused frame step through the padded host interface (plus one state read per frame: "
+                         "the per-class wrapper needs the classes of the live trackers)" if name == "hybridsort" else
+                         "one-stream context of the fused frame step through the packed host interface"),
                 "clocks": sampler.summary()}
         if not args.no_cpu:
             c50, c99, cmean = run(cpu_step(mk_orc()), frames)

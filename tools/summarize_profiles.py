@@ -38,7 +38,11 @@ def short(name):
     return name[:110]
 
 
-for wl in ("bytetrack", "ocsort", "botsort", "deepocsort", "strongsort", "ops"):
+try:                                                  # optional per-workload remarks: profiles/rNN_notes.json {workload: text}
+    NOTES = json.load(open(os.path.join(P, f"{R}_notes.json")))
+except Exception:
+    NOTES = {}
+for wl in ("bytetrack", "ocsort", "botsort", "deepocsort", "strongsort", "hybridsort", "ops"):
     src = os.path.join(G, f"{R}_launches_{wl}.csv")
     if not os.path.exists(src):
         continue
@@ -58,6 +62,8 @@ for wl in ("bytetrack", "ocsort", "botsort", "deepocsort", "strongsort", "ops"):
         a[1] += v_us
     tot = sum(a[1] for a in agg.values()) or 1.0
     md.append(f"\n## Launch list: {wl} (`profiles/{R}_launches_{wl}.csv`)\n")
+    if wl in NOTES:
+        md.append(f"> NOTE: {NOTES[wl]}\n")
     md.append("| kernel | launches | mean us | share of GPU time |\n|---|---|---|---|")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:12]:
         md.append(f"| `{short(k)}` | {n} | {t / n:.1f} | {100 * t / tot:.2f} % |")
@@ -67,7 +73,7 @@ try:
     traffic = json.load(open(os.path.join(P, "traffic.json")))
 except Exception:
     pass
-for cap in ("bytetrack", "ocsort", "botsort", "deepocsort", "strongsort", "appearance", "gallery", "kf"):
+for cap in ("bytetrack", "ocsort", "botsort", "deepocsort", "strongsort", "hybridsort", "appearance", "gallery", "kf"):
     rep = os.path.join(G, f"{R}_full_{cap}.ncu-rep")
     raw = os.path.join(G, f"{R}_full_{cap}.raw.csv")          # exported on the GPU box by tools/profile_round.sh
     if os.path.exists(raw):
@@ -80,7 +86,8 @@ for cap in ("bytetrack", "ocsort", "botsort", "deepocsort", "strongsort", "appea
     if len(rows) < 3:
         continue
     hdr, units = rows[0], rows[1]
-    md.append(f"\n## `--set full` capture: {cap} (`gpurun_out/{R}_full_{cap}.ncu-rep`, not tracked)\n")
+    md.append(f"\n## `--set full` capture: {cap} (`gpurun_out/{R}_full_{cap}.ncu-rep`, not tracked; the raw-metric page is exported on the "
+              f"GPU box, per-line source pages of the ByteTrack / OC-SORT / HybridSORT captures in `profiles/{R}_full_*.source.csv.gz`)\n")
     last = {}
     for row in rows[2:]:                                  # one entry per kernel: the last captured launch (after the warm-ups)
         last[dict(zip(hdr, row)).get('Kernel Name', '?')] = row
@@ -99,7 +106,9 @@ for cap in ("bytetrack", "ocsort", "botsort", "deepocsort", "strongsort", "appea
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             tot_b = rd * scale.get(u["dram__bytes_read.sum"], 1) + wr * scale.get(u["dram__bytes_write.sum"], 1)
             key = {"bytetrack": "bytetrack_step_kernel", "ocsort": "ocsort_step_kernel", "botsort": "bytetrack_step_kernel<BOT>",
-                   "deepocsort": "deepocsort_step_kernel"}.get(cap)
+                   "deepocsort": "deepocsort_step_kernel", "hybridsort": "hybridsort_step_kernel"}.get(cap)
+            if cap in NOTES and "experiment" in NOTES[cap]:
+                key = None                               # a capture of a variant that is not the kernel in the tree
             if key:
                 traffic[key] = {"streams": int(d.get("Grid Size", "0").replace(",", "").split()[0].strip("()")) if d.get("Grid Size") else 0,
                                 "dram_bytes_per_launch": int(tot_b),
