@@ -634,7 +634,7 @@ def gen_hybridsort():
 def gen_fullsize():
     """Rows-only goldens at the BASELINE config sizes (scenarios.FULLSIZE)."""
     rh.install()
-    from scenarios import (BOTSORT_YAML, DEEPOCSORT_YAML, FULLSIZE, STRONGSORT_YAML, fullsize_inputs)
+    from scenarios import (BOTSORT_YAML, DEEPOCSORT_YAML, FULLSIZE, HYBRIDSORT_YAML, STRONGSORT_YAML, fullsize_inputs)
     img = np.zeros((2160, 3840, 3), dtype=np.uint8)
     only = os.environ.get("GOLDEN_ONLY")
     for name, sc in FULLSIZE.items():
@@ -656,11 +656,14 @@ def gen_fullsize():
             from boxmot.trackers.deepocsort.deep_ocsort import DeepOCSort
             trk = DeepOCSort(None, "cpu", False, False, **DEEPOCSORT_YAML)
             trk.cmc = rh.IdentityCMC()
+        elif kind == "hybridsort":
+            from boxmot.trackers.hybridsort.hybridsort import HybridSORT
+            trk = HybridSORT(None, "cpu", False, **HYBRIDSORT_YAML)
         else:
             from boxmot.trackers.strongsort.strong_sort import StrongSORT
             trk = StrongSORT(None, "cpu", False, **STRONGSORT_YAML)
             trk.cmc = rh.IdentityCMC()
-        ids, dis, offs, boxes, box_frames = [], [], [0], [], []
+        ids, dis, offs, boxes, box_frames, lasts = [], [], [0], [], [], []
         for f in range(sc["n_frames"]):
             d = dets[f, :nd[f]]
             if kind == "botsort":
@@ -671,10 +674,11 @@ def gen_fullsize():
                 keep = d[:, 4] > DEEPOCSORT_YAML["det_thresh"]
                 if keep.any():
                     rh.FakeReID.queue.append(embs[f, :nd[f]][keep])
-            elif kind == "strongsort" and nd[f]:
-                rh.FakeReID.queue.append(embs[f, :nd[f]])
+            elif kind in ("strongsort", "hybridsort") and nd[f]:
+                rh.FakeReID.queue.append(embs[f, :nd[f]])              # one class: one get_features call on every box
             o = np.asarray(trk.update(d, None if kind == "bytetrack" else img), dtype=np.float64).reshape(-1, 8)
             ids.append(o[:, 4].astype(np.int32))
+            lasts.append(o[:, 7].copy())
             dis.append(o[:, 7].astype(np.int32))
             offs.append(offs[-1] + len(o))
             if f % sc["box_every"] == sc["box_every"] - 1 or f == sc["n_frames"] - 1:
@@ -683,10 +687,40 @@ def gen_fullsize():
         assert not rh.FakeReID.queue
         _save(name, ndets=nd, dets_sum=np.array([dets.sum(), 0.0 if embs is None else float(np.abs(embs.astype(np.float64)).sum())]),
               ids=np.concatenate(ids), det_ind=np.concatenate(dis).astype(np.int16), offs=np.array(offs, dtype=np.int64),
-              boxes=np.concatenate(boxes), box_frames=np.array(box_frames, dtype=np.int32))
+              boxes=np.concatenate(boxes), box_frames=np.array(box_frames, dtype=np.int32),
+              **({"last_col": np.concatenate(lasts)} if kind == "hybridsort" else {}))      # HybridSORT's last column is a score
 
 
-GENERATORS = {"fullsize": gen_fullsize, "hybridsort": gen_hybridsort, "deepocsort": gen_deepocsort, "mot_deepocsort": gen_mot_deepocsort, "mot_strongsort": gen_mot_strongsort, "mot_botsort": gen_mot_botsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
+def gen_mot_hybridsort():
+    """The three MOT17-mini detection streams through the reference's HybridSORT (hybridsort.yaml as the factory forwards it)
+    with seeded stand-in embeddings for every detection: integer MOT rows per sequence."""
+    rh.install()
+    from scenarios import HYBRIDSORT_YAML, mot_feats
+    from yolo_tracking_b200 import mot_io
+    from yolo_tracking_b200.replay import dense_frames
+    from boxmot.trackers.hybridsort.hybridsort import HybridSORT
+    g = np.load(os.path.join(HERE, "mot17_mini.npz"))
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    out = {}
+    for si, name in enumerate(MOT_SEQS):
+        frames, dets = mot_io.split_det_rows(g[name + "_det"])
+        seq = dense_frames(frames, dets, int(g[name + "_len"]))
+        trk = HybridSORT(None, "cpu", False, **HYBRIDSORT_YAML)
+        rows = []
+        for f, d in enumerate(seq):
+            assert len(set(d[:, 5])) <= 1                           # one class: the per-class wrapper makes one call
+            if len(d):
+                rh.FakeReID.queue.append(mot_feats(si, f, len(d)))
+            o = trk.update(d, img)
+            if o.size:
+                rows.append(mot_io.mot_rows(o, f))
+        assert not rh.FakeReID.queue
+        out[name] = mot_io.as_int_rows(np.concatenate(rows, axis=0))
+        print(name, "hybridsort", len(out[name]), "rows")
+    _save("mot17_mini_hybridsort", **out)
+
+
+GENERATORS = {"fullsize": gen_fullsize, "hybridsort": gen_hybridsort, "mot_hybridsort": gen_mot_hybridsort, "deepocsort": gen_deepocsort, "mot_deepocsort": gen_mot_deepocsort, "mot_strongsort": gen_mot_strongsort, "mot_botsort": gen_mot_botsort, "kf": gen_kf, "costs": gen_costs, "bytetrack": gen_bytetrack, "ocsort": gen_ocsort, "botsort": gen_botsort,
               "mot": gen_mot, "strongsort": gen_strongsort, "aux": gen_aux}
 
 if __name__ == "__main__":

@@ -210,6 +210,7 @@ FULLSIZE = {
     # config 4: 200 tracks x 200 detections with 512-d embeddings through DeepOCSORT and StrongSORT
     "full_deepocsort_c4": dict(kind="deepocsort", config=4, stream=3, n_objects=190, n_frames=100, emb_dim=512, kw={}, box_every=5),
     "full_strongsort_c4": dict(kind="strongsort", config=4, stream=3, n_objects=200, n_frames=60, emb_dim=512, kw={}, box_every=5),
+    "full_hybridsort_c4": dict(kind="hybridsort", config=4, stream=3, n_objects=190, n_frames=100, emb_dim=512, kw={}, box_every=5),
 }
 
 

@@ -118,6 +118,39 @@ def test_deepocsort_cuda_replay_matches_reference_files():
     _deepocsort_replay(lambda **kw: pkg.DeepOCSORT(None, 0, False, False, **kw), lambda t, d, f: t.update(d, (1080, 1920), feats=f))
 
 
+def _hybridsort_replay(make, update):
+    import sys
+    from _util import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    from scenarios import HYBRIDSORT_YAML, mot_feats
+    g, ref = load_golden("mot17_mini"), load_golden("mot17_mini_hybridsort")
+    for si, (name, seq) in enumerate(zip(SEQS, _sequences(g))):
+        trk = make(**HYBRIDSORT_YAML)
+        rows = []
+        for f, d in enumerate(seq):
+            raw = mot_feats(si, f, len(d))
+            feats = raw / np.linalg.norm(raw) if len(raw) else raw
+            o = update(trk, d, feats)
+            if o.size:
+                rows.append(mot_io.mot_rows(o, f))
+        assert np.array_equal(mot_io.as_int_rows(np.concatenate(rows)), ref[name]), name
+
+
+def test_hybridsort_oracle_replay_matches_reference_files():
+    """Real MOT17 public detections (duplicate boxes, confidences down to 0.05) with seeded stand-in embeddings through the
+    HybridSORT oracle: the result rows equal the live reference's (tests/golden/mot17_mini_hybridsort.npz)."""
+    from oracle.hybridsort import HybridSortOracle
+    _hybridsort_replay(lambda **kw: HybridSortOracle(**kw), lambda t, d, f: t.update(d, f[d[:, 4] > 0], (1080, 1920)))
+
+
+@pytest.mark.gpu
+def test_hybridsort_cuda_replay_matches_reference_files():
+    """GPU twin: the same streams through the fused CUDA HybridSORT step (the drop-in is a one-stream context of it)."""
+    import yolo_tracking_b200 as pkg
+    _hybridsort_replay(lambda **kw: pkg.HybridSORT(None, 0, False, **kw), lambda t, d, f: t.update(d, (1080, 1920), feats=f))
+
+
 @pytest.mark.gpu
 def test_deepocsort_cuda_replay_batched_streams():
     """The three sequences as three streams of ONE batched DeepOCSORT context (ragged frame counts: a finished sequence

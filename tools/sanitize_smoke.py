@@ -11,6 +11,7 @@ from yolo_tracking_b200.batch import BatchedTracker  # noqa: E402
 from yolo_tracking_b200.synth import make_batch  # noqa: E402
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 12
+ONLY = sys.argv[2].split(",") if len(sys.argv) > 2 else None          # tracker kinds to run (then the operators are skipped)
 for kind, cap, kw, params in (
         ("bytetrack", 64, dict(miss_prob=0.2, fp_rate=3.0), dict(track_thresh=0.5, match_thresh=0.8, track_buffer=5, frame_rate=30)),
         ("bytetrack", 224, {}, dict(track_thresh=0.5, match_thresh=0.8, track_buffer=30, frame_rate=30)),
@@ -18,10 +19,16 @@ for kind, cap, kw, params in (
                                                                   asso_func="giou", inertia=0.2, use_byte=True)),
         ("botsort", 128, dict(miss_prob=0.2, fp_rate=2.0, emb_dim=128), dict(track_high_thresh=0.5, track_low_thresh=0.1, new_track_thresh=0.6,
                                                                             track_buffer=5, match_thresh=0.8, proximity_thresh=0.5,
-                                                                            appearance_thresh=0.25, frame_rate=30))):
+                                                                            appearance_thresh=0.25, frame_rate=30)),
+        ("hybridsort", 64, dict(occlusion=True, miss_prob=0.2, fp_rate=2.0, emb_dim=36), dict(det_thresh=0.3, max_age=5, min_hits=1, iou_threshold=0.3,
+                                                                                             delta_t=3, asso_func="giou", inertia=0.2)),
+        ("hybridsort", 128, dict(occlusion=True, emb_dim=512), dict(det_thresh=0.0, max_age=30, min_hits=1, iou_threshold=0.3, delta_t=3,
+                                                                    asso_func="diou", inertia=0.2))):
+    if ONLY and kind not in ONLY:
+        continue
     n_obj = 150 if cap == 224 else 30
     dets, nd, embs = make_batch(7, 3, n_obj, F, dmax=cap, **kw)
-    trk = BatchedTracker(kind, 3, max_tracks=cap, max_dets=cap, feat_dim=128 if kind == "botsort" else 0, **params)
+    trk = BatchedTracker(kind, 3, max_tracks=cap, max_dets=cap, feat_dim=embs.shape[-1] if embs is not None else 0, **params)
     rows = 0
     for f in range(F):
         feats = None
@@ -33,6 +40,8 @@ for kind, cap, kw, params in (
     trk.sync()
     trk.close()
     print(kind, cap, "rows", rows, flush=True)
+if ONLY:
+    sys.exit(0)
 rng = np.random.default_rng(0)
 z = np.stack([rng.uniform(100, 900, 50), rng.uniform(100, 900, 50), rng.uniform(0.3, 0.8, 50), rng.uniform(60, 220, 50)], axis=1)
 for kind in (_lib.KF_XYAH, _lib.KF_XYWH, _lib.KF_XYAH_CONF):
