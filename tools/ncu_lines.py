@@ -16,7 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = os.path.join(ROOT, "yolo_tracking_b200", "lib", "libb200track.so")
 tmp = tempfile.mkdtemp()
 subprocess.run(["cuobjdump", "-xelf", "all", so], cwd=tmp, capture_output=True)
-cubin = [f for f in os.listdir(tmp) if cubin_sub in f and f.count("-") == 0][0]
+cands = sorted(f for f in os.listdir(tmp) if cubin_sub in f and f.count("-") == 0)
+cubin = ([f for f in cands if f.startswith(cubin_sub)] or cands)[0]          # "ocsort_step" must not pick deepocsort_step
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout.splitlines()
 # instruction index -> (file, line) for the wanted function
 lines, cur, infn = [], ("?", 0), False

@@ -357,6 +357,15 @@ class BatchedTracker:
         _lib.check(self._lib.b200track_footprint(self._ctx, C.byref(a), C.byref(b)))
         return dict(state_bytes_per_stream=a.value, smem_bytes=b.value)
 
+    def live_classes(self, stream: int = 0):
+        """HybridSORT contexts: the classes of the live trackers of one stream in list order (what the reference's
+        PerClassDecorator reads before every frame) - one small state read, no embeddings."""
+        T = self.max_tracks
+        counts = np.zeros(4, dtype=np.int32)
+        aux = np.zeros((T, 3))
+        _lib.check(self._lib.b200track_get_state_hybridsort(self._ctx, int(stream), _ptr(counts), None, None, None, None, None, _ptr(aux)))
+        return aux[:int(counts[0]), 1].copy()
+
     def state(self, stream: int = 0):
         """Track records of one stream in list order, in the reference's dense form."""
         T = self.max_tracks

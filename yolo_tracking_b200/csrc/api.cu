@@ -817,11 +817,13 @@ extern "C" int b200track_get_features(b200track_ctx* ctx, int32_t stream_index, 
         int counts[4];
         CU_TRY(cudaMemcpy(counts, ctx->p.counts + 4 * s, sizeof(counts), cudaMemcpyDeviceToHost));
         std::vector<int> iv((size_t)ctx->ni * T);
+        std::vector<float> pool(T * F);                              // the stream's whole pool in one copy, rows picked on the host
         CU_TRY(cudaMemcpy(iv.data(), ctx->p.state_i + s * ctx->ni * T, iv.size() * sizeof(int), cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(pool.data(), ctx->p.feat_pool + s * T * F, pool.size() * sizeof(float), cudaMemcpyDeviceToHost));
         int k = 0;
         for (int t = 0; t < counts[0] && t < ctx->cfg.max_tracks; ++t) {
             if (!(iv[B200_OCI_FLAGS * T + t] & 8)) continue;
-            CU_TRY(cudaMemcpy(h_feat + (size_t)k * F, ctx->p.feat_pool + (s * T + iv[B200_HYI_FROW * T + t]) * F, F * sizeof(float), cudaMemcpyDeviceToHost));
+            memcpy(h_feat + (size_t)k * F, pool.data() + (size_t)iv[B200_HYI_FROW * T + t] * F, F * sizeof(float));
             ++k;
         }
         return 0;

@@ -76,6 +76,7 @@ __device__ void dense_lap_augment(const DenseLap& w, const CostFn& cost, int R, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j = tid;
     const bool mine = j < Cn;
+    const int nwa = (Cn + 31) >> 5;                         // warps that own columns: only they reduce, only their minima are read
     int par = 0;
     // the rows the row reduction left free, ascending (warp 0 compacts them; usually none or one)
     int nfree = 0;
@@ -114,19 +115,20 @@ __device__ void dense_lap_augment(const DenseLap& w, const CostFn& cost, int R, 
                 }
                 cand = dist; cj = j;
             }
+            if (warp < nwa) {                               // warps without columns have nothing to offer
 #pragma unroll
-            for (int d = 16; d; d >>= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, cand, d);
-                const int oj = __shfl_xor_sync(0xffffffffu, cj, d);
-                if (ob < cand || (ob == cand && oj >= 0 && (cj < 0 || oj < cj))) { cand = ob; cj = oj; }
+                for (int d = 16; d; d >>= 1) {
+                    const double ob = __shfl_xor_sync(0xffffffffu, cand, d);
+                    const int oj = __shfl_xor_sync(0xffffffffu, cj, d);
+                    if (ob < cand || (ob == cand && oj >= 0 && (cj < 0 || oj < cj))) { cand = ob; cj = oj; }
+                }
+                if (lane == 0) { w.red_v[par * 32 + warp] = cand; w.red_i[par * 32 + warp] = cj; }
             }
-            if (lane == 0) { w.red_v[par * 32 + warp] = cand; w.red_i[par * 32 + warp] = cj; }
             if (w.dbg && tid == 0) atomicAdd(&w.dbg[10], 1ull);
             __syncthreads();
             double b = w.red_v[par * 32];
             int bj = w.red_i[par * 32];
-#pragma unroll
-            for (int k = 1; k < NW; ++k) {
+            for (int k = 1; k < nwa; ++k) {
                 const double ob = w.red_v[par * 32 + k];
                 const int oj = w.red_i[par * 32 + k];
                 if (ob < b || (ob == b && oj >= 0 && (bj < 0 || oj < bj))) { b = ob; bj = oj; }

@@ -342,14 +342,17 @@ ocsort_step_kernel(const StepParams p) {
                 int total = 0;
 #pragma unroll
                 for (int k = 0; k < NCH; ++k) {
-                    const int c = k * 32 + lane;
-                    bool cand = false;
-                    if (k * 32 < Cn && c < Cn) {
-                        const float4 tf = sm.cboxf[c];
-                        cand = (tf.x < dx2) & (dx1 < tf.z) & (tf.y < dy2) & (dy1 < tf.w);
+                    bits[k] = 0u;
+                    if (k * 32 < Cn) {                        // uniform: chunks past the live columns cost nothing
+                        const int c = k * 32 + lane;
+                        bool cand = false;
+                        if (c < Cn) {
+                            const float4 tf = sm.cboxf[c];
+                            cand = (tf.x < dx2) & (dx1 < tf.z) & (tf.y < dy2) & (dy1 < tf.w);
+                        }
+                        bits[k] = __ballot_sync(0xffffffffu, cand);
+                        total += __popc(bits[k]);
                     }
-                    bits[k] = __ballot_sync(0xffffffffu, cand);
-                    total += __popc(bits[k]);
                 }
                 int base = 0;
                 if (lane == 0 && total) base = atomicAdd(&sm.misc[0], total);

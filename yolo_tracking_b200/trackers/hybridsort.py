@@ -94,7 +94,7 @@ class HybridSORT:
             idx_of = {class_id: np.array([i for i, det in enumerate(dets) if det[5] == class_id], dtype=np.int64)
                       for class_id in set(det[5] for det in dets)}
             detected_classes = set(idx_of.keys())
-            active_classes = set(np.float64(c) for c in self.state()["cls"])
+            active_classes = set(np.float64(c) for c in (self._batch.live_classes(0) if self._batch is not None else ()))
             relevant_classes = active_classes.union(detected_classes)
             mc_dets = np.empty(shape=(0, 8))
             for class_id in relevant_classes:
