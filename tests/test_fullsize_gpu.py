@@ -178,3 +178,54 @@ def test_config3_botsort_shape_determinism_and_sampled_oracle():
             assert ref.shape == (k, 8), f"frame {f} stream {i}"
             assert np.array_equal(a[f][0][i, :k, 4:], ref[:, 4:]), f"frame {f} stream {i}: ids"
             assert_close(a[f][0][i, :k, :4], ref[:, :4], what=f"frame {f} stream {i} boxes")
+
+
+def test_config4_hybridsort_shape_determinism_and_sampled_oracle():
+    """BASELINE config 4 shape through HybridSORT (128 streams x 190 objects, 512-d embeddings for every detection,
+    hybridsort.yaml, 256 slots / 224 detection rows like bench.py's workload): two runs identical bit for bit, the copies
+    of a stream in one batch identical (the cosine pass's tiles and reduction order do not depend on the CTA's
+    neighbours), sampled streams equal the oracle."""
+    import sys
+    from _util import GOLDEN
+    if GOLDEN not in sys.path:
+        sys.path.insert(0, GOLDEN)
+    from scenarios import HYBRIDSORT_YAML
+    from oracle.hybridsort import HybridSortOracle
+    from yolo_tracking_b200.batch import BatchedTracker
+    from yolo_tracking_b200.synth import make_batch
+    S4, F4, D4, T4, E = 128, 14, 224, 256, 512
+    base_d, base_n, base_e = make_batch(4, 4, 190, F4, dmax=D4, emb_dim=E)
+    feats4 = np.zeros_like(base_e)
+    for f in range(F4):
+        for s in range(4):
+            n = base_n[f, s]
+            if n:
+                feats4[f, s, :n] = base_e[f, s, :n] / np.linalg.norm(base_e[f, s, :n])
+    rep = S4 // 4
+
+    def run():
+        trk = BatchedTracker("hybridsort", S4, max_tracks=T4, max_dets=D4, feat_dim=E, **HYBRIDSORT_YAML)
+        outs = []
+        for f in range(F4):
+            out, nout = trk.update_batch(np.ascontiguousarray(np.tile(base_d[f], (rep, 1, 1))), np.ascontiguousarray(np.tile(base_n[f], rep)),
+                                         feats=np.ascontiguousarray(np.tile(feats4[f], (rep, 1, 1))), img_hw=(2160, 3840))
+            outs.append((out.copy(), nout.copy()))
+        trk.sync()
+        trk.close()
+        return outs
+    a, b = run(), run()
+    oracles = [HybridSortOracle(**HYBRIDSORT_YAML) for _ in range(2)]
+    for f in range(F4):
+        assert np.array_equal(a[f][1], b[f][1])
+        for s in range(0, S4, 3):
+            k = a[f][1][s]
+            assert np.array_equal(a[f][0][s, :k], b[f][0][s, :k]), f"frame {f} stream {s}: not deterministic"
+            assert np.array_equal(a[f][0][s, :k], a[f][0][s % 4, :k]), f"frame {f} stream {s}: copies of a stream differ"
+        for i in range(2):
+            n = base_n[f, i]
+            keep = base_d[f, i, :n, 4] > HYBRIDSORT_YAML["det_thresh"]
+            ref = oracles[i].update(base_d[f, i, :n], feats4[f, i, :n][keep], (2160, 3840)).reshape(-1, 8)
+            k = a[f][1][i]
+            assert ref.shape == (k, 8), f"frame {f} stream {i}"
+            assert np.array_equal(a[f][0][i, :k, 4:], ref[:, 4:]), f"frame {f} stream {i}: ids / conf / cls / last column"
+            assert_close(a[f][0][i, :k, :4], ref[:, :4], what=f"frame {f} stream {i} boxes")
