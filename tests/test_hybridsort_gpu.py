@@ -145,3 +145,33 @@ def test_hybridsort_factory_and_rejections():
         BatchedTracker("hybridsort", 1, max_tracks=64, max_dets=32, feat_dim=8, det_thresh=0.0, use_byte=True)
     with pytest.raises(_lib.B200TrackError):
         BatchedTracker("hybridsort", 1, max_tracks=64, max_dets=32, feat_dim=0, det_thresh=0.0)
+
+
+def test_hybridsort_capacity_overflow_is_reported_not_silent():
+    """More detections than max_dets / more live trackers than max_tracks: the step that overflowed reports it when its
+    results are collected, b200track_sync repeats it (a context must be reset afterwards)."""
+    from yolo_tracking_b200 import _lib
+    from yolo_tracking_b200.batch import BatchedTracker
+    cap, E = 32, 8
+    rng = np.random.default_rng(0)
+
+    def boxes(n):
+        c = np.stack([rng.uniform(50, 1800, n), rng.uniform(50, 1000, n)], axis=1)
+        return np.concatenate([c - 15, c + 15, np.full((n, 1), 0.9), np.zeros((n, 1))], axis=1)
+    trk = BatchedTracker("hybridsort", 1, max_tracks=cap, max_dets=cap, feat_dim=E, det_thresh=0.1, max_age=30, min_hits=1)
+    d = np.zeros((1, cap, 6))
+    f = rng.standard_normal((1, cap, E)).astype(np.float32)
+    d[0] = boxes(cap)
+    with pytest.raises(_lib.B200TrackError) as e:
+        trk.update_batch(d, np.array([cap + 5], dtype=np.int32), feats=f)      # claims more detections than the buffer holds
+    assert e.value.code == _lib.ERR_CAPACITY and "detections" in str(e.value)
+    with pytest.raises(_lib.B200TrackError):
+        trk.sync()
+    trk.reset()
+    with pytest.raises(_lib.B200TrackError) as e:
+        for _ in range(3):                                            # 3 x 32 well separated boxes with unrelated embeddings:
+            d[0] = boxes(cap)                                         # every forced match is corrected away -> > 32 live trackers
+            f = rng.standard_normal((1, cap, E)).astype(np.float32)
+            trk.update_batch(d, np.array([cap], dtype=np.int32), feats=f)
+    assert e.value.code == _lib.ERR_CAPACITY and "tracks" in str(e.value)
+    trk.close()

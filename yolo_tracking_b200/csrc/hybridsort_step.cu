@@ -61,15 +61,32 @@ struct alignas(16) HySmem {
     unsigned char kvalid[TMAX], alive[TMAX], dstate[DMAX], rowused[TMAX], ema[TMAX];
     // staging of the smoothed track embeddings for the dense cosine matrix: two tiles of eight fp32 rows (up to 512 values)
     float4 etile[2][8][128];
+    unsigned long long ebar[2];     // "tile landed" mbarriers of the two buffers
 };
 
-__device__ __forceinline__ void hy_cp_async16(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc));
+// ---- bulk copies (TMA, 1-D) into shared memory, completion on an mbarrier -------------------------------------
+__device__ __forceinline__ uint32_t hy_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void hy_mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(hy_smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void hy_cp_async_commit() { asm volatile("cp.async.commit_group;" ::); }
-template <int N>
-__device__ __forceinline__ void hy_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void hy_mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(hy_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bounded wait: a protocol error becomes an error flag instead of a hung GPU
+__device__ __forceinline__ bool hy_mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t a = hy_smem_u32(bar);
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void hy_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(hy_smem_u32(dst)), "l"(src), "r"(bytes), "r"(hy_smem_u32(bar)) : "memory");
+}
 
 // the stored cost matrix behind the solver's functor interface
 struct HyMatCost {
@@ -351,24 +368,33 @@ hybridsort_step_kernel(const StepParams p) {
         // embedding distances -> Cm: one warp per detection row, the row in registers as doubles (rows of up to 512 values)
         if (nv <= 128) {
             // Every warp holds TWO detection rows in registers; the smoothed rows of the trackers pass through shared memory
-            // in tiles of eight (cp.async, double buffered), so a tile fetched once from L2 serves all 2 NW detection rows of
+            // in tiles of eight (1-D TMA bulk copies, double buffered), so a tile fetched once from L2 serves all 2 NW detection rows of
             // the round - read per pair from L2 instead, the 2 KB rows made the step L2-bandwidth bound (83 MB per stream
             // and frame at config 4).
             for (int i = tid; i < 2 * 8 * 128; i += NT) (&sm.etile[0][0][0])[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // padding stays zero
+            if (tid == 0) {
+                hy_mbar_init(&sm.ebar[0], 1); hy_mbar_init(&sm.ebar[1], 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the zero fill is ordered before the bulk copies
             __syncthreads();
             const int ntile = (Cn + 7) >> 3;
+            const uint32_t rowbytes = (uint32_t)nv * 16u;
+            // one elected thread moves a tile: eight 1-D bulk copies (a tracker's row is contiguous, the rows are not), their
+            // bytes counted on the buffer's mbarrier
             auto issue_tile = [&](int ti, int buf) {
-                const int c0 = ti * 8, ncols = min(8, Cn - c0);
-                for (int i = tid; i < ncols * 128; i += NT) {
-                    const int qq = i >> 7, e = i & 127;
-                    if (e < nv) hy_cp_async16(&sm.etile[buf][qq][e], reinterpret_cast<const float4*>(pool + (size_t)sm.frow[sm.ht[c0 + qq]] * F) + e);
+                if (tid == 0) {
+                    const int c0 = ti * 8, ncols = min(8, Cn - c0);
+                    hy_mbar_expect_tx(&sm.ebar[buf], rowbytes * ncols);
+                    for (int qq = 0; qq < ncols; ++qq)
+                        hy_bulk_g2s(&sm.etile[buf][qq][0], pool + (size_t)sm.frow[sm.ht[c0 + qq]] * F, rowbytes, &sm.ebar[buf]);
                 }
-                hy_cp_async_commit();
             };
             const int qi = lane >> 2;                                 // the value of a group this lane finalises
+            int g = 0;                                                // tiles consumed so far: buffer g & 1, its use (g >> 1)
             for (int r0 = 0; r0 < R; r0 += 2 * NW) {
                 const int rA = r0 + 2 * warp, rB = rA + 1;
-                const bool actA = rA < R, actB = rB < R;              // warp-uniform; idle warps still copy and synchronise
+                const bool actA = rA < R, actB = rB < R;              // warp-uniform; idle warps still synchronise
                 const int jA = actA ? sm.hd[rA] : 0, jB = actB ? sm.hd[rB] : jA;
                 double d0[16], d1[16];
                 hy_load_row16(d0, reinterpret_cast<const float4*>(dfeat + (size_t)jA * F), nv, lane);
@@ -376,24 +402,25 @@ hybridsort_step_kernel(const StepParams p) {
                 const int myr = (qi & 4) ? rB : rA;
                 const bool myact = (lane & 3) == 0 && ((qi & 4) ? actB : actA);
                 const double nj = sm.dnorm[(qi & 4) ? jB : jA];
-                issue_tile(0, 0);
+                issue_tile(0, g & 1);
                 for (int ti = 0; ti < ntile; ++ti) {
-                    const int buf = ti & 1;
-                    if (ti + 1 < ntile) { issue_tile(ti + 1, buf ^ 1); hy_cp_async_wait<1>(); } else hy_cp_async_wait<0>();
-                    __syncthreads();
+                    const int cur = g + ti, buf = cur & 1;
+                    if (ti + 1 < ntile) issue_tile(ti + 1, buf ^ 1);  // its last readers passed the barrier below
+                    if (!hy_mbar_wait(&sm.ebar[buf], (uint32_t)(cur >> 1) & 1u)) err |= B200_ERR_LSA;
                     if (actA) {
 #pragma unroll
-                        for (int g = 0; g < 2; ++g) {
-                            const int c0 = ti * 8 + 4 * g;
+                        for (int gq = 0; gq < 2; ++gq) {
+                            const int c0 = ti * 8 + 4 * gq;
                             if (c0 < Cn) {                            // uniform
-                                const double uv = hy_dot2x4(d0, d1, &sm.etile[buf][4 * g], lane);
+                                const double uv = hy_dot2x4(d0, d1, &sm.etile[buf][4 * gq], lane);
                                 const int c = c0 + (qi & 3);
                                 if (myact && c < Cn) Cm[(size_t)myr * TMAX + c] = hy_cosine(uv, sm.tnorm[sm.ht[c]], nj);
                             }
                         }
                     }
-                    __syncthreads();                                  // the next iteration's prefetch overwrites this tile's twin
+                    __syncthreads();                                  // the buffer may be refilled
                 }
+                g += ntile;
             }
         } else {
             for (int k = warp; k < R * Cn; k += NW) {
