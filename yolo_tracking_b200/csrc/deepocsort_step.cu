@@ -853,15 +853,35 @@ deepocsort_step_kernel(const StepParams p) {
             const double beta = xsub(1.0, alpha);
             double* e = pool + (size_t)sm.erow[q] * F;
             const float* d = dfeat + (size_t)j * F;
+            // The renormalisation multiplies by one correctly rounded reciprocal per row instead of dividing every element
+            // (a double division is a ~15-instruction sequence; 512 of them per matched tracker were a sixth of the step's
+            // instructions): each value is within one ulp of the reference's quotient - the embedding's own tolerance is
+            // 1e-6 (float32 products upstream).  Rows of up to 512 values stay in registers between the two passes.
             double acc = 0.0;
+            if (F <= 512) {
+                double v[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int i = lane + 32 * k;
+                    v[k] = 0.0;
+                    if (i < F) { v[k] = xadd(xmul(alpha, e[i]), xmul(beta, (double)d[i])); acc += v[k] * v[k]; }
+                }
+                const double rinv = xdiv(1.0, sqrt(warp_sum_d(acc)));
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    const int i = lane + 32 * k;
+                    if (i < F) e[i] = xmul(v[k], rinv);
+                }
+                continue;
+            }
             for (int i = lane; i < F; i += 32) {
                 const double v = xadd(xmul(alpha, e[i]), xmul(beta, (double)d[i]));
                 e[i] = v;
                 acc += v * v;
             }
-            const double nrm = sqrt(warp_sum_d(acc));
+            const double rinv = xdiv(1.0, sqrt(warp_sum_d(acc)));
             __syncwarp();
-            for (int i = lane; i < F; i += 32) e[i] = xdiv(e[i], nrm);
+            for (int i = lane; i < F; i += 32) e[i] = xmul(e[i], rinv);
         }
     }
 
