@@ -415,23 +415,6 @@ __device__ __forceinline__ double warp_sum(double x) {
     for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
     return x;
 }
-// Division of a whole row by one norm.  __fdiv_rn's fast path is: y0 = rcp.approx(n); y = fma(y0, fma(-n, y0, 1), y0);
-// q0 = a * y; q = fma(y, fma(-n, q0, a), q0) - ten instructions per quotient with its range check and branch, and these
-// divisions were 38 % of the BoT-SORT step's instructions (ncu, per-line).  The refined reciprocal only depends on n, so
-// it is formed once per row and every element takes the remaining three operations: the SAME operation sequence, hence
-// the same correctly rounded quotients, for every normal operand (what the range check would send to the slow path -
-// denormal or zero divisors, quotients near the under / overflow thresholds - cannot occur for components of a unit-scale
-// embedding divided by its norm; tools/micro/fdiv_row.cu compares the two forms bit for bit).
-struct RowDiv { float n, y; };
-__device__ __forceinline__ RowDiv row_div(float n) {
-    float y0;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(y0) : "f"(n));
-    return RowDiv{n, __fmaf_rn(y0, __fmaf_rn(-n, y0, 1.0f), y0)};
-}
-__device__ __forceinline__ float fdiv_row(float a, const RowDiv& d) {
-    const float q0 = __fmul_rn(a, d.y);
-    return __fmaf_rn(d.y, __fmaf_rn(-d.n, q0, a), q0);
-}
 __device__ __forceinline__ float4 f4_div(float4 a, const RowDiv& d) {
     return make_float4(fdiv_row(a.x, d), fdiv_row(a.y, d), fdiv_row(a.z, d), fdiv_row(a.w, d));
 }

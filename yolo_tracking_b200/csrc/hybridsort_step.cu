@@ -109,8 +109,8 @@ __device__ __forceinline__ double hy_warp_sum(double x) {
     for (int d = 16; d; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
     return x;
 }
-__device__ __forceinline__ float4 hy_f4_div(float4 a, float n) {
-    return make_float4(__fdiv_rn(a.x, n), __fdiv_rn(a.y, n), __fdiv_rn(a.z, n), __fdiv_rn(a.w, n));
+__device__ __forceinline__ float4 hy_f4_div(float4 a, const RowDiv& d) {       // common.cuh: the quotients of __fdiv_rn
+    return make_float4(fdiv_row(a.x, d), fdiv_row(a.y, d), fdiv_row(a.z, d), fdiv_row(a.w, d));
 }
 __device__ __forceinline__ double hy_f4_sq(float4 a) {
     return (double)a.x * a.x + (double)a.y * a.y + (double)a.z * a.z + (double)a.w * a.w;
@@ -726,10 +726,10 @@ hybridsort_step_kernel(const StepParams p) {
         // feat /= |feat| (float32 norm), blend, renormalise
         double acc = 0.0;
         for (int i = lane; i < nv; i += 32) acc += hy_f4_sq(det[i]);
-        const float n1 = hy_norm_f32(hy_warp_sum(acc));
+        const RowDiv n1 = row_div(hy_norm_f32(hy_warp_sum(acc)));
         acc = 0.0;
         for (int i = lane; i < nv; i += 32) acc += hy_f4_sq(hy_blend(trk[i], hy_f4_div(det[i], n1)));
-        const float n2 = hy_norm_f32(hy_warp_sum(acc));
+        const RowDiv n2 = row_div(hy_norm_f32(hy_warp_sum(acc)));
         for (int i = lane; i < nv; i += 32) trk[i] = hy_f4_div(hy_blend(trk[i], hy_f4_div(det[i], n1)), n2);
     }
 
@@ -856,10 +856,10 @@ hybridsort_step_kernel(const StepParams p) {
         const float4* d = reinterpret_cast<const float4*>(dfeat + (size_t)j * F);
         double acc = 0.0;
         for (int i = lane; i < nv; i += 32) acc += hy_f4_sq(d[i]);
-        const float n1 = hy_norm_f32(hy_warp_sum(acc));
+        const RowDiv n1 = row_div(hy_norm_f32(hy_warp_sum(acc)));
         acc = 0.0;
         for (int i = lane; i < nv; i += 32) acc += hy_f4_sq(hy_f4_div(d[i], n1));
-        const float n2 = hy_norm_f32(hy_warp_sum(acc));
+        const RowDiv n2 = row_div(hy_norm_f32(hy_warp_sum(acc)));
         for (int i = lane; i < nv; i += 32) e[i] = hy_f4_div(hy_f4_div(d[i], n1), n2);
     }
     const int n1c = min(n0 + n_new, tcap);

@@ -329,18 +329,51 @@ __global__ void __launch_bounds__(NT) ss_post_kernel(const SSParams p, const dou
         float* a = p.feat + ((size_t)s * T + sl) * F;
         const int dj = sm.mdet[k];
         if (dj >= 0) {
-            const float* b = feats + ((size_t)s * D + dj) * F;
-            double acc = 0.0;
-            for (int i = lane; i < F; i += 32) acc += (double)b[i] * b[i];
-            const float nb = sqrtf((float)warp_sum_d(acc));
-            acc = 0.0;
-            for (int i = lane; i < F; i += 32) {
-                const float v = __fadd_rn(__fmul_rn(p.ema_alpha, a[i]), __fmul_rn(p.ema_beta, __fdiv_rn(b[i], nb)));
-                a[i] = v;
-                acc += (double)v * v;
+            // feature /= |feature|; smooth = alpha * smooth + beta * feature; smooth /= |smooth| - float32 like numpy.  The row
+            // (F <= 512: four float4 per lane) stays in registers across the passes, and the divisions of a row share one
+            // refined reciprocal (common.cuh: the same quotients as __fdiv_rn).
+            const float4* b4 = reinterpret_cast<const float4*>(feats + ((size_t)s * D + dj) * F);
+            float4* a4 = reinterpret_cast<float4*>(a);
+            if (nv <= 128) {
+                float4 bv[4], av[4];
+                double acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool in = lane + 32 * q < nv;
+                    bv[q] = in ? b4[lane + 32 * q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    av[q] = in ? a4[lane + 32 * q] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    acc += (double)bv[q].x * bv[q].x + (double)bv[q].y * bv[q].y + (double)bv[q].z * bv[q].z + (double)bv[q].w * bv[q].w;
+                }
+                const RowDiv nb = row_div(sqrtf((float)warp_sum_d(acc)));
+                acc = 0.0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float4& v = av[q];
+                    v.x = __fadd_rn(__fmul_rn(p.ema_alpha, v.x), __fmul_rn(p.ema_beta, fdiv_row(bv[q].x, nb)));
+                    v.y = __fadd_rn(__fmul_rn(p.ema_alpha, v.y), __fmul_rn(p.ema_beta, fdiv_row(bv[q].y, nb)));
+                    v.z = __fadd_rn(__fmul_rn(p.ema_alpha, v.z), __fmul_rn(p.ema_beta, fdiv_row(bv[q].z, nb)));
+                    v.w = __fadd_rn(__fmul_rn(p.ema_alpha, v.w), __fmul_rn(p.ema_beta, fdiv_row(bv[q].w, nb)));
+                    acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+                }
+                const RowDiv ns = row_div(sqrtf((float)warp_sum_d(acc)));
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (lane + 32 * q < nv)
+                        a4[lane + 32 * q] = make_float4(fdiv_row(av[q].x, ns), fdiv_row(av[q].y, ns), fdiv_row(av[q].z, ns), fdiv_row(av[q].w, ns));
+            } else {
+                const float* b = feats + ((size_t)s * D + dj) * F;
+                double acc = 0.0;
+                for (int i = lane; i < F; i += 32) acc += (double)b[i] * b[i];
+                const RowDiv nb = row_div(sqrtf((float)warp_sum_d(acc)));
+                acc = 0.0;
+                for (int i = lane; i < F; i += 32) {
+                    const float v = __fadd_rn(__fmul_rn(p.ema_alpha, a[i]), __fmul_rn(p.ema_beta, fdiv_row(b[i], nb)));
+                    a[i] = v;
+                    acc += (double)v * v;
+                }
+                const RowDiv ns = row_div(sqrtf((float)warp_sum_d(acc)));
+                for (int i = lane; i < F; i += 32) a[i] = fdiv_row(a[i], ns);
             }
-            const float ns = sqrtf((float)warp_sum_d(acc));
-            for (int i = lane; i < F; i += 32) a[i] = __fdiv_rn(a[i], ns);
             __syncwarp();
         }
         if (sm.st_after[k] == SS_CONFIRMED) {
@@ -369,8 +402,8 @@ __global__ void __launch_bounds__(NT) ss_post_kernel(const SSParams p, const dou
         float* a = p.feat + ((size_t)s * T + sm.born_slot[k]) * F;
         double acc = 0.0;
         for (int i = lane; i < F; i += 32) acc += (double)b[i] * b[i];
-        const float nb = sqrtf((float)warp_sum_d(acc));
-        for (int i = lane; i < F; i += 32) a[i] = __fdiv_rn(b[i], nb);
+        const RowDiv nb = row_div(sqrtf((float)warp_sum_d(acc)));
+        for (int i = lane; i < F; i += 32) a[i] = fdiv_row(b[i], nb);
     }
     // ---- result rows: confirmed tracks updated this frame, list order (strong_sort.py:84-99)
     const bool listed = tid < n && st == SS_CONFIRMED && tsu < 1;
