@@ -97,7 +97,7 @@ extern "C" void b200track_destroy(b200track_ctx* ctx) {
     cudaDeviceSynchronize();
     cudaFree(ctx->p.state_f); cudaFree(ctx->p.state_i); cudaFree(ctx->p.counts);
     cudaFree(ctx->p.track_updates); cudaFree(ctx->p.err); cudaFree(ctx->p.stats); cudaFree(ctx->p.err_slot); cudaFree(ctx->p.dbg); cudaFree(ctx->p.scratch);
-    cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.feat_curr); cudaFree(ctx->p.cls_hist); cudaFree(ctx->p.emb_pool);
+    cudaFree(ctx->p.feat_pool); cudaFree(ctx->p.cls_hist); cudaFree(ctx->p.emb_pool);
     {
         b200::SSParams& q = ctx->ss;
         cudaFree(q.mean); cudaFree(q.cov); cudaFree(q.conf); cudaFree(q.cls); cudaFree(q.ti); cudaFree(q.order); cudaFree(q.feat);
@@ -269,7 +269,6 @@ extern "C" int b200track_create(const b200track_config* cfg, b200track_ctx** out
         CU_TRY_CTX(cudaMalloc(&p.cls_hist, S * T * 9 * sizeof(double)));
         if (cfg->with_reid) {
             CU_TRY_CTX(cudaMalloc(&p.feat_pool, S * T * (size_t)cfg->feat_dim * sizeof(float)));
-            CU_TRY_CTX(cudaMalloc(&p.feat_curr, S * D * (size_t)cfg->feat_dim * sizeof(float)));
         }
     }
     CU_TRY_CTX(cudaMalloc(&p.counts, S * 4 * sizeof(int)));

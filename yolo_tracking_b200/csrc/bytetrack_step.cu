@@ -78,6 +78,7 @@ struct BotSmem<TMAX, DMAX, true> {
     static constexpr int PCAP = 4 * TMAX;
     double pcost[PCAP];              // iou-side cost of a pair waiting for its appearance distance
     uint32_t epairs[PCAP];           // (row << 16) | det
+    float dn0[DMAX], dn1[DMAX];      // the two norms a detection's raw embedding row is divided by (curr_feat = (row / dn0) / dn1)
     float dn2[DMAX];                 // norm of a detection's curr_feat (the third in-place normalisation divides by it)
     int nepairs[4];
     short frow[TMAX];                // embedding-pool row of a slot
@@ -425,9 +426,11 @@ __device__ __forceinline__ double f4_sq(float4 a) {
 __device__ __forceinline__ float norm_f32(double sumsq) { return sqrtf((float)sumsq); }
 
 // A detection embedding as the reference holds it when costs are computed: get_features row -> STrack.__init__
-// (feat /= |feat|, then the aliased smooth_feat /= |smooth_feat|).  The twice-normalised row (curr_feat) is written
-// to the stream's scratch block once, so pair costs, blends and new tracks read it without redoing the divisions;
-// the return value is its norm, which update_features of a matched track divides by once more.
+// (feat /= |feat|, then the aliased smooth_feat /= |smooth_feat|).  The twice-normalised row (curr_feat) is never
+// stored: its two divisors (and its own norm, which update_features of a matched track divides by once more) are kept
+// per detection, and pair costs, blends and new tracks redo the two row divisions (three operations each with the shared
+// reciprocal of common.cuh - the same bits) on the raw input row instead of writing a [max_dets, feat_dim] scratch
+// block per stream and reading it back.
 // Rows of up to 512 floats are held in registers (four float4 per lane, every load in flight at once): the three
 // normalisation passes, the blend and the distance then run without touching memory again.  Written as loops of single
 // loads they were serialised on the memory latency - the embedding phases took 90 % of the BoT-SORT step.
@@ -445,7 +448,17 @@ __device__ __forceinline__ double row4_sq(const Row4& r) {
     return a;
 }
 
-__device__ __forceinline__ float det_curr_feat(const float4* row, float4* out, int nv, int lane) {
+// curr_feat values of a raw row: (x / n0) / n1
+__device__ __forceinline__ float4 f4_curr(float4 a, const RowDiv& d0, const RowDiv& d1) { return f4_div(f4_div(a, d0), d1); }
+__device__ __forceinline__ Row4 load_curr4(const float4* row, int nv, int lane, const RowDiv& d0, const RowDiv& d1) {
+    Row4 r = load_row4(row, nv, lane);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r.v[k] = f4_curr(r.v[k], d0, d1);
+    return r;
+}
+
+// the three norms of a detection's embedding: of the raw row, of row / n0, of (row / n0) / n1
+__device__ __forceinline__ float3 det_curr_feat(const float4* row, int nv, int lane) {
     if (nv <= 128) {
         Row4 r = load_row4(row, nv, lane);
         const float n0 = norm_f32(warp_sum(row4_sq(r)));
@@ -455,11 +468,8 @@ __device__ __forceinline__ float det_curr_feat(const float4* row, float4* out, i
         const float n1 = norm_f32(warp_sum(row4_sq(r)));
         const RowDiv d1 = row_div(n1);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            r.v[k] = f4_div(r.v[k], d1);
-            if (lane + 32 * k < nv) out[lane + 32 * k] = r.v[k];
-        }
-        return norm_f32(warp_sum(row4_sq(r)));
+        for (int k = 0; k < 4; ++k) r.v[k] = f4_div(r.v[k], d1);
+        return make_float3(n0, n1, norm_f32(warp_sum(row4_sq(r))));
     }
     double a = 0.0;
     for (int i = lane; i < nv; i += 32) a += f4_sq(row[i]);
@@ -470,20 +480,16 @@ __device__ __forceinline__ float det_curr_feat(const float4* row, float4* out, i
     const float n1 = norm_f32(warp_sum(a));
     const RowDiv d1 = row_div(n1);
     a = 0.0;
-    for (int i = lane; i < nv; i += 32) {
-        const float4 v = f4_div(f4_div(row[i], d0), d1);
-        out[i] = v;
-        a += f4_sq(v);
-    }
-    return norm_f32(warp_sum(a));
+    for (int i = lane; i < nv; i += 32) a += f4_sq(f4_curr(row[i], d0, d1));
+    return make_float3(n0, n1, norm_f32(warp_sum(a)));
 }
 
 // embedding_distance (matching.py:145-167) of one (smoothed track embedding, detection curr_feat) pair:
 // scipy cdist 'cosine' in double on the fp32 values, clamped at 0
-__device__ __forceinline__ double emb_distance(const float4* trk, const float4* det, int nv, int lane) {
+__device__ __forceinline__ double emb_distance(const float4* trk, const float4* det, const RowDiv& d0, const RowDiv& d1, int nv, int lane) {
     double uv = 0.0, uu = 0.0, vv = 0.0;
     if (nv <= 128) {
-        const Row4 ra = load_row4(trk, nv, lane), rb = load_row4(det, nv, lane);
+        const Row4 ra = load_row4(trk, nv, lane), rb = load_curr4(det, nv, lane, d0, d1);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float4 a = ra.v[k], b = rb.v[k];
@@ -494,7 +500,7 @@ __device__ __forceinline__ double emb_distance(const float4* trk, const float4* 
     } else
     for (int i = lane; i < nv; i += 32) {
         const float4 a = trk[i];
-        const float4 b = det[i];
+        const float4 b = f4_curr(det[i], d0, d1);
         uv += (double)a.x * b.x + (double)a.y * b.y + (double)a.z * b.z + (double)a.w * b.w;
         uu += f4_sq(a);
         vv += f4_sq(b);
@@ -507,7 +513,7 @@ __device__ __forceinline__ double emb_distance(const float4* trk, const float4* 
 
 // appearance stage of the candidate graph (BoT-SORT): one warp per pair that passed the proximity mask
 template <int NT, int KIND, class SM>
-__device__ __forceinline__ void graph_phase_emb(SM& sm, const StepParams& p, int s, const PassLimit& lim) {
+__device__ __forceinline__ void graph_phase_emb(SM& sm, const StepParams& p, int s, const float* dfeat, const PassLimit& lim) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ne = sm.bot.nepairs[0];
     const int nv = p.feat_dim >> 2;
@@ -515,8 +521,8 @@ __device__ __forceinline__ void graph_phase_emb(SM& sm, const StepParams& p, int
         const uint32_t pr = sm.bot.epairs[k];
         const int t = pr >> 16, j = pr & 0xffff;
         const float4* trk = reinterpret_cast<const float4*>(p.feat_pool + ((size_t)s * SM::TCAP + sm.bot.frow[t]) * p.feat_dim);
-        const float4* det = reinterpret_cast<const float4*>(p.feat_curr + ((size_t)s * p.max_dets + j) * p.feat_dim);
-        double e = xmul(emb_distance(trk, det, nv, lane), 0.5);
+        const float4* det = reinterpret_cast<const float4*>(dfeat + (size_t)j * p.feat_dim);
+        double e = xmul(emb_distance(trk, det, row_div(sm.bot.dn0[j]), row_div(sm.bot.dn1[j]), nv, lane), 0.5);
         if (e > p.appearance_thresh) e = 1.0;
         const double c = fmin(sm.bot.pcost[k], e);
         if (lane == 0 && c <= (sm.rowtype[t] == RT_A ? lim.limA : lim.limB)) graph_add_edge<KIND>(sm, t, j, c);
@@ -576,6 +582,8 @@ bytetrack_step_kernel(const StepParams p) {
     if (packed) { roff = p.det_off[s]; nd_in = p.det_off[s + 1] - roff; }
     const double* dets_g = packed ? p.dets + (size_t)roff * 6 : p.dets + (size_t)s * p.max_dets * 6;
     const float* dets32_g = p.dets32 ? p.dets32 + (size_t)roff * 6 : nullptr;
+    // this stream's raw detection embeddings (BoT-SORT): row j at dfeat + j * feat_dim
+    const float* dfeat = (BOT && p.feats) ? p.feats + (packed ? (size_t)roff : (size_t)s * p.max_dets) * p.feat_dim : nullptr;
     auto det_cls = [&](int j) -> double { return dets32_g ? (double)dets32_g[j * 6 + 5] : dets_g[j * 6 + 5]; };
     // thread j fetches detection row j whole (three 16-byte loads: 48-byte rows, 16-byte aligned) - no transposition pass
     double mv[8];
@@ -774,10 +782,8 @@ bytetrack_step_kernel(const StepParams p) {
             const int nv = p.feat_dim >> 2;
             for (int j = warp; j < nd; j += NT / 32) {
                 if (sm.dflag[j] != DF_HIGH) continue;
-                const size_t off = ((size_t)s * p.max_dets + j) * p.feat_dim;
-                const size_t off_in = packed ? ((size_t)roff + j) * p.feat_dim : off;
-                const float n2 = det_curr_feat(reinterpret_cast<const float4*>(p.feats + off_in), reinterpret_cast<float4*>(p.feat_curr + off), nv, lane);
-                if (lane == 0) sm.bot.dn2[j] = n2;
+                const float3 nn = det_curr_feat(reinterpret_cast<const float4*>(dfeat + (size_t)j * p.feat_dim), nv, lane);
+                if (lane == 0) { sm.bot.dn0[j] = nn.x; sm.bot.dn1[j] = nn.y; sm.bot.dn2[j] = nn.z; }
             }
         }
         if (tid == 0) sm.bot.nepairs[0] = 0;
@@ -799,7 +805,7 @@ bytetrack_step_kernel(const StepParams p) {
     __syncthreads();
     if constexpr (BOT) {
         if (sm.npairs[0] > SM::PCAP || sm.ecount[0] > SM::ECAP) err |= B200_ERR_BOT_CAPACITY;
-        graph_phase_emb<NT, KIND>(sm, p, s, lim);
+        graph_phase_emb<NT, KIND>(sm, p, s, dfeat, lim);
         __syncthreads();
     }
     if (sm.ecount[0] > SM::ECAP) {                        // uniform
@@ -851,7 +857,7 @@ bytetrack_step_kernel(const StepParams p) {
         __syncthreads();
         if constexpr (BOT) {
             if (sm.npairs[0] > SM::PCAP || sm.ecount[0] > SM::ECAP) err |= B200_ERR_BOT_CAPACITY;
-            graph_phase_emb<NT, KIND>(sm, p, s, lim);
+            graph_phase_emb<NT, KIND>(sm, p, s, dfeat, lim);
             __syncthreads();
         }
     }
@@ -1009,16 +1015,16 @@ bytetrack_step_kernel(const StepParams p) {
                 const int j = sm.bot.emadet[q];
                 if (j < 0) continue;
                 float4* trk = reinterpret_cast<float4*>(p.feat_pool + ((size_t)s * TMAX + sm.bot.frow[q]) * p.feat_dim);
-                const float4* det = reinterpret_cast<const float4*>(p.feat_curr + ((size_t)s * p.max_dets + j) * p.feat_dim);
-                const RowDiv n2 = row_div(sm.bot.dn2[j]);
+                const float4* det = reinterpret_cast<const float4*>(dfeat + (size_t)j * p.feat_dim);
+                const RowDiv n0 = row_div(sm.bot.dn0[j]), n1 = row_div(sm.bot.dn1[j]), n2 = row_div(sm.bot.dn2[j]);
                 auto blend = [&](int i) {
-                    const float4 f = f4_div(det[i], n2);
+                    const float4 f = f4_div(f4_curr(det[i], n0, n1), n2);
                     const float4 a = trk[i];
                     return make_float4(__fadd_rn(__fmul_rn(A, a.x), __fmul_rn(B, f.x)), __fadd_rn(__fmul_rn(A, a.y), __fmul_rn(B, f.y)),
                                        __fadd_rn(__fmul_rn(A, a.z), __fmul_rn(B, f.z)), __fadd_rn(__fmul_rn(A, a.w), __fmul_rn(B, f.w)));
                 };
                 if (nv <= 128) {
-                    const Row4 ra = load_row4(trk, nv, lane), rd = load_row4(det, nv, lane);
+                    const Row4 ra = load_row4(trk, nv, lane), rd = load_curr4(det, nv, lane, n0, n1);
                     Row4 rb;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -1276,13 +1282,14 @@ bytetrack_step_kernel(const StepParams p) {
                 const int j = sm.bot.nbdet[k];
                 if (j < 0) continue;
                 float4* trk = reinterpret_cast<float4*>(p.feat_pool + ((size_t)s * TMAX + sm.bot.nbrow[k]) * p.feat_dim);
-                const float4* det = reinterpret_cast<const float4*>(p.feat_curr + ((size_t)s * p.max_dets + j) * p.feat_dim);
+                const float4* det = reinterpret_cast<const float4*>(dfeat + (size_t)j * p.feat_dim);
+                const RowDiv n0 = row_div(sm.bot.dn0[j]), n1 = row_div(sm.bot.dn1[j]);
                 if (nv <= 128) {
-                    const Row4 r = load_row4(det, nv, lane);
+                    const Row4 r = load_curr4(det, nv, lane, n0, n1);
 #pragma unroll
                     for (int k = 0; k < 4; ++k) if (lane + 32 * k < nv) trk[lane + 32 * k] = r.v[k];
                 } else
-                for (int i = lane; i < nv; i += 32) trk[i] = det[i];
+                for (int i = lane; i < nv; i += 32) trk[i] = f4_curr(det[i], n0, n1);
             }
         }
     }

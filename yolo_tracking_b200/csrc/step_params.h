@@ -26,7 +26,6 @@ struct StepParams {
     int with_reid;
     int fuse_first;           // fuse_first_associate (bot_sort.py:300-301)
     float* feat_pool;         // [S, Tcap, feat_dim] smoothed track embeddings, row-indexed (layout.h)
-    float* feat_curr;         // [S, max_dets, feat_dim] scratch: this frame's twice-normalised detection embeddings
     double* cls_hist;         // [S, Tcap, 9] class-vote tables, row-indexed
     // DeepOCSORT (deepocsort.yaml keys)
     double w_assoc_emb, alpha_fixed_emb, aw_param;
