@@ -58,7 +58,7 @@ struct alignas(16) HySmem {
     int misc[8];
     short hd[DMAX], ht[TMAX], drow[DMAX], dmatch[DMAX], tmatch[TMAX], ud[DMAX], ut[TMAX], frow[TMAX], freelist[TMAX];
     short nbrow[DMAX], nbdet[DMAX];
-    unsigned char kvalid[TMAX], alive[TMAX], dstate[DMAX], rowused[TMAX], ema[TMAX];
+    unsigned char kvalid[TMAX], alive[TMAX], dstate[DMAX], rowused[TMAX], ema[TMAX], tdeg[TMAX], ddeg[DMAX];
     // staging of the smoothed track embeddings for the dense cosine matrix: two tiles of eight fp32 rows (up to 512 values)
     float4 etile[2][8][128];
     unsigned long long ebar[2];     // "tile landed" mbarriers of the two buffers
@@ -88,12 +88,53 @@ __device__ __forceinline__ void hy_bulk_g2s(void* dst, const void* src, uint32_t
                  ::"r"(hy_smem_u32(dst)), "l"(src), "r"(bytes), "r"(hy_smem_u32(bar)) : "memory");
 }
 
-// the stored cost matrix behind the solver's functor interface
-struct HyMatCost {
-    const double* C;
-    int ld;
-    __device__ __forceinline__ double operator()(int r, int c) const { return C[(size_t)r * ld + c]; }
-    __device__ __forceinline__ double lower(int, int) const { return -__longlong_as_double(0x7ff0000000000000LL); }
+// Cost of (row r = detection hd[r], column c = live tracker ht[c]) in the first association (association.py:508-541):
+//   -(similarity + (lt + rt + lb + rb)) + 1.3 * embedding distance, plus the canonical tie-break.
+// The embedding distances E are a stored matrix (the dense cosine pass); the geometric part - a similarity and four
+// direction terms with a square root, a reciprocal and an arc cosine each - is evaluated ON DEMAND: for iou / giou a pair
+// of disjoint regular boxes has similarity exactly +0.0 and the four direction terms are bounded by 2 |inertia| score, so
+// lower() = 1.3 E - that bound is a valid lower bound of the cost, and with unrelated embeddings (E around 1) it lies far
+// above the cost of a row's real partner: the row reduction and the solver skip nearly every pair without evaluating it.
+// Evaluated in full for every pair, this geometry was a quarter of the step's instructions.
+template <class SM>
+struct HyCost {
+    const SM& sm;
+    const double* E;
+    int ld, Cn, func;
+    double W, H, inertia;
+    bool sparse;                    // iou / giou: a disjoint pair has similarity exactly +0.0
+    __device__ __forceinline__ Box dbox(int j) const { return Box{sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]}; }
+    __device__ __forceinline__ Box tbox(int sl) const { return Box{sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]}; }
+    __device__ __forceinline__ double bound(int j) const { return xmul(2.0, fabs(xmul(inertia, sm.dconf[j]))) + 1e-6; }
+    __device__ __forceinline__ bool free_pair(int j, int sl) const {
+        return sparse && !sm.ddeg[j] && !sm.tdeg[sl] && !box_overlap(dbox(j), tbox(sl));
+    }
+    __device__ __forceinline__ double operator()(int r, int c) const {
+        const int j = sm.hd[r], sl = sm.ht[c];
+        const Box db = dbox(j);
+        const double sv = oc_sim(func, db, tbox(sl), W, H);
+        double ang = 0.0;
+        if (sm.kvalid[sl]) {
+            const double kx1 = sm.kbox[0][sl], ky1 = sm.kbox[1][sl], kx2 = sm.kbox[2][sl], ky2 = sm.kbox[3][sl];
+            const double sc = sm.dconf[j];
+            // corner order of the reference's sum: lt = (x1, y1), rt = (x1, y2), lb = (x2, y1), rb = (x2, y2)
+            double a4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double vy = sm.vel[2 * q][sl], vx = sm.vel[2 * q + 1][sl];
+                const double kcx = q < 2 ? kx1 : kx2, kcy = (q & 1) ? ky2 : ky1;
+                const double dcx = q < 2 ? db.x1 : db.x2, dcy = (q & 1) ? db.y2 : db.y1;
+                a4[q] = (vx == 0.0 && vy == 0.0) ? 0.0 : oc_angle(vy, vx, kcx, kcy, true, dcx, dcy, inertia, sc);
+            }
+            ang = xadd(xadd(xadd(a4[0], a4[1]), a4[2]), a4[3]);
+        }
+        const double cst = xadd(-xadd(sv, ang), xmul(1.3, E[(size_t)r * ld + c]));
+        return xadd(cst, xmul((double)(r * Cn + c), TIE_EPS));
+    }
+    __device__ __forceinline__ double lower(int r, int c) const {
+        const int j = sm.hd[r];
+        return free_pair(j, sm.ht[c]) ? xmul(1.3, E[(size_t)r * ld + c]) - bound(j) : -__longlong_as_double(0x7ff0000000000000LL);
+    }
 };
 
 template <int NT, class SM>
@@ -139,7 +180,7 @@ __device__ __forceinline__ double hy_cosine(double uv, double nu, double nv) {
 // still carries (bits 4, 3, 2 of the lane index pick the half it keeps) and two plain steps, 9 shuffles of a double
 // instead of 40; afterwards lane 4 q holds the sum of value q and eight lanes finalise their pairs in parallel.  Every
 // value is summed over the lanes in the same pairing order, so a pair's bits do not depend on its position in the
-// group: the correction pass recomputes single pairs with the same chain and the same tree.
+// group.
 __device__ __forceinline__ double hy_chain(const double (&d)[16], const float4 (&v)[4]) {
     double acc = 0.0;
 #pragma unroll
@@ -181,14 +222,6 @@ __device__ __forceinline__ double hy_dot2x4(const double (&d0)[16], const double
         p[q] = hy_chain(d0, v);
         p[q + 4] = hy_chain(d1, v);
     }
-    return hy_reduce8(p, lane);
-}
-// one pair, the smoothed row read from global memory: lane 0 holds the sum
-__device__ __forceinline__ double hy_dot1(const double (&d)[16], const float4* b, int nv, int lane) {
-    float4 v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v[k] = lane + 32 * k < nv ? b[lane + 32 * k] : make_float4(0.f, 0.f, 0.f, 0.f);
-    double p[8] = {hy_chain(d, v), 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     return hy_reduce8(p, lane);
 }
 // the detection row in that register form
@@ -431,43 +464,46 @@ hybridsort_step_kernel(const StepParams p) {
             }
         }
         __syncthreads();
-        // full cost of every pair, one thread each (association.py:508-541):
-        //   -(similarity + (lt + rt + lb + rb)) + 1.3 * embedding distance, plus the canonical tie-break
-        for (int idx = tid; idx < R * Cn; idx += NT) {
-            const int r = idx / Cn, c = idx - r * Cn;
-            const int j = sm.hd[r], sl = sm.ht[c];
-            const Box db = {sm.dbox[0][j], sm.dbox[1][j], sm.dbox[2][j], sm.dbox[3][j]};
-            const Box tb = {sm.tbox[0][sl], sm.tbox[1][sl], sm.tbox[2][sl], sm.tbox[3][sl]};
-            const double sv = oc_sim(func, db, tb, W, H);
-            double ang = 0.0;
-            if (sm.kvalid[sl]) {
-                const double kx1 = sm.kbox[0][sl], ky1 = sm.kbox[1][sl], kx2 = sm.kbox[2][sl], ky2 = sm.kbox[3][sl];
-                const double sc = sm.dconf[j];
-                // corner order of the reference's sum: lt = (x1, y1), rt = (x1, y2), lb = (x2, y1), rb = (x2, y2)
-                double a4[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const double vy = sm.vel[2 * q][sl], vx = sm.vel[2 * q + 1][sl];
-                    const double kcx = q < 2 ? kx1 : kx2, kcy = (q & 1) ? ky2 : ky1;
-                    const double dcx = q < 2 ? db.x1 : db.x2, dcy = (q & 1) ? db.y2 : db.y1;
-                    a4[q] = (vx == 0.0 && vy == 0.0) ? 0.0 : oc_angle(vy, vx, kcx, kcy, true, dcx, dcy, p.inertia, sc);
-                }
-                ang = xadd(xadd(xadd(a4[0], a4[1]), a4[2]), a4[3]);
-            }
-            const double e = Cm[(size_t)r * TMAX + c];
-            const double cst = xadd(-xadd(sv, ang), xmul(1.3, e));
-            Cm[(size_t)r * TMAX + c] = xadd(cst, xmul((double)(r * Cn + c), TIE_EPS));
-        }
+        // ---- row reduction (lap_dense.cuh step 1) with on-demand costs, one warp per row -------------------------------
+        if (tid < Cn) sm.tdeg[sm.ht[tid]] = !oc_regular_box(sm.tbox[0][sm.ht[tid]], sm.tbox[1][sm.ht[tid]], sm.tbox[2][sm.ht[tid]], sm.tbox[3][sm.ht[tid]]);
+        if (tid < R) sm.ddeg[sm.hd[tid]] = !oc_regular_box(sm.dbox[0][sm.hd[tid]], sm.dbox[1][sm.hd[tid]], sm.dbox[2][sm.hd[tid]], sm.dbox[3][sm.hd[tid]]);
         __syncthreads();
-        // row reduction (lap_dense.cuh step 1) over the stored matrix, one warp per row; the largest cost bounds lambda
-        double amax = 0.0;
+        const HyCost<SM> cost{sm, Cm, TMAX, Cn, func, W, H, p.inertia, func <= 1};
+        double bmax = 0.0;
         for (int r = warp; r < R; r += NW) {
-            double m = INF;
-            int a = -1;
+            // pass 1: pairs without a usable bound (overlapping or irregular boxes; every pair for diou / ciou / centroid)
+            // are evaluated; of the others the smallest bound is remembered
+            double m = INF, lbmin = INF;
+            int a = -1, lbc = -1;
             for (int c = lane; c < Cn; c += 32) {
-                const double cst = Cm[(size_t)r * TMAX + c];
-                amax = fmax(amax, fabs(cst));
-                if (cst < m) { m = cst; a = c; }
+                const double lb = cost.lower(r, c);
+                if (lb == -INF) {
+                    const double cst = cost(r, c);
+                    if (cst < m) { m = cst; a = c; }
+                } else if (lb < lbmin) { lbmin = lb; lbc = c; }
+            }
+            double mall = m;
+#pragma unroll
+            for (int d = 16; d; d >>= 1) mall = fmin(mall, __shfl_xor_sync(0xffffffffu, mall, d));
+            if (mall == INF) {
+                // a row without such a pair (a new object, a false positive): the pair with the smallest bound sets the bar
+                int lbc_all = lbc;
+                double lball = lbmin;
+#pragma unroll
+                for (int d = 16; d; d >>= 1) {
+                    const double ol = __shfl_xor_sync(0xffffffffu, lball, d);
+                    const int oc = __shfl_xor_sync(0xffffffffu, lbc_all, d);
+                    if (ol < lball || (ol == lball && oc >= 0 && (lbc_all < 0 || oc < lbc_all))) { lball = ol; lbc_all = oc; }
+                }
+                if (lbc_all >= 0) mall = cost(r, lbc_all);                  // every lane: the same value
+            }
+            // pass 2: a bounded pair can only be the row minimum (or tie with it) if its bound does not exceed the bar
+            for (int c = lane; c < Cn; c += 32) {
+                const double lb = cost.lower(r, c);
+                if (lb != -INF && lb <= mall) {
+                    const double cst = cost(r, c);
+                    if (cst < m || (cst == m && c < a)) { m = cst; a = c; }
+                }
             }
 #pragma unroll
             for (int d = 16; d; d >>= 1) {
@@ -476,30 +512,20 @@ hybridsort_step_kernel(const StepParams p) {
                 if (om < m || (om == m && oa >= 0 && (a < 0 || oa < a))) { m = om; a = oa; }
             }
             if (lane == 0) { sm.u[r] = m; sm.claim[r] = a; }
+            bmax = fmax(bmax, cost.bound(sm.hd[r]));
         }
         int d1 = 0, d2 = 0;
-        block_max3<NT>(sm, amax, d1, d2);
+        block_max3<NT>(sm, bmax, d1, d2);
         if (tid == 0) atomicAdd(&p.stats[0], 1ull);
         {
             const DenseLap w = make_dense<NT>(sm);
-            const HyMatCost cost{Cm, TMAX};
-            const double lambda = 2.0 * (amax + 1.0);          // >= lapjv's 2 * (max cost + 1): same assignment (lap_dense.cuh)
+            // every cost is below 1 (similarity) + the direction bound + 1.3 * 2 (cosine distance): any upper bound of
+            // lapjv's 2 * (max cost + 1) gives the same assignment (lap_dense.cuh)
+            const double lambda = 2.0 * (1.0 + bmax + 2.6 + 1e-3 + 1.0);
             dense_lap_init<NT>(w, R, Cn, lambda);
             dense_lap_augment<NT>(w, cost, R, Cn, lambda);
         }
-        // embedding distance of every assigned pair again (the matrix now holds costs), one warp per row, same routine
-        for (int r = warp; r < R; r += NW) {
-            const int c = sm.xr[r];
-            if (c < 0) continue;
-            const int j = sm.hd[r], sl = sm.ht[c];
-            double uv;
-            if (nv <= 128) {
-                double d[16];
-                hy_load_row16(d, reinterpret_cast<const float4*>(dfeat + (size_t)j * F), nv, lane);
-                uv = hy_dot1(d, reinterpret_cast<const float4*>(pool + (size_t)sm.frow[sl] * F), nv, lane);
-            } else uv = emb_dot(j, sl);
-            if (lane == 0) sm.remb[r] = hy_cosine(uv, sm.tnorm[sl], sm.dnorm[j]);
-        }
+        if (tid < R && sm.xr[tid] >= 0) sm.remb[tid] = Cm[(size_t)tid * TMAX + sm.xr[tid]];     // the matrix still holds the distances
         __syncthreads();
         // long-term-ReID correction (association.py:557-566): far in appearance AND below the score-penalised threshold
         if (tid < R) {
