@@ -30,6 +30,7 @@ OC="python bench.py --workload ocsort --streams 2048 --steps 20 --warmup 5 --no-
 BS="python bench.py --workload botsort --streams 1024 --steps 20 --warmup 5 --no-cpu-baseline"
 DO="python bench.py --workload deepocsort --streams 256 --steps 5 --warmup 3 --no-cpu-baseline"
 SS="python bench.py --workload strongsort --streams 64 --steps 3 --warmup 3 --no-cpu-baseline"
+HY="python bench.py --workload hybridsort --streams 256 --steps 5 --warmup 3 --no-cpu-baseline"
 OP="python tools/bench_ops.py --iters 3 --gallery-streams 64"
 run ll_bytetrack $LL --log-file $O/${R}_launches_bytetrack.csv -- $BT
 run ll_ocsort $LL --log-file $O/${R}_launches_ocsort.csv -- $OC
@@ -38,6 +39,7 @@ run ll_ops $LL --log-file $O/${R}_launches_ops.csv -- $OP
 LLT="--metrics gpu__time_duration.sum --clock-control none -s 330 -c 160 --csv"     # skip the pre-roll's launches
 run ll_deepocsort $LL --log-file $O/${R}_launches_deepocsort.csv -- $DO
 run ll_strongsort $LLT --log-file $O/${R}_launches_strongsort.csv -- $SS
+run ll_hybridsort $LL --log-file $O/${R}_launches_hybridsort.csv -- $HY
 if [ "${2:-}" = "lists" ]; then ls -la $O | grep ${R}_; exit 0; fi
 FULL="--set full --clock-control none --import-source on"
 if [ -z "${SKIP_BT_OC:-}" ]; then      # SKIP_BT_OC=1: keep earlier captures of kernels that did not change
@@ -47,6 +49,7 @@ fi
 run full_botsort $FULL -k regex:bytetrack_step -s 12 -c 1 -o $O/${R}_full_botsort -f -- $BS
 run full_deepocsort $FULL -k regex:deepocsort_step -s 12 -c 1 -o $O/${R}_full_deepocsort -f -- $DO
 run full_strongsort $FULL -k regex:"gallery_cost|ss_match|ss_post" -s 126 -c 3 -o $O/${R}_full_strongsort -f -- $SS
+run full_hybridsort $FULL -k regex:hybridsort_step -s 44 -c 1 -o $O/${R}_full_hybridsort -f -- $HY
 if [ "${2:-}" = "steps" ]; then ls -la $O | grep ${R}_; exit 0; fi
 run full_appearance $FULL -k regex:appearance_cost -s 1 -c 1 -o $O/${R}_full_appearance -f -- $OP --only appearance
 run full_kf $FULL -k regex:"kf_(predict|update|project|gating)" -c 24 -o $O/${R}_full_kf -f -- python tools/bench_ops.py --iters 1 --only kf_predict,kf_update,kf_project,gating
