@@ -587,6 +587,14 @@ def run_b200(args, rank, world, local_rank):
             line["tensor"] = {"what": "gallery rows x detections x 2 F per step, over the whole step time (eight launches)",
                               "gallery_rows_per_step": gal_rows / args.steps, "tflops_over_step": flops / (mean_ms * 1e-3) / 1e12,
                               "peak_bf16_tflops": peaks.get("bf16_tflops")}
+        if W["kind"] == "hybridsort":
+            # the step's arithmetic: one exact (fp64-accumulated) 512-d dot product per (detection, live tracker) pair; pairs
+            # estimated from the mean detections and live trackers per stream and step
+            pairs = (dets_timed / max(1, S * args.steps)) * (tu_dev / max(1, S * args.steps)) * S
+            flops = 2.0 * W["emb"] * pairs
+            line["fp64"] = {"what": "dense cosine matrix: 2 F flop per (detection, tracker) pair, over the whole step time",
+                            "pairs_per_step_approx": pairs, "tflops_over_step": flops / (mean_ms * 1e-3) / 1e12,
+                            "peak_fp64_tflops": 34.0, "peak_source": "profiles/r01_fp64_rate.txt (tools/micro/fp64_rate.cu on this B200 pool)"}
         emit(line)
     if world > 1:
         dist.barrier()
