@@ -76,6 +76,8 @@ class HybridSORT:
             return np.empty((0, 7))
         feats = np.asarray(feats, dtype=np.float32).reshape(n, -1) if n else None
         trk = self._context(feats.shape[1] if n else self._feat_dim)
+        if n and feats.shape[1] != self._feat_dim:
+            raise ValueError(f"embedding size changed from {self._feat_dim} to {feats.shape[1]}")
         self._dets[0, :n] = dets
         self._nd[0] = n
         if n:
