@@ -175,3 +175,19 @@ def test_hybridsort_capacity_overflow_is_reported_not_silent():
             trk.update_batch(d, np.array([cap], dtype=np.int32), feats=f)
     assert e.value.code == _lib.ERR_CAPACITY and "tracks" in str(e.value)
     trk.close()
+
+
+@pytest.mark.skipif("__import__('torch').cuda.device_count() < 2")
+def test_hybridsort_on_second_device():
+    """HybridSORT(device=1): the context, its state probes and the per-class wrapper's class read follow the tracker's
+    device and leave the caller's current device alone."""
+    import torch
+    from yolo_tracking_b200.trackers.hybridsort import HybridSORT
+    sc, cfg, dets, nd, feats, g = hybridsort_scenario("hybridsort_2cls", full=True)
+    a, b = HybridSORT(None, 0, False, max_tracks=128, max_dets=64, **cfg), HybridSORT(None, 1, False, max_tracks=128, max_dets=64, **cfg)
+    for f in range(40):
+        ra = a.update(dets[f, :nd[f]], IMG, feats=feats[f])
+        rb = b.update(dets[f, :nd[f]], IMG, feats=feats[f])
+        assert np.array_equal(ra, rb), f
+    assert np.array_equal(a.state()["x"], b.state()["x"])
+    assert torch.cuda.current_device() == 0
