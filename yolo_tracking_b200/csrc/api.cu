@@ -366,6 +366,7 @@ static std::string capacity_message(int e) {
            ((e & B200_ERR_TRACK_OVERFLOW) ? " tracks > max_tracks" : "") +
            ((e & B200_ERR_BOT_CAPACITY) ? " BoT-SORT candidate graph or class history (> 4 classes on a track)" : "") +
            ((e & B200_ERR_LSA) ? " StrongSORT: cost matrix contains invalid numeric entries" : "") +
+           ((e & B200_ERR_PIPELINE) ? " HybridSORT: bulk-copy pipeline protocol error in the cosine pass" : "") +
            ((e & B200_ERR_PACKED_ROW) ? " OC-SORT exception area of the result block is full (rows that report the filter's box)" : "") +
            "; the context's state is truncated - b200track_reset before reuse";
 }

@@ -439,7 +439,7 @@ hybridsort_step_kernel(const StepParams p) {
                 for (int ti = 0; ti < ntile; ++ti) {
                     const int cur = g + ti, buf = cur & 1;
                     if (ti + 1 < ntile) issue_tile(ti + 1, buf ^ 1);  // its last readers passed the barrier below
-                    if (!hy_mbar_wait(&sm.ebar[buf], (uint32_t)(cur >> 1) & 1u)) err |= B200_ERR_LSA;
+                    if (!hy_mbar_wait(&sm.ebar[buf], (uint32_t)(cur >> 1) & 1u)) err |= B200_ERR_PIPELINE;
                     if (actA) {
 #pragma unroll
                         for (int gq = 0; gq < 2; ++gq) {

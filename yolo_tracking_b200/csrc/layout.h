@@ -36,6 +36,7 @@
 #define B200_ERR_BOT_CAPACITY 4     // BoT-SORT: candidate graph overflow or more than 4 classes voted on one track
 #define B200_ERR_LSA 16             // StrongSORT: an assignment problem with nan / inf costs (scipy raises ValueError there)
 #define B200_ERR_PACKED_ROW 8       // OC-SORT compact rows: more filter-box rows than the exception area of the result block holds
+#define B200_ERR_PIPELINE 32        // HybridSORT: a bulk-copy / mbarrier wait of the cosine pass ran into its spin limit (protocol error)
 
 // BoT-SORT contexts created with camera_motion keep the covariance as the two 4x4 blocks a camera warp leaves (kf44.cuh):
 // 8 mean + group A (x, y, vx, vy) 10 + group B (w, h, vw, vh) 10 + score + cls
