@@ -369,6 +369,24 @@ int b200track_kf_xysr_update(int32_t n, double* d_x, double* d_P, const double* 
 int b200track_kf_xysr_unfreeze_update(int32_t n, double* d_x, double* d_P, const double* d_last_z, const int32_t* d_gap,
                                       const double* d_z, double* d_virtual_last, int32_t* d_err, void* stream);
 
+/* ---- HybridSORT's score-carrying filter at operator level (csrc/kf_hybrid.cu): the 9-d [u, v, s, c, r, du, dv, ds, dc]
+ * filter KalmanBoxTracker configures (hybridsort.py:126-150) on dense d_x [n, 9] / d_P [n, 9, 9] arrays, in place, with the
+ * same device functions the fused HybridSORT step runs.  Measurements are [x, y, s, score, r] (convert_bbox_to_z,
+ * hybridsort.py:33-49).  *d_err |= 1 (may be NULL) if a covariance does not have the structure of this filter (four
+ * (position, velocity) 2x2 blocks + P_rr).
+ * b200track_kf_xyscr_predict         <- KalmanFilter.predict (hybridsort_kf.py:339-379); the tracker-level guard of
+ *                                       KalmanBoxTracker.predict (hybridsort.py:303-304) stays with the caller
+ * b200track_kf_xyscr_update          <- KalmanFilter.update(z) (hybridsort_kf.py:439-528: Joseph form), d_z [n, 5]
+ * b200track_kf_xyscr_unfreeze_update <- KalmanFilter.update(z) on a frozen filter: unfreeze() (:390-436, which unpacks the
+ *                                       five-vector as x, y, s, r, c - the score read as the aspect ratio, kept) replays the
+ *                                       virtual trajectory from d_last_z [n, 5] to d_z over d_gap [n] frames starting from the
+ *                                       state saved by freeze() (passed as d_x / d_P), then applies the real measurement;
+ *                                       d_virtual_last [n, 5] (may be NULL) receives the last virtual box. */
+int b200track_kf_xyscr_predict(int32_t n, double* d_x, double* d_P, int32_t* d_err, void* stream);
+int b200track_kf_xyscr_update(int32_t n, double* d_x, double* d_P, const double* d_z, int32_t* d_err, void* stream);
+int b200track_kf_xyscr_unfreeze_update(int32_t n, double* d_x, double* d_P, const double* d_last_z, const int32_t* d_gap,
+                                       const double* d_z, double* d_virtual_last, int32_t* d_err, void* stream);
+
 /* ---- DeepOCSORT operators (csrc/kf8.cu): the 8-d [x, y, w, h, vx, vy, vw, vh] filter the reference configures in
  * KalmanBoxTracker.__init__ (deep_ocsort.py:103-138), dense [n, 8] / [n, 8, 8] arrays.
  * b200track_kf8_predict <- KalmanBoxTracker.predict's kf.predict(Q=new_kf_process_noise(w, h)) (deep_ocsort.py:76-80, :263-266,

@@ -402,3 +402,57 @@ def test_xysr_filter_operators_match_the_oracle_filter():
     bad = P.copy(); bad[0, 0, 1] = 1.0
     with pytest.raises(ValueError):
         _ops.kf_xysr_predict(x, bad)
+
+
+def test_hybrid_filter_operators_match_the_oracle_filter():
+    """b200track_kf_xyscr_predict / _update / _unfreeze_update (HybridSORT's 9-d score-carrying filter at operator level,
+    hybridsort_kf.py:339-528) against oracle/hybridsort.py's filter object through occlusion gaps: every filter gets the same
+    measurements as its twin (the unfreeze reads the score as the aspect ratio, like the reference)."""
+    from oracle.hybridsort import _KF
+    from yolo_tracking_b200 import _ops
+    rng = np.random.default_rng(12)
+    n, frames = 40, 30
+    z0 = np.stack([rng.uniform(100, 1800, n), rng.uniform(100, 900, n), rng.uniform(2000, 20000, n), rng.uniform(0.3, 0.95, n),
+                   rng.uniform(0.3, 0.8, n)], axis=1)
+    kfs = [_KF(z0[i]) for i in range(n)]
+    x = np.stack([k.x for k in kfs]); P = np.stack([k.P for k in kfs])
+    observed = np.zeros(n, dtype=bool)
+    saved = [None] * n
+    last_z = z0.copy()
+    gap = np.zeros(n, dtype=np.int64)
+    n_oru = 0
+    for f in range(frames):
+        for k in kfs:
+            k.predict()
+        x, P = _ops.kf_xyscr_predict(x, P)
+        seen = rng.random(n) > 0.35
+        z = np.stack([x[:, 0] + rng.normal(0, 3, n), x[:, 1] + rng.normal(0, 3, n), np.abs(x[:, 2]) * rng.uniform(0.9, 1.1, n) + 50,
+                      rng.uniform(0.3, 0.95, n), rng.uniform(0.3, 0.8, n)], axis=1)
+        for i, k in enumerate(kfs):
+            k.update(z[i] if seen[i] else None)
+        gap += 1
+        for i in np.nonzero(~seen)[0]:
+            if observed[i]:
+                saved[i] = (x[i].copy(), P[i].copy())
+            observed[i] = False
+        thaw = np.array([i for i in np.nonzero(seen)[0] if not observed[i] and saved[i] is not None], dtype=np.int64)
+        plain = np.array([i for i in np.nonzero(seen)[0] if i not in set(thaw.tolist())], dtype=np.int64)
+        if len(plain):
+            x[plain], P[plain] = _ops.kf_xyscr_update(x[plain], P[plain], z[plain])
+            last_z[plain] = z[plain]
+        if len(thaw):
+            xs = np.stack([saved[i][0] for i in thaw]); Ps = np.stack([saved[i][1] for i in thaw])
+            x[thaw], P[thaw], vl = _ops.kf_xyscr_unfreeze_update(xs, Ps, last_z[thaw], gap[thaw], z[thaw])
+            last_z[thaw] = vl
+            n_oru += len(thaw)
+            for i in thaw:
+                saved[i] = None
+        observed[seen] = True
+        gap[seen] = 0
+        assert_close(x, np.stack([k.x for k in kfs]), what=f"frame {f} x")
+        assert_close(P.reshape(n, 81), np.stack([k.P for k in kfs]).reshape(n, 81), abs_=1e-9, what=f"frame {f} P")
+        assert_close(last_z, np.stack([k.last_z if k.last_z is not None else z0[i] for i, k in enumerate(kfs)]), what=f"frame {f} last z")
+    assert n_oru > 20
+    bad = P.copy(); bad[0, 0, 1] = 1.0
+    with pytest.raises(ValueError):
+        _ops.kf_xyscr_predict(x, bad)

@@ -102,6 +102,9 @@ SIGNATURES = {
     "b200track_kf_xysr_predict": (C.c_int, [_I, _P, _P, _P, _P]),
     "b200track_kf_xysr_update": (C.c_int, [_I, _P, _P, _P, _P, _P]),
     "b200track_kf_xysr_unfreeze_update": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "b200track_kf_xyscr_predict": (C.c_int, [_I, _P, _P, _P, _P]),
+    "b200track_kf_xyscr_update": (C.c_int, [_I, _P, _P, _P, _P, _P]),
+    "b200track_kf_xyscr_unfreeze_update": (C.c_int, [_I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "b200track_gallery_append": (C.c_int, [_I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "b200track_ema_unit_features": (C.c_int, [_I, _I, _P, _P, _D, _P]),
     "b200track_unit_features": (C.c_int, [_I, _I, _P, _P]),

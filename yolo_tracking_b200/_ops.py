@@ -511,3 +511,45 @@ def kf_xysr_unfreeze_update(x_saved, P_saved, last_z, gap, z):
     """update(z) on a frozen filter: the virtual trajectory of unfreeze() (ocsort_kf.py:383-434) from the saved state, then
     the real measurement; returns (x, P, last virtual box)."""
     return _xysr(2, x_saved, P_saved, z, last_z, gap)
+
+
+# ---- HybridSORT's score-carrying filter at operator level (csrc/kf_hybrid.cu) ------------------------------------------
+def _xyscr(mode, x, P, z=None, last_z=None, gap=None):
+    lib = _lib.load()
+    torch = _torch()
+    dx = _dev(np.asarray(x, dtype=np.float64).reshape(-1, 9), np.float64)
+    dP = _dev(np.asarray(P, dtype=np.float64).reshape(-1, 9, 9), np.float64)
+    n = dx.shape[0]
+    err = torch.zeros((1,), dtype=torch.int32, device=dx.device)
+    vl = None
+    if mode == 0:
+        _sync_check(lib.b200track_kf_xyscr_predict(n, _p(dx), _p(dP), _p(err), None))
+    else:
+        dz = _dev(np.asarray(z, dtype=np.float64).reshape(n, 5), np.float64)
+        if mode == 1:
+            _sync_check(lib.b200track_kf_xyscr_update(n, _p(dx), _p(dP), _p(dz), _p(err), None))
+        else:
+            dl = _dev(np.asarray(last_z, dtype=np.float64).reshape(n, 5), np.float64)
+            dg = _dev(np.asarray(gap).reshape(n), np.int32)
+            vl = torch.zeros((n, 5), dtype=torch.float64, device=dx.device)
+            _sync_check(lib.b200track_kf_xyscr_unfreeze_update(n, _p(dx), _p(dP), _p(dl), _p(dg), _p(dz), _p(vl), _p(err), None))
+    if int(err.item()):
+        raise ValueError("covariance does not have the structure of HybridSORT's filter")
+    out = (dx.cpu().numpy(), dP.cpu().numpy())
+    return out + (vl.cpu().numpy(),) if vl is not None else out
+
+
+def kf_xyscr_predict(x, P):
+    """KalmanFilter.predict of HybridSORT's 9-d filter (hybridsort_kf.py:339-379, hybridsort.py:126-150): x [n, 9], P [n, 9, 9]."""
+    return _xyscr(0, x, P)
+
+
+def kf_xyscr_update(x, P, z):
+    """KalmanFilter.update(z) (hybridsort_kf.py:439-528), z [n, 5] = [x, y, s, score, r]."""
+    return _xyscr(1, x, P, z)
+
+
+def kf_xyscr_unfreeze_update(x_saved, P_saved, last_z, gap, z):
+    """update(z) on a frozen filter: the virtual trajectory of unfreeze() (hybridsort_kf.py:390-436) from the saved state,
+    then the real measurement; returns (x, P, last virtual box)."""
+    return _xyscr(2, x_saved, P_saved, z, last_z, gap)
