@@ -191,3 +191,36 @@ def test_hybridsort_on_second_device():
         assert np.array_equal(ra, rb), f
     assert np.array_equal(a.state()["x"], b.state()["x"])
     assert torch.cuda.current_device() == 0
+
+
+@pytest.mark.parametrize("cap", [224, 512])
+def test_hybridsort_kernel_variants(cap):
+    """The (224, 224) and (512, 512) instantiations of the step kernel (the other tests run the 64 / 128 / 256 ones): two
+    streams against the oracle."""
+    from oracle.hybridsort import HybridSortOracle          # checker only
+    from yolo_tracking_b200.batch import BatchedTracker
+    from yolo_tracking_b200.synth import make_stream
+    S, F, E = 2, 20, 64
+    cfg = dict(det_thresh=0.2, max_age=10, min_hits=1, iou_threshold=0.3, delta_t=3, asso_func="giou", inertia=0.2)
+    streams = [make_stream(4, 800 + s, 40 + 30 * s, F, dmax=cap, emb_dim=E, miss_prob=0.1, fp_rate=2.0, occlusion=True) for s in range(S)]
+    trk = BatchedTracker("hybridsort", S, max_tracks=cap, max_dets=cap, feat_dim=E, **cfg)
+    orc = [HybridSortOracle(**cfg) for _ in range(S)]
+    dets = np.zeros((S, cap, 6))
+    ndv = np.zeros(S, dtype=np.int32)
+    feats = np.zeros((S, cap, E), dtype=np.float32)
+    for f in range(F):
+        for s in range(S):
+            d, n, e = streams[s]
+            dets[s], ndv[s] = d[f], n[f]
+            feats[s] = 0
+            if n[f]:
+                feats[s, :n[f]] = e[f, :n[f]] / np.linalg.norm(e[f, :n[f]])
+        out, nout = trk.update_batch(dets, ndv, feats=feats, img_hw=IMG)
+        for s in range(S):
+            n = ndv[s]
+            ref = orc[s].update(dets[s, :n], feats[s, :n][dets[s, :n, 4] > cfg["det_thresh"]]).reshape(-1, 8)
+            got = out[s, :nout[s]]
+            assert got.shape == ref.shape and np.array_equal(got[:, 4:], ref[:, 4:]), (f, s)
+            assert_close(got[:, :4], ref[:, :4], what=f"frame {f} stream {s} boxes")
+    trk.sync()
+    trk.close()
